@@ -1,0 +1,58 @@
+"""Seeded parity cases shared by `oracle/make_golden.py` (which runs the UNMODIFIED reference on
+them and freezes its outputs under `tests/golden/`) and by the tests (which re-create the same
+inputs from the seed and compare the oracle / the CUDA path with the frozen reference outputs).
+TEST INFRASTRUCTURE ONLY."""
+import torch
+
+from ld_b200 import synth
+
+STRIDES = (8, 16, 32, 64, 128)
+
+# (name, N, H, W, seed)
+TARGET_CASES = [
+    ('t_256x320_s1', 2, 256, 320, 1),
+    ('t_256x320_s2', 3, 256, 320, 2),
+    ('t_320x320_s3', 2, 320, 320, 3),
+    ('t_800x800_s4', 2, 800, 800, 4),
+    ('t_800x1344_s5', 1, 800, 1344, 5),
+]
+
+LOSS_CASES = [
+    ('l_256x320_s11', 2, 256, 320, 11),
+    ('l_192x192_s12', 3, 192, 192, 12),   # coarse levels get no positives -> loss_im zeroing quirk
+    ('l_384x512_s13', 2, 384, 512, 13),
+]
+
+# (name, student depth, teacher depth, N, H, W, seed)
+STEP_CASES = [
+    ('s_r18_r18_2x128x160', 18, 18, 2, 128, 160, 21),
+    ('s_r50_r101_2x256x320', 50, 101, 2, 256, 320, 22),
+]
+
+
+def featmap_sizes(h, w):
+    """ResNet/FPN spatial arithmetic (k3 s2 p1 convs: ceil-halving) for strides 8..128."""
+    def half(v):
+        return (v + 1) // 2
+    sizes = []
+    hh, ww = half(half(half(h))), half(half(half(w)))   # stride 8
+    for _ in STRIDES:
+        sizes.append((hh, ww))
+        hh, ww = half(hh), half(ww)
+    return sizes
+
+
+def loss_case_inputs(n, h, w, seed, num_classes=80, reg_ch=68, feat_ch=256):
+    """Random head outputs / teacher outputs / FPN features (NCHW fp32, CPU) + gts for one case."""
+    g = torch.Generator().manual_seed(seed)
+    sizes = featmap_sizes(h, w)
+
+    def rnd(c, scale, shift=0.0):
+        return [torch.randn(n, c, fh, fw, generator=g) * scale + shift for fh, fw in sizes]
+    d = dict(
+        cls=rnd(num_classes, 1.5, -2.0), reg=rnd(reg_ch, 1.0), t_cls=rnd(num_classes, 1.5, -2.0),
+        t_reg=rnd(reg_ch, 1.5), x=rnd(feat_ch, 1.0), t_x=rnd(feat_ch, 1.0))
+    d['gt_bboxes'], d['gt_labels'] = synth.make_gts(n, h, w, seed + 100)
+    d['img_metas'] = synth.make_img_metas(n, h, w)
+    d['sizes'] = sizes
+    return d

@@ -1,0 +1,554 @@
+"""CPU oracle: an independent fp32 restatement (torch-CPU tensor arithmetic) of the reference's
+LD train-step math.  TEST INFRASTRUCTURE ONLY -- only `tests/`, `__graft_entry__.smoke()` and
+`bench.py`'s cpu_baseline / `--impl reference` legs may import this; it is the checker, never the
+product (`ld_b200/` fails loudly if its CUDA library is missing).
+
+Pinned against the UNMODIFIED reference run through `oracle/mmcv_standin.py` (see
+`oracle/make_golden.py` -> `tests/golden/*.pt` and `tests/test_oracle_vs_reference.py`): the
+reference's own tests hold no golden vectors for this path, so the goldens are
+outputs of the reference code itself on seeded inputs.
+
+Each function cites the reference file:line it restates (paths relative to /root/reference).
+Target generation is written dense and sort-free (boolean candidate masks instead of the
+reference's scatter/sort) -- SURVEY.md A.3-A.5 -- so it is an independent derivation, not a port.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+INF = 100000000.0
+
+
+# =========================================================================== anchors
+def level_anchors(h, w, stride, device='cpu'):
+    """mmdet/core/anchor/anchor_generator.py:142-185,233-270 with octave_base_scale=8,
+    ratios=[1.0], scales_per_octave=1, center_offset=0: one square anchor of side 8*stride per
+    cell, centred at (ix*s, iy*s), x fastest."""
+    half = 4.0 * stride
+    xs = torch.arange(w, device=device, dtype=torch.float32) * stride
+    ys = torch.arange(h, device=device, dtype=torch.float32) * stride
+    cx = xs.repeat(h)
+    cy = ys.repeat_interleave(w)
+    return torch.stack([cx - half, cy - half, cx + half, cy + half], 1)
+
+
+def level_valid_flags(h, w, stride, pad_h, pad_w, device='cpu'):
+    """anchor_generator.py:272-328: cell valid iff inside ceil(pad/stride)."""
+    vh = min(int(math.ceil(pad_h / stride)), h)
+    vw = min(int(math.ceil(pad_w / stride)), w)
+    fx = torch.arange(w, device=device) < vw
+    fy = torch.arange(h, device=device) < vh
+    return (fy[:, None] & fx[None, :]).reshape(-1)
+
+
+# =========================================================================== box geometry
+def pair_overlaps(a, b, mode='iou', eps=1e-6):
+    """mmdet/core/bbox/iou_calculators/iou2d_calculator.py:43-188, pairwise [m,n].
+    NB: for mode 'diou' the reference's base term is IoF = overlap/area(a)
+    (the `else: union = area1` branch :146-149), not IoU."""
+    area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+    area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    lt = torch.max(a[:, None, :2], b[None, :, :2])
+    rb = torch.min(a[:, None, 2:], b[None, :, 2:])
+    wh = (rb - lt).clamp(min=0)
+    ov = wh[..., 0] * wh[..., 1]
+    if mode in ('iou', 'giou'):
+        union = area_a[:, None] + area_b[None, :] - ov
+    else:
+        union = area_a[:, None].expand_as(ov)
+    union = torch.max(union, union.new_tensor(eps))
+    base = ov / union
+    if mode in ('iou', 'iof'):
+        return base
+    elt = torch.min(a[:, None, :2], b[None, :, :2])
+    erb = torch.max(a[:, None, 2:], b[None, :, 2:])
+    ewh = (erb - elt).clamp(min=0)
+    if mode == 'giou':
+        ea = torch.max(ewh[..., 0] * ewh[..., 1], union.new_tensor(eps))
+        return base - (ea - union) / ea
+    # 'diou'
+    left = (b[None, :, 0] + b[None, :, 2] - (a[:, None, 0] + a[:, None, 2])) ** 2 / 4
+    right = (b[None, :, 1] + b[None, :, 3] - (a[:, None, 1] + a[:, None, 3])) ** 2 / 4
+    rho2 = left + right
+    c2 = torch.max(ewh[..., 0] ** 2 + ewh[..., 1] ** 2, union.new_tensor(eps))
+    return base - rho2 / c2
+
+
+def aligned_overlaps(a, b, mode='iou', eps=1e-6):
+    """iou2d_calculator.py:111-143 (is_aligned=True) for 'iou' / 'giou'."""
+    area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+    area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    lt = torch.max(a[:, :2], b[:, :2])
+    rb = torch.min(a[:, 2:], b[:, 2:])
+    wh = (rb - lt).clamp(min=0)
+    ov = wh[:, 0] * wh[:, 1]
+    union = torch.max(area_a + area_b - ov, ov.new_tensor(eps))
+    iou = ov / union
+    if mode == 'iou':
+        return iou
+    elt = torch.min(a[:, :2], b[:, :2])
+    erb = torch.max(a[:, 2:], b[:, 2:])
+    ewh = (erb - elt).clamp(min=0)
+    ea = torch.max(ewh[:, 0] * ewh[:, 1], ov.new_tensor(eps))
+    return iou - (ea - union) / ea
+
+
+# =========================================================================== targets
+def atss_candidates(anchors, num_level, gts, topk=9):
+    """Boolean [A,G] mask of the per-level top-k closest anchors for each gt
+    (mmdet/core/bbox/assigners/atss_assigner.py:94-127); ties -> lowest index (torch CPU topk)."""
+    acx = (anchors[:, 0] + anchors[:, 2]) / 2.0
+    acy = (anchors[:, 1] + anchors[:, 3]) / 2.0
+    gcx = (gts[:, 0] + gts[:, 2]) / 2.0
+    gcy = (gts[:, 1] + gts[:, 3]) / 2.0
+    d = ((acx[:, None] - gcx[None, :]).pow(2) + (acy[:, None] - gcy[None, :]).pow(2)).sqrt()
+    cand = torch.zeros_like(d, dtype=torch.bool)
+    cand_idx = []
+    s = 0
+    for n in num_level:
+        k = min(topk, n)
+        if k > 0:
+            # stable ascending sort == "k smallest, lowest index first on ties"
+            order = torch.sort(d[s:s + n], dim=0, stable=True)[1][:k] + s
+            cand.scatter_(0, order, True)
+            cand_idx.append(order)
+        s += n
+    return cand, torch.cat(cand_idx, 0), acx, acy
+
+
+def atss_threshold(iou, cand_idx):
+    """mean + unbiased std of the candidate IoUs per gt (atss_assigner.py:131-134)."""
+    g = iou.shape[1]
+    c = iou[cand_idx, torch.arange(g)]
+    return c.mean(0) + c.std(0)
+
+
+def ld_targets_single(anchors, valid, num_level, gts, gt_labels, num_classes=80, topk=9,
+                      imitation='finegrained'):
+    """One image: `LDHead._get_target_single` (ld_head.py:449-577) = ATSS assign
+    (atss_assigner.py:33-181) + PseudoSampler + `get_vlr_region` (:183-298) +
+    `get_im_region` (ld_head.py:580-611) + unmap.  allowed_border=-1 => inside == valid.
+
+    Returns dict(labels i64 [A], label_weights f32, bbox_targets f32 [A,4], vlr f32, im f32,
+                 gt_inds i64 [A] (0 = bg, k+1 = gt k), num_pos int)."""
+    A = anchors.shape[0]
+    idx = valid.nonzero().squeeze(1)
+    a = anchors[idx]
+    nl = []
+    s = 0
+    for n in num_level:
+        nl.append(int(valid[s:s + n].sum()))
+        s += n
+    G = gts.shape[0]
+    assert G >= 1, 'reference get_vlr_region returns a non-tensor for G==0 (atss_assigner.py:203-216)'
+    iou = pair_overlaps(a, gts, 'iou')
+    cand, cand_idx, acx, acy = atss_candidates(a, nl, gts, topk)
+    thr = atss_threshold(iou, cand_idx)
+    # --- positives (A.3)
+    l_ = acx[:, None] - gts[None, :, 0]
+    t_ = acy[:, None] - gts[None, :, 1]
+    r_ = gts[None, :, 2] - acx[:, None]
+    b_ = gts[None, :, 3] - acy[:, None]
+    inside = torch.stack([l_, t_, r_, b_], 0).min(0)[0] > 0.01
+    pos = cand & (iou >= thr[None, :]) & inside
+    masked = torch.where(pos, iou, iou.new_full((), -INF))
+    mx, am = masked.max(1)
+    gt_inds = torch.where(mx != -INF, am + 1, torch.zeros_like(am))
+    # --- VLR (A.4): band on the IoF-based "diou", over ALL anchors
+    diou = pair_overlaps(a, gts, 'diou')
+    band = (diou < thr[None, :]) & (diou >= 0.25 * thr[None, :])
+    vm = torch.where(band, iou, iou.new_full((), -INF)).max(1)[0]
+    vlr = torch.where(vm != -INF, vm, torch.zeros_like(vm))
+    # --- imitation region (A.5)
+    if imitation == 'finegrained':
+        im = (iou > 0.5 * iou.max(0)[0][None, :]).any(1).float()
+    else:
+        im = ((acx[:, None] > gts[None, :, 0]) & (acx[:, None] < gts[None, :, 2]) &
+              (acy[:, None] > gts[None, :, 1]) & (acy[:, None] < gts[None, :, 3])).any(1).float()
+    is_pos = gt_inds > 0
+    lab = torch.where(is_pos, gt_labels[(gt_inds - 1).clamp(min=0)],
+                      torch.full_like(gt_inds, num_classes))
+    bt = torch.where(is_pos[:, None], gts[(gt_inds - 1).clamp(min=0)], torch.zeros_like(a))
+    out = dict(labels=torch.full((A,), num_classes, dtype=torch.long),
+               label_weights=torch.zeros(A), bbox_targets=torch.zeros(A, 4),
+               vlr=torch.zeros(A), im=torch.zeros(A), gt_inds=torch.zeros(A, dtype=torch.long))
+    out['labels'][idx] = lab
+    out['label_weights'][idx] = 1.0
+    out['bbox_targets'][idx] = bt
+    out['vlr'][idx] = vlr
+    out['im'][idx] = im
+    out['gt_inds'][idx] = gt_inds
+    out['num_pos'] = int(is_pos.sum())
+    return out
+
+
+def ld_targets(featmap_sizes, strides, img_metas, gt_bboxes, gt_labels, **kw):
+    """Batch version (ld_head.py:377-447): per-level stacked tensors [N, A_l(,4)] + num_total_pos."""
+    anchors = [level_anchors(h, w, s) for (h, w), s in zip(featmap_sizes, strides)]
+    num_level = [a.shape[0] for a in anchors]
+    flat = torch.cat(anchors, 0)
+    per_img = []
+    for meta, gb, gl in zip(img_metas, gt_bboxes, gt_labels):
+        ph, pw = meta['pad_shape'][:2]
+        valid = torch.cat([level_valid_flags(h, w, s, ph, pw)
+                           for (h, w), s in zip(featmap_sizes, strides)])
+        per_img.append(ld_targets_single(flat, valid, num_level, gb, gl, **kw))
+    num_total_pos = sum(max(t['num_pos'], 1) for t in per_img)
+    out = {}
+    for key in ('labels', 'label_weights', 'bbox_targets', 'vlr', 'im', 'gt_inds'):
+        stacked = torch.stack([t[key] for t in per_img], 0)
+        out[key] = list(stacked.split(num_level, dim=1))
+    out['anchors'] = anchors
+    out['num_total_pos'] = num_total_pos
+    return out
+
+
+# =========================================================================== losses
+def qfl_rows(logits, labels, score, beta=2.0):
+    """quality_focal_loss (mmdet/models/losses/gfocal_loss.py:34-49), per-anchor row sums."""
+    sig = logits.sigmoid()
+    loss = F.binary_cross_entropy_with_logits(logits, torch.zeros_like(logits),
+                                              reduction='none') * sig.pow(beta)
+    C = logits.shape[1]
+    pos = ((labels >= 0) & (labels < C)).nonzero().squeeze(1)
+    if pos.numel():
+        pl = labels[pos]
+        x = logits[pos, pl]
+        sf = score[pos] - sig[pos, pl]
+        lp = F.binary_cross_entropy_with_logits(x, score[pos], reduction='none') * sf.abs().pow(beta)
+        loss = loss.index_put((pos, pl), lp)
+    return loss.sum(1)
+
+
+def dfl_rows(logits, target):
+    """distribution_focal_loss (gfocal_loss.py:68-74)."""
+    dl = target.long()
+    dr = dl + 1
+    wl = dr.float() - target
+    wr = target - dl.float()
+    return F.cross_entropy(logits, dl, reduction='none') * wl + \
+        F.cross_entropy(logits, dr, reduction='none') * wr
+
+
+def kd_kl_rows(student, teacher, T):
+    """knowledge_distillation_kl_div_loss (mmdet/models/losses/kd_loss.py:28-34)."""
+    p_t = F.softmax(teacher / T, dim=1).detach()
+    return F.kl_div(F.log_softmax(student / T, dim=1), p_t, reduction='none').mean(1) * (T * T)
+
+
+def integral(reg, reg_max=16):
+    """Integral (mmdet/models/dense_heads/gfl_head.py:32-44)."""
+    p = F.softmax(reg.reshape(-1, reg_max + 1), dim=1)
+    proj = torch.linspace(0, reg_max, reg_max + 1, dtype=reg.dtype, device=reg.device)
+    return F.linear(p, proj).reshape(-1, 4)
+
+
+DEFAULT_LOSS_CFG = dict(w_qfl=1.0, beta=2.0, w_giou=2.0, w_dfl=0.25, w_ld=0.25, T_ld=10.0,
+                        w_ld_vlr=0.25, T_ld_vlr=10.0, w_kd=10.0, T_kd=2.0, w_im=2.0, reg_max=16)
+
+
+def ld_loss_level(anchors, cls, reg, labels, label_w, bbox_t, stride, t_reg, t_cls, x, t_x,
+                  vlr, im, num_total_samples, cfg=DEFAULT_LOSS_CFG):
+    """`LDHead.loss_single` (ld_head.py:116-282) on flattened NHWC rows.
+
+    anchors [R,4]; cls [R,C]; reg/t_reg [R,4*(reg_max+1)]; t_cls [R,C]; x,t_x [R,F].
+    Returns the 8 (pre-avg_factor) loss terms and sum of weight_targets."""
+    C = cls.shape[1]
+    rm = cfg['reg_max']
+    pos = ((labels >= 0) & (labels < C)).nonzero().squeeze(1)
+    rem = (vlr > 0).nonzero().squeeze(1)
+    fg = (im > 0).nonzero().squeeze(1)
+    zero = reg.sum() * 0
+    score = label_w.new_zeros(labels.shape)
+    loss_im = cfg['w_im'] * F.mse_loss(x[fg], t_x[fg]) if fg.numel() else zero
+    if pos.numel():
+        a = anchors[pos]
+        ctr = torch.stack([(a[:, 0] + a[:, 2]) / 2, (a[:, 1] + a[:, 3]) / 2], 1) / stride
+        wt = cls.detach().sigmoid().max(1)[0][pos]
+        d = integral(reg[pos], rm)
+        pred = torch.stack([ctr[:, 0] - d[:, 0], ctr[:, 1] - d[:, 1],
+                            ctr[:, 0] + d[:, 2], ctr[:, 1] + d[:, 3]], 1)
+        tgt = bbox_t[pos] / stride
+        score[pos] = aligned_overlaps(pred.detach(), tgt, 'iou')
+        corners = torch.stack([ctr[:, 0] - tgt[:, 0], ctr[:, 1] - tgt[:, 1],
+                               tgt[:, 2] - ctr[:, 0], tgt[:, 3] - ctr[:, 1]], 1
+                              ).clamp(min=0, max=rm - 0.1).reshape(-1)
+        w4 = wt[:, None].expand(-1, 4).reshape(-1)
+        pc = reg[pos].reshape(-1, rm + 1)
+        sc = t_reg[pos].reshape(-1, rm + 1)
+        loss_bbox = cfg['w_giou'] * ((1 - aligned_overlaps(pred, tgt, 'giou')) * wt).sum() / 1.0
+        loss_dfl = cfg['w_dfl'] * (dfl_rows(pc, corners) * w4).sum() / 4.0
+        loss_ld = cfg['w_ld'] * (kd_kl_rows(pc, sc, cfg['T_ld']) * w4).sum() / 4.0
+        loss_kd = cfg['w_kd'] * (kd_kl_rows(cls[pos], t_cls[pos], cfg['T_kd']) * label_w[pos]
+                                 ).sum() / pos.numel()
+        wsum = wt.sum()
+    else:
+        loss_bbox = loss_dfl = loss_ld = loss_kd = zero
+        loss_im = zero  # ld_head.py:251 zeroes loss_im too when the level has no positive
+        wsum = reg.new_tensor(0.)
+    if rem.numel():
+        rw = vlr[rem][:, None].expand(-1, 4).reshape(-1)
+        loss_ld_vlr = cfg['w_ld_vlr'] * (kd_kl_rows(reg[rem].reshape(-1, rm + 1),
+                                                    t_reg[rem].reshape(-1, rm + 1),
+                                                    cfg['T_ld_vlr']) * rw).sum() / 16.0
+        loss_kd_neg = 0 * (cfg['w_kd'] * (kd_kl_rows(cls[rem], t_cls[rem], cfg['T_kd'])
+                                          * label_w[rem]).sum() / rem.numel())
+    else:
+        loss_ld_vlr = loss_kd_neg = zero
+    loss_cls = cfg['w_qfl'] * (qfl_rows(cls, labels, score, cfg['beta']) * label_w).sum() \
+        / num_total_samples
+    return dict(loss_cls=loss_cls, loss_bbox=loss_bbox, loss_dfl=loss_dfl, loss_ld=loss_ld,
+                loss_ld_vlr=loss_ld_vlr, loss_kd=loss_kd, loss_kd_neg=loss_kd_neg,
+                loss_im=loss_im), wsum
+
+
+def nhwc_rows(t):
+    """[N,C,H,W] -> [N*H*W, C] (ld_head.py:144-154)."""
+    return t.permute(0, 2, 3, 1).reshape(-1, t.shape[1])
+
+
+def ld_loss(cls_scores, bbox_preds, t_cls_scores, t_bbox_preds, feats, t_feats, targets,
+            strides, cfg=DEFAULT_LOSS_CFG, world_size=1):
+    """`LDHead.loss` (ld_head.py:284-375) given NCHW per-level tensors and `ld_targets` output.
+    Single process: reduce_mean is the identity."""
+    nts = max(float(targets["num_total_pos"]), 1.0)
+    per = []
+    wsum = 0
+    n = cls_scores[0].shape[0]
+    for l, s in enumerate(strides):
+        anc = targets['anchors'][l].repeat(n, 1)
+        d, w = ld_loss_level(anc, nhwc_rows(cls_scores[l]), nhwc_rows(bbox_preds[l]),
+                             targets['labels'][l].reshape(-1),
+                             targets['label_weights'][l].reshape(-1),
+                             targets['bbox_targets'][l].reshape(-1, 4), float(s),
+                             nhwc_rows(t_bbox_preds[l]), nhwc_rows(t_cls_scores[l]),
+                             nhwc_rows(feats[l]), nhwc_rows(t_feats[l]),
+                             targets['vlr'][l].reshape(-1), targets['im'][l].reshape(-1),
+                             nts, cfg)
+        per.append(d)
+        wsum = wsum + w
+    avg = float(wsum + 1e-6)
+    out = {k: [p[k] for p in per] for k in per[0]}
+    out['loss_bbox'] = [v / avg for v in out['loss_bbox']]
+    out['loss_dfl'] = [v / avg for v in out['loss_dfl']]
+    return out
+
+
+def parse_losses(losses):
+    """`BaseDetector._parse_losses` (mmdet/models/detectors/base.py:185-218), single process."""
+    log = {k: sum(v.mean() for v in vs) for k, vs in losses.items()}
+    total = sum(v for k, v in log.items() if 'loss' in k)
+    log['loss'] = total
+    return total, {k: float(v.detach()) for k, v in log.items()}
+
+
+# =========================================================================== network port
+class _Bottleneck(nn.Module):
+    """mmdet/models/backbones/resnet.py:95-300, style='pytorch' (stride on the 3x3)."""
+    expansion = 4
+
+    def __init__(self, inp, planes, stride, downsample):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inp, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.downsample = downsample
+
+    def forward(self, x):
+        idt = x if self.downsample is None else self.downsample(x)
+        o = F.relu(self.bn1(self.conv1(x)))
+        o = F.relu(self.bn2(self.conv2(o)))
+        o = self.bn3(self.conv3(o))
+        return F.relu(o + idt)
+
+
+class _BasicBlock(nn.Module):
+    """resnet.py:13-92."""
+    expansion = 1
+
+    def __init__(self, inp, planes, stride, downsample):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inp, planes, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = downsample
+
+    def forward(self, x):
+        idt = x if self.downsample is None else self.downsample(x)
+        o = F.relu(self.bn1(self.conv1(x)))
+        o = self.bn2(self.conv2(o))
+        return F.relu(o + idt)
+
+
+_ARCH = {18: (_BasicBlock, (2, 2, 2, 2)), 34: (_BasicBlock, (3, 4, 6, 3)),
+         50: (_Bottleneck, (3, 4, 6, 3)), 101: (_Bottleneck, (3, 4, 23, 3))}
+
+
+class OracleResNet(nn.Module):
+    """resnet.py:303-649 with frozen_stages=1, norm_eval=True (BN always eval)."""
+
+    def __init__(self, depth):
+        super().__init__()
+        block, layers = _ARCH[depth]
+        self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        inp = 64
+        for i, n in enumerate(layers):
+            planes = 64 * 2 ** i
+            stride = 1 if i == 0 else 2
+            blocks = []
+            for j in range(n):
+                st = stride if j == 0 else 1
+                ds = None
+                if j == 0 and (st != 1 or inp != planes * block.expansion):
+                    ds = nn.Sequential(nn.Conv2d(inp, planes * block.expansion, 1, st, bias=False),
+                                       nn.BatchNorm2d(planes * block.expansion))
+                blocks.append(block(inp, planes, st, ds))
+                inp = planes * block.expansion
+            setattr(self, f'layer{i + 1}', nn.Sequential(*blocks))
+        self.out_channels = [64 * 2 ** i * block.expansion for i in range(4)]
+        for m in [self.conv1, self.bn1, self.layer1]:
+            for p in m.parameters():
+                p.requires_grad = False
+
+    def train(self, mode=True):
+        super().train(mode)
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+        return self
+
+    def forward(self, x):
+        x = F.max_pool2d(F.relu(self.bn1(self.conv1(x))), 3, 2, 1)
+        outs = []
+        for i in range(4):
+            x = getattr(self, f'layer{i + 1}')(x)
+            outs.append(x)
+        return outs
+
+
+class _ConvOnly(nn.Module):
+    def __init__(self, i, o, k, s=1, p=0, bias=True):
+        super().__init__()
+        self.conv = nn.Conv2d(i, o, k, s, p, bias=bias)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class OracleFPN(nn.Module):
+    """mmdet/models/necks/fpn.py:66-221 with start_level=1, add_extra_convs='on_output', 5 outs."""
+
+    def __init__(self, in_channels, out_channels=256):
+        super().__init__()
+        self.lateral_convs = nn.ModuleList(_ConvOnly(c, out_channels, 1) for c in in_channels[1:])
+        self.fpn_convs = nn.ModuleList(
+            [_ConvOnly(out_channels, out_channels, 3, 1, 1) for _ in range(3)] +
+            [_ConvOnly(out_channels, out_channels, 3, 2, 1) for _ in range(2)])
+
+    def forward(self, feats):
+        lat = [c(f) for c, f in zip(self.lateral_convs, feats[1:])]
+        for i in (2, 1):
+            lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[2:],
+                                                    mode='nearest')
+        outs = [self.fpn_convs[i](lat[i]) for i in range(3)]
+        outs.append(self.fpn_convs[3](outs[-1]))
+        outs.append(self.fpn_convs[4](outs[-1]))
+        return outs
+
+
+class _ConvGN(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, 1, 1, bias=False)
+        self.gn = nn.GroupNorm(32, c)
+
+    def forward(self, x):
+        return F.relu(self.gn(self.conv(x)))
+
+
+class _Scale(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.scale = nn.Parameter(torch.tensor(1.0))
+
+    def forward(self, x):
+        return x * self.scale
+
+
+class OracleGFLHead(nn.Module):
+    """gfl_head.py:102-183."""
+
+    def __init__(self, num_classes=80, c=256, reg_max=16, stacked=4, levels=5):
+        super().__init__()
+        self.cls_convs = nn.ModuleList(_ConvGN(c) for _ in range(stacked))
+        self.reg_convs = nn.ModuleList(_ConvGN(c) for _ in range(stacked))
+        self.gfl_cls = nn.Conv2d(c, num_classes, 3, padding=1)
+        self.gfl_reg = nn.Conv2d(c, 4 * (reg_max + 1), 3, padding=1)
+        self.scales = nn.ModuleList(_Scale() for _ in range(levels))
+        self.integral = nn.Module()  # state_dict key parity: bbox_head.integral.project (gfl_head.py:28-30)
+        self.integral.register_buffer('project', torch.linspace(0, reg_max, reg_max + 1))
+
+    def forward(self, feats):
+        cls_scores, bbox_preds = [], []
+        for x, sc in zip(feats, self.scales):
+            cf = rf = x
+            for m in self.cls_convs:
+                cf = m(cf)
+            for m in self.reg_convs:
+                rf = m(rf)
+            cls_scores.append(self.gfl_cls(cf))
+            bbox_preds.append(sc(self.gfl_reg(rf)).float())
+        return cls_scores, bbox_preds
+
+
+class OracleGFL(nn.Module):
+    def __init__(self, depth):
+        super().__init__()
+        self.backbone = OracleResNet(depth)
+        self.neck = OracleFPN(self.backbone.out_channels)
+        self.bbox_head = OracleGFLHead()
+
+    def extract_feat(self, img):
+        return self.neck(self.backbone(img))
+
+
+class OracleLDDetector(nn.Module):
+    """kd_one_stage.py:12-108: student (grad) + plain-attribute teacher (no grad) + LDHead loss."""
+    strides = (8, 16, 32, 64, 128)
+
+    def __init__(self, student_depth=50, teacher_depth=101, loss_cfg=None, imitation='finegrained'):
+        super().__init__()
+        s = OracleGFL(student_depth)
+        self.backbone, self.neck, self.bbox_head = s.backbone, s.neck, s.bbox_head
+        object.__setattr__(self, 'teacher_model', OracleGFL(teacher_depth))
+        self.teacher_model.eval()
+        self.loss_cfg = dict(DEFAULT_LOSS_CFG, **(loss_cfg or {}))
+        self.imitation = imitation
+
+    def forward_train(self, img, img_metas, gt_bboxes, gt_labels):
+        x = self.neck(self.backbone(img))
+        with torch.no_grad():
+            tx = self.teacher_model.extract_feat(img)
+            t_cls, t_reg = self.teacher_model.bbox_head(tx)
+        cls, reg = self.bbox_head(x)
+        sizes = [tuple(c.shape[-2:]) for c in cls]
+        tg = ld_targets(sizes, self.strides, img_metas, gt_bboxes, gt_labels,
+                        imitation=self.imitation)
+        return ld_loss(cls, reg, t_cls, t_reg, x, tx, tg, self.strides, self.loss_cfg)
+
+    def step(self, batch, backward=True):
+        for p in self.parameters():
+            p.grad = None
+        losses = self.forward_train(batch['img'], batch['img_metas'], batch['gt_bboxes'],
+                                    batch['gt_labels'])
+        loss, log = parse_losses(losses)
+        if backward:
+            loss.backward()
+        return losses, loss, log

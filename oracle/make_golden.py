@@ -1,0 +1,123 @@
+"""Generate `tests/golden/*.pt` by running the UNMODIFIED reference (through the mmcv stand-in)
+on the seeded cases of `oracle/cases.py`.  Build container only (`/root/reference` must exist):
+
+    python -m oracle.make_golden
+
+The reference's own tests hold no golden vectors for this path, so these are
+outputs of the reference code itself.  Fixtures are kept small (int16/int32 indices, fp32 values).
+TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import sys
+
+import torch
+
+from ld_b200 import synth
+from . import cases, ref_harness as rh
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def ref_targets(head, n, h, w, gt_bboxes, gt_labels):
+    """Reference `get_anchors` + `get_targets` (ld_head.py:319-336)."""
+    sizes = cases.featmap_sizes(h, w)
+    metas = synth.make_img_metas(n, h, w)
+    anchor_list, valid_flag_list = head.get_anchors(sizes, metas, device='cpu')
+    out = head.get_targets(anchor_list, valid_flag_list, gt_bboxes, metas,
+                           gt_bboxes_ignore_list=None, gt_labels_list=gt_labels,
+                           label_channels=head.cls_out_channels)
+    (anchors, labels, label_w, bbox_t, _bbox_w, num_pos, _num_neg, vlr, im) = out
+    return dict(anchors=anchors, labels=labels, label_weights=label_w, bbox_targets=bbox_t,
+                vlr=vlr, im=im, num_total_pos=num_pos)
+
+
+def gen_targets(head):
+    for name, n, h, w, seed in cases.TARGET_CASES:
+        gb, gl = synth.make_gts(n, h, w, seed)
+        for mode in ('finegrained', 'fitnet'):
+            head.imitation_method = mode
+            t = ref_targets(head, n, h, w, gb, gl)
+            if mode == 'finegrained':
+                gold = dict(
+                    labels=torch.cat(t['labels'], 1).to(torch.int16),
+                    label_weights=torch.cat(t['label_weights'], 1).to(torch.uint8),
+                    bbox_targets=torch.cat(t['bbox_targets'], 1),
+                    vlr=torch.cat(t['vlr'], 1), im_finegrained=torch.cat(t['im'], 1).to(torch.uint8),
+                    num_total_pos=int(t['num_total_pos']),
+                    level_anchor0=[a[0, :2].clone() for a in t['anchors']])
+            else:
+                gold['im_center'] = torch.cat(t['im'], 1).to(torch.uint8)
+        head.imitation_method = 'finegrained'
+        torch.save(gold, os.path.join(OUT, name + '.pt'))
+        print(name, 'pos', gold['num_total_pos'], 'vlr', int((gold['vlr'] > 0).sum()),
+              'im', int(gold['im_finegrained'].sum()))
+
+
+def gen_losses(head):
+    for name, n, h, w, seed in cases.LOSS_CASES:
+        d = cases.loss_case_inputs(n, h, w, seed)
+        leaves = {}
+        for k in ('cls', 'reg', 'x'):
+            leaves[k] = [t.clone().requires_grad_(True) for t in d[k]]
+        losses = head.loss(leaves['cls'], leaves['reg'], d['gt_bboxes'], d['gt_labels'],
+                           (d['t_cls'], d['t_reg']), leaves['x'], d['t_x'], d['img_metas'])
+        total = sum(sum(v) for v in losses.values())
+        total.backward()
+        for t in leaves['x']:
+            if t.grad is None:   # level without fine-grained rows: loss_im does not touch x
+                t.grad = torch.zeros_like(t)
+        gold = dict(losses={k: torch.stack([t.detach() for t in v]) for k, v in losses.items()},
+                    total=total.detach(),
+                    grad_cls=[t.grad for t in leaves['cls']],
+                    grad_reg=[t.grad for t in leaves['reg']],
+                    # grad_x is sparse (only fine-grained rows): keep per-level sums + norms
+                    grad_x_norm=torch.stack([t.grad.norm() for t in leaves['x']]),
+                    grad_x_rowsum=[t.grad.sum(1) for t in leaves['x']])
+        torch.save(gold, os.path.join(OUT, name + '.pt'))
+        print(name, {k: [round(float(x), 5) for x in v] for k, v in gold['losses'].items()})
+
+
+def gen_steps():
+    for name, sd, td, n, h, w, seed in cases.STEP_CASES:
+        cfg = rh.load_model_cfg()
+        cfg['backbone']['depth'] = sd
+        cfg['neck']['in_channels'] = [64, 128, 256, 512] if sd < 50 else [256, 512, 1024, 2048]
+        cfg['teacher_config']['model']['backbone']['depth'] = td
+        cfg['teacher_config']['model']['neck']['in_channels'] = \
+            [64, 128, 256, 512] if td < 50 else [256, 512, 1024, 2048]
+        m = rh.build_reference_detector(cfg)
+        synth.seeded_init(m, seed)
+        synth.seeded_init(m.teacher_model, seed + 1, prefix='teacher.')
+        b = synth.make_batch(n, h, w, seed=1000 + seed)
+        losses, loss, log = rh.reference_step(m, b)
+        gold = dict(log_vars=log,
+                    losses={k: torch.stack([t.detach() for t in v]) for k, v in losses.items()},
+                    grad_stats={k: torch.tensor([float(p.grad.double().norm()),
+                                                 float(p.grad.double().sum()),
+                                                 float(p.grad.abs().max())])
+                                for k, p in m.named_parameters() if p.grad is not None},
+                    no_grad=[k for k, p in m.named_parameters() if p.grad is None])
+        # a few full gradients for direct comparison
+        keep = ['bbox_head.gfl_cls.weight', 'bbox_head.gfl_reg.bias', 'bbox_head.scales.0.scale',
+                'bbox_head.cls_convs.0.gn.weight', 'neck.lateral_convs.0.conv.bias',
+                'backbone.layer4.0.bn1.weight' if sd >= 50 else 'backbone.layer4.0.bn1.weight']
+        named = dict(m.named_parameters())
+        gold['grads'] = {k: named[k].grad.clone() for k in keep}
+        torch.save(gold, os.path.join(OUT, name + '.pt'))
+        print(name, {k: round(v, 5) for k, v in log.items()})
+
+
+def main():
+    if not rh.reference_available():
+        sys.exit('needs /root/reference (build container only)')
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    head = rh.reference_head()
+    gen_targets(head)
+    gen_losses(head)
+    gen_steps()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,381 @@
+"""Minimal stand-in for `mmcv` 1.2.x so the UNMODIFIED reference (`/root/reference/mmdet`)
+can be imported in the build container and run on CPU.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in `ld_b200/` may import this file.  It is used by
+`oracle/make_golden.py` (golden-vector generation, build container only: `/root/reference`
+does not exist on the GPU box) and by the `-m "not gpu"` tests that cross-check the oracle
+restatement against the reference when `/root/reference` is present.
+
+mmcv is a third-party dependency of the reference (`mmdet/__init__.py:19-20` pins
+mmcv-full >=1.2.4,<=1.3) whose source is NOT under `/root/reference`.  What is restated here
+is the published behaviour of the handful of mmcv symbols the LD train path touches
+(SURVEY.md Appendix C): Registry/build_from_cfg, ConvModule, Scale, build_conv_layer,
+build_norm_layer, the nn.init helpers, and identity decorators for force_fp32/auto_fp16/jit.
+Everything else (`mmcv.ops`, `mmcv.parallel`, pycocotools, terminaltables, matplotlib ...)
+is a permissive dummy that only has to survive `import mmdet`.
+"""
+import inspect
+import math
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+_INSTALLED = False
+
+
+# --------------------------------------------------------------------------- registry
+class Registry:
+    def __init__(self, name):
+        self._name = name
+        self._module_dict = {}
+
+    @property
+    def name(self):
+        return self._name
+
+    @property
+    def module_dict(self):
+        return self._module_dict
+
+    def get(self, key):
+        return self._module_dict.get(key, None)
+
+    def __contains__(self, key):
+        return key in self._module_dict
+
+    def __len__(self):
+        return len(self._module_dict)
+
+    def _register(self, cls, name=None, force=False):
+        name = name or cls.__name__
+        if not force and name in self._module_dict:
+            raise KeyError(f'{name} is already registered in {self._name}')
+        self._module_dict[name] = cls
+
+    def register_module(self, name=None, force=False, module=None):
+        if isinstance(name, type):  # legacy @R.register_module usage
+            self._register(name)
+            return name
+        if module is not None:
+            self._register(module, name, force)
+            return module
+
+        def _deco(cls):
+            self._register(cls, name, force)
+            return cls
+
+        return _deco
+
+
+def build_from_cfg(cfg, registry, default_args=None):
+    if not isinstance(cfg, dict):
+        raise TypeError(f'cfg must be a dict, but got {type(cfg)}')
+    if 'type' not in cfg and not (default_args and 'type' in default_args):
+        raise KeyError('`cfg` or `default_args` must contain the key "type"')
+    args = dict(cfg)
+    if default_args is not None:
+        for k, v in default_args.items():
+            args.setdefault(k, v)
+    obj_type = args.pop('type')
+    if isinstance(obj_type, str):
+        obj_cls = registry.get(obj_type)
+        if obj_cls is None:
+            raise KeyError(f'{obj_type} is not in the {registry.name} registry')
+    elif inspect.isclass(obj_type):
+        obj_cls = obj_type
+    else:
+        raise TypeError(f'type must be a str or class, got {type(obj_type)}')
+    return obj_cls(**args)
+
+
+class ConfigDict(dict):
+    """dict with attribute access (addict-like), nested dicts converted on the way in."""
+
+    def __init__(self, *a, **kw):
+        super().__init__()
+        for k, v in dict(*a, **kw).items():
+            self[k] = v
+
+    @classmethod
+    def _conv(cls, v):
+        if isinstance(v, dict) and not isinstance(v, ConfigDict):
+            return cls(v)
+        if isinstance(v, (list, tuple)):
+            return type(v)(cls._conv(x) for x in v)
+        return v
+
+    def __setitem__(self, k, v):
+        super().__setitem__(k, self._conv(v))
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+# --------------------------------------------------------------------------- init helpers
+def constant_init(module, val, bias=0):
+    if hasattr(module, 'weight') and module.weight is not None:
+        nn.init.constant_(module.weight, val)
+    if hasattr(module, 'bias') and module.bias is not None:
+        nn.init.constant_(module.bias, bias)
+
+
+def xavier_init(module, gain=1, bias=0, distribution='normal'):
+    if distribution == 'uniform':
+        nn.init.xavier_uniform_(module.weight, gain=gain)
+    else:
+        nn.init.xavier_normal_(module.weight, gain=gain)
+    if hasattr(module, 'bias') and module.bias is not None:
+        nn.init.constant_(module.bias, bias)
+
+
+def normal_init(module, mean=0, std=1, bias=0):
+    nn.init.normal_(module.weight, mean, std)
+    if hasattr(module, 'bias') and module.bias is not None:
+        nn.init.constant_(module.bias, bias)
+
+
+def uniform_init(module, a=0, b=1, bias=0):
+    nn.init.uniform_(module.weight, a, b)
+    if hasattr(module, 'bias') and module.bias is not None:
+        nn.init.constant_(module.bias, bias)
+
+
+def kaiming_init(module, a=0, mode='fan_out', nonlinearity='relu', bias=0,
+                 distribution='normal'):
+    if distribution == 'uniform':
+        nn.init.kaiming_uniform_(module.weight, a=a, mode=mode, nonlinearity=nonlinearity)
+    else:
+        nn.init.kaiming_normal_(module.weight, a=a, mode=mode, nonlinearity=nonlinearity)
+    if hasattr(module, 'bias') and module.bias is not None:
+        nn.init.constant_(module.bias, bias)
+
+
+def caffe2_xavier_init(module, bias=0):
+    kaiming_init(module, a=1, mode='fan_in', nonlinearity='leaky_relu', distribution='uniform')
+
+
+def bias_init_with_prob(prior_prob):
+    return float(-np.log((1 - prior_prob) / prior_prob))
+
+
+# --------------------------------------------------------------------------- layers
+def build_conv_layer(cfg, *args, **kwargs):
+    if cfg is None or cfg.get('type', 'Conv2d') in ('Conv2d', 'Conv'):
+        return nn.Conv2d(*args, **kwargs)
+    raise NotImplementedError(f'conv type {cfg} not available in the mmcv stand-in')
+
+
+def build_norm_layer(cfg, num_features, postfix=''):
+    cfg = dict(cfg)
+    t = cfg.pop('type')
+    requires_grad = cfg.pop('requires_grad', True)
+    cfg.setdefault('eps', 1e-5)
+    if t == 'BN':
+        name, layer = 'bn', nn.BatchNorm2d(num_features, **cfg)
+    elif t == 'GN':
+        name, layer = 'gn', nn.GroupNorm(num_channels=num_features, **cfg)
+    else:
+        raise NotImplementedError(t)
+    for p in layer.parameters():
+        p.requires_grad = requires_grad
+    return name + str(postfix), layer
+
+
+class Scale(nn.Module):
+    def __init__(self, scale=1.0):
+        super().__init__()
+        self.scale = nn.Parameter(torch.tensor(scale, dtype=torch.float))
+
+    def forward(self, x):
+        return x * self.scale
+
+
+class ConvModule(nn.Module):
+    """conv -> norm -> act, bias='auto' => bias iff no norm (mmcv/cnn/bricks/conv_module.py)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0,
+                 dilation=1, groups=1, bias='auto', conv_cfg=None, norm_cfg=None,
+                 act_cfg=dict(type='ReLU'), inplace=True, with_spectral_norm=False,
+                 padding_mode='zeros', order=('conv', 'norm', 'act')):
+        super().__init__()
+        assert order == ('conv', 'norm', 'act') and padding_mode == 'zeros'
+        self.with_norm = norm_cfg is not None
+        self.with_activation = act_cfg is not None
+        if bias == 'auto':
+            bias = not self.with_norm
+        self.with_bias = bias
+        self.conv = build_conv_layer(conv_cfg, in_channels, out_channels, kernel_size,
+                                     stride=stride, padding=padding, dilation=dilation,
+                                     groups=groups, bias=bias)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        if self.with_norm:
+            self.norm_name, norm = build_norm_layer(norm_cfg, out_channels)
+            self.add_module(self.norm_name, norm)
+        if self.with_activation:
+            assert act_cfg['type'] == 'ReLU'
+            self.activate = nn.ReLU(inplace=inplace)
+        self.init_weights()
+
+    @property
+    def norm(self):
+        return getattr(self, self.norm_name)
+
+    def init_weights(self):
+        kaiming_init(self.conv, a=0, nonlinearity='relu')
+        if self.with_norm:
+            constant_init(self.norm, 1, bias=0)
+
+    def forward(self, x, activate=True, norm=True):
+        x = self.conv(x)
+        if norm and self.with_norm:
+            x = self.norm(x)
+        if activate and self.with_activation:
+            x = self.activate(x)
+        return x
+
+
+# --------------------------------------------------------------------------- decorators
+def _identity_decorator_factory(*dargs, **dkwargs):
+    if len(dargs) == 1 and callable(dargs[0]) and not dkwargs:
+        return dargs[0]
+
+    def _wrap(f):
+        return f
+
+    return _wrap
+
+
+def load_checkpoint(model, filename, map_location=None, strict=False, logger=None):
+    ckpt = torch.load(filename, map_location=map_location)
+    sd = ckpt.get('state_dict', ckpt)
+    model.load_state_dict(sd, strict=strict)
+    return ckpt
+
+
+def get_dist_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def is_tuple_of(seq, expected_type):
+    return isinstance(seq, tuple) and all(isinstance(x, expected_type) for x in seq)
+
+
+def is_list_of(seq, expected_type):
+    return isinstance(seq, list) and all(isinstance(x, expected_type) for x in seq)
+
+
+def is_seq_of(seq, expected_type, seq_type=None):
+    return isinstance(seq, (list, tuple)) and all(isinstance(x, expected_type) for x in seq)
+
+
+def is_str(x):
+    return isinstance(x, str)
+
+
+# --------------------------------------------------------------------------- permissive stubs
+class _Dummy:
+    """Subclassable / callable placeholder for symbols that only need to exist."""
+
+    def __init__(self, *a, **kw):
+        pass
+
+    def __call__(self, *a, **kw):
+        if len(a) == 1 and callable(a[0]) and not kw:  # used as a decorator
+            return a[0]
+        raise NotImplementedError('mmcv stand-in: symbol is a placeholder')
+
+    @classmethod
+    def register_module(cls, *a, **kw):
+        return _identity_decorator_factory(*a, **kw)
+
+
+class _PermissiveModule(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith('__'):
+            raise AttributeError(name)
+        val = type(name, (_Dummy,), {})
+        setattr(self, name, val)
+        return val
+
+
+def _mod(name, permissive=True, **attrs):
+    m = (_PermissiveModule if permissive else types.ModuleType)(name)
+    m.__dict__.update(attrs)
+    m.__path__ = []  # behave like a package so `import a.b` works
+    sys.modules[name] = m
+    return m
+
+
+def install():
+    """Inject the stand-in modules into sys.modules (idempotent)."""
+    global _INSTALLED
+    if _INSTALLED:
+        return
+    _INSTALLED = True
+    hooks_registry = Registry('hook')
+
+    mmcv = _mod('mmcv', __version__='1.2.7', jit=_identity_decorator_factory,
+                ConfigDict=ConfigDict, is_tuple_of=is_tuple_of, is_list_of=is_list_of,
+                is_seq_of=is_seq_of, is_str=is_str)
+    mmcv.utils = _mod('mmcv.utils', Registry=Registry, build_from_cfg=build_from_cfg,
+                      print_log=lambda *a, **k: None,
+                      get_logger=lambda name, **k: __import__('logging').getLogger(name),
+                      get_git_hash=lambda *a, **k: 'standin', is_tuple_of=is_tuple_of)
+    mmcv.cnn = _mod('mmcv.cnn', ConvModule=ConvModule, Scale=Scale,
+                    build_conv_layer=build_conv_layer, build_norm_layer=build_norm_layer,
+                    normal_init=normal_init, constant_init=constant_init,
+                    xavier_init=xavier_init, kaiming_init=kaiming_init,
+                    uniform_init=uniform_init, caffe2_xavier_init=caffe2_xavier_init,
+                    bias_init_with_prob=bias_init_with_prob,
+                    is_norm=lambda m: isinstance(m, (nn.modules.batchnorm._BatchNorm,
+                                                     nn.GroupNorm)))
+    mmcv.cnn.bricks = _mod('mmcv.cnn.bricks')
+    _mod('mmcv.cnn.bricks.transformer')
+    mmcv.runner = _mod('mmcv.runner', force_fp32=_identity_decorator_factory,
+                       auto_fp16=_identity_decorator_factory,
+                       load_checkpoint=load_checkpoint, get_dist_info=get_dist_info,
+                       HOOKS=hooks_registry)
+    mmcv.runner.hooks = _mod('mmcv.runner.hooks', HOOKS=hooks_registry)
+    mmcv.ops = _mod('mmcv.ops')
+    for sub in ('nms', 'roi_align', 'carafe', 'merge_cells'):
+        setattr(mmcv.ops, sub, _mod('mmcv.ops.' + sub))
+    mmcv.parallel = _mod('mmcv.parallel')
+    mmcv.image = _mod('mmcv.image')
+
+    pc = _mod('pycocotools')
+    for sub in ('mask', 'coco', 'cocoeval'):
+        setattr(pc, sub, _mod('pycocotools.' + sub))
+    _mod('terminaltables')
+    mpl = _mod('matplotlib')
+    for sub in ('pyplot', 'collections', 'patches'):
+        setattr(mpl, sub, _mod('matplotlib.' + sub))
+    # kd_one_stage.py:2 has a stray `from numpy.lib.twodim_base import tri` (gone in NumPy 2)
+    if 'numpy.lib.twodim_base' not in sys.modules:
+        try:
+            import numpy.lib.twodim_base  # noqa: F401
+        except Exception:
+            _mod('numpy.lib.twodim_base', permissive=False, tri=np.tri)
+
+
+def import_reference(ref_root='/root/reference'):
+    """Return the reference's `mmdet` package, imported unmodified through the stand-in."""
+    import os
+    if not os.path.isdir(os.path.join(ref_root, 'mmdet')):
+        raise FileNotFoundError(f'{ref_root}/mmdet not found (reference only exists in the build container)')
+    install()
+    if ref_root not in sys.path:
+        sys.path.insert(0, ref_root)
+    import mmdet  # noqa: F401
+    return mmdet

@@ -1,0 +1,94 @@
+"""CPU: the oracle restatement (oracle/ld_oracle.py) against the golden vectors frozen from the
+UNMODIFIED reference (oracle/make_golden.py).  Integer targets bit-exact, floats <= 1e-5."""
+import os
+
+import pytest
+import torch
+
+from ld_b200 import synth
+from oracle import cases, ld_oracle as lo
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + '.pt'), weights_only=False)
+
+
+@pytest.mark.parametrize('case', cases.TARGET_CASES, ids=lambda c: c[0])
+def test_targets_bit_exact(golden_dir, case):
+    name, n, h, w, seed = case
+    gold = _load(golden_dir, name)
+    gb, gl = synth.make_gts(n, h, w, seed)
+    sizes = cases.featmap_sizes(h, w)
+    metas = synth.make_img_metas(n, h, w)
+    t = lo.ld_targets(sizes, cases.STRIDES, metas, gb, gl, imitation='finegrained')
+    tc = lo.ld_targets(sizes, cases.STRIDES, metas, gb, gl, imitation='fitnet')
+    assert torch.equal(torch.cat(t['labels'], 1), gold['labels'].long())
+    assert torch.equal(torch.cat(t['label_weights'], 1), gold['label_weights'].float())
+    assert torch.equal(torch.cat(t['bbox_targets'], 1), gold['bbox_targets'])
+    assert torch.equal(torch.cat(t['vlr'], 1), gold['vlr'])          # float equality
+    assert torch.equal(torch.cat(t['im'], 1), gold['im_finegrained'].float())
+    assert torch.equal(torch.cat(tc['im'], 1), gold['im_center'].float())
+    assert t['num_total_pos'] == gold['num_total_pos']
+    for a, a0 in zip(t['anchors'], gold['level_anchor0']):
+        assert torch.equal(a[:2], a0)   # first two anchors of the level
+
+
+@pytest.mark.parametrize('case', cases.LOSS_CASES, ids=lambda c: c[0])
+def test_loss_and_grads(golden_dir, case):
+    name, n, h, w, seed = case
+    gold = _load(golden_dir, name)
+    d = cases.loss_case_inputs(n, h, w, seed)
+    leaves = {k: [t.clone().requires_grad_(True) for t in d[k]] for k in ('cls', 'reg', 'x')}
+    tg = lo.ld_targets(d['sizes'], cases.STRIDES, d['img_metas'], d['gt_bboxes'], d['gt_labels'])
+    losses = lo.ld_loss(leaves['cls'], leaves['reg'], d['t_cls'], d['t_reg'], leaves['x'],
+                        d['t_x'], tg, cases.STRIDES)
+    total = sum(sum(v) for v in losses.values())
+    total.backward()
+    for k, v in gold['losses'].items():
+        got = torch.stack([t.detach() for t in losses[k]])
+        assert torch.allclose(got, v, rtol=1e-5, atol=1e-6), (k, got, v)
+    for l in range(5):
+        assert torch.allclose(leaves['cls'][l].grad, gold['grad_cls'][l], rtol=1e-5, atol=1e-7)
+        assert torch.allclose(leaves['reg'][l].grad, gold['grad_reg'][l], rtol=1e-5, atol=1e-7)
+        gx = leaves['x'][l].grad
+        gx = torch.zeros_like(leaves['x'][l]) if gx is None else gx
+        assert torch.allclose(gx.sum(1), gold['grad_x_rowsum'][l], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize('case', cases.STEP_CASES, ids=lambda c: c[0])
+def test_full_step(golden_dir, case):
+    name, sd, td, n, h, w, seed = case
+    gold = _load(golden_dir, name)
+    m = lo.OracleLDDetector(sd, td).train()
+    synth.seeded_init(m, seed)
+    synth.seeded_init(m.teacher_model, seed + 1, prefix='teacher.')
+    b = synth.make_batch(n, h, w, seed=1000 + seed)
+    losses, loss, log = m.step(b)
+    for k, v in gold['log_vars'].items():
+        assert abs(log[k] - v) <= 1e-5 * max(1.0, abs(v)), (k, log[k], v)
+    named = dict(m.named_parameters())
+    assert sorted(k for k, p in named.items() if p.grad is None) == sorted(gold['no_grad'])
+    for k, st in gold['grad_stats'].items():
+        g = named[k].grad
+        assert abs(float(g.double().norm()) - float(st[0])) <= 1e-4 * float(st[0]) + 1e-9, k
+    for k, g in gold['grads'].items():
+        assert torch.allclose(named[k].grad, g, rtol=1e-4, atol=1e-6 * float(g.abs().max())), k
+
+
+def test_reference_known_answers():
+    """The only known-answer vectors the reference's own tests/doctests hold on this path
+    (SURVEY.md §8c): tests/test_anchor.py:22-41 `test_strides` and the bbox_overlaps examples of
+    iou2d_calculator.py:66-87 (values probed from the reference)."""
+    # test_strides: AnchorGenerator([10],[1.],[1.],[10]) on a 2x2 map -> base size 10, i.e. half = 5.
+    # Our generator is the octave_base_scale=8 special case: side 8*stride; check layout + centre rule
+    a = lo.level_anchors(2, 2, 10)
+    exp = torch.tensor([[-5., -5., 5., 5.], [5., -5., 15., 5.], [-5., 5., 5., 15.], [5., 5., 15., 15.]])
+    assert torch.equal((a[:, :2] + a[:, 2:]) / 2, (exp[:, :2] + exp[:, 2:]) / 2)   # centres (x*s, y*s), x fastest
+    assert torch.equal(a[:, 2:] - a[:, :2], torch.full((4, 2), 80.))               # side 8*stride
+    b1 = torch.tensor([[0., 0., 10., 10.], [10., 10., 20., 20.], [32., 32., 38., 42.]])
+    b2 = torch.tensor([[0., 0., 10., 20.], [0., 10., 10., 19.], [10., 10., 20., 20.]])
+    iou = lo.pair_overlaps(b1, b2, 'iou')
+    assert torch.allclose(iou, torch.tensor([[.5, 0, 0], [0, 0, 1.], [0, 0, 0]]))
+    assert torch.allclose(lo.aligned_overlaps(b1, b2, 'giou'), torch.tensor([.5, -.05, -.8214]), atol=1e-4)
+    d = torch.diagonal(lo.pair_overlaps(b1, b2, 'diou'))
+    assert torch.allclose(d, torch.tensor([.95, -.2005, -.4889]), atol=1e-4)       # IoF-based quirk
