@@ -1,0 +1,157 @@
+/* ld_b200 -- C-ABI of the B200-native LD (Localization Distillation) train-step hot path.
+ *
+ * The reference (HikariTJU/LD, an mmdetection 2.10 fork) has NO C-ABI / FFI boundary: it is 100 %
+ * Python and its "plugin API" is mmcv's string->class registry.  This header is
+ * the drop-in boundary underneath that registry: every entry point replaces the body of one
+ * reference Python function on the path (cited per function as file:line under /root/reference)
+ * and is what a binding from the reference side would call (INTEGRATION.md shows the ctypes stub).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the parameter name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); every call is
+ *     asynchronous on that stream and never synchronises the device;
+ *   - return value: 0 on success, otherwise a cudaError_t (>0) or an LDB_E* code (<0);
+ *     ldb200_last_error() returns a message for the calling thread's last failure;
+ *   - "row space": per-anchor arrays are laid out level-major, then image, then (y,x):
+ *         row(l, n, a) = lvl_off[l] * N + n * A_l + a,   A_l = H_l*W_l,  lvl_off = prefix sum of A_l
+ *     which is exactly the reference's per-level `[N, A_l]` stacking (ld_head.py:433-442) with the
+ *     five levels stored back to back, so one kernel launch covers all levels.
+ */
+#ifndef LD_B200_H_
+#define LD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDB_MAX_LEVELS 8
+#define LDB_NUM_TERMS 9 /* loss_cls, loss_bbox, loss_dfl, loss_ld, loss_ld_vlr, loss_kd, loss_kd_neg, loss_im, sum_weight_targets */
+
+#define LDB_EINVAL (-1)   /* bad argument */
+#define LDB_ENOSUP (-2)   /* unsupported configuration */
+#define LDB_EARCH (-3)    /* device is not sm_100 */
+
+enum ldb_dtype { LDB_F32 = 0, LDB_BF16 = 1 };
+enum ldb_im_mode { LDB_IM_FINEGRAINED = 0, LDB_IM_CENTER = 1 /* 'fitnet' / 'decouple' region */ };
+
+const char* ldb200_last_error(void);
+int ldb200_version(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), LDB_EARCH otherwise. */
+int ldb200_check_device(void);
+
+/* Pyramid description shared by the target and loss entry points. */
+typedef struct {
+  int num_levels;                 /* L <= LDB_MAX_LEVELS */
+  int num_imgs;                   /* N */
+  int h[LDB_MAX_LEVELS];          /* feature map height per level */
+  int w[LDB_MAX_LEVELS];          /* feature map width  per level */
+  int stride[LDB_MAX_LEVELS];     /* anchor stride per level (8,16,32,64,128) */
+} ldb_pyramid;
+
+/* ------------------------------------------------------------------------------------------
+ * Target generation.  Replaces LDHead.get_targets/_get_target_single (mmdet/models/dense_heads/
+ * ld_head.py:377-577) = AnchorGenerator.grid_anchors/valid_flags (core/anchor/anchor_generator.py:
+ * 233-328), ATSSAssigner.assign (core/bbox/assigners/atss_assigner.py:33-181), PseudoSampler
+ * (samplers/pseudo_sampler.py:23-41), ATSSAssigner.get_vlr_region (atss_assigner.py:183-298),
+ * LDHead.get_im_region (ld_head.py:580-611), unmap + images_to_levels.
+ * Integer outputs are bit-exact with the reference CPU path; vlr (an IoU value) is float-equal.
+ *
+ *   gt_boxes    [sumG,4] f32 xyxy pixels, all images back to back
+ *   gt_labels   [sumG]   i32
+ *   gt_offsets  [N+1]    i32 prefix offsets into the two arrays above (every image needs G >= 1,
+ *                            the reference itself breaks on G == 0: atss_assigner.py:203-216)
+ *   pad_hw      [N,2]    i32 img_meta['pad_shape'][:2] (valid-flag extent)
+ * outputs (row space, R = N * sum_l A_l rows):
+ *   labels      [R] i32 (num_classes = background)     label_weights [R] f32
+ *   bbox_targets[R,4] f32 (assigned gt, pixels; 0 for non-positives)
+ *   vlr         [R] f32 (IoU with the banded gt, else 0)   im_region [R] f32 {0,1}
+ *   gt_inds     [R] i32 (0 = bg, k+1 = k-th gt of the image) -- may be NULL
+ *   sparse_rows [R] i32 compacted rows with (positive || vlr > 0), arbitrary order
+ *   fg_rows     [R] i32 compacted rows with im_region > 0, arbitrary order
+ *   counts      i32[4 + 3*LDB_MAX_LEVELS]: [0]=n_sparse [1]=n_fg [2]=num_total_pos (sum_img max(P,1))
+ *               [3]=sum_img P, then per level: pos count, vlr count, fg count
+ *   workspace   ldb200_targets_workspace_bytes() bytes
+ */
+size_t ldb200_targets_workspace_bytes(const ldb_pyramid* pyr, int sum_gt);
+int ldb200_ld_targets(const ldb_pyramid* pyr, const float* gt_boxes, const int32_t* gt_labels,
+                      const int32_t* gt_offsets, int sum_gt, const int32_t* pad_hw, int topk,
+                      int im_mode, int num_classes, int32_t* labels, float* label_weights,
+                      float* bbox_targets, float* vlr, float* im_region, int32_t* gt_inds,
+                      int32_t* sparse_rows, int32_t* fg_rows, int32_t* counts, void* workspace,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Loss hyper-parameters (config keys of LDHead, ld_head.py:46-71 + gfl_head.py:77-100).
+ */
+typedef struct {
+  int num_classes;      /* C = cls_out_channels (80; 81 for the LDv2 configs) */
+  int reg_max;          /* 16 -> 17 bins */
+  int feat_channels;    /* 256 (ld_head.py:153-154 hard-codes it) */
+  float qfl_weight, qfl_beta;          /* QualityFocalLoss  (gfocal_loss.py:77-135) */
+  float giou_weight, giou_eps;         /* GIoULoss          (iou_loss.py:325-360)   */
+  float dfl_weight;                    /* DistributionFocalLoss (gfocal_loss.py:138-179) */
+  float ld_weight, ld_T;               /* KnowledgeDistillationKLDivLoss (kd_loss.py:39-88) */
+  float ld_vlr_weight, ld_vlr_T;
+  float kd_weight, kd_T;
+  float im_weight;                     /* IMLoss (kd_loss.py:99-120) */
+} ldb_loss_cfg;
+
+/* Pre-pass over the positive rows.  Replaces ld_head.py:196-207 (weight_targets, Integral,
+ * distance2bbox, IoU score) and the sum feeding ld_head.py:362:
+ *   score [R] f32: IoU(decoded student box, target) on positives (must be zero elsewhere: the
+ *                  call zero-fills it), partial[0] += sum_i weight_targets_i
+ * so that the global normalisers (ld_head.py:338-341, 362-363) can be all-reduced BEFORE the fused
+ * kernel emits final gradients. */
+int ldb200_ld_loss_prepass(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const float* cls,
+                           const float* reg, const int32_t* labels, const float* bbox_targets,
+                           const int32_t* sparse_rows, const int32_t* counts, float* score,
+                           float* wsum, void* stream);
+
+/* Fused LDHead.loss_single x L (ld_head.py:116-282) forward AND gradient in one launch:
+ * dense QFL over all R x C logits, and on the compacted rows GIoU + DFL + LD-KL (positives),
+ * LD-KL on the Valuable Localization Region, KD-KL on class logits, feature-imitation MSE.
+ *
+ *   cls, t_cls [R,C] f32 ; reg, t_reg [R,4*(reg_max+1)] f32 (NHWC rows, row space)
+ *   x, t_x     [R,F] feat_dtype (student / teacher FPN features)
+ *   norm       f32[2] device: [0] num_total_samples (already max(.,1), ld_head.py:341)
+ *                             [1] avg_factor (sum weight_targets + 1e-6, reduced: ld_head.py:362-363)
+ *   term_grad_host f32[LDB_NUM_TERMS-1][LDB_MAX_LEVELS] upstream d(total)/d(term_l) (all 1 for
+ *                  BaseDetector._parse_losses, base.py:198-209); NULL = no gradients
+ *   losses     f32[LDB_NUM_TERMS][LDB_MAX_LEVELS] device (zero-filled by the call): the 8 terms per
+ *              level with loss_bbox/loss_dfl already divided by avg_factor (ld_head.py:364-365)
+ *              and row 8 = sum of weight_targets per level
+ *   d_cls [R,C], d_reg [R,4*(reg_max+1)] grad_dtype (d_reg zero-filled by the call)
+ *   d_im  [n_fg,F] grad_dtype: gradient w.r.t. x at fg_rows[i] (compact; scatter-add downstream)
+ */
+int ldb200_ld_loss_fused(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const float* cls,
+                         const float* reg, const float* t_cls, const float* t_reg, const void* x,
+                         const void* t_x, int feat_dtype, const int32_t* labels,
+                         const float* label_weights, const float* bbox_targets, const float* vlr,
+                         const float* score, const int32_t* sparse_rows, const int32_t* fg_rows,
+                         const int32_t* counts, const float* norm, const float* term_grad_host,
+                         float* losses, void* d_cls, void* d_reg, void* d_im, int grad_dtype,
+                         void* stream);
+
+/* dst[rows[i], :] += src[i, :]  (rows unique).  Adds the compact IM gradient into the dense
+ * gradient of the student FPN map. */
+int ldb200_scatter_add_rows(void* dst, const void* src, const int32_t* rows, const int32_t* n_rows_dev,
+                            int max_rows, int channels, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense LD-KL micro-benchmark (BASELINE.json configs[4]); replaces
+ * knowledge_distillation_kl_div_loss + weight_reduce_loss forward and autograd backward
+ * (kd_loss.py:10-36, losses/utils.py:27-54) on dense [rows, bins] logits:
+ *   loss += loss_weight/avg_factor * sum_r w_r * T^2/bins * KL(softmax(t_r/T) || softmax(s_r/T))
+ *   d_student[r,k] = grad_out * loss_weight/avg_factor * w_r * T/bins * (p_s - p_t)
+ * student, teacher, d_student: [rows, bins] f32; weight [rows] f32; loss f32[1] (accumulated). */
+int ldb200_kl_dense_fwd_bwd(const float* student, const float* teacher, const float* weight,
+                            int64_t rows, int bins, float T, float loss_weight, float avg_factor,
+                            float grad_out, float* loss, float* d_student, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LD_B200_H_ */

@@ -1,0 +1,112 @@
+"""ctypes binding of the C-ABI shared library (include/ld_b200.h).
+
+The CUDA library IS the product: importing this module without a built `libld_b200.so` raises,
+there is no CPU or PyTorch fallback anywhere in `ld_b200`.  PyTorch is only used for device
+memory, streams and `torch.distributed`; tensors cross the boundary as raw device pointers.
+"""
+import ctypes as C
+import os
+
+MAX_LEVELS = 8
+NUM_TERMS = 9
+F32, BF16 = 0, 1
+IM_FINEGRAINED, IM_CENTER = 0, 1
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libld_b200.so')
+
+
+class Pyramid(C.Structure):
+    _fields_ = [('num_levels', C.c_int), ('num_imgs', C.c_int), ('h', C.c_int * MAX_LEVELS),
+                ('w', C.c_int * MAX_LEVELS), ('stride', C.c_int * MAX_LEVELS)]
+
+    @staticmethod
+    def make(num_imgs, sizes, strides):
+        p = Pyramid()
+        assert len(sizes) == len(strides) <= MAX_LEVELS
+        p.num_levels, p.num_imgs = len(sizes), int(num_imgs)
+        for i, ((h, w), s) in enumerate(zip(sizes, strides)):
+            p.h[i], p.w[i], p.stride[i] = int(h), int(w), int(s)
+        return p
+
+    @property
+    def level_anchors(self):
+        return [self.h[i] * self.w[i] for i in range(self.num_levels)]
+
+    @property
+    def rows(self):
+        return self.num_imgs * sum(self.level_anchors)
+
+
+class LossCfg(C.Structure):
+    _fields_ = [('num_classes', C.c_int), ('reg_max', C.c_int), ('feat_channels', C.c_int),
+                ('qfl_weight', C.c_float), ('qfl_beta', C.c_float),
+                ('giou_weight', C.c_float), ('giou_eps', C.c_float),
+                ('dfl_weight', C.c_float),
+                ('ld_weight', C.c_float), ('ld_T', C.c_float),
+                ('ld_vlr_weight', C.c_float), ('ld_vlr_T', C.c_float),
+                ('kd_weight', C.c_float), ('kd_T', C.c_float),
+                ('im_weight', C.c_float)]
+
+
+_SIGS = {
+    'ldb200_last_error': (C.c_char_p, []),
+    'ldb200_version': (C.c_int, []),
+    'ldb200_check_device': (C.c_int, []),
+    'ldb200_targets_workspace_bytes': (C.c_size_t, [C.POINTER(Pyramid), C.c_int]),
+    'ldb200_ld_targets': (C.c_int, [C.POINTER(Pyramid)] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p,
+                                    C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 11),
+    'ldb200_ld_loss_prepass': (C.c_int, [C.POINTER(Pyramid), C.POINTER(LossCfg)] + [C.c_void_p] * 9),
+    'ldb200_ld_loss_fused': (C.c_int, [C.POINTER(Pyramid), C.POINTER(LossCfg)] + [C.c_void_p] * 6 +
+                             [C.c_int] + [C.c_void_p] * 9 + [C.c_void_p] + [C.c_void_p] * 4 +
+                             [C.c_int, C.c_void_p]),
+    'ldb200_scatter_add_rows': (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ldb200_kl_dense_fwd_bwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int, C.c_float, C.c_float,
+                                          C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+class LdB200Error(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    """Every entry point `include/ld_b200.h` declares (kept in sync by tests/test_capi_symbols.py)."""
+    return sorted(_SIGS)
+
+
+def load():
+    """Load the shared library; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise LdB200Error(
+            f'{_LIB_PATH} is missing: ld_b200 has no CPU / PyTorch fallback. Build the CUDA library '
+            f'first (`python -m ld_b200.build` or `__graft_entry__.build()`).')
+    lib = C.CDLL(_LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)   # AttributeError if the symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(code, what=''):
+    if code != 0:
+        msg = load().ldb200_last_error().decode(errors='replace')
+        raise LdB200Error(f'{what} failed with code {code}: {msg}')
+
+
+def ptr(t):
+    """Device (or host) pointer of a contiguous torch tensor, None -> NULL."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), 'ld_b200 kernels need contiguous tensors'
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

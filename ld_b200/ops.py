@@ -1,0 +1,180 @@
+"""Tensor-level wrappers over the C-ABI (`ld_b200/lib.py`): allocate outputs with torch, pass raw
+device pointers + the current CUDA stream, never synchronise."""
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import lib as L
+
+TERMS = ('loss_cls', 'loss_bbox', 'loss_dfl', 'loss_ld', 'loss_ld_vlr', 'loss_kd', 'loss_kd_neg',
+         'loss_im')
+
+
+def _dt(t):
+    return {torch.float32: L.F32, torch.bfloat16: L.BF16}[t]
+
+
+# ------------------------------------------------------------------------------------ row space
+def to_rows(tensors: List[torch.Tensor]) -> torch.Tensor:
+    """List of per-level NCHW tensors -> one [R, C] row-space tensor (level-major, n, y, x).
+    Zero-copy per level when the tensor is channels-last in memory."""
+    return torch.cat([t.permute(0, 2, 3, 1).reshape(-1, t.shape[1]) for t in tensors], 0).contiguous()
+
+
+def from_rows(rows: torch.Tensor, pyr: L.Pyramid) -> List[torch.Tensor]:
+    """[R, C] row-space -> list of per-level [N, C, H, W] views (channels-last memory)."""
+    out, o, n = [], 0, pyr.num_imgs
+    for l in range(pyr.num_levels):
+        h, w = pyr.h[l], pyr.w[l]
+        cnt = n * h * w
+        out.append(rows[o:o + cnt].view(n, h, w, -1).permute(0, 3, 1, 2))
+        o += cnt
+    return out
+
+
+def rows_to_levels(v: torch.Tensor, pyr: L.Pyramid) -> List[torch.Tensor]:
+    """[R(,k)] row-space per-anchor array -> list of [N, A_l(,k)] (the reference's layout)."""
+    out, o, n = [], 0, pyr.num_imgs
+    for a in pyr.level_anchors:
+        out.append(v[o:o + n * a].view(n, a, *v.shape[1:]))
+        o += n * a
+    return out
+
+
+# ------------------------------------------------------------------------------------ targets
+@dataclass
+class LDTargets:
+    pyr: L.Pyramid
+    labels: torch.Tensor         # [R] i32
+    label_weights: torch.Tensor  # [R] f32
+    bbox_targets: torch.Tensor   # [R,4] f32
+    vlr: torch.Tensor            # [R] f32
+    im: torch.Tensor             # [R] f32
+    gt_inds: torch.Tensor        # [R] i32
+    sparse_rows: torch.Tensor    # [R] i32 (first counts[0] valid)
+    fg_rows: torch.Tensor        # [R] i32 (first counts[1] valid)
+    counts: torch.Tensor         # i32 [4 + 3*MAX_LEVELS]
+
+
+def ld_targets(pyr: L.Pyramid, gt_bboxes: List[torch.Tensor], gt_labels: List[torch.Tensor],
+               pad_hw, topk=9, im_mode=L.IM_FINEGRAINED, num_classes=80, device=None) -> LDTargets:
+    lib = L.load()
+    device = device or torch.device('cuda')
+    n = pyr.num_imgs
+    assert len(gt_bboxes) == len(gt_labels) == n
+    offs = [0]
+    for b in gt_bboxes:
+        assert b.dim() == 2 and b.shape[1] == 4 and b.shape[0] >= 1, \
+            'every image needs >= 1 gt box (the reference breaks on G == 0, atss_assigner.py:203-216)'
+        offs.append(offs[-1] + b.shape[0])
+    boxes = torch.cat([b.to(device=device, dtype=torch.float32, non_blocking=True) for b in gt_bboxes]).contiguous()
+    labs = torch.cat([b.to(device=device, dtype=torch.int32, non_blocking=True) for b in gt_labels]).contiguous()
+    host = torch.tensor(offs + [int(v) for hw in pad_hw for v in hw[:2]], dtype=torch.int32)
+    if device.type == 'cuda':
+        host = host.pin_memory()
+    meta = host.to(device, non_blocking=True)
+    offsets, pad = meta[:n + 1], meta[n + 1:]
+    R = pyr.rows
+    i32 = dict(dtype=torch.int32, device=device)
+    f32 = dict(dtype=torch.float32, device=device)
+    t = LDTargets(pyr, torch.empty(R, **i32), torch.empty(R, **f32), torch.empty(R, 4, **f32),
+                  torch.empty(R, **f32), torch.empty(R, **f32), torch.empty(R, **i32),
+                  torch.empty(R, **i32), torch.empty(R, **i32),
+                  torch.empty(4 + 3 * L.MAX_LEVELS, **i32))
+    ws = torch.empty(lib.ldb200_targets_workspace_bytes(C.byref(pyr), offs[-1]), dtype=torch.uint8,
+                     device=device)
+    L.check(lib.ldb200_ld_targets(C.byref(pyr), L.ptr(boxes), L.ptr(labs), L.ptr(offsets), offs[-1],
+                                  L.ptr(pad), topk, im_mode, num_classes, L.ptr(t.labels),
+                                  L.ptr(t.label_weights), L.ptr(t.bbox_targets), L.ptr(t.vlr), L.ptr(t.im),
+                                  L.ptr(t.gt_inds), L.ptr(t.sparse_rows), L.ptr(t.fg_rows),
+                                  L.ptr(t.counts), L.ptr(ws), L.stream_ptr()), 'ldb200_ld_targets')
+    return t
+
+
+# ------------------------------------------------------------------------------------ loss
+def make_loss_cfg(num_classes=80, reg_max=16, feat_channels=256, qfl_weight=1.0, qfl_beta=2.0,
+                  giou_weight=2.0, giou_eps=1e-6, dfl_weight=0.25, ld_weight=0.25, ld_T=10.0,
+                  ld_vlr_weight=0.25, ld_vlr_T=10.0, kd_weight=10.0, kd_T=2.0, im_weight=2.0) -> L.LossCfg:
+    return L.LossCfg(num_classes, reg_max, feat_channels, qfl_weight, qfl_beta, giou_weight, giou_eps,
+                     dfl_weight, ld_weight, ld_T, ld_vlr_weight, ld_vlr_T, kd_weight, kd_T, im_weight)
+
+
+def ld_loss_prepass(cfg: L.LossCfg, cls, reg, tg: LDTargets, want_score=False):
+    """-> (wsum [1] f32 device, score [R] f32 or None)."""
+    lib = L.load()
+    wsum = torch.empty(1, dtype=torch.float32, device=cls.device)
+    score = torch.empty(tg.pyr.rows, dtype=torch.float32, device=cls.device) if want_score else None
+    L.check(lib.ldb200_ld_loss_prepass(C.byref(tg.pyr), C.byref(cfg), L.ptr(cls), L.ptr(reg),
+                                       L.ptr(tg.labels), L.ptr(tg.bbox_targets), L.ptr(tg.sparse_rows),
+                                       L.ptr(tg.counts), L.ptr(score), L.ptr(wsum), L.stream_ptr()),
+            'ldb200_ld_loss_prepass')
+    return wsum, score
+
+
+def loss_normalisers(tg: LDTargets, wsum: torch.Tensor, group=None):
+    """[num_total_samples, avg_factor] on the device (ld_head.py:338-341, 362-363); one 8-byte
+    all-reduce when distributed, no host sync."""
+    norm = torch.stack([tg.counts[2].float(), wsum[0] + 1e-6])
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(norm, group=group)
+        norm = norm / dist.get_world_size(group)
+    norm[0].clamp_(min=1.0)
+    return norm
+
+
+def ld_loss_fused(cfg: L.LossCfg, cls, reg, t_cls, t_reg, x, t_x, tg: LDTargets, norm,
+                  term_grad: Optional[torch.Tensor] = None, grad_dtype=torch.float32, max_fg=None):
+    """One launch: losses [9, MAX_LEVELS] (+ d_cls [R,C], d_reg [R,4*bins], d_im [max_fg,F] when
+    `term_grad` ([8, MAX_LEVELS] host floats or True for all-ones) is given)."""
+    lib = L.load()
+    dev = cls.device
+    R = tg.pyr.rows
+    assert cls.shape == (R, cfg.num_classes) and reg.shape == (R, 4 * (cfg.reg_max + 1))
+    assert x.dtype == t_x.dtype and x.shape == t_x.shape == (R, cfg.feat_channels)
+    losses = torch.empty(L.NUM_TERMS, L.MAX_LEVELS, dtype=torch.float32, device=dev)
+    d_cls = d_reg = d_im = None
+    tgp = None
+    if term_grad is not None:
+        if term_grad is True:
+            term_grad = torch.ones(L.NUM_TERMS - 1, L.MAX_LEVELS)
+        tgh = term_grad.detach().to('cpu', torch.float32).contiguous()
+        assert tgh.shape == (L.NUM_TERMS - 1, L.MAX_LEVELS)
+        tgp = C.c_void_p(tgh.data_ptr())
+        max_fg = R if max_fg is None else max_fg
+        d_cls = torch.empty(R, cfg.num_classes, dtype=grad_dtype, device=dev)
+        d_reg = torch.empty(R, 4 * (cfg.reg_max + 1), dtype=grad_dtype, device=dev)
+        d_im = torch.empty(max_fg, cfg.feat_channels, dtype=grad_dtype, device=dev)
+    L.check(lib.ldb200_ld_loss_fused(C.byref(tg.pyr), C.byref(cfg), L.ptr(cls), L.ptr(reg), L.ptr(t_cls),
+                                     L.ptr(t_reg), L.ptr(x), L.ptr(t_x), _dt(x.dtype), L.ptr(tg.labels),
+                                     L.ptr(tg.label_weights), L.ptr(tg.bbox_targets), L.ptr(tg.vlr), None,
+                                     L.ptr(tg.sparse_rows), L.ptr(tg.fg_rows), L.ptr(tg.counts),
+                                     L.ptr(norm), tgp, L.ptr(losses), L.ptr(d_cls), L.ptr(d_reg),
+                                     L.ptr(d_im), _dt(grad_dtype), L.stream_ptr()), 'ldb200_ld_loss_fused')
+    return losses, d_cls, d_reg, d_im
+
+
+def scatter_add_rows(dst, src, rows, n_rows_dev, max_rows=None):
+    lib = L.load()
+    max_rows = src.shape[0] if max_rows is None else max_rows
+    L.check(lib.ldb200_scatter_add_rows(L.ptr(dst), L.ptr(src), L.ptr(rows), L.ptr(n_rows_dev),
+                                        int(max_rows), int(dst.shape[-1]), _dt(dst.dtype),
+                                        L.stream_ptr()), 'ldb200_scatter_add_rows')
+
+
+def kl_dense_fwd_bwd(student, teacher, weight, T=10.0, loss_weight=0.25, avg_factor=4.0, grad_out=1.0,
+                     loss=None, d_student=None):
+    """Dense LD-KL forward+backward (BASELINE configs[4]); accumulates into `loss` [1]."""
+    lib = L.load()
+    rows, bins = student.shape
+    if loss is None:
+        loss = torch.zeros(1, dtype=torch.float32, device=student.device)
+    if d_student is None:
+        d_student = torch.empty_like(student)
+    L.check(lib.ldb200_kl_dense_fwd_bwd(L.ptr(student), L.ptr(teacher), L.ptr(weight), rows, bins,
+                                        float(T), float(loss_weight), float(avg_factor), float(grad_out),
+                                        L.ptr(loss), L.ptr(d_student), L.stream_ptr()),
+            'ldb200_kl_dense_fwd_bwd')
+    return loss, d_student
