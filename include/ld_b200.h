@@ -151,6 +151,44 @@ int ldb200_kl_dense_fwd_bwd(const float* student, const float* teacher, const fl
                             int64_t rows, int bins, float T, float loss_weight, float avg_factor,
                             float grad_out, float* loss, float* d_student, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (bf16 x bf16 -> fp32 accumulate), NHWC.
+ * Replaces the cuDNN `nn.Conv2d` calls of the reference's ResNet / FPN / GFLHead forward
+ * (backbones/resnet.py:65-92,260-299; necks/fpn.py:170-221; dense_heads/gfl_head.py:161-183) and,
+ * called with rotated weights, autograd's conv backward-data.
+ *
+ *   out[n, y*oys+oyo, x*oxs+oxo, co] = epi( sum_t sum_ci in[n, y*sy + tap_dy[t], x*sx + tap_dx[t], ci]
+ *                                                        * weight[co, tap_wk[t] + ci] )
+ *   epi(v) = relu?( v*scale[co] + bias[co] + add_src[n, y*add_H/HO, x*add_W/WO, co] ) * (mask_src > 0)
+ *            (+ previous out when accumulate)
+ * Out-of-range input coordinates read as zero (padding).  Cin must be a multiple of 64.
+ */
+typedef struct {
+  const void* in;      /* [N, H, W, in_ld] bf16, channels [0, Cin) used */
+  int N, H, W, Cin, in_ld;
+  const void* weight;  /* [Cout, w_k] bf16, K-major; tap t / input channel ci at column tap_wk[t] + ci */
+  int Cout, w_k;
+  int ntaps;           /* <= 9 */
+  int tap_dx[9], tap_dy[9], tap_wk[9];
+  int sx, sy;          /* stride in input coordinates */
+  int HO, WO;          /* logical output extent (tile space) */
+  int flat;            /* 1: 1x1 stride-1 conv, pixels flattened to one dimension (no tile padding) */
+  void* out;           /* [N, OH, OW, out_ld] bf16 or f32 */
+  int OH, OW;          /* physical output extent (0 = HO, WO) */
+  int oys, oyo, oxs, oxo; /* output pixel = (y*oys + oyo, x*oxs + oxo)   (0,0,0,0 = identity) */
+  int out_ld, out_f32;
+  const float* scale;  /* [Cout] or NULL */
+  const float* bias;   /* [Cout] or NULL */
+  const void* add_src; /* [N, add_H, add_W, add_ld] bf16 or NULL (nearest-resampled to the output grid) */
+  int add_H, add_W, add_ld;
+  const void* mask_src; /* bf16, same pixel addressing as out with row stride mask_ld, or NULL */
+  int mask_ld;
+  int relu;
+  int accumulate;
+} ldb_conv_desc;
+
+int ldb200_conv2d_tc(const ldb_conv_desc* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

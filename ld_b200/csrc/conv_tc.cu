@@ -1,0 +1,496 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), operands staged by TMA.
+//
+// Replaces every `nn.Conv2d` the reference's hot path runs through cuDNN
+// (mmdet/models/backbones/resnet.py:65-92,260-299 bottleneck/basic-block convs, necks/fpn.py:170-221
+// lateral/output/extra convs, dense_heads/gfl_head.py:161-183 tower + gfl_cls/gfl_reg convs) and,
+// with rotated weights, their data-gradient (autograd's conv backward-data).
+//
+//   out[n, y, x, co] = epilogue( sum_{tap} sum_{ci} A[n, y*sy + dy_tap, x*sx + dx_tap, ci] * W[co, tap, ci] )
+//
+// * activations are NHWC bf16; one CTA tile = TH x TW output pixels (TH*TW = 128 = UMMA M) of one
+//   image x BN output channels.  For every tap and every 64-channel slice the A operand is ONE 4-D
+//   TMA box {64 ch, TW, TH, 1} at the shifted coordinate: the box lands in shared memory as 128 rows
+//   x 128 B, which is exactly the K-major SWIZZLE_128B canonical UMMA layout, padding comes for free
+//   from TMA out-of-bounds zero fill, stride-2 convs use the tensor map's element strides.  1x1 convs
+//   use the same map with the pixels flattened ({C, N*H*W, 1, 1}).
+// * weights are [Cout][taps*Cin] bf16 (K-major), one 2-D TMA box {64, BN} per k-block.
+// * warp-specialised persistent kernel: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma
+//   issuer (kind::f16, bf16 x bf16 -> fp32 in TMEM, M=128, N=BN, K=16), warp 2 = TMEM allocator,
+//   warps 4-7 = epilogue (tcgen05.ld 32x32b -> registers -> fused scale/bias (folded BN, conv bias,
+//   Scale), residual / nearest-upsample add, ReLU or ReLU-mask, optional accumulate -> NHWC store).
+//   Two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ldb {
+
+constexpr int CONV_THREADS = 256;
+constexpr int TILE_M = 128;
+constexpr int KCH = 64;                        // channels per k-block (128 B of bf16)
+constexpr int A_TILE_BYTES = TILE_M * KCH * 2;  // 16 KB
+
+struct ConvParams {
+  int N, HO, WO;            // tile space = logical output pixels
+  int TH, TW, tiles_y, tiles_x, tiles_n;
+  int Cout, Cin;
+  int ntaps;
+  int tap_dx[9], tap_dy[9], tap_wk[9];
+  int sx, sy;               // input coordinate = out coordinate * s + tap offset
+  // output addressing: element offset of pixel (n,y,x) = ((n*OH + y*oys + oyo)*OW + x*oxs + oxo)*ldc
+  int OH, OW, oys, oyo, oxs, oxo, ldc;
+  void* out;
+  int out_f32;
+  const float* scale;       // [Cout] or null (1)
+  const float* bias;        // [Cout] or null (0)
+  const __nv_bfloat16* add_src;  // optional add, nearest-resampled from [N, add_H, add_W, add_ld]
+  int add_H, add_W, add_ld;
+  const __nv_bfloat16* mask_src; // optional: multiply by (mask_src > 0), same addressing as out (bf16, ld = mask_ld)
+  int mask_ld;
+  int relu;
+  int accumulate;           // out += result (read-modify-write in the output dtype)
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarrier_init(uint64_t* b, int cnt) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s2u(b)), "r"(cnt));
+}
+__device__ __forceinline__ void mbarrier_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t}" ::"r"(s2u(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbarrier_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarrier_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(b)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(s2u(dst)), "l"(map), "r"(s2u(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(s2u(dst)), "l"(map), "r"(s2u(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO), version 1, layout type 2.
+__device__ __forceinline__ uint64_t smem_desc_k128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;                 // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;       // SBO
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+
+template <int BN> struct ConvCfg {
+  static constexpr int B_TILE_BYTES = BN * KCH * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=BN, M=128
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                    ((uint32_t)(TILE_M >> 4) << 24);
+};
+
+__device__ __forceinline__ size_t out_offset(const ConvParams& p, int n, int y, int x) {
+  return (((size_t)n * p.OH + (size_t)(y * p.oys + p.oyo)) * p.OW + (size_t)(x * p.oxs + p.oxo));
+}
+
+template <int BN>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  extern __shared__ unsigned char conv_smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)conv_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tfull = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cchunks = p.Cin / KCH;
+  const int kblocks = p.ntaps * cchunks;
+  const int total_tiles = p.N * p.tiles_y * p.tiles_x * p.tiles_n;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbarrier_init(&full[s], 1);
+      mbarrier_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbarrier_init(&tfull[a], 1);
+      mbarrier_init(&tempty[a], 4);   // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)),
+                 "n"(Cfg::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.tiles_n;
+        int sp = t / p.tiles_n;
+        const int tx = sp % p.tiles_x;
+        sp /= p.tiles_x;
+        const int ty = sp % p.tiles_y;
+        const int n = sp / p.tiles_y;
+        const int x0 = tx * p.TW * p.sx, y0 = ty * p.TH * p.sy;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * KCH;
+          mbarrier_wait(&empty[stage], phase ^ 1);
+          unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+          mbarrier_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(sa, &tmA, &full[stage], c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], n);
+          tma_load_2d(sa + A_TILE_BYTES, &tmB, &full[stage], p.tap_wk[tap] + c0, nt * BN);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbarrier_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbarrier_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = s2u(smem + (size_t)stage * Cfg::STAGE_BYTES);
+          const uint64_t da = smem_desc_k128(sa), db = smem_desc_k128(sa + A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < KCH / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), Cfg::IDESC, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);                 // frees the smem slot when the MMAs retire
+          if (kb == kblocks - 1) umma_commit(&tfull[acc]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue ==========================================
+    const int ew = warp - 4;   // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int nt = t % p.tiles_n;
+      int sp = t / p.tiles_n;
+      const int tx = sp % p.tiles_x;
+      sp /= p.tiles_x;
+      const int ty = sp % p.tiles_y;
+      const int n = sp / p.tiles_y;
+      const int m = ew * 32 + lane;
+      const int y = ty * p.TH + m / p.TW, x = tx * p.TW + m % p.TW;
+      const bool pix_ok = (y < p.HO) && (x < p.WO);
+      const size_t pix = pix_ok ? out_offset(p, n, y, x) : 0;
+      size_t add_pix = 0;
+      if (p.add_src && pix_ok) {
+        const int ay = (int)(((long long)y * p.add_H) / p.HO), ax = (int)(((long long)x * p.add_W) / p.WO);
+        add_pix = (((size_t)n * p.add_H + ay) * p.add_W + ax) * (size_t)p.add_ld;
+      }
+      mbarrier_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int cbase = nt * BN + ch * 32;
+        if (cbase >= p.Cout) break;   // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + ch * 32), r);
+        if (pix_ok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.scale) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cbase + j < p.Cout) v[j] *= __ldg(p.scale + cbase + j);
+          }
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cbase + j < p.Cout) v[j] += __ldg(p.bias + cbase + j);
+          }
+          if (p.add_src) {
+            const __nv_bfloat16* a = p.add_src + add_pix + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (cbase + j + 8 <= p.Cout) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(a + j));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h[e]);
+                  v[j + 2 * e] += f.x;
+                  v[j + 2 * e + 1] += f.y;
+                }
+              } else {
+                for (int e = 0; e < 8; ++e)
+                  if (cbase + j + e < p.Cout) v[j + e] += __bfloat162float(a[j + e]);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.mask_src) {
+            const __nv_bfloat16* mk = p.mask_src + pix * (size_t)p.mask_ld + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cbase + j < p.Cout && !(__bfloat162float(mk[j]) > 0.f)) v[j] = 0.f;
+          }
+          if (p.out_f32) {
+            float* o = (float*)p.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (cbase + j + 4 <= p.Cout) {
+                float4 w4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (p.accumulate) {
+                  const float4 old = *reinterpret_cast<const float4*>(o + j);
+                  w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w;
+                }
+                *reinterpret_cast<float4*>(o + j) = w4;
+              } else {
+                for (int e = 0; e < 4; ++e)
+                  if (cbase + j + e < p.Cout) o[j + e] = v[j + e] + (p.accumulate ? o[j + e] : 0.f);
+              }
+            }
+          } else {
+            __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (cbase + j + 8 <= p.Cout) {
+                if (p.accumulate) {
+                  const uint4 q = *reinterpret_cast<const uint4*>(o + j);
+                  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h[e]);
+                    v[j + 2 * e] += f.x;
+                    v[j + 2 * e + 1] += f.y;
+                  }
+                }
+                uint4 q;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(o + j) = q;
+              } else {
+                for (int e = 0; e < 8; ++e)
+                  if (cbase + j + e < p.Cout)
+                    o[j + e] = __float2bfloat16_rn(v[j + e] + (p.accumulate ? __bfloat162float(o[j + e]) : 0.f));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbarrier_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box, const cuuint32_t* estr, const char* what) {
+  PFN_encodeTiled enc = get_encode();
+  LDB_REQUIRE(enc, LDB_ENOSUP, "cuTensorMapEncodeTiled not available from the driver");
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LDB_REQUIRE(r == CUDA_SUCCESS, LDB_EINVAL, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return 0;
+}
+
+static int g_conv_sms = 0;
+
+template <int BN>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    LDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr = true;
+  }
+  if (!g_conv_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_conv_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int total = p.N * p.tiles_y * p.tiles_x * p.tiles_n;
+  const int grid = total < g_conv_sms ? total : g_conv_sms;
+  conv_tc_kernel<BN><<<grid, CONV_THREADS, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ldb
+
+using namespace ldb;
+
+extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
+  LDB_REQUIRE(d && d->in && d->weight && d->out, LDB_EINVAL, "conv2d_tc: null pointer");
+  LDB_REQUIRE(d->Cin > 0 && d->Cin % KCH == 0, LDB_ENOSUP, "conv2d_tc: Cin=%d must be a multiple of 64", d->Cin);
+  LDB_REQUIRE(d->in_ld >= d->Cin && d->in_ld % 8 == 0, LDB_EINVAL, "conv2d_tc: in_ld");
+  LDB_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, LDB_EINVAL, "conv2d_tc: ntaps");
+  LDB_REQUIRE(d->N >= 1 && d->HO >= 1 && d->WO >= 1 && d->Cout >= 1, LDB_EINVAL, "conv2d_tc: shape");
+  LDB_REQUIRE(d->sx >= 1 && d->sy >= 1 && d->sx <= 8 && d->sy <= 8, LDB_EINVAL, "conv2d_tc: stride");
+  LDB_REQUIRE(d->out_ld >= d->Cout && d->out_ld % (d->out_f32 ? 4 : 8) == 0, LDB_EINVAL, "conv2d_tc: out_ld alignment");
+  LDB_REQUIRE(((uintptr_t)d->in & 15) == 0 && ((uintptr_t)d->weight & 15) == 0 && ((uintptr_t)d->out & 15) == 0,
+              LDB_EINVAL, "conv2d_tc: pointers must be 16-byte aligned");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N; p.HO = d->HO; p.WO = d->WO; p.Cout = d->Cout; p.Cin = d->Cin; p.ntaps = d->ntaps;
+  for (int t = 0; t < d->ntaps; ++t) {
+    p.tap_dx[t] = d->tap_dx[t]; p.tap_dy[t] = d->tap_dy[t]; p.tap_wk[t] = d->tap_wk[t];
+  }
+  p.sx = d->sx; p.sy = d->sy;
+  p.OH = d->OH ? d->OH : d->HO; p.OW = d->OW ? d->OW : d->WO;
+  p.oys = d->oys ? d->oys : 1; p.oxs = d->oxs ? d->oxs : 1; p.oyo = d->oyo; p.oxo = d->oxo;
+  p.ldc = d->out_ld; p.out = d->out; p.out_f32 = d->out_f32;
+  p.scale = d->scale; p.bias = d->bias;
+  p.add_src = (const __nv_bfloat16*)d->add_src;
+  p.add_H = d->add_H ? d->add_H : p.OH; p.add_W = d->add_W ? d->add_W : p.OW;
+  p.add_ld = d->add_ld ? d->add_ld : d->Cout;
+  p.mask_src = (const __nv_bfloat16*)d->mask_src; p.mask_ld = d->mask_ld ? d->mask_ld : d->out_ld;
+  p.relu = d->relu; p.accumulate = d->accumulate;
+  if (p.add_src) LDB_REQUIRE(((uintptr_t)p.add_src & 15) == 0 && p.add_ld % 8 == 0, LDB_EINVAL, "conv2d_tc: add_src alignment");
+
+  // tile shape: flattened pixels for "flat" problems, else the TH x TW (TH*TW = 128) minimising padding waste
+  CUtensorMap tmA, tmB;
+  if (d->flat) {
+    LDB_REQUIRE(d->ntaps == 1 && d->sx == 1 && d->sy == 1, LDB_EINVAL, "conv2d_tc: flat mode needs a 1x1 stride-1 conv");
+    const long long M = (long long)d->N * d->HO * d->WO;
+    p.N = 1; p.HO = 1; p.WO = (int)M; p.TH = 1; p.TW = TILE_M;
+    p.OH = 1; p.OW = (int)M; p.oys = p.oxs = 1; p.oyo = p.oxo = 0;
+    LDB_REQUIRE(!p.add_src || (p.add_H == (d->OH ? d->OH : d->HO) && p.add_W == (d->OW ? d->OW : d->WO)), LDB_ENOSUP,
+                "conv2d_tc: flat mode cannot resample add_src");
+    if (p.add_src) { p.add_H = 1; p.add_W = (int)M; }
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)M, 1, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)d->in_ld * 2 * (cuuint64_t)M,
+                             (cuuint64_t)d->in_ld * 2 * (cuuint64_t)M};
+    cuuint32_t box[4] = {KCH, TILE_M, 1, 1}, es[4] = {1, 1, 1, 1};
+    int e = encode_map(&tmA, d->in, 4, dims, strides, box, es, "A(flat)");
+    if (e) return e;
+  } else {
+    int best_th = 8, best_tiles = 1 << 30;
+    for (int th = 1; th <= TILE_M; th *= 2) {
+      const int tw = TILE_M / th;
+      if (tw * d->sx > 256 || th * d->sy > 256) continue;
+      const int tiles = ((d->HO + th - 1) / th) * ((d->WO + tw - 1) / tw);
+      if (tiles < best_tiles || (tiles == best_tiles && abs(th - 8) < abs(best_th - 8))) {
+        best_tiles = tiles;
+        best_th = th;
+      }
+    }
+    p.TH = best_th; p.TW = TILE_M / best_th;
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)d->in_ld * 2 * d->W,
+                             (cuuint64_t)d->in_ld * 2 * d->W * d->H};
+    cuuint32_t box[4] = {KCH, (cuuint32_t)(p.TW * d->sx), (cuuint32_t)(p.TH * d->sy), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)d->sx, (cuuint32_t)d->sy, 1};
+    int e = encode_map(&tmA, d->in, 4, dims, strides, box, es, "A");
+    if (e) return e;
+  }
+  p.tiles_y = (p.HO + p.TH - 1) / p.TH;
+  p.tiles_x = (p.WO + p.TW - 1) / p.TW;
+  const int BN = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
+  p.tiles_n = (d->Cout + BN - 1) / BN;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->w_k, (cuuint64_t)d->Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)d->w_k * 2};
+    cuuint32_t box[2] = {KCH, (cuuint32_t)BN}, es[2] = {1, 1};
+    LDB_REQUIRE(d->w_k % 8 == 0, LDB_EINVAL, "conv2d_tc: weight row length must be a multiple of 8");
+    int e = encode_map(&tmB, d->weight, 2, dims, strides, box, es, "B");
+    if (e) return e;
+  }
+  if (BN == 256) return launch_conv<256>(tmA, tmB, p, stream);
+  if (BN == 128) return launch_conv<128>(tmA, tmB, p, stream);
+  return launch_conv<64>(tmA, tmB, p, stream);
+}

@@ -12,6 +12,8 @@
 // and their autograd backward.  HBM-bound: the only dense traffic is one read of the class logits
 // and one write of their gradient; everything else runs on the compacted positive / VLR / fine-
 // grained row lists produced by targets.cu (one warp per row, warp-shuffle softmaxes).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ldb {
@@ -33,6 +35,7 @@ struct LossParams {
   const float* norm;
   float tg[LDB_NUM_TERMS - 1][LDB_MAX_LEVELS];
   int want_grad;
+  int phases;   // bit0 dense QFL, bit1 sparse rows, bit2 imitation rows (all set normally)
   float* losses;
   void *d_cls, *d_reg, *d_im;
   int grad_bf16;
@@ -43,6 +46,17 @@ struct LossParams {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 __device__ __forceinline__ float softplusf_(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
 
+// Dense-phase variant of qfl_neg: one ex2 + one lg2 + one fast reciprocal per logit (relative error
+// ~1e-6, far inside the 1e-4 parity tolerance; the sparse positive rows keep the precise path).
+__device__ __forceinline__ void qfl_neg_fast(float x, float beta, float& loss, float& grad) {
+  const float e = __expf(-fabsf(x));
+  const float r = __fdividef(1.f, 1.f + e);
+  const float s = x >= 0.f ? r : e * r;
+  const float sp = fmaxf(x, 0.f) + __logf(1.f + e);
+  const float sb = (beta == 2.f) ? s * s : __powf(s, beta);
+  loss = sp * sb;
+  grad = sb * (s + sp * beta * (1.f - s));
+}
 // QFL element, negative class (gfocal_loss.py:34-39): sp(x) * sigma^beta and d/dx.
 __device__ __forceinline__ void qfl_neg(float x, float beta, float& loss, float& grad) {
   float s = sigmoidf_(x), sp = softplusf_(x);
@@ -204,7 +218,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, 2) ld_loss_fused_kernel(LossPara
 
   // ---------------- phase 1: dense QFL over every non-positive row (gfocal_loss.py:34-49) -----
   const int vpr = C >> 2;  // float4 per row (C % 4 == 0 fast path), else scalar path below
-  for (int l = 0; l < P.pyr.L; ++l) {
+  for (int l = 0; l < ((P.phases & 1) ? P.pyr.L : 0); ++l) {
     const long long r0 = (long long)P.pyr.off[l] * N, r1 = (long long)P.pyr.off[l + 1] * N;
     const float gsc = P.tg[0][l];
     float acc = 0.f;
@@ -218,10 +232,10 @@ __global__ void __launch_bounds__(LOSS_THREADS, 2) ld_loss_fused_kernel(LossPara
         const float sc = P.qfl_w * __ldg(P.label_w + r) / nts;
         const float4 xv = __ldg(reinterpret_cast<const float4*>(P.cls) + v);
         float lo[4], gr[4];
-        qfl_neg(xv.x, P.beta, lo[0], gr[0]);
-        qfl_neg(xv.y, P.beta, lo[1], gr[1]);
-        qfl_neg(xv.z, P.beta, lo[2], gr[2]);
-        qfl_neg(xv.w, P.beta, lo[3], gr[3]);
+        qfl_neg_fast(xv.x, P.beta, lo[0], gr[0]);
+        qfl_neg_fast(xv.y, P.beta, lo[1], gr[1]);
+        qfl_neg_fast(xv.z, P.beta, lo[2], gr[2]);
+        qfl_neg_fast(xv.w, P.beta, lo[3], gr[3]);
         acc += sc * ((lo[0] + lo[1]) + (lo[2] + lo[3]));
         if (wg) {
           const float k = sc * gsc;
@@ -256,7 +270,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, 2) ld_loss_fused_kernel(LossPara
   }
 
   // ---------------- phase 2: compacted positive / VLR rows, one warp per row ------------------
-  const int n_sparse = P.counts[0];
+  const int n_sparse = (P.phases & 2) ? P.counts[0] : 0;
   const bool active = lane < bins;
   for (int i = blockIdx.x * LOSS_WARPS + wid; i < n_sparse; i += gridDim.x * LOSS_WARPS) {
     const int r = P.sparse_rows[i];
@@ -394,7 +408,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, 2) ld_loss_fused_kernel(LossPara
   }
 
   // ---------------- phase 3: feature imitation on the fine-grained rows (kd_loss.py:91-96) ----
-  const int n_fg = P.counts[1];
+  const int n_fg = (P.phases & 4) ? P.counts[1] : 0;
   const int F = P.F;
   const FT* __restrict__ xs_ = (const FT*)P.x;
   const FT* __restrict__ xt_ = (const FT*)P.t_x;
@@ -723,6 +737,10 @@ extern "C" int ldb200_ld_loss_fused(const ldb_pyramid* pyr, const ldb_loss_cfg* 
   P.labels = labels; P.label_w = label_weights; P.bbox_t = bbox_targets; P.vlr = vlr;
   P.sparse_rows = sparse_rows; P.fg_rows = fg_rows; P.counts = counts; P.norm = norm;
   P.want_grad = wg ? 1 : 0;
+  {
+    const char* ph = getenv("LDB200_LOSS_PHASES");   // profiling aid only
+    P.phases = ph ? atoi(ph) : 7;
+  }
   if (wg) memcpy(P.tg, term_grad_host, sizeof(P.tg));
   P.losses = losses; P.d_cls = d_cls; P.d_reg = d_reg; P.d_im = d_im;
   P.grad_bf16 = grad_dtype == LDB_BF16;
@@ -759,9 +777,9 @@ extern "C" int ldb200_scatter_add_rows(void* dst, const void* src, const int32_t
 extern "C" int ldb200_kl_dense_fwd_bwd(const float* student, const float* teacher, const float* weight,
                                        int64_t rows, int bins, float T, float loss_weight, float avg_factor,
                                        float grad_out, float* loss, float* d_student, void* stream_) {
-  LDB_REQUIRE(student && teacher && weight && loss && d_student, LDB_EINVAL, "kl_dense: null pointer");
   LDB_REQUIRE(rows >= 0 && bins >= 2 && T >= 1.f && avg_factor > 0.f, LDB_EINVAL, "kl_dense: bad argument");
-  if (rows == 0) return 0;
+  if (rows == 0) return 0;   // empty input: loss unchanged, nothing to write (pointers may be null)
+  LDB_REQUIRE(student && teacher && weight && loss && d_student, LDB_EINVAL, "kl_dense: null pointer");
   cudaStream_t stream = (cudaStream_t)stream_;
   const float kscale = loss_weight / avg_factor;
   const bool aligned = (((uintptr_t)student | (uintptr_t)teacher | (uintptr_t)weight | (uintptr_t)d_student) & 15) == 0;

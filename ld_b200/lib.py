@@ -48,6 +48,18 @@ class LossCfg(C.Structure):
                 ('im_weight', C.c_float)]
 
 
+class ConvDesc(C.Structure):
+    _fields_ = [('in_', C.c_void_p), ('N', C.c_int), ('H', C.c_int), ('W', C.c_int), ('Cin', C.c_int),
+                ('in_ld', C.c_int), ('weight', C.c_void_p), ('Cout', C.c_int), ('w_k', C.c_int),
+                ('ntaps', C.c_int), ('tap_dx', C.c_int * 9), ('tap_dy', C.c_int * 9), ('tap_wk', C.c_int * 9),
+                ('sx', C.c_int), ('sy', C.c_int), ('HO', C.c_int), ('WO', C.c_int), ('flat', C.c_int),
+                ('out', C.c_void_p), ('OH', C.c_int), ('OW', C.c_int), ('oys', C.c_int), ('oyo', C.c_int),
+                ('oxs', C.c_int), ('oxo', C.c_int), ('out_ld', C.c_int), ('out_f32', C.c_int),
+                ('scale', C.c_void_p), ('bias', C.c_void_p), ('add_src', C.c_void_p), ('add_H', C.c_int),
+                ('add_W', C.c_int), ('add_ld', C.c_int), ('mask_src', C.c_void_p), ('mask_ld', C.c_int),
+                ('relu', C.c_int), ('accumulate', C.c_int)]
+
+
 _SIGS = {
     'ldb200_last_error': (C.c_char_p, []),
     'ldb200_version': (C.c_int, []),
@@ -60,6 +72,7 @@ _SIGS = {
                              [C.c_int] + [C.c_void_p] * 9 + [C.c_void_p] + [C.c_void_p] * 4 +
                              [C.c_int, C.c_void_p]),
     'ldb200_scatter_add_rows': (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ldb200_conv2d_tc': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     'ldb200_kl_dense_fwd_bwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int, C.c_float, C.c_float,
                                           C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

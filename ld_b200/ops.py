@@ -178,3 +178,76 @@ def kl_dense_fwd_bwd(student, teacher, weight, T=10.0, loss_weight=0.25, avg_fac
                                         L.ptr(loss), L.ptr(d_student), L.stream_ptr()),
             'ldb200_kl_dense_fwd_bwd')
     return loss, d_student
+
+
+# ------------------------------------------------------------------------------------ convolution
+def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, kh, kw] (PyTorch OIHW) -> [Cout, kh*kw*Cin] bf16, tap-major then channel
+    (the K-major operand layout of ldb200_conv2d_tc)."""
+    co, ci, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(torch.bfloat16).contiguous()
+
+
+def pack_conv_weight_dgrad(w: torch.Tensor) -> torch.Tensor:
+    """Weights of the data-gradient conv: roles of Cin/Cout swapped, taps kept in forward order
+    (the tap table of `conv2d_tc` is given the mirrored offsets)."""
+    return pack_conv_weight(w.transpose(0, 1))
+
+
+def conv2d_tc(x, w_packed, cout, kh=1, kw=1, stride=1, pad=0, out=None, out_dtype=torch.bfloat16,
+              scale=None, bias=None, add=None, mask=None, relu=False, accumulate=False, flat=None,
+              taps=None, out_hw=None, out_map=None):
+    """NHWC bf16 convolution on tcgen05 (ldb200_conv2d_tc).  x: [N,H,W,Cin] bf16 contiguous (or a
+    channel slice with stride(2) = ld).  Returns [N,HO,WO,Cout] NHWC `out_dtype`."""
+    lib = L.load()
+    assert x.dtype == torch.bfloat16 and x.dim() == 4
+    n, h, w_, cin = x.shape
+    in_ld = x.stride(2)
+    assert x.stride(3) == 1 and x.stride(1) == w_ * in_ld and x.stride(0) == h * w_ * in_ld
+    if out_hw is None:
+        ho = (h + 2 * pad - kh) // stride + 1
+        wo = (w_ + 2 * pad - kw) // stride + 1
+    else:
+        ho, wo = out_hw
+    d = L.ConvDesc()
+    d.in_ = x.data_ptr()
+    d.N, d.H, d.W, d.Cin, d.in_ld = n, h, w_, cin, in_ld
+    d.weight = w_packed.data_ptr()
+    d.Cout, d.w_k = cout, w_packed.shape[1]
+    if taps is None:
+        taps = [(s - pad, r - pad, (r * kw + s) * cin) for r in range(kh) for s in range(kw)]
+    d.ntaps = len(taps)
+    for i, (dx, dy, wk) in enumerate(taps):
+        d.tap_dx[i], d.tap_dy[i], d.tap_wk[i] = dx, dy, wk
+    d.sx = d.sy = stride
+    d.HO, d.WO = ho, wo
+    if flat is None:
+        flat = (kh == 1 and kw == 1 and stride == 1 and pad == 0 and taps == [(0, 0, 0)] and out_map is None
+                and (add is None or tuple(add.shape[1:3]) == (ho, wo)))
+    d.flat = int(flat)
+    if out is None:
+        oh, ow = (ho, wo) if out_map is None else out_map[0]
+        alloc = torch.zeros if out_map is not None else torch.empty
+        out = alloc(n, oh, ow, cout, dtype=out_dtype, device=x.device)
+    assert out.stride(3) == 1
+    d.out = out.data_ptr()
+    d.OH, d.OW = out.shape[1], out.shape[2]
+    if out_map is not None:
+        (_, _), (d.oys, d.oyo, d.oxs, d.oxo) = out_map
+    d.out_ld = out.stride(2)
+    d.out_f32 = int(out.dtype == torch.float32)
+    keep = [x, w_packed, out]
+    for name, t in (('scale', scale), ('bias', bias)):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.numel() == cout and t.is_contiguous()
+            setattr(d, name, t.data_ptr())
+            keep.append(t)
+    if add is not None:
+        assert add.dtype == torch.bfloat16 and add.stride(3) == 1
+        d.add_src, d.add_H, d.add_W, d.add_ld = add.data_ptr(), add.shape[1], add.shape[2], add.stride(2)
+    if mask is not None:
+        assert mask.dtype == torch.bfloat16 and mask.shape[:3] == out.shape[:3]
+        d.mask_src, d.mask_ld = mask.data_ptr(), mask.stride(2)
+    d.relu, d.accumulate = int(relu), int(accumulate)
+    L.check(lib.ldb200_conv2d_tc(C.byref(d), L.stream_ptr()), 'ldb200_conv2d_tc')
+    return out

@@ -79,14 +79,51 @@ def bench_loss_targets(which):
             print(json.dumps(dict(kernel=f'ld_loss_fused grad={gd}', rows=R, n_sparse=int(cnt[0]), n_fg=int(cnt[1]),
                                   ms_median=med, ms_best=best, algorithmic_bytes=byts, gbs=byts / med / 1e6,
                                   frac_of_measured_hbm=byts / med / 1e6 / PEAK)))
+        for ph in (1, 2, 4):
+            os.environ['LDB200_LOSS_PHASES'] = str(ph)
+            med, best = timeit(lambda: ops.ld_loss_fused(cfg, cls, reg, t_cls, t_reg, x, t_x, tg, norm,
+                                                         term_grad=True, grad_dtype=torch.bfloat16, max_fg=int(cnt[1])))
+            print(json.dumps(dict(kernel=f'ld_loss_fused phase_mask={ph} (bf16 grads)', ms_median=med, ms_best=best)))
+        os.environ.pop('LDB200_LOSS_PHASES')
         med, best = timeit(lambda: ops.ld_loss_prepass(cfg, cls, reg, tg))
         print(json.dumps(dict(kernel='ld_loss_prepass', ms_median=med, ms_best=best)))
 
 
+def bench_conv():
+    dev = torch.device('cuda')
+    peak = 1680.9
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(__file__), '..', 'MEASURED_PEAKS.json')))['bf16_tflops']
+    except Exception:
+        pass
+    shapes = [('head P3 3x3 256->256', 16, 100, 168, 256, 256, 3, 1, 1),
+              ('head P4 3x3 256->256', 16, 50, 84, 256, 256, 3, 1, 1),
+              ('head P5 3x3 256->256', 16, 25, 42, 256, 256, 3, 1, 1),
+              ('l2 1x1 512->128', 16, 100, 168, 512, 128, 1, 1, 0),
+              ('l2 1x1 128->512', 16, 100, 168, 128, 512, 1, 1, 0),
+              ('l3 3x3 256->256', 16, 50, 84, 256, 256, 3, 1, 1),
+              ('l4 1x1 2048->512', 16, 25, 42, 2048, 512, 1, 1, 0),
+              ('l1 3x3 64->64', 16, 200, 336, 64, 64, 3, 1, 1)]
+    for name, n, h, w, ci, co, k, st, pad in shapes:
+        x = torch.randn(n, h, w, ci, device=dev).bfloat16()
+        wt = ops.pack_conv_weight(torch.randn(co, ci, k, k, device=dev) * 0.02)
+        out = torch.empty(n, h, w, co, device=dev, dtype=torch.bfloat16)
+        med, best = timeit(lambda: ops.conv2d_tc(x, wt, co, k, k, st, pad, out=out), iters=10, warm=3)
+        fl = 2.0 * n * h * w * ci * co * k * k
+        xt = x.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+        wtt = torch.randn(co, ci, k, k, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+        medc, bestc = timeit(lambda: torch.nn.functional.conv2d(xt, wtt, None, st, pad), iters=10, warm=3)
+        print(json.dumps(dict(kernel='conv2d_tc ' + name, ms_median=med, tflops=fl / med / 1e9,
+                              frac_of_measured_bf16=fl / med / 1e9 / peak, cudnn_bf16_ms=medc,
+                              cudnn_tflops=fl / medc / 1e9)))
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['kl', 'loss', 'targets']
+    which = sys.argv[1:] or ['kl', 'loss', 'targets', 'conv']
     L.check(L.load().ldb200_check_device(), 'check_device')
     if 'kl' in which:
         bench_kl()
     if 'loss' in which or 'targets' in which:
         bench_loss_targets(which)
+    if 'conv' in which:
+        bench_conv()
