@@ -189,6 +189,50 @@ typedef struct {
 
 int ldb200_conv2d_tc(const ldb_conv_desc* desc, void* stream);
 
+/* Weight gradient of the same convolution (autograd's conv backward-weight), split-K over pixel
+ * tiles with fp32 atomics:
+ *   dw[co, tap_wk[t] + ci] += sum_{n,y,x} dy[n,y,x,co] * x[n, y*sy + tap_dy[t], x*sx + tap_dx[t], ci]
+ * dy: [N,HO,WO,dy_ld] bf16, x: [N,H,W,x_ld] bf16, dw: [Cout, w_k] f32 (NOT zeroed by the call: gradients
+ * of the level-shared head convs accumulate across the five FPN levels). */
+typedef struct {
+  const void* dy; int N, HO, WO, Cout, dy_ld;
+  const void* x;  int H, W, Cin, x_ld;
+  int ntaps; int tap_dx[9], tap_dy[9], tap_wk[9];
+  int sx, sy;
+  float* dw; int w_k;
+} ldb_wgrad_desc;
+int ldb200_conv2d_wgrad_tc(const ldb_wgrad_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * HBM-bound glue around the convolutions (NHWC bf16 activations unless noted).
+ */
+/* 7x7/2 pad-3 stem conv as a GEMM operand: img [N,3,H,W] f32 (NCHW) -> out [N*HO*WO, 192] bf16 with
+ * column (r*7+s)*3+c, zero-padded from 147 (resnet.py:524-570, 626). */
+int ldb200_stem_im2col(const float* img, void* out, int N, int H, int W, void* stream);
+/* 3x3 stride-2 pad-1 max pool (resnet.py:630). */
+int ldb200_maxpool3x3s2(const void* in, void* out, int N, int H, int W, int C, void* stream);
+/* GroupNorm(G) [+ReLU] of mmcv ConvModule in the GFL towers (gfl_head.py:102-133, 177-180);
+ * x,y: [N, HW, C] bf16; stats: [N, G, 2] f32 (sum, sum of squares; zero-filled by gn_stats). */
+int ldb200_gn_stats(const void* x, float* stats, int N, int HW, int C, int G, void* stream);
+int ldb200_gn_apply(const void* x, const float* stats, const float* gamma, const float* beta, void* y,
+                    int N, int HW, int C, int G, float eps, int relu, void* stream);
+/* backward of y = relu(GN(x)): dx [N,HW,C] bf16, dgamma/dbeta [C] f32 ACCUMULATED (shared towers),
+ * red_ws: [N, G, 2] f32 scratch. */
+int ldb200_gn_relu_bwd(const void* dy, const void* y, const void* x, const float* stats, const float* gamma,
+                       float* red_ws, float* dgamma, float* dbeta, void* dx, int N, int HW, int C, int G,
+                       float eps, void* stream);
+/* backward of the FPN top-down `fine += nearest_upsample(coarse)` (fpn.py:182-191): dcoarse += gather-sum(dfine). */
+int ldb200_upsample_add_bwd(const void* dfine, void* dcoarse, int N, int Hf, int Wf, int Hc, int Wc, int C,
+                            void* stream);
+/* out = dy * (y > 0), bf16. */
+int ldb200_relu_bwd(const void* dy, const void* y, void* out, int64_t numel, void* stream);
+/* out[c] += sum_rows x[row, c]; x [rows, ld] (dtype LDB_BF16 / LDB_F32): conv-bias and BN-beta gradients. */
+int ldb200_colsum(const void* x, float* out, int64_t rows, int C, int ld, int dtype, void* stream);
+/* torch.optim.SGD (momentum, weight decay, dampening 0) on a flat fp32 parameter buffer;
+ * grad_scale folds the data-parallel mean.  configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py:53. */
+int ldb200_sgd_flat(float* w, const float* g, float* momentum_buf, int64_t n, float lr, float momentum,
+                    float weight_decay, float grad_scale, int first_step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,7 +48,8 @@ struct ConvParams {
   const __nv_bfloat16* mask_src; // optional: multiply by (mask_src > 0), same addressing as out (bf16, ld = mask_ld)
   int mask_ld;
   int relu;
-  int accumulate;           // out += result (read-modify-write in the output dtype)
+  int accumulate;           // result += previous out (before ReLU / mask)
+  int vec_ok;               // output rows 16-byte aligned -> vector stores
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -292,6 +293,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
+          if (p.accumulate) {
+            if (p.out_f32) {
+              const float* o = (const float*)p.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cbase + j < p.Cout) v[j] += o[j];
+            } else {
+              const __nv_bfloat16* o = (const __nv_bfloat16*)p.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cbase + j < p.Cout) v[j] += __bfloat162float(o[j]);
+            }
+          }
           if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -306,33 +320,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float* o = (float*)p.out + pix * (size_t)p.ldc + cbase;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              if (cbase + j + 4 <= p.Cout) {
-                float4 w4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (p.accumulate) {
-                  const float4 old = *reinterpret_cast<const float4*>(o + j);
-                  w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w;
-                }
-                *reinterpret_cast<float4*>(o + j) = w4;
+              if (p.vec_ok && cbase + j + 4 <= p.Cout) {
+                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
               } else {
                 for (int e = 0; e < 4; ++e)
-                  if (cbase + j + e < p.Cout) o[j + e] = v[j + e] + (p.accumulate ? o[j + e] : 0.f);
+                  if (cbase + j + e < p.Cout) o[j + e] = v[j + e];
               }
             }
           } else {
             __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * (size_t)p.ldc + cbase;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              if (cbase + j + 8 <= p.Cout) {
-                if (p.accumulate) {
-                  const uint4 q = *reinterpret_cast<const uint4*>(o + j);
-                  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = __bfloat1622float2(h[e]);
-                    v[j + 2 * e] += f.x;
-                    v[j + 2 * e + 1] += f.y;
-                  }
-                }
+              if (p.vec_ok && cbase + j + 8 <= p.Cout) {
                 uint4 q;
                 __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
 #pragma unroll
@@ -340,8 +339,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 *reinterpret_cast<uint4*>(o + j) = q;
               } else {
                 for (int e = 0; e < 8; ++e)
-                  if (cbase + j + e < p.Cout)
-                    o[j + e] = __float2bfloat16_rn(v[j + e] + (p.accumulate ? __bfloat162float(o[j + e]) : 0.f));
+                  if (cbase + j + e < p.Cout) o[j + e] = __float2bfloat16_rn(v[j + e]);
               }
             }
           }
@@ -350,6 +348,189 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbarrier_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
+  }
+}
+
+// =============================================================================================
+// Weight gradient: dW[co, tap, ci] += sum_{n,y,x} dY[n,y,x,co] * X[n, y*sy+dy_tap, x*sx+dx_tap, ci]
+// (autograd's conv backward-weight for every trainable conv of the student).  GEMM with the
+// reduction over pixels: both operands are "MN-major" straight out of NHWC memory -- the same 4-D TMA
+// boxes {64 ch, TW, TH, 1} as the forward pass land as [128 pixels][128 B] tiles, read by tcgen05 as
+// MN-major SWIZZLE_128B (rows = K = pixels; 8-pixel groups 1024 B apart = SBO; 64-channel chunks one
+// box = 16 KB apart = LBO).  One work unit = (128 output channels) x (BN input channels) x one tap x
+// one slice of the pixel tiles (split-K); the fp32 partial leaves TMEM through vector red.global.add.
+struct WgradParams {
+  int N, TH, TW, tiles_y, tiles_x;
+  int Cout, Cin, ntaps;
+  int tap_dx[9], tap_dy[9], tap_wk[9];
+  int sx, sy;
+  int co_tiles, ci_tiles, splits;
+  float* dw;
+  int w_k;
+};
+
+// MN-major SWIZZLE_128B descriptor: LBO = 16 KB between 64-element chunks, SBO = 1 KB between 8-row groups
+__device__ __forceinline__ uint64_t smem_desc_mn128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)(A_TILE_BYTES >> 4) << 16;   // LBO
+  d |= (uint64_t)(1024 >> 4) << 32;           // SBO
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN> struct WgradCfg {
+  static constexpr int A_BYTES = 2 * A_TILE_BYTES;             // 128 output channels
+  static constexpr int B_BYTES = (BN / 64) * A_TILE_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradParams p) {
+  using Cfg = WgradCfg<BN>;
+  extern __shared__ unsigned char conv_smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)conv_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tfull = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ptiles = p.N * p.tiles_y * p.tiles_x;
+  const int units = p.co_tiles * p.ci_tiles * p.ntaps * p.splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbarrier_init(&full[s], 1);
+      mbarrier_init(&empty[s], 1);
+    }
+    mbarrier_init(tfull, 1);
+    mbarrier_init(tempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)),
+                 "n"(Cfg::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int split = u % p.splits;
+        int rest = u / p.splits;
+        const int tap = rest % p.ntaps;
+        rest /= p.ntaps;
+        const int ci_t = rest % p.ci_tiles, co_t = rest / p.ci_tiles;
+        const int pt0 = (int)(((long long)ptiles * split) / p.splits);
+        const int pt1 = (int)(((long long)ptiles * (split + 1)) / p.splits);
+        for (int pt = pt0; pt < pt1; ++pt) {
+          const int tx = pt % p.tiles_x;
+          const int ty = (pt / p.tiles_x) % p.tiles_y;
+          const int n = pt / (p.tiles_x * p.tiles_y);
+          mbarrier_wait(&empty[stage], phase ^ 1);
+          unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+          mbarrier_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_4d(sa + j * A_TILE_BYTES, &tmA, &full[stage], co_t * TILE_M + 64 * j, tx * p.TW, ty * p.TH, n);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(sa + Cfg::A_BYTES + j * A_TILE_BYTES, &tmB, &full[stage], ci_t * BN + 64 * j,
+                        tx * p.TW * p.sx + p.tap_dx[tap], ty * p.TH * p.sy + p.tap_dy[tap], n);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        const int split = u % p.splits;
+        const int pt0 = (int)(((long long)ptiles * split) / p.splits);
+        const int pt1 = (int)(((long long)ptiles * (split + 1)) / p.splits);
+        mbarrier_wait(tempty, (it & 1) ^ 1);
+        tc_fence_after();
+        for (int pt = pt0; pt < pt1; ++pt) {
+          mbarrier_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = s2u(smem + (size_t)stage * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < TILE_M / 16; ++k) {
+            // 16 pixels = two 8-row groups = 2 KB further down the tile
+            umma_bf16(tmem_base, smem_desc_mn128(sa + k * 2048), smem_desc_mn128(sa + Cfg::A_BYTES + k * 2048),
+                      Cfg::IDESC, (pt > pt0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (pt == pt1 - 1) umma_commit(tfull);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (pt1 == pt0) umma_commit(tfull);   // empty slice: nothing accumulated (epilogue skips it)
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    int it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+      const int split = u % p.splits;
+      int rest = u / p.splits;
+      const int tap = rest % p.ntaps;
+      rest /= p.ntaps;
+      const int ci_t = rest % p.ci_tiles, co_t = rest / p.ci_tiles;
+      const int pt0 = (int)(((long long)ptiles * split) / p.splits);
+      const int pt1 = (int)(((long long)ptiles * (split + 1)) / p.splits);
+      const int co = co_t * TILE_M + ew * 32 + lane;
+      mbarrier_wait(tfull, it & 1);
+      tc_fence_after();
+      if (pt1 > pt0) {
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          const int cbase = ci_t * BN + ch * 32;
+          if (cbase >= p.Cin) break;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ch * 32), r);
+          if (co < p.Cout) {
+            float* o = p.dw + (size_t)co * p.w_k + p.tap_wk[tap] + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (cbase + j + 4 <= p.Cin) {
+                atomicAdd(reinterpret_cast<float4*>(o + j),
+                          make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                      __uint_as_float(r[j + 3])));
+              } else {
+                for (int e = 0; e < 4; ++e)
+                  if (cbase + j + e < p.Cin) atomicAdd(o + j + e, __uint_as_float(r[j + e]));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbarrier_arrive(tempty);
     }
   }
   tc_fence_before();
@@ -420,9 +601,10 @@ extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
   LDB_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, LDB_EINVAL, "conv2d_tc: ntaps");
   LDB_REQUIRE(d->N >= 1 && d->HO >= 1 && d->WO >= 1 && d->Cout >= 1, LDB_EINVAL, "conv2d_tc: shape");
   LDB_REQUIRE(d->sx >= 1 && d->sy >= 1 && d->sx <= 8 && d->sy <= 8, LDB_EINVAL, "conv2d_tc: stride");
-  LDB_REQUIRE(d->out_ld >= d->Cout && d->out_ld % (d->out_f32 ? 4 : 8) == 0, LDB_EINVAL, "conv2d_tc: out_ld alignment");
+  LDB_REQUIRE(d->out_ld >= d->Cout, LDB_EINVAL, "conv2d_tc: out_ld < Cout");
   LDB_REQUIRE(((uintptr_t)d->in & 15) == 0 && ((uintptr_t)d->weight & 15) == 0 && ((uintptr_t)d->out & 15) == 0,
               LDB_EINVAL, "conv2d_tc: pointers must be 16-byte aligned");
+  const int vec_ok = d->out_ld % (d->out_f32 ? 4 : 8) == 0;
   cudaStream_t stream = (cudaStream_t)stream_;
   ConvParams p;
   memset(&p, 0, sizeof(p));
@@ -439,7 +621,7 @@ extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
   p.add_H = d->add_H ? d->add_H : p.OH; p.add_W = d->add_W ? d->add_W : p.OW;
   p.add_ld = d->add_ld ? d->add_ld : d->Cout;
   p.mask_src = (const __nv_bfloat16*)d->mask_src; p.mask_ld = d->mask_ld ? d->mask_ld : d->out_ld;
-  p.relu = d->relu; p.accumulate = d->accumulate;
+  p.relu = d->relu; p.accumulate = d->accumulate; p.vec_ok = vec_ok;
   if (p.add_src) LDB_REQUIRE(((uintptr_t)p.add_src & 15) == 0 && p.add_ld % 8 == 0, LDB_EINVAL, "conv2d_tc: add_src alignment");
 
   // tile shape: flattened pixels for "flat" problems, else the TH x TW (TH*TW = 128) minimising padding waste
@@ -493,4 +675,86 @@ extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
   if (BN == 256) return launch_conv<256>(tmA, tmB, p, stream);
   if (BN == 128) return launch_conv<128>(tmA, tmB, p, stream);
   return launch_conv<64>(tmA, tmB, p, stream);
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p, cudaStream_t stream) {
+  using Cfg = WgradCfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    LDB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr = true;
+  }
+  const int units = p.co_tiles * p.ci_tiles * p.ntaps * p.splits;
+  const int grid = units < g_conv_sms ? units : g_conv_sms;
+  wgrad_tc_kernel<BN><<<grid, CONV_THREADS, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_conv2d_wgrad_tc(const ldb_wgrad_desc* d, void* stream_) {
+  LDB_REQUIRE(d && d->dy && d->x && d->dw, LDB_EINVAL, "wgrad_tc: null pointer");
+  LDB_REQUIRE(d->Cin > 0 && d->Cin % KCH == 0, LDB_ENOSUP, "wgrad_tc: Cin=%d must be a multiple of 64", d->Cin);
+  LDB_REQUIRE(d->Cout > 0 && d->Cout % 8 == 0, LDB_ENOSUP, "wgrad_tc: Cout=%d must be a multiple of 8", d->Cout);
+  LDB_REQUIRE(d->dy_ld >= d->Cout && d->dy_ld % 8 == 0 && d->x_ld >= d->Cin && d->x_ld % 8 == 0, LDB_EINVAL,
+              "wgrad_tc: leading dimensions");
+  LDB_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9 && d->sx >= 1 && d->sy >= 1, LDB_EINVAL, "wgrad_tc: taps/stride");
+  LDB_REQUIRE(d->w_k % 4 == 0 && ((uintptr_t)d->dw & 15) == 0, LDB_EINVAL, "wgrad_tc: dw alignment");
+  LDB_REQUIRE(((uintptr_t)d->dy & 15) == 0 && ((uintptr_t)d->x & 15) == 0, LDB_EINVAL, "wgrad_tc: pointer alignment");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!g_conv_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_conv_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N; p.Cout = d->Cout; p.Cin = d->Cin; p.ntaps = d->ntaps;
+  for (int t = 0; t < d->ntaps; ++t) {
+    p.tap_dx[t] = d->tap_dx[t]; p.tap_dy[t] = d->tap_dy[t]; p.tap_wk[t] = d->tap_wk[t];
+  }
+  p.sx = d->sx; p.sy = d->sy; p.dw = d->dw; p.w_k = d->w_k;
+  int best_th = 8, best_tiles = 1 << 30;
+  for (int th = 1; th <= TILE_M; th *= 2) {
+    const int tw = TILE_M / th;
+    if (tw * d->sx > 256 || th * d->sy > 256) continue;
+    const int tiles = ((d->HO + th - 1) / th) * ((d->WO + tw - 1) / tw);
+    if (tiles < best_tiles || (tiles == best_tiles && abs(th - 8) < abs(best_th - 8))) {
+      best_tiles = tiles;
+      best_th = th;
+    }
+  }
+  p.TH = best_th; p.TW = TILE_M / best_th;
+  p.tiles_y = (d->HO + p.TH - 1) / p.TH;
+  p.tiles_x = (d->WO + p.TW - 1) / p.TW;
+  const int BN = d->Cin > 128 ? 256 : (d->Cin > 64 ? 128 : 64);
+  p.co_tiles = (d->Cout + TILE_M - 1) / TILE_M;
+  p.ci_tiles = (d->Cin + BN - 1) / BN;
+  const int ptiles = p.N * p.tiles_y * p.tiles_x;
+  const int base_units = p.co_tiles * p.ci_tiles * p.ntaps;
+  int splits = (2 * g_conv_sms + base_units - 1) / base_units;
+  if (splits > ptiles) splits = ptiles;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->WO, (cuuint64_t)d->HO, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->dy_ld * 2, (cuuint64_t)d->dy_ld * 2 * d->WO,
+                             (cuuint64_t)d->dy_ld * 2 * d->WO * d->HO};
+    cuuint32_t box[4] = {KCH, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1}, es[4] = {1, 1, 1, 1};
+    int e = encode_map(&tmA, d->dy, 4, dims, strides, box, es, "wgrad dY");
+    if (e) return e;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->x_ld * 2, (cuuint64_t)d->x_ld * 2 * d->W,
+                             (cuuint64_t)d->x_ld * 2 * d->W * d->H};
+    cuuint32_t box[4] = {KCH, (cuuint32_t)(p.TW * d->sx), (cuuint32_t)(p.TH * d->sy), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)d->sx, (cuuint32_t)d->sy, 1};
+    int e = encode_map(&tmB, d->x, 4, dims, strides, box, es, "wgrad X");
+    if (e) return e;
+  }
+  if (BN == 256) return launch_wgrad<256>(tmA, tmB, p, stream);
+  if (BN == 128) return launch_wgrad<128>(tmA, tmB, p, stream);
+  return launch_wgrad<64>(tmA, tmB, p, stream);
 }

@@ -1,0 +1,481 @@
+// HBM-bound glue kernels around the tensor-core convolutions (NHWC bf16 activations):
+// stem im2col, max-pool, GroupNorm(+ReLU) forward/backward, nearest-upsample-add backward,
+// ReLU-mask, per-channel column sums (bias / BN-beta gradients) and the flat SGD update.
+//
+// Replaces (reference, under /root/reference/mmdet): backbones/resnet.py:626-630 (stem BN/ReLU/
+// maxpool after the 7x7 conv), dense_heads/gfl_head.py:177-180 via mmcv ConvModule (GroupNorm(32) +
+// ReLU, torch native_group_norm / native_group_norm_backward), necks/fpn.py:182-191 backward,
+// torch.optim.SGD (configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py:53).
+#include "common.cuh"
+
+namespace ldb {
+
+__device__ __forceinline__ void unpack8(const uint4& q, float v[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __bfloat1622float2(h[e]);
+    v[2 * e] = f.x;
+    v[2 * e + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float v[8]) {
+  uint4 q;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+  return q;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stem: 7x7 stride-2 pad-3 conv on a 3-channel NCHW fp32 image as a GEMM: A[pixel, (r*7+s)*3+c],
+// K = 147 zero-padded to 192 (3 x 64) so the tcgen05 kernel can consume it in flat mode.
+__global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int H,
+                                   int W, int HO, int WO) {
+  const long long total = (long long)N * HO * WO * 24;  // 24 groups of 8 columns = 192
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int grp = (int)(t % 24);
+    const long long pix = t / 24;
+    const int xo = (int)(pix % WO);
+    const int yo = (int)((pix / WO) % HO);
+    const int n = (int)(pix / ((long long)WO * HO));
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = grp * 8 + e;
+      float val = 0.f;
+      if (k < 147) {
+        const int c = k % 3, rs = k / 3, s = rs % 7, r = rs / 7;
+        const int y = yo * 2 - 3 + r, x = xo * 2 - 3 + s;
+        if (y >= 0 && y < H && x >= 0 && x < W) val = __ldg(img + (((size_t)n * 3 + c) * H + y) * W + x);
+      }
+      v[e] = val;
+    }
+    reinterpret_cast<uint4*>(out)[t] = pack8(v);
+  }
+}
+
+// 3x3 stride-2 pad-1 max pool, NHWC bf16, 8 channels per thread.
+__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int N,
+                                    int H, int W, int C, int HO, int WO) {
+  const int cg = C / 8;
+  const long long total = (long long)N * HO * WO * cg;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % cg);
+    const long long pix = t / cg;
+    const int xo = (int)(pix % WO), yo = (int)((pix / WO) % HO), n = (int)(pix / ((long long)WO * HO));
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+    for (int r = 0; r < 3; ++r) {
+      const int y = yo * 2 - 1 + r;
+      if (y < 0 || y >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int x = xo * 2 - 1 + s;
+        if (x < 0 || x >= W) continue;
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(in + (((size_t)n * H + y) * W + x) * C) + g), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+      }
+    }
+    reinterpret_cast<uint4*>(out)[t] = pack8(m);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm with 8 channels per group (256 ch / 32 groups): one thread owns one (pixel, group)
+// uint4.  x: [N, HW, C] bf16.  stats: [N, G, 2] fp32 (sum, sum of squares), accumulated.
+constexpr int GN_CPG = 8;
+constexpr int GN_PIX_PER_BLOCK = 64;
+
+__global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats,
+                                                        int HW, int C) {
+  const int G = C / GN_CPG;          // threads along x cover the groups
+  const int n = blockIdx.y;
+  const int gpt = threadIdx.x % G;   // group of this thread
+  const int rows_par = blockDim.x / G;
+  const int r0 = threadIdx.x / G;
+  float s = 0.f, ss = 0.f;
+  const int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
+  const int p1 = min(p0 + GN_PIX_PER_BLOCK, HW);
+  for (int p = p0 + r0; p < p1; p += rows_par) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((size_t)n * HW + p) * C) + gpt), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s += v[e];
+      ss += v[e] * v[e];
+    }
+  }
+  // combine the rows_par partials of each group through shared memory
+  __shared__ float sh[2][256];
+  sh[0][threadIdx.x] = s;
+  sh[1][threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.x < G) {
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < rows_par; ++r) {
+      a += sh[0][r * G + threadIdx.x];
+      b += sh[1][r * G + threadIdx.x];
+    }
+    atomicAdd(stats + ((size_t)n * G + threadIdx.x) * 2, a);
+    atomicAdd(stats + ((size_t)n * G + threadIdx.x) * 2 + 1, b);
+  }
+}
+
+// y = relu((x - mean) * rstd * gamma + beta)   (relu optional)
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int N, int HW, int C, float eps, int relu) {
+  const int G = C / GN_CPG;
+  const long long total = (long long)N * HW * G;
+  const float inv_m = 1.f / ((float)HW * GN_CPG);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    const int n = (int)(t / ((long long)HW * G));
+    const float s = __ldg(stats + ((size_t)n * G + g) * 2), ss = __ldg(stats + ((size_t)n * G + g) * 2 + 1);
+    const float mean = s * inv_m;
+    const float var = fmaxf(ss * inv_m - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + t), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = g * GN_CPG + e;
+      float o = (v[e] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      v[e] = relu ? fmaxf(o, 0.f) : o;
+    }
+    reinterpret_cast<uint4*>(y)[t] = pack8(v);
+  }
+}
+
+// GroupNorm+ReLU backward, pass 1: per-(n,group) sums of dxh and dxh*xh, per-channel dgamma/dbeta.
+//   g = dy * (y > 0), xh = (x - mean)*rstd, dxh = g*gamma
+// red: [N, G, 2] fp32 accumulated; dgamma/dbeta: [C] fp32 accumulated.
+__global__ void __launch_bounds__(256)
+gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                    const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
+                    const float* __restrict__ gamma, float* __restrict__ red, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, int HW, int C, float eps) {
+  const int G = C / GN_CPG;
+  const int n = blockIdx.y;
+  const int gpt = threadIdx.x % G;
+  const int rows_par = blockDim.x / G;
+  const int r0 = threadIdx.x / G;
+  const float inv_m = 1.f / ((float)HW * GN_CPG);
+  const float s = __ldg(stats + ((size_t)n * G + gpt) * 2), ss = __ldg(stats + ((size_t)n * G + gpt) * 2 + 1);
+  const float mean = s * inv_m;
+  const float rstd = rsqrtf(fmaxf(ss * inv_m - mean * mean, 0.f) + eps);
+  float gam[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) gam[e] = __ldg(gamma + gpt * GN_CPG + e);
+  float a = 0.f, b = 0.f, dg[8], db[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) dg[e] = db[e] = 0.f;
+  const int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
+  const int p1 = min(p0 + GN_PIX_PER_BLOCK, HW);
+  for (int p = p0 + r0; p < p1; p += rows_par) {
+    const size_t o = ((size_t)n * HW + p) * C;
+    float vd[8], vy[8], vx[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + o) + gpt), vd);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(y + o) + gpt), vy);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + o) + gpt), vx);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float gg = vy[e] > 0.f ? vd[e] : 0.f;
+      const float xh = (vx[e] - mean) * rstd;
+      const float dxh = gg * gam[e];
+      a += dxh;
+      b += dxh * xh;
+      dg[e] += gg * xh;
+      db[e] += gg;
+    }
+  }
+  __shared__ float sh[2][256];
+  sh[0][threadIdx.x] = a;
+  sh[1][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.x < G) {
+    float ta = 0.f, tb = 0.f;
+    for (int r = 0; r < rows_par; ++r) {
+      ta += sh[0][r * G + threadIdx.x];
+      tb += sh[1][r * G + threadIdx.x];
+    }
+    atomicAdd(red + ((size_t)n * G + threadIdx.x) * 2, ta);
+    atomicAdd(red + ((size_t)n * G + threadIdx.x) * 2 + 1, tb);
+  }
+  // per-channel partials: reduce across the rows_par threads of the same group via smem, 8 rounds
+  for (int e = 0; e < 8; ++e) {
+    __syncthreads();
+    sh[0][threadIdx.x] = dg[e];
+    sh[1][threadIdx.x] = db[e];
+    __syncthreads();
+    if (threadIdx.x < G) {
+      float ta = 0.f, tb = 0.f;
+      for (int r = 0; r < rows_par; ++r) {
+        ta += sh[0][r * G + threadIdx.x];
+        tb += sh[1][r * G + threadIdx.x];
+      }
+      atomicAdd(dgamma + threadIdx.x * GN_CPG + e, ta);
+      atomicAdd(dbeta + threadIdx.x * GN_CPG + e, tb);
+    }
+  }
+}
+
+// pass 2: dx = rstd * (dxh - mean(dxh) - xh * mean(dxh*xh))
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                    const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
+                    const float* __restrict__ gamma, const float* __restrict__ red, __nv_bfloat16* __restrict__ dx,
+                    int N, int HW, int C, float eps) {
+  const int G = C / GN_CPG;
+  const long long total = (long long)N * HW * G;
+  const float inv_m = 1.f / ((float)HW * GN_CPG);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    const int n = (int)(t / ((long long)HW * G));
+    const float s = __ldg(stats + ((size_t)n * G + g) * 2), ss = __ldg(stats + ((size_t)n * G + g) * 2 + 1);
+    const float mean = s * inv_m;
+    const float rstd = rsqrtf(fmaxf(ss * inv_m - mean * mean, 0.f) + eps);
+    const float m1 = __ldg(red + ((size_t)n * G + g) * 2) * inv_m, m2 = __ldg(red + ((size_t)n * G + g) * 2 + 1) * inv_m;
+    float vd[8], vy[8], vx[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + t), vd);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(y) + t), vy);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + t), vx);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float gg = vy[e] > 0.f ? vd[e] : 0.f;
+      const float xh = (vx[e] - mean) * rstd;
+      const float dxh = gg * __ldg(gamma + g * GN_CPG + e);
+      vd[e] = rstd * (dxh - m1 - xh * m2);
+    }
+    reinterpret_cast<uint4*>(dx)[t] = pack8(vd);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward of `fine += nearest_upsample(coarse)` (fpn.py:182-191): coarse_grad[n,yc,xc,:] +=
+// sum of fine_grad over the fine pixels that read it (src index = floor(dst * Hc / Hf)).
+__global__ void upsample_add_bwd_kernel(const __nv_bfloat16* __restrict__ dfine, __nv_bfloat16* __restrict__ dcoarse,
+                                        int N, int Hf, int Wf, int Hc, int Wc, int C) {
+  const int cg = C / 8;
+  const long long total = (long long)N * Hc * Wc * cg;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % cg);
+    const long long pix = t / cg;
+    const int xc = (int)(pix % Wc), yc = (int)((pix / Wc) % Hc), n = (int)(pix / ((long long)Wc * Hc));
+    // fine rows y with floor(y*Hc/Hf) == yc  <=>  y in [ceil(yc*Hf/Hc), ceil((yc+1)*Hf/Hc))
+    const int y0 = (yc * Hf + Hc - 1) / Hc, y1 = min(((yc + 1) * Hf + Hc - 1) / Hc, Hf);
+    const int x0 = (xc * Wf + Wc - 1) / Wc, x1 = min(((xc + 1) * Wf + Wc - 1) / Wc, Wf);
+    float acc[8];
+    unpack8(reinterpret_cast<const uint4*>(dcoarse)[t], acc);
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dfine + (((size_t)n * Hf + y) * Wf + x) * C) + g), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+      }
+    reinterpret_cast<uint4*>(dcoarse)[t] = pack8(acc);
+  }
+}
+
+// out = dy * (y > 0), bf16, 8 elements per thread
+__global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                __nv_bfloat16* __restrict__ out, long long n8) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n8;
+       t += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + t), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(y) + t), b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = b[e] > 0.f ? a[e] : 0.f;
+    reinterpret_cast<uint4*>(out)[t] = pack8(a);
+  }
+}
+
+// out[c] += sum_rows x[row, c]   (x: [M, ld] bf16 or f32, C channels, C % 8 == 0 for bf16)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long M,
+                                                      int C, int ld) {
+  // each block handles a band of rows; thread layout: tx over channel groups, ty over rows
+  const int cg = (sizeof(T) == 2) ? C / 8 : C / 4;
+  const int VW = (sizeof(T) == 2) ? 8 : 4;
+  const int rows_par = 256 / min(cg, 256);
+  const int tx = threadIdx.x % min(cg, 256), ty = threadIdx.x / min(cg, 256);
+  const long long band = (M + gridDim.x - 1) / gridDim.x;
+  const long long m0 = (long long)blockIdx.x * band, m1 = (m0 + band < M) ? m0 + band : M;
+  __shared__ float sh[256];
+  for (int g = tx; g < cg; g += min(cg, 256)) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    if (ty < rows_par) {
+      for (long long m = m0 + ty; m < m1; m += rows_par) {
+        if (sizeof(T) == 2) {
+          float v[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>((const __nv_bfloat16*)x + (size_t)m * ld) + g), v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += v[e];
+        } else {
+          const float4 v = __ldg(reinterpret_cast<const float4*>((const float*)x + (size_t)m * ld) + g);
+          acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+        }
+      }
+    }
+    for (int e = 0; e < VW; ++e) {
+      __syncthreads();
+      sh[threadIdx.x] = acc[e];
+      __syncthreads();
+      if (ty == 0) {
+        float t = 0.f;
+        for (int r = 0; r < rows_par; ++r) t += sh[r * min(cg, 256) + tx];
+        atomicAdd(out + g * VW + e, t);
+      }
+    }
+  }
+}
+
+// SGD with momentum and weight decay on a flat fp32 buffer (torch.optim.SGD semantics, dampening 0):
+//   g += wd*w ; buf = first ? g : mom*buf + g ; w -= lr*buf
+// grad_scale folds the data-parallel mean (1/world) into the update.
+__global__ void sgd_flat_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ buf,
+                                long long n, float lr, float mom, float wd, float grad_scale, int first) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale + wd * w[i];
+    float b = first ? gi : mom * buf[i] + gi;
+    buf[i] = b;
+    w[i] -= lr * b;
+  }
+}
+
+static int grid_for(long long total, int threads = 256, int cap = 148 * 16) {
+  long long b = (total + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace ldb
+
+using namespace ldb;
+
+extern "C" int ldb200_stem_im2col(const float* img, void* out, int N, int H, int W, void* stream_) {
+  LDB_REQUIRE(img && out && N > 0 && H > 0 && W > 0, LDB_EINVAL, "stem_im2col: bad argument");
+  const int HO = (H + 6 - 7) / 2 + 1, WO = (W + 6 - 7) / 2 + 1;
+  const long long total = (long long)N * HO * WO * 24;
+  stem_im2col_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream_>>>(img, (__nv_bfloat16*)out, N, H, W, HO, WO);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_maxpool3x3s2(const void* in, void* out, int N, int H, int W, int C, void* stream_) {
+  LDB_REQUIRE(in && out && C % 8 == 0, LDB_EINVAL, "maxpool: bad argument (C %% 8)");
+  const int HO = (H + 2 - 3) / 2 + 1, WO = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * HO * WO * (C / 8);
+  maxpool3x3s2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out,
+                                                                          N, H, W, C, HO, WO);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int gn_check(int C, int G) {
+  LDB_REQUIRE(G > 0 && C == G * GN_CPG && G <= 256 && 256 % G == 0, LDB_ENOSUP,
+              "group norm kernels support 8 channels per group and a group count dividing 256 (C=%d, G=%d)", C, G);
+  return 0;
+}
+
+extern "C" int ldb200_gn_stats(const void* x, float* stats, int N, int HW, int C, int G, void* stream_) {
+  int e = gn_check(C, G);
+  if (e) return e;
+  LDB_REQUIRE(x && stats, LDB_EINVAL, "gn_stats: null pointer");
+  cudaStream_t s = (cudaStream_t)stream_;
+  LDB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * N * G, s));
+  dim3 grid((HW + GN_PIX_PER_BLOCK - 1) / GN_PIX_PER_BLOCK, N);
+  gn_stats_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, stats, HW, C);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_gn_apply(const void* x, const float* stats, const float* gamma, const float* beta, void* y,
+                               int N, int HW, int C, int G, float eps, int relu, void* stream_) {
+  int e = gn_check(C, G);
+  if (e) return e;
+  LDB_REQUIRE(x && stats && gamma && beta && y, LDB_EINVAL, "gn_apply: null pointer");
+  const long long total = (long long)N * HW * G;
+  gn_apply_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, stats, gamma, beta,
+                                                                      (__nv_bfloat16*)y, N, HW, C, eps, relu);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_gn_relu_bwd(const void* dy, const void* y, const void* x, const float* stats, const float* gamma,
+                                  float* red_ws, float* dgamma, float* dbeta, void* dx, int N, int HW, int C, int G,
+                                  float eps, void* stream_) {
+  int e = gn_check(C, G);
+  if (e) return e;
+  LDB_REQUIRE(dy && y && x && stats && gamma && red_ws && dgamma && dbeta && dx, LDB_EINVAL, "gn_relu_bwd: null pointer");
+  cudaStream_t s = (cudaStream_t)stream_;
+  LDB_CUDA(cudaMemsetAsync(red_ws, 0, sizeof(float) * 2 * N * G, s));
+  dim3 grid((HW + GN_PIX_PER_BLOCK - 1) / GN_PIX_PER_BLOCK, N);
+  gn_bwd_stats_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)x,
+                                           stats, gamma, red_ws, dgamma, dbeta, HW, C, eps);
+  LDB_CUDA(cudaGetLastError());
+  const long long total = (long long)N * HW * G;
+  gn_bwd_apply_kernel<<<grid_for(total), 256, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
+                                                      (const __nv_bfloat16*)x, stats, gamma, red_ws, (__nv_bfloat16*)dx,
+                                                      N, HW, C, eps);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_upsample_add_bwd(const void* dfine, void* dcoarse, int N, int Hf, int Wf, int Hc, int Wc, int C,
+                                       void* stream_) {
+  LDB_REQUIRE(dfine && dcoarse && C % 8 == 0 && Hc <= Hf && Wc <= Wf, LDB_EINVAL, "upsample_add_bwd: bad argument");
+  const long long total = (long long)N * Hc * Wc * (C / 8);
+  upsample_add_bwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)dfine,
+                                                                              (__nv_bfloat16*)dcoarse, N, Hf, Wf, Hc, Wc, C);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_relu_bwd(const void* dy, const void* y, void* out, int64_t numel, void* stream_) {
+  LDB_REQUIRE(dy && y && out && numel % 8 == 0, LDB_EINVAL, "relu_bwd: bad argument (numel %% 8)");
+  relu_bwd_kernel<<<grid_for(numel / 8), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)dy,
+                                                                          (const __nv_bfloat16*)y, (__nv_bfloat16*)out,
+                                                                          numel / 8);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_colsum(const void* x, float* out, int64_t rows, int C, int ld, int dtype, void* stream_) {
+  LDB_REQUIRE(x && out && rows >= 0 && C > 0 && ld >= C, LDB_EINVAL, "colsum: bad argument");
+  if (rows == 0) return 0;
+  int grid = (int)((rows + 511) / 512);
+  if (grid > 148 * 4) grid = 148 * 4;
+  if (dtype == LDB_BF16) {
+    LDB_REQUIRE(C % 8 == 0 && ld % 8 == 0, LDB_EINVAL, "colsum: bf16 needs C, ld %% 8 == 0");
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, out, rows, C, ld);
+  } else {
+    LDB_REQUIRE(C % 4 == 0 && ld % 4 == 0, LDB_EINVAL, "colsum: f32 needs C, ld %% 4 == 0");
+    colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream_>>>((const float*)x, out, rows, C, ld);
+  }
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_sgd_flat(float* w, const float* g, float* buf, int64_t n, float lr, float momentum,
+                               float weight_decay, float grad_scale, int first_step, void* stream_) {
+  LDB_REQUIRE(w && g && buf && n >= 0, LDB_EINVAL, "sgd_flat: bad argument");
+  if (n == 0) return 0;
+  sgd_flat_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(w, g, buf, n, lr, momentum, weight_decay, grad_scale,
+                                                                  first_step);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -60,6 +60,13 @@ class ConvDesc(C.Structure):
                 ('relu', C.c_int), ('accumulate', C.c_int)]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [('dy', C.c_void_p), ('N', C.c_int), ('HO', C.c_int), ('WO', C.c_int), ('Cout', C.c_int),
+                ('dy_ld', C.c_int), ('x', C.c_void_p), ('H', C.c_int), ('W', C.c_int), ('Cin', C.c_int),
+                ('x_ld', C.c_int), ('ntaps', C.c_int), ('tap_dx', C.c_int * 9), ('tap_dy', C.c_int * 9),
+                ('tap_wk', C.c_int * 9), ('sx', C.c_int), ('sy', C.c_int), ('dw', C.c_void_p), ('w_k', C.c_int)]
+
+
 _SIGS = {
     'ldb200_last_error': (C.c_char_p, []),
     'ldb200_version': (C.c_int, []),
@@ -73,6 +80,16 @@ _SIGS = {
                              [C.c_int, C.c_void_p]),
     'ldb200_scatter_add_rows': (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ldb200_conv2d_tc': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    'ldb200_conv2d_wgrad_tc': (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
+    'ldb200_stem_im2col': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ldb200_maxpool3x3s2': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    'ldb200_gn_stats': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    'ldb200_gn_apply': (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_float, C.c_int, C.c_void_p]),
+    'ldb200_gn_relu_bwd': (C.c_int, [C.c_void_p] * 9 + [C.c_int] * 4 + [C.c_float, C.c_void_p]),
+    'ldb200_upsample_add_bwd': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    'ldb200_relu_bwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]),
+    'ldb200_colsum': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ldb200_sgd_flat': (C.c_int, [C.c_void_p] * 3 + [C.c_int64] + [C.c_float] * 4 + [C.c_int, C.c_void_p]),
     'ldb200_kl_dense_fwd_bwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int, C.c_float, C.c_float,
                                           C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

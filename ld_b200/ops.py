@@ -251,3 +251,95 @@ def conv2d_tc(x, w_packed, cout, kh=1, kw=1, stride=1, pad=0, out=None, out_dtyp
     d.relu, d.accumulate = int(relu), int(accumulate)
     L.check(lib.ldb200_conv2d_tc(C.byref(d), L.stream_ptr()), 'ldb200_conv2d_tc')
     return out
+
+
+# ------------------------------------------------------------------------------------ glue kernels
+def stem_im2col(img):
+    """img [N,3,H,W] f32 NCHW -> ([N*HO*WO, 192] bf16, HO, WO)."""
+    n, c, h, w = img.shape
+    assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    out = torch.empty(n * ho * wo, 192, dtype=torch.bfloat16, device=img.device)
+    L.check(L.load().ldb200_stem_im2col(L.ptr(img), L.ptr(out), n, h, w, L.stream_ptr()), 'ldb200_stem_im2col')
+    return out, ho, wo
+
+
+def maxpool3x3s2(x):
+    n, h, w, c = x.shape
+    out = torch.empty(n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c, dtype=x.dtype, device=x.device)
+    L.check(L.load().ldb200_maxpool3x3s2(L.ptr(x), L.ptr(out), n, h, w, c, L.stream_ptr()), 'ldb200_maxpool3x3s2')
+    return out
+
+
+def gn_relu_fwd(x, gamma, beta, groups=32, eps=1e-5, relu=True):
+    """x [N,H,W,C] bf16 -> (y, stats[N,G,2])."""
+    n, h, w, c = x.shape
+    lib = L.load()
+    stats = torch.empty(n, groups, 2, dtype=torch.float32, device=x.device)
+    y = torch.empty_like(x)
+    L.check(lib.ldb200_gn_stats(L.ptr(x), L.ptr(stats), n, h * w, c, groups, L.stream_ptr()), 'ldb200_gn_stats')
+    L.check(lib.ldb200_gn_apply(L.ptr(x), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(y), n, h * w, c, groups,
+                                float(eps), int(relu), L.stream_ptr()), 'ldb200_gn_apply')
+    return y, stats
+
+
+def gn_relu_bwd(dy, y, x, stats, gamma, dgamma, dbeta, groups=32, eps=1e-5):
+    """-> dx [N,H,W,C] bf16; dgamma/dbeta [C] f32 accumulated in place."""
+    n, h, w, c = x.shape
+    ws = torch.empty(n, groups, 2, dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x)
+    L.check(L.load().ldb200_gn_relu_bwd(L.ptr(dy), L.ptr(y), L.ptr(x), L.ptr(stats), L.ptr(gamma), L.ptr(ws),
+                                        L.ptr(dgamma), L.ptr(dbeta), L.ptr(dx), n, h * w, c, groups, float(eps),
+                                        L.stream_ptr()), 'ldb200_gn_relu_bwd')
+    return dx
+
+
+def upsample_add_bwd(dfine, dcoarse):
+    n, hf, wf, c = dfine.shape
+    _, hc, wc, _ = dcoarse.shape
+    L.check(L.load().ldb200_upsample_add_bwd(L.ptr(dfine), L.ptr(dcoarse), n, hf, wf, hc, wc, c, L.stream_ptr()),
+            'ldb200_upsample_add_bwd')
+    return dcoarse
+
+
+def relu_bwd(dy, y, out=None):
+    out = torch.empty_like(dy) if out is None else out
+    L.check(L.load().ldb200_relu_bwd(L.ptr(dy), L.ptr(y), L.ptr(out), dy.numel(), L.stream_ptr()), 'ldb200_relu_bwd')
+    return out
+
+
+def colsum(x2d, out):
+    """out[c] += sum over rows of x2d [M, C] (bf16 or f32, row stride = x2d.stride(0))."""
+    assert x2d.dim() == 2 and x2d.stride(1) == 1 and out.dtype == torch.float32
+    L.check(L.load().ldb200_colsum(C.c_void_p(x2d.data_ptr()), L.ptr(out), x2d.shape[0], x2d.shape[1], x2d.stride(0),
+                                   _dt(x2d.dtype), L.stream_ptr()), 'ldb200_colsum')
+    return out
+
+
+def sgd_flat(w, g, buf, lr, momentum=0.9, weight_decay=1e-4, grad_scale=1.0, first_step=False):
+    L.check(L.load().ldb200_sgd_flat(L.ptr(w), L.ptr(g), L.ptr(buf), w.numel(), float(lr), float(momentum),
+                                     float(weight_decay), float(grad_scale), int(first_step), L.stream_ptr()),
+            'ldb200_sgd_flat')
+
+
+def conv2d_wgrad_tc(dy, x, dw, kh=1, kw=1, stride=1, pad=0):
+    """dw [Cout, kh*kw*Cin] f32 (packed tap-major layout) += wgrad(dy [N,HO,WO,Cout], x [N,H,W,Cin]) (bf16 NHWC)."""
+    assert dy.dtype == x.dtype == torch.bfloat16 and dw.dtype == torch.float32 and dw.is_contiguous()
+    n, ho, wo, cout = dy.shape
+    _, h, w_, cin = x.shape
+    d = L.WgradDesc()
+    d.dy, d.N, d.HO, d.WO, d.Cout, d.dy_ld = dy.data_ptr(), n, ho, wo, cout, dy.stride(2)
+    d.x, d.H, d.W, d.Cin, d.x_ld = x.data_ptr(), h, w_, cin, x.stride(2)
+    taps = [(s - pad, r - pad, (r * kw + s) * cin) for r in range(kh) for s in range(kw)]
+    d.ntaps = len(taps)
+    for i, (dx, dy_, wk) in enumerate(taps):
+        d.tap_dx[i], d.tap_dy[i], d.tap_wk[i] = dx, dy_, wk
+    d.sx = d.sy = stride
+    d.dw, d.w_k = dw.data_ptr(), dw.shape[1]
+    L.check(L.load().ldb200_conv2d_wgrad_tc(C.byref(d), L.stream_ptr()), 'ldb200_conv2d_wgrad_tc')
+    return dw
+
+
+def unpack_conv_weight_grad(dw_packed, cout, cin, kh, kw):
+    """[Cout, kh*kw*Cin] -> [Cout, Cin, kh, kw] (PyTorch OIHW view of the packed gradient)."""
+    return dw_packed.view(cout, kh, kw, cin).permute(0, 3, 1, 2)

@@ -104,3 +104,98 @@ def test_conv_dgrad_matches_autograd():
         dx = ops.conv2d_tc(dy, wd, cin, k, k, 1, pad, out_dtype=torch.float32, taps=taps, flat=False if k == 3 else None)
         torch.cuda.synchronize()
         check(dx, want, 1e-4)
+
+
+WG_CASES = [
+    # n, h, w, cin, cout, k, stride, pad
+    (2, 16, 24, 64, 64, 3, 1, 1),
+    (2, 25, 42, 256, 256, 3, 1, 1),
+    (2, 13, 21, 256, 80, 3, 1, 1),      # gfl_cls: Cout < 128 (second 64-channel box partly out of range)
+    (1, 20, 28, 128, 512, 1, 1, 0),
+    (2, 33, 47, 128, 128, 3, 2, 1),
+    (2, 32, 48, 256, 512, 1, 2, 0),
+    (1, 50, 84, 512, 128, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize('case', WG_CASES, ids=lambda c: 'x'.join(map(str, c)))
+def test_conv_wgrad(case):
+    from ld_b200 import ops
+    n, h, w, cin, cout, k, stride, pad = case
+    g = torch.Generator(device='cuda').manual_seed(sum(case) + 1)
+    x = torch.randn(n, h, w, cin, device='cuda', generator=g).bfloat16()
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    dy = torch.randn(n, ho, wo, cout, device='cuda', generator=g).bfloat16()
+    wt = torch.zeros(cout, cin, k, k, device='cuda', requires_grad=True)
+    F.conv2d(x.float().permute(0, 3, 1, 2), wt, None, stride, pad).backward(dy.float().permute(0, 3, 1, 2))
+    dw = torch.zeros(cout, k * k * cin, device='cuda')
+    ops.conv2d_wgrad_tc(dy, x, dw, k, k, stride, pad)
+    ops.conv2d_wgrad_tc(dy, x, dw, k, k, stride, pad)      # accumulates
+    torch.cuda.synchronize()
+    got = ops.unpack_conv_weight_grad(dw, cout, cin, k, k)
+    check(got, 2 * wt.grad, 1e-4)
+
+
+def test_glue_kernels():
+    from ld_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(5)
+    # stem im2col + flat GEMM == 7x7/2 conv
+    img = torch.randn(2, 3, 70, 94, device='cuda', generator=g)
+    wt = torch.randn(64, 3, 7, 7, device='cuda', generator=g) * 0.1
+    a, ho, wo = ops.stem_im2col(img)
+    wp = torch.zeros(64, 192, device='cuda', dtype=torch.bfloat16)
+    wp[:, :147] = wt.permute(0, 2, 3, 1).reshape(64, 147).bfloat16()
+    y = ops.conv2d_tc(a.view(1, 1, -1, 192), wp, 64, out_dtype=torch.float32, relu=True).view(2, ho, wo, 64)
+    want = F.conv2d(img.bfloat16().float(), wt.bfloat16().float(), None, 2, 3).relu().permute(0, 2, 3, 1)
+    check(y, want, 1e-4)
+    # max pool
+    yb = y.bfloat16()
+    mp = ops.maxpool3x3s2(yb)
+    want = F.max_pool2d(yb.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(mp.float(), want)
+    # group norm + relu forward / backward vs torch
+    x = (torch.randn(2, 13, 21, 256, device='cuda', generator=g) * 2 + 0.5).bfloat16()
+    gamma = torch.rand(256, device='cuda', generator=g) + 0.5
+    beta = torch.randn(256, device='cuda', generator=g) * 0.2
+    yq, stats = ops.gn_relu_fwd(x, gamma, beta)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.relu(F.group_norm(xr, 32, gr, br, 1e-5))
+    check(yq, yr.detach().permute(0, 2, 3, 1), 6e-3)
+    dy = torch.randn(2, 13, 21, 256, device='cuda', generator=g).bfloat16()
+    yr.backward(dy.float().permute(0, 3, 1, 2) * (yq.float().permute(0, 3, 1, 2) > 0) / (yr.detach() > 0).float().clamp(min=1e-9) * (yr.detach() > 0))
+    dgam = torch.zeros(256, device='cuda')
+    dbet = torch.zeros(256, device='cuda')
+    dx = ops.gn_relu_bwd(dy, yq, x, stats, gamma, dgam, dbet)
+    check(dx, xr.grad.permute(0, 2, 3, 1), 1.5e-2)
+    check(dgam, gr.grad, 2e-3)
+    check(dbet, br.grad, 2e-3)
+    # upsample-add backward (13x21 -> 25x42 nearest)
+    dfine = torch.randn(2, 25, 42, 64, device='cuda', generator=g).bfloat16()
+    dco = torch.randn(2, 13, 21, 64, device='cuda', generator=g).bfloat16()
+    c = dco.float().permute(0, 3, 1, 2).requires_grad_(True)
+    F.interpolate(c, size=(25, 42), mode='nearest').backward(dfine.float().permute(0, 3, 1, 2))
+    got = ops.upsample_add_bwd(dfine, dco.clone())
+    check(got, dco.float() + c.grad.permute(0, 2, 3, 1), 1e-2)
+    # colsum / relu_bwd / sgd
+    m = torch.randn(1000, 80, device='cuda', generator=g)
+    out = torch.zeros(80, device='cuda')
+    ops.colsum(m, out)
+    check(out, m.sum(0), 1e-5)
+    mb = torch.randn(777, 256, device='cuda', generator=g).bfloat16()
+    out = torch.zeros(256, device='cuda')
+    ops.colsum(mb, out)
+    check(out, mb.float().sum(0), 1e-5)
+    rb = ops.relu_bwd(dy, yq)
+    assert torch.equal(rb, torch.where(yq > 0, dy, torch.zeros_like(dy)))
+    w0 = torch.randn(10001, device='cuda', generator=g)
+    gg = torch.randn(10001, device='cuda', generator=g)
+    p = torch.nn.Parameter(w0.clone())
+    opt = torch.optim.SGD([p], lr=0.01, momentum=0.9, weight_decay=1e-4)
+    wmine, buf = w0.clone(), torch.zeros_like(w0)
+    for it in range(3):
+        p.grad = gg * (it + 1)
+        opt.step()
+        ops.sgd_flat(wmine, gg * (it + 1), buf, 0.01, 0.9, 1e-4, 1.0, first_step=(it == 0))
+    torch.cuda.synchronize()
+    check(wmine, p.detach(), 1e-6)
