@@ -125,6 +125,8 @@ int ldb200_ld_loss_prepass(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, cons
  *              and row 8 = sum of weight_targets per level
  *   d_cls [R,C], d_reg [R,4*(reg_max+1)] grad_dtype (d_reg zero-filled by the call)
  *   d_im  [n_fg,F] grad_dtype: gradient w.r.t. x at fg_rows[i] (compact; scatter-add downstream)
+ *   d_cls_ld / d_reg_ld: row strides in elements (0 = dense); padding columns of d_cls are left
+ *              untouched, those of d_reg are zero (so d_reg can feed a TMA operand with ld % 8 == 0)
  */
 int ldb200_ld_loss_fused(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const float* cls,
                          const float* reg, const float* t_cls, const float* t_reg, const void* x,
@@ -132,8 +134,8 @@ int ldb200_ld_loss_fused(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const 
                          const float* label_weights, const float* bbox_targets, const float* vlr,
                          const float* score, const int32_t* sparse_rows, const int32_t* fg_rows,
                          const int32_t* counts, const float* norm, const float* term_grad_host,
-                         float* losses, void* d_cls, void* d_reg, void* d_im, int grad_dtype,
-                         void* stream);
+                         float* losses, void* d_cls, void* d_reg, void* d_im, int d_cls_ld, int d_reg_ld,
+                         int grad_dtype, void* stream);
 
 /* dst[rows[i], :] += src[i, :]  (rows unique).  Adds the compact IM gradient into the dense
  * gradient of the student FPN map. */

@@ -1,0 +1,310 @@
+"""ResNet backbone and FPN neck registered under the reference's names, constructor kwargs and
+parameter names (checkpoint keys `backbone.layer2.0.conv1.weight`, `neck.lateral_convs.0.conv.weight`,
+...), executing on the tcgen05 convolution kernels.
+
+Reference: mmdet/models/backbones/resnet.py:303-649, mmdet/models/utils/res_layer.py:24-103,
+mmdet/models/necks/fpn.py:66-221.  Tensors cross module boundaries as NCHW-*shaped* bf16 tensors with
+channels-last strides (zero-copy views of the NHWC buffers the kernels work on).
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import engine, ops
+from .registry import BACKBONES, NECKS
+
+
+def nhwc(x):
+    """NCHW-shaped tensor -> contiguous NHWC bf16 (zero-copy for channels-last bf16 inputs)."""
+    y = x.permute(0, 2, 3, 1)
+    if y.dtype != torch.bfloat16:
+        y = y.to(torch.bfloat16)
+    return y if y.is_contiguous() else y.contiguous()
+
+
+def nchw_view(y):
+    return y.permute(0, 3, 1, 2)
+
+
+class _Conv2d(nn.Conv2d):
+    """nn.Conv2d parameter container (same state_dict keys / init) whose weight lives channels-last."""
+
+    def _cl(self):
+        if not self.weight.is_contiguous(memory_format=torch.channels_last):
+            engine.as_channels_last_param(self.weight)
+        return self.weight
+
+
+class _Block(nn.Module):
+    def _bn_affine(self, bn):
+        return engine.bn_affine(bn)
+
+
+class BasicBlock(_Block):
+    """resnet.py:13-92."""
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = _Conv2d(inplanes, planes, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = _Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        idt = x
+        if self.downsample is not None:
+            s, b = engine.bn_affine(self.downsample[1])
+            idt = engine.conv_affine_act(x, self.downsample[0]._cl(), s, b, None, self.stride, 0, False)
+        s, b = engine.bn_affine(self.bn1)
+        o = engine.conv_affine_act(x, self.conv1._cl(), s, b, None, self.stride, 1, True)
+        s, b = engine.bn_affine(self.bn2)
+        return engine.conv_affine_act(o, self.conv2._cl(), s, b, idt, 1, 1, True)
+
+
+class Bottleneck(_Block):
+    """resnet.py:95-300, style='pytorch' (the stride sits on the 3x3 conv)."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = _Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = _Conv2d(planes, planes, 3, stride, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = _Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        idt = x
+        if self.downsample is not None:
+            s, b = engine.bn_affine(self.downsample[1])
+            idt = engine.conv_affine_act(x, self.downsample[0]._cl(), s, b, None, self.stride, 0, False)
+        s, b = engine.bn_affine(self.bn1)
+        o = engine.conv_affine_act(x, self.conv1._cl(), s, b, None, 1, 0, True)
+        s, b = engine.bn_affine(self.bn2)
+        o = engine.conv_affine_act(o, self.conv2._cl(), s, b, None, self.stride, 1, True)
+        s, b = engine.bn_affine(self.bn3)
+        return engine.conv_affine_act(o, self.conv3._cl(), s, b, idt, 1, 0, True)
+
+
+@BACKBONES.register_module()
+class ResNet(nn.Module):
+    arch_settings = {18: (BasicBlock, (2, 2, 2, 2)), 34: (BasicBlock, (3, 4, 6, 3)),
+                     50: (Bottleneck, (3, 4, 6, 3)), 101: (Bottleneck, (3, 4, 23, 3)),
+                     152: (Bottleneck, (3, 8, 36, 3))}
+
+    def __init__(self, depth, in_channels=3, stem_channels=64, base_channels=64, num_stages=4,
+                 strides=(1, 2, 2, 2), dilations=(1, 1, 1, 1), out_indices=(0, 1, 2, 3), style='pytorch',
+                 deep_stem=False, avg_down=False, frozen_stages=-1, conv_cfg=None,
+                 norm_cfg=dict(type='BN', requires_grad=True), norm_eval=True, dcn=None,
+                 stage_with_dcn=(False, False, False, False), plugins=None, with_cp=False,
+                 zero_init_residual=True):
+        super().__init__()
+        if depth not in self.arch_settings:
+            raise KeyError(f'invalid depth {depth} for resnet')
+        unsupported = dict(in_channels=in_channels != 3, stem_channels=stem_channels != 64,
+                           base_channels=base_channels != 64, strides=tuple(strides) != (1, 2, 2, 2)[:num_stages],
+                           dilations=any(d != 1 for d in dilations), style=style != 'pytorch', deep_stem=deep_stem,
+                           avg_down=avg_down, conv_cfg=conv_cfg is not None, norm=norm_cfg.get('type') != 'BN',
+                           norm_eval=not norm_eval, dcn=dcn is not None, plugins=plugins is not None, with_cp=with_cp)
+        bad = [k for k, v in unsupported.items() if v]
+        if bad:
+            raise NotImplementedError(f'ld_b200 ResNet implements the LD/GFL configuration only; unsupported: {bad}')
+        assert 1 <= num_stages <= 4 and max(out_indices) < num_stages
+        self.depth, self.num_stages, self.out_indices = depth, num_stages, tuple(out_indices)
+        self.frozen_stages, self.norm_eval, self.zero_init_residual = frozen_stages, norm_eval, zero_init_residual
+        block, stage_blocks = self.arch_settings[depth]
+        self.block = block
+        self.conv1 = _Conv2d(3, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        inplanes = 64
+        self.res_layers = []
+        for i, nb in enumerate(stage_blocks[:num_stages]):
+            planes = 64 * 2 ** i
+            stride = strides[i]
+            blocks = []
+            for j in range(nb):
+                st = stride if j == 0 else 1
+                ds = None
+                if j == 0 and (st != 1 or inplanes != planes * block.expansion):
+                    ds = nn.Sequential(_Conv2d(inplanes, planes * block.expansion, 1, st, bias=False),
+                                       nn.BatchNorm2d(planes * block.expansion))
+                blocks.append(block(inplanes, planes, st, ds))
+                inplanes = planes * block.expansion
+            name = f'layer{i + 1}'
+            self.add_module(name, nn.Sequential(*blocks))
+            self.res_layers.append(name)
+        self.feat_dim = inplanes
+        if not norm_cfg.get('requires_grad', True):
+            for m in self.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    for p in m.parameters():
+                        p.requires_grad = False
+        self._freeze_stages()
+
+    def _freeze_stages(self):
+        """resnet.py:572-588."""
+        if self.frozen_stages >= 0:
+            for m in (self.conv1, self.bn1):
+                m.eval()
+                for p in m.parameters():
+                    p.requires_grad = False
+        for i in range(1, self.frozen_stages + 1):
+            m = getattr(self, f'layer{i}')
+            m.eval()
+            for p in m.parameters():
+                p.requires_grad = False
+
+    def init_weights(self, pretrained=None):
+        """resnet.py:590-620 (pretrained checkpoints are loaded by the caller via load_state_dict)."""
+        if isinstance(pretrained, str):
+            raise NotImplementedError('no network on the B200 box: load weights with load_state_dict / seeded_init')
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+        if self.zero_init_residual:
+            for m in self.modules():
+                if isinstance(m, Bottleneck):
+                    nn.init.constant_(m.bn3.weight, 0)
+                elif isinstance(m, BasicBlock):
+                    nn.init.constant_(m.bn2.weight, 0)
+
+    def train(self, mode=True):
+        """resnet.py:639-649: BN layers stay in eval mode (norm_eval=True)."""
+        super().train(mode)
+        self._freeze_stages()
+        if mode and self.norm_eval:
+            for m in self.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    m.eval()
+        return self
+
+    def stem(self, img=None, im2col=None):
+        """conv1 7x7/2 + BN + ReLU + 3x3/2 max-pool (resnet.py:626-630) -> NHWC bf16."""
+        if im2col is None:
+            im2col = ops.stem_im2col(img.float().contiguous())
+        a, ho, wo = im2col
+        n = a.shape[0] // (ho * wo)
+        w = self.conv1.weight.detach()
+        wp = torch.zeros(64, 192, dtype=torch.bfloat16, device=w.device)
+        wp[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147).to(torch.bfloat16)
+        s, b = engine.bn_affine(self.bn1)
+        y = ops.conv2d_tc(a.view(1, 1, -1, 192), wp, 64, scale=s.detach().contiguous(), bias=b.detach().contiguous(),
+                          relu=True).view(n, ho, wo, 64)
+        return ops.maxpool3x3s2(y)
+
+    def forward(self, x, im2col=None):
+        if any(p.requires_grad for p in (self.conv1.weight, self.bn1.weight)):
+            raise NotImplementedError('the stem runs forward-only (frozen_stages >= 0 in every LD/GFL config)')
+        with torch.no_grad():
+            y = self.stem(x, im2col)
+        outs = []
+        for i, name in enumerate(self.res_layers):
+            y = getattr(self, name)(y)
+            if i in self.out_indices:
+                outs.append(nchw_view(y))
+        return tuple(outs)
+
+
+class _ConvOnly(nn.Module):
+    """mmcv ConvModule with norm_cfg=None, act_cfg=None: just `.conv` (fpn.py:121-137)."""
+
+    def __init__(self, cin, cout, k, stride=1, padding=0):
+        super().__init__()
+        self.conv = _Conv2d(cin, cout, k, stride, padding, bias=True)
+
+
+@NECKS.register_module()
+class FPN(nn.Module):
+    def __init__(self, in_channels, out_channels, num_outs, start_level=0, end_level=-1, add_extra_convs=False,
+                 extra_convs_on_inputs=True, relu_before_extra_convs=False, no_norm_on_lateral=False, conv_cfg=None,
+                 norm_cfg=None, act_cfg=None, upsample_cfg=dict(mode='nearest')):
+        super().__init__()
+        assert isinstance(in_channels, (list, tuple))
+        self.in_channels, self.out_channels, self.num_ins, self.num_outs = list(in_channels), out_channels, \
+            len(in_channels), num_outs
+        self.backbone_end_level = self.num_ins if end_level == -1 else end_level
+        self.start_level = start_level
+        if isinstance(add_extra_convs, bool) and add_extra_convs:
+            add_extra_convs = 'on_input' if extra_convs_on_inputs else 'on_output'
+        self.add_extra_convs = add_extra_convs
+        bad = []
+        if end_level != -1: bad.append('end_level')
+        if add_extra_convs not in ('on_output',): bad.append(f'add_extra_convs={add_extra_convs}')
+        if relu_before_extra_convs: bad.append('relu_before_extra_convs')
+        if conv_cfg is not None or norm_cfg is not None or act_cfg is not None: bad.append('conv/norm/act cfg')
+        if upsample_cfg.get('mode', 'nearest') != 'nearest': bad.append('upsample mode')
+        if bad:
+            raise NotImplementedError(f'ld_b200 FPN implements the LD/GFL configuration only; unsupported: {bad}')
+        self.lateral_convs = nn.ModuleList()
+        self.fpn_convs = nn.ModuleList()
+        for i in range(self.start_level, self.backbone_end_level):
+            self.lateral_convs.append(_ConvOnly(in_channels[i], out_channels, 1))
+            self.fpn_convs.append(_ConvOnly(out_channels, out_channels, 3, padding=1))
+        extra = num_outs - self.backbone_end_level + self.start_level
+        for _ in range(extra):
+            self.fpn_convs.append(_ConvOnly(out_channels, out_channels, 3, stride=2, padding=1))
+
+    def init_weights(self):
+        """fpn.py:163-167."""
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.xavier_uniform_(m.weight)
+                nn.init.constant_(m.bias, 0)
+
+    def forward(self, inputs):
+        assert len(inputs) == len(self.in_channels)
+        feats = [nhwc(x) for x in inputs[self.start_level:]]
+        nb = len(feats)
+        lat = [None] * nb
+        for i in range(nb - 1, -1, -1):   # top-down: lateral conv with the coarser level's upsample fused in
+            c = self.lateral_convs[i].conv
+            lat[i] = engine.conv_affine_act(feats[i], c._cl(), None, c.bias, lat[i + 1] if i + 1 < nb else None,
+                                            1, 0, False)
+        # one row-space buffer for all output levels (ld_b200.h "row space")
+        n = feats[0].shape[0]
+        sizes = [tuple(l.shape[1:3]) for l in lat]
+        for _ in range(len(self.fpn_convs) - nb):
+            h, w = sizes[-1]
+            sizes.append(((h - 1) // 2 + 1, (w - 1) // 2 + 1))
+        rows = torch.empty(n * sum(h * w for h, w in sizes), self.out_channels, dtype=torch.bfloat16,
+                           device=feats[0].device)
+        outs, o = [], 0
+        for i, (h, w) in enumerate(sizes):
+            view = rows[o:o + n * h * w].view(n, h, w, self.out_channels)
+            o += n * h * w
+            c = self.fpn_convs[i].conv
+            src = lat[i] if i < nb else outs[-1]
+            outs.append(engine.conv_affine_act(src, c._cl(), None, c.bias, None, c.stride[0], 1, False, out=view))
+        return tuple(nchw_view(y) for y in outs)
+
+
+def rows_of(levels):
+    """Per-level NCHW-shaped views laid out back to back in one storage -> the [R, C] row-space tensor
+    (zero-copy); anything else is copied into a fresh row-space buffer."""
+    c = levels[0].shape[1]
+    try:
+        base = levels[0].permute(0, 2, 3, 1)
+        ptr = base.data_ptr()
+        es = base.element_size()
+        total = 0
+        ok = True
+        for t in levels:
+            v = t.permute(0, 2, 3, 1)
+            ok = ok and v.is_contiguous() and v.data_ptr() == ptr + total * c * es and v.dtype == base.dtype \
+                and t.shape[1] == c and v.untyped_storage().data_ptr() == base.untyped_storage().data_ptr()
+            total += v.shape[0] * v.shape[1] * v.shape[2]
+        if ok:
+            return torch.as_strided(base, (total, c), (c, 1), base.storage_offset())
+    except Exception:
+        pass
+    return ops.to_rows(list(levels))

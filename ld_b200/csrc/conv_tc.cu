@@ -596,8 +596,8 @@ using namespace ldb;
 
 extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
   LDB_REQUIRE(d && d->in && d->weight && d->out, LDB_EINVAL, "conv2d_tc: null pointer");
-  LDB_REQUIRE(d->Cin > 0 && d->Cin % KCH == 0, LDB_ENOSUP, "conv2d_tc: Cin=%d must be a multiple of 64", d->Cin);
-  LDB_REQUIRE(d->in_ld >= d->Cin && d->in_ld % 8 == 0, LDB_EINVAL, "conv2d_tc: in_ld");
+  LDB_REQUIRE(d->Cin > 0, LDB_EINVAL, "conv2d_tc: Cin");
+  LDB_REQUIRE(d->in_ld >= d->Cin && d->in_ld % 8 == 0, LDB_EINVAL, "conv2d_tc: in_ld must be >= Cin and a multiple of 8");
   LDB_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, LDB_EINVAL, "conv2d_tc: ntaps");
   LDB_REQUIRE(d->N >= 1 && d->HO >= 1 && d->WO >= 1 && d->Cout >= 1, LDB_EINVAL, "conv2d_tc: shape");
   LDB_REQUIRE(d->sx >= 1 && d->sy >= 1 && d->sx <= 8 && d->sy <= 8, LDB_EINVAL, "conv2d_tc: stride");
@@ -608,7 +608,9 @@ extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   ConvParams p;
   memset(&p, 0, sizeof(p));
-  p.N = d->N; p.HO = d->HO; p.WO = d->WO; p.Cout = d->Cout; p.Cin = d->Cin; p.ntaps = d->ntaps;
+  // channels beyond Cin inside the last 64-wide k-block are TMA out-of-bounds reads (zeros); the
+  // weight rows must hold finite values there (tap_wk spacing >= round_up(Cin, 64))
+  p.N = d->N; p.HO = d->HO; p.WO = d->WO; p.Cout = d->Cout; p.Cin = (d->Cin + KCH - 1) / KCH * KCH; p.ntaps = d->ntaps;
   for (int t = 0; t < d->ntaps; ++t) {
     p.tap_dx[t] = d->tap_dx[t]; p.tap_dy[t] = d->tap_dy[t]; p.tap_wk[t] = d->tap_wk[t];
   }
@@ -695,7 +697,7 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const Wg
 extern "C" int ldb200_conv2d_wgrad_tc(const ldb_wgrad_desc* d, void* stream_) {
   LDB_REQUIRE(d && d->dy && d->x && d->dw, LDB_EINVAL, "wgrad_tc: null pointer");
   LDB_REQUIRE(d->Cin > 0 && d->Cin % KCH == 0, LDB_ENOSUP, "wgrad_tc: Cin=%d must be a multiple of 64", d->Cin);
-  LDB_REQUIRE(d->Cout > 0 && d->Cout % 8 == 0, LDB_ENOSUP, "wgrad_tc: Cout=%d must be a multiple of 8", d->Cout);
+  LDB_REQUIRE(d->Cout > 0, LDB_EINVAL, "wgrad_tc: Cout");
   LDB_REQUIRE(d->dy_ld >= d->Cout && d->dy_ld % 8 == 0 && d->x_ld >= d->Cin && d->x_ld % 8 == 0, LDB_EINVAL,
               "wgrad_tc: leading dimensions");
   LDB_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9 && d->sx >= 1 && d->sy >= 1, LDB_EINVAL, "wgrad_tc: taps/stride");

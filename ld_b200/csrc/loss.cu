@@ -38,6 +38,7 @@ struct LossParams {
   int phases;   // bit0 dense QFL, bit1 sparse rows, bit2 imitation rows (all set normally)
   float* losses;
   void *d_cls, *d_reg, *d_im;
+  int dcls_ld, dreg_ld;   // row strides (elements) of d_cls / d_reg
   int grad_bf16;
   float* score;  // prepass only (may be null)
   float* wsum;   // prepass only
@@ -239,15 +240,16 @@ __global__ void __launch_bounds__(LOSS_THREADS, 2) ld_loss_fused_kernel(LossPara
         acc += sc * ((lo[0] + lo[1]) + (lo[2] + lo[3]));
         if (wg) {
           const float k = sc * gsc;
+          const size_t go = (size_t)r * P.dcls_ld + (size_t)(v - (long long)r * vpr) * 4;
           if (sizeof(GT) == 4) {
-            reinterpret_cast<float4*>(d_cls)[v] = make_float4(k * gr[0], k * gr[1], k * gr[2], k * gr[3]);
+            *reinterpret_cast<float4*>((float*)d_cls + go) = make_float4(k * gr[0], k * gr[1], k * gr[2], k * gr[3]);
           } else {
             __nv_bfloat162 a = __floats2bfloat162_rn(k * gr[0], k * gr[1]);
             __nv_bfloat162 b = __floats2bfloat162_rn(k * gr[2], k * gr[3]);
             uint2 pk;
             pk.x = *reinterpret_cast<unsigned*>(&a);
             pk.y = *reinterpret_cast<unsigned*>(&b);
-            reinterpret_cast<uint2*>(d_cls)[v] = pk;
+            *reinterpret_cast<uint2*>((__nv_bfloat16*)d_cls + go) = pk;
           }
         }
       }
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, 2) ld_loss_fused_kernel(LossPara
         float lo, gr;
         qfl_neg(__ldg(P.cls + e), P.beta, lo, gr);
         acc += sc * lo;
-        if (wg) store_grad<GT>(d_cls + e, sc * gsc * gr);
+        if (wg) store_grad<GT>(d_cls + (size_t)r * P.dcls_ld + (e - (long long)r * C), sc * gsc * gr);
       }
     }
     acc = warp_sum(acc);
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, 2) ld_loss_fused_kernel(LossPara
           else qfl_neg(xs[q], P.beta, lo, gr);
           qsum += lo;
           if (wg)
-            store_grad<GT>(d_cls + (size_t)r * C + c,
+            store_grad<GT>(d_cls + (size_t)r * P.dcls_ld + c,
                            P.tg[0][l] * k_cls * gr + P.tg[5][l] * k_kd * (P.kd_T / (float)C) * (ps - pt));
         }
       }
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, 2) ld_loss_fused_kernel(LossPara
     }
     if (wg && active) {
 #pragma unroll
-      for (int s = 0; s < 4; ++s) store_grad<GT>(d_reg + (size_t)r * 4 * bins + s * bins + lane, gz[s]);
+      for (int s = 0; s < 4; ++s) store_grad<GT>(d_reg + (size_t)r * P.dreg_ld + s * bins + lane, gz[s]);
     }
     if (lane == 0) {
       if (pos) {
@@ -719,8 +721,8 @@ extern "C" int ldb200_ld_loss_fused(const ldb_pyramid* pyr, const ldb_loss_cfg* 
                                     const float* label_weights, const float* bbox_targets, const float* vlr,
                                     const float* score, const int32_t* sparse_rows, const int32_t* fg_rows,
                                     const int32_t* counts, const float* norm, const float* term_grad_host,
-                                    float* losses, void* d_cls, void* d_reg, void* d_im, int grad_dtype,
-                                    void* stream_) {
+                                    float* losses, void* d_cls, void* d_reg, void* d_im, int d_cls_ld,
+                                    int d_reg_ld, int grad_dtype, void* stream_) {
   (void)score;
   LossParams P;
   int e = fill_params(pyr, cfg, &P);
@@ -744,10 +746,14 @@ extern "C" int ldb200_ld_loss_fused(const ldb_pyramid* pyr, const ldb_loss_cfg* 
   if (wg) memcpy(P.tg, term_grad_host, sizeof(P.tg));
   P.losses = losses; P.d_cls = d_cls; P.d_reg = d_reg; P.d_im = d_im;
   P.grad_bf16 = grad_dtype == LDB_BF16;
+  P.dcls_ld = d_cls_ld > 0 ? d_cls_ld : P.C;
+  P.dreg_ld = d_reg_ld > 0 ? d_reg_ld : 4 * P.bins;
+  LDB_REQUIRE(P.dcls_ld >= P.C && P.dreg_ld >= 4 * P.bins && P.dcls_ld % 4 == 0, LDB_EINVAL,
+              "ld_loss_fused: gradient leading dimensions");
   const size_t R = (size_t)P.pyr.N * P.pyr.off[P.pyr.L];
   const size_t gsz = P.grad_bf16 ? 2 : 4;
   LDB_CUDA(cudaMemsetAsync(losses, 0, sizeof(float) * LDB_NUM_TERMS * LDB_MAX_LEVELS, stream));
-  if (wg) LDB_CUDA(cudaMemsetAsync(d_reg, 0, R * 4 * P.bins * gsz, stream));
+  if (wg) LDB_CUDA(cudaMemsetAsync(d_reg, 0, R * P.dreg_ld * gsz, stream));
   const int grid = num_sms() * 2;
   if (!P.grad_bf16 && !P.feat_bf16) ld_loss_fused_kernel<float, float><<<grid, LOSS_THREADS, 0, stream>>>(P);
   else if (!P.grad_bf16 && P.feat_bf16) ld_loss_fused_kernel<float, __nv_bfloat16><<<grid, LOSS_THREADS, 0, stream>>>(P);

@@ -1,0 +1,373 @@
+"""GFLHead / LDHead registered under the reference's names with the reference's constructor kwargs,
+parameter names and call signatures, executing on the sm_100a kernels.
+
+Reference: mmdet/models/dense_heads/anchor_head.py:36-96, gfl_head.py:15-194, ld_head.py:43-638.
+The per-level Python loops of the reference (`multi_apply(forward_single)`, `multi_apply(loss_single)`,
+`multi_apply(_get_target_single)`) collapse into: tower convs (tcgen05) + GroupNorm kernels per level,
+ONE target-generation call for the whole batch, ONE pre-pass and ONE fused loss launch for all five
+levels (row space).
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import engine, lib as L, ops
+from .anchors import AnchorGenerator  # noqa: F401  (registers)
+from .backbones import _Conv2d, nchw_view, nhwc, rows_of
+from .registry import (HEADS, build_anchor_generator, build_assigner, build_bbox_coder, build_loss,
+                       build_sampler)
+
+
+class _ConvGN(nn.Module):
+    """mmcv ConvModule(conv no-bias -> GN -> ReLU): parameters `.conv.weight`, `.gn.{weight,bias}`."""
+
+    def __init__(self, cin, cout, norm_cfg):
+        super().__init__()
+        self.conv = _Conv2d(cin, cout, 3, 1, 1, bias=False)
+        self.gn = nn.GroupNorm(norm_cfg.get('num_groups', 32), cout, eps=norm_cfg.get('eps', 1e-5))
+        for p in self.gn.parameters():
+            p.requires_grad = norm_cfg.get('requires_grad', True)
+
+    def forward(self, x):
+        c = engine.conv_affine_act(x, self.conv._cl(), None, None, None, 1, 1, False)
+        return engine.gn_relu(c, self.gn.weight, self.gn.bias, self.gn.num_groups, self.gn.eps)
+
+
+class Scale(nn.Module):
+    """mmcv.cnn.Scale."""
+
+    def __init__(self, scale=1.0):
+        super().__init__()
+        self.scale = nn.Parameter(torch.tensor(scale, dtype=torch.float))
+
+    def forward(self, x):
+        return x * self.scale
+
+
+class Integral(nn.Module):
+    """gfl_head.py:15-44 (buffer kept for state_dict parity; the expectation is computed in-kernel)."""
+
+    def __init__(self, reg_max=16):
+        super().__init__()
+        self.reg_max = reg_max
+        self.register_buffer('project', torch.linspace(0, reg_max, reg_max + 1))
+
+
+@HEADS.register_module()
+class GFLHead(nn.Module):
+    def __init__(self, num_classes, in_channels, stacked_convs=4, conv_cfg=None,
+                 norm_cfg=dict(type='GN', num_groups=32, requires_grad=True),
+                 loss_dfl=dict(type='DistributionFocalLoss', loss_weight=0.25), reg_max=16,
+                 feat_channels=256,
+                 anchor_generator=dict(type='AnchorGenerator', scales=[8, 16, 32], ratios=[0.5, 1.0, 2.0],
+                                       strides=[4, 8, 16, 32, 64]),
+                 bbox_coder=dict(type='DeltaXYWHBBoxCoder', clip_border=True, target_means=(.0, .0, .0, .0),
+                                 target_stds=(1.0, 1.0, 1.0, 1.0)),
+                 reg_decoded_bbox=False,
+                 loss_cls=dict(type='CrossEntropyLoss', use_sigmoid=True, loss_weight=1.0),
+                 loss_bbox=dict(type='SmoothL1Loss', beta=1.0 / 9.0, loss_weight=1.0),
+                 train_cfg=None, test_cfg=None):
+        super().__init__()
+        # ---- AnchorHead.__init__ (anchor_head.py:36-96)
+        self.in_channels, self.num_classes, self.feat_channels = in_channels, num_classes, feat_channels
+        self.use_sigmoid_cls = loss_cls.get('use_sigmoid', False)
+        self.cls_out_channels = num_classes if self.use_sigmoid_cls else num_classes + 1
+        if self.cls_out_channels <= 0:
+            raise ValueError(f'num_classes={num_classes} is too small')
+        self.reg_decoded_bbox = reg_decoded_bbox
+        self.bbox_coder = build_bbox_coder(bbox_coder)
+        self.loss_cls = build_loss(loss_cls)
+        self.loss_bbox = build_loss(loss_bbox)
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        if self.train_cfg:
+            self.assigner = build_assigner(self.train_cfg.assigner)
+            self.sampler = build_sampler(dict(type='PseudoSampler'), context=self)
+        self.anchor_generator = build_anchor_generator(anchor_generator)
+        self.num_anchors = self.anchor_generator.num_base_anchors[0]
+        # ---- GFLHead.__init__ (gfl_head.py:77-100)
+        self.stacked_convs, self.conv_cfg, self.norm_cfg, self.reg_max = stacked_convs, conv_cfg, norm_cfg, reg_max
+        if conv_cfg is not None or norm_cfg.get('type') != 'GN':
+            raise NotImplementedError('ld_b200 GFLHead implements conv_cfg=None + GN towers (all GFL/LD configs)')
+        self.integral = Integral(reg_max)
+        self.loss_dfl = build_loss(loss_dfl)
+        self._init_layers()
+
+    def _init_layers(self):
+        self.cls_convs = nn.ModuleList()
+        self.reg_convs = nn.ModuleList()
+        for i in range(self.stacked_convs):
+            chn = self.in_channels if i == 0 else self.feat_channels
+            self.cls_convs.append(_ConvGN(chn, self.feat_channels, self.norm_cfg))
+            self.reg_convs.append(_ConvGN(chn, self.feat_channels, self.norm_cfg))
+        assert self.num_anchors == 1, 'anchor free version'
+        self.gfl_cls = _Conv2d(self.feat_channels, self.cls_out_channels, 3, padding=1)
+        self.gfl_reg = _Conv2d(self.feat_channels, 4 * (self.reg_max + 1), 3, padding=1)
+        self.scales = nn.ModuleList([Scale(1.0) for _ in self.anchor_generator.strides])
+
+    def init_weights(self):
+        """gfl_head.py:135-143."""
+        for m in list(self.cls_convs) + list(self.reg_convs):
+            nn.init.normal_(m.conv.weight, 0, 0.01)
+        nn.init.normal_(self.gfl_cls.weight, 0, 0.01)
+        nn.init.constant_(self.gfl_cls.bias, float(-math.log((1 - 0.01) / 0.01)))
+        nn.init.normal_(self.gfl_reg.weight, 0, 0.01)
+        nn.init.constant_(self.gfl_reg.bias, 0)
+
+    # ------------------------------------------------------------------ forward
+    def towers(self, feats):
+        """feats: NCHW-shaped level tensors -> per-level (cls_feat, reg_feat) NHWC bf16."""
+        out = []
+        for x in feats:
+            cf = rf = nhwc(x)
+            for m in self.cls_convs:
+                cf = m(cf)
+            for m in self.reg_convs:
+                rf = m(rf)
+            out.append((cf, rf))
+        return out
+
+    def final_convs(self, tower_out, cls_rows, reg_rows):
+        """gfl_cls / gfl_reg*scale (gfl_head.py:181-182) written as fp32 NHWC rows (row space)."""
+        o = 0
+        wc, wr = engine.packed_weight(self.gfl_cls._cl()), engine.packed_weight(self.gfl_reg._cl())
+        bc = self.gfl_cls.bias.detach()
+        nb = 4 * (self.reg_max + 1)
+        for (cf, rf), sc in zip(tower_out, self.scales):
+            n, h, w, _ = cf.shape
+            cnt = n * h * w
+            s = sc.scale.detach()
+            ops.conv2d_tc(cf, wc, self.cls_out_channels, 3, 3, 1, 1, out=cls_rows[o:o + cnt].view(n, h, w, -1),
+                          bias=bc)
+            ops.conv2d_tc(rf, wr, nb, 3, 3, 1, 1, out=reg_rows[o:o + cnt].view(n, h, w, -1),
+                          scale=s.expand(nb).contiguous(), bias=(self.gfl_reg.bias.detach() * s).contiguous())
+            o += cnt
+
+    def alloc_rows(self, feats):
+        n = feats[0].shape[0]
+        sizes = [tuple(f.shape[2:]) for f in feats]
+        R = n * sum(h * w for h, w in sizes)
+        dev = feats[0].device
+        return (torch.empty(R, self.cls_out_channels, dtype=torch.float32, device=dev),
+                torch.empty(R, 4 * (self.reg_max + 1), dtype=torch.float32, device=dev), sizes)
+
+    def forward(self, feats):
+        """gfl_head.py:145-159: -> (cls_scores, bbox_preds), lists of NCHW-shaped fp32 level tensors.
+        Inference-style forward (no autograd through the two output convs); training goes through
+        `LDHead.forward_train`, which fuses them with the loss."""
+        with torch.no_grad():
+            cls_rows, reg_rows, sizes = self.alloc_rows(feats)
+            self.final_convs(self.towers(feats), cls_rows, reg_rows)
+        pyr = L.Pyramid.make(feats[0].shape[0], sizes, [s[0] for s in self.anchor_generator.strides])
+        return ops.from_rows(cls_rows, pyr), ops.from_rows(reg_rows, pyr)
+
+
+IM_MODES = {'finegrained': L.IM_FINEGRAINED, 'fitnet': L.IM_CENTER, 'decouple': L.IM_CENTER}
+
+
+class _LDLossFn(torch.autograd.Function):
+    """gfl_cls/gfl_reg output convs + LDHead.loss (ld_head.py:284-375) as one autograd node.
+
+    inputs: per-level tower outputs (cls_feat, reg_feat), per-level student FPN maps, the four output
+    conv parameters and the per-level Scale parameters.  forward computes the losses AND all input
+    gradients (the fused kernel emits d_cls/d_reg/d_x in the same launch, upstream weights = 1 as in
+    BaseDetector._parse_losses); backward hands them out."""
+
+    @staticmethod
+    def forward(ctx, head, aux, *tensors):
+        nl = aux['num_levels']
+        cls_feats, reg_feats, xs = tensors[:nl], tensors[nl:2 * nl], tensors[2 * nl:3 * nl]
+        w_cls, b_cls, w_reg, b_reg = tensors[3 * nl:3 * nl + 4]
+        scales = tensors[3 * nl + 4:]
+        dev = cls_feats[0].device
+        C, NB = head.cls_out_channels, 4 * (head.reg_max + 1)
+        x_rows = rows_of([nchw_view(x.detach()) for x in xs])
+        pyr = aux['pyr']
+        R = pyr.rows
+        cls_rows = torch.empty(R, C, dtype=torch.float32, device=dev)
+        reg_rows = torch.empty(R, NB, dtype=torch.float32, device=dev)
+        head.final_convs(list(zip(cls_feats, reg_feats)), cls_rows, reg_rows)
+        tg = aux['targets']
+        cfg = aux['loss_cfg']
+        wsum, _ = ops.ld_loss_prepass(cfg, cls_rows, reg_rows, tg)
+        norm = ops.loss_normalisers(tg, wsum)
+        dcls_ld, dreg_ld = (C + 7) // 8 * 8, (NB + 7) // 8 * 8
+        losses, d_cls, d_reg, d_im = ops.ld_loss_fused(
+            cfg, cls_rows, reg_rows, aux['t_cls_rows'], aux['t_reg_rows'], x_rows, aux['t_x_rows'], tg, norm,
+            term_grad=aux['term_grad'], grad_dtype=torch.bfloat16, max_fg=aux.get('max_fg'),
+            d_cls_ld=dcls_ld, d_reg_ld=dreg_ld)
+        ctx.head, ctx.aux = head, aux
+        ctx.save_for_backward(*tensors, cls_rows, reg_rows, d_cls, d_reg, d_im)
+        ctx.mark_non_differentiable(norm)
+        aux['cls_rows'], aux['reg_rows'] = cls_rows, reg_rows
+        return losses, norm
+
+    @staticmethod
+    def backward(ctx, g_losses, _g_norm):
+        head, aux = ctx.head, ctx.aux
+        nl = aux['num_levels']
+        saved = ctx.saved_tensors
+        tensors, (cls_rows, reg_rows, d_cls, d_reg, d_im) = saved[:-5], saved[-5:]
+        cls_feats, reg_feats, xs = tensors[:nl], tensors[nl:2 * nl], tensors[2 * nl:3 * nl]
+        w_cls, b_cls, w_reg, b_reg = tensors[3 * nl:3 * nl + 4]
+        scales = tensors[3 * nl + 4:]
+        C, NB = head.cls_out_channels, 4 * (head.reg_max + 1)
+        tg = aux['targets']
+        dev = d_cls.device
+        # conv biases: column sums of the row-space gradients
+        g_bc = torch.zeros(d_cls.shape[1], dtype=torch.float32, device=dev)
+        ops.colsum(d_cls, g_bc)
+        g_bc = g_bc[:C]
+        ci = w_cls.shape[1]
+        Gc = torch.zeros(C, 9 * ci, dtype=torch.float32, device=dev)
+        g_wr = torch.zeros(NB, 9 * ci, dtype=torch.float32, device=dev)
+        g_br = torch.zeros(NB, dtype=torch.float32, device=dev)
+        g_scales, g_cf, g_rf, g_x = [], [], [], []
+        o = 0
+        x_dense = None
+        if aux['im_active']:
+            x_dense = torch.zeros(tg.pyr.rows, xs[0].shape[-1], dtype=torch.bfloat16, device=dev)
+            ops.scatter_add_rows(x_dense, d_im, tg.fg_rows, tg.counts[1:2])
+        for l in range(nl):
+            n, h, w, _ = cls_feats[l].shape
+            cnt = n * h * w
+            gc = d_cls[o:o + cnt].view(n, h, w, -1)[..., :C]
+            gr = d_reg[o:o + cnt].view(n, h, w, -1)[..., :NB]
+            s = scales[l].detach()
+            # bbox_pred = scale_l * (conv(reg_feat) + b)  (gfl_head.py:182):
+            #   d scale_l = sum d_reg * bbox_pred / scale_l ; dW += scale_l * wgrad ; db += scale_l * colsum
+            g_scales.append((gr.float() * reg_rows[o:o + cnt].view(n, h, w, NB)).sum() / s)
+            ops.conv2d_wgrad_tc(gc, cls_feats[l], Gc, 3, 3, 1, 1)
+            Gr = torch.zeros(NB, 9 * ci, dtype=torch.float32, device=dev)
+            ops.conv2d_wgrad_tc(gr, reg_feats[l], Gr, 3, 3, 1, 1)
+            g_wr += Gr * s
+            blk = torch.zeros(d_reg.shape[1], dtype=torch.float32, device=dev)
+            ops.colsum(d_reg[o:o + cnt], blk)
+            g_br += blk[:NB] * s
+            g_cf.append(engine.conv_dgrad(gc, w_cls, None, 1, 1, (h, w)))
+            g_rf.append(engine.conv_dgrad(gr, w_reg, s.expand(NB), 1, 1, (h, w)))
+            g_x.append(None if x_dense is None else x_dense[o:o + cnt].view(n, h, w, -1))
+            o += cnt
+        g_wc = Gc.view(C, 3, 3, ci).permute(0, 3, 1, 2)
+        g_wr = g_wr.view(NB, 3, 3, ci).permute(0, 3, 1, 2)
+        return (None, None, *g_cf, *g_rf, *g_x, g_wc, g_bc, g_wr, g_br, *g_scales)
+
+
+@HEADS.register_module()
+class LDHead(GFLHead):
+    """ld_head.py:43-71: GFLHead + localization distillation (LD), VLR LD, classification KD and
+    feature imitation losses."""
+
+    def __init__(self, num_classes, in_channels,
+                 loss_ld=dict(type='KnowledgeDistillationKLDivLoss', loss_weight=0.25, T=10),
+                 loss_ld_vlr=dict(type='KnowledgeDistillationKLDivLoss', loss_weight=0.25, T=10),
+                 loss_kd=dict(type='KnowledgeDistillationKLDivLoss', loss_weight=10, T=2),
+                 loss_im=dict(type='IMLoss', loss_weight=0), imitation_method='gibox', **kwargs):
+        super().__init__(num_classes, in_channels, **kwargs)
+        self.imitation_method = imitation_method
+        self.loss_im = build_loss(loss_im)
+        self.loss_ld = build_loss(loss_ld)
+        self.loss_ld_vlr = build_loss(loss_ld_vlr)
+        self.loss_kd = build_loss(loss_kd)
+        from .registry import build_iou_calculator
+        self.iou_calculator = build_iou_calculator(dict(type='BboxOverlaps2D'))
+
+    # ------------------------------------------------------------------ config -> kernel parameters
+    def loss_cfg(self):
+        if type(self.loss_bbox).__name__ != 'GIoULoss' or type(self.loss_cls).__name__ != 'QualityFocalLoss':
+            raise NotImplementedError('the fused LD loss kernel implements QualityFocalLoss + GIoULoss '
+                                      '(every configs/ld/*gflv1* file)')
+        if not self.loss_cls.use_sigmoid:
+            raise NotImplementedError('QualityFocalLoss(use_sigmoid=False) (LDv2 configs) is not implemented yet')
+        return ops.make_loss_cfg(
+            num_classes=self.cls_out_channels, reg_max=self.reg_max, feat_channels=self.in_channels,
+            qfl_weight=self.loss_cls.loss_weight, qfl_beta=self.loss_cls.beta,
+            giou_weight=self.loss_bbox.loss_weight, giou_eps=self.loss_bbox.eps,
+            dfl_weight=self.loss_dfl.loss_weight, ld_weight=self.loss_ld.loss_weight, ld_T=self.loss_ld.T,
+            ld_vlr_weight=self.loss_ld_vlr.loss_weight, ld_vlr_T=self.loss_ld_vlr.T,
+            kd_weight=self.loss_kd.loss_weight, kd_T=self.loss_kd.T, im_weight=self.loss_im.loss_weight)
+
+    def get_targets(self, featmap_sizes, img_metas, gt_bboxes, gt_labels, device):
+        """ld_head.py:377-447 for the whole batch in one call (row space)."""
+        if self.imitation_method not in IM_MODES:
+            raise NotImplementedError(f"imitation_method='{self.imitation_method}' (GI boxes + NMS, ld_head.py:613-638) "
+                                      f"is not implemented; use 'finegrained' (configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py:47)")
+        if getattr(self.train_cfg, 'allowed_border', -1) >= 0:
+            raise NotImplementedError('allowed_border >= 0 (LD configs use -1)')
+        pyr = L.Pyramid.make(len(img_metas), featmap_sizes, [s[0] for s in self.anchor_generator.strides])
+        pad_hw = [m['pad_shape'][:2] for m in img_metas]
+        return ops.ld_targets(pyr, gt_bboxes, gt_labels, pad_hw, topk=self.assigner.topk,
+                              im_mode=IM_MODES[self.imitation_method], num_classes=self.num_classes, device=device)
+
+    # ------------------------------------------------------------------ training entry points
+    def forward_train(self, x, out_teacher, teacher_x, img_metas, gt_bboxes, gt_labels=None,
+                      gt_bboxes_ignore=None, proposal_cfg=None, **kwargs):
+        """ld_head.py:73-114.  x / teacher_x: tuples of NCHW-shaped FPN levels, out_teacher = (cls_scores,
+        bbox_preds) of the teacher head."""
+        assert gt_labels is not None and proposal_cfg is None
+        if gt_bboxes_ignore is not None and any(g is not None and g.numel() for g in gt_bboxes_ignore):
+            raise NotImplementedError('gt_bboxes_ignore (ignore_iof_thr=-1 in all LD configs)')
+        sizes = [tuple(f.shape[2:]) for f in x]
+        assert len(sizes) == self.anchor_generator.num_levels
+        dev = x[0].device
+        tg = self.get_targets(sizes, img_metas, gt_bboxes, gt_labels, dev)
+        t_cls, t_reg = out_teacher
+        aux = dict(num_levels=len(sizes), pyr=tg.pyr, targets=tg, loss_cfg=self.loss_cfg(),
+                   t_cls_rows=rows_of([t.detach() for t in t_cls]).float(),
+                   t_reg_rows=rows_of([t.detach() for t in t_reg]).float(),
+                   t_x_rows=rows_of([t.detach() for t in teacher_x]),
+                   term_grad=True, im_active=self.loss_im.loss_weight != 0)
+        tow = self.towers(x)
+        xs = [nhwc(f) for f in x]
+        if aux['t_x_rows'].dtype != xs[0].dtype:
+            aux['t_x_rows'] = aux['t_x_rows'].to(xs[0].dtype)
+        args = [t[0] for t in tow] + [t[1] for t in tow] + xs + \
+               [self.gfl_cls._cl(), self.gfl_cls.bias, self.gfl_reg._cl(), self.gfl_reg.bias] + \
+               [s.scale for s in self.scales]
+        losses, norm = _LDLossFn.apply(self, aux, *args)
+        self._last_aux = aux
+        nl = len(sizes)
+        return {k: [losses[i, l] for l in range(nl)] for i, k in enumerate(ops.TERMS)}
+
+    def loss(self, cls_scores, bbox_preds, gt_bboxes, gt_labels, soft_teacher, x, teacher_x, img_metas,
+             gt_bboxes_ignore=None):
+        """ld_head.py:284-375 on given head outputs (API parity; differentiable w.r.t. cls_scores,
+        bbox_preds and x through the same fused kernel, gradients returned in fp32)."""
+        sizes = [tuple(f.shape[2:]) for f in cls_scores]
+        dev = cls_scores[0].device
+        tg = self.get_targets(sizes, img_metas, gt_bboxes, gt_labels, dev)
+        soft_label, soft_target = soft_teacher
+        nl = len(sizes)
+        losses = _LossOnlyFn.apply(self, tg, nl, *cls_scores, *bbox_preds, *x, *soft_label, *soft_target, *teacher_x)
+        return {k: [losses[i, l] for l in range(nl)] for i, k in enumerate(ops.TERMS)}
+
+
+class _LossOnlyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, head, tg, nl, *t):
+        cls, reg, xs, t_cls, t_reg, t_x = (t[i * nl:(i + 1) * nl] for i in range(6))
+        cfg = head.loss_cfg()
+        rows = [ops.to_rows([v.detach().float() for v in grp]) for grp in (cls, reg, t_cls, t_reg)]
+        xr = ops.to_rows([v.detach() for v in xs])
+        txr = ops.to_rows([v.detach() for v in t_x]).to(xr.dtype)
+        if xr.dtype not in (torch.float32, torch.bfloat16):
+            xr, txr = xr.float(), txr.float()
+        wsum, _ = ops.ld_loss_prepass(cfg, rows[0], rows[1], tg)
+        norm = ops.loss_normalisers(tg, wsum)
+        losses, d_cls, d_reg, d_im = ops.ld_loss_fused(cfg, rows[0], rows[1], rows[2], rows[3], xr, txr, tg, norm,
+                                                       term_grad=True, grad_dtype=torch.float32)
+        d_x = torch.zeros(tg.pyr.rows, xr.shape[1], dtype=torch.float32, device=xr.device)
+        ops.scatter_add_rows(d_x, d_im, tg.fg_rows, tg.counts[1:2])
+        ctx.pyr, ctx.nl = tg.pyr, nl
+        ctx.save_for_backward(d_cls, d_reg, d_x)
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        d_cls, d_reg, d_x = ctx.saved_tensors
+        nl = ctx.nl
+        out = [None, None, None]
+        for d in (d_cls, d_reg, d_x):
+            out += [v for v in ops.from_rows(d, ctx.pyr)]
+        out += [None] * (3 * nl)
+        return tuple(out)

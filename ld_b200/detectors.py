@@ -1,0 +1,227 @@
+"""Detectors registered under the reference's names: `GFL` (the teacher's type) and
+`KnowledgeDistillationSingleStageDetector` (mmdet/models/detectors/{base,single_stage,gfl,
+kd_one_stage}.py), plus the data-parallel train step (flat gradient buffer, ONE NCCL all-reduce, fused
+SGD) that replaces mmcv's MMDistributedDataParallel + OptimizerHook + torch.optim.SGD
+(mmdet/apis/train.py:74-127)."""
+import os
+from collections import OrderedDict
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import engine, lib as L, ops
+from .config import Config
+from .registry import DETECTORS, build_backbone, build_head, build_neck
+
+
+class BaseDetector(nn.Module):
+    """detectors/base.py: forward dispatch, train_step, _parse_losses."""
+
+    def forward(self, img, img_metas, return_loss=True, **kwargs):
+        if return_loss:
+            return self.forward_train(img, img_metas, **kwargs)
+        raise NotImplementedError('inference (forward_test / simple_test) is outside the LD train path')
+
+    def _parse_losses(self, losses):
+        """base.py:185-218: loss = sum over keys containing 'loss' of the per-level sums; one device->host
+        copy for the 9+1 log scalars instead of ten allreduce+.item() pairs."""
+        log_vars = OrderedDict()
+        for name, value in losses.items():
+            if isinstance(value, torch.Tensor):
+                log_vars[name] = value.mean()
+            elif isinstance(value, list):
+                log_vars[name] = sum(v.mean() for v in value)
+            else:
+                raise TypeError(f'{name} is not a tensor or list of tensors')
+        loss = sum(v for k, v in log_vars.items() if 'loss' in k)
+        log_vars['loss'] = loss
+        keys = list(log_vars)
+        vec = torch.stack([log_vars[k].detach().float() for k in keys])
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(vec)
+            vec = vec / dist.get_world_size()
+        host = vec.cpu()
+        return loss, OrderedDict((k, float(host[i])) for i, k in enumerate(keys))
+
+    def train_step(self, data, optimizer):
+        """base.py:220-253."""
+        losses = self(**data)
+        loss, log_vars = self._parse_losses(losses)
+        return dict(loss=loss, log_vars=log_vars, num_samples=len(data['img_metas']))
+
+
+@DETECTORS.register_module()
+class SingleStageDetector(BaseDetector):
+    """detectors/single_stage.py:17-57."""
+
+    def __init__(self, backbone, neck=None, bbox_head=None, train_cfg=None, test_cfg=None, pretrained=None):
+        super().__init__()
+        self.backbone = build_backbone(backbone)
+        if neck is not None:
+            self.neck = build_neck(neck)
+        bbox_head = dict(bbox_head)
+        bbox_head.update(train_cfg=train_cfg, test_cfg=test_cfg)
+        self.bbox_head = build_head(bbox_head)
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.init_weights(pretrained=pretrained)
+
+    @property
+    def with_neck(self):
+        return hasattr(self, 'neck') and self.neck is not None
+
+    def init_weights(self, pretrained=None):
+        if isinstance(pretrained, str):
+            # the reference downloads torchvision://resnetNN here; there is no network on the B200 box, the
+            # caller loads weights afterwards (load_state_dict / synth.seeded_init)
+            pretrained = None
+        self.backbone.init_weights(pretrained=pretrained)
+        if self.with_neck:
+            self.neck.init_weights()
+        self.bbox_head.init_weights()
+
+    def extract_feat(self, img, im2col=None):
+        x = self.backbone(img, im2col=im2col)
+        if self.with_neck:
+            x = self.neck(x)
+        return x
+
+
+@DETECTORS.register_module()
+class GFL(SingleStageDetector):
+    """detectors/gfl.py."""
+
+
+def _resolve_config(path):
+    for root in ('', os.environ.get('LD_B200_CONFIG_ROOT', ''), '/root/reference'):
+        p = os.path.join(root, path) if root else path
+        if os.path.isfile(p):
+            return p
+    raise FileNotFoundError(f'teacher_config {path} not found (relative to CWD, $LD_B200_CONFIG_ROOT)')
+
+
+@DETECTORS.register_module()
+class KnowledgeDistillationSingleStageDetector(SingleStageDetector):
+    """kd_one_stage.py:12-108."""
+
+    def __init__(self, backbone, neck, bbox_head, teacher_config, output_feature=False, teacher_ckpt=None,
+                 eval_teacher=True, train_cfg=None, test_cfg=None, pretrained=None):
+        super().__init__(backbone, neck, bbox_head, train_cfg, test_cfg, pretrained)
+        self.eval_teacher = eval_teacher
+        self.output_feature = output_feature
+        if isinstance(teacher_config, str):
+            teacher_config = Config.fromfile(_resolve_config(teacher_config))
+        from .registry import build_detector
+        tmodel = teacher_config['model']
+        tmodel = tmodel.to_dict() if hasattr(tmodel, 'to_dict') else dict(tmodel)
+        from .config import ConfigDict
+        self.teacher_model = build_detector(ConfigDict(tmodel))
+        if teacher_ckpt is not None and os.path.isfile(str(teacher_ckpt)):
+            ckpt = torch.load(teacher_ckpt, map_location='cpu')
+            self.teacher_model.load_state_dict(ckpt.get('state_dict', ckpt), strict=False)
+        for p in self.teacher_model.parameters():
+            p.requires_grad = False
+
+    def forward_train(self, img, img_metas, gt_bboxes, gt_labels, gt_bboxes_ignore=None):
+        """kd_one_stage.py:46-81.  The stem's im2col operand is built once and shared by student and teacher."""
+        if not self.output_feature:
+            raise NotImplementedError('LDHead needs output_feature=True (kd_one_stage.py:73-76 mis-binds its '
+                                      'arguments otherwise; both COCO LD configs set it)')
+        im2col = ops.stem_im2col(img.float().contiguous())
+        x = self.extract_feat(img, im2col=im2col)
+        with torch.no_grad():
+            teacher_x = self.teacher_model.extract_feat(img, im2col=im2col)
+            out_teacher = self.teacher_model.bbox_head(teacher_x)
+        return self.bbox_head.forward_train(x, out_teacher, teacher_x, img_metas, gt_bboxes, gt_labels,
+                                            gt_bboxes_ignore)
+
+    def cuda(self, device=None):
+        self.teacher_model.cuda(device=device)
+        return super().cuda(device=device)
+
+    def to(self, *args, **kwargs):
+        self.teacher_model.to(*args, **kwargs)
+        return super().to(*args, **kwargs)
+
+    def train(self, mode=True):
+        if self.eval_teacher:
+            self.teacher_model.train(False)
+        else:
+            self.teacher_model.train(mode)
+        super().train(mode)
+        return self
+
+    def __setattr__(self, name, value):
+        """The teacher is a plain attribute: absent from parameters()/state_dict()/the gradient
+        all-reduce (kd_one_stage.py:97-108)."""
+        if name == 'teacher_model':
+            object.__setattr__(self, name, value)
+        else:
+            super().__setattr__(name, value)
+
+
+class LDTrainStep:
+    """One data-parallel LD training iteration on B200:
+
+        zero flat grad -> forward (student + teacher) -> fused loss -> backward -> ONE NCCL all-reduce of
+        the flat fp32 gradient buffer -> fused SGD(momentum, weight decay, linear warm-up) on the flat
+        parameter buffer.
+
+    Replaces MMDistributedDataParallel's bucketed all-reduce, mmcv OptimizerHook, LrUpdaterHook
+    (warm-up) and torch.optim.SGD (configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py:53,
+    configs/_base_/schedules/schedule_1x.py)."""
+
+    def __init__(self, model, lr=0.01, momentum=0.9, weight_decay=1e-4, warmup_iters=500, warmup_ratio=0.001):
+        self.model = model
+        self.base_lr, self.momentum, self.wd = lr, momentum, weight_decay
+        self.warmup_iters, self.warmup_ratio = warmup_iters, warmup_ratio
+        self.iter = 0
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.params = params
+        n = sum(p.numel() for p in params)
+        dev = params[0].device
+        self.flat_w = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(n, dtype=torch.float32, device=dev)
+        o = 0
+        for p in params:
+            k = p.numel()
+            if p.dim() == 4:   # conv weight: channels-last storage == packed operand layout
+                co, ci, kh, kw = p.shape
+                seg = self.flat_w[o:o + k].view(co, kh, kw, ci)
+                seg.copy_(p.data.permute(0, 2, 3, 1))
+                p.data = seg.permute(0, 3, 1, 2)
+                p.grad = self.flat_g[o:o + k].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+            else:
+                seg = self.flat_w[o:o + k].view(p.shape)
+                seg.copy_(p.data)
+                p.data = seg
+                p.grad = self.flat_g[o:o + k].view(p.shape)
+            o += k
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if self.world > 1:
+            dist.broadcast(self.flat_w, src=0)
+
+    def lr_at(self, it):
+        """mmcv LrUpdaterHook, warmup='linear': lr = base * (1 - (1 - it/warmup_iters) * (1 - ratio))."""
+        if it < self.warmup_iters:
+            k = (1 - it / self.warmup_iters) * (1 - self.warmup_ratio)
+            return self.base_lr * (1 - k)
+        return self.base_lr
+
+    def step(self, data, sync_logs=True):
+        self.flat_g.zero_()
+        losses = self.model(**data)
+        if sync_logs:
+            loss, log_vars = self.model._parse_losses(losses)
+        else:
+            loss = sum(sum(v) for k, v in losses.items() if 'loss' in k)
+            log_vars = None
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.flat_g)
+        ops.sgd_flat(self.flat_w, self.flat_g, self.flat_m, self.lr_at(self.iter), self.momentum, self.wd,
+                     1.0 / self.world, first_step=(self.iter == 0))
+        engine.clear_step_cache()
+        self.iter += 1
+        return loss.detach(), log_vars

@@ -1,0 +1,188 @@
+"""Autograd glue between the reference-shaped nn.Modules and the sm_100a kernels.
+
+Activations are NHWC bf16 tensors `[N, H, W, C]`.  Conv weights are ordinary `nn.Parameter`s of
+shape `[Cout, Cin, kh, kw]` (checkpoint-compatible with the reference) kept in channels_last
+memory, i.e. physically `[Cout, kh, kw, Cin]` -- which IS the K-major operand layout of the tcgen05
+kernels, so packing is a dtype cast and the fp32 weight gradient produced by the wgrad kernel is a
+zero-copy view with the parameter's own strides.
+
+Backward of `y = act(scale * conv(x, W) + shift + residual)`:
+    g        = dy * (y > 0)                       (relu_bwd kernel)
+    d_shift  = colsum(g)                          (conv bias / BN beta)
+    G        = wgrad(g, x)                        (tcgen05, fp32)
+    dW       = scale[co] * G ,  d_scale[co] = <W[co], G[co]>      (never needs the pre-BN conv output)
+    dx       = dgrad(g, (scale*W)^T)              (same tcgen05 kernel, mirrored taps; stride-2 convs as
+                                                   4 output-parity classes)
+    d_resid  = g  (or its nearest-upsample adjoint when the residual is a coarser FPN map)
+"""
+import torch
+
+from . import ops
+
+
+_step_cache = {}
+
+
+def clear_step_cache():
+    """Drop the bf16 operand copies of the weights (call after every optimizer step)."""
+    _step_cache.clear()
+
+
+def packed_weight(w):
+    """[Cout,Cin,kh,kw] channels_last fp32 -> [Cout, kh*kw*Cin] bf16 (a cast, no transpose)."""
+    key = ('fwd', id(w), w._version)
+    hit = _step_cache.get(key)
+    if hit is None:
+        co, ci, kh, kw = w.shape
+        hit = w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(torch.bfloat16)
+        _step_cache[key] = hit
+    return hit
+
+
+def as_channels_last_param(conv_weight):
+    """In-place: give an OIHW parameter channels_last storage (values unchanged)."""
+    conv_weight.data = conv_weight.data.contiguous(memory_format=torch.channels_last)
+    return conv_weight
+
+
+def _round64(c):
+    return (c + 63) // 64 * 64
+
+
+def dgrad_weight(w, scale):
+    """(scale*W) transposed for the data-gradient conv: [Cin, kh*kw*pad64(Cout)] bf16, zero padded."""
+    key = ('bwd', id(w), w._version, None if scale is None else (id(scale), scale._version))
+    hit = _step_cache.get(key)
+    if hit is not None:
+        return hit
+    co, ci, kh, kw = w.shape
+    ws = w.detach()
+    if scale is not None:
+        ws = ws * scale.detach().view(-1, 1, 1, 1)
+    t = ws.permute(1, 2, 3, 0)                       # [Cin, kh, kw, Cout]
+    cop = _round64(co)
+    if cop != co:
+        t = torch.nn.functional.pad(t, (0, cop - co))
+    hit = (t.reshape(ci, kh * kw * cop).to(torch.bfloat16).contiguous(), cop)
+    _step_cache[key] = hit
+    return hit
+
+
+def conv_dgrad(g, w, scale, stride, pad, in_hw, out=None, accumulate=False, mask=None, add=None):
+    """dx [N,H,W,Cin] bf16 = conv_transpose(g [N,HO,WO,Cout]) through ldb200_conv2d_tc."""
+    co, ci, kh, kw = w.shape
+    wd, cop = dgrad_weight(w, scale)
+    h, w_ = in_hw
+    n = g.shape[0]
+    if stride == 1:
+        taps = [(pad - s, pad - r, (r * kw + s) * cop) for r in range(kh) for s in range(kw)]
+        return ops.conv2d_tc(g, wd, ci, kh, kw, 1, pad, out=out, taps=taps, out_hw=(h, w_),
+                             accumulate=accumulate, mask=mask, add=add)
+    assert stride == 2 and mask is None and add is None
+    if out is None:   # parity classes write disjoint pixels; untouched ones (1x1 s2) must read as zero
+        out = torch.zeros(n, h, w_, ci, dtype=torch.bfloat16, device=g.device)
+        accumulate = False
+    for py in range(2):
+        for px in range(2):
+            taps = []
+            for r in range(kh):
+                if (py + pad - r) % 2:
+                    continue
+                for s in range(kw):
+                    if (px + pad - s) % 2:
+                        continue
+                    taps.append(((px + pad - s) // 2, (py + pad - r) // 2, (r * kw + s) * cop))
+            hp, wp = (h - py + 1) // 2, (w_ - px + 1) // 2
+            if not taps or hp <= 0 or wp <= 0:
+                continue
+            ops.conv2d_tc(g, wd, ci, kh, kw, 1, 0, out=out, taps=taps, out_hw=(hp, wp), flat=False,
+                          out_map=((h, w_), (2, py, 2, px)), accumulate=accumulate)
+    return out
+
+
+class ConvAffineAct(torch.autograd.Function):
+    """y = relu?(scale * conv(x, W) + shift + resample(residual))  -- one tcgen05 launch forward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, scale, shift, residual, stride, pad, relu, out, out_dtype):
+        co, ci, kh, kw = weight.shape
+        wp = packed_weight(weight)
+        y = ops.conv2d_tc(x, wp, co, kh, kw, stride, pad, out=out, out_dtype=out_dtype,
+                          scale=None if scale is None else scale.detach().contiguous(),
+                          bias=None if shift is None else shift.detach().contiguous(),
+                          add=residual, relu=relu)
+        ctx.cfg = (stride, pad, relu, residual is not None and tuple(residual.shape[1:3]) != tuple(y.shape[1:3]))
+        ctx.save_for_backward(x, weight, scale, shift, residual, y if relu else None)
+        if out is not None:
+            ctx.mark_dirty(out)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, scale, shift, residual, y = ctx.saved_tensors
+        stride, pad, relu, resampled = ctx.cfg
+        co, ci, kh, kw = weight.shape
+        need_x, need_w, need_scale, need_shift, need_res = ctx.needs_input_grad[:5]
+        if dy.dtype != torch.bfloat16:
+            # fp32 head outputs: gradients arrive from the fused loss kernel already in bf16 rows
+            dy = dy.to(torch.bfloat16)
+        dy = dy.contiguous()
+        g = ops.relu_bwd(dy, y) if relu else dy
+        d_x = d_w = d_scale = d_shift = d_res = None
+        if need_shift:
+            d_shift = torch.zeros(co, dtype=torch.float32, device=g.device)
+            ops.colsum(g.reshape(-1, g.shape[-1]), d_shift)
+        if need_w or need_scale:
+            G = torch.zeros(co, kh * kw * ci, dtype=torch.float32, device=g.device)
+            ops.conv2d_wgrad_tc(g, x, G, kh, kw, stride, pad)
+            if need_scale:
+                d_scale = (G * weight.detach().permute(0, 2, 3, 1).reshape(co, -1)).sum(1)
+            if need_w:
+                Gs = G if scale is None else G * scale.detach().view(-1, 1)
+                d_w = Gs.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+        if need_x:
+            d_x = conv_dgrad(g, weight, scale, stride, pad, x.shape[1:3])
+        if need_res:
+            if resampled:
+                d_res = ops.upsample_add_bwd(g, torch.zeros_like(residual))
+            else:
+                d_res = g
+        return d_x, d_w, d_scale, d_shift, d_res, None, None, None, None, None
+
+
+def conv_affine_act(x, weight, scale=None, shift=None, residual=None, stride=1, pad=0, relu=False,
+                    out=None, out_dtype=torch.bfloat16):
+    return ConvAffineAct.apply(x, weight, scale, shift, residual, stride, pad, relu, out, out_dtype)
+
+
+class GNReLU(torch.autograd.Function):
+    """y = relu(GroupNorm(x)) on NHWC bf16 (gfl_head.py:102-133 ConvModule norm+act)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps):
+        y, stats = ops.gn_relu_fwd(x, gamma.detach().contiguous(), beta.detach().contiguous(), groups, eps, True)
+        ctx.save_for_backward(x, y, stats, gamma)
+        ctx.cfg = (groups, eps)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, stats, gamma = ctx.saved_tensors
+        groups, eps = ctx.cfg
+        dg = torch.zeros_like(gamma, dtype=torch.float32)
+        db = torch.zeros_like(gamma, dtype=torch.float32)
+        dx = ops.gn_relu_bwd(dy.contiguous(), y, x, stats, gamma.detach().contiguous(), dg, db, groups, eps)
+        return dx, dg, db, None, None
+
+
+def gn_relu(x, gamma, beta, groups=32, eps=1e-5):
+    return GNReLU.apply(x, gamma, beta, groups, eps)
+
+
+def bn_affine(bn):
+    """Eval-mode BatchNorm (norm_eval=True, resnet.py:639-649) as a per-channel affine (scale, shift);
+    differentiable w.r.t. the (trainable) gamma / beta."""
+    rstd = torch.rsqrt(bn.running_var + bn.eps)
+    scale = bn.weight * rstd
+    shift = bn.bias - bn.running_mean * scale
+    return scale, shift

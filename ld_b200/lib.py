@@ -77,7 +77,7 @@ _SIGS = {
     'ldb200_ld_loss_prepass': (C.c_int, [C.POINTER(Pyramid), C.POINTER(LossCfg)] + [C.c_void_p] * 9),
     'ldb200_ld_loss_fused': (C.c_int, [C.POINTER(Pyramid), C.POINTER(LossCfg)] + [C.c_void_p] * 6 +
                              [C.c_int] + [C.c_void_p] * 9 + [C.c_void_p] + [C.c_void_p] * 4 +
-                             [C.c_int, C.c_void_p]),
+                             [C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ldb200_scatter_add_rows': (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ldb200_conv2d_tc': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     'ldb200_conv2d_wgrad_tc': (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),

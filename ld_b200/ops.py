@@ -126,7 +126,8 @@ def loss_normalisers(tg: LDTargets, wsum: torch.Tensor, group=None):
 
 
 def ld_loss_fused(cfg: L.LossCfg, cls, reg, t_cls, t_reg, x, t_x, tg: LDTargets, norm,
-                  term_grad: Optional[torch.Tensor] = None, grad_dtype=torch.float32, max_fg=None):
+                  term_grad: Optional[torch.Tensor] = None, grad_dtype=torch.float32, max_fg=None,
+                  d_cls_ld=0, d_reg_ld=0):
     """One launch: losses [9, MAX_LEVELS] (+ d_cls [R,C], d_reg [R,4*bins], d_im [max_fg,F] when
     `term_grad` ([8, MAX_LEVELS] host floats or True for all-ones) is given)."""
     lib = L.load()
@@ -144,15 +145,16 @@ def ld_loss_fused(cfg: L.LossCfg, cls, reg, t_cls, t_reg, x, t_x, tg: LDTargets,
         assert tgh.shape == (L.NUM_TERMS - 1, L.MAX_LEVELS)
         tgp = C.c_void_p(tgh.data_ptr())
         max_fg = R if max_fg is None else max_fg
-        d_cls = torch.empty(R, cfg.num_classes, dtype=grad_dtype, device=dev)
-        d_reg = torch.empty(R, 4 * (cfg.reg_max + 1), dtype=grad_dtype, device=dev)
+        d_cls = torch.empty(R, d_cls_ld or cfg.num_classes, dtype=grad_dtype, device=dev)
+        d_reg = torch.empty(R, d_reg_ld or 4 * (cfg.reg_max + 1), dtype=grad_dtype, device=dev)
         d_im = torch.empty(max_fg, cfg.feat_channels, dtype=grad_dtype, device=dev)
     L.check(lib.ldb200_ld_loss_fused(C.byref(tg.pyr), C.byref(cfg), L.ptr(cls), L.ptr(reg), L.ptr(t_cls),
                                      L.ptr(t_reg), L.ptr(x), L.ptr(t_x), _dt(x.dtype), L.ptr(tg.labels),
                                      L.ptr(tg.label_weights), L.ptr(tg.bbox_targets), L.ptr(tg.vlr), None,
                                      L.ptr(tg.sparse_rows), L.ptr(tg.fg_rows), L.ptr(tg.counts),
                                      L.ptr(norm), tgp, L.ptr(losses), L.ptr(d_cls), L.ptr(d_reg),
-                                     L.ptr(d_im), _dt(grad_dtype), L.stream_ptr()), 'ldb200_ld_loss_fused')
+                                     L.ptr(d_im), int(d_cls_ld), int(d_reg_ld), _dt(grad_dtype), L.stream_ptr()),
+            'ldb200_ld_loss_fused')
     return losses, d_cls, d_reg, d_im
 
 

@@ -1,0 +1,85 @@
+"""CPU: the reference's own config files load through ld_b200.Config and their `model` section builds
+UNCHANGED through the ld_b200 registries (build container only: needs /root/reference); the presets used
+on the GPU box are the same dictionaries."""
+import os
+
+import pytest
+import torch
+
+REF = '/root/reference'
+needs_ref = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'configs')), reason='reference tree absent')
+
+
+def _norm(d):
+    if isinstance(d, dict):
+        return {k: _norm(v) for k, v in d.items()}
+    if isinstance(d, (list, tuple)):
+        return [_norm(v) for v in d]
+    return d
+
+
+@needs_ref
+def test_reference_config_builds_unchanged(monkeypatch):
+    import ld_b200
+    from ld_b200 import presets
+    monkeypatch.chdir(REF)    # the reference resolves teacher_config relative to CWD (kd_one_stage.py:39-40)
+    cfg = ld_b200.Config.fromfile('configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py')
+    assert cfg.optimizer.lr == 0.0025 and cfg.data.samples_per_gpu == 2       # child overrides base
+    assert cfg.lr_config.warmup_iters == 500                                   # inherited through two levels
+    model = ld_b200.build_detector(cfg.model, train_cfg=cfg.get('train_cfg'), test_cfg=cfg.get('test_cfg'))
+    assert type(model).__name__ == 'KnowledgeDistillationSingleStageDetector'
+    assert type(model.bbox_head).__name__ == 'LDHead' and model.bbox_head.imitation_method == 'finegrained'
+    assert model.bbox_head.loss_im.loss_weight == 2.0 and model.bbox_head.loss_kd.T == 2
+    assert model.teacher_model.backbone.depth == 101 and model.backbone.depth == 50
+    assert 'teacher_model' not in dict(model.named_modules()) and not any('teacher' in k for k in model.state_dict())
+    n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    assert n_train == 32215193
+    # presets == the reference files
+    want = _norm(cfg.model.to_dict())
+    got = _norm(presets.ld_model('r50'))
+    for k in ('backbone', 'neck', 'bbox_head', 'train_cfg', 'test_cfg', 'output_feature', 'type'):
+        assert got[k] == want[k], k
+    tcfg = ld_b200.Config.fromfile('configs/gfl/gfl_r101_fpn_mstrain_2x_coco.py')
+    tw = _norm(tcfg.model.to_dict())
+    tg = _norm(presets.gfl_model(101))
+    for k in ('backbone', 'neck', 'bbox_head', 'train_cfg', 'test_cfg', 'type'):
+        assert tg[k] == tw[k], k
+
+
+@needs_ref
+def test_r18_config_and_registry_errors(monkeypatch):
+    import ld_b200
+    monkeypatch.chdir(REF)
+    cfg = ld_b200.Config.fromfile('configs/ld/ld_r18_gflv1_r101_fpn_coco_1x.py')
+    model = ld_b200.build_detector(cfg.model)
+    assert model.bbox_head.imitation_method == 'gibox'       # LDHead ctor default (ld_head.py:62)
+    with pytest.raises(KeyError):
+        ld_b200.build_loss(dict(type='NoSuchLoss'))
+    with pytest.raises(TypeError):
+        ld_b200.build_loss(dict(type='IMLoss', bogus=1))
+
+
+def test_state_dict_keys_match_oracle_port():
+    import ld_b200
+    from ld_b200 import presets
+    from ld_b200.config import ConfigDict
+    from oracle import ld_oracle as lo
+    m = ld_b200.build_detector(ConfigDict(presets.ld_model('r18', teacher_depth=18)))
+    o = lo.OracleLDDetector(18, 18)
+    assert set(m.state_dict()) == set(o.state_dict())
+    assert set(m.teacher_model.state_dict()) == set(o.teacher_model.state_dict())
+    for k, v in o.state_dict().items():
+        assert m.state_dict()[k].shape == v.shape, k
+    # frozen stem + layer1 (resnet.py:572-588), BN always eval (norm_eval)
+    m.train()
+    assert not m.backbone.conv1.weight.requires_grad and not m.backbone.layer1[0].conv1.weight.requires_grad
+    assert m.backbone.layer2[0].conv1.weight.requires_grad and not m.backbone.layer2[0].bn1.training
+    assert not m.teacher_model.training
+
+
+def test_warmup_schedule():
+    from ld_b200.detectors import LDTrainStep
+    s = LDTrainStep.__new__(LDTrainStep)
+    s.base_lr, s.warmup_iters, s.warmup_ratio = 0.01, 500, 0.001
+    assert abs(s.lr_at(0) - 0.01 * 0.001) < 1e-12 and abs(s.lr_at(250) - 0.01 * (1 - 0.5 * 0.999)) < 1e-12
+    assert s.lr_at(500) == 0.01
