@@ -222,6 +222,6 @@ class LDTrainStep:
             dist.all_reduce(self.flat_g)
         ops.sgd_flat(self.flat_w, self.flat_g, self.flat_m, self.lr_at(self.iter), self.momentum, self.wd,
                      1.0 / self.world, first_step=(self.iter == 0))
-        engine.clear_step_cache()
+        engine.clear_step_cache(self.params)
         self.iter += 1
         return loss.detach(), log_vars

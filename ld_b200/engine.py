@@ -20,23 +20,24 @@ import torch
 from . import ops
 
 
-_step_cache = {}
-
-
-def clear_step_cache():
-    """Drop the bf16 operand copies of the weights (call after every optimizer step)."""
-    _step_cache.clear()
+def clear_step_cache(params=()):
+    """Drop the bf16 operand copies cached on the parameters.  They are keyed by `_version`, which
+    torch bumps for in-place torch ops -- but the fused SGD kernel updates the flat parameter buffer
+    through raw pointers, so `LDTrainStep` invalidates them explicitly after every step."""
+    for p in params:
+        p.__dict__.pop('_ldb_packed', None)
+        p.__dict__.pop('_ldb_dgrad', None)
 
 
 def packed_weight(w):
-    """[Cout,Cin,kh,kw] channels_last fp32 -> [Cout, kh*kw*Cin] bf16 (a cast, no transpose)."""
-    key = ('fwd', id(w), w._version)
-    hit = _step_cache.get(key)
-    if hit is None:
+    """[Cout,Cin,kh,kw] channels_last fp32 -> [Cout, kh*kw*Cin] bf16 (a cast, no transpose).
+    Cached on the parameter (never in an id()-keyed dict: ids are reused after garbage collection)."""
+    hit = getattr(w, '_ldb_packed', None)
+    if hit is None or hit[0] != w._version or hit[1].device != w.device:
         co, ci, kh, kw = w.shape
-        hit = w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(torch.bfloat16)
-        _step_cache[key] = hit
-    return hit
+        hit = (w._version, w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(torch.bfloat16))
+        w._ldb_packed = hit
+    return hit[1]
 
 
 def as_channels_last_param(conv_weight):
@@ -51,10 +52,10 @@ def _round64(c):
 
 def dgrad_weight(w, scale):
     """(scale*W) transposed for the data-gradient conv: [Cin, kh*kw*pad64(Cout)] bf16, zero padded."""
-    key = ('bwd', id(w), w._version, None if scale is None else (id(scale), scale._version))
-    hit = _step_cache.get(key)
-    if hit is not None:
-        return hit
+    if scale is None:   # level-shared head convs: reuse across the five levels of one backward pass
+        hit = getattr(w, '_ldb_dgrad', None)
+        if hit is not None and hit[0] == w._version and hit[1][0].device == w.device:
+            return hit[1]
     co, ci, kh, kw = w.shape
     ws = w.detach()
     if scale is not None:
@@ -63,9 +64,10 @@ def dgrad_weight(w, scale):
     cop = _round64(co)
     if cop != co:
         t = torch.nn.functional.pad(t, (0, cop - co))
-    hit = (t.reshape(ci, kh * kw * cop).to(torch.bfloat16).contiguous(), cop)
-    _step_cache[key] = hit
-    return hit
+    out = (t.reshape(ci, kh * kw * cop).to(torch.bfloat16).contiguous(), cop)
+    if scale is None:
+        w._ldb_dgrad = (w._version, out)
+    return out
 
 
 def conv_dgrad(g, w, scale, stride, pad, in_hw, out=None, accumulate=False, mask=None, add=None):
@@ -100,6 +102,14 @@ def conv_dgrad(g, w, scale, stride, pad, in_hw, out=None, accumulate=False, mask
     return out
 
 
+class OutSlot:
+    """Pre-allocated output view (e.g. a level slice of a row-space buffer) handed to a Function as a
+    non-tensor argument: autograd then sees an ordinary fresh output, not an in-place write into a view."""
+
+    def __init__(self, t):
+        self.t = t
+
+
 class ConvAffineAct(torch.autograd.Function):
     """y = relu?(scale * conv(x, W) + shift + resample(residual))  -- one tcgen05 launch forward."""
 
@@ -107,14 +117,12 @@ class ConvAffineAct(torch.autograd.Function):
     def forward(ctx, x, weight, scale, shift, residual, stride, pad, relu, out, out_dtype):
         co, ci, kh, kw = weight.shape
         wp = packed_weight(weight)
-        y = ops.conv2d_tc(x, wp, co, kh, kw, stride, pad, out=out, out_dtype=out_dtype,
+        y = ops.conv2d_tc(x, wp, co, kh, kw, stride, pad, out=None if out is None else out.t, out_dtype=out_dtype,
                           scale=None if scale is None else scale.detach().contiguous(),
                           bias=None if shift is None else shift.detach().contiguous(),
                           add=residual, relu=relu)
         ctx.cfg = (stride, pad, relu, residual is not None and tuple(residual.shape[1:3]) != tuple(y.shape[1:3]))
         ctx.save_for_backward(x, weight, scale, shift, residual, y if relu else None)
-        if out is not None:
-            ctx.mark_dirty(out)
         return y
 
     @staticmethod
@@ -152,7 +160,8 @@ class ConvAffineAct(torch.autograd.Function):
 
 def conv_affine_act(x, weight, scale=None, shift=None, residual=None, stride=1, pad=0, relu=False,
                     out=None, out_dtype=torch.bfloat16):
-    return ConvAffineAct.apply(x, weight, scale, shift, residual, stride, pad, relu, out, out_dtype)
+    return ConvAffineAct.apply(x, weight, scale, shift, residual, stride, pad, relu,
+                               None if out is None else OutSlot(out), out_dtype)
 
 
 class GNReLU(torch.autograd.Function):
