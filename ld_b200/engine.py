@@ -191,7 +191,17 @@ def gn_relu(x, gamma, beta, groups=32, eps=1e-5):
 def bn_affine(bn):
     """Eval-mode BatchNorm (norm_eval=True, resnet.py:639-649) as a per-channel affine (scale, shift);
     differentiable w.r.t. the (trainable) gamma / beta."""
+    frozen = not (bn.weight.requires_grad or bn.bias.requires_grad)
+    if frozen:
+        key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+               bn.weight.device)
+        hit = bn.__dict__.get('_ldb_affine')
+        if hit is not None and hit[0] == key:
+            return hit[1]
     rstd = torch.rsqrt(bn.running_var + bn.eps)
     scale = bn.weight * rstd
     shift = bn.bias - bn.running_mean * scale
+    if frozen:
+        scale, shift = scale.detach().contiguous(), shift.detach().contiguous()
+        bn.__dict__['_ldb_affine'] = (key, (scale, shift))
     return scale, shift

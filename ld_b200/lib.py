@@ -123,7 +123,18 @@ def load():
     return lib
 
 
+# kernels launched by one call of each entry point (memsets not counted); `launch_count` is what
+# bench.py reports as "gpu_launches"
+_LAUNCHES = {'ldb200_ld_targets': 3, 'ldb200_ld_loss_prepass': 1, 'ldb200_ld_loss_fused': 1,
+             'ldb200_scatter_add_rows': 1, 'ldb200_conv2d_tc': 1, 'ldb200_conv2d_wgrad_tc': 1,
+             'ldb200_stem_im2col': 1, 'ldb200_maxpool3x3s2': 1, 'ldb200_gn_stats': 1, 'ldb200_gn_apply': 1,
+             'ldb200_gn_relu_bwd': 2, 'ldb200_upsample_add_bwd': 1, 'ldb200_relu_bwd': 1, 'ldb200_colsum': 1,
+             'ldb200_sgd_flat': 1, 'ldb200_kl_dense_fwd_bwd': 1}
+launch_count = {'n': 0}
+
+
 def check(code, what=''):
+    launch_count['n'] += _LAUNCHES.get(what, 0)
     if code != 0:
         msg = load().ldb200_last_error().decode(errors='replace')
         raise LdB200Error(f'{what} failed with code {code}: {msg}')
