@@ -49,7 +49,8 @@ struct ConvParams {
   int mask_ld;
   int relu;
   int accumulate;           // result += previous out (before ReLU / mask)
-  int vec_ok;               // output rows 16-byte aligned -> vector stores
+  int vec_ok;               // leading dimensions allow 4-channel vector accesses
+  int tw_shift;             // log2(TW)
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -123,9 +124,15 @@ __device__ __forceinline__ uint64_t smem_desc_k128(uint32_t saddr) {
 template <int BN> struct ConvCfg {
   static constexpr int B_TILE_BYTES = BN * KCH * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 5 : 7);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // epilogue staging: each epilogue warp owns 32 rows x HALF fp32 columns (+16 B row padding: conflict-free
+  // 16-byte accesses), written row-per-lane from TMEM and read back row-per-instruction so that global
+  // loads/stores of a warp cover one contiguous output row segment
+  static constexpr int HALF = BN < 128 ? BN : 128;
+  static constexpr int ROW_BYTES = HALF * 4 + 16;
+  static constexpr int STAGING_BYTES = 4 * 32 * ROW_BYTES;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=BN, M=128
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                     ((uint32_t)(TILE_M >> 4) << 24);
@@ -141,7 +148,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using Cfg = ConvCfg<BN>;
   extern __shared__ unsigned char conv_smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)conv_smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+  unsigned char* staging = smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = (uint64_t*)(staging + Cfg::STAGING_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;
   uint64_t* tfull = bars + 2 * Cfg::STAGES;
@@ -233,6 +241,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     // ===================================== epilogue ==========================================
     const int ew = warp - 4;   // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+    unsigned char* stg = staging + (size_t)ew * 32 * Cfg::ROW_BYTES;
+    const uint32_t stg_u = s2u(stg);
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -243,111 +253,118 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       sp /= p.tiles_x;
       const int ty = sp % p.tiles_y;
       const int n = sp / p.tiles_y;
-      const int m = ew * 32 + lane;
-      const int y = ty * p.TH + m / p.TW, x = tx * p.TW + m % p.TW;
-      const bool pix_ok = (y < p.HO) && (x < p.WO);
-      const size_t pix = pix_ok ? out_offset(p, n, y, x) : 0;
-      size_t add_pix = 0;
-      if (p.add_src && pix_ok) {
-        const int ay = (int)(((long long)y * p.add_H) / p.HO), ax = (int)(((long long)x * p.add_W) / p.WO);
-        add_pix = (((size_t)n * p.add_H + ay) * p.add_W + ax) * (size_t)p.add_ld;
-      }
       mbarrier_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        const int cbase = nt * BN + ch * 32;
-        if (cbase >= p.Cout) break;   // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + ch * 32), r);
-        if (pix_ok) {
-          float v[32];
+      for (int h = 0; h < BN / Cfg::HALF; ++h) {
+        const int hbase = nt * BN + h * Cfg::HALF;     // first output channel of this pass
+        if (hbase < p.Cout) {
+          // ---- phase 1: TMEM -> registers -> staging (lane = tile row, raw fp32 accumulators)
+#pragma unroll 1
+          for (int ch = 0; ch < Cfg::HALF / 32; ++ch) {
+            if (hbase + ch * 32 >= p.Cout) break;
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + h * Cfg::HALF + ch * 32), r);
+            const uint32_t dst = stg_u + (uint32_t)lane * Cfg::ROW_BYTES + (uint32_t)ch * 128;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.scale) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cbase + j < p.Cout) v[j] *= __ldg(p.scale + cbase + j);
-          }
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cbase + j < p.Cout) v[j] += __ldg(p.bias + cbase + j);
-          }
-          if (p.add_src) {
-            const __nv_bfloat16* a = p.add_src + add_pix + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (cbase + j + 8 <= p.Cout) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(a + j));
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(h[e]);
-                  v[j + 2 * e] += f.x;
-                  v[j + 2 * e + 1] += f.y;
-                }
-              } else {
-                for (int e = 0; e < 8; ++e)
-                  if (cbase + j + e < p.Cout) v[j + e] += __bfloat162float(a[j + e]);
-              }
-            }
-          }
-          if (p.accumulate) {
-            if (p.out_f32) {
-              const float* o = (const float*)p.out + pix * (size_t)p.ldc + cbase;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (cbase + j < p.Cout) v[j] += o[j];
-            } else {
-              const __nv_bfloat16* o = (const __nv_bfloat16*)p.out + pix * (size_t)p.ldc + cbase;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (cbase + j < p.Cout) v[j] += __bfloat162float(o[j]);
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (p.mask_src) {
-            const __nv_bfloat16* mk = p.mask_src + pix * (size_t)p.mask_ld + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cbase + j < p.Cout && !(__bfloat162float(mk[j]) > 0.f)) v[j] = 0.f;
-          }
-          if (p.out_f32) {
-            float* o = (float*)p.out + pix * (size_t)p.ldc + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (p.vec_ok && cbase + j + 4 <= p.Cout) {
-                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              } else {
-                for (int e = 0; e < 4; ++e)
-                  if (cbase + j + e < p.Cout) o[j + e] = v[j + e];
-              }
-            }
-          } else {
-            __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * (size_t)p.ldc + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (p.vec_ok && cbase + j + 8 <= p.Cout) {
-                uint4 q;
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-                *reinterpret_cast<uint4*>(o + j) = q;
-              } else {
-                for (int e = 0; e < 8; ++e)
-                  if (cbase + j + e < p.Cout) o[j + e] = __float2bfloat16_rn(v[j + e]);
-              }
-            }
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + j * 4), "r"(r[j]), "r"(r[j + 1]),
+                           "r"(r[j + 2]), "r"(r[j + 3]) : "memory");
           }
         }
+        if (h == BN / Cfg::HALF - 1) {
+          // all accumulator columns of this tile are out of TMEM: hand the stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbarrier_arrive(&tempty[acc]);
+        } else {
+          __syncwarp();
+        }
+        if (hbase < p.Cout) {
+          // ---- phase 2: one tile row per instruction, lane = 4 consecutive channels (coalesced)
+          // HALF/4 lanes cover one row; with HALF = 64 a warp instruction covers two tile rows
+          constexpr int LPR = Cfg::HALF / 4, RPI = 32 / LPR;
+          const int cl = lane % LPR, rsub = lane / LPR;
+          const int c0 = hbase + cl * 4;
+          const bool c_any = c0 < p.Cout, c_all = c0 + 4 <= p.Cout && p.vec_ok;
+          float sc[4] = {1.f, 1.f, 1.f, 1.f}, bi[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (c0 + e < p.Cout) {
+              if (p.scale) sc[e] = __ldg(p.scale + c0 + e);
+              if (p.bias) bi[e] = __ldg(p.bias + c0 + e);
+            }
+          }
+          if (c_any) {
+#pragma unroll 4
+            for (int ii = 0; ii < 32 / RPI; ++ii) {
+              const int i = ii * RPI + rsub;
+              const int m = ew * 32 + i;
+              const int y = ty * p.TH + (m >> p.tw_shift), x = tx * p.TW + (m & (p.TW - 1));
+              if (y >= p.HO || x >= p.WO) continue;
+              const size_t pix = out_offset(p, n, y, x);
+              float4 a4;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
+                           : "r"(stg_u + (uint32_t)i * Cfg::ROW_BYTES + (uint32_t)cl * 16));
+              float v[4] = {a4.x * sc[0] + bi[0], a4.y * sc[1] + bi[1], a4.z * sc[2] + bi[2], a4.w * sc[3] + bi[3]};
+              if (p.add_src) {
+                const int ay = (int)(((long long)y * p.add_H) / p.HO), ax = (int)(((long long)x * p.add_W) / p.WO);
+                const __nv_bfloat16* a = p.add_src + (((size_t)n * p.add_H + ay) * p.add_W + ax) * (size_t)p.add_ld + c0;
+                if (c_all && (p.add_ld & 3) == 0) {
+                  const uint2 q = __ldg(reinterpret_cast<const uint2*>(a));
+                  const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+                  const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+                  v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
+                } else {
+                  for (int e = 0; e < 4; ++e)
+                    if (c0 + e < p.Cout) v[e] += __bfloat162float(a[e]);
+                }
+              }
+              if (p.accumulate) {
+                if (p.out_f32) {
+                  const float* o = (const float*)p.out + pix * (size_t)p.ldc + c0;
+                  for (int e = 0; e < 4; ++e)
+                    if (c0 + e < p.Cout) v[e] += o[e];
+                } else {
+                  const __nv_bfloat16* o = (const __nv_bfloat16*)p.out + pix * (size_t)p.ldc + c0;
+                  for (int e = 0; e < 4; ++e)
+                    if (c0 + e < p.Cout) v[e] += __bfloat162float(o[e]);
+                }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+              }
+              if (p.mask_src) {
+                const __nv_bfloat16* mk = p.mask_src + pix * (size_t)p.mask_ld + c0;
+                for (int e = 0; e < 4; ++e)
+                  if (c0 + e < p.Cout && !(__bfloat162float(mk[e]) > 0.f)) v[e] = 0.f;
+              }
+              if (p.out_f32) {
+                float* o = (float*)p.out + pix * (size_t)p.ldc + c0;
+                if (c_all) {
+                  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+                  for (int e = 0; e < 4; ++e)
+                    if (c0 + e < p.Cout) o[e] = v[e];
+                }
+              } else {
+                __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * (size_t)p.ldc + c0;
+                if (c_all) {
+                  uint2 q;
+                  *reinterpret_cast<__nv_bfloat162*>(&q.x) = __floats2bfloat162_rn(v[0], v[1]);
+                  *reinterpret_cast<__nv_bfloat162*>(&q.y) = __floats2bfloat162_rn(v[2], v[3]);
+                  *reinterpret_cast<uint2*>(o) = q;
+                } else {
+                  for (int e = 0; e < 4; ++e)
+                    if (c0 + e < p.Cout) o[e] = __float2bfloat16_rn(v[e]);
+                }
+              }
+            }
+          }
+          __syncwarp();   // staging is rewritten by the next pass / tile
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbarrier_arrive(&tempty[acc]);
     }
   }
   tc_fence_before();
@@ -604,7 +621,7 @@ extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
   LDB_REQUIRE(d->out_ld >= d->Cout, LDB_EINVAL, "conv2d_tc: out_ld < Cout");
   LDB_REQUIRE(((uintptr_t)d->in & 15) == 0 && ((uintptr_t)d->weight & 15) == 0 && ((uintptr_t)d->out & 15) == 0,
               LDB_EINVAL, "conv2d_tc: pointers must be 16-byte aligned");
-  const int vec_ok = d->out_ld % (d->out_f32 ? 4 : 8) == 0;
+  const int vec_ok = d->out_ld % 4 == 0 && (!d->mask_src || true);
   cudaStream_t stream = (cudaStream_t)stream_;
   ConvParams p;
   memset(&p, 0, sizeof(p));
@@ -664,6 +681,8 @@ extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
   }
   p.tiles_y = (p.HO + p.TH - 1) / p.TH;
   p.tiles_x = (p.WO + p.TW - 1) / p.TW;
+  p.tw_shift = 0;
+  while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
   const int BN = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
   p.tiles_n = (d->Cout + BN - 1) / BN;
   {

@@ -30,29 +30,34 @@ __device__ __forceinline__ uint4 pack8(const float v[8]) {
 // ---------------------------------------------------------------------------------------------
 // Stem: 7x7 stride-2 pad-3 conv on a 3-channel NCHW fp32 image as a GEMM: A[pixel, (r*7+s)*3+c],
 // K = 147 zero-padded to 192 (3 x 64) so the tcgen05 kernel can consume it in flat mode.
-__global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int H,
-                                   int W, int HO, int WO) {
-  const long long total = (long long)N * HO * WO * 24;  // 24 groups of 8 columns = 192
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int grp = (int)(t % 24);
-    const long long pix = t / 24;
-    const int xo = (int)(pix % WO);
-    const int yo = (int)((pix / WO) % HO);
-    const int n = (int)(pix / ((long long)WO * HO));
+// One block = 64 consecutive output pixels of one output row: the 3 x 7 x 133 input patch is staged in
+// shared memory with coalesced loads, every thread then emits 16-byte (8-column) pieces of the rows.
+constexpr int IM_PX = 64;
+constexpr int IM_COLS = 2 * IM_PX + 5;   // input columns touched by 64 outputs
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int H, int W, int HO, int WO) {
+  __shared__ float tile[3][7][IM_COLS + 1];
+  const int xo0 = blockIdx.x * IM_PX, yo = blockIdx.y, n = blockIdx.z;
+  const int xi0 = xo0 * 2 - 3, yi0 = yo * 2 - 3;
+  for (int i = threadIdx.x; i < 3 * 7 * IM_COLS; i += 256) {
+    const int xx = i % IM_COLS, r = (i / IM_COLS) % 7, c = i / (IM_COLS * 7);
+    const int y = yi0 + r, x = xi0 + xx;
+    float v = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(img + (((size_t)n * 3 + c) * H + y) * W + x);
+    tile[c][r][xx] = v;
+  }
+  __syncthreads();
+  const int npx = min(IM_PX, WO - xo0);
+  uint4* orow = reinterpret_cast<uint4*>(out + (((size_t)n * HO + yo) * WO + xo0) * 192);
+  for (int j = threadIdx.x; j < npx * 24; j += 256) {
+    const int px = j / 24, grp = j % 24;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int k = grp * 8 + e;
-      float val = 0.f;
-      if (k < 147) {
-        const int c = k % 3, rs = k / 3, s = rs % 7, r = rs / 7;
-        const int y = yo * 2 - 3 + r, x = xo * 2 - 3 + s;
-        if (y >= 0 && y < H && x >= 0 && x < W) val = __ldg(img + (((size_t)n * 3 + c) * H + y) * W + x);
-      }
-      v[e] = val;
+      v[e] = (k < 147) ? tile[k % 3][k / 21][px * 2 + (k / 3) % 7] : 0.f;
     }
-    reinterpret_cast<uint4*>(out)[t] = pack8(v);
+    orow[j] = pack8(v);
   }
 }
 
@@ -317,7 +322,23 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
     if (ty < rows_par) {
-      for (long long m = m0 + ty; m < m1; m += rows_par) {
+      long long m = m0 + ty;
+      if (sizeof(T) == 2) {
+        for (; m + 3LL * rows_par < m1; m += 4LL * rows_par) {   // 4 independent 16-byte loads in flight
+          uint4 q[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            q[u] = __ldg(reinterpret_cast<const uint4*>((const __nv_bfloat16*)x + (size_t)(m + (long long)u * rows_par) * ld) + g);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float v[8];
+            unpack8(q[u], v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += v[e];
+          }
+        }
+      }
+      for (; m < m1; m += rows_par) {
         if (sizeof(T) == 2) {
           float v[8];
           unpack8(__ldg(reinterpret_cast<const uint4*>((const __nv_bfloat16*)x + (size_t)m * ld) + g), v);
@@ -369,8 +390,8 @@ using namespace ldb;
 extern "C" int ldb200_stem_im2col(const float* img, void* out, int N, int H, int W, void* stream_) {
   LDB_REQUIRE(img && out && N > 0 && H > 0 && W > 0, LDB_EINVAL, "stem_im2col: bad argument");
   const int HO = (H + 6 - 7) / 2 + 1, WO = (W + 6 - 7) / 2 + 1;
-  const long long total = (long long)N * HO * WO * 24;
-  stem_im2col_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream_>>>(img, (__nv_bfloat16*)out, N, H, W, HO, WO);
+  dim3 grid((WO + IM_PX - 1) / IM_PX, HO, N);
+  stem_im2col_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(img, (__nv_bfloat16*)out, N, H, W, HO, WO);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -457,8 +478,8 @@ extern "C" int ldb200_relu_bwd(const void* dy, const void* y, void* out, int64_t
 extern "C" int ldb200_colsum(const void* x, float* out, int64_t rows, int C, int ld, int dtype, void* stream_) {
   LDB_REQUIRE(x && out && rows >= 0 && C > 0 && ld >= C, LDB_EINVAL, "colsum: bad argument");
   if (rows == 0) return 0;
-  int grid = (int)((rows + 511) / 512);
-  if (grid > 148 * 4) grid = 148 * 4;
+  int grid = (int)((rows + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
   if (dtype == LDB_BF16) {
     LDB_REQUIRE(C % 8 == 0 && ld % 8 == 0, LDB_EINVAL, "colsum: bf16 needs C, ld %% 8 == 0");
     colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, out, rows, C, ld);
