@@ -124,7 +124,8 @@ __device__ __forceinline__ uint64_t smem_desc_k128(uint32_t saddr) {
 template <int BN> struct ConvCfg {
   static constexpr int B_TILE_BYTES = BN * KCH * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 5 : 7);
+  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 4 : 7);
+  static_assert((size_t)STAGES * STAGE_BYTES + 4 * 32 * ((BN < 128 ? BN : 128) * 4 + 16) + 1280 <= 232448, "smem budget");
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   // epilogue staging: each epilogue warp owns 32 rows x HALF fp32 columns (+16 B row padding: conflict-free
   // 16-byte accesses), written row-per-lane from TMEM and read back row-per-instruction so that global
