@@ -25,7 +25,8 @@
 
 namespace ldb {
 
-constexpr int CONV_THREADS = 256;
+constexpr int CONV_THREADS = 256;       // wgrad kernel
+constexpr int CONV_FWD_THREADS = 384;   // 4 control warps + 8 epilogue warps
 constexpr int TILE_M = 128;
 constexpr int KCH = 64;                        // channels per k-block (128 B of bf16)
 constexpr int A_TILE_BYTES = TILE_M * KCH * 2;  // 16 KB
@@ -109,6 +110,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO), version 1, layout type 2.
 __device__ __forceinline__ uint64_t smem_desc_k128(uint32_t saddr) {
@@ -124,16 +138,10 @@ __device__ __forceinline__ uint64_t smem_desc_k128(uint32_t saddr) {
 template <int BN> struct ConvCfg {
   static constexpr int B_TILE_BYTES = BN * KCH * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 4 : 7);
-  static_assert((size_t)STAGES * STAGE_BYTES + 4 * 32 * ((BN < 128 ? BN : 128) * 4 + 16) + 1280 <= 232448, "smem budget");
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  // epilogue staging: each epilogue warp owns 32 rows x HALF fp32 columns (+16 B row padding: conflict-free
-  // 16-byte accesses), written row-per-lane from TMEM and read back row-per-instruction so that global
-  // loads/stores of a warp cover one contiguous output row segment
-  static constexpr int HALF = BN < 128 ? BN : 128;
-  static constexpr int ROW_BYTES = HALF * 4 + 16;
-  static constexpr int STAGING_BYTES = 4 * 32 * ROW_BYTES;
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = 0;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=BN, M=128
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                     ((uint32_t)(TILE_M >> 4) << 24);
@@ -144,7 +152,7 @@ __device__ __forceinline__ size_t out_offset(const ConvParams& p, int n, int y, 
 }
 
 template <int BN>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(CONV_FWD_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
   using Cfg = ConvCfg<BN>;
   extern __shared__ unsigned char conv_smem_raw[];
@@ -169,7 +177,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbarrier_init(&tfull[a], 1);
-      mbarrier_init(&tempty[a], 4);   // one arrive per epilogue warp
+      mbarrier_init(&tempty[a], 8);   // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -241,9 +249,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================================== epilogue ==========================================
-    const int ew = warp - 4;   // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
-    unsigned char* stg = staging + (size_t)ew * 32 * Cfg::ROW_BYTES;
-    const uint32_t stg_u = s2u(stg);
+    // 8 warps (two per SM sub-partition, so ALU/TMEM-load latency of one is hidden by the other): warp w
+    // reads TMEM lanes [32*(w%4), +32) = 32 tile rows, and half of the tile's BN columns.  Per 32-column
+    // chunk: tcgen05.ld (software-pipelined one chunk ahead), per-channel scale/bias (float4 loads),
+    // residual / accumulate / ReLU / mask, 16-byte stores along the thread's own output row.
+    const int ew = warp & 3, half = (warp - 4) >> 2;
+    constexpr int NCH = BN / 64;                    // 32-column chunks per warp
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -254,118 +265,138 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       sp /= p.tiles_x;
       const int ty = sp % p.tiles_y;
       const int n = sp / p.tiles_y;
+      const int m = ew * 32 + lane;
+      const int y = ty * p.TH + (m >> p.tw_shift), x = tx * p.TW + (m & (p.TW - 1));
+      const bool pix_ok = (y < p.HO) && (x < p.WO);
+      const size_t pix = pix_ok ? out_offset(p, n, y, x) : 0;
+      const __nv_bfloat16* addp = nullptr;
+      if (p.add_src && pix_ok) {
+        const int ay = (int)(((long long)y * p.add_H) / p.HO), ax = (int)(((long long)x * p.add_W) / p.WO);
+        addp = p.add_src + (((size_t)n * p.add_H + ay) * p.add_W + ax) * (size_t)p.add_ld;
+      }
+      const int col0 = nt * BN + half * (BN / 2);
+      const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
       mbarrier_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int h = 0; h < BN / Cfg::HALF; ++h) {
-        const int hbase = nt * BN + h * Cfg::HALF;     // first output channel of this pass
-        if (hbase < p.Cout) {
-          // ---- phase 1: TMEM -> registers -> staging (lane = tile row, raw fp32 accumulators)
-#pragma unroll 1
-          for (int ch = 0; ch < Cfg::HALF / 32; ++ch) {
-            if (hbase + ch * 32 >= p.Cout) break;
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + h * Cfg::HALF + ch * 32), r);
-            const uint32_t dst = stg_u + (uint32_t)lane * Cfg::ROW_BYTES + (uint32_t)ch * 128;
+      uint32_t rbuf[2][32];
+      if (col0 < p.Cout) tmem_ld32_nowait(tbase, rbuf[0]);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + j * 4), "r"(r[j]), "r"(r[j + 1]),
-                           "r"(r[j + 2]), "r"(r[j + 3]) : "memory");
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int cbase = col0 + ch * 32;
+        if (cbase >= p.Cout) break;   // warp-uniform
+        tmem_ld_wait();
+        if (ch + 1 < NCH && cbase + 32 < p.Cout) tmem_ld32_nowait(tbase + (ch + 1) * 32, rbuf[(ch + 1) & 1]);
+        const uint32_t* r = rbuf[ch & 1];
+        if (!pix_ok) continue;
+        const bool full = (cbase + 32 <= p.Cout) && p.vec_ok;   // warp-uniform fast path
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (full) {
+          if (p.scale) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + cbase + j));
+              v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+            }
           }
-        }
-        if (h == BN / Cfg::HALF - 1) {
-          // all accumulator columns of this tile are out of TMEM: hand the stage back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbarrier_arrive(&tempty[acc]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+          if (addp) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(addp + cbase + j));
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(hh[e]);
+                v[j + 2 * e] += f.x;
+                v[j + 2 * e + 1] += f.y;
+              }
+            }
+          }
+          if (p.accumulate) {
+            if (p.out_f32) {
+              const float* o = (const float*)p.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 o4 = *reinterpret_cast<const float4*>(o + j);
+                v[j] += o4.x; v[j + 1] += o4.y; v[j + 2] += o4.z; v[j + 3] += o4.w;
+              }
+            } else {
+              const __nv_bfloat16* o = (const __nv_bfloat16*)p.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 q = *reinterpret_cast<const uint4*>(o + j);
+                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(hh[e]);
+                  v[j + 2 * e] += f.x;
+                  v[j + 2 * e + 1] += f.y;
+                }
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.mask_src) {
+            const __nv_bfloat16* mk = p.mask_src + pix * (size_t)p.mask_ld + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(mk + j));
+              const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (!(__bfloat162float(hb[e]) > 0.f)) v[j + e] = 0.f;
+            }
+          }
+          if (p.out_f32) {
+            float* o = (float*)p.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 q;
+              __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(o + j) = q;
+            }
+          }
         } else {
-          __syncwarp();
-        }
-        if (hbase < p.Cout) {
-          // ---- phase 2: one tile row per instruction, lane = 4 consecutive channels (coalesced)
-          // HALF/4 lanes cover one row; with HALF = 64 a warp instruction covers two tile rows
-          constexpr int LPR = Cfg::HALF / 4, RPI = 32 / LPR;
-          const int cl = lane % LPR, rsub = lane / LPR;
-          const int c0 = hbase + cl * 4;
-          const bool c_any = c0 < p.Cout, c_all = c0 + 4 <= p.Cout && p.vec_ok;
-          float sc[4] = {1.f, 1.f, 1.f, 1.f}, bi[4] = {0.f, 0.f, 0.f, 0.f};
+          // ragged tail (Cout not a multiple of 32, or unaligned leading dimension): scalar path
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (c0 + e < p.Cout) {
-              if (p.scale) sc[e] = __ldg(p.scale + c0 + e);
-              if (p.bias) bi[e] = __ldg(p.bias + c0 + e);
-            }
+          for (int j = 0; j < 32; ++j) {
+            const int c = cbase + j;
+            if (c >= p.Cout) continue;
+            float vv = v[j];
+            if (p.scale) vv *= __ldg(p.scale + c);
+            if (p.bias) vv += __ldg(p.bias + c);
+            if (addp) vv += __bfloat162float(addp[c]);
+            if (p.accumulate)
+              vv += p.out_f32 ? ((const float*)p.out)[pix * (size_t)p.ldc + c]
+                              : __bfloat162float(((const __nv_bfloat16*)p.out)[pix * (size_t)p.ldc + c]);
+            if (p.relu) vv = fmaxf(vv, 0.f);
+            if (p.mask_src && !(__bfloat162float(p.mask_src[pix * (size_t)p.mask_ld + c]) > 0.f)) vv = 0.f;
+            if (p.out_f32) ((float*)p.out)[pix * (size_t)p.ldc + c] = vv;
+            else ((__nv_bfloat16*)p.out)[pix * (size_t)p.ldc + c] = __float2bfloat16_rn(vv);
           }
-          if (c_any) {
-#pragma unroll 4
-            for (int ii = 0; ii < 32 / RPI; ++ii) {
-              const int i = ii * RPI + rsub;
-              const int m = ew * 32 + i;
-              const int y = ty * p.TH + (m >> p.tw_shift), x = tx * p.TW + (m & (p.TW - 1));
-              if (y >= p.HO || x >= p.WO) continue;
-              const size_t pix = out_offset(p, n, y, x);
-              float4 a4;
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
-                           : "r"(stg_u + (uint32_t)i * Cfg::ROW_BYTES + (uint32_t)cl * 16));
-              float v[4] = {a4.x * sc[0] + bi[0], a4.y * sc[1] + bi[1], a4.z * sc[2] + bi[2], a4.w * sc[3] + bi[3]};
-              if (p.add_src) {
-                const int ay = (int)(((long long)y * p.add_H) / p.HO), ax = (int)(((long long)x * p.add_W) / p.WO);
-                const __nv_bfloat16* a = p.add_src + (((size_t)n * p.add_H + ay) * p.add_W + ax) * (size_t)p.add_ld + c0;
-                if (c_all && (p.add_ld & 3) == 0) {
-                  const uint2 q = __ldg(reinterpret_cast<const uint2*>(a));
-                  const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
-                  const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
-                  v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
-                } else {
-                  for (int e = 0; e < 4; ++e)
-                    if (c0 + e < p.Cout) v[e] += __bfloat162float(a[e]);
-                }
-              }
-              if (p.accumulate) {
-                if (p.out_f32) {
-                  const float* o = (const float*)p.out + pix * (size_t)p.ldc + c0;
-                  for (int e = 0; e < 4; ++e)
-                    if (c0 + e < p.Cout) v[e] += o[e];
-                } else {
-                  const __nv_bfloat16* o = (const __nv_bfloat16*)p.out + pix * (size_t)p.ldc + c0;
-                  for (int e = 0; e < 4; ++e)
-                    if (c0 + e < p.Cout) v[e] += __bfloat162float(o[e]);
-                }
-              }
-              if (p.relu) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
-              }
-              if (p.mask_src) {
-                const __nv_bfloat16* mk = p.mask_src + pix * (size_t)p.mask_ld + c0;
-                for (int e = 0; e < 4; ++e)
-                  if (c0 + e < p.Cout && !(__bfloat162float(mk[e]) > 0.f)) v[e] = 0.f;
-              }
-              if (p.out_f32) {
-                float* o = (float*)p.out + pix * (size_t)p.ldc + c0;
-                if (c_all) {
-                  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                } else {
-                  for (int e = 0; e < 4; ++e)
-                    if (c0 + e < p.Cout) o[e] = v[e];
-                }
-              } else {
-                __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * (size_t)p.ldc + c0;
-                if (c_all) {
-                  uint2 q;
-                  *reinterpret_cast<__nv_bfloat162*>(&q.x) = __floats2bfloat162_rn(v[0], v[1]);
-                  *reinterpret_cast<__nv_bfloat162*>(&q.y) = __floats2bfloat162_rn(v[2], v[3]);
-                  *reinterpret_cast<uint2*>(o) = q;
-                } else {
-                  for (int e = 0; e < 4; ++e)
-                    if (c0 + e < p.Cout) o[e] = __float2bfloat16_rn(v[e]);
-                }
-              }
-            }
-          }
-          __syncwarp();   // staging is rewritten by the next pass / tile
         }
       }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbarrier_arrive(&tempty[acc]);
     }
   }
   tc_fence_before();
@@ -603,7 +634,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   }
   const int total = p.N * p.tiles_y * p.tiles_x * p.tiles_n;
   const int grid = total < g_conv_sms ? total : g_conv_sms;
-  conv_tc_kernel<BN><<<grid, CONV_THREADS, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  conv_tc_kernel<BN><<<grid, CONV_FWD_THREADS, Cfg::SMEM, stream>>>(tmA, tmB, p);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
