@@ -234,6 +234,11 @@ int ldb200_colsum(const void* x, float* out, int64_t rows, int C, int ld, int dt
  * grad_scale folds the data-parallel mean.  configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py:53. */
 int ldb200_sgd_flat(float* w, const float* g, float* momentum_buf, int64_t n, float lr, float momentum,
                     float weight_decay, float grad_scale, int first_step, void* stream);
+/* same update with the hyper-parameters read from device memory, hyper_dev = f32[5]
+ * {lr, momentum, weight_decay, grad_scale, first_step(0/1)}: the launch can sit inside a CUDA graph
+ * while the warm-up schedule changes lr every iteration. */
+int ldb200_sgd_flat_dev(float* w, const float* g, float* momentum_buf, int64_t n, const float* hyper_dev,
+                        void* stream);
 
 #ifdef __cplusplus
 }

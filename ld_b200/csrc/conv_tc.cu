@@ -653,7 +653,10 @@ extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
   LDB_REQUIRE(d->out_ld >= d->Cout, LDB_EINVAL, "conv2d_tc: out_ld < Cout");
   LDB_REQUIRE(((uintptr_t)d->in & 15) == 0 && ((uintptr_t)d->weight & 15) == 0 && ((uintptr_t)d->out & 15) == 0,
               LDB_EINVAL, "conv2d_tc: pointers must be 16-byte aligned");
-  const int vec_ok = d->out_ld % 4 == 0 && (!d->mask_src || true);
+  // the fast epilogue path moves 16 bytes per access: bf16 rows need ld % 8 == 0, fp32 rows ld % 4 == 0
+  const int vec_ok = (d->out_ld % (d->out_f32 ? 4 : 8) == 0) && (!d->mask_src || (d->mask_ld ? d->mask_ld : d->out_ld) % 8 == 0) &&
+                     (!d->add_src || (d->add_ld ? d->add_ld : d->Cout) % 8 == 0) &&
+                     (!d->scale || ((uintptr_t)d->scale & 15) == 0) && (!d->bias || ((uintptr_t)d->bias & 15) == 0);
   cudaStream_t stream = (cudaStream_t)stream_;
   ConvParams p;
   memset(&p, 0, sizeof(p));

@@ -376,6 +376,19 @@ __global__ void sgd_flat_kernel(float* __restrict__ w, const float* __restrict__
   }
 }
 
+// graph-capturable variant: hyper-parameters live in device memory [lr, momentum, wd, grad_scale, first(0/1)]
+__global__ void sgd_flat_dev_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ buf,
+                                    long long n, const float* __restrict__ hyper) {
+  const float lr = hyper[0], mom = hyper[1], wd = hyper[2], gs = hyper[3];
+  const bool first = hyper[4] != 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * gs + wd * w[i];
+    float b = first ? gi : mom * buf[i] + gi;
+    buf[i] = b;
+    w[i] -= lr * b;
+  }
+}
+
 static int grid_for(long long total, int threads = 256, int cap = 148 * 16) {
   long long b = (total + threads - 1) / threads;
   if (b > cap) b = cap;
@@ -497,6 +510,15 @@ extern "C" int ldb200_sgd_flat(float* w, const float* g, float* buf, int64_t n, 
   if (n == 0) return 0;
   sgd_flat_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(w, g, buf, n, lr, momentum, weight_decay, grad_scale,
                                                                   first_step);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_sgd_flat_dev(float* w, const float* g, float* buf, int64_t n, const float* hyper_dev,
+                                   void* stream_) {
+  LDB_REQUIRE(w && g && buf && hyper_dev && n >= 0, LDB_EINVAL, "sgd_flat_dev: bad argument");
+  if (n == 0) return 0;
+  sgd_flat_dev_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(w, g, buf, n, hyper_dev);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -287,8 +287,12 @@ class LDHead(GFLHead):
             ld_vlr_weight=self.loss_ld_vlr.loss_weight, ld_vlr_T=self.loss_ld_vlr.T,
             kd_weight=self.loss_kd.loss_weight, kd_T=self.loss_kd.T, im_weight=self.loss_im.loss_weight)
 
-    def get_targets(self, featmap_sizes, img_metas, gt_bboxes, gt_labels, device):
+    _static_targets = None   # set by LDTrainStep.capture(): targets are produced outside the CUDA graph
+
+    def get_targets(self, featmap_sizes, img_metas, gt_bboxes, gt_labels, device, static=True):
         """ld_head.py:377-447 for the whole batch in one call (row space)."""
+        if static and self._static_targets is not None and gt_bboxes is None:
+            return self._static_targets
         if self.imitation_method not in IM_MODES:
             raise NotImplementedError(f"imitation_method='{self.imitation_method}' (GI boxes + NMS, ld_head.py:613-638) "
                                       f"is not implemented; use 'finegrained' (configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py:47)")
@@ -304,7 +308,7 @@ class LDHead(GFLHead):
                       gt_bboxes_ignore=None, proposal_cfg=None, **kwargs):
         """ld_head.py:73-114.  x / teacher_x: tuples of NCHW-shaped FPN levels, out_teacher = (cls_scores,
         bbox_preds) of the teacher head."""
-        assert gt_labels is not None and proposal_cfg is None
+        assert (gt_labels is not None or self._static_targets is not None) and proposal_cfg is None
         if gt_bboxes_ignore is not None and any(g is not None and g.numel() for g in gt_bboxes_ignore):
             raise NotImplementedError('gt_bboxes_ignore (ignore_iof_thr=-1 in all LD configs)')
         sizes = [tuple(f.shape[2:]) for f in x]

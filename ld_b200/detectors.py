@@ -225,3 +225,85 @@ class LDTrainStep:
         engine.clear_step_cache(self.params)
         self.iter += 1
         return loss.detach(), log_vars
+
+    # ------------------------------------------------------------------ CUDA-graph replay
+    def _body(self, data):
+        """Everything of one iteration that depends only on device-resident state: captured once."""
+        self.flat_g.zero_()
+        losses = self.model(**data)
+        terms = torch.stack([sum(v) for v in losses.values()])
+        loss = terms.sum()
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.flat_g)
+        ops.sgd_flat_dev(self.flat_w, self.flat_g, self.flat_m, self._hyper)
+        self._terms.copy_(terms.detach())
+        self._loss.copy_(loss.detach())
+
+    def capture(self, data, warmup=2):
+        """Capture forward + fused loss + backward + all-reduce + SGD into one CUDA graph.
+
+        Target assignment stays outside the graph (its grid depends on the number of gt boxes): each
+        replay first runs `ldb200_ld_targets` eagerly into the static target buffers the graph reads.
+        The image batch is copied into a static device buffer; lr / first-step flag live in device memory."""
+        dev = self.flat_w.device
+        head = self.model.bbox_head
+        self._hyper = torch.zeros(5, dtype=torch.float32, device=dev)
+        self._loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self._terms = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._static_img = data['img'].to(dev).float().contiguous().clone()
+        self._metas = data['img_metas']
+        sizes = self._featmap_sizes(self._static_img.shape[2:])
+        self._static_targets = head.get_targets(sizes, self._metas, data['gt_bboxes'], data['gt_labels'], dev)
+        head._static_targets = self._static_targets
+        static = dict(img=self._static_img, img_metas=self._metas, gt_bboxes=None, gt_labels=None)
+        self._set_hyper()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._body(static)
+                engine.clear_step_cache(self.params)
+                self.iter += 1
+                self._set_hyper()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        engine.clear_step_cache(self.params)
+        self._graph = torch.cuda.CUDAGraph()
+        l0 = L.launch_count['n']
+        with torch.cuda.graph(self._graph):
+            self._body(static)
+        self.launches_per_step = L.launch_count['n'] - l0   # ld_b200 kernels inside the graph
+        engine.clear_step_cache(self.params)
+        return self
+
+    def _featmap_sizes(self, hw):
+        def half(v):
+            return (v + 1) // 2
+        h, w = half(half(half(hw[0]))), half(half(half(hw[1])))
+        out = []
+        for _ in self.model.bbox_head.anchor_generator.strides:
+            out.append((h, w))
+            h, w = half(h), half(w)
+        return out
+
+    def _set_hyper(self):
+        vals = torch.tensor([self.lr_at(self.iter), self.momentum, self.wd, 1.0 / self.world,
+                             1.0 if self.iter == 0 else 0.0], dtype=torch.float32)
+        self._hyper.copy_(vals, non_blocking=True)
+
+    def step_graphed(self, data=None):
+        """Replay the captured iteration on a new batch (same shapes).  Returns the device loss scalar."""
+        if data is not None:
+            self._static_img.copy_(data['img'], non_blocking=True)
+            tg = self.model.bbox_head.get_targets(self._featmap_sizes(self._static_img.shape[2:]), data['img_metas'],
+                                                  data['gt_bboxes'], data['gt_labels'], self.flat_w.device,
+                                                  static=False)
+            st = self._static_targets
+            for name in ('labels', 'label_weights', 'bbox_targets', 'vlr', 'im', 'gt_inds', 'sparse_rows',
+                         'fg_rows', 'counts'):
+                getattr(st, name).copy_(getattr(tg, name))
+        self._set_hyper()
+        self._graph.replay()
+        self.iter += 1
+        return self._loss

@@ -345,3 +345,9 @@ def conv2d_wgrad_tc(dy, x, dw, kh=1, kw=1, stride=1, pad=0):
 def unpack_conv_weight_grad(dw_packed, cout, cin, kh, kw):
     """[Cout, kh*kw*Cin] -> [Cout, Cin, kh, kw] (PyTorch OIHW view of the packed gradient)."""
     return dw_packed.view(cout, kh, kw, cin).permute(0, 3, 1, 2)
+
+
+def sgd_flat_dev(w, g, buf, hyper_dev):
+    """Graph-capturable SGD: hyper_dev = f32[5] device {lr, momentum, wd, grad_scale, first_step}."""
+    L.check(L.load().ldb200_sgd_flat_dev(L.ptr(w), L.ptr(g), L.ptr(buf), w.numel(), L.ptr(hyper_dev), L.stream_ptr()),
+            'ldb200_sgd_flat_dev')

@@ -86,3 +86,24 @@ def test_train_steps_reduce_loss_and_match_sgd():
                     assert err <= 2e-3 * float(b.abs().max()) + 1e-6, (it, k, err)
     assert min(logs[1:3]) < logs[0], logs
     assert float(ts.flat_g.abs().sum()) > 0
+
+
+def test_cuda_graph_step_matches_eager():
+    """LDTrainStep.capture()/step_graphed(): the whole iteration (forward, fused loss, backward, SGD) replayed
+    from one CUDA graph gives the same parameters as the eager path, also when the batch (and its number of
+    gt boxes) changes between replays."""
+    import ld_b200
+    a, b = build(18, 18, 5), build(18, 18, 5)
+    batches = [to_dev(synth.make_batch(2, 128, 160, seed=s)) for s in (81, 82, 83)]
+    ta = ld_b200.LDTrainStep(a, lr=0.0005, warmup_iters=2)
+    tb = ld_b200.LDTrainStep(b, lr=0.0005, warmup_iters=2)
+    tb.capture(batches[0], warmup=0)
+    for d in batches:
+        la, _ = ta.step(d, sync_logs=False)
+        lb = tb.step_graphed(d)
+        torch.cuda.synchronize()
+        assert abs(float(la) - float(lb)) <= 2e-3 * abs(float(la)), (float(la), float(lb))
+    for (k, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        if p.requires_grad:
+            err = float((p - q).abs().max())
+            assert err <= 2e-3 * float(p.abs().max()) + 1e-6, (k, err)
