@@ -246,6 +246,9 @@ class LDTrainStep:
         Target assignment stays outside the graph (its grid depends on the number of gt boxes): each
         replay first runs `ldb200_ld_targets` eagerly into the static target buffers the graph reads.
         The image batch is copied into a static device buffer; lr / first-step flag live in device memory."""
+        if warmup < 1:
+            raise ValueError('capture() needs >= 1 eager warm-up iteration (lazy initialisation must not happen '
+                             'inside stream capture)')
         dev = self.flat_w.device
         head = self.model.bbox_head
         self._hyper = torch.zeros(5, dtype=torch.float32, device=dev)
