@@ -202,6 +202,9 @@ typedef struct {
   int ntaps; int tap_dx[9], tap_dy[9], tap_wk[9];
   int sx, sy;
   float* dw; int w_k;
+  const float* scale;     /* optional [Cout]: dw += scale[co] * G (folded eval-BN / Scale factor) */
+  const float* w_master;  /* optional fp32 weights [Cout, w_k], needed for d_scale */
+  float* d_scale;         /* optional [Cout]: d_scale[co] += <w_master[co,:], G[co,:]> (gradient of the factor) */
 } ldb_wgrad_desc;
 int ldb200_conv2d_wgrad_tc(const ldb_wgrad_desc* desc, void* stream);
 

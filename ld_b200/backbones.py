@@ -55,14 +55,8 @@ class BasicBlock(_Block):
         self.stride = stride
 
     def forward(self, x):
-        idt = x
-        if self.downsample is not None:
-            s, b = engine.bn_affine(self.downsample[1])
-            idt = engine.conv_affine_act(x, self.downsample[0]._cl(), s, b, None, self.stride, 0, False)
-        s, b = engine.bn_affine(self.bn1)
-        o = engine.conv_affine_act(x, self.conv1._cl(), s, b, None, self.stride, 1, True)
-        s, b = engine.bn_affine(self.bn2)
-        return engine.conv_affine_act(o, self.conv2._cl(), s, b, idt, 1, 1, True)
+        ds = None if self.downsample is None else (self.downsample[0], self.downsample[1])
+        return engine.res_block(x, [(self.conv1, self.bn1, self.stride, 1), (self.conv2, self.bn2, 1, 1)], ds)
 
 
 class Bottleneck(_Block):
@@ -81,16 +75,9 @@ class Bottleneck(_Block):
         self.stride = stride
 
     def forward(self, x):
-        idt = x
-        if self.downsample is not None:
-            s, b = engine.bn_affine(self.downsample[1])
-            idt = engine.conv_affine_act(x, self.downsample[0]._cl(), s, b, None, self.stride, 0, False)
-        s, b = engine.bn_affine(self.bn1)
-        o = engine.conv_affine_act(x, self.conv1._cl(), s, b, None, 1, 0, True)
-        s, b = engine.bn_affine(self.bn2)
-        o = engine.conv_affine_act(o, self.conv2._cl(), s, b, None, self.stride, 1, True)
-        s, b = engine.bn_affine(self.bn3)
-        return engine.conv_affine_act(o, self.conv3._cl(), s, b, idt, 1, 0, True)
+        ds = None if self.downsample is None else (self.downsample[0], self.downsample[1])
+        return engine.res_block(x, [(self.conv1, self.bn1, 1, 0), (self.conv2, self.bn2, self.stride, 1),
+                                    (self.conv3, self.bn3, 1, 0)], ds)
 
 
 @BACKBONES.register_module()
@@ -245,6 +232,8 @@ class FPN(nn.Module):
         if upsample_cfg.get('mode', 'nearest') != 'nearest': bad.append('upsample mode')
         if bad:
             raise NotImplementedError(f'ld_b200 FPN implements the LD/GFL configuration only; unsupported: {bad}')
+        # the backbone's stage outputs are ReLU outputs of ResBlockFn nodes, which expect pre-masked gradients
+        self.inputs_are_relu = True
         self.lateral_convs = nn.ModuleList()
         self.fpn_convs = nn.ModuleList()
         for i in range(self.start_level, self.backbone_end_level):
@@ -269,7 +258,7 @@ class FPN(nn.Module):
         for i in range(nb - 1, -1, -1):   # top-down: lateral conv with the coarser level's upsample fused in
             c = self.lateral_convs[i].conv
             lat[i] = engine.conv_affine_act(feats[i], c._cl(), None, c.bias, lat[i + 1] if i + 1 < nb else None,
-                                            1, 0, False)
+                                            1, 0, False, x_premask=self.inputs_are_relu)
         # one row-space buffer for all output levels (ld_b200.h "row space")
         n = feats[0].shape[0]
         sizes = [tuple(l.shape[1:3]) for l in lat]

@@ -26,7 +26,7 @@
 namespace ldb {
 
 constexpr int CONV_THREADS = 256;       // wgrad kernel
-constexpr int CONV_FWD_THREADS = 384;   // 4 control warps + 8 epilogue warps
+constexpr int CONV_FWD_MAX_THREADS = 640;   // 4 control warps + up to 16 epilogue warps
 constexpr int TILE_M = 128;
 constexpr int KCH = 64;                        // channels per k-block (128 B of bf16)
 constexpr int A_TILE_BYTES = TILE_M * KCH * 2;  // 16 KB
@@ -141,6 +141,10 @@ template <int BN> struct ConvCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int STAGING_BYTES = 0;
+  // epilogue warp groups of 4 warps (one per TMEM lane quadrant); each group owns BN/EPI_GROUPS columns.
+  // Four groups (4 warps per SM sub-partition) hide the latency of the residual / mask loads.
+  static constexpr int EPI_GROUPS = BN >= 128 ? 4 : 2;
+  static constexpr int THREADS = 128 + 128 * EPI_GROUPS;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=BN, M=128
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
@@ -152,7 +156,7 @@ __device__ __forceinline__ size_t out_offset(const ConvParams& p, int n, int y, 
 }
 
 template <int BN>
-__global__ void __launch_bounds__(CONV_FWD_THREADS, 1)
+__global__ void __launch_bounds__(ConvCfg<BN>::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
   using Cfg = ConvCfg<BN>;
   extern __shared__ unsigned char conv_smem_raw[];
@@ -177,7 +181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbarrier_init(&tfull[a], 1);
-      mbarrier_init(&tempty[a], 8);   // one arrive per epilogue warp
+      mbarrier_init(&tempty[a], 4 * Cfg::EPI_GROUPS);   // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -249,12 +253,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================================== epilogue ==========================================
-    // 8 warps (two per SM sub-partition, so ALU/TMEM-load latency of one is hidden by the other): warp w
-    // reads TMEM lanes [32*(w%4), +32) = 32 tile rows, and half of the tile's BN columns.  Per 32-column
+    // 4*EPI_GROUPS warps (EPI_GROUPS per SM sub-partition, hiding each other's ALU / TMEM-load / residual-load
+    // latency): warp w reads TMEM lanes [32*(w%4), +32) = 32 tile rows, and BN/EPI_GROUPS of the tile's columns.  Per 32-column
     // chunk: tcgen05.ld (software-pipelined one chunk ahead), per-channel scale/bias (float4 loads),
     // residual / accumulate / ReLU / mask, 16-byte stores along the thread's own output row.
-    const int ew = warp & 3, half = (warp - 4) >> 2;
-    constexpr int NCH = BN / 64;                    // 32-column chunks per warp
+    const int ew = warp & 3, half = (warp - 4) >> 2;              // half = column group of this warp
+    constexpr int GCOLS = BN / Cfg::EPI_GROUPS;                  // columns per group
+    constexpr int NCH = GCOLS / 32;                               // 32-column chunks per warp
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -274,8 +279,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ay = (int)(((long long)y * p.add_H) / p.HO), ax = (int)(((long long)x * p.add_W) / p.WO);
         addp = p.add_src + (((size_t)n * p.add_H + ay) * p.add_W + ax) * (size_t)p.add_ld;
       }
-      const int col0 = nt * BN + half * (BN / 2);
-      const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+      const int col0 = nt * BN + half * GCOLS;
+      const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * GCOLS);
       mbarrier_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       uint32_t rbuf[2][32];
@@ -423,6 +428,9 @@ struct WgradParams {
   int co_tiles, ci_tiles, splits;
   float* dw;
   int w_k;
+  const float* scale;     // optional per-output-channel factor applied to the accumulated gradient
+  const float* w_master;  // optional fp32 weights [Cout, w_k]: d_scale[co] += <w[co,:], G[co,:]>
+  float* d_scale;
 };
 
 // MN-major SWIZZLE_128B descriptor: LBO = 16 KB between 64-element chunks, SBO = 1 KB between 8-row groups
@@ -562,18 +570,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ch * 32), r);
           if (co < p.Cout) {
-            float* o = p.dw + (size_t)co * p.w_k + p.tap_wk[tap] + cbase;
+            const size_t woff = (size_t)co * p.w_k + p.tap_wk[tap] + cbase;
+            float* o = p.dw + woff;
+            const float sc = p.scale ? __ldg(p.scale + co) : 1.f;
+            float dot = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (cbase + j + 4 <= p.Cin) {
-                atomicAdd(reinterpret_cast<float4*>(o + j),
-                          make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                      __uint_as_float(r[j + 3])));
+                const float4 g4 = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                if (p.d_scale) {
+                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.w_master + woff + j));
+                  dot += g4.x * w4.x + g4.y * w4.y + g4.z * w4.z + g4.w * w4.w;
+                }
+                atomicAdd(reinterpret_cast<float4*>(o + j), make_float4(g4.x * sc, g4.y * sc, g4.z * sc, g4.w * sc));
               } else {
                 for (int e = 0; e < 4; ++e)
-                  if (cbase + j + e < p.Cin) atomicAdd(o + j + e, __uint_as_float(r[j + e]));
+                  if (cbase + j + e < p.Cin) {
+                    const float gv = __uint_as_float(r[j + e]);
+                    if (p.d_scale) dot += gv * __ldg(p.w_master + woff + j + e);
+                    atomicAdd(o + j + e, gv * sc);
+                  }
               }
             }
+            if (p.d_scale) atomicAdd(p.d_scale + co, dot);
           }
         }
       }
@@ -634,7 +654,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   }
   const int total = p.N * p.tiles_y * p.tiles_x * p.tiles_n;
   const int grid = total < g_conv_sms ? total : g_conv_sms;
-  conv_tc_kernel<BN><<<grid, CONV_FWD_THREADS, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  conv_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(tmA, tmB, p);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -770,6 +790,8 @@ extern "C" int ldb200_conv2d_wgrad_tc(const ldb_wgrad_desc* d, void* stream_) {
     p.tap_dx[t] = d->tap_dx[t]; p.tap_dy[t] = d->tap_dy[t]; p.tap_wk[t] = d->tap_wk[t];
   }
   p.sx = d->sx; p.sy = d->sy; p.dw = d->dw; p.w_k = d->w_k;
+  p.scale = d->scale; p.w_master = d->w_master; p.d_scale = d->d_scale;
+  LDB_REQUIRE(!d->d_scale || (d->w_master && ((uintptr_t)d->w_master & 15) == 0), LDB_EINVAL, "wgrad_tc: d_scale needs aligned w_master");
   int best_th = 8, best_tiles = 1 << 30;
   for (int th = 1; th <= TILE_M; th *= 2) {
     const int tw = TILE_M / th;

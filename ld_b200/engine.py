@@ -80,7 +80,7 @@ def conv_dgrad(g, w, scale, stride, pad, in_hw, out=None, accumulate=False, mask
         taps = [(pad - s, pad - r, (r * kw + s) * cop) for r in range(kh) for s in range(kw)]
         return ops.conv2d_tc(g, wd, ci, kh, kw, 1, pad, out=out, taps=taps, out_hw=(h, w_),
                              accumulate=accumulate, mask=mask, add=add)
-    assert stride == 2 and mask is None and add is None
+    assert stride == 2 and add is None
     if out is None:   # parity classes write disjoint pixels; untouched ones (1x1 s2) must read as zero
         out = torch.zeros(n, h, w_, ci, dtype=torch.bfloat16, device=g.device)
         accumulate = False
@@ -98,7 +98,7 @@ def conv_dgrad(g, w, scale, stride, pad, in_hw, out=None, accumulate=False, mask
             if not taps or hp <= 0 or wp <= 0:
                 continue
             ops.conv2d_tc(g, wd, ci, kh, kw, 1, 0, out=out, taps=taps, out_hw=(hp, wp), flat=False,
-                          out_map=((h, w_), (2, py, 2, px)), accumulate=accumulate)
+                          out_map=((h, w_), (2, py, 2, px)), accumulate=accumulate, mask=mask)
     return out
 
 
@@ -114,21 +114,22 @@ class ConvAffineAct(torch.autograd.Function):
     """y = relu?(scale * conv(x, W) + shift + resample(residual))  -- one tcgen05 launch forward."""
 
     @staticmethod
-    def forward(ctx, x, weight, scale, shift, residual, stride, pad, relu, out, out_dtype):
+    def forward(ctx, x, weight, scale, shift, residual, stride, pad, relu, out, out_dtype, x_premask=False):
         co, ci, kh, kw = weight.shape
         wp = packed_weight(weight)
         y = ops.conv2d_tc(x, wp, co, kh, kw, stride, pad, out=None if out is None else out.t, out_dtype=out_dtype,
                           scale=None if scale is None else scale.detach().contiguous(),
                           bias=None if shift is None else shift.detach().contiguous(),
                           add=residual, relu=relu)
-        ctx.cfg = (stride, pad, relu, residual is not None and tuple(residual.shape[1:3]) != tuple(y.shape[1:3]))
+        ctx.cfg = (stride, pad, relu, residual is not None and tuple(residual.shape[1:3]) != tuple(y.shape[1:3]),
+                   x_premask)
         ctx.save_for_backward(x, weight, scale, shift, residual, y if relu else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, weight, scale, shift, residual, y = ctx.saved_tensors
-        stride, pad, relu, resampled = ctx.cfg
+        stride, pad, relu, resampled, x_premask = ctx.cfg
         co, ci, kh, kw = weight.shape
         need_x, need_w, need_scale, need_shift, need_res = ctx.needs_input_grad[:5]
         if dy.dtype != torch.bfloat16:
@@ -141,27 +142,34 @@ class ConvAffineAct(torch.autograd.Function):
             d_shift = torch.zeros(co, dtype=torch.float32, device=g.device)
             ops.colsum(g.reshape(-1, g.shape[-1]), d_shift)
         if need_w or need_scale:
-            G = torch.zeros(co, kh * kw * ci, dtype=torch.float32, device=g.device)
-            ops.conv2d_wgrad_tc(g, x, G, kh, kw, stride, pad)
+            # the wgrad kernel accumulates scale[co]*G straight into the parameter's gradient buffer (the flat
+            # gradient buffer of LDTrainStep, or a lazily created channels-last .grad) and emits d_scale from
+            # its epilogue: no temporaries, no autograd accumulation kernels
+            if weight.grad is None:
+                weight.grad = torch.zeros_like(weight, memory_format=torch.channels_last)
+            gbuf = weight.grad.permute(0, 2, 3, 1)
+            assert gbuf.is_contiguous(), 'conv weight gradients must be channels-last'
             if need_scale:
-                d_scale = (G * weight.detach().permute(0, 2, 3, 1).reshape(co, -1)).sum(1)
-            if need_w:
-                Gs = G if scale is None else G * scale.detach().view(-1, 1)
-                d_w = Gs.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+                d_scale = torch.zeros(co, dtype=torch.float32, device=g.device)
+            wm = weight.detach().permute(0, 2, 3, 1).reshape(co, -1)
+            ops.conv2d_wgrad_tc(g, x, gbuf.reshape(co, -1), kh, kw, stride, pad,
+                                scale=None if scale is None else scale.detach().contiguous(),
+                                w_master=wm if need_scale else None, d_scale=d_scale)
         if need_x:
-            d_x = conv_dgrad(g, weight, scale, stride, pad, x.shape[1:3])
+            # x_premask: x is a ResBlockFn output -> hand it a gradient already multiplied by (x > 0)
+            d_x = conv_dgrad(g, weight, scale, stride, pad, x.shape[1:3], mask=x if x_premask else None)
         if need_res:
             if resampled:
                 d_res = ops.upsample_add_bwd(g, torch.zeros_like(residual))
             else:
                 d_res = g
-        return d_x, d_w, d_scale, d_shift, d_res, None, None, None, None, None
+        return d_x, d_w, d_scale, d_shift, d_res, None, None, None, None, None, None
 
 
 def conv_affine_act(x, weight, scale=None, shift=None, residual=None, stride=1, pad=0, relu=False,
-                    out=None, out_dtype=torch.bfloat16):
+                    out=None, out_dtype=torch.bfloat16, x_premask=False):
     return ConvAffineAct.apply(x, weight, scale, shift, residual, stride, pad, relu,
-                               None if out is None else OutSlot(out), out_dtype)
+                               None if out is None else OutSlot(out), out_dtype, x_premask)
 
 
 class GNReLU(torch.autograd.Function):
@@ -205,3 +213,118 @@ def bn_affine(bn):
         scale, shift = scale.detach().contiguous(), shift.detach().contiguous()
         bn.__dict__['_ldb_affine'] = (key, (scale, shift))
     return scale, shift
+
+
+# ------------------------------------------------------------------------------------------------------
+# Residual blocks as ONE autograd node each, so that the backward chain can use the fused dgrad epilogues:
+# ReLU masks are applied by the dgrad that PRODUCES a gradient (mask = the forward activation it flows into) and
+# the identity / downsample branch is added in the same epilogue -- no relu_bwd and no add kernels.
+#
+# Convention between blocks ("pre-masked gradients"): the gradient a block RECEIVES for its output has already
+# been multiplied by (out > 0), and the gradient it RETURNS for its input has been multiplied by (x > 0).  Every
+# consumer of a block output must follow it (next block, FPN lateral conv with `x_premask=True`).
+def _wgrad_into(weight, g, x, scale, stride, pad, need_scale):
+    co, ci, kh, kw = weight.shape
+    if weight.grad is None:
+        weight.grad = torch.zeros_like(weight, memory_format=torch.channels_last)
+    gbuf = weight.grad.permute(0, 2, 3, 1)
+    assert gbuf.is_contiguous(), 'conv weight gradients must be channels-last'
+    d_scale = torch.zeros(co, dtype=torch.float32, device=g.device) if need_scale else None
+    ops.conv2d_wgrad_tc(g, x, gbuf.reshape(co, -1), kh, kw, stride, pad,
+                        scale=None if scale is None else scale.detach().contiguous(),
+                        w_master=weight.detach().permute(0, 2, 3, 1).reshape(co, -1) if need_scale else None,
+                        d_scale=d_scale)
+    return d_scale
+
+
+def _colsum(g):
+    out = torch.zeros(g.shape[-1], dtype=torch.float32, device=g.device)
+    ops.colsum(g.reshape(-1, g.shape[-1]), out)
+    return out
+
+
+class ResBlockFn(torch.autograd.Function):
+    """Bottleneck (3 convs) or BasicBlock (2 convs) with eval-BN folded into per-channel scale/shift.
+
+    args: x, then for every conv (weight, scale, shift) in order [main convs..., downsample?]."""
+
+    @staticmethod
+    def forward(ctx, x, strides, pads, has_ds, *params):
+        nmain = len(strides)
+        convs = [params[3 * i:3 * i + 3] for i in range(nmain + (1 if has_ds else 0))]
+        stride = max(strides)
+        acts = [x]
+        idt = x
+        if has_ds:
+            w, s, b = convs[nmain]
+            idt = ops.conv2d_tc(x, packed_weight(w), w.shape[0], 1, 1, stride, 0, scale=s.detach().contiguous(),
+                                bias=b.detach().contiguous())
+        h = x
+        for i in range(nmain):
+            w, s, b = convs[i]
+            last = i == nmain - 1
+            h = ops.conv2d_tc(h, packed_weight(w), w.shape[0], w.shape[2], w.shape[3], strides[i], pads[i],
+                              scale=s.detach().contiguous(), bias=b.detach().contiguous(),
+                              add=idt if last else None, relu=True)
+            acts.append(h)
+        ctx.cfg = (strides, pads, has_ds)
+        ctx.save_for_backward(*acts[:nmain], *params)   # the block output itself is not needed (pre-masked grads)
+        return h
+
+    @staticmethod
+    def backward(ctx, g):
+        strides, pads, has_ds = ctx.cfg
+        nmain = len(strides)
+        saved = ctx.saved_tensors
+        acts, params = saved[:nmain], saved[nmain:]
+        convs = [params[3 * i:3 * i + 3] for i in range(nmain + (1 if has_ds else 0))]
+        x = acts[0]
+        need_x = ctx.needs_input_grad[0]
+        grads = [None] * len(params)
+        g = g.contiguous()          # grad w.r.t. the block output, pre-masked by (out > 0)
+        g_out = g
+        for i in range(nmain - 1, -1, -1):
+            w, s, b = convs[i]
+            a_in = acts[i]
+            ns, nb = ctx.needs_input_grad[4 + 3 * i + 1], ctx.needs_input_grad[4 + 3 * i + 2]
+            if nb:
+                grads[3 * i + 2] = _colsum(g)
+            if ctx.needs_input_grad[4 + 3 * i] or ns:
+                grads[3 * i + 1] = _wgrad_into(w, g, a_in, s, strides[i], pads[i], ns)
+            if i > 0:
+                g = conv_dgrad(g, w, s, strides[i], pads[i], a_in.shape[1:3], mask=a_in)
+            elif need_x:
+                if has_ds:
+                    wd, sd, bd = convs[nmain]
+                    t = conv_dgrad(g_out, wd, sd, max(strides), 0, x.shape[1:3])
+                    if strides[0] == 1:
+                        g = conv_dgrad(g, w, s, 1, pads[0], x.shape[1:3], add=t, mask=x)
+                    else:   # BasicBlock: the strided 3x3 covers every pixel through its four parity classes
+                        g = conv_dgrad(g, w, s, strides[0], pads[0], x.shape[1:3], out=t, accumulate=True, mask=x)
+                else:
+                    g = conv_dgrad(g, w, s, strides[0], pads[0], x.shape[1:3], add=g_out, mask=x)
+            else:
+                g = None
+        if has_ds:
+            wd, sd, bd = convs[nmain]
+            j = nmain
+            ns, nb = ctx.needs_input_grad[4 + 3 * j + 1], ctx.needs_input_grad[4 + 3 * j + 2]
+            if nb:
+                grads[3 * j + 2] = _colsum(g_out)
+            if ctx.needs_input_grad[4 + 3 * j] or ns:
+                grads[3 * j + 1] = _wgrad_into(wd, g_out, x, sd, max(strides), 0, ns)
+        return (g, None, None, None, *grads)
+
+
+def res_block(x, main, downsample=None):
+    """main: list of (conv, bn, stride, pad); downsample: (conv, bn) or None."""
+    params, strides, pads = [], [], []
+    for conv, bn, st, pd in main:
+        s, b = bn_affine(bn)
+        params += [conv._cl(), s, b]
+        strides.append(st)
+        pads.append(pd)
+    if downsample is not None:
+        s, b = bn_affine(downsample[1])
+        params += [downsample[0]._cl(), s, b]
+    return ResBlockFn.apply(x, tuple(strides), tuple(pads), downsample is not None, *params)

@@ -64,7 +64,8 @@ class WgradDesc(C.Structure):
     _fields_ = [('dy', C.c_void_p), ('N', C.c_int), ('HO', C.c_int), ('WO', C.c_int), ('Cout', C.c_int),
                 ('dy_ld', C.c_int), ('x', C.c_void_p), ('H', C.c_int), ('W', C.c_int), ('Cin', C.c_int),
                 ('x_ld', C.c_int), ('ntaps', C.c_int), ('tap_dx', C.c_int * 9), ('tap_dy', C.c_int * 9),
-                ('tap_wk', C.c_int * 9), ('sx', C.c_int), ('sy', C.c_int), ('dw', C.c_void_p), ('w_k', C.c_int)]
+                ('tap_wk', C.c_int * 9), ('sx', C.c_int), ('sy', C.c_int), ('dw', C.c_void_p), ('w_k', C.c_int),
+                ('scale', C.c_void_p), ('w_master', C.c_void_p), ('d_scale', C.c_void_p)]
 
 
 _SIGS = {

@@ -324,8 +324,9 @@ def sgd_flat(w, g, buf, lr, momentum=0.9, weight_decay=1e-4, grad_scale=1.0, fir
             'ldb200_sgd_flat')
 
 
-def conv2d_wgrad_tc(dy, x, dw, kh=1, kw=1, stride=1, pad=0):
-    """dw [Cout, kh*kw*Cin] f32 (packed tap-major layout) += wgrad(dy [N,HO,WO,Cout], x [N,H,W,Cin]) (bf16 NHWC)."""
+def conv2d_wgrad_tc(dy, x, dw, kh=1, kw=1, stride=1, pad=0, scale=None, w_master=None, d_scale=None):
+    """dw [Cout, kh*kw*Cin] f32 (packed tap-major layout) += scale[co] * wgrad(dy [N,HO,WO,Cout], x [N,H,W,Cin])
+    (bf16 NHWC); optionally d_scale[co] += <w_master[co], wgrad[co]>."""
     assert dy.dtype == x.dtype == torch.bfloat16 and dw.dtype == torch.float32 and dw.is_contiguous()
     n, ho, wo, cout = dy.shape
     _, h, w_, cin = x.shape
@@ -338,6 +339,13 @@ def conv2d_wgrad_tc(dy, x, dw, kh=1, kw=1, stride=1, pad=0):
         d.tap_dx[i], d.tap_dy[i], d.tap_wk[i] = dx, dy_, wk
     d.sx = d.sy = stride
     d.dw, d.w_k = dw.data_ptr(), dw.shape[1]
+    if scale is not None:
+        assert scale.dtype == torch.float32 and scale.is_contiguous()
+        d.scale = scale.data_ptr()
+    if d_scale is not None:
+        assert w_master is not None and w_master.dtype == torch.float32 and w_master.shape == dw.shape \
+            and w_master.is_contiguous() and d_scale.dtype == torch.float32
+        d.w_master, d.d_scale = w_master.data_ptr(), d_scale.data_ptr()
     L.check(L.load().ldb200_conv2d_wgrad_tc(C.byref(d), L.stream_ptr()), 'ldb200_conv2d_wgrad_tc')
     return dw
 
