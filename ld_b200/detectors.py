@@ -274,7 +274,8 @@ class LDTrainStep:
         engine.clear_step_cache(self.params)
         self._graph = torch.cuda.CUDAGraph()
         l0 = L.launch_count['n']
-        with torch.cuda.graph(self._graph):
+        # thread_local: the NCCL watchdog thread may query events while this thread captures
+        with torch.cuda.graph(self._graph, capture_error_mode='thread_local'):
             self._body(static)
         self.launches_per_step = L.launch_count['n'] - l0   # ld_b200 kernels inside the graph
         engine.clear_step_cache(self.params)
