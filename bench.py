@@ -257,9 +257,15 @@ def main():
             v, sec = cpu_reference_step(2, 1, 1)
             out['cpu_baseline'] = dict(value=v, unit='images/s', cores=host_cores(), kind='port',
                                        sample='one timed fp32 step (after one warm-up) on 2 images of 800x1344 of the batch; oracle port == reference ATen-CPU path')
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # tearing down NCCL communicators that a captured CUDA graph still references can block forever:
+        # make sure every rank is done, flush, and leave without running the destructors
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':
