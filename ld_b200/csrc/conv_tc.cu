@@ -52,6 +52,7 @@ struct ConvParams {
   int accumulate;           // result += previous out (before ReLU / mask)
   int vec_ok;               // leading dimensions allow 4-channel vector accesses
   int tw_shift;             // log2(TW)
+  int pf_add, pf_mask;      // L2-prefetch the residual / mask tile with TMA while the main loop runs
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -84,6 +85,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(s2u(dst)), "l"(map), "r"(s2u(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -157,7 +162,8 @@ __device__ __forceinline__ size_t out_offset(const ConvParams& p, int n, int y, 
 
 template <int BN>
 __global__ void __launch_bounds__(ConvCfg<BN>::THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmM, const ConvParams p) {
   using Cfg = ConvCfg<BN>;
   extern __shared__ unsigned char conv_smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)conv_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -212,6 +218,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ty = sp % p.tiles_y;
         const int n = sp / p.tiles_y;
         const int x0 = tx * p.TW * p.sx, y0 = ty * p.TH * p.sy;
+        // the epilogue will read this tile's residual / ReLU-mask rows a whole main loop from now: pull them into
+        // L2 with one TMA prefetch each so those loads see L2 latency instead of HBM latency
+        if (p.pf_add) tma_prefetch_4d(&tmR, nt * BN, tx * p.TW, ty * p.TH, n);
+        if (p.pf_mask) tma_prefetch_4d(&tmM, nt * BN, tx * p.TW, ty * p.TH, n);
         for (int kb = 0; kb < kblocks; ++kb) {
           const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * KCH;
           mbarrier_wait(&empty[stage], phase ^ 1);
@@ -627,11 +637,12 @@ static PFN_encodeTiled get_encode() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                      const cuuint32_t* box, const cuuint32_t* estr, const char* what) {
+                      const cuuint32_t* box, const cuuint32_t* estr, const char* what,
+                      CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode();
   LDB_REQUIRE(enc, LDB_ENOSUP, "cuTensorMapEncodeTiled not available from the driver");
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LDB_REQUIRE(r == CUDA_SUCCESS, LDB_EINVAL, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
   return 0;
@@ -640,7 +651,8 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 static int g_conv_sms = 0;
 
 template <int BN>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmM,
+                       const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
   static bool attr = false;
   if (!attr) {
@@ -654,7 +666,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   }
   const int total = p.N * p.tiles_y * p.tiles_x * p.tiles_n;
   const int grid = total < g_conv_sms ? total : g_conv_sms;
-  conv_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(tmA, tmB, p);
+  conv_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(tmA, tmB, tmR, tmM, p);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -748,9 +760,25 @@ extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
     int e = encode_map(&tmB, d->weight, 2, dims, strides, box, es, "B");
     if (e) return e;
   }
-  if (BN == 256) return launch_conv<256>(tmA, tmB, p, stream);
-  if (BN == 128) return launch_conv<128>(tmA, tmB, p, stream);
-  return launch_conv<64>(tmA, tmB, p, stream);
+  // optional L2 prefetch maps for the residual / mask tensors (identity pixel mapping, same extent as the output)
+  CUtensorMap tmR = tmA, tmM = tmA;
+  const bool ident = p.oys == 1 && p.oxs == 1 && p.oyo == 0 && p.oxo == 0;
+  auto aux_map = [&](CUtensorMap* m, const void* base, int ld, int HH, int WW, const char* what) -> int {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)WW, (cuuint64_t)HH, (cuuint64_t)p.N};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * WW, (cuuint64_t)ld * 2 * WW * HH};
+    cuuint32_t box[4] = {(cuuint32_t)(d->Cout < BN ? (d->Cout + 7) / 8 * 8 : BN), (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    return encode_map(m, base, 4, dims, strides, box, es, what, CU_TENSOR_MAP_SWIZZLE_NONE);
+  };
+  if (p.add_src && ident && p.add_H == p.OH && p.add_W == p.OW && p.add_ld % 8 == 0 && !d->out_f32) {
+    if (aux_map(&tmR, p.add_src, p.add_ld, p.OH, p.OW, "residual prefetch") == 0) p.pf_add = 1;
+  }
+  if (p.mask_src && ident && p.mask_ld % 8 == 0) {
+    if (aux_map(&tmM, p.mask_src, p.mask_ld, p.OH, p.OW, "mask prefetch") == 0) p.pf_mask = 1;
+  }
+  if (BN == 256) return launch_conv<256>(tmA, tmB, tmR, tmM, p, stream);
+  if (BN == 128) return launch_conv<128>(tmA, tmB, tmR, tmM, p, stream);
+  return launch_conv<64>(tmA, tmB, tmR, tmM, p, stream);
 }
 
 template <int BN>

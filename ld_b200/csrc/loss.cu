@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) ld_prepass_kernel(LossParams P) 
 // ---------------------------------------------------------------------------------------------
 // The fused loss kernel.
 template <typename GT, typename FT>
-__global__ void __launch_bounds__(LOSS_THREADS, 2) ld_loss_fused_kernel(LossParams P) {
+__global__ void __launch_bounds__(LOSS_THREADS, 3) ld_loss_fused_kernel(LossParams P) {
   __shared__ float s_loss[LDB_NUM_TERMS][LDB_MAX_LEVELS];
   __shared__ float s_red[LOSS_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -219,14 +219,19 @@ __global__ void __launch_bounds__(LOSS_THREADS, 2) ld_loss_fused_kernel(LossPara
 
   // ---------------- phase 1: dense QFL over every non-positive row (gfocal_loss.py:34-49) -----
   const int vpr = C >> 2;  // float4 per row (C % 4 == 0 fast path), else scalar path below
-  for (int l = 0; l < ((P.phases & 1) ? P.pyr.L : 0); ++l) {
+  // block roles: two of every three blocks stream the dense QFL phase, the third walks the compacted rows, so the
+  // latency-bound sparse phases overlap the bandwidth-bound dense one instead of following it
+  const int role_sparse = (blockIdx.x % 3) == 2;
+  const int dense_blocks = gridDim.x - gridDim.x / 3, sparse_blocks = gridDim.x / 3;
+  const int dense_id = blockIdx.x - blockIdx.x / 3, sparse_id = blockIdx.x / 3;
+  for (int l = 0; l < (((P.phases & 1) && !role_sparse) ? P.pyr.L : 0); ++l) {
     const long long r0 = (long long)P.pyr.off[l] * N, r1 = (long long)P.pyr.off[l + 1] * N;
     const float gsc = P.tg[0][l];
     float acc = 0.f;
     if ((C & 3) == 0) {
       const long long v0 = r0 * vpr, v1 = r1 * vpr;
-      for (long long v = v0 + (long long)blockIdx.x * LOSS_THREADS + tid; v < v1;
-           v += (long long)gridDim.x * LOSS_THREADS) {
+      for (long long v = v0 + (long long)dense_id * LOSS_THREADS + tid; v < v1;
+           v += (long long)dense_blocks * LOSS_THREADS) {
         const int r = (int)(v / vpr);
         const int lab = __ldg(P.labels + r);
         if (lab >= 0 && lab < C) continue;  // positive rows are owned by phase 2
@@ -255,8 +260,8 @@ __global__ void __launch_bounds__(LOSS_THREADS, 2) ld_loss_fused_kernel(LossPara
       }
     } else {
       const long long e0 = r0 * C, e1 = r1 * C;
-      for (long long e = e0 + (long long)blockIdx.x * LOSS_THREADS + tid; e < e1;
-           e += (long long)gridDim.x * LOSS_THREADS) {
+      for (long long e = e0 + (long long)dense_id * LOSS_THREADS + tid; e < e1;
+           e += (long long)dense_blocks * LOSS_THREADS) {
         const int r = (int)(e / C);
         const int lab = __ldg(P.labels + r);
         if (lab >= 0 && lab < C) continue;
@@ -272,9 +277,9 @@ __global__ void __launch_bounds__(LOSS_THREADS, 2) ld_loss_fused_kernel(LossPara
   }
 
   // ---------------- phase 2: compacted positive / VLR rows, one warp per row ------------------
-  const int n_sparse = (P.phases & 2) ? P.counts[0] : 0;
+  const int n_sparse = ((P.phases & 2) && role_sparse) ? P.counts[0] : 0;
   const bool active = lane < bins;
-  for (int i = blockIdx.x * LOSS_WARPS + wid; i < n_sparse; i += gridDim.x * LOSS_WARPS) {
+  for (int i = sparse_id * LOSS_WARPS + wid; i < n_sparse; i += sparse_blocks * LOSS_WARPS) {
     const int r = P.sparse_rows[i];
     const RowGeom g = row_geom(P.pyr, r);
     const int l = g.l;
@@ -410,12 +415,12 @@ __global__ void __launch_bounds__(LOSS_THREADS, 2) ld_loss_fused_kernel(LossPara
   }
 
   // ---------------- phase 3: feature imitation on the fine-grained rows (kd_loss.py:91-96) ----
-  const int n_fg = (P.phases & 4) ? P.counts[1] : 0;
+  const int n_fg = ((P.phases & 4) && role_sparse) ? P.counts[1] : 0;
   const int F = P.F;
   const FT* __restrict__ xs_ = (const FT*)P.x;
   const FT* __restrict__ xt_ = (const FT*)P.t_x;
   GT* __restrict__ d_im = (GT*)P.d_im;
-  for (int i = blockIdx.x * LOSS_WARPS + wid; i < n_fg; i += gridDim.x * LOSS_WARPS) {
+  for (int i = sparse_id * LOSS_WARPS + wid; i < n_fg; i += sparse_blocks * LOSS_WARPS) {
     const int r = P.fg_rows[i];
     const int l = level_of_row(P.pyr, r);
     // ld_head.py:246-252: a level without positives contributes no loss_im (and no gradient)
@@ -754,7 +759,7 @@ extern "C" int ldb200_ld_loss_fused(const ldb_pyramid* pyr, const ldb_loss_cfg* 
   const size_t gsz = P.grad_bf16 ? 2 : 4;
   LDB_CUDA(cudaMemsetAsync(losses, 0, sizeof(float) * LDB_NUM_TERMS * LDB_MAX_LEVELS, stream));
   if (wg) LDB_CUDA(cudaMemsetAsync(d_reg, 0, R * P.dreg_ld * gsz, stream));
-  const int grid = num_sms() * 2;
+  const int grid = num_sms() * 3;
   if (!P.grad_bf16 && !P.feat_bf16) ld_loss_fused_kernel<float, float><<<grid, LOSS_THREADS, 0, stream>>>(P);
   else if (!P.grad_bf16 && P.feat_bf16) ld_loss_fused_kernel<float, __nv_bfloat16><<<grid, LOSS_THREADS, 0, stream>>>(P);
   else if (P.grad_bf16 && !P.feat_bf16) ld_loss_fused_kernel<__nv_bfloat16, float><<<grid, LOSS_THREADS, 0, stream>>>(P);
