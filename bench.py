@@ -233,6 +233,24 @@ def main():
     ms_e2e = timed(run_e2e, args.steps)
     assert torch.isfinite(host_loss).all(), 'loss diverged'
 
+    # dominant kernel, timed live: conv_tc_kernel<256> on the head-tower shape (P3 level, 3x3 256->256), the
+    # single largest-FLOP launch of the step (32 forward + 16 dgrad launches of this shape per step)
+    from ld_b200 import ops as _ops
+    kx = torch.randn(n, 100, 168, 256, device=dev).bfloat16()
+    kw = _ops.pack_conv_weight(torch.randn(256, 256, 3, 3, device=dev) * 0.02)
+    ko = torch.empty(n, 100, 168, 256, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        _ops.conv2d_tc(kx, kw, 256, 3, 3, 1, 1, out=ko)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(20):
+        _ops.conv2d_tc(kx, kw, 256, 3, 3, 1, 1, out=ko)
+    k1.record()
+    torch.cuda.synchronize()
+    k_ms = k0.elapsed_time(k1) / 20
+    k_flop = 2.0 * n * 100 * 168 * 256 * 256 * 9
+
     if rank == 0:
         pk = peaks()
         ips = GLOBAL_BATCH * args.steps / (ms / 1e3)
@@ -248,10 +266,18 @@ def main():
                                                    + sum(b.numel() * 8 for b in gtl_pinned)) * world,
                             d2h_bytes_per_step=4 * world),
                    gpu_launches=int(launches),
-                   roofline=dict(bound='tensor', achieved=ach, peak=peak_tf, unit='TFLOP/s', frac=ach / peak_tf,
-                                 traffic=None,
-                                 note='conv MACs of the whole step (1.8356 TFLOP/image) / step time per GPU, against '
-                                      + ('measured sustained bf16 peak' if 'bf16_tflops_sustained' in pk else 'fallback peak')),
+                   roofline=dict(bound='tensor', kernel='conv_tc_kernel<256> head tower P3 3x3 256->256',
+                                 achieved=k_flop / k_ms / 1e9, peak=pk.get('bf16_tflops', 1590.0), unit='TFLOP/s',
+                                 frac=k_flop / k_ms / 1e9 / pk.get('bf16_tflops', 1590.0),
+                                 traffic=230.1e6 * n / 16,
+                                 note='algorithmic 2*N*H*W*Cin*Cout*9 FLOP per launch / live CUDA-event duration (20 '
+                                      'back-to-back launches), of ' + ('measured' if 'bf16_tflops' in pk else 'fallback')
+                                      + ' burst bf16 peak; traffic = dram read+write of the same launch from '
+                                        'profiles/r01_conv_head_p3_summary.txt (ncu --set full, batch 16)'),
+                   roofline_step=dict(bound='tensor', achieved=ach, peak=peak_tf, unit='TFLOP/s', frac=ach / peak_tf,
+                                      note='conv MACs of the whole step (1.8356 TFLOP/image) / step time per GPU, of '
+                                           + ('measured' if 'bf16_tflops_sustained' in pk else 'fallback')
+                                           + ' sustained bf16 peak'),
                    clocks=clocks)
         if world == 1 and not args.no_cpu_baseline:
             v, sec = cpu_reference_step(2, 1, 1)

@@ -128,12 +128,29 @@ class KnowledgeDistillationSingleStageDetector(SingleStageDetector):
             raise NotImplementedError('LDHead needs output_feature=True (kd_one_stage.py:73-76 mis-binds its '
                                       'arguments otherwise; both COCO LD configs set it)')
         im2col = ops.stem_im2col(img.float().contiguous())
-        x = self.extract_feat(img, im2col=im2col)
-        with torch.no_grad():
+        # the frozen teacher and the student only share the input: run the teacher on a second stream so its
+        # kernels fill the SMs the student's tails / latency-bound epilogues leave idle (also captured as a
+        # fork/join inside the CUDA graph)
+        main = torch.cuda.current_stream()
+        side = self._teacher_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side), torch.no_grad():
             teacher_x = self.teacher_model.extract_feat(img, im2col=im2col)
             out_teacher = self.teacher_model.bbox_head(teacher_x)
+        x = self.extract_feat(img, im2col=im2col)
+        main.wait_stream(side)
+        for t in list(teacher_x) + list(out_teacher[0]) + list(out_teacher[1]) + [im2col[0]]:
+            t.record_stream(main)
         return self.bbox_head.forward_train(x, out_teacher, teacher_x, img_metas, gt_bboxes, gt_labels,
                                             gt_bboxes_ignore)
+
+    def _teacher_stream(self):
+        dev = torch.cuda.current_device()
+        st = self.__dict__.get('_side_stream')
+        if st is None or st.device.index != dev:
+            st = torch.cuda.Stream(device=dev)
+            self.__dict__['_side_stream'] = st
+        return st
 
     def cuda(self, device=None):
         self.teacher_model.cuda(device=device)
