@@ -233,6 +233,12 @@ int ldb200_upsample_add_bwd(const void* dfine, void* dcoarse, int N, int Hf, int
 int ldb200_relu_bwd(const void* dy, const void* y, void* out, int64_t numel, void* stream);
 /* out[c] += sum_rows x[row, c]; x [rows, ld] (dtype LDB_BF16 / LDB_F32): conv-bias and BN-beta gradients. */
 int ldb200_colsum(const void* x, float* out, int64_t rows, int C, int ld, int dtype, void* stream);
+/* eval-mode BatchNorm (norm_eval=True, resnet.py:639-649) folded into the conv epilogue's per-channel affine:
+ * scale = gamma*rsqrt(var+eps), shift = beta - mean*scale; and the adjoint for the trainable gamma/beta. */
+int ldb200_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                   float* scale, float* shift, int C, void* stream);
+int ldb200_bn_fold_bwd(const float* d_scale, const float* d_shift, const float* mean, const float* var, float eps,
+                       float* dgamma, float* dbeta, int C, void* stream);
 /* torch.optim.SGD (momentum, weight decay, dampening 0) on a flat fp32 parameter buffer;
  * grad_scale folds the data-parallel mean.  configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py:53. */
 int ldb200_sgd_flat(float* w, const float* g, float* momentum_buf, int64_t n, float lr, float momentum,

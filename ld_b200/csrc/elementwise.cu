@@ -91,175 +91,207 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
 }
 
 // ---------------------------------------------------------------------------------------------
-// GroupNorm with 8 channels per group (256 ch / 32 groups): one thread owns one (pixel, group)
-// uint4.  x: [N, HW, C] bf16.  stats: [N, G, 2] fp32 (sum, sum of squares), accumulated.
+// GroupNorm with 8 channels per group (256 ch / 32 groups).  x: [N, HW, C] bf16.  One thread owns one group of
+// one pixel per step (a 16-byte load); a block is 32 groups x 8 pixel lanes and walks GN_PIX pixels of ONE image, so
+// mean / rstd / gamma / beta are loop invariants and a warp always reads one contiguous 512-byte pixel row.
+// stats: [N, G, 2] fp32 (sum, sum of squares), accumulated with one atomic pair per (block, group).
 constexpr int GN_CPG = 8;
-constexpr int GN_PIX_PER_BLOCK = 64;
+constexpr int GN_PIX = 256;       // pixels per block
+constexpr int GN_THREADS = 256;
 
-__global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats,
-                                                        int HW, int C) {
-  const int G = C / GN_CPG;          // threads along x cover the groups
-  const int n = blockIdx.y;
-  const int gpt = threadIdx.x % G;   // group of this thread
-  const int rows_par = blockDim.x / G;
-  const int r0 = threadIdx.x / G;
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats,
+                                                               int HW, int C) {
+  const int G = C / GN_CPG;
+  const int n = blockIdx.y, g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
+  const int p0 = blockIdx.x * GN_PIX, p1 = min(p0 + GN_PIX, HW);
+  const uint4* base = reinterpret_cast<const uint4*>(x + (size_t)n * HW * C) + g;
+  const int rs = C / 8;   // uint4 per pixel row
   float s = 0.f, ss = 0.f;
-  const int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
-  const int p1 = min(p0 + GN_PIX_PER_BLOCK, HW);
-  for (int p = p0 + r0; p < p1; p += rows_par) {
-    float v[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((size_t)n * HW + p) * C) + gpt), v);
+  int p = p0 + r0;
+  for (; p + 3 * lanes < p1; p += 4 * lanes) {
+    uint4 q[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      s += v[e];
-      ss += v[e] * v[e];
+    for (int u = 0; u < 4; ++u) q[u] = __ldg(base + (size_t)(p + u * lanes) * rs);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float v[8];
+      unpack8(q[u], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s += v[e]; ss += v[e] * v[e]; }
     }
   }
-  // combine the rows_par partials of each group through shared memory
-  __shared__ float sh[2][256];
+  for (; p < p1; p += lanes) {
+    float v[8];
+    unpack8(__ldg(base + (size_t)p * rs), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s += v[e]; ss += v[e] * v[e]; }
+  }
+  __shared__ float sh[2][GN_THREADS];
   sh[0][threadIdx.x] = s;
   sh[1][threadIdx.x] = ss;
   __syncthreads();
   if (threadIdx.x < G) {
     float a = 0.f, b = 0.f;
-    for (int r = 0; r < rows_par; ++r) {
-      a += sh[0][r * G + threadIdx.x];
-      b += sh[1][r * G + threadIdx.x];
-    }
+    for (int r = 0; r < lanes; ++r) { a += sh[0][r * G + threadIdx.x]; b += sh[1][r * G + threadIdx.x]; }
     atomicAdd(stats + ((size_t)n * G + threadIdx.x) * 2, a);
     atomicAdd(stats + ((size_t)n * G + threadIdx.x) * 2 + 1, b);
   }
 }
 
 // y = relu((x - mean) * rstd * gamma + beta)   (relu optional)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int N, int HW, int C, float eps, int relu) {
   const int G = C / GN_CPG;
-  const long long total = (long long)N * HW * G;
+  const int n = blockIdx.y, g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
+  const int p0 = blockIdx.x * GN_PIX, p1 = min(p0 + GN_PIX, HW);
   const float inv_m = 1.f / ((float)HW * GN_CPG);
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(t % G);
-    const int n = (int)(t / ((long long)HW * G));
-    const float s = __ldg(stats + ((size_t)n * G + g) * 2), ss = __ldg(stats + ((size_t)n * G + g) * 2 + 1);
-    const float mean = s * inv_m;
-    const float var = fmaxf(ss * inv_m - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
+  const float mean = __ldg(stats + ((size_t)n * G + g) * 2) * inv_m;
+  const float rstd = rsqrtf(fmaxf(__ldg(stats + ((size_t)n * G + g) * 2 + 1) * inv_m - mean * mean, 0.f) + eps);
+  float a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    a[e] = rstd * __ldg(gamma + g * GN_CPG + e);
+    b[e] = __ldg(beta + g * GN_CPG + e) - mean * a[e];
+  }
+  const int rs = C / 8;
+  const uint4* xin = reinterpret_cast<const uint4*>(x + (size_t)n * HW * C) + g;
+  uint4* yout = reinterpret_cast<uint4*>(y + (size_t)n * HW * C) + g;
+  int p = p0 + r0;
+  for (; p + 3 * lanes < p1; p += 4 * lanes) {
+    uint4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = __ldg(xin + (size_t)(p + u * lanes) * rs);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float v[8];
+      unpack8(q[u], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float o = v[e] * a[e] + b[e];
+        v[e] = relu ? fmaxf(o, 0.f) : o;
+      }
+      yout[(size_t)(p + u * lanes) * rs] = pack8(v);
+    }
+  }
+  for (; p < p1; p += lanes) {
     float v[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + t), v);
+    unpack8(__ldg(xin + (size_t)p * rs), v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int c = g * GN_CPG + e;
-      float o = (v[e] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      const float o = v[e] * a[e] + b[e];
       v[e] = relu ? fmaxf(o, 0.f) : o;
     }
-    reinterpret_cast<uint4*>(y)[t] = pack8(v);
+    yout[(size_t)p * rs] = pack8(v);
   }
 }
 
 // GroupNorm+ReLU backward, pass 1: per-(n,group) sums of dxh and dxh*xh, per-channel dgamma/dbeta.
 //   g = dy * (y > 0), xh = (x - mean)*rstd, dxh = g*gamma
 // red: [N, G, 2] fp32 accumulated; dgamma/dbeta: [C] fp32 accumulated.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(GN_THREADS)
 gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                     const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
                     const float* __restrict__ gamma, float* __restrict__ red, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, int HW, int C, float eps) {
   const int G = C / GN_CPG;
-  const int n = blockIdx.y;
-  const int gpt = threadIdx.x % G;
-  const int rows_par = blockDim.x / G;
-  const int r0 = threadIdx.x / G;
+  const int n = blockIdx.y, g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
+  const int p0 = blockIdx.x * GN_PIX, p1 = min(p0 + GN_PIX, HW);
   const float inv_m = 1.f / ((float)HW * GN_CPG);
-  const float s = __ldg(stats + ((size_t)n * G + gpt) * 2), ss = __ldg(stats + ((size_t)n * G + gpt) * 2 + 1);
-  const float mean = s * inv_m;
-  const float rstd = rsqrtf(fmaxf(ss * inv_m - mean * mean, 0.f) + eps);
-  float gam[8];
+  const float mean = __ldg(stats + ((size_t)n * G + g) * 2) * inv_m;
+  const float rstd = rsqrtf(fmaxf(__ldg(stats + ((size_t)n * G + g) * 2 + 1) * inv_m - mean * mean, 0.f) + eps);
+  float gam[8], acc[18];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) gam[e] = __ldg(gamma + gpt * GN_CPG + e);
-  float a = 0.f, b = 0.f, dg[8], db[8];
+  for (int e = 0; e < 8; ++e) gam[e] = __ldg(gamma + g * GN_CPG + e);
 #pragma unroll
-  for (int e = 0; e < 8; ++e) dg[e] = db[e] = 0.f;
-  const int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
-  const int p1 = min(p0 + GN_PIX_PER_BLOCK, HW);
-  for (int p = p0 + r0; p < p1; p += rows_par) {
-    const size_t o = ((size_t)n * HW + p) * C;
-    float vd[8], vy[8], vx[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + o) + gpt), vd);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(y + o) + gpt), vy);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + o) + gpt), vx);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float gg = vy[e] > 0.f ? vd[e] : 0.f;
-      const float xh = (vx[e] - mean) * rstd;
-      const float dxh = gg * gam[e];
-      a += dxh;
-      b += dxh * xh;
-      dg[e] += gg * xh;
-      db[e] += gg;
+  for (int e = 0; e < 18; ++e) acc[e] = 0.f;   // [0]=sum dxh, [1]=sum dxh*xh, [2..9]=dgamma, [10..17]=dbeta
+  const int rs = C / 8;
+  const size_t img = (size_t)n * HW * C;
+  const uint4* pdy = reinterpret_cast<const uint4*>(dy + img) + g;
+  const uint4* py = reinterpret_cast<const uint4*>(y + img) + g;
+  const uint4* px = reinterpret_cast<const uint4*>(x + img) + g;
+  for (int p = p0 + r0; p < p1; p += 2 * lanes) {
+    const bool two = p + lanes < p1;
+    uint4 q[6];
+    q[0] = __ldg(pdy + (size_t)p * rs); q[1] = __ldg(py + (size_t)p * rs); q[2] = __ldg(px + (size_t)p * rs);
+    if (two) {
+      q[3] = __ldg(pdy + (size_t)(p + lanes) * rs); q[4] = __ldg(py + (size_t)(p + lanes) * rs);
+      q[5] = __ldg(px + (size_t)(p + lanes) * rs);
     }
-  }
-  __shared__ float sh[2][256];
-  sh[0][threadIdx.x] = a;
-  sh[1][threadIdx.x] = b;
-  __syncthreads();
-  if (threadIdx.x < G) {
-    float ta = 0.f, tb = 0.f;
-    for (int r = 0; r < rows_par; ++r) {
-      ta += sh[0][r * G + threadIdx.x];
-      tb += sh[1][r * G + threadIdx.x];
-    }
-    atomicAdd(red + ((size_t)n * G + threadIdx.x) * 2, ta);
-    atomicAdd(red + ((size_t)n * G + threadIdx.x) * 2 + 1, tb);
-  }
-  // per-channel partials: reduce across the rows_par threads of the same group via smem, 8 rounds
-  for (int e = 0; e < 8; ++e) {
-    __syncthreads();
-    sh[0][threadIdx.x] = dg[e];
-    sh[1][threadIdx.x] = db[e];
-    __syncthreads();
-    if (threadIdx.x < G) {
-      float ta = 0.f, tb = 0.f;
-      for (int r = 0; r < rows_par; ++r) {
-        ta += sh[0][r * G + threadIdx.x];
-        tb += sh[1][r * G + threadIdx.x];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      float vd[8], vy[8], vx[8];
+      unpack8(q[3 * u], vd); unpack8(q[3 * u + 1], vy); unpack8(q[3 * u + 2], vx);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float gg = vy[e] > 0.f ? vd[e] : 0.f;
+        const float xh = (vx[e] - mean) * rstd;
+        const float dxh = gg * gam[e];
+        acc[0] += dxh;
+        acc[1] += dxh * xh;
+        acc[2 + e] += gg * xh;
+        acc[10 + e] += gg;
       }
-      atomicAdd(dgamma + threadIdx.x * GN_CPG + e, ta);
-      atomicAdd(dbeta + threadIdx.x * GN_CPG + e, tb);
     }
+  }
+  __shared__ float sh[18][GN_THREADS];
+#pragma unroll
+  for (int e = 0; e < 18; ++e) sh[e][threadIdx.x] = acc[e];
+  __syncthreads();
+  for (int o = threadIdx.x; o < 18 * G; o += GN_THREADS) {
+    const int e = o / G, gg = o % G;
+    float t = 0.f;
+    for (int r = 0; r < lanes; ++r) t += sh[e][r * G + gg];
+    if (e < 2) atomicAdd(red + ((size_t)n * G + gg) * 2 + e, t);
+    else if (e < 10) atomicAdd(dgamma + gg * GN_CPG + (e - 2), t);
+    else atomicAdd(dbeta + gg * GN_CPG + (e - 10), t);
   }
 }
 
 // pass 2: dx = rstd * (dxh - mean(dxh) - xh * mean(dxh*xh))
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(GN_THREADS)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                     const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
                     const float* __restrict__ gamma, const float* __restrict__ red, __nv_bfloat16* __restrict__ dx,
                     int N, int HW, int C, float eps) {
   const int G = C / GN_CPG;
-  const long long total = (long long)N * HW * G;
+  const int n = blockIdx.y, g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
+  const int p0 = blockIdx.x * GN_PIX, p1 = min(p0 + GN_PIX, HW);
   const float inv_m = 1.f / ((float)HW * GN_CPG);
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(t % G);
-    const int n = (int)(t / ((long long)HW * G));
-    const float s = __ldg(stats + ((size_t)n * G + g) * 2), ss = __ldg(stats + ((size_t)n * G + g) * 2 + 1);
-    const float mean = s * inv_m;
-    const float rstd = rsqrtf(fmaxf(ss * inv_m - mean * mean, 0.f) + eps);
-    const float m1 = __ldg(red + ((size_t)n * G + g) * 2) * inv_m, m2 = __ldg(red + ((size_t)n * G + g) * 2 + 1) * inv_m;
-    float vd[8], vy[8], vx[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + t), vd);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(y) + t), vy);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + t), vx);
+  const float mean = __ldg(stats + ((size_t)n * G + g) * 2) * inv_m;
+  const float rstd = rsqrtf(fmaxf(__ldg(stats + ((size_t)n * G + g) * 2 + 1) * inv_m - mean * mean, 0.f) + eps);
+  const float m1 = __ldg(red + ((size_t)n * G + g) * 2) * inv_m, m2 = __ldg(red + ((size_t)n * G + g) * 2 + 1) * inv_m;
+  float gam[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float gg = vy[e] > 0.f ? vd[e] : 0.f;
-      const float xh = (vx[e] - mean) * rstd;
-      const float dxh = gg * __ldg(gamma + g * GN_CPG + e);
-      vd[e] = rstd * (dxh - m1 - xh * m2);
+  for (int e = 0; e < 8; ++e) gam[e] = __ldg(gamma + g * GN_CPG + e);
+  const int rs = C / 8;
+  const size_t img = (size_t)n * HW * C;
+  const uint4* pdy = reinterpret_cast<const uint4*>(dy + img) + g;
+  const uint4* py = reinterpret_cast<const uint4*>(y + img) + g;
+  const uint4* px = reinterpret_cast<const uint4*>(x + img) + g;
+  uint4* pdx = reinterpret_cast<uint4*>(dx + img) + g;
+  for (int p = p0 + r0; p < p1; p += 2 * lanes) {
+    const bool two = p + lanes < p1;
+    uint4 q[6];
+    q[0] = __ldg(pdy + (size_t)p * rs); q[1] = __ldg(py + (size_t)p * rs); q[2] = __ldg(px + (size_t)p * rs);
+    if (two) {
+      q[3] = __ldg(pdy + (size_t)(p + lanes) * rs); q[4] = __ldg(py + (size_t)(p + lanes) * rs);
+      q[5] = __ldg(px + (size_t)(p + lanes) * rs);
     }
-    reinterpret_cast<uint4*>(dx)[t] = pack8(vd);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      float vd[8], vy[8], vx[8];
+      unpack8(q[3 * u], vd); unpack8(q[3 * u + 1], vy); unpack8(q[3 * u + 2], vx);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float gg = vy[e] > 0.f ? vd[e] : 0.f;
+        const float xh = (vx[e] - mean) * rstd;
+        vd[e] = rstd * (gg * gam[e] - m1 - xh * m2);
+      }
+      pdx[(size_t)(p + u * lanes) * rs] = pack8(vd);
+    }
   }
 }
 
@@ -389,6 +421,30 @@ __global__ void sgd_flat_dev_kernel(float* __restrict__ w, const float* __restri
   }
 }
 
+// Eval-mode BatchNorm folded to a per-channel affine (resnet.py:639-649 norm_eval=True):
+//   scale = gamma * rsqrt(var + eps), shift = beta - mean * scale      and its adjoint
+//   dgamma = (d_scale - d_shift * mean) * rsqrt(var + eps), dbeta = d_shift
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                               float* __restrict__ scale, float* __restrict__ shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float s = gamma[c] * rsqrtf(var[c] + eps);
+    scale[c] = s;
+    shift[c] = beta[c] - mean[c] * s;
+  }
+}
+__global__ void bn_fold_bwd_kernel(const float* __restrict__ d_scale, const float* __restrict__ d_shift,
+                                   const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                   float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float ds = d_scale ? d_scale[c] : 0.f, db = d_shift ? d_shift[c] : 0.f;
+    dgamma[c] = (ds - db * mean[c]) * rsqrtf(var[c] + eps);
+    dbeta[c] = db;
+  }
+}
+
 static int grid_for(long long total, int threads = 256, int cap = 148 * 16) {
   long long b = (total + threads - 1) / threads;
   if (b > cap) b = cap;
@@ -431,8 +487,8 @@ extern "C" int ldb200_gn_stats(const void* x, float* stats, int N, int HW, int C
   LDB_REQUIRE(x && stats, LDB_EINVAL, "gn_stats: null pointer");
   cudaStream_t s = (cudaStream_t)stream_;
   LDB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * N * G, s));
-  dim3 grid((HW + GN_PIX_PER_BLOCK - 1) / GN_PIX_PER_BLOCK, N);
-  gn_stats_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, stats, HW, C);
+  dim3 grid((HW + GN_PIX - 1) / GN_PIX, N);
+  gn_stats_kernel<<<grid, GN_THREADS, 0, s>>>((const __nv_bfloat16*)x, stats, HW, C);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -442,9 +498,9 @@ extern "C" int ldb200_gn_apply(const void* x, const float* stats, const float* g
   int e = gn_check(C, G);
   if (e) return e;
   LDB_REQUIRE(x && stats && gamma && beta && y, LDB_EINVAL, "gn_apply: null pointer");
-  const long long total = (long long)N * HW * G;
-  gn_apply_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, stats, gamma, beta,
-                                                                      (__nv_bfloat16*)y, N, HW, C, eps, relu);
+  dim3 grid((HW + GN_PIX - 1) / GN_PIX, N);
+  gn_apply_kernel<<<grid, GN_THREADS, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, stats, gamma, beta,
+                                                                  (__nv_bfloat16*)y, N, HW, C, eps, relu);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -457,12 +513,11 @@ extern "C" int ldb200_gn_relu_bwd(const void* dy, const void* y, const void* x, 
   LDB_REQUIRE(dy && y && x && stats && gamma && red_ws && dgamma && dbeta && dx, LDB_EINVAL, "gn_relu_bwd: null pointer");
   cudaStream_t s = (cudaStream_t)stream_;
   LDB_CUDA(cudaMemsetAsync(red_ws, 0, sizeof(float) * 2 * N * G, s));
-  dim3 grid((HW + GN_PIX_PER_BLOCK - 1) / GN_PIX_PER_BLOCK, N);
-  gn_bwd_stats_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)x,
+  dim3 grid((HW + GN_PIX - 1) / GN_PIX, N);
+  gn_bwd_stats_kernel<<<grid, GN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)x,
                                            stats, gamma, red_ws, dgamma, dbeta, HW, C, eps);
   LDB_CUDA(cudaGetLastError());
-  const long long total = (long long)N * HW * G;
-  gn_bwd_apply_kernel<<<grid_for(total), 256, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
+  gn_bwd_apply_kernel<<<grid, GN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
                                                       (const __nv_bfloat16*)x, stats, gamma, red_ws, (__nv_bfloat16*)dx,
                                                       N, HW, C, eps);
   LDB_CUDA(cudaGetLastError());
@@ -519,6 +574,22 @@ extern "C" int ldb200_sgd_flat_dev(float* w, const float* g, float* buf, int64_t
   LDB_REQUIRE(w && g && buf && hyper_dev && n >= 0, LDB_EINVAL, "sgd_flat_dev: bad argument");
   if (n == 0) return 0;
   sgd_flat_dev_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream_>>>(w, g, buf, n, hyper_dev);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                              float* scale, float* shift, int C, void* stream_) {
+  LDB_REQUIRE(gamma && beta && mean && var && scale && shift && C > 0, LDB_EINVAL, "bn_fold: bad argument");
+  bn_fold_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(gamma, beta, mean, var, eps, scale, shift, C);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_bn_fold_bwd(const float* d_scale, const float* d_shift, const float* mean, const float* var,
+                                  float eps, float* dgamma, float* dbeta, int C, void* stream_) {
+  LDB_REQUIRE(mean && var && dgamma && dbeta && C > 0, LDB_EINVAL, "bn_fold_bwd: bad argument");
+  bn_fold_bwd_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(d_scale, d_shift, mean, var, eps, dgamma, dbeta, C);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }

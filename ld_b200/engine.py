@@ -196,6 +196,31 @@ def gn_relu(x, gamma, beta, groups=32, eps=1e-5):
     return GNReLU.apply(x, gamma, beta, groups, eps)
 
 
+class _BNFold(torch.autograd.Function):
+    """(gamma, beta) -> (scale, shift) of an eval-mode BatchNorm: one launch forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, gamma, beta, mean, var, eps):
+        from . import lib as L
+        scale, shift = torch.empty_like(gamma), torch.empty_like(gamma)
+        L.check(L.load().ldb200_bn_fold(L.ptr(gamma.detach()), L.ptr(beta.detach()), L.ptr(mean), L.ptr(var), float(eps),
+                                        L.ptr(scale), L.ptr(shift), gamma.numel(), L.stream_ptr()), 'ldb200_bn_fold')
+        ctx.save_for_backward(mean, var)
+        ctx.eps = eps
+        return scale, shift
+
+    @staticmethod
+    def backward(ctx, d_scale, d_shift):
+        from . import lib as L
+        mean, var = ctx.saved_tensors
+        dg, db = torch.empty_like(mean), torch.empty_like(mean)
+        L.check(L.load().ldb200_bn_fold_bwd(L.ptr(None if d_scale is None else d_scale.contiguous()),
+                                            L.ptr(None if d_shift is None else d_shift.contiguous()), L.ptr(mean),
+                                            L.ptr(var), float(ctx.eps), L.ptr(dg), L.ptr(db), mean.numel(),
+                                            L.stream_ptr()), 'ldb200_bn_fold_bwd')
+        return dg, db, None, None, None
+
+
 def bn_affine(bn):
     """Eval-mode BatchNorm (norm_eval=True, resnet.py:639-649) as a per-channel affine (scale, shift);
     differentiable w.r.t. the (trainable) gamma / beta."""
@@ -206,6 +231,8 @@ def bn_affine(bn):
         hit = bn.__dict__.get('_ldb_affine')
         if hit is not None and hit[0] == key:
             return hit[1]
+    if not frozen and bn.weight.is_cuda:
+        return _BNFold.apply(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
     rstd = torch.rsqrt(bn.running_var + bn.eps)
     scale = bn.weight * rstd
     shift = bn.bias - bn.running_mean * scale
