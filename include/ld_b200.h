@@ -190,6 +190,10 @@ typedef struct {
 } ldb_conv_desc;
 
 int ldb200_conv2d_tc(const ldb_conv_desc* desc, void* stream);
+/* `count` (<= 5) convolutions sharing weights, taps, stride and epilogue configuration -- the five FPN levels of
+ * a level-shared GFLHead conv (gfl_head.py:145-183 `multi_apply(forward_single, feats, scales)`) -- as ONE
+ * persistent launch over the concatenated tile list (small levels no longer waste whole waves). */
+int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, void* stream);
 
 /* Weight gradient of the same convolution (autograd's conv backward-weight), split-K over pixel
  * tiles with fp32 atomics:

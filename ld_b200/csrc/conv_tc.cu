@@ -31,28 +31,41 @@ constexpr int TILE_M = 128;
 constexpr int KCH = 64;                        // channels per k-block (128 B of bf16)
 constexpr int A_TILE_BYTES = TILE_M * KCH * 2;  // 16 KB
 
-struct ConvParams {
+constexpr int CONV_MAX_SEG = 5;   // pyramid levels batched into one launch (shared weights, one tile list)
+
+struct ConvSeg {            // geometry of one segment (= one FPN level of a level-shared head conv, or the whole conv)
   int N, HO, WO;            // tile space = logical output pixels
-  int TH, TW, tiles_y, tiles_x, tiles_n;
+  int TH, TW, tiles_y, tiles_x, tw_shift;
+  // output addressing: element offset of pixel (n,y,x) = ((n*OH + y*oys + oyo)*OW + x*oxs + oxo)*ldc
+  int OH, OW, oys, oyo, oxs, oxo;
+  void* out;
+  const __nv_bfloat16* add_src;  // optional add, nearest-resampled from [N, add_H, add_W, add_ld]
+  int add_H, add_W;
+  const __nv_bfloat16* mask_src; // optional: multiply by (mask_src > 0), same addressing as out (bf16, ld = mask_ld)
+  int pf_add, pf_mask;      // L2-prefetch the residual / mask tile with TMA while the main loop runs
+};
+
+struct ConvParams {
+  int nseg;
+  int seg_tile0[CONV_MAX_SEG + 1];   // first tile of each segment; [nseg] = total tiles
+  ConvSeg seg[CONV_MAX_SEG];
+  int tiles_n;
   int Cout, Cin;
   int ntaps;
   int tap_dx[9], tap_dy[9], tap_wk[9];
   int sx, sy;               // input coordinate = out coordinate * s + tap offset
-  // output addressing: element offset of pixel (n,y,x) = ((n*OH + y*oys + oyo)*OW + x*oxs + oxo)*ldc
-  int OH, OW, oys, oyo, oxs, oxo, ldc;
-  void* out;
+  int ldc;
   int out_f32;
   const float* scale;       // [Cout] or null (1)
   const float* bias;        // [Cout] or null (0)
-  const __nv_bfloat16* add_src;  // optional add, nearest-resampled from [N, add_H, add_W, add_ld]
-  int add_H, add_W, add_ld;
-  const __nv_bfloat16* mask_src; // optional: multiply by (mask_src > 0), same addressing as out (bf16, ld = mask_ld)
-  int mask_ld;
+  int add_ld, mask_ld;
   int relu;
   int accumulate;           // result += previous out (before ReLU / mask)
-  int vec_ok;               // leading dimensions allow 4-channel vector accesses
-  int tw_shift;             // log2(TW)
-  int pf_add, pf_mask;      // L2-prefetch the residual / mask tile with TMA while the main loop runs
+  int vec_ok;               // leading dimensions allow 16-byte vector accesses
+};
+
+struct ConvMaps {           // per-segment TMA descriptors: A operand, residual prefetch, mask prefetch
+  CUtensorMap a[CONV_MAX_SEG], r[CONV_MAX_SEG], m[CONV_MAX_SEG];
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -156,14 +169,14 @@ template <int BN> struct ConvCfg {
                                     ((uint32_t)(TILE_M >> 4) << 24);
 };
 
-__device__ __forceinline__ size_t out_offset(const ConvParams& p, int n, int y, int x) {
+__device__ __forceinline__ size_t out_offset(const ConvSeg& p, int n, int y, int x) {
   return (((size_t)n * p.OH + (size_t)(y * p.oys + p.oyo)) * p.OW + (size_t)(x * p.oxs + p.oxo));
 }
 
 template <int BN>
 __global__ void __launch_bounds__(ConvCfg<BN>::THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmM, const ConvParams p) {
+conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN>;
   extern __shared__ unsigned char conv_smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)conv_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -178,7 +191,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cchunks = p.Cin / KCH;
   const int kblocks = p.ntaps * cchunks;
-  const int total_tiles = p.N * p.tiles_y * p.tiles_x * p.tiles_n;
+  const int total_tiles = p.seg_tile0[p.nseg];
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -192,7 +205,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (warp == 2) {
@@ -211,23 +224,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t % p.tiles_n;
-        int sp = t / p.tiles_n;
-        const int tx = sp % p.tiles_x;
-        sp /= p.tiles_x;
-        const int ty = sp % p.tiles_y;
-        const int n = sp / p.tiles_y;
-        const int x0 = tx * p.TW * p.sx, y0 = ty * p.TH * p.sy;
+        int sg = 0;
+        while (sg + 1 < p.nseg && t >= p.seg_tile0[sg + 1]) ++sg;
+        const ConvSeg& S = p.seg[sg];
+        const int tl = t - p.seg_tile0[sg];
+        const int nt = tl % p.tiles_n;
+        int sp = tl / p.tiles_n;
+        const int tx = sp % S.tiles_x;
+        sp /= S.tiles_x;
+        const int ty = sp % S.tiles_y;
+        const int n = sp / S.tiles_y;
+        const int x0 = tx * S.TW * p.sx, y0 = ty * S.TH * p.sy;
         // the epilogue will read this tile's residual / ReLU-mask rows a whole main loop from now: pull them into
         // L2 with one TMA prefetch each so those loads see L2 latency instead of HBM latency
-        if (p.pf_add) tma_prefetch_4d(&tmR, nt * BN, tx * p.TW, ty * p.TH, n);
-        if (p.pf_mask) tma_prefetch_4d(&tmM, nt * BN, tx * p.TW, ty * p.TH, n);
+        if (S.pf_add) tma_prefetch_4d(&maps.r[sg], nt * BN, tx * S.TW, ty * S.TH, n);
+        if (S.pf_mask) tma_prefetch_4d(&maps.m[sg], nt * BN, tx * S.TW, ty * S.TH, n);
         for (int kb = 0; kb < kblocks; ++kb) {
           const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * KCH;
           mbarrier_wait(&empty[stage], phase ^ 1);
           unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
           mbarrier_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          tma_load_4d(sa, &tmA, &full[stage], c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], n);
+          tma_load_4d(sa, &maps.a[sg], &full[stage], c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], n);
           tma_load_2d(sa + A_TILE_BYTES, &tmB, &full[stage], p.tap_wk[tap] + c0, nt * BN);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -274,20 +291,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = t % p.tiles_n;
-      int sp = t / p.tiles_n;
-      const int tx = sp % p.tiles_x;
-      sp /= p.tiles_x;
-      const int ty = sp % p.tiles_y;
-      const int n = sp / p.tiles_y;
+      int sg = 0;
+      while (sg + 1 < p.nseg && t >= p.seg_tile0[sg + 1]) ++sg;
+      const ConvSeg& S = p.seg[sg];
+      const int tl = t - p.seg_tile0[sg];
+      const int nt = tl % p.tiles_n;
+      int sp = tl / p.tiles_n;
+      const int tx = sp % S.tiles_x;
+      sp /= S.tiles_x;
+      const int ty = sp % S.tiles_y;
+      const int n = sp / S.tiles_y;
       const int m = ew * 32 + lane;
-      const int y = ty * p.TH + (m >> p.tw_shift), x = tx * p.TW + (m & (p.TW - 1));
-      const bool pix_ok = (y < p.HO) && (x < p.WO);
-      const size_t pix = pix_ok ? out_offset(p, n, y, x) : 0;
+      const int y = ty * S.TH + (m >> S.tw_shift), x = tx * S.TW + (m & (S.TW - 1));
+      const bool pix_ok = (y < S.HO) && (x < S.WO);
+      const size_t pix = pix_ok ? out_offset(S, n, y, x) : 0;
       const __nv_bfloat16* addp = nullptr;
-      if (p.add_src && pix_ok) {
-        const int ay = (int)(((long long)y * p.add_H) / p.HO), ax = (int)(((long long)x * p.add_W) / p.WO);
-        addp = p.add_src + (((size_t)n * p.add_H + ay) * p.add_W + ax) * (size_t)p.add_ld;
+      if (S.add_src && pix_ok) {
+        const int ay = (int)(((long long)y * S.add_H) / S.HO), ax = (int)(((long long)x * S.add_W) / S.WO);
+        addp = S.add_src + (((size_t)n * S.add_H + ay) * S.add_W + ax) * (size_t)p.add_ld;
       }
       const int col0 = nt * BN + half * GCOLS;
       const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * GCOLS);
@@ -337,14 +358,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (p.accumulate) {
             if (p.out_f32) {
-              const float* o = (const float*)p.out + pix * (size_t)p.ldc + cbase;
+              const float* o = (const float*)S.out + pix * (size_t)p.ldc + cbase;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const float4 o4 = *reinterpret_cast<const float4*>(o + j);
                 v[j] += o4.x; v[j + 1] += o4.y; v[j + 2] += o4.z; v[j + 3] += o4.w;
               }
             } else {
-              const __nv_bfloat16* o = (const __nv_bfloat16*)p.out + pix * (size_t)p.ldc + cbase;
+              const __nv_bfloat16* o = (const __nv_bfloat16*)S.out + pix * (size_t)p.ldc + cbase;
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 const uint4 q = *reinterpret_cast<const uint4*>(o + j);
@@ -362,8 +383,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-          if (p.mask_src) {
-            const __nv_bfloat16* mk = p.mask_src + pix * (size_t)p.mask_ld + cbase;
+          if (S.mask_src) {
+            const __nv_bfloat16* mk = S.mask_src + pix * (size_t)p.mask_ld + cbase;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               const uint4 q = __ldg(reinterpret_cast<const uint4*>(mk + j));
@@ -374,11 +395,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           if (p.out_f32) {
-            float* o = (float*)p.out + pix * (size_t)p.ldc + cbase;
+            float* o = (float*)S.out + pix * (size_t)p.ldc + cbase;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {
-            __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * (size_t)p.ldc + cbase;
+            __nv_bfloat16* o = (__nv_bfloat16*)S.out + pix * (size_t)p.ldc + cbase;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint4 q;
@@ -399,12 +420,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.bias) vv += __ldg(p.bias + c);
             if (addp) vv += __bfloat162float(addp[c]);
             if (p.accumulate)
-              vv += p.out_f32 ? ((const float*)p.out)[pix * (size_t)p.ldc + c]
-                              : __bfloat162float(((const __nv_bfloat16*)p.out)[pix * (size_t)p.ldc + c]);
+              vv += p.out_f32 ? ((const float*)S.out)[pix * (size_t)p.ldc + c]
+                              : __bfloat162float(((const __nv_bfloat16*)S.out)[pix * (size_t)p.ldc + c]);
             if (p.relu) vv = fmaxf(vv, 0.f);
-            if (p.mask_src && !(__bfloat162float(p.mask_src[pix * (size_t)p.mask_ld + c]) > 0.f)) vv = 0.f;
-            if (p.out_f32) ((float*)p.out)[pix * (size_t)p.ldc + c] = vv;
-            else ((__nv_bfloat16*)p.out)[pix * (size_t)p.ldc + c] = __float2bfloat16_rn(vv);
+            if (S.mask_src && !(__bfloat162float(S.mask_src[pix * (size_t)p.mask_ld + c]) > 0.f)) vv = 0.f;
+            if (p.out_f32) ((float*)S.out)[pix * (size_t)p.ldc + c] = vv;
+            else ((__nv_bfloat16*)S.out)[pix * (size_t)p.ldc + c] = __float2bfloat16_rn(vv);
           }
         }
       }
@@ -651,80 +672,50 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 static int g_conv_sms = 0;
 
 template <int BN>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmM,
-                       const ConvParams& p, cudaStream_t stream) {
+static int launch_conv(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
   static bool attr = false;
   if (!attr) {
     LDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr = true;
   }
-  if (!g_conv_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_conv_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  const int total = p.N * p.tiles_y * p.tiles_x * p.tiles_n;
+  const int total = p.seg_tile0[p.nseg];
   const int grid = total < g_conv_sms ? total : g_conv_sms;
-  conv_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(tmA, tmB, tmR, tmM, p);
+  conv_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(maps, tmB, p);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
 
-}  // namespace ldb
-
-using namespace ldb;
-
-extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
-  LDB_REQUIRE(d && d->in && d->weight && d->out, LDB_EINVAL, "conv2d_tc: null pointer");
-  LDB_REQUIRE(d->Cin > 0, LDB_EINVAL, "conv2d_tc: Cin");
+// geometry + tensor maps of one segment
+static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& common, ConvSeg* g, CUtensorMap* tmA,
+                         CUtensorMap* tmR, CUtensorMap* tmM) {
+  LDB_REQUIRE(d->in && d->out, LDB_EINVAL, "conv2d_tc: null pointer");
   LDB_REQUIRE(d->in_ld >= d->Cin && d->in_ld % 8 == 0, LDB_EINVAL, "conv2d_tc: in_ld must be >= Cin and a multiple of 8");
-  LDB_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, LDB_EINVAL, "conv2d_tc: ntaps");
-  LDB_REQUIRE(d->N >= 1 && d->HO >= 1 && d->WO >= 1 && d->Cout >= 1, LDB_EINVAL, "conv2d_tc: shape");
-  LDB_REQUIRE(d->sx >= 1 && d->sy >= 1 && d->sx <= 8 && d->sy <= 8, LDB_EINVAL, "conv2d_tc: stride");
-  LDB_REQUIRE(d->out_ld >= d->Cout, LDB_EINVAL, "conv2d_tc: out_ld < Cout");
-  LDB_REQUIRE(((uintptr_t)d->in & 15) == 0 && ((uintptr_t)d->weight & 15) == 0 && ((uintptr_t)d->out & 15) == 0,
-              LDB_EINVAL, "conv2d_tc: pointers must be 16-byte aligned");
-  // the fast epilogue path moves 16 bytes per access: bf16 rows need ld % 8 == 0, fp32 rows ld % 4 == 0
-  const int vec_ok = (d->out_ld % (d->out_f32 ? 4 : 8) == 0) && (!d->mask_src || (d->mask_ld ? d->mask_ld : d->out_ld) % 8 == 0) &&
-                     (!d->add_src || (d->add_ld ? d->add_ld : d->Cout) % 8 == 0) &&
-                     (!d->scale || ((uintptr_t)d->scale & 15) == 0) && (!d->bias || ((uintptr_t)d->bias & 15) == 0);
-  cudaStream_t stream = (cudaStream_t)stream_;
-  ConvParams p;
-  memset(&p, 0, sizeof(p));
-  // channels beyond Cin inside the last 64-wide k-block are TMA out-of-bounds reads (zeros); the
-  // weight rows must hold finite values there (tap_wk spacing >= round_up(Cin, 64))
-  p.N = d->N; p.HO = d->HO; p.WO = d->WO; p.Cout = d->Cout; p.Cin = (d->Cin + KCH - 1) / KCH * KCH; p.ntaps = d->ntaps;
-  for (int t = 0; t < d->ntaps; ++t) {
-    p.tap_dx[t] = d->tap_dx[t]; p.tap_dy[t] = d->tap_dy[t]; p.tap_wk[t] = d->tap_wk[t];
-  }
-  p.sx = d->sx; p.sy = d->sy;
-  p.OH = d->OH ? d->OH : d->HO; p.OW = d->OW ? d->OW : d->WO;
-  p.oys = d->oys ? d->oys : 1; p.oxs = d->oxs ? d->oxs : 1; p.oyo = d->oyo; p.oxo = d->oxo;
-  p.ldc = d->out_ld; p.out = d->out; p.out_f32 = d->out_f32;
-  p.scale = d->scale; p.bias = d->bias;
-  p.add_src = (const __nv_bfloat16*)d->add_src;
-  p.add_H = d->add_H ? d->add_H : p.OH; p.add_W = d->add_W ? d->add_W : p.OW;
-  p.add_ld = d->add_ld ? d->add_ld : d->Cout;
-  p.mask_src = (const __nv_bfloat16*)d->mask_src; p.mask_ld = d->mask_ld ? d->mask_ld : d->out_ld;
-  p.relu = d->relu; p.accumulate = d->accumulate; p.vec_ok = vec_ok;
-  if (p.add_src) LDB_REQUIRE(((uintptr_t)p.add_src & 15) == 0 && p.add_ld % 8 == 0, LDB_EINVAL, "conv2d_tc: add_src alignment");
-
-  // tile shape: flattened pixels for "flat" problems, else the TH x TW (TH*TW = 128) minimising padding waste
-  CUtensorMap tmA, tmB;
+  LDB_REQUIRE(d->N >= 1 && d->HO >= 1 && d->WO >= 1, LDB_EINVAL, "conv2d_tc: shape");
+  LDB_REQUIRE(((uintptr_t)d->in & 15) == 0 && ((uintptr_t)d->out & 15) == 0, LDB_EINVAL,
+              "conv2d_tc: pointers must be 16-byte aligned");
+  memset(g, 0, sizeof(*g));
+  g->N = d->N; g->HO = d->HO; g->WO = d->WO;
+  g->OH = d->OH ? d->OH : d->HO; g->OW = d->OW ? d->OW : d->WO;
+  g->oys = d->oys ? d->oys : 1; g->oxs = d->oxs ? d->oxs : 1; g->oyo = d->oyo; g->oxo = d->oxo;
+  g->out = d->out;
+  g->add_src = (const __nv_bfloat16*)d->add_src;
+  g->add_H = d->add_H ? d->add_H : g->OH; g->add_W = d->add_W ? d->add_W : g->OW;
+  g->mask_src = (const __nv_bfloat16*)d->mask_src;
+  if (g->add_src) LDB_REQUIRE(((uintptr_t)g->add_src & 15) == 0, LDB_EINVAL, "conv2d_tc: add_src alignment");
   if (d->flat) {
     LDB_REQUIRE(d->ntaps == 1 && d->sx == 1 && d->sy == 1, LDB_EINVAL, "conv2d_tc: flat mode needs a 1x1 stride-1 conv");
     const long long M = (long long)d->N * d->HO * d->WO;
-    p.N = 1; p.HO = 1; p.WO = (int)M; p.TH = 1; p.TW = TILE_M;
-    p.OH = 1; p.OW = (int)M; p.oys = p.oxs = 1; p.oyo = p.oxo = 0;
-    LDB_REQUIRE(!p.add_src || (p.add_H == (d->OH ? d->OH : d->HO) && p.add_W == (d->OW ? d->OW : d->WO)), LDB_ENOSUP,
+    LDB_REQUIRE(!g->add_src || (g->add_H == g->OH && g->add_W == g->OW), LDB_ENOSUP,
                 "conv2d_tc: flat mode cannot resample add_src");
-    if (p.add_src) { p.add_H = 1; p.add_W = (int)M; }
+    g->N = 1; g->HO = 1; g->WO = (int)M; g->TH = 1; g->TW = TILE_M;
+    g->OH = 1; g->OW = (int)M; g->oys = g->oxs = 1; g->oyo = g->oxo = 0;
+    g->add_H = 1; g->add_W = (int)M;
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)M, 1, 1};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)d->in_ld * 2 * (cuuint64_t)M,
                              (cuuint64_t)d->in_ld * 2 * (cuuint64_t)M};
     cuuint32_t box[4] = {KCH, TILE_M, 1, 1}, es[4] = {1, 1, 1, 1};
-    int e = encode_map(&tmA, d->in, 4, dims, strides, box, es, "A(flat)");
+    int e = encode_map(tmA, d->in, 4, dims, strides, box, es, "A(flat)");
     if (e) return e;
   } else {
     int best_th = 8, best_tiles = 1 << 30;
@@ -737,49 +728,123 @@ extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
         best_th = th;
       }
     }
-    p.TH = best_th; p.TW = TILE_M / best_th;
+    g->TH = best_th; g->TW = TILE_M / best_th;
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)d->in_ld * 2 * d->W,
                              (cuuint64_t)d->in_ld * 2 * d->W * d->H};
-    cuuint32_t box[4] = {KCH, (cuuint32_t)(p.TW * d->sx), (cuuint32_t)(p.TH * d->sy), 1};
+    cuuint32_t box[4] = {KCH, (cuuint32_t)(g->TW * d->sx), (cuuint32_t)(g->TH * d->sy), 1};
     cuuint32_t es[4] = {1, (cuuint32_t)d->sx, (cuuint32_t)d->sy, 1};
-    int e = encode_map(&tmA, d->in, 4, dims, strides, box, es, "A");
+    int e = encode_map(tmA, d->in, 4, dims, strides, box, es, "A");
     if (e) return e;
   }
-  p.tiles_y = (p.HO + p.TH - 1) / p.TH;
-  p.tiles_x = (p.WO + p.TW - 1) / p.TW;
-  p.tw_shift = 0;
-  while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
+  g->tiles_y = (g->HO + g->TH - 1) / g->TH;
+  g->tiles_x = (g->WO + g->TW - 1) / g->TW;
+  g->tw_shift = 0;
+  while ((1 << g->tw_shift) < g->TW) ++g->tw_shift;
+  // optional L2 prefetch maps for the residual / mask tensors (identity pixel mapping, same extent as the output)
+  *tmR = *tmA;
+  *tmM = *tmA;
+  const bool ident = g->oys == 1 && g->oxs == 1 && g->oyo == 0 && g->oxo == 0;
+  auto aux_map = [&](CUtensorMap* m, const void* base, int ld, const char* what) -> int {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)g->OW, (cuuint64_t)g->OH, (cuuint64_t)g->N};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * g->OW, (cuuint64_t)ld * 2 * g->OW * g->OH};
+    cuuint32_t box[4] = {(cuuint32_t)(d->Cout < BN ? (d->Cout + 7) / 8 * 8 : BN), (cuuint32_t)g->TW, (cuuint32_t)g->TH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    return encode_map(m, base, 4, dims, strides, box, es, what, CU_TENSOR_MAP_SWIZZLE_NONE);
+  };
+  if (g->add_src && ident && g->add_H == g->OH && g->add_W == g->OW && common.add_ld % 8 == 0 && !d->out_f32) {
+    if (aux_map(tmR, g->add_src, common.add_ld, "residual prefetch") == 0) g->pf_add = 1;
+  }
+  if (g->mask_src && ident && common.mask_ld % 8 == 0) {
+    if (aux_map(tmM, g->mask_src, common.mask_ld, "mask prefetch") == 0) g->pf_mask = 1;
+  }
+  return 0;
+}
+
+}  // namespace ldb
+
+using namespace ldb;
+
+// `count` convolutions that share weights, taps, stride and epilogue configuration (the five FPN levels of a
+// level-shared GFL head conv, gfl_head.py:145-183) as ONE launch over the concatenated tile list.
+extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, void* stream_) {
+  LDB_REQUIRE(descs && count >= 1 && count <= CONV_MAX_SEG, LDB_EINVAL, "conv2d_tc: 1..%d segments", CONV_MAX_SEG);
+  const ldb_conv_desc* d = &descs[0];
+  LDB_REQUIRE(d->weight, LDB_EINVAL, "conv2d_tc: null weight");
+  LDB_REQUIRE(d->Cin > 0 && d->Cout >= 1, LDB_EINVAL, "conv2d_tc: channels");
+  LDB_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, LDB_EINVAL, "conv2d_tc: ntaps");
+  LDB_REQUIRE(d->sx >= 1 && d->sy >= 1 && d->sx <= 8 && d->sy <= 8, LDB_EINVAL, "conv2d_tc: stride");
+  LDB_REQUIRE(d->out_ld >= d->Cout, LDB_EINVAL, "conv2d_tc: out_ld < Cout");
+  LDB_REQUIRE(((uintptr_t)d->weight & 15) == 0, LDB_EINVAL, "conv2d_tc: weight must be 16-byte aligned");
+  LDB_REQUIRE(d->w_k % 8 == 0, LDB_EINVAL, "conv2d_tc: weight row length must be a multiple of 8");
+  for (int i = 1; i < count; ++i) {
+    const ldb_conv_desc* e = &descs[i];
+    LDB_REQUIRE(e->weight == d->weight && e->Cin == d->Cin && e->Cout == d->Cout && e->w_k == d->w_k &&
+                e->ntaps == d->ntaps && e->sx == d->sx && e->sy == d->sy && e->out_ld == d->out_ld &&
+                e->out_f32 == d->out_f32 && e->scale == d->scale && e->bias == d->bias && e->relu == d->relu &&
+                e->accumulate == d->accumulate && e->flat == d->flat && e->in_ld == d->in_ld &&
+                (e->add_src != nullptr) == (d->add_src != nullptr) && e->add_ld == d->add_ld &&
+                (e->mask_src != nullptr) == (d->mask_src != nullptr) && e->mask_ld == d->mask_ld &&
+                memcmp(e->tap_dx, d->tap_dx, sizeof(d->tap_dx)) == 0 && memcmp(e->tap_dy, d->tap_dy, sizeof(d->tap_dy)) == 0 &&
+                memcmp(e->tap_wk, d->tap_wk, sizeof(d->tap_wk)) == 0,
+                LDB_EINVAL, "conv2d_tc_multi: segment %d does not share weights / taps / epilogue with segment 0", i);
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!g_conv_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_conv_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  // channels beyond Cin inside the last 64-wide k-block are TMA out-of-bounds reads (zeros); the weight rows must
+  // hold finite values there (tap_wk spacing >= round_up(Cin, 64))
+  p.Cout = d->Cout; p.Cin = (d->Cin + KCH - 1) / KCH * KCH; p.ntaps = d->ntaps;
+  for (int t = 0; t < d->ntaps; ++t) {
+    p.tap_dx[t] = d->tap_dx[t]; p.tap_dy[t] = d->tap_dy[t]; p.tap_wk[t] = d->tap_wk[t];
+  }
+  p.sx = d->sx; p.sy = d->sy;
+  p.ldc = d->out_ld; p.out_f32 = d->out_f32;
+  p.scale = d->scale; p.bias = d->bias;
+  p.add_ld = d->add_ld ? d->add_ld : d->Cout;
+  p.mask_ld = d->mask_ld ? d->mask_ld : d->out_ld;
+  p.relu = d->relu; p.accumulate = d->accumulate;
+  // the fast epilogue path moves 16 bytes per access: bf16 rows need ld % 8 == 0, fp32 rows ld % 4 == 0
+  p.vec_ok = (d->out_ld % (d->out_f32 ? 4 : 8) == 0) && (!d->mask_src || p.mask_ld % 8 == 0) &&
+             (!d->add_src || p.add_ld % 8 == 0) && (!d->scale || ((uintptr_t)d->scale & 15) == 0) &&
+             (!d->bias || ((uintptr_t)d->bias & 15) == 0);
   const int BN = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
   p.tiles_n = (d->Cout + BN - 1) / BN;
+  p.nseg = count;
+  ConvMaps maps;
+  int tile0 = 0;
+  for (int i = 0; i < count; ++i) {
+    int e = build_segment(&descs[i], BN, p, &p.seg[i], &maps.a[i], &maps.r[i], &maps.m[i]);
+    if (e) return e;
+    p.seg_tile0[i] = tile0;
+    tile0 += p.seg[i].N * p.seg[i].tiles_y * p.seg[i].tiles_x * p.tiles_n;
+  }
+  for (int i = count; i <= CONV_MAX_SEG; ++i) p.seg_tile0[i] = tile0;
+  for (int i = count; i < CONV_MAX_SEG; ++i) { maps.a[i] = maps.a[0]; maps.r[i] = maps.a[0]; maps.m[i] = maps.a[0]; }
+  CUtensorMap tmB;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->w_k, (cuuint64_t)d->Cout};
     cuuint64_t strides[1] = {(cuuint64_t)d->w_k * 2};
     cuuint32_t box[2] = {KCH, (cuuint32_t)BN}, es[2] = {1, 1};
-    LDB_REQUIRE(d->w_k % 8 == 0, LDB_EINVAL, "conv2d_tc: weight row length must be a multiple of 8");
     int e = encode_map(&tmB, d->weight, 2, dims, strides, box, es, "B");
     if (e) return e;
   }
-  // optional L2 prefetch maps for the residual / mask tensors (identity pixel mapping, same extent as the output)
-  CUtensorMap tmR = tmA, tmM = tmA;
-  const bool ident = p.oys == 1 && p.oxs == 1 && p.oyo == 0 && p.oxo == 0;
-  auto aux_map = [&](CUtensorMap* m, const void* base, int ld, int HH, int WW, const char* what) -> int {
-    cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)WW, (cuuint64_t)HH, (cuuint64_t)p.N};
-    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * WW, (cuuint64_t)ld * 2 * WW * HH};
-    cuuint32_t box[4] = {(cuuint32_t)(d->Cout < BN ? (d->Cout + 7) / 8 * 8 : BN), (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    return encode_map(m, base, 4, dims, strides, box, es, what, CU_TENSOR_MAP_SWIZZLE_NONE);
-  };
-  if (p.add_src && ident && p.add_H == p.OH && p.add_W == p.OW && p.add_ld % 8 == 0 && !d->out_f32) {
-    if (aux_map(&tmR, p.add_src, p.add_ld, p.OH, p.OW, "residual prefetch") == 0) p.pf_add = 1;
-  }
-  if (p.mask_src && ident && p.mask_ld % 8 == 0) {
-    if (aux_map(&tmM, p.mask_src, p.mask_ld, p.OH, p.OW, "mask prefetch") == 0) p.pf_mask = 1;
-  }
-  if (BN == 256) return launch_conv<256>(tmA, tmB, tmR, tmM, p, stream);
-  if (BN == 128) return launch_conv<128>(tmA, tmB, tmR, tmM, p, stream);
-  return launch_conv<64>(tmA, tmB, tmR, tmM, p, stream);
+  if (BN == 256) return launch_conv<256>(maps, tmB, p, stream);
+  if (BN == 128) return launch_conv<128>(maps, tmB, p, stream);
+  return launch_conv<64>(maps, tmB, p, stream);
 }
+
+extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
+  LDB_REQUIRE(d, LDB_EINVAL, "conv2d_tc: null descriptor");
+  return ldb200_conv2d_tc_multi(d, 1, stream_);
+}
+
+namespace ldb {
 
 template <int BN>
 static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p, cudaStream_t stream) {
@@ -795,6 +860,8 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const Wg
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
+
+}  // namespace ldb
 
 extern "C" int ldb200_conv2d_wgrad_tc(const ldb_wgrad_desc* d, void* stream_) {
   LDB_REQUIRE(d && d->dy && d->x && d->dw, LDB_EINVAL, "wgrad_tc: null pointer");

@@ -337,59 +337,70 @@ __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv
   }
 }
 
-// out[c] += sum_rows x[row, c]   (x: [M, ld] bf16 or f32, C channels, C % 8 == 0 for bf16)
+// out[c] += sum_rows x[row, c]   (x: [M, ld] bf16 or f32; C % 8 == 0 for bf16, C % 4 == 0 for f32)
+// block = (channel groups) x (row lanes); each block owns a band of rows, 4 independent 16-byte loads in flight
+// per thread, ONE shared-memory pass to fold the row lanes, one atomic per (block, channel).
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long M,
-                                                      int C, int ld) {
-  // each block handles a band of rows; thread layout: tx over channel groups, ty over rows
-  const int cg = (sizeof(T) == 2) ? C / 8 : C / 4;
-  const int VW = (sizeof(T) == 2) ? 8 : 4;
-  const int rows_par = 256 / min(cg, 256);
-  const int tx = threadIdx.x % min(cg, 256), ty = threadIdx.x / min(cg, 256);
-  const long long band = (M + gridDim.x - 1) / gridDim.x;
-  const long long m0 = (long long)blockIdx.x * band, m1 = (m0 + band < M) ? m0 + band : M;
-  __shared__ float sh[256];
-  for (int g = tx; g < cg; g += min(cg, 256)) {
-    float acc[8];
+                                                      int C, int ld, int rows_per_block) {
+  constexpr int VW = (sizeof(T) == 2) ? 8 : 4;
+  const int cg = C / VW;                       // vector columns
+  const int cgb = cg < 256 ? cg : 256;          // vector columns handled per pass by this block
+  const int lanes = 256 / cgb;
+  const int tx = threadIdx.x % cgb, ty = threadIdx.x / cgb;
+  const long long m0 = (long long)blockIdx.x * rows_per_block;
+  const long long m1 = (m0 + rows_per_block < M) ? m0 + rows_per_block : M;
+  __shared__ float sh[VW][256];
+  for (int g = tx; g < cg; g += cgb) {          // cg > 256 only for C > 2048 bf16
+    float acc[VW];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    if (ty < rows_par) {
+    for (int e = 0; e < VW; ++e) acc[e] = 0.f;
+    if (ty < lanes) {
       long long m = m0 + ty;
-      if (sizeof(T) == 2) {
-        for (; m + 3LL * rows_par < m1; m += 4LL * rows_par) {   // 4 independent 16-byte loads in flight
+      for (; m + 3LL * lanes < m1; m += 4LL * lanes) {
+        if (sizeof(T) == 2) {
           uint4 q[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            q[u] = __ldg(reinterpret_cast<const uint4*>((const __nv_bfloat16*)x + (size_t)(m + (long long)u * rows_par) * ld) + g);
+            q[u] = __ldg(reinterpret_cast<const uint4*>((const __nv_bfloat16*)x + (size_t)(m + (long long)u * lanes) * ld) + g);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             float v[8];
             unpack8(q[u], v);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] += v[e];
+            for (int e = 0; e < VW; ++e) acc[e] += v[e];
           }
+        } else {
+          float4 q[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            q[u] = __ldg(reinterpret_cast<const float4*>((const float*)x + (size_t)(m + (long long)u * lanes) * ld) + g);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { acc[0] += q[u].x; acc[1] += q[u].y; acc[2] += q[u].z; acc[3] += q[u].w; }
         }
       }
-      for (; m < m1; m += rows_par) {
+      for (; m < m1; m += lanes) {
         if (sizeof(T) == 2) {
           float v[8];
           unpack8(__ldg(reinterpret_cast<const uint4*>((const __nv_bfloat16*)x + (size_t)m * ld) + g), v);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] += v[e];
+          for (int e = 0; e < VW; ++e) acc[e] += v[e];
         } else {
           const float4 v = __ldg(reinterpret_cast<const float4*>((const float*)x + (size_t)m * ld) + g);
           acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
         }
       }
     }
-    for (int e = 0; e < VW; ++e) {
-      __syncthreads();
-      sh[threadIdx.x] = acc[e];
-      __syncthreads();
-      if (ty == 0) {
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < VW; ++e) sh[e][threadIdx.x] = acc[e];
+    __syncthreads();
+    for (int o = threadIdx.x; o < VW * cgb; o += 256) {
+      const int e = o / cgb, gx = o % cgb;
+      if (gx + (g - tx) < cg) {
         float t = 0.f;
-        for (int r = 0; r < rows_par; ++r) t += sh[r * min(cg, 256) + tx];
-        atomicAdd(out + g * VW + e, t);
+        for (int r = 0; r < lanes; ++r) t += sh[e][r * cgb + gx];
+        atomicAdd(out + (size_t)(g - tx + gx) * VW + e, t);
       }
     }
   }
@@ -546,14 +557,16 @@ extern "C" int ldb200_relu_bwd(const void* dy, const void* y, void* out, int64_t
 extern "C" int ldb200_colsum(const void* x, float* out, int64_t rows, int C, int ld, int dtype, void* stream_) {
   LDB_REQUIRE(x && out && rows >= 0 && C > 0 && ld >= C, LDB_EINVAL, "colsum: bad argument");
   if (rows == 0) return 0;
-  int grid = (int)((rows + 255) / 256);
-  if (grid > 148 * 8) grid = 148 * 8;
+  // aim for ~4 blocks per SM, at least 32 rows per block
+  long long rpb = (rows + 148 * 4 - 1) / (148 * 4);
+  if (rpb < 32) rpb = 32;
+  const int grid = (int)((rows + rpb - 1) / rpb);
   if (dtype == LDB_BF16) {
     LDB_REQUIRE(C % 8 == 0 && ld % 8 == 0, LDB_EINVAL, "colsum: bf16 needs C, ld %% 8 == 0");
-    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, out, rows, C, ld);
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, out, rows, C, ld, (int)rpb);
   } else {
     LDB_REQUIRE(C % 4 == 0 && ld % 4 == 0, LDB_EINVAL, "colsum: f32 needs C, ld %% 4 == 0");
-    colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream_>>>((const float*)x, out, rows, C, ld);
+    colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream_>>>((const float*)x, out, rows, C, ld, (int)rpb);
   }
   LDB_CUDA(cudaGetLastError());
   return 0;

@@ -117,15 +117,16 @@ class GFLHead(nn.Module):
     # ------------------------------------------------------------------ forward
     def towers(self, feats):
         """feats: NCHW-shaped level tensors -> per-level (cls_feat, reg_feat) NHWC bf16."""
-        out = []
-        for x in feats:
-            cf = rf = nhwc(x)
-            for m in self.cls_convs:
-                cf = m(cf)
-            for m in self.reg_convs:
-                rf = m(rf)
-            out.append((cf, rf))
-        return out
+        xs = [nhwc(x) for x in feats]
+        if len(xs) > 5:
+            raise NotImplementedError('more than 5 pyramid levels')
+        cfs, rfs = xs, xs
+        for mc, mr in zip(self.cls_convs, self.reg_convs):   # all levels of one tower layer in one launch
+            cs = engine.conv_levels(mc.conv._cl(), cfs)
+            cfs = [engine.gn_relu(c, mc.gn.weight, mc.gn.bias, mc.gn.num_groups, mc.gn.eps) for c in cs]
+            rs = engine.conv_levels(mr.conv._cl(), rfs)
+            rfs = [engine.gn_relu(r, mr.gn.weight, mr.gn.bias, mr.gn.num_groups, mr.gn.eps) for r in rs]
+        return list(zip(cfs, rfs))
 
     def final_convs(self, tower_out, cls_rows, reg_rows):
         """gfl_cls / gfl_reg*scale (gfl_head.py:181-182) written as fp32 NHWC rows (row space)."""
@@ -133,15 +134,18 @@ class GFLHead(nn.Module):
         wc, wr = engine.packed_weight(self.gfl_cls._cl()), engine.packed_weight(self.gfl_reg._cl())
         bc = self.gfl_cls.bias.detach()
         nb = 4 * (self.reg_max + 1)
+        cls_outs = []
         for (cf, rf), sc in zip(tower_out, self.scales):
             n, h, w, _ = cf.shape
             cnt = n * h * w
             s = sc.scale.detach()
-            ops.conv2d_tc(cf, wc, self.cls_out_channels, 3, 3, 1, 1, out=cls_rows[o:o + cnt].view(n, h, w, -1),
-                          bias=bc)
+            cls_outs.append(cls_rows[o:o + cnt].view(n, h, w, -1))
             ops.conv2d_tc(rf, wr, nb, 3, 3, 1, 1, out=reg_rows[o:o + cnt].view(n, h, w, -1),
                           scale=s.expand(nb).contiguous(), bias=(self.gfl_reg.bias.detach() * s).contiguous())
             o += cnt
+        # gfl_cls shares weights AND epilogue (bias) across levels: one launch for the whole pyramid
+        ops.conv2d_tc_multi([t[0] for t in tower_out], wc, self.cls_out_channels, 3, 3, 1, 1, outs=cls_outs,
+                            bias=bc.contiguous())
 
     def alloc_rows(self, feats):
         n = feats[0].shape[0]
@@ -244,10 +248,13 @@ class _LDLossFn(torch.autograd.Function):
             blk = torch.zeros(d_reg.shape[1], dtype=torch.float32, device=dev)
             ops.colsum(d_reg[o:o + cnt], blk)
             g_br += blk[:NB] * s
-            g_cf.append(engine.conv_dgrad(gc, w_cls, None, 1, 1, (h, w)))
+            g_cf.append(gc)
             g_rf.append(engine.conv_dgrad(gr, w_reg, s.expand(NB), 1, 1, (h, w)))
             g_x.append(None if x_dense is None else x_dense[o:o + cnt].view(n, h, w, -1))
             o += cnt
+        wd, cop = engine.dgrad_weight(w_cls, None)
+        taps = [(1 - s_, 1 - r_, (r_ * 3 + s_) * cop) for r_ in range(3) for s_ in range(3)]
+        g_cf = ops.conv2d_tc_multi(g_cf, wd, ci, 3, 3, 1, 1, taps=taps)
         g_wc = Gc.view(C, 3, 3, ci).permute(0, 3, 1, 2)
         g_wr = g_wr.view(NB, 3, 3, ci).permute(0, 3, 1, 2)
         return (None, None, *g_cf, *g_rf, *g_x, g_wc, g_bc, g_wr, g_br, *g_scales)

@@ -355,3 +355,36 @@ def res_block(x, main, downsample=None):
         s, b = bn_affine(downsample[1])
         params += [downsample[0]._cl(), s, b]
     return ResBlockFn.apply(x, tuple(strides), tuple(pads), downsample is not None, *params)
+
+
+class ConvLevelsFn(torch.autograd.Function):
+    """A level-shared 3x3 head conv (no bias / norm handled by the caller) on all FPN levels in ONE tcgen05 launch
+    forward and ONE for the data gradients; weight gradients accumulate level by level into `weight.grad`."""
+
+    @staticmethod
+    def forward(ctx, weight, pad, *xs):
+        co, ci, kh, kw = weight.shape
+        ys = ops.conv2d_tc_multi(list(xs), packed_weight(weight), co, kh, kw, 1, pad)
+        ctx.pad = pad
+        ctx.save_for_backward(weight, *xs)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        weight, xs = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+        pad = ctx.pad
+        co, ci, kh, kw = weight.shape
+        gs = [g.contiguous() for g in gs]
+        if ctx.needs_input_grad[0]:
+            for g, x in zip(gs, xs):
+                _wgrad_into(weight, g, x, None, 1, pad, False)
+        dxs = [None] * len(xs)
+        if any(ctx.needs_input_grad[2:]):
+            wd, cop = dgrad_weight(weight, None)
+            taps = [(pad - s, pad - r, (r * kw + s) * cop) for r in range(kh) for s in range(kw)]
+            dxs = ops.conv2d_tc_multi(gs, wd, ci, kh, kw, 1, pad, taps=taps)
+        return (None, None, *dxs)
+
+
+def conv_levels(weight, xs, pad=1):
+    return list(ConvLevelsFn.apply(weight, pad, *xs))

@@ -196,12 +196,8 @@ def pack_conv_weight_dgrad(w: torch.Tensor) -> torch.Tensor:
     return pack_conv_weight(w.transpose(0, 1))
 
 
-def conv2d_tc(x, w_packed, cout, kh=1, kw=1, stride=1, pad=0, out=None, out_dtype=torch.bfloat16,
-              scale=None, bias=None, add=None, mask=None, relu=False, accumulate=False, flat=None,
-              taps=None, out_hw=None, out_map=None):
-    """NHWC bf16 convolution on tcgen05 (ldb200_conv2d_tc).  x: [N,H,W,Cin] bf16 contiguous (or a
-    channel slice with stride(2) = ld).  Returns [N,HO,WO,Cout] NHWC `out_dtype`."""
-    lib = L.load()
+def _conv_desc(d, x, w_packed, cout, kh, kw, stride, pad, out, out_dtype, scale, bias, add, mask, relu, accumulate,
+               flat, taps, out_hw, out_map):
     assert x.dtype == torch.bfloat16 and x.dim() == 4
     n, h, w_, cin = x.shape
     in_ld = x.stride(2)
@@ -211,7 +207,6 @@ def conv2d_tc(x, w_packed, cout, kh=1, kw=1, stride=1, pad=0, out=None, out_dtyp
         wo = (w_ + 2 * pad - kw) // stride + 1
     else:
         ho, wo = out_hw
-    d = L.ConvDesc()
     d.in_ = x.data_ptr()
     d.N, d.H, d.W, d.Cin, d.in_ld = n, h, w_, cin, in_ld
     d.weight = w_packed.data_ptr()
@@ -238,12 +233,10 @@ def conv2d_tc(x, w_packed, cout, kh=1, kw=1, stride=1, pad=0, out=None, out_dtyp
         (_, _), (d.oys, d.oyo, d.oxs, d.oxo) = out_map
     d.out_ld = out.stride(2)
     d.out_f32 = int(out.dtype == torch.float32)
-    keep = [x, w_packed, out]
     for name, t in (('scale', scale), ('bias', bias)):
         if t is not None:
             assert t.dtype == torch.float32 and t.numel() == cout and t.is_contiguous()
             setattr(d, name, t.data_ptr())
-            keep.append(t)
     if add is not None:
         assert add.dtype == torch.bfloat16 and add.stride(3) == 1
         d.add_src, d.add_H, d.add_W, d.add_ld = add.data_ptr(), add.shape[1], add.shape[2], add.stride(2)
@@ -251,19 +244,34 @@ def conv2d_tc(x, w_packed, cout, kh=1, kw=1, stride=1, pad=0, out=None, out_dtyp
         assert mask.dtype == torch.bfloat16 and mask.shape[:3] == out.shape[:3]
         d.mask_src, d.mask_ld = mask.data_ptr(), mask.stride(2)
     d.relu, d.accumulate = int(relu), int(accumulate)
-    L.check(lib.ldb200_conv2d_tc(C.byref(d), L.stream_ptr()), 'ldb200_conv2d_tc')
     return out
 
 
-# ------------------------------------------------------------------------------------ glue kernels
-def stem_im2col(img):
-    """img [N,3,H,W] f32 NCHW -> ([N*HO*WO, 192] bf16, HO, WO)."""
-    n, c, h, w = img.shape
-    assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
-    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-    out = torch.empty(n * ho * wo, 192, dtype=torch.bfloat16, device=img.device)
-    L.check(L.load().ldb200_stem_im2col(L.ptr(img), L.ptr(out), n, h, w, L.stream_ptr()), 'ldb200_stem_im2col')
-    return out, ho, wo
+def conv2d_tc(x, w_packed, cout, kh=1, kw=1, stride=1, pad=0, out=None, out_dtype=torch.bfloat16,
+              scale=None, bias=None, add=None, mask=None, relu=False, accumulate=False, flat=None,
+              taps=None, out_hw=None, out_map=None):
+    """NHWC bf16 convolution on tcgen05 (ldb200_conv2d_tc).  x: [N,H,W,Cin] bf16 contiguous (or a
+    channel slice with stride(2) = ld).  Returns [N,HO,WO,Cout] NHWC `out_dtype`."""
+    d = L.ConvDesc()
+    out = _conv_desc(d, x, w_packed, cout, kh, kw, stride, pad, out, out_dtype, scale, bias, add, mask, relu,
+                     accumulate, flat, taps, out_hw, out_map)
+    L.check(L.load().ldb200_conv2d_tc(C.byref(d), L.stream_ptr()), 'ldb200_conv2d_tc')
+    return out
+
+
+def conv2d_tc_multi(xs, w_packed, cout, kh=1, kw=1, stride=1, pad=0, outs=None, out_dtype=torch.bfloat16,
+                    scale=None, bias=None, masks=None, relu=False, taps=None):
+    """The same convolution on several inputs (the FPN levels of a level-shared head conv) in ONE launch."""
+    n = len(xs)
+    descs = (L.ConvDesc * n)()
+    res = []
+    for i, x in enumerate(xs):
+        res.append(_conv_desc(descs[i], x, w_packed, cout, kh, kw, stride, pad, None if outs is None else outs[i],
+                              out_dtype, scale, bias, None, None if masks is None else masks[i], relu, False, False,
+                              taps, None if taps is None else tuple(x.shape[1:3]), None))
+    L.check(L.load().ldb200_conv2d_tc_multi(descs, n, L.stream_ptr()), 'ldb200_conv2d_tc_multi')
+    return res
+
 
 
 def maxpool3x3s2(x):

@@ -199,3 +199,19 @@ def test_glue_kernels():
         ops.sgd_flat(wmine, gg * (it + 1), buf, 0.01, 0.9, 1e-4, 1.0, first_step=(it == 0))
     torch.cuda.synchronize()
     check(wmine, p.detach(), 1e-6)
+
+
+def test_conv_multi_level_equals_per_level():
+    """The five FPN levels of a level-shared head conv in ONE launch == five single launches (bit-identical)."""
+    from ld_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(3)
+    sizes = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+    for cout, out_dtype, bias in ((256, torch.bfloat16, False), (80, torch.float32, True)):
+        wt = ops.pack_conv_weight(torch.randn(cout, 256, 3, 3, device='cuda', generator=g) * 0.03)
+        b = torch.randn(cout, device='cuda', generator=g) if bias else None
+        xs = [torch.randn(2, h, w, 256, device='cuda', generator=g).bfloat16() for h, w in sizes]
+        ys = ops.conv2d_tc_multi(xs, wt, cout, 3, 3, 1, 1, out_dtype=out_dtype, bias=b)
+        for x, y in zip(xs, ys):
+            one = ops.conv2d_tc(x, wt, cout, 3, 3, 1, 1, out_dtype=out_dtype, bias=b)
+            assert torch.equal(y, one)
+    torch.cuda.synchronize()
