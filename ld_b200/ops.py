@@ -274,6 +274,17 @@ def conv2d_tc_multi(xs, w_packed, cout, kh=1, kw=1, stride=1, pad=0, outs=None, 
 
 
 
+# ------------------------------------------------------------------------------------ glue kernels
+def stem_im2col(img):
+    """img [N,3,H,W] f32 NCHW -> ([N*HO*WO, 192] bf16, HO, WO)."""
+    n, c, h, w = img.shape
+    assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    out = torch.empty(n * ho * wo, 192, dtype=torch.bfloat16, device=img.device)
+    L.check(L.load().ldb200_stem_im2col(L.ptr(img), L.ptr(out), n, h, w, L.stream_ptr()), 'ldb200_stem_im2col')
+    return out, ho, wo
+
+
 def maxpool3x3s2(x):
     n, h, w, c = x.shape
     out = torch.empty(n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c, dtype=x.dtype, device=x.device)
