@@ -238,7 +238,8 @@ int ldb200_relu_bwd(const void* dy, const void* y, void* out, int64_t numel, voi
 /* out[c] += sum_rows x[row, c]; x [rows, ld] (dtype LDB_BF16 / LDB_F32): conv-bias and BN-beta gradients. */
 int ldb200_colsum(const void* x, float* out, int64_t rows, int C, int ld, int dtype, void* stream);
 /* eval-mode BatchNorm (norm_eval=True, resnet.py:639-649) folded into the conv epilogue's per-channel affine:
- * scale = gamma*rsqrt(var+eps), shift = beta - mean*scale; and the adjoint for the trainable gamma/beta. */
+ * scale = gamma*rsqrt(var+eps), shift = beta - mean*scale; and the adjoint for the trainable gamma/beta
+ * (bn_fold_bwd ACCUMULATES into dgamma / dbeta, i.e. straight into the parameter gradient buffers). */
 int ldb200_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                    float* scale, float* shift, int C, void* stream);
 int ldb200_bn_fold_bwd(const float* d_scale, const float* d_shift, const float* mean, const float* var, float eps,

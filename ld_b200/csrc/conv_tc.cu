@@ -905,7 +905,9 @@ extern "C" int ldb200_conv2d_wgrad_tc(const ldb_wgrad_desc* d, void* stream_) {
   p.ci_tiles = (d->Cin + BN - 1) / BN;
   const int ptiles = p.N * p.tiles_y * p.tiles_x;
   const int base_units = p.co_tiles * p.ci_tiles * p.ntaps;
-  int splits = (2 * g_conv_sms + base_units - 1) / base_units;
+  // one wave of work units: every extra split costs a 128 x BN fp32 tile of L2 atomics and the mainloop per unit
+  // shrinks, so fill the SMs once (round to nearest) instead of twice
+  int splits = (g_conv_sms + base_units / 2) / base_units;
   if (splits > ptiles) splits = ptiles;
   if (splits < 1) splits = 1;
   p.splits = splits;

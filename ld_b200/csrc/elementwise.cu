@@ -395,12 +395,22 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
 #pragma unroll
     for (int e = 0; e < VW; ++e) sh[e][threadIdx.x] = acc[e];
     __syncthreads();
-    for (int o = threadIdx.x; o < VW * cgb; o += 256) {
-      const int e = o / cgb, gx = o % cgb;
-      if (gx + (g - tx) < cg) {
-        float t = 0.f;
-        for (int r = 0; r < lanes; ++r) t += sh[e][r * cgb + gx];
-        atomicAdd(out + (size_t)(g - tx + gx) * VW + e, t);
+    // one thread per vector column folds the row lanes and issues 16-byte vector atomics (same-address atomic
+    // contention between blocks, not bandwidth, bounds this kernel)
+    if (threadIdx.x < cgb && threadIdx.x + (g - tx) < cg) {
+      float t[VW];
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        t[e] = 0.f;
+        for (int r = 0; r < lanes; ++r) t[e] += sh[e][r * cgb + threadIdx.x];
+      }
+      float* o = out + (size_t)(g - tx + threadIdx.x) * VW;
+      if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+        for (int e = 0; e < VW; e += 4) atomicAdd(reinterpret_cast<float4*>(o + e), make_float4(t[e], t[e + 1], t[e + 2], t[e + 3]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < VW; ++e) atomicAdd(o + e, t[e]);
       }
     }
   }
@@ -451,8 +461,8 @@ __global__ void bn_fold_bwd_kernel(const float* __restrict__ d_scale, const floa
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     const float ds = d_scale ? d_scale[c] : 0.f, db = d_shift ? d_shift[c] : 0.f;
-    dgamma[c] = (ds - db * mean[c]) * rsqrtf(var[c] + eps);
-    dbeta[c] = db;
+    dgamma[c] += (ds - db * mean[c]) * rsqrtf(var[c] + eps);   // accumulates into the parameter gradients
+    dbeta[c] += db;
   }
 }
 
@@ -557,8 +567,8 @@ extern "C" int ldb200_relu_bwd(const void* dy, const void* y, void* out, int64_t
 extern "C" int ldb200_colsum(const void* x, float* out, int64_t rows, int C, int ld, int dtype, void* stream_) {
   LDB_REQUIRE(x && out && rows >= 0 && C > 0 && ld >= C, LDB_EINVAL, "colsum: bad argument");
   if (rows == 0) return 0;
-  // aim for ~4 blocks per SM, at least 32 rows per block
-  long long rpb = (rows + 148 * 4 - 1) / (148 * 4);
+  // two blocks per SM (each extra block is one more contended atomic per channel), at least 32 rows per block
+  long long rpb = (rows + 148 * 2 - 1) / (148 * 2);
   if (rpb < 32) rpb = 32;
   const int grid = (int)((rows + rpb - 1) / rpb);
   if (dtype == LDB_BF16) {

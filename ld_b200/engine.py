@@ -205,20 +205,22 @@ class _BNFold(torch.autograd.Function):
         scale, shift = torch.empty_like(gamma), torch.empty_like(gamma)
         L.check(L.load().ldb200_bn_fold(L.ptr(gamma.detach()), L.ptr(beta.detach()), L.ptr(mean), L.ptr(var), float(eps),
                                         L.ptr(scale), L.ptr(shift), gamma.numel(), L.stream_ptr()), 'ldb200_bn_fold')
-        ctx.save_for_backward(mean, var)
+        ctx.save_for_backward(mean, var, gamma, beta)
         ctx.eps = eps
         return scale, shift
 
     @staticmethod
     def backward(ctx, d_scale, d_shift):
         from . import lib as L
-        mean, var = ctx.saved_tensors
-        dg, db = torch.empty_like(mean), torch.empty_like(mean)
+        mean, var, gamma, beta = ctx.saved_tensors
+        for p_ in (gamma, beta):     # accumulate straight into the (flat-buffer) parameter gradients
+            if p_.grad is None:
+                p_.grad = torch.zeros_like(p_)
         L.check(L.load().ldb200_bn_fold_bwd(L.ptr(None if d_scale is None else d_scale.contiguous()),
                                             L.ptr(None if d_shift is None else d_shift.contiguous()), L.ptr(mean),
-                                            L.ptr(var), float(ctx.eps), L.ptr(dg), L.ptr(db), mean.numel(),
-                                            L.stream_ptr()), 'ldb200_bn_fold_bwd')
-        return dg, db, None, None, None
+                                            L.ptr(var), float(ctx.eps), L.ptr(gamma.grad), L.ptr(beta.grad),
+                                            mean.numel(), L.stream_ptr()), 'ldb200_bn_fold_bwd')
+        return None, None, None, None, None
 
 
 def bn_affine(bn):
