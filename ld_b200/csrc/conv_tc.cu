@@ -20,6 +20,7 @@
 //   Scale), residual / nearest-upsample add, ReLU or ReLU-mask, optional accumulate -> NHWC store).
 //   Two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -153,10 +154,16 @@ __device__ __forceinline__ uint64_t smem_desc_k128(uint32_t saddr) {
   return d;
 }
 
-template <int BN> struct ConvCfg {
+// SHORTK: convolutions whose whole reduction is <= 4 k-blocks (1x1 convs with Cin <= 256: the bottleneck "expand"
+// convs and their dgrads).  They are bound by the epilogue's memory traffic, not by the MMAs: run TWO CTAs per SM
+// (2 pipeline stages, BN <= 128 so that both fit the 512 TMEM columns) so that one CTA's epilogue loads/stores
+// overlap the other's.
+template <int BN, bool SHORTK = false> struct ConvCfg {
   static constexpr int B_TILE_BYTES = BN * KCH * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = SHORTK ? 2 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int MIN_BLOCKS = SHORTK ? 2 : 1;
+  static_assert(!SHORTK || BN <= 128, "two resident CTAs need 2 * (2*BN) <= 512 TMEM columns");
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int STAGING_BYTES = 0;
   // epilogue warp groups of 4 warps (one per TMEM lane quadrant); each group owns BN/EPI_GROUPS columns.
@@ -173,11 +180,11 @@ __device__ __forceinline__ size_t out_offset(const ConvSeg& p, int n, int y, int
   return (((size_t)n * p.OH + (size_t)(y * p.oys + p.oyo)) * p.OW + (size_t)(x * p.oxs + p.oxo));
 }
 
-template <int BN>
-__global__ void __launch_bounds__(ConvCfg<BN>::THREADS, 1)
+template <int BN, bool SHORTK>
+__global__ void __launch_bounds__(ConvCfg<BN, SHORTK>::THREADS, ConvCfg<BN, SHORTK>::MIN_BLOCKS)
 conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, SHORTK>;
   extern __shared__ unsigned char conv_smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)conv_smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* staging = smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -314,15 +321,18 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
       const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * GCOLS);
       mbarrier_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      uint32_t rbuf[2][32];
-      if (col0 < p.Cout) tmem_ld32_nowait(tbase, rbuf[0]);
-#pragma unroll
+      // SHORTK (two CTAs per SM, 85-register budget): one TMEM buffer, chunks strictly one after the other -- the
+      // second CTA provides the latency hiding.  Otherwise the next chunk's tcgen05.ld is issued one chunk ahead.
+      uint32_t rbuf[SHORTK ? 1 : 2][32];
+      if (!SHORTK && col0 < p.Cout) tmem_ld32_nowait(tbase, rbuf[0]);
+#pragma unroll(SHORTK ? 1 : NCH)
       for (int ch = 0; ch < NCH; ++ch) {
         const int cbase = col0 + ch * 32;
         if (cbase >= p.Cout) break;   // warp-uniform
+        if (SHORTK) tmem_ld32_nowait(tbase + ch * 32, rbuf[0]);
         tmem_ld_wait();
-        if (ch + 1 < NCH && cbase + 32 < p.Cout) tmem_ld32_nowait(tbase + (ch + 1) * 32, rbuf[(ch + 1) & 1]);
-        const uint32_t* r = rbuf[ch & 1];
+        if (!SHORTK && ch + 1 < NCH && cbase + 32 < p.Cout) tmem_ld32_nowait(tbase + (ch + 1) * 32, rbuf[(ch + 1) & 1]);
+        const uint32_t* r = rbuf[SHORTK ? 0 : (ch & 1)];
         if (!pix_ok) continue;
         const bool full = (cbase + 32 <= p.Cout) && p.vec_ok;   // warp-uniform fast path
         float v[32];
@@ -671,17 +681,18 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 
 static int g_conv_sms = 0;
 
-template <int BN>
+template <int BN, bool SHORTK>
 static int launch_conv(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, SHORTK>;
   static bool attr = false;
   if (!attr) {
-    LDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    LDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, SHORTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr = true;
   }
   const int total = p.seg_tile0[p.nseg];
-  const int grid = total < g_conv_sms ? total : g_conv_sms;
-  conv_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(maps, tmB, p);
+  const int slots = g_conv_sms * Cfg::MIN_BLOCKS;
+  const int grid = total < slots ? total : slots;
+  conv_tc_kernel<BN, SHORTK><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(maps, tmB, p);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -813,7 +824,8 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
   p.vec_ok = (d->out_ld % (d->out_f32 ? 4 : 8) == 0) && (!d->mask_src || p.mask_ld % 8 == 0) &&
              (!d->add_src || p.add_ld % 8 == 0) && (!d->scale || ((uintptr_t)d->scale & 15) == 0) &&
              (!d->bias || ((uintptr_t)d->bias & 15) == 0);
-  const int BN = d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64);
+  const bool shortk = d->ntaps * (p.Cin / KCH) <= 4 && getenv("LDB200_NO_SHORTK") == nullptr;
+  const int BN = shortk ? (d->Cout > 64 ? 128 : 64) : (d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64));
   p.tiles_n = (d->Cout + BN - 1) / BN;
   p.nseg = count;
   ConvMaps maps;
@@ -834,9 +846,10 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
     int e = encode_map(&tmB, d->weight, 2, dims, strides, box, es, "B");
     if (e) return e;
   }
-  if (BN == 256) return launch_conv<256>(maps, tmB, p, stream);
-  if (BN == 128) return launch_conv<128>(maps, tmB, p, stream);
-  return launch_conv<64>(maps, tmB, p, stream);
+  if (shortk) return BN == 128 ? launch_conv<128, true>(maps, tmB, p, stream) : launch_conv<64, true>(maps, tmB, p, stream);
+  if (BN == 256) return launch_conv<256, false>(maps, tmB, p, stream);
+  if (BN == 128) return launch_conv<128, false>(maps, tmB, p, stream);
+  return launch_conv<64, false>(maps, tmB, p, stream);
 }
 
 extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
