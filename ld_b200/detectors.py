@@ -313,10 +313,32 @@ class LDTrainStep:
                              1.0 if self.iter == 0 else 0.0], dtype=torch.float32)
         self._hyper.copy_(vals, non_blocking=True)
 
+    def prefetch(self, data):
+        """Start the host->device copy of the NEXT batch's images on a copy stream (pinned host memory), so that it
+        overlaps the current replay; `step_graphed(data)` then only does a device-to-device move."""
+        dev = self.flat_w.device
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staging_img = torch.empty_like(self._static_img)
+            self._staged = None
+            self._d2d_done = None
+        if self._d2d_done is not None:      # the staging buffer must have been drained by the last step's D2D move
+            self._copy_stream.wait_event(self._d2d_done)   # (NOT the whole replay that was enqueued after it)
+        with torch.cuda.stream(self._copy_stream):
+            self._staging_img.copy_(data['img'], non_blocking=True)
+        self._staged = data
+
     def step_graphed(self, data=None):
         """Replay the captured iteration on a new batch (same shapes).  Returns the device loss scalar."""
         if data is not None:
-            self._static_img.copy_(data['img'], non_blocking=True)
+            if getattr(self, '_staged', None) is data:
+                torch.cuda.current_stream().wait_stream(self._copy_stream)
+                self._static_img.copy_(self._staging_img, non_blocking=True)
+                self._d2d_done = torch.cuda.Event()
+                self._d2d_done.record()
+                self._staged = None
+            else:
+                self._static_img.copy_(data['img'], non_blocking=True)
             tg = self.model.bbox_head.get_targets(self._featmap_sizes(self._static_img.shape[2:]), data['img_metas'],
                                                   data['gt_bboxes'], data['gt_labels'], self.flat_w.device,
                                                   static=False)
