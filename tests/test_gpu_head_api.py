@@ -1,0 +1,73 @@
+"""GPU: the reference-shaped public API -- `LDHead.loss(...)` with the reference's argument list
+(ld_head.py:284-294) and the stand-alone `KnowledgeDistillationKLDivLoss` module (kd_loss.py:39-88) -- against
+the golden vectors of the unmodified reference / the oracle (fp32, 1e-4)."""
+import os
+
+import pytest
+import torch
+
+from oracle import cases, ld_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+
+def make_head():
+    import ld_b200
+    from ld_b200 import presets
+    from ld_b200.config import ConfigDict
+    cfg = ConfigDict(presets.ld_model('r50'))
+    head_cfg = cfg.bbox_head
+    head_cfg['train_cfg'] = cfg.train_cfg
+    head_cfg['test_cfg'] = cfg.test_cfg
+    return ld_b200.build_head(head_cfg).cuda().train()
+
+
+@pytest.mark.parametrize('case', cases.LOSS_CASES[:2], ids=lambda c: c[0])
+def test_ldhead_loss_api_matches_reference(golden_dir, case):
+    name, n, h, w, seed = case
+    gold = torch.load(os.path.join(golden_dir, name + '.pt'), weights_only=False)
+    d = cases.loss_case_inputs(n, h, w, seed)
+    head = make_head()
+    dev = torch.device('cuda')
+    leaves = {k: [t.to(dev).requires_grad_(True) for t in d[k]] for k in ('cls', 'reg', 'x')}
+    losses = head.loss(leaves['cls'], leaves['reg'], [b.to(dev) for b in d['gt_bboxes']],
+                       [b.to(dev) for b in d['gt_labels']],
+                       ([t.to(dev) for t in d['t_cls']], [t.to(dev) for t in d['t_reg']]),
+                       leaves['x'], [t.to(dev) for t in d['t_x']], d['img_metas'])
+    assert list(losses) == ['loss_cls', 'loss_bbox', 'loss_dfl', 'loss_ld', 'loss_ld_vlr', 'loss_kd', 'loss_kd_neg',
+                            'loss_im']
+    total = sum(sum(v) for v in losses.values())
+    total.backward()
+    torch.cuda.synchronize()
+    for k, v in gold['losses'].items():
+        got = torch.stack([t.detach().cpu() for t in losses[k]])
+        assert torch.allclose(got, v, rtol=1e-4, atol=1e-6), (k, got, v)
+    for l in range(5):
+        for key, gk in (('cls', 'grad_cls'), ('reg', 'grad_reg')):
+            g, ref = leaves[key][l].grad.cpu(), gold[gk][l]
+            assert float((g - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-9, (key, l)
+        gx = leaves['x'][l].grad
+        gx = torch.zeros_like(leaves['x'][l]) if gx is None else gx
+        ref = gold['grad_x_rowsum'][l]
+        assert float((gx.cpu().sum(1) - ref).abs().max()) <= 2e-4 * max(float(ref.abs().max()), 1e-6), l
+
+
+def test_kd_kl_module_standalone():
+    import ld_b200
+    g = torch.Generator().manual_seed(0)
+    pred = (torch.randn(4000, 17, generator=g) * 2).requires_grad_(True)
+    soft = torch.randn(4000, 17, generator=g) * 2
+    w = torch.rand(4000, generator=g)
+    ref = 0.25 * (lo.kd_kl_rows(pred, soft, 10.0) * w).sum() / 4.0
+    ref.backward()
+    mod = ld_b200.build_loss(dict(type='KnowledgeDistillationKLDivLoss', loss_weight=0.25, T=10))
+    p2 = pred.detach().cuda().requires_grad_(True)
+    out = mod(p2, soft.cuda(), weight=w.cuda(), avg_factor=4.0)
+    out.backward()
+    torch.cuda.synchronize()
+    assert abs(float(out) - float(ref)) <= 1e-4 * abs(float(ref))
+    assert float((p2.grad.cpu() - pred.grad).abs().max()) <= 1e-4 * float(pred.grad.abs().max())
+    with pytest.raises(ValueError):
+        mod(p2, soft.cuda(), avg_factor=4.0, reduction_override='sum')
+    with pytest.raises(TypeError):
+        ld_b200.build_loss(dict(type='KnowledgeDistillationKLDivLoss', T=10, bogus=1))
