@@ -8,6 +8,7 @@ ONE target-generation call for the whole batch, ONE pre-pass and ONE fused loss 
 levels (row space).
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -120,13 +121,39 @@ class GFLHead(nn.Module):
         xs = [nhwc(x) for x in feats]
         if len(xs) > 5:
             raise NotImplementedError('more than 5 pyramid levels')
+        # the two towers are independent chains: the regression tower runs on a second stream so that its
+        # (bandwidth-bound, small-smem) GroupNorm kernels overlap the other tower's tensor-core convs; autograd
+        # replays each backward op on its forward stream, so the backward overlaps the same way
         cfs, rfs = xs, xs
-        for mc, mr in zip(self.cls_convs, self.reg_convs):   # all levels of one tower layer in one launch
+        use_side = xs[0].is_cuda and os.environ.get('LDB200_NO_TOWER_STREAM') is None
+        main = torch.cuda.current_stream() if use_side else None
+        side = self._tower_stream() if use_side else None
+        if use_side:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for mr in self.reg_convs:     # all levels of one tower layer in one launch
+                    rs = engine.conv_levels(mr.conv._cl(), rfs)
+                    rfs = [engine.gn_relu(r, mr.gn.weight, mr.gn.bias, mr.gn.num_groups, mr.gn.eps) for r in rs]
+        for mc in self.cls_convs:
             cs = engine.conv_levels(mc.conv._cl(), cfs)
             cfs = [engine.gn_relu(c, mc.gn.weight, mc.gn.bias, mc.gn.num_groups, mc.gn.eps) for c in cs]
-            rs = engine.conv_levels(mr.conv._cl(), rfs)
-            rfs = [engine.gn_relu(r, mr.gn.weight, mr.gn.bias, mr.gn.num_groups, mr.gn.eps) for r in rs]
+        if use_side:
+            main.wait_stream(side)
+            for r in rfs:
+                r.record_stream(main)
+        else:
+            for mr in self.reg_convs:
+                rs = engine.conv_levels(mr.conv._cl(), rfs)
+                rfs = [engine.gn_relu(r, mr.gn.weight, mr.gn.bias, mr.gn.num_groups, mr.gn.eps) for r in rs]
         return list(zip(cfs, rfs))
+
+    def _tower_stream(self):
+        dev = torch.cuda.current_device()
+        st = self.__dict__.get('_side_stream')
+        if st is None or st.device.index != dev:
+            st = torch.cuda.Stream(device=dev)
+            self.__dict__['_side_stream'] = st
+        return st
 
     def final_convs(self, tower_out, cls_rows, reg_rows):
         """gfl_cls / gfl_reg*scale (gfl_head.py:181-182) written as fp32 NHWC rows (row space)."""
