@@ -104,6 +104,11 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, 
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
                "r"(c2), "r"(c3) : "memory");
 }
+// Programmatic dependent launch: let the next kernel in the stream start its prologue (barrier init, TMEM
+// allocation, descriptor prefetch) while this grid drains, and wait for the previous grid's memory before the
+// first global access (no-ops when the kernel was not launched with the PDL attribute).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -224,10 +229,12 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
+      pdl_wait();   // inputs are produced by the previous kernel
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -291,6 +298,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
     // latency): warp w reads TMEM lanes [32*(w%4), +32) = 32 tile rows, and BN/EPI_GROUPS of the tile's columns.  Per 32-column
     // chunk: tcgen05.ld (software-pipelined one chunk ahead), per-channel scale/bias (float4 loads),
     // residual / accumulate / ReLU / mask, 16-byte stores along the thread's own output row.
+    pdl_wait();   // residual / mask / accumulate reads and the output stores touch memory of earlier kernels
     const int ew = warp & 3, half = (warp - 4) >> 2;              // half = column group of this warp
     constexpr int GCOLS = BN / Cfg::EPI_GROUPS;                  // columns per group
     constexpr int NCH = GCOLS / 32;                               // 32-column chunks per warp
@@ -530,9 +538,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -590,6 +600,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
+    pdl_wait();
     const int ew = warp - 4;
     int it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
@@ -681,6 +692,24 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 
 static int g_conv_sms = 0;
 
+// launch with the programmatic-stream-serialization attribute (PDL); LDB200_NO_PDL=1 falls back to plain launches
+template <typename K, typename... Args>
+static cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaStream_t stream, const Args&... args) {
+  static const bool use_pdl = getenv("LDB200_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int BN, bool SHORTK>
 static int launch_conv(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, SHORTK>;
@@ -692,8 +721,7 @@ static int launch_conv(const ConvMaps& maps, const CUtensorMap& tmB, const ConvP
   const int total = p.seg_tile0[p.nseg];
   const int slots = g_conv_sms * Cfg::MIN_BLOCKS;
   const int grid = total < slots ? total : slots;
-  conv_tc_kernel<BN, SHORTK><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(maps, tmB, p);
-  LDB_CUDA(cudaGetLastError());
+  LDB_CUDA(launch_pdl(conv_tc_kernel<BN, SHORTK>, grid, Cfg::THREADS, Cfg::SMEM, stream, maps, tmB, p));
   return 0;
 }
 
@@ -869,8 +897,7 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const Wg
   }
   const int units = p.co_tiles * p.ci_tiles * p.ntaps * p.splits;
   const int grid = units < g_conv_sms ? units : g_conv_sms;
-  wgrad_tc_kernel<BN><<<grid, CONV_THREADS, Cfg::SMEM, stream>>>(tmA, tmB, p);
-  LDB_CUDA(cudaGetLastError());
+  LDB_CUDA(launch_pdl(wgrad_tc_kernel<BN>, grid, CONV_THREADS, Cfg::SMEM, stream, tmA, tmB, p));
   return 0;
 }
 
