@@ -244,6 +244,10 @@ int ldb200_bn_fold(const float* gamma, const float* beta, const float* mean, con
                    float* scale, float* shift, int C, void* stream);
 int ldb200_bn_fold_bwd(const float* d_scale, const float* d_shift, const float* mean, const float* var, float eps,
                        float* dgamma, float* dbeta, int C, void* stream);
+/* IMLoss stand-alone (kd_loss.py:91-120): loss[0] += loss_weight * mean((x - target)^2); dx = d loss / d x (may be
+ * NULL).  Inside LDHead the same term is part of ldb200_ld_loss_fused. */
+int ldb200_mse_fwd_bwd(const void* x, const void* target, int64_t numel, float loss_weight, int dtype, float* loss,
+                       void* dx, void* stream);
 /* torch.optim.SGD (momentum, weight decay, dampening 0) on a flat fp32 parameter buffer;
  * grad_scale folds the data-parallel mean.  configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py:53. */
 int ldb200_sgd_flat(float* w, const float* g, float* momentum_buf, int64_t n, float lr, float momentum,

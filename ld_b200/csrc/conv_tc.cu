@@ -692,10 +692,11 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 
 static int g_conv_sms = 0;
 
-// launch with the programmatic-stream-serialization attribute (PDL); LDB200_NO_PDL=1 falls back to plain launches
+// optional programmatic dependent launch (LDB200_PDL=1): measured neutral on the LD step (299 vs 300 img/s: the
+// 197 KB-smem CTAs cannot co-reside with their successors), so plain launches are the default
 template <typename K, typename... Args>
 static cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaStream_t stream, const Args&... args) {
-  static const bool use_pdl = getenv("LDB200_NO_PDL") == nullptr;
+  static const bool use_pdl = getenv("LDB200_PDL") != nullptr;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);

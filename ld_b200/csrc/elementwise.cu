@@ -466,6 +466,33 @@ __global__ void bn_fold_bwd_kernel(const float* __restrict__ d_scale, const floa
   }
 }
 
+// IMLoss (kd_loss.py:91-120): loss_weight * mean((x - t)^2) over all elements, and d/dx.
+template <typename T>
+__global__ void __launch_bounds__(256) mse_fwd_bwd_kernel(const T* __restrict__ x, const T* __restrict__ t, long long n,
+                                                           float scale, float* __restrict__ loss, T* __restrict__ dx) {
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float a, b;
+    if (sizeof(T) == 4) { a = ((const float*)x)[i]; b = ((const float*)t)[i]; }
+    else { a = __bfloat162float(((const __nv_bfloat16*)x)[i]); b = __bfloat162float(((const __nv_bfloat16*)t)[i]); }
+    const float d = a - b;
+    acc += d * d;
+    if (dx) {
+      if (sizeof(T) == 4) ((float*)dx)[i] = 2.f * scale * d;
+      else ((__nv_bfloat16*)dx)[i] = __float2bfloat16_rn(2.f * scale * d);
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ float sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += sh[i];
+    atomicAdd(loss, s * scale);
+  }
+}
+
 static int grid_for(long long total, int threads = 256, int cap = 148 * 16) {
   long long b = (total + threads - 1) / threads;
   if (b > cap) b = cap;
@@ -613,6 +640,22 @@ extern "C" int ldb200_bn_fold_bwd(const float* d_scale, const float* d_shift, co
                                   float eps, float* dgamma, float* dbeta, int C, void* stream_) {
   LDB_REQUIRE(mean && var && dgamma && dbeta && C > 0, LDB_EINVAL, "bn_fold_bwd: bad argument");
   bn_fold_bwd_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(d_scale, d_shift, mean, var, eps, dgamma, dbeta, C);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_mse_fwd_bwd(const void* x, const void* target, int64_t numel, float loss_weight, int dtype,
+                                  float* loss, void* dx, void* stream_) {
+  LDB_REQUIRE(numel >= 0 && loss, LDB_EINVAL, "mse_fwd_bwd: bad argument");
+  if (numel == 0) return 0;
+  LDB_REQUIRE(x && target, LDB_EINVAL, "mse_fwd_bwd: null pointer");
+  const float scale = loss_weight / (float)numel;
+  if (dtype == LDB_F32)
+    mse_fwd_bwd_kernel<float><<<grid_for(numel), 256, 0, (cudaStream_t)stream_>>>((const float*)x, (const float*)target, numel, scale, loss, (float*)dx);
+  else if (dtype == LDB_BF16)
+    mse_fwd_bwd_kernel<__nv_bfloat16><<<grid_for(numel), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)target, numel, scale, loss, (__nv_bfloat16*)dx);
+  else
+    LDB_REQUIRE(false, LDB_EINVAL, "mse_fwd_bwd: dtype");
   LDB_CUDA(cudaGetLastError());
   return 0;
 }

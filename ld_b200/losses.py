@@ -23,6 +23,24 @@ class _KLDenseFn(torch.autograd.Function):
         return d * g, None, None, None, None, None
 
 
+class _MSEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target, loss_weight):
+        from . import lib as L
+        loss = torch.zeros(1, dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        xd = x.detach()
+        L.check(L.load().ldb200_mse_fwd_bwd(L.ptr(xd), L.ptr(target), x.numel(), loss_weight, ops._dt(x.dtype),
+                                            L.ptr(loss), L.ptr(dx), L.stream_ptr()), 'ldb200_mse_fwd_bwd')
+        ctx.save_for_backward(dx)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return dx * g.to(dx.dtype), None, None
+
+
 @LOSSES.register_module()
 class KnowledgeDistillationKLDivLoss(nn.Module):
     """kd_loss.py:39-88: loss_weight * sum_r w_r * mean_bins[KL(softmax(t/T) || softmax(s/T))] * T^2 / avg."""
@@ -60,8 +78,9 @@ class IMLoss(nn.Module):
         self.reduction, self.loss_weight = reduction, loss_weight
 
     def forward(self, x, soft_target, weight=None, avg_factor=None, reduction_override=None):
-        raise NotImplementedError('IMLoss is evaluated inside the fused LDHead loss kernel (gather + MSE on the '
-                                  'fine-grained rows, ld_head.py:187-191); no stand-alone path is provided')
+        """Stand-alone path (ldb200_mse_fwd_bwd); inside LDHead the term is part of the fused loss kernel."""
+        assert x.shape == soft_target.shape
+        return _MSEFn.apply(x.contiguous(), soft_target.detach().to(x.dtype).contiguous(), float(self.loss_weight))
 
 
 class _HeadLossCfg(nn.Module):

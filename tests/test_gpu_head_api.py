@@ -71,3 +71,19 @@ def test_kd_kl_module_standalone():
         mod(p2, soft.cuda(), avg_factor=4.0, reduction_override='sum')
     with pytest.raises(TypeError):
         ld_b200.build_loss(dict(type='KnowledgeDistillationKLDivLoss', T=10, bogus=1))
+
+
+def test_imloss_module_standalone():
+    import ld_b200
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(300, 256, generator=g).requires_grad_(True)
+    t = torch.randn(300, 256, generator=g)
+    ref = 2.0 * torch.nn.functional.mse_loss(x, t)
+    ref.backward()
+    mod = ld_b200.build_loss(dict(type='IMLoss', loss_weight=2.0))
+    xg = x.detach().cuda().requires_grad_(True)
+    out = mod(xg, t.cuda())
+    out.backward()
+    torch.cuda.synchronize()
+    assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert float((xg.grad.cpu() - x.grad).abs().max()) <= 1e-5 * float(x.grad.abs().max())
