@@ -136,12 +136,13 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
+        config['launch'] = 'reference CPU path (oracle port, torch CPU fp32), bounded sample of 2 of the 16 images per step'
         n_imgs = 2
         v, sec = cpu_reference_step(n_imgs, max(1, min(args.steps, 3)), min(args.warmup, 1))
         cores = host_cores()
         print(json.dumps(dict(
             metric='images/sec GFocal-R50 student + R101 teacher LD train step, 1333x800 bs=16', impl='reference',
-            value=v, unit='images/s', n_gpus=0, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1),
+            value=v, unit='images/s', n_gpus=args.gpus, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1),
             ms_per_step=sec * 1e3 * GLOBAL_BATCH / n_imgs, higher_is_better=True, scaling='strong', vs_baseline=None,
             dtype='f32', data='synthetic', config=config,
             cpu_baseline=dict(value=v, unit='images/s', cores=cores, kind='port',
