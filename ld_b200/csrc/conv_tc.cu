@@ -461,6 +461,340 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a pair of SMs computes one 256 x 256 output tile; every CTA stages its own 128
+// pixel rows of A and HALF of the weight tile, so shared-memory fill + operand reads drop from 192 to 128 B/cycle per
+// SM (the measured limit of the 1-CTA kernel: 73-79 % tensor-pipe) and L2 weight traffic halves.
+struct Conv2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int B_TILE_BYTES = (BN / 2) * KCH * 2;        // this CTA's half of the weight tile
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;  // 32 KB
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int STAGING_BYTES = 0;
+  static constexpr int EPI_GROUPS = 2;
+  static constexpr int THREADS = 128 + 128 * EPI_GROUPS;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                    ((uint32_t)(256 >> 4) << 24);
+};
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(s2u(dst)), "l"(map), "r"(s2u(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(s2u(dst)), "l"(map), "r"(s2u(bar) & PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(s2u(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbarrier_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(s2u(bar) & PEER_MASK) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Conv2Cfg::THREADS, 1)
+conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ ConvParams p) {
+  using Cfg = Conv2Cfg;
+  constexpr int BN = Conv2Cfg::BN;
+  constexpr bool SHORTK = false;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  extern __shared__ unsigned char conv_smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)conv_smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* staging = smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = (uint64_t*)(staging + Cfg::STAGING_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tfull = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cchunks = p.Cin / KCH;
+  const int kblocks = p.ntaps * cchunks;
+  // pair-tiles: CTA rank r of pair q owns M-tile 2*(q % half_m) + r of output-channel tile q / half_m; an odd
+  // M-tile count is padded with a dummy tile (fully out-of-bounds loads, no stores)
+  const int mt_total = p.seg_tile0[p.nseg] / p.tiles_n;
+  const int half_m = (mt_total + 1) >> 1;
+  const int pairs = p.tiles_n * half_m;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbarrier_init(&full[s], 1);
+      mbarrier_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbarrier_init(&tfull[a], 1);
+      mbarrier_init(&tempty[a], 2 * 4 * Cfg::EPI_GROUPS);   // one arrive per epilogue warp of BOTH CTAs (leader's copy is used)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)),
+                 "n"(Cfg::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      pdl_wait();   // inputs are produced by the previous kernel
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int q = blockIdx.x >> 1; q < pairs; q += gridDim.x >> 1) {
+        const int nt = q / half_m;
+        const int mt = 2 * (q - nt * half_m) + (int)rank;
+        const bool dummy = mt >= mt_total;
+        int sg = 0;
+        while (!dummy && sg + 1 < p.nseg && mt >= p.seg_tile0[sg + 1] / p.tiles_n) ++sg;
+        const ConvSeg& S = p.seg[sg];
+        int sp = dummy ? 0 : mt - p.seg_tile0[sg] / p.tiles_n;
+        const int tx = sp % S.tiles_x;
+        sp /= S.tiles_x;
+        const int ty = sp % S.tiles_y;
+        const int n = dummy ? S.N : sp / S.tiles_y;   // image index N is out of bounds: TMA zero-fills
+        const int x0 = tx * S.TW * p.sx, y0 = ty * S.TH * p.sy;
+        // the epilogue will read this tile's residual / ReLU-mask rows a whole main loop from now: pull them into
+        // L2 with one TMA prefetch each so those loads see L2 latency instead of HBM latency
+        if (S.pf_add) tma_prefetch_4d(&maps.r[sg], nt * BN, tx * S.TW, ty * S.TH, n);
+        if (S.pf_mask) tma_prefetch_4d(&maps.m[sg], nt * BN, tx * S.TW, ty * S.TH, n);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * KCH;
+          mbarrier_wait(&empty[stage], phase ^ 1);
+          unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+          // both CTAs' loads complete on the LEADER's barrier; only the leader arms it (bytes of the pair)
+          if (rank == 0) mbarrier_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+          tma_load_4d_2sm(sa, &maps.a[sg], &full[stage], c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], n);
+          tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, &full[stage], p.tap_wk[tap] + c0, nt * BN + (int)rank * (BN / 2));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int q = blockIdx.x >> 1; q < pairs; q += gridDim.x >> 1, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbarrier_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbarrier_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = s2u(smem + (size_t)stage * Cfg::STAGE_BYTES);
+          const uint64_t da = smem_desc_k128(sa), db = smem_desc_k128(sa + A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < KCH / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16_2cta(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), Cfg::IDESC, (kb | k) ? 1u : 0u);
+          }
+          umma_commit_2cta(&empty[stage]);            // frees the smem slot in BOTH CTAs when the MMAs retire
+          if (kb == kblocks - 1) umma_commit_2cta(&tfull[acc]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue ==========================================
+    // 4*EPI_GROUPS warps (EPI_GROUPS per SM sub-partition, hiding each other's ALU / TMEM-load / residual-load
+    // latency): warp w reads TMEM lanes [32*(w%4), +32) = 32 tile rows, and BN/EPI_GROUPS of the tile's columns.  Per 32-column
+    // chunk: tcgen05.ld (software-pipelined one chunk ahead), per-channel scale/bias (float4 loads),
+    // residual / accumulate / ReLU / mask, 16-byte stores along the thread's own output row.
+    pdl_wait();   // residual / mask / accumulate reads and the output stores touch memory of earlier kernels
+    const int ew = warp & 3, half = (warp - 4) >> 2;              // half = column group of this warp
+    constexpr int GCOLS = BN / Cfg::EPI_GROUPS;                  // columns per group
+    constexpr int NCH = GCOLS / 32;                               // 32-column chunks per warp
+    int it = 0;
+    for (int q = blockIdx.x >> 1; q < pairs; q += gridDim.x >> 1, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int nt = q / half_m;
+      const int mt = 2 * (q - nt * half_m) + (int)rank;
+      const bool dummy = mt >= mt_total;
+      int sg = 0;
+      while (!dummy && sg + 1 < p.nseg && mt >= p.seg_tile0[sg + 1] / p.tiles_n) ++sg;
+      const ConvSeg& S = p.seg[sg];
+      int sp = dummy ? 0 : mt - p.seg_tile0[sg] / p.tiles_n;
+      const int tx = sp % S.tiles_x;
+      sp /= S.tiles_x;
+      const int ty = sp % S.tiles_y;
+      const int n = dummy ? S.N : sp / S.tiles_y;   // image index N is out of bounds: TMA zero-fills
+      const int m = ew * 32 + lane;
+      const int y = ty * S.TH + (m >> S.tw_shift), x = tx * S.TW + (m & (S.TW - 1));
+      const bool pix_ok = !dummy && (y < S.HO) && (x < S.WO);
+      const size_t pix = pix_ok ? out_offset(S, n, y, x) : 0;
+      const __nv_bfloat16* addp = nullptr;
+      if (S.add_src && pix_ok) {
+        const int ay = (int)(((long long)y * S.add_H) / S.HO), ax = (int)(((long long)x * S.add_W) / S.WO);
+        addp = S.add_src + (((size_t)n * S.add_H + ay) * S.add_W + ax) * (size_t)p.add_ld;
+      }
+      const int col0 = nt * BN + half * GCOLS;
+      const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * GCOLS);
+      mbarrier_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      // SHORTK (two CTAs per SM, 85-register budget): one TMEM buffer, chunks strictly one after the other -- the
+      // second CTA provides the latency hiding.  Otherwise the next chunk's tcgen05.ld is issued one chunk ahead.
+      uint32_t rbuf[SHORTK ? 1 : 2][32];
+      if (!SHORTK && col0 < p.Cout) tmem_ld32_nowait(tbase, rbuf[0]);
+#pragma unroll(SHORTK ? 1 : NCH)
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int cbase = col0 + ch * 32;
+        if (cbase >= p.Cout) break;   // warp-uniform
+        if (SHORTK) tmem_ld32_nowait(tbase + ch * 32, rbuf[0]);
+        tmem_ld_wait();
+        if (!SHORTK && ch + 1 < NCH && cbase + 32 < p.Cout) tmem_ld32_nowait(tbase + (ch + 1) * 32, rbuf[(ch + 1) & 1]);
+        const uint32_t* r = rbuf[SHORTK ? 0 : (ch & 1)];
+        if (!pix_ok) continue;
+        const bool full = (cbase + 32 <= p.Cout) && p.vec_ok;   // warp-uniform fast path
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (full) {
+          if (p.scale) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + cbase + j));
+              v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+            }
+          }
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+          if (addp) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(addp + cbase + j));
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(hh[e]);
+                v[j + 2 * e] += f.x;
+                v[j + 2 * e + 1] += f.y;
+              }
+            }
+          }
+          if (p.accumulate) {
+            if (p.out_f32) {
+              const float* o = (const float*)S.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 o4 = *reinterpret_cast<const float4*>(o + j);
+                v[j] += o4.x; v[j + 1] += o4.y; v[j + 2] += o4.z; v[j + 3] += o4.w;
+              }
+            } else {
+              const __nv_bfloat16* o = (const __nv_bfloat16*)S.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 q = *reinterpret_cast<const uint4*>(o + j);
+                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(hh[e]);
+                  v[j + 2 * e] += f.x;
+                  v[j + 2 * e + 1] += f.y;
+                }
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (S.mask_src) {
+            const __nv_bfloat16* mk = S.mask_src + pix * (size_t)p.mask_ld + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(mk + j));
+              const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (!(__bfloat162float(hb[e]) > 0.f)) v[j + e] = 0.f;
+            }
+          }
+          if (p.out_f32) {
+            float* o = (float*)S.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            __nv_bfloat16* o = (__nv_bfloat16*)S.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 q;
+              __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(o + j) = q;
+            }
+          }
+        } else {
+          // ragged tail (Cout not a multiple of 32, or unaligned leading dimension): scalar path
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = cbase + j;
+            if (c >= p.Cout) continue;
+            float vv = v[j];
+            if (p.scale) vv *= __ldg(p.scale + c);
+            if (p.bias) vv += __ldg(p.bias + c);
+            if (addp) vv += __bfloat162float(addp[c]);
+            if (p.accumulate)
+              vv += p.out_f32 ? ((const float*)S.out)[pix * (size_t)p.ldc + c]
+                              : __bfloat162float(((const __nv_bfloat16*)S.out)[pix * (size_t)p.ldc + c]);
+            if (p.relu) vv = fmaxf(vv, 0.f);
+            if (S.mask_src && !(__bfloat162float(S.mask_src[pix * (size_t)p.mask_ld + c]) > 0.f)) vv = 0.f;
+            if (p.out_f32) ((float*)S.out)[pix * (size_t)p.ldc + c] = vv;
+            else ((__nv_bfloat16*)S.out)[pix * (size_t)p.ldc + c] = __float2bfloat16_rn(vv);
+          }
+        }
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbarrier_arrive_leader(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
+  }
+}
+
 // =============================================================================================
 // Weight gradient: dW[co, tap, ci] += sum_{n,y,x} dY[n,y,x,co] * X[n, y*sy+dy_tap, x*sx+dx_tap, ci]
 // (autograd's conv backward-weight for every trainable conv of the student).  GEMM with the
@@ -726,6 +1060,29 @@ static int launch_conv(const ConvMaps& maps, const CUtensorMap& tmB, const ConvP
   return 0;
 }
 
+// 2-CTA kernel (default for Cout % 256 == 0 and more than 4 k-blocks; LDB200_NO_CONV2=1 falls back to the 1-CTA kernel): one cluster of two CTAs per pair-tile, grid = resident clusters
+static int launch_conv2(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+  static int max_clusters = 0;
+  if (!max_clusters) {
+    LDB_CUDA(cudaFuncSetAttribute(conv2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Conv2Cfg::SMEM));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(g_conv_sms / 2 * 2);
+    cfg.blockDim = dim3(Conv2Cfg::THREADS);
+    cfg.dynamicSmemBytes = Conv2Cfg::SMEM;
+    int n = 0;
+    LDB_CUDA(cudaOccupancyMaxActiveClusters(&n, conv2_tc_kernel, &cfg));
+    LDB_REQUIRE(n >= 1, LDB_ENOSUP, "conv2d_tc: no resident 2-CTA cluster");
+    max_clusters = n < g_conv_sms / 2 ? n : g_conv_sms / 2;
+  }
+  const int mt_total = p.seg_tile0[p.nseg] / p.tiles_n;
+  const int pairs = p.tiles_n * ((mt_total + 1) / 2);
+  const int clusters = pairs < max_clusters ? pairs : max_clusters;
+  conv2_tc_kernel<<<2 * clusters, Conv2Cfg::THREADS, Conv2Cfg::SMEM, stream>>>(maps, tmB, p);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // geometry + tensor maps of one segment
 static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& common, ConvSeg* g, CUtensorMap* tmA,
                          CUtensorMap* tmR, CUtensorMap* tmM) {
@@ -867,14 +1224,17 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
   }
   for (int i = count; i <= CONV_MAX_SEG; ++i) p.seg_tile0[i] = tile0;
   for (int i = count; i < CONV_MAX_SEG; ++i) { maps.a[i] = maps.a[0]; maps.r[i] = maps.a[0]; maps.m[i] = maps.a[0]; }
+  static const bool conv2_env = getenv("LDB200_NO_CONV2") == nullptr;   // 2-CTA kernel is the default for 256-wide tiles
+  const bool use2 = conv2_env && !shortk && BN == 256 && d->Cout % 256 == 0;
   CUtensorMap tmB;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->w_k, (cuuint64_t)d->Cout};
     cuuint64_t strides[1] = {(cuuint64_t)d->w_k * 2};
-    cuuint32_t box[2] = {KCH, (cuuint32_t)BN}, es[2] = {1, 1};
+    cuuint32_t box[2] = {KCH, (cuuint32_t)(use2 ? BN / 2 : BN)}, es[2] = {1, 1};
     int e = encode_map(&tmB, d->weight, 2, dims, strides, box, es, "B");
     if (e) return e;
   }
+  if (use2) return launch_conv2(maps, tmB, p, stream);
   if (shortk) return BN == 128 ? launch_conv<128, true>(maps, tmB, p, stream) : launch_conv<64, true>(maps, tmB, p, stream);
   if (BN == 256) return launch_conv<256, false>(maps, tmB, p, stream);
   if (BN == 128) return launch_conv<128, false>(maps, tmB, p, stream);
