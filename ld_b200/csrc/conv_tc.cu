@@ -44,6 +44,7 @@ struct ConvSeg {            // geometry of one segment (= one FPN level of a lev
   int add_H, add_W;
   const __nv_bfloat16* mask_src; // optional: multiply by (mask_src > 0), same addressing as out (bf16, ld = mask_ld)
   int pf_add, pf_mask;      // L2-prefetch the residual / mask tile with TMA while the main loop runs
+  int tl_add, tl_mask;      // TMA epilogue: residual / mask boxes are TMA-loaded into the warp's staging buffer
 };
 
 struct ConvParams {
@@ -63,11 +64,16 @@ struct ConvParams {
   int relu;
   int accumulate;           // result += previous out (before ReLU / mask)
   int vec_ok;               // leading dimensions allow 16-byte vector accesses
+  int tma_epi;              // epilogue stages 32-pixel x 64-channel boxes in shared memory and TMA-stores them
 };
 
-struct ConvMaps {           // per-segment TMA descriptors: A operand, residual prefetch, mask prefetch
+struct ConvMaps {           // per-segment TMA descriptors: A operand, residual prefetch, mask prefetch,
   CUtensorMap a[CONV_MAX_SEG], r[CONV_MAX_SEG], m[CONV_MAX_SEG];
+  // TMA epilogue: output store, residual load, mask load (boxes of EPI_BOX_PIX pixels x 64 channels, SWIZZLE_128B)
+  CUtensorMap o[CONV_MAX_SEG], rl[CONV_MAX_SEG], ml[CONV_MAX_SEG];
 };
+constexpr int EPI_BOX_PIX = 32;                       // one epilogue warp = 32 TMEM lanes = 32 output pixels
+constexpr int EPI_BOX_BYTES = EPI_BOX_PIX * 64 * 2;   // 4 KB staging buffer per epilogue warp
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,6 +110,14 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, 
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
                "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(s2u(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // Programmatic dependent launch: let the next kernel in the stream start its prologue (barrier init, TMEM
 // allocation, descriptor prefetch) while this grid drains, and wait for the previous grid's memory before the
 // first global access (no-ops when the kernel was not launched with the PDL attribute).
@@ -170,12 +184,13 @@ template <int BN, bool SHORTK = false> struct ConvCfg {
   static constexpr int MIN_BLOCKS = SHORTK ? 2 : 1;
   static_assert(!SHORTK || BN <= 128, "two resident CTAs need 2 * (2*BN) <= 512 TMEM columns");
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int STAGING_BYTES = 0;
+  static constexpr int STAGING_BYTES = BN >= 128 ? 4 * 2 * EPI_BOX_BYTES : 0;   // TMA-epilogue staging, one box per warp
   // epilogue warp groups of 4 warps (one per TMEM lane quadrant); each group owns BN/EPI_GROUPS columns.
   // Four groups (4 warps per SM sub-partition) hide the latency of the residual / mask loads.
   static constexpr int EPI_GROUPS = 2;   // 8 epilogue warps (16 measured slower: 67.6 vs 65.2 ms/step)
   static constexpr int THREADS = 128 + 128 * EPI_GROUPS;
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert((SMEM + 1024) * MIN_BLOCKS <= 228 * 1024 && SMEM <= 227 * 1024, "shared memory budget");
   // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=BN, M=128
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                     ((uint32_t)(TILE_M >> 4) << 24);
@@ -183,6 +198,237 @@ template <int BN, bool SHORTK = false> struct ConvCfg {
 
 __device__ __forceinline__ size_t out_offset(const ConvSeg& p, int n, int y, int x) {
   return (((size_t)n * p.OH + (size_t)(y * p.oys + p.oyo)) * p.OW + (size_t)(x * p.oxs + p.oxo));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue of ONE output tile for one epilogue warp (shared by the 1-CTA and 2-CTA kernels): warp (ew, half) owns
+// TMEM lanes [32*ew, +32) = 32 tile rows and the tile's columns [half*GCOLS, +GCOLS).  Per 32-column chunk:
+// tcgen05.ld (software-pipelined one chunk ahead), per-channel scale/bias (float4 loads), residual / accumulate /
+// ReLU / mask, then either
+//   * direct path: 16-byte global stores along the thread's own output row (any layout / dtype), or
+//   * TMA path (p.tma_epi; bf16, identity pixel mapping, Cout % 64 == 0): the warp's 32 pixels x 64 channels go
+//     through a 4 KB SWIZZLE_128B staging box -- residual and ReLU-mask boxes arrive by TMA load, the result leaves by
+//     TMA store -- so global memory only sees full 128-byte lines instead of 32 scattered 16-byte accesses per
+//     warp instruction (the scattered form held the 1x1 "expand" convs at ~40 % of the HBM roofline).
+// Leaves the TMEM accumulator drained (caller signals tmem-empty).
+template <int BN, bool SHORTK, int EPI_GROUPS>
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMaps& maps, const ConvSeg& S, int sg, int nt,
+                                              int tx, int ty, int n, bool live, uint32_t tmem_acc, uint64_t* tfull_bar,
+                                              uint32_t acc_phase, int ew, int half, int lane, unsigned char* ebuf,
+                                              uint64_t* rbar, uint32_t& rph) {
+  constexpr int GCOLS = BN / EPI_GROUPS;   // columns per warp
+  constexpr int NCH = GCOLS / 32;          // 32-column chunks per warp
+  const bool tma = (BN >= 128) && p.tma_epi;   // warp-uniform
+  const int m = ew * 32 + lane;
+  const int y = ty * S.TH + (m >> S.tw_shift), x = tx * S.TW + (m & (S.TW - 1));
+  const bool pix_ok = live && (y < S.HO) && (x < S.WO);
+  const size_t pix = pix_ok ? out_offset(S, n, y, x) : 0;
+  const __nv_bfloat16* addp = nullptr;
+  if (S.add_src && pix_ok && !(tma && S.tl_add)) {
+    const int ay = (int)(((long long)y * S.add_H) / S.HO), ax = (int)(((long long)x * S.add_W) / S.WO);
+    addp = S.add_src + (((size_t)n * S.add_H + ay) * S.add_W + ax) * (size_t)p.add_ld;
+  }
+  const int col0 = nt * BN + half * GCOLS;
+  const uint32_t tbase = tmem_acc + ((uint32_t)(ew * 32) << 16) + (uint32_t)(half * GCOLS);
+  // TMA path: first pixel of this warp's box, this lane's 128-byte row in the staging box and its swizzle phase
+  const int bx = tx * S.TW + ((ew * 32) & (S.TW - 1)), by = ty * S.TH + ((ew * 32) >> S.tw_shift);
+  unsigned char* erow = ebuf + lane * 128;
+  const int sw = lane & 7;
+  uint32_t mb0 = 0xffffffffu, mb1 = 0xffffffffu;   // ReLU-mask bits of this lane's 64 box columns
+  // staging buffer free again (the previous TMA store has read it), then mask bits and the residual box
+  auto acquire = [&](int colb) {
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+    if (S.tl_mask) {
+      if (lane == 0) {
+        mbarrier_expect_tx(rbar, EPI_BOX_BYTES);
+        tma_load_4d(ebuf, &maps.ml[sg], rbar, colb, bx, by, n);
+      }
+      mbarrier_wait(rbar, rph);
+      rph ^= 1;
+      mb0 = mb1 = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 mv = *reinterpret_cast<const uint4*>(erow + ((q ^ sw) << 4));
+        const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&mv);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bits |= (__bfloat162float(hb[e]) > 0.f ? 1u : 0u) << e;
+        if (q < 4) mb0 |= bits << (8 * q);
+        else mb1 |= bits << (8 * (q - 4));
+      }
+      fence_proxy_async();
+      __syncwarp();
+    }
+    if (S.tl_add) {
+      if (lane == 0) {
+        mbarrier_expect_tx(rbar, EPI_BOX_BYTES);
+        tma_load_4d(ebuf, &maps.rl[sg], rbar, colb, bx, by, n);
+      }
+      mbarrier_wait(rbar, rph);
+      rph ^= 1;
+    }
+  };
+  if (tma && col0 < p.Cout) acquire(col0);   // overlaps this tile's main loop
+  mbarrier_wait(tfull_bar, acc_phase);
+  tc_fence_after();
+  // SHORTK (two CTAs per SM, 85-register budget): one TMEM buffer, chunks strictly one after the other -- the
+  // second CTA provides the latency hiding.  Otherwise the next chunk's tcgen05.ld is issued one chunk ahead.
+  uint32_t rbuf[SHORTK ? 1 : 2][32];
+  if (!SHORTK && col0 < p.Cout) tmem_ld32_nowait(tbase, rbuf[0]);
+#pragma unroll(SHORTK ? 1 : NCH)
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int cbase = col0 + ch * 32;
+    if (cbase >= p.Cout) break;   // warp-uniform
+    if (tma && ch > 0 && (ch & 1) == 0) acquire(cbase);   // next 64-column box of this warp (BN = 256)
+    if (SHORTK) tmem_ld32_nowait(tbase + ch * 32, rbuf[0]);
+    tmem_ld_wait();
+    if (!SHORTK && ch + 1 < NCH && cbase + 32 < p.Cout) tmem_ld32_nowait(tbase + (ch + 1) * 32, rbuf[(ch + 1) & 1]);
+    const uint32_t* r = rbuf[SHORTK ? 0 : (ch & 1)];
+    if (pix_ok) {
+      const bool full = (cbase + 32 <= p.Cout) && p.vec_ok;   // warp-uniform fast path
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (full) {
+        if (p.scale) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + cbase + j));
+            v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+          }
+        }
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        }
+        if (tma && S.tl_add) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 q = *reinterpret_cast<const uint4*>(erow + ((((ch & 1) * 4 + (j >> 3)) ^ sw) << 4));
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(hh[e]);
+              v[j + 2 * e] += f.x;
+              v[j + 2 * e + 1] += f.y;
+            }
+          }
+        } else if (addp) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(addp + cbase + j));
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(hh[e]);
+              v[j + 2 * e] += f.x;
+              v[j + 2 * e + 1] += f.y;
+            }
+          }
+        }
+        if (p.accumulate) {
+          if (p.out_f32) {
+            const float* o = (const float*)S.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 o4 = *reinterpret_cast<const float4*>(o + j);
+              v[j] += o4.x; v[j + 1] += o4.y; v[j + 2] += o4.z; v[j + 3] += o4.w;
+            }
+          } else {
+            const __nv_bfloat16* o = (const __nv_bfloat16*)S.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 q = *reinterpret_cast<const uint4*>(o + j);
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(hh[e]);
+                v[j + 2 * e] += f.x;
+                v[j + 2 * e + 1] += f.y;
+              }
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (tma && S.tl_mask) {
+          const uint32_t word = (ch & 1) ? mb1 : mb0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (!((word >> j) & 1u)) v[j] = 0.f;
+        } else if (S.mask_src) {
+          const __nv_bfloat16* mk = S.mask_src + pix * (size_t)p.mask_ld + cbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(mk + j));
+            const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (!(__bfloat162float(hb[e]) > 0.f)) v[j + e] = 0.f;
+          }
+        }
+        if (tma) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 q;
+            __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(erow + ((((ch & 1) * 4 + (j >> 3)) ^ sw) << 4)) = q;
+          }
+        } else if (p.out_f32) {
+          float* o = (float*)S.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          __nv_bfloat16* o = (__nv_bfloat16*)S.out + pix * (size_t)p.ldc + cbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 q;
+            __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(o + j) = q;
+          }
+        }
+      } else {
+        // ragged tail (Cout not a multiple of 32, or unaligned leading dimension): scalar path
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = cbase + j;
+          if (c >= p.Cout) continue;
+          float vv = v[j];
+          if (p.scale) vv *= __ldg(p.scale + c);
+          if (p.bias) vv += __ldg(p.bias + c);
+          if (addp) vv += __bfloat162float(addp[c]);
+          if (p.accumulate)
+            vv += p.out_f32 ? ((const float*)S.out)[pix * (size_t)p.ldc + c]
+                            : __bfloat162float(((const __nv_bfloat16*)S.out)[pix * (size_t)p.ldc + c]);
+          if (p.relu) vv = fmaxf(vv, 0.f);
+          if (S.mask_src && !(__bfloat162float(S.mask_src[pix * (size_t)p.mask_ld + c]) > 0.f)) vv = 0.f;
+          if (p.out_f32) ((float*)S.out)[pix * (size_t)p.ldc + c] = vv;
+          else ((__nv_bfloat16*)S.out)[pix * (size_t)p.ldc + c] = __float2bfloat16_rn(vv);
+        }
+      }
+    }
+    if (tma && (ch & 1)) {   // 64 columns staged: hand the box to the TMA (rows outside the tensor are clipped)
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&maps.o[sg], ebuf, cbase - 32, bx, by, n);
+        bulk_commit();
+      }
+    }
+  }
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncwarp();
 }
 
 template <int BN, bool SHORTK>
@@ -199,6 +445,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
   uint64_t* tfull = bars + 2 * Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint64_t* rbars = tempty + 3;   // one per epilogue warp (TMA-epilogue residual / mask loads)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cchunks = p.Cin / KCH;
@@ -214,6 +461,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
       mbarrier_init(&tfull[a], 1);
       mbarrier_init(&tempty[a], 4 * Cfg::EPI_GROUPS);   // one arrive per epilogue warp
     }
+    for (int w = 0; w < 4 * Cfg::EPI_GROUPS; ++w) mbarrier_init(&rbars[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -300,8 +548,9 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
     // residual / accumulate / ReLU / mask, 16-byte stores along the thread's own output row.
     pdl_wait();   // residual / mask / accumulate reads and the output stores touch memory of earlier kernels
     const int ew = warp & 3, half = (warp - 4) >> 2;              // half = column group of this warp
-    constexpr int GCOLS = BN / Cfg::EPI_GROUPS;                  // columns per group
-    constexpr int NCH = GCOLS / 32;                               // 32-column chunks per warp
+    unsigned char* ebuf = staging + (size_t)(warp - 4) * EPI_BOX_BYTES;   // TMA-epilogue staging box of this warp
+    uint64_t* rbar = rbars + (warp - 4);
+    uint32_t rph = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -316,142 +565,11 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
       sp /= S.tiles_x;
       const int ty = sp % S.tiles_y;
       const int n = sp / S.tiles_y;
-      const int m = ew * 32 + lane;
-      const int y = ty * S.TH + (m >> S.tw_shift), x = tx * S.TW + (m & (S.TW - 1));
-      const bool pix_ok = (y < S.HO) && (x < S.WO);
-      const size_t pix = pix_ok ? out_offset(S, n, y, x) : 0;
-      const __nv_bfloat16* addp = nullptr;
-      if (S.add_src && pix_ok) {
-        const int ay = (int)(((long long)y * S.add_H) / S.HO), ax = (int)(((long long)x * S.add_W) / S.WO);
-        addp = S.add_src + (((size_t)n * S.add_H + ay) * S.add_W + ax) * (size_t)p.add_ld;
-      }
-      const int col0 = nt * BN + half * GCOLS;
-      const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * GCOLS);
-      mbarrier_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      // SHORTK (two CTAs per SM, 85-register budget): one TMEM buffer, chunks strictly one after the other -- the
-      // second CTA provides the latency hiding.  Otherwise the next chunk's tcgen05.ld is issued one chunk ahead.
-      uint32_t rbuf[SHORTK ? 1 : 2][32];
-      if (!SHORTK && col0 < p.Cout) tmem_ld32_nowait(tbase, rbuf[0]);
-#pragma unroll(SHORTK ? 1 : NCH)
-      for (int ch = 0; ch < NCH; ++ch) {
-        const int cbase = col0 + ch * 32;
-        if (cbase >= p.Cout) break;   // warp-uniform
-        if (SHORTK) tmem_ld32_nowait(tbase + ch * 32, rbuf[0]);
-        tmem_ld_wait();
-        if (!SHORTK && ch + 1 < NCH && cbase + 32 < p.Cout) tmem_ld32_nowait(tbase + (ch + 1) * 32, rbuf[(ch + 1) & 1]);
-        const uint32_t* r = rbuf[SHORTK ? 0 : (ch & 1)];
-        if (!pix_ok) continue;
-        const bool full = (cbase + 32 <= p.Cout) && p.vec_ok;   // warp-uniform fast path
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (full) {
-          if (p.scale) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + cbase + j));
-              v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-            }
-          }
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          }
-          if (addp) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 q = __ldg(reinterpret_cast<const uint4*>(addp + cbase + j));
-              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(hh[e]);
-                v[j + 2 * e] += f.x;
-                v[j + 2 * e + 1] += f.y;
-              }
-            }
-          }
-          if (p.accumulate) {
-            if (p.out_f32) {
-              const float* o = (const float*)S.out + pix * (size_t)p.ldc + cbase;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 o4 = *reinterpret_cast<const float4*>(o + j);
-                v[j] += o4.x; v[j + 1] += o4.y; v[j + 2] += o4.z; v[j + 3] += o4.w;
-              }
-            } else {
-              const __nv_bfloat16* o = (const __nv_bfloat16*)S.out + pix * (size_t)p.ldc + cbase;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 q = *reinterpret_cast<const uint4*>(o + j);
-                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(hh[e]);
-                  v[j + 2 * e] += f.x;
-                  v[j + 2 * e + 1] += f.y;
-                }
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (S.mask_src) {
-            const __nv_bfloat16* mk = S.mask_src + pix * (size_t)p.mask_ld + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 q = __ldg(reinterpret_cast<const uint4*>(mk + j));
-              const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&q);
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (!(__bfloat162float(hb[e]) > 0.f)) v[j + e] = 0.f;
-            }
-          }
-          if (p.out_f32) {
-            float* o = (float*)S.out + pix * (size_t)p.ldc + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            __nv_bfloat16* o = (__nv_bfloat16*)S.out + pix * (size_t)p.ldc + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q;
-              __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&q);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-              *reinterpret_cast<uint4*>(o + j) = q;
-            }
-          }
-        } else {
-          // ragged tail (Cout not a multiple of 32, or unaligned leading dimension): scalar path
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = cbase + j;
-            if (c >= p.Cout) continue;
-            float vv = v[j];
-            if (p.scale) vv *= __ldg(p.scale + c);
-            if (p.bias) vv += __ldg(p.bias + c);
-            if (addp) vv += __bfloat162float(addp[c]);
-            if (p.accumulate)
-              vv += p.out_f32 ? ((const float*)S.out)[pix * (size_t)p.ldc + c]
-                              : __bfloat162float(((const __nv_bfloat16*)S.out)[pix * (size_t)p.ldc + c]);
-            if (p.relu) vv = fmaxf(vv, 0.f);
-            if (S.mask_src && !(__bfloat162float(S.mask_src[pix * (size_t)p.mask_ld + c]) > 0.f)) vv = 0.f;
-            if (p.out_f32) ((float*)S.out)[pix * (size_t)p.ldc + c] = vv;
-            else ((__nv_bfloat16*)S.out)[pix * (size_t)p.ldc + c] = __float2bfloat16_rn(vv);
-          }
-        }
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
+      epilogue_tile<BN, SHORTK, Cfg::EPI_GROUPS>(p, maps, S, sg, nt, tx, ty, n, true, tmem_base + (uint32_t)(acc * BN),
+                                                 &tfull[acc], acc_phase, ew, half, lane, ebuf, rbar, rph);
       if (lane == 0) mbarrier_arrive(&tempty[acc]);
     }
+    if (lane == 0) bulk_wait_all();   // staging buffers must outlive the TMA stores that read them
   }
   tc_fence_before();
   __syncthreads();
@@ -471,10 +589,11 @@ struct Conv2Cfg {
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;  // 32 KB
   static constexpr int STAGES = 6;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int STAGING_BYTES = 0;
+  static constexpr int STAGING_BYTES = 4 * 2 * EPI_BOX_BYTES;
   static constexpr int EPI_GROUPS = 2;
   static constexpr int THREADS = 128 + 128 * EPI_GROUPS;
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                     ((uint32_t)(256 >> 4) << 24);
 };
@@ -526,6 +645,7 @@ conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ C
   uint64_t* tfull = bars + 2 * Cfg::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint64_t* rbars = tempty + 3;   // one per epilogue warp (TMA-epilogue residual / mask loads)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cchunks = p.Cin / KCH;
@@ -545,6 +665,7 @@ conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ C
       mbarrier_init(&tfull[a], 1);
       mbarrier_init(&tempty[a], 2 * 4 * Cfg::EPI_GROUPS);   // one arrive per epilogue warp of BOTH CTAs (leader's copy is used)
     }
+    for (int w = 0; w < 4 * Cfg::EPI_GROUPS; ++w) mbarrier_init(&rbars[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -633,8 +754,9 @@ conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ C
     // residual / accumulate / ReLU / mask, 16-byte stores along the thread's own output row.
     pdl_wait();   // residual / mask / accumulate reads and the output stores touch memory of earlier kernels
     const int ew = warp & 3, half = (warp - 4) >> 2;              // half = column group of this warp
-    constexpr int GCOLS = BN / Cfg::EPI_GROUPS;                  // columns per group
-    constexpr int NCH = GCOLS / 32;                               // 32-column chunks per warp
+    unsigned char* ebuf = staging + (size_t)(warp - 4) * EPI_BOX_BYTES;   // TMA-epilogue staging box of this warp
+    uint64_t* rbar = rbars + (warp - 4);
+    uint32_t rph = 0;
     int it = 0;
     for (int q = blockIdx.x >> 1; q < pairs; q += gridDim.x >> 1, ++it) {
       const int acc = it & 1;
@@ -650,142 +772,11 @@ conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ C
       sp /= S.tiles_x;
       const int ty = sp % S.tiles_y;
       const int n = dummy ? S.N : sp / S.tiles_y;   // image index N is out of bounds: TMA zero-fills
-      const int m = ew * 32 + lane;
-      const int y = ty * S.TH + (m >> S.tw_shift), x = tx * S.TW + (m & (S.TW - 1));
-      const bool pix_ok = !dummy && (y < S.HO) && (x < S.WO);
-      const size_t pix = pix_ok ? out_offset(S, n, y, x) : 0;
-      const __nv_bfloat16* addp = nullptr;
-      if (S.add_src && pix_ok) {
-        const int ay = (int)(((long long)y * S.add_H) / S.HO), ax = (int)(((long long)x * S.add_W) / S.WO);
-        addp = S.add_src + (((size_t)n * S.add_H + ay) * S.add_W + ax) * (size_t)p.add_ld;
-      }
-      const int col0 = nt * BN + half * GCOLS;
-      const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * GCOLS);
-      mbarrier_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      // SHORTK (two CTAs per SM, 85-register budget): one TMEM buffer, chunks strictly one after the other -- the
-      // second CTA provides the latency hiding.  Otherwise the next chunk's tcgen05.ld is issued one chunk ahead.
-      uint32_t rbuf[SHORTK ? 1 : 2][32];
-      if (!SHORTK && col0 < p.Cout) tmem_ld32_nowait(tbase, rbuf[0]);
-#pragma unroll(SHORTK ? 1 : NCH)
-      for (int ch = 0; ch < NCH; ++ch) {
-        const int cbase = col0 + ch * 32;
-        if (cbase >= p.Cout) break;   // warp-uniform
-        if (SHORTK) tmem_ld32_nowait(tbase + ch * 32, rbuf[0]);
-        tmem_ld_wait();
-        if (!SHORTK && ch + 1 < NCH && cbase + 32 < p.Cout) tmem_ld32_nowait(tbase + (ch + 1) * 32, rbuf[(ch + 1) & 1]);
-        const uint32_t* r = rbuf[SHORTK ? 0 : (ch & 1)];
-        if (!pix_ok) continue;
-        const bool full = (cbase + 32 <= p.Cout) && p.vec_ok;   // warp-uniform fast path
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (full) {
-          if (p.scale) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + cbase + j));
-              v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-            }
-          }
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          }
-          if (addp) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 q = __ldg(reinterpret_cast<const uint4*>(addp + cbase + j));
-              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(hh[e]);
-                v[j + 2 * e] += f.x;
-                v[j + 2 * e + 1] += f.y;
-              }
-            }
-          }
-          if (p.accumulate) {
-            if (p.out_f32) {
-              const float* o = (const float*)S.out + pix * (size_t)p.ldc + cbase;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 o4 = *reinterpret_cast<const float4*>(o + j);
-                v[j] += o4.x; v[j + 1] += o4.y; v[j + 2] += o4.z; v[j + 3] += o4.w;
-              }
-            } else {
-              const __nv_bfloat16* o = (const __nv_bfloat16*)S.out + pix * (size_t)p.ldc + cbase;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 q = *reinterpret_cast<const uint4*>(o + j);
-                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(hh[e]);
-                  v[j + 2 * e] += f.x;
-                  v[j + 2 * e + 1] += f.y;
-                }
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (S.mask_src) {
-            const __nv_bfloat16* mk = S.mask_src + pix * (size_t)p.mask_ld + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 q = __ldg(reinterpret_cast<const uint4*>(mk + j));
-              const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&q);
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (!(__bfloat162float(hb[e]) > 0.f)) v[j + e] = 0.f;
-            }
-          }
-          if (p.out_f32) {
-            float* o = (float*)S.out + pix * (size_t)p.ldc + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            __nv_bfloat16* o = (__nv_bfloat16*)S.out + pix * (size_t)p.ldc + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q;
-              __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&q);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-              *reinterpret_cast<uint4*>(o + j) = q;
-            }
-          }
-        } else {
-          // ragged tail (Cout not a multiple of 32, or unaligned leading dimension): scalar path
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = cbase + j;
-            if (c >= p.Cout) continue;
-            float vv = v[j];
-            if (p.scale) vv *= __ldg(p.scale + c);
-            if (p.bias) vv += __ldg(p.bias + c);
-            if (addp) vv += __bfloat162float(addp[c]);
-            if (p.accumulate)
-              vv += p.out_f32 ? ((const float*)S.out)[pix * (size_t)p.ldc + c]
-                              : __bfloat162float(((const __nv_bfloat16*)S.out)[pix * (size_t)p.ldc + c]);
-            if (p.relu) vv = fmaxf(vv, 0.f);
-            if (S.mask_src && !(__bfloat162float(S.mask_src[pix * (size_t)p.mask_ld + c]) > 0.f)) vv = 0.f;
-            if (p.out_f32) ((float*)S.out)[pix * (size_t)p.ldc + c] = vv;
-            else ((__nv_bfloat16*)S.out)[pix * (size_t)p.ldc + c] = __float2bfloat16_rn(vv);
-          }
-        }
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
+      epilogue_tile<BN, SHORTK, Cfg::EPI_GROUPS>(p, maps, S, sg, nt, tx, ty, n, !dummy, tmem_base + (uint32_t)(acc * BN),
+                                                 &tfull[acc], acc_phase, ew, half, lane, ebuf, rbar, rph);
       if (lane == 0) mbarrier_arrive_leader(&tempty[acc]);
     }
+    if (lane == 0) bulk_wait_all();   // staging buffers must outlive the TMA stores that read them
   }
   tc_fence_before();
   cluster_sync_all();
@@ -1085,7 +1076,7 @@ static int launch_conv2(const ConvMaps& maps, const CUtensorMap& tmB, const Conv
 
 // geometry + tensor maps of one segment
 static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& common, ConvSeg* g, CUtensorMap* tmA,
-                         CUtensorMap* tmR, CUtensorMap* tmM) {
+                         CUtensorMap* tmR, CUtensorMap* tmM, CUtensorMap* tmO, CUtensorMap* tmRL, CUtensorMap* tmML) {
   LDB_REQUIRE(d->in && d->out, LDB_EINVAL, "conv2d_tc: null pointer");
   LDB_REQUIRE(d->in_ld >= d->Cin && d->in_ld % 8 == 0, LDB_EINVAL, "conv2d_tc: in_ld must be >= Cin and a multiple of 8");
   LDB_REQUIRE(d->N >= 1 && d->HO >= 1 && d->WO >= 1, LDB_EINVAL, "conv2d_tc: shape");
@@ -1155,6 +1146,31 @@ static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& commo
   if (g->mask_src && ident && common.mask_ld % 8 == 0) {
     if (aux_map(tmM, g->mask_src, common.mask_ld, "mask prefetch") == 0) g->pf_mask = 1;
   }
+  // TMA epilogue: one box = the 32 pixels of an epilogue warp (32 x 1 of a wide tile, TW x 32/TW of a narrow one)
+  // x 64 channels, 128-byte swizzled in shared memory
+  *tmO = *tmA; *tmRL = *tmA; *tmML = *tmA;
+  if (common.tma_epi) {
+    const cuuint32_t bw = g->TW < EPI_BOX_PIX ? g->TW : EPI_BOX_PIX, bh = EPI_BOX_PIX / bw;
+    auto box_map = [&](CUtensorMap* m, const void* base, int ld, const char* what) -> int {
+      cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)g->OW, (cuuint64_t)g->OH, (cuuint64_t)g->N};
+      cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * g->OW, (cuuint64_t)ld * 2 * g->OW * g->OH};
+      cuuint32_t box[4] = {64, bw, bh, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      return encode_map(m, base, 4, dims, strides, box, es, what);
+    };
+    int e = box_map(tmO, g->out, common.ldc, "output store");
+    if (e) return e;
+    if (g->add_src && g->add_H == g->OH && g->add_W == g->OW) {
+      e = box_map(tmRL, g->add_src, common.add_ld, "residual load");
+      if (e) return e;
+      g->tl_add = 1;
+    }
+    if (g->mask_src) {
+      e = box_map(tmML, g->mask_src, common.mask_ld, "mask load");
+      if (e) return e;
+      g->tl_mask = 1;
+    }
+  }
   return 0;
 }
 
@@ -1214,16 +1230,37 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
   const int BN = shortk ? (d->Cout > 64 ? 128 : 64) : (d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64));
   p.tiles_n = (d->Cout + BN - 1) / BN;
   p.nseg = count;
+  // TMA-staged epilogue: bf16 output with the identity pixel mapping (everything but the stride-2 dgrad parity
+  // classes, fp32 head outputs and accumulating launches); LDB200_NO_TMA_EPI=1 forces the direct stores
+  static const bool tma_epi_env = getenv("LDB200_NO_TMA_EPI") == nullptr;
+  p.tma_epi = tma_epi_env && BN >= 128 && !d->out_f32 && !d->accumulate && p.vec_ok && d->Cout % 64 == 0;
+  for (int i = 0; i < count && p.tma_epi; ++i) {
+    const ldb_conv_desc* e = &descs[i];
+    const bool ident = e->oys <= 1 && e->oxs <= 1 && e->oyo == 0 && e->oxo == 0 && (e->OH == 0 || e->OH == e->HO) &&
+                       (e->OW == 0 || e->OW == e->WO);
+    if (!ident || ((uintptr_t)e->out & 15) || (e->mask_src && ((uintptr_t)e->mask_src & 15))) p.tma_epi = 0;
+  }
+  // 256-wide tiles push TWO 64-column boxes per warp through the one staging buffer; measured on the LD shapes this
+  // only pays when a residual or mask box comes in through it too (plain 1x1 convs: 768 vs 814 TFLOP/s)
+  static const bool tma_epi_all = getenv("LDB200_TMA_EPI_ALL") != nullptr;
+  if (p.tma_epi && BN == 256 && !tma_epi_all) {
+    const bool same_size_add = d->add_src && (d->add_H == 0 || d->add_H == (d->OH ? d->OH : d->HO)) &&
+                               (d->add_W == 0 || d->add_W == (d->OW ? d->OW : d->WO));
+    if (!same_size_add && !d->mask_src) p.tma_epi = 0;
+  }
   ConvMaps maps;
   int tile0 = 0;
   for (int i = 0; i < count; ++i) {
-    int e = build_segment(&descs[i], BN, p, &p.seg[i], &maps.a[i], &maps.r[i], &maps.m[i]);
+    int e = build_segment(&descs[i], BN, p, &p.seg[i], &maps.a[i], &maps.r[i], &maps.m[i], &maps.o[i], &maps.rl[i],
+                          &maps.ml[i]);
     if (e) return e;
     p.seg_tile0[i] = tile0;
     tile0 += p.seg[i].N * p.seg[i].tiles_y * p.seg[i].tiles_x * p.tiles_n;
   }
   for (int i = count; i <= CONV_MAX_SEG; ++i) p.seg_tile0[i] = tile0;
-  for (int i = count; i < CONV_MAX_SEG; ++i) { maps.a[i] = maps.a[0]; maps.r[i] = maps.a[0]; maps.m[i] = maps.a[0]; }
+  for (int i = count; i < CONV_MAX_SEG; ++i) {
+    maps.a[i] = maps.r[i] = maps.m[i] = maps.o[i] = maps.rl[i] = maps.ml[i] = maps.a[0];
+  }
   static const bool conv2_env = getenv("LDB200_NO_CONV2") == nullptr;   // 2-CTA kernel is the default for 256-wide tiles
   const bool use2 = conv2_env && !shortk && BN == 256 && d->Cout % 256 == 0;
   CUtensorMap tmB;

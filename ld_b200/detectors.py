@@ -228,6 +228,7 @@ class LDTrainStep:
 
     def step(self, data, sync_logs=True):
         self.flat_g.zero_()
+        engine.zero_pool_begin(self.flat_g.device)
         losses = self.model(**data)
         if sync_logs:
             loss, log_vars = self.model._parse_losses(losses)
@@ -235,6 +236,7 @@ class LDTrainStep:
             loss = sum(sum(v) for k, v in losses.items() if 'loss' in k)
             log_vars = None
         loss.backward()
+        engine.zero_pool_end()
         if self.world > 1:
             dist.all_reduce(self.flat_g)
         ops.sgd_flat(self.flat_w, self.flat_g, self.flat_m, self.lr_at(self.iter), self.momentum, self.wd,
@@ -247,10 +249,12 @@ class LDTrainStep:
     def _body(self, data):
         """Everything of one iteration that depends only on device-resident state: captured once."""
         self.flat_g.zero_()
+        engine.zero_pool_begin(self.flat_g.device)
         losses = self.model(**data)
         terms = torch.stack([sum(v) for v in losses.values()])
         loss = terms.sum()
         loss.backward()
+        engine.zero_pool_end()
         if self.world > 1:
             dist.all_reduce(self.flat_g)
         ops.sgd_flat_dev(self.flat_w, self.flat_g, self.flat_m, self._hyper)

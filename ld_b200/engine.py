@@ -139,8 +139,11 @@ class ConvAffineAct(torch.autograd.Function):
         g = ops.relu_bwd(dy, y) if relu else dy
         d_x = d_w = d_scale = d_shift = d_res = None
         if need_shift:
-            d_shift = torch.zeros(co, dtype=torch.float32, device=g.device)
+            sink = _grad_sink(shift)          # conv bias parameter: accumulate straight into its gradient
+            d_shift = sink if sink is not None else zeros_f32(co, g.device)
             ops.colsum(g.reshape(-1, g.shape[-1]), d_shift)
+            if sink is not None:
+                d_shift = None
         if need_w or need_scale:
             # the wgrad kernel accumulates scale[co]*G straight into the parameter's gradient buffer (the flat
             # gradient buffer of LDTrainStep, or a lazily created channels-last .grad) and emits d_scale from
@@ -150,7 +153,7 @@ class ConvAffineAct(torch.autograd.Function):
             gbuf = weight.grad.permute(0, 2, 3, 1)
             assert gbuf.is_contiguous(), 'conv weight gradients must be channels-last'
             if need_scale:
-                d_scale = torch.zeros(co, dtype=torch.float32, device=g.device)
+                d_scale = zeros_f32(co, g.device)
             wm = weight.detach().permute(0, 2, 3, 1).reshape(co, -1)
             ops.conv2d_wgrad_tc(g, x, gbuf.reshape(co, -1), kh, kw, stride, pad,
                                 scale=None if scale is None else scale.detach().contiguous(),
@@ -172,24 +175,72 @@ def conv_affine_act(x, weight, scale=None, shift=None, residual=None, stride=1, 
                                None if out is None else OutSlot(out), out_dtype, x_premask)
 
 
+class _ZeroPool:
+    """Bump allocator over ONE zero-filled fp32 buffer for the small per-channel reduction outputs of the backward
+    pass (d_scale, d_shift, column sums): `LDTrainStep` re-zeroes the used extent with one memset per step instead
+    of ~270 fill launches.  Inactive outside `zero_pool_begin/.._end` (plain autograd use): `zeros_f32` then falls
+    back to `torch.zeros`."""
+    buf = None
+    off = 0
+    active = False
+
+
+def zero_pool_begin(device, capacity=1 << 20):
+    zp = _ZeroPool
+    if zp.buf is None or zp.buf.device != device:
+        zp.buf, zp.off = torch.zeros(capacity, dtype=torch.float32, device=device), 0
+    if zp.off:
+        zp.buf[:zp.off].zero_()
+    zp.off, zp.active = 0, True
+
+
+def zero_pool_end():
+    _ZeroPool.active = False
+
+
+def zeros_f32(n, device):
+    zp = _ZeroPool
+    if zp.active and zp.buf.device == device:
+        m = (n + 31) & ~31                      # 128-byte granules keep every view 16-byte aligned
+        if zp.off + m <= zp.buf.numel():
+            v = zp.buf[zp.off:zp.off + n]
+            zp.off += m
+            return v
+    return torch.zeros(n, dtype=torch.float32, device=device)
+
+
+def _grad_sink(p):
+    """The fp32 `.grad` of a leaf parameter that kernels may accumulate into directly (the flat gradient buffer of
+    `LDTrainStep`): saves the zero-fill of a temporary and autograd's AccumulateGrad add.  None -> return the
+    gradient through autograd as usual."""
+    if p is None or not p.is_leaf or not p.requires_grad:
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.device != p.device:
+        return None
+    return g
+
+
 class GNReLU(torch.autograd.Function):
     """y = relu(GroupNorm(x)) on NHWC bf16 (gfl_head.py:102-133 ConvModule norm+act)."""
 
     @staticmethod
     def forward(ctx, x, gamma, beta, groups, eps):
         y, stats = ops.gn_relu_fwd(x, gamma.detach().contiguous(), beta.detach().contiguous(), groups, eps, True)
-        ctx.save_for_backward(x, y, stats, gamma)
+        ctx.save_for_backward(x, y, stats, gamma, beta)
         ctx.cfg = (groups, eps)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, stats, gamma = ctx.saved_tensors
+        x, y, stats, gamma, beta = ctx.saved_tensors
         groups, eps = ctx.cfg
-        dg = torch.zeros_like(gamma, dtype=torch.float32)
-        db = torch.zeros_like(gamma, dtype=torch.float32)
+        sg, sb = _grad_sink(gamma), _grad_sink(beta)
+        direct = sg is not None and sb is not None
+        dg = sg if direct else zeros_f32(gamma.numel(), x.device)
+        db = sb if direct else zeros_f32(gamma.numel(), x.device)
         dx = ops.gn_relu_bwd(dy.contiguous(), y, x, stats, gamma.detach().contiguous(), dg, db, groups, eps)
-        return dx, dg, db, None, None
+        return (dx, None, None, None, None) if direct else (dx, dg, db, None, None)
 
 
 def gn_relu(x, gamma, beta, groups=32, eps=1e-5):
@@ -258,7 +309,7 @@ def _wgrad_into(weight, g, x, scale, stride, pad, need_scale):
         weight.grad = torch.zeros_like(weight, memory_format=torch.channels_last)
     gbuf = weight.grad.permute(0, 2, 3, 1)
     assert gbuf.is_contiguous(), 'conv weight gradients must be channels-last'
-    d_scale = torch.zeros(co, dtype=torch.float32, device=g.device) if need_scale else None
+    d_scale = zeros_f32(co, g.device) if need_scale else None
     ops.conv2d_wgrad_tc(g, x, gbuf.reshape(co, -1), kh, kw, stride, pad,
                         scale=None if scale is None else scale.detach().contiguous(),
                         w_master=weight.detach().permute(0, 2, 3, 1).reshape(co, -1) if need_scale else None,
@@ -267,7 +318,7 @@ def _wgrad_into(weight, g, x, scale, stride, pad, need_scale):
 
 
 def _colsum(g):
-    out = torch.zeros(g.shape[-1], dtype=torch.float32, device=g.device)
+    out = zeros_f32(g.shape[-1], g.device)
     ops.colsum(g.reshape(-1, g.shape[-1]), out)
     return out
 

@@ -88,6 +88,48 @@ def test_conv_epilogue_fusions():
     torch.cuda.synchronize()
 
 
+TMA_EPI_CASES = [
+    # n, h, w, cin, cout, k, pad  -- bf16 outputs with Cout % 64 == 0 leave through the TMA-staged epilogue
+    (2, 20, 28, 128, 512, 1, 0),    # flat 1x1, short reduction (2 CTAs / SM kernel), 128-pixel rows
+    (2, 20, 28, 512, 256, 1, 0),    # flat 1x1, 2-CTA kernel
+    (1, 25, 42, 256, 256, 3, 1),    # 3x3, 2-CTA kernel, odd number of pixel tiles (dummy pair tile)
+    (3, 7, 6, 256, 256, 3, 1),      # narrow map: 8-wide tiles, 8 x 4 pixel boxes, clipped on both edges
+    (2, 9, 70, 128, 128, 3, 1),     # wide map: 32 x 1 boxes
+    (2, 13, 21, 320, 192, 3, 1),    # Cin, Cout multiples of 64 only (BN = 256 tile half empty)
+]
+
+
+@pytest.mark.parametrize('case', TMA_EPI_CASES, ids=lambda c: 'x'.join(map(str, c)))
+def test_conv_tma_epilogue_fusions(case):
+    """bf16 output + folded-BN scale/bias + residual + ReLU, and + ReLU-mask, through the TMA-staged epilogue
+    (residual / mask boxes TMA-loaded, result TMA-stored) against the fp32 reference."""
+    from ld_b200 import ops
+    n, h, w, cin, cout, k, pad = case
+    g = torch.Generator(device='cuda').manual_seed(sum(case))
+    x = torch.randn(n, h, w, cin, device='cuda', generator=g).bfloat16()
+    wt = torch.randn(cout, cin, k, k, device='cuda', generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    wp = ops.pack_conv_weight(wt)
+    scale = torch.rand(cout, device='cuda', generator=g) + 0.5
+    bias = torch.randn(cout, device='cuda', generator=g)
+    res = torch.randn(n, h, w, cout, device='cuda', generator=g).bfloat16()
+    mask = torch.randn(n, h, w, cout, device='cuda', generator=g).bfloat16()
+    mask[..., ::7] = 0       # exact zeros and negative zeros are "not > 0"
+    mask[..., 3::11] = -0.0
+    y = ops.conv2d_tc(x, wp, cout, k, k, 1, pad, scale=scale, bias=bias, add=res, relu=True)
+    check(y, ref_conv(x, wt, 1, pad, scale, bias, res, True), 5e-3)
+    y = ops.conv2d_tc(x, wp, cout, k, k, 1, pad, scale=scale, add=res, mask=mask)
+    check(y, ref_conv(x, wt, 1, pad, scale, None, res) * (mask.float() > 0), 5e-3)
+    y = ops.conv2d_tc(x, wp, cout, k, k, 1, pad, mask=mask)
+    want = ref_conv(x, wt, 1, pad) * (mask.float() > 0)
+    check(y, want, 5e-3)
+    # output written into a channel slice of a wider buffer (row-space buffers): neighbours stay untouched
+    wide = torch.full((n, h, w, cout + 64), 7.0, device='cuda', dtype=torch.bfloat16)
+    ops.conv2d_tc(x, wp, cout, k, k, 1, pad, out=wide[..., :cout], bias=bias)
+    check(wide[..., :cout], ref_conv(x, wt, 1, pad, None, bias), 5e-3)
+    assert bool((wide[..., cout:] == 7.0).all())
+    torch.cuda.synchronize()
+
+
 def test_conv_dgrad_matches_autograd():
     """Data gradient of a stride-1 3x3 and a 1x1 conv through the same kernel with rotated weights."""
     from ld_b200 import ops
