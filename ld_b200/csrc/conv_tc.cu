@@ -987,6 +987,184 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// 2-CTA weight gradient (cta_group::2): 256 output channels x 256 input channels per cluster, every CTA stages its
+// own 128 + 128 channels of the pixel tile.  The 1-CTA 128 x 256 tile needs (128 + 256) * 128 * 2 B of operands per
+// 8.4 MFLOP = 131 GB/s per SM at tensor peak -- more than an SM can pull from L2; the pair tile needs 87 GB/s.
+struct Wgrad2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int A_BYTES = 2 * A_TILE_BYTES;     // this CTA's 128 output channels
+  static constexpr int B_BYTES = 2 * A_TILE_BYTES;     // this CTA's 128 input channels
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 3;
+  static constexpr int TMEM_COLS = 256;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradParams p) {
+  using Cfg = Wgrad2Cfg;
+  constexpr int BN = Wgrad2Cfg::BN;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  extern __shared__ unsigned char conv_smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)conv_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tfull = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ptiles = p.N * p.tiles_y * p.tiles_x;
+  const int units = p.co_tiles * p.ci_tiles * p.ntaps * p.splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbarrier_init(&full[s], 1);
+      mbarrier_init(&empty[s], 1);
+    }
+    mbarrier_init(tfull, 1);
+    mbarrier_init(tempty, 2 * 4);   // epilogue warps of both CTAs arrive on the leader's copy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)),
+                 "n"(Cfg::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      pdl_wait();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x >> 1; u < units; u += gridDim.x >> 1) {
+        const int split = u % p.splits;
+        int rest = u / p.splits;
+        const int tap = rest % p.ntaps;
+        rest /= p.ntaps;
+        const int ci_t = rest % p.ci_tiles, co_t = rest / p.ci_tiles;
+        const int pt0 = (int)(((long long)ptiles * split) / p.splits);
+        const int pt1 = (int)(((long long)ptiles * (split + 1)) / p.splits);
+        for (int pt = pt0; pt < pt1; ++pt) {
+          const int tx = pt % p.tiles_x;
+          const int ty = (pt / p.tiles_x) % p.tiles_y;
+          const int n = pt / (p.tiles_x * p.tiles_y);
+          mbarrier_wait(&empty[stage], phase ^ 1);
+          unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+          // this CTA's 128 of the pair's 256 output channels and 128 of its 256 input channels; all four boxes of
+          // both CTAs complete on the leader's barrier
+          if (rank == 0) mbarrier_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_4d_2sm(sa + j * A_TILE_BYTES, &tmA, &full[stage], co_t * 2 * TILE_M + (int)rank * TILE_M + 64 * j,
+                            tx * p.TW, ty * p.TH, n);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_4d_2sm(sa + Cfg::A_BYTES + j * A_TILE_BYTES, &tmB, &full[stage], ci_t * BN + (int)rank * (BN / 2) + 64 * j,
+                            tx * p.TW * p.sx + p.tap_dx[tap], ty * p.TH * p.sy + p.tap_dy[tap], n);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = blockIdx.x >> 1; u < units; u += gridDim.x >> 1, ++it) {
+        const int split = u % p.splits;
+        const int pt0 = (int)(((long long)ptiles * split) / p.splits);
+        const int pt1 = (int)(((long long)ptiles * (split + 1)) / p.splits);
+        mbarrier_wait(tempty, (it & 1) ^ 1);
+        tc_fence_after();
+        for (int pt = pt0; pt < pt1; ++pt) {
+          mbarrier_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = s2u(smem + (size_t)stage * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < TILE_M / 16; ++k) {
+            // 16 pixels = two 8-row groups = 2 KB further down the tile
+            umma_bf16_2cta(tmem_base, smem_desc_mn128(sa + k * 2048), smem_desc_mn128(sa + Cfg::A_BYTES + k * 2048),
+                      Cfg::IDESC, (pt > pt0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2cta(&empty[stage]);
+          if (pt == pt1 - 1) umma_commit_2cta(tfull);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (pt1 == pt0) umma_commit_2cta(tfull);   // empty slice: nothing accumulated (epilogue skips it)
+      }
+    }
+  } else if (warp >= 4) {
+    pdl_wait();
+    const int ew = warp - 4;
+    int it = 0;
+    for (int u = blockIdx.x >> 1; u < units; u += gridDim.x >> 1, ++it) {
+      const int split = u % p.splits;
+      int rest = u / p.splits;
+      const int tap = rest % p.ntaps;
+      rest /= p.ntaps;
+      const int ci_t = rest % p.ci_tiles, co_t = rest / p.ci_tiles;
+      const int pt0 = (int)(((long long)ptiles * split) / p.splits);
+      const int pt1 = (int)(((long long)ptiles * (split + 1)) / p.splits);
+      const int co = co_t * 2 * TILE_M + (int)rank * TILE_M + ew * 32 + lane;
+      mbarrier_wait(tfull, it & 1);
+      tc_fence_after();
+      if (pt1 > pt0) {
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          const int cbase = ci_t * BN + ch * 32;
+          if (cbase >= p.Cin) break;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ch * 32), r);
+          if (co < p.Cout) {
+            const size_t woff = (size_t)co * p.w_k + p.tap_wk[tap] + cbase;
+            float* o = p.dw + woff;
+            const float sc = p.scale ? __ldg(p.scale + co) : 1.f;
+            float dot = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (cbase + j + 4 <= p.Cin) {
+                const float4 g4 = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                if (p.d_scale) {
+                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.w_master + woff + j));
+                  dot += g4.x * w4.x + g4.y * w4.y + g4.z * w4.z + g4.w * w4.w;
+                }
+                atomicAdd(reinterpret_cast<float4*>(o + j), make_float4(g4.x * sc, g4.y * sc, g4.z * sc, g4.w * sc));
+              } else {
+                for (int e = 0; e < 4; ++e)
+                  if (cbase + j + e < p.Cin) {
+                    const float gv = __uint_as_float(r[j + e]);
+                    if (p.d_scale) dot += gv * __ldg(p.w_master + woff + j + e);
+                    atomicAdd(o + j + e, gv * sc);
+                  }
+              }
+            }
+            if (p.d_scale) atomicAdd(p.d_scale + co, dot);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbarrier_arrive_leader(tempty);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS));
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1366,6 +1544,33 @@ extern "C" int ldb200_conv2d_wgrad_tc(const ldb_wgrad_desc* d, void* stream_) {
     cuuint32_t es[4] = {1, (cuuint32_t)d->sx, (cuuint32_t)d->sy, 1};
     int e = encode_map(&tmB, d->x, 4, dims, strides, box, es, "wgrad X");
     if (e) return e;
+  }
+  static const bool wgrad2_env = getenv("LDB200_NO_WGRAD2") == nullptr;
+  if (wgrad2_env && BN == 256 && d->Cout % 256 == 0 && d->Cin % 256 == 0) {
+    static int max_clusters = 0;
+    if (!max_clusters) {
+      LDB_CUDA(cudaFuncSetAttribute(wgrad2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Wgrad2Cfg::SMEM));
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(g_conv_sms / 2 * 2);
+      cfg.blockDim = dim3(CONV_THREADS);
+      cfg.dynamicSmemBytes = Wgrad2Cfg::SMEM;
+      int n = 0;
+      LDB_CUDA(cudaOccupancyMaxActiveClusters(&n, wgrad2_tc_kernel, &cfg));
+      LDB_REQUIRE(n >= 1, LDB_ENOSUP, "wgrad_tc: no resident 2-CTA cluster");
+      max_clusters = n < g_conv_sms / 2 ? n : g_conv_sms / 2;
+    }
+    p.co_tiles = d->Cout / 256;
+    const int base2 = p.co_tiles * p.ci_tiles * p.ntaps;
+    int sp = (max_clusters + base2 / 2) / base2;
+    if (sp > ptiles) sp = ptiles;
+    if (sp < 1) sp = 1;
+    p.splits = sp;
+    const int units = base2 * sp;
+    const int clusters = units < max_clusters ? units : max_clusters;
+    wgrad2_tc_kernel<<<2 * clusters, CONV_THREADS, Wgrad2Cfg::SMEM, stream>>>(tmA, tmB, p);
+    LDB_CUDA(cudaGetLastError());
+    return 0;
   }
   if (BN == 256) return launch_wgrad<256>(tmA, tmB, p, stream);
   if (BN == 128) return launch_wgrad<128>(tmA, tmB, p, stream);

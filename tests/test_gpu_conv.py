@@ -157,6 +157,8 @@ WG_CASES = [
     (2, 33, 47, 128, 128, 3, 2, 1),
     (2, 32, 48, 256, 512, 1, 2, 0),
     (1, 50, 84, 512, 128, 1, 1, 0),
+    (2, 20, 28, 512, 256, 1, 1, 0),     # 2-CTA pair tile, two input-channel tiles
+    (3, 9, 11, 256, 768, 3, 1, 1),      # 2-CTA, three output-channel pair tiles, tiny maps (more splits than tiles)
 ]
 
 

@@ -34,3 +34,24 @@ for n, h, w, ci, co, k, st, pad in SHAPES:
     ms = e0.elapsed_time(e1) / reps
     tf = 2.0 * n * ho * wo * co * ci * k * k / ms / 1e9
     print(f'{tag} {n}x{h}x{w} {ci}->{co} k{k}s{st}: {ms * 1e3:8.1f} us  {tf:7.1f} TF/s  relerr {err:.2e}', flush=True)
+
+# weight gradients (LDB200_NO_WGRAD2=1 selects the 1-CTA kernel)
+wtag = 'wgrad1' if os.environ.get('LDB200_NO_WGRAD2') else 'wgrad2'
+for n, h, w, ci, co, k, st, pad in SHAPES[:1] + SHAPES[2:3] + SHAPES[1:2] + SHAPES[4:5]:
+    ho, wo = (h + 2 * pad - k) // st + 1, (w + 2 * pad - k) // st + 1
+    x = torch.randn(n, h, w, ci, device='cuda').bfloat16()
+    dy = torch.randn(n, ho, wo, co, device='cuda').bfloat16()
+    dw = torch.zeros(co, k * k * ci, device='cuda')
+    for _ in range(3):
+        ops.conv2d_wgrad_tc(dy, x, dw, k, k, st, pad)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        ops.conv2d_wgrad_tc(dy, x, dw, k, k, st, pad)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    tf = 2.0 * n * ho * wo * co * ci * k * k / ms / 1e9
+    print(f'{wtag} {n}x{h}x{w} {ci}->{co} k{k}s{st}: {ms * 1e3:8.1f} us  {tf:7.1f} TF/s', flush=True)
