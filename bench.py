@@ -11,7 +11,9 @@ teacher forward, target assignment, fused loss, gradient all-reduce, SGD.
 
 One JSON line on rank 0.  `value` = whole-job images/s with inputs resident in HBM, `e2e` = the same step
 through the public API with the batch copied from pinned host memory and the loss read back every step.
-The global batch is fixed at 16 (configs/ld: 8 GPUs x samples_per_gpu=2), so scaling is "strong".
+Scaling: every GPU runs the metric's bs=16 batch (weak scaling, global batch 16 x N, lr scaled linearly as the
+reference's configs prescribe) -- one gradient all-reduce per step is the only exchange.  `--global-batch 16` pins the
+reference's own 8 x 2 global batch instead (strong scaling: 16/N images per GPU).
 """
 import argparse
 import json
@@ -123,13 +125,16 @@ def main():
     ap.add_argument('--student', default='r50')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
+    ap.add_argument('--global-batch', type=int, default=0,
+                    help='fix the global batch (strong scaling); default: 16 images per GPU (weak scaling)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     config = dict(workload='GFocal-R50 student + GFocal-R101 teacher LD train step, 16 x 800x1344 synthetic '
                            'COCO-shaped (configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py model section)',
-                  global_batch=GLOBAL_BATCH, image=[H, W], parallelism=f'dp{args.gpus}',
+                  global_batch=args.global_batch or GLOBAL_BATCH * args.gpus, per_gpu_batch=(args.global_batch or GLOBAL_BATCH * args.gpus) // args.gpus,
+                  image=[H, W], parallelism=f'dp{args.gpus}',
                   launch='CUDA graph replay' if not args.no_graph else 'eager',
                   timing='inputs (51.6 MB images + activations >> 126 MB L2) exceed L2; no explicit flush')
 
@@ -143,7 +148,8 @@ def main():
         print(json.dumps(dict(
             metric='images/sec GFocal-R50 student + R101 teacher LD train step, 1333x800 bs=16', impl='reference',
             value=v, unit='images/s', n_gpus=args.gpus, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1),
-            ms_per_step=sec * 1e3 * GLOBAL_BATCH / n_imgs, higher_is_better=True, scaling='strong', vs_baseline=None,
+            ms_per_step=sec * 1e3 * (args.global_batch or GLOBAL_BATCH * args.gpus) / n_imgs, higher_is_better=True,
+            scaling='strong' if args.global_batch else 'weak', vs_baseline=None,
             dtype='f32', data='synthetic', config=config,
             cpu_baseline=dict(value=v, unit='images/s', cores=cores, kind='port',
                               sample=f'{n_imgs} images of 800x1344 per step (of the 16-image batch), fp32, torch CPU'),
@@ -161,14 +167,16 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     L.check(L.load().ldb200_check_device(), 'check_device')
-    assert GLOBAL_BATCH % world == 0
-    n = GLOBAL_BATCH // world
+    global_batch = args.global_batch or GLOBAL_BATCH * world
+    scaling = 'strong' if args.global_batch else 'weak'
+    assert global_batch % world == 0
+    n = global_batch // world
 
     model = ld_b200.build_detector(ConfigDict(presets.ld_model(args.student)))
     synth.seeded_init(model, 0)
     synth.seeded_init(model.teacher_model, 1, prefix='teacher.')
     model = model.to(dev).train()
-    step = ld_b200.LDTrainStep(model, lr=0.01 * GLOBAL_BATCH / 16)
+    step = ld_b200.LDTrainStep(model, lr=0.01 * global_batch / 16)   # linear scaling rule of the reference configs
     batch = synth.make_batch(n, H, W, seed=1000 + rank)
     img_pinned = batch['img'].pin_memory()
     gtb_pinned = [b.pin_memory() for b in batch['gt_bboxes']]
@@ -239,7 +247,7 @@ def main():
     ms_e2e = timed(run_e2e, args.steps)
     assert torch.isfinite(host_loss).all(), 'loss diverged'
 
-    # dominant kernel, timed live: conv_tc_kernel<256> on the head-tower shape (P3 level, 3x3 256->256), the
+    # dominant kernel, timed live: conv2_tc_kernel on the head-tower shape (P3 level, 3x3 256->256), the
     # single largest-FLOP launch of the step (32 forward + 16 dgrad launches of this shape per step)
     from ld_b200 import ops as _ops
     kx = torch.randn(n, 100, 168, 256, device=dev).bfloat16()
@@ -259,27 +267,27 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        ips = GLOBAL_BATCH * args.steps / (ms / 1e3)
-        ips_e2e = GLOBAL_BATCH * args.steps / (ms_e2e / 1e3)
+        ips = global_batch * args.steps / (ms / 1e3)
+        ips_e2e = global_batch * args.steps / (ms_e2e / 1e3)
         peak_tf = pk.get('bf16_tflops_sustained', 1400.0)
         ach = ips * FLOP_PER_IMAGE / 1e12 / world
         out = dict(metric='images/sec GFocal-R50 student + R101 teacher LD train step, 1333x800 bs=16',
                    value=ips, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-                   ms_per_step=ms / args.steps, higher_is_better=True, scaling='strong', vs_baseline=None,
+                   ms_per_step=ms / args.steps, higher_is_better=True, scaling=scaling, vs_baseline=None,
                    dtype='bf16', data='synthetic', config=config,
                    e2e=dict(value=ips_e2e, unit='images/s',
                             h2d_bytes_per_step=int(img_pinned.numel() * 4 + sum(b.numel() * 4 for b in gtb_pinned)
                                                    + sum(b.numel() * 8 for b in gtl_pinned)) * world,
                             d2h_bytes_per_step=4 * world),
                    gpu_launches=int(launches),
-                   roofline=dict(bound='tensor', kernel='conv_tc_kernel<256> head tower P3 3x3 256->256',
+                   roofline=dict(bound='tensor', kernel='conv2_tc_kernel (2-CTA tcgen05, 256x256 pair tile) head tower P3 3x3 256->256',
                                  achieved=k_flop / k_ms / 1e9, peak=pk.get('bf16_tflops', 1590.0), unit='TFLOP/s',
                                  frac=k_flop / k_ms / 1e9 / pk.get('bf16_tflops', 1590.0),
-                                 traffic=230.1e6 * n / 16,
+                                 traffic=230.7e6 * n / 16,
                                  note='algorithmic 2*N*H*W*Cin*Cout*9 FLOP per launch / live CUDA-event duration (20 '
                                       'back-to-back launches), of ' + ('measured' if 'bf16_tflops' in pk else 'fallback')
                                       + ' burst bf16 peak; traffic = dram read+write of the same launch from '
-                                        'profiles/r01_conv_head_p3_summary.txt (ncu --set full, batch 16)'),
+                                        'profiles/r01_conv2_head_p3_summary.txt (ncu --set full, batch 16)'),
                    roofline_step=dict(bound='tensor', achieved=ach, peak=peak_tf, unit='TFLOP/s', frac=ach / peak_tf,
                                       note='conv MACs of the whole step (1.8356 TFLOP/image) / step time per GPU, of '
                                            + ('measured' if 'bf16_tflops_sustained' in pk else 'fallback')

@@ -26,7 +26,7 @@
 
 namespace ldb {
 
-constexpr int CONV_THREADS = 256;       // wgrad kernel
+constexpr int CONV_THREADS = 384;       // wgrad kernels: 4 control warps + 8 epilogue warps
 constexpr int CONV_FWD_MAX_THREADS = 640;   // 4 control warps + up to 16 epilogue warps
 constexpr int TILE_M = 128;
 constexpr int KCH = 64;                        // channels per k-block (128 B of bf16)
@@ -851,7 +851,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbarrier_init(&empty[s], 1);
     }
     mbarrier_init(tfull, 1);
-    mbarrier_init(tempty, 4);
+    mbarrier_init(tempty, 8);   // one arrive per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -926,7 +926,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp >= 4) {
     pdl_wait();
-    const int ew = warp - 4;
+    // 8 warps: lane quadrant ew (TMEM lanes 32*ew..+31 = output channels), column half `half` of the accumulator
+    const int ew = warp & 3, half = (warp - 4) >> 2;
     int it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
       const int split = u % p.splits;
@@ -941,7 +942,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
       if (pt1 > pt0) {
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = half * (BN / 64); ch < (half + 1) * (BN / 64); ++ch) {
           const int cbase = ci_t * BN + ch * 32;
           if (cbase >= p.Cin) break;
           uint32_t r[32];
@@ -1026,7 +1027,7 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbarrier_init(&empty[s], 1);
     }
     mbarrier_init(tfull, 1);
-    mbarrier_init(tempty, 2 * 4);   // epilogue warps of both CTAs arrive on the leader's copy
+    mbarrier_init(tempty, 2 * 8);   // epilogue warps of both CTAs arrive on the leader's copy
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -1104,7 +1105,8 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     pdl_wait();
-    const int ew = warp - 4;
+    // 8 warps: lane quadrant ew (TMEM lanes 32*ew..+31 = output channels), column half `half` of the accumulator
+    const int ew = warp & 3, half = (warp - 4) >> 2;
     int it = 0;
     for (int u = blockIdx.x >> 1; u < units; u += gridDim.x >> 1, ++it) {
       const int split = u % p.splits;
@@ -1119,7 +1121,7 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       if (pt1 > pt0) {
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = half * (BN / 64); ch < (half + 1) * (BN / 64); ++ch) {
           const int cbase = ci_t * BN + ch * 32;
           if (cbase >= p.Cin) break;
           uint32_t r[32];
