@@ -250,6 +250,7 @@ def main():
     # dominant kernel, timed live: conv2_tc_kernel on the head-tower shape (P3 level, 3x3 256->256), the
     # single largest-FLOP launch of the step (32 forward + 16 dgrad launches of this shape per step)
     from ld_b200 import ops as _ops
+    time.sleep(2.0)   # 'timed alone': let the power-capped clocks recover from the step loop before the burst measurement
     kx = torch.randn(n, 100, 168, 256, device=dev).bfloat16()
     kw = _ops.pack_conv_weight(torch.randn(256, 256, 3, 3, device=dev) * 0.02)
     ko = torch.empty(n, 100, 168, 256, device=dev, dtype=torch.bfloat16)
