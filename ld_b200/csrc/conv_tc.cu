@@ -65,6 +65,7 @@ struct ConvParams {
   int accumulate;           // result += previous out (before ReLU / mask)
   int vec_ok;               // leading dimensions allow 16-byte vector accesses
   int tma_epi;              // epilogue stages 32-pixel x 64-channel boxes in shared memory and TMA-stores them
+  int nt_inner;             // 1-CTA kernel: a CTA walks all output-channel tiles of one pixel tile back to back
 };
 
 struct ConvMaps {           // per-segment TMA descriptors: A operand, residual prefetch, mask prefetch,
@@ -200,6 +201,35 @@ __device__ __forceinline__ size_t out_offset(const ConvSeg& p, int n, int y, int
   return (((size_t)n * p.OH + (size_t)(y * p.oys + p.oyo)) * p.OW + (size_t)(x * p.oxs + p.oxo));
 }
 
+// Tile schedule of the 1-CTA kernel: the i-th work item of CTA `b`.  nt_inner: the CTA takes pixel tile
+// b + (i / tiles_n) * grid and walks its tiles_n output-channel tiles consecutively, so the A operand of the later ones
+// comes out of L2 a few microseconds after the first read (with the channel tile fastest ACROSS CTAs, the CTAs sharing a
+// pixel tile drift apart and big maps re-read A from HBM: 975 MB instead of 688 MB on the layer-1 expand conv).
+struct TileCoord { int sg, nt, tx, ty, n; };
+__device__ __forceinline__ bool decode_tile(const ConvParams& p, int b, int grid, int i, TileCoord& c) {
+  int mt;
+  if (p.nt_inner) {
+    const int r = i / p.tiles_n;
+    mt = b + r * grid;
+    c.nt = i - r * p.tiles_n;
+  } else {
+    const int t = b + i * grid;
+    mt = t / p.tiles_n;
+    c.nt = t - mt * p.tiles_n;
+  }
+  if (mt >= p.seg_tile0[p.nseg] / p.tiles_n) return false;
+  int sg = 0;
+  while (sg + 1 < p.nseg && mt >= p.seg_tile0[sg + 1] / p.tiles_n) ++sg;
+  const ConvSeg& S = p.seg[sg];
+  int sp = mt - p.seg_tile0[sg] / p.tiles_n;
+  c.sg = sg;
+  c.tx = sp % S.tiles_x;
+  sp /= S.tiles_x;
+  c.ty = sp % S.tiles_y;
+  c.n = sp / S.tiles_y;
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Epilogue of ONE output tile for one epilogue warp (shared by the 1-CTA and 2-CTA kernels): warp (ew, half) owns
 // TMEM lanes [32*ew, +32) = 32 tile rows and the tile's columns [half*GCOLS, +GCOLS).  Per 32-column chunk:
@@ -241,6 +271,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
     __syncwarp();
     if (S.tl_mask) {
       if (lane == 0) {
+        if (S.tl_add) tma_prefetch_4d(&maps.rl[sg], colb, bx, by, n);   // residual box follows: start its fetch now
         mbarrier_expect_tx(rbar, EPI_BOX_BYTES);
         tma_load_4d(ebuf, &maps.ml[sg], rbar, colb, bx, by, n);
       }
@@ -450,7 +481,6 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cchunks = p.Cin / KCH;
   const int kblocks = p.ntaps * cchunks;
-  const int total_tiles = p.seg_tile0[p.nseg];
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -485,17 +515,10 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
       pdl_wait();   // inputs are produced by the previous kernel
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int sg = 0;
-        while (sg + 1 < p.nseg && t >= p.seg_tile0[sg + 1]) ++sg;
+      TileCoord tc;
+      for (int i = 0; decode_tile(p, blockIdx.x, gridDim.x, i, tc); ++i) {
+        const int sg = tc.sg, nt = tc.nt, tx = tc.tx, ty = tc.ty, n = tc.n;
         const ConvSeg& S = p.seg[sg];
-        const int tl = t - p.seg_tile0[sg];
-        const int nt = tl % p.tiles_n;
-        int sp = tl / p.tiles_n;
-        const int tx = sp % S.tiles_x;
-        sp /= S.tiles_x;
-        const int ty = sp % S.tiles_y;
-        const int n = sp / S.tiles_y;
         const int x0 = tx * S.TW * p.sx, y0 = ty * S.TH * p.sy;
         // the epilogue will read this tile's residual / ReLU-mask rows a whole main loop from now: pull them into
         // L2 with one TMA prefetch each so those loads see L2 latency instead of HBM latency
@@ -518,7 +541,8 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      TileCoord tc;
+      for (; decode_tile(p, blockIdx.x, gridDim.x, it, tc); ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbarrier_wait(&tempty[acc], acc_phase ^ 1);
@@ -552,19 +576,12 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
     uint64_t* rbar = rbars + (warp - 4);
     uint32_t rph = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    TileCoord tc;
+    for (; decode_tile(p, blockIdx.x, gridDim.x, it, tc); ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      int sg = 0;
-      while (sg + 1 < p.nseg && t >= p.seg_tile0[sg + 1]) ++sg;
+      const int sg = tc.sg, nt = tc.nt, tx = tc.tx, ty = tc.ty, n = tc.n;
       const ConvSeg& S = p.seg[sg];
-      const int tl = t - p.seg_tile0[sg];
-      const int nt = tl % p.tiles_n;
-      int sp = tl / p.tiles_n;
-      const int tx = sp % S.tiles_x;
-      sp /= S.tiles_x;
-      const int ty = sp % S.tiles_y;
-      const int n = sp / S.tiles_y;
       epilogue_tile<BN, SHORTK, Cfg::EPI_GROUPS>(p, maps, S, sg, nt, tx, ty, n, true, tmem_base + (uint32_t)(acc * BN),
                                                  &tfull[acc], acc_phase, ew, half, lane, ebuf, rbar, rph);
       if (lane == 0) mbarrier_arrive(&tempty[acc]);
@@ -1226,8 +1243,13 @@ static int launch_conv(const ConvMaps& maps, const CUtensorMap& tmB, const ConvP
   }
   const int total = p.seg_tile0[p.nseg];
   const int slots = g_conv_sms * Cfg::MIN_BLOCKS;
+  ConvParams q = p;
+  // enough pixel tiles to fill the GPU: keep a pixel tile's output-channel tiles on one CTA (A re-read from L2)
+  // (opt-in, LDB200_NT_INNER=1: measured neutral-to-slower on the LD shapes, DRAM reads unchanged)
+  static const bool nt_inner_env = getenv("LDB200_NT_INNER") != nullptr;
+  q.nt_inner = (nt_inner_env && p.tiles_n > 1 && total / p.tiles_n >= slots) ? 1 : 0;
   const int grid = total < slots ? total : slots;
-  LDB_CUDA(launch_pdl(conv_tc_kernel<BN, SHORTK>, grid, Cfg::THREADS, Cfg::SMEM, stream, maps, tmB, p));
+  LDB_CUDA(launch_pdl(conv_tc_kernel<BN, SHORTK>, grid, Cfg::THREADS, Cfg::SMEM, stream, maps, tmB, q));
   return 0;
 }
 
@@ -1320,10 +1342,11 @@ static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& commo
     cuuint32_t es[4] = {1, 1, 1, 1};
     return encode_map(m, base, 4, dims, strides, box, es, what, CU_TENSOR_MAP_SWIZZLE_NONE);
   };
-  if (g->add_src && ident && g->add_H == g->OH && g->add_W == g->OW && common.add_ld % 8 == 0 && !d->out_f32) {
+  static const bool l2_prefetch = getenv("LDB200_NO_L2_PREFETCH") == nullptr;
+  if (l2_prefetch && g->add_src && ident && g->add_H == g->OH && g->add_W == g->OW && common.add_ld % 8 == 0 && !d->out_f32) {
     if (aux_map(tmR, g->add_src, common.add_ld, "residual prefetch") == 0) g->pf_add = 1;
   }
-  if (g->mask_src && ident && common.mask_ld % 8 == 0) {
+  if (l2_prefetch && g->mask_src && ident && common.mask_ld % 8 == 0) {
     if (aux_map(tmM, g->mask_src, common.mask_ld, "mask prefetch") == 0) g->pf_mask = 1;
   }
   // TMA epilogue: one box = the 32 pixels of an epilogue warp (32 x 1 of a wide tile, TW x 32/TW of a narrow one)
@@ -1350,6 +1373,10 @@ static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& commo
       if (e) return e;
       g->tl_mask = 1;
     }
+    // the staging-box loads are issued before the accumulator wait already; an additional producer-side L2 prefetch
+    // of the same tile only duplicated the DRAM reads (ncu, layer-1 expand conv: 975 MB read vs 688 MB without)
+    if (g->tl_add) g->pf_add = 0;
+    if (g->tl_mask) g->pf_mask = 0;
   }
   return 0;
 }
