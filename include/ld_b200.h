@@ -137,6 +137,22 @@ int ldb200_ld_loss_fused(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const 
                          float* losses, void* d_cls, void* d_reg, void* d_im, int d_cls_ld, int d_reg_ld,
                          int grad_dtype, void* stream);
 
+/* General-Instance imitation region.  Replaces LDHead.get_gi_region (ld_head.py:613-638), the row selection of
+ * imitation_method='gibox' (ld_head.py:170-176; the LDHead constructor default): per level, over all N*A_l
+ * locations, GI score = max_c |sigmoid(t_cls) - sigmoid(cls)|, GI box = teacher's decoded box where the teacher
+ * scores higher at that class else the student's (Integral + distance2bbox, grid units), then the first `topk`
+ * keeps of torchvision.ops.nms(boxes, scores, iou_thr) (reference: 0.3, 10).
+ *   cls, t_cls [R,C] f32 ; reg, t_reg [R,4*(reg_max+1)] f32 (row space)
+ *   counts_in  the counts vector of ldb200_ld_targets
+ *   gi_rows    i32[num_levels*topk]: picked rows, levels back to back in pick order (first counts_out[1] valid)
+ *   counts_out counts_in with [1] = number of picked rows and the per-level "fg" entries = picks per level: pass
+ *              (gi_rows, counts_out) to ldb200_ld_loss_fused / ldb200_scatter_add_rows as (fg_rows, counts)
+ *   workspace  ldb200_gi_region_workspace_bytes() bytes, 16-byte aligned */
+size_t ldb200_gi_region_workspace_bytes(const ldb_pyramid* pyr, int topk);
+int ldb200_gi_region(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const float* cls, const float* reg,
+                     const float* t_cls, const float* t_reg, float iou_thr, int topk, const int32_t* counts_in,
+                     int32_t* gi_rows, int32_t* counts_out, void* workspace, void* stream);
+
 /* dst[rows[i], :] += src[i, :]  (rows unique).  Adds the compact IM gradient into the dense
  * gradient of the student FPN map. */
 int ldb200_scatter_add_rows(void* dst, const void* src, const int32_t* rows, const int32_t* n_rows_dev,

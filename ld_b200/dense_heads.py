@@ -7,6 +7,7 @@ The per-level Python loops of the reference (`multi_apply(forward_single)`, `mul
 ONE target-generation call for the whole batch, ONE pre-pass and ONE fused loss launch for all five
 levels (row space).
 """
+import dataclasses
 import math
 import os
 
@@ -193,7 +194,9 @@ class GFLHead(nn.Module):
         return ops.from_rows(cls_rows, pyr), ops.from_rows(reg_rows, pyr)
 
 
-IM_MODES = {'finegrained': L.IM_FINEGRAINED, 'fitnet': L.IM_CENTER, 'decouple': L.IM_CENTER}
+# region mask produced by the target pass; 'gibox' rows come from `ops.gi_region` at loss time instead (the mask
+# of the target pass is then unused)
+IM_MODES = {'finegrained': L.IM_FINEGRAINED, 'fitnet': L.IM_CENTER, 'gibox': L.IM_FINEGRAINED}
 
 
 class _LDLossFn(torch.autograd.Function):
@@ -223,9 +226,18 @@ class _LDLossFn(torch.autograd.Function):
         wsum, _ = ops.ld_loss_prepass(cfg, cls_rows, reg_rows, tg)
         norm = ops.loss_normalisers(tg, wsum)
         dcls_ld, dreg_ld = (C + 7) // 8 * 8, (NB + 7) // 8 * 8
+        tg_im, max_fg = tg, aux.get('max_fg')
+        if head.imitation_method == 'gibox' and aux['im_active']:
+            # ld_head.py:170-176: imitate on the General-Instance rows (GI-box NMS picks, 10 per level) instead of a
+            # target-derived region; they depend on this iteration's student and teacher head outputs
+            gi_rows, gi_counts = ops.gi_region(cfg, cls_rows, reg_rows, aux['t_cls_rows'], aux['t_reg_rows'], tg,
+                                               iou_thr=head.gi_iou_thr, topk=head.gi_topk)
+            tg_im = dataclasses.replace(tg, fg_rows=gi_rows, counts=gi_counts)
+            max_fg = gi_rows.numel()
+        aux['targets_im'] = tg_im
         losses, d_cls, d_reg, d_im = ops.ld_loss_fused(
-            cfg, cls_rows, reg_rows, aux['t_cls_rows'], aux['t_reg_rows'], x_rows, aux['t_x_rows'], tg, norm,
-            term_grad=aux['term_grad'], grad_dtype=torch.bfloat16, max_fg=aux.get('max_fg'),
+            cfg, cls_rows, reg_rows, aux['t_cls_rows'], aux['t_reg_rows'], x_rows, aux['t_x_rows'], tg_im, norm,
+            term_grad=aux['term_grad'], grad_dtype=torch.bfloat16, max_fg=max_fg,
             d_cls_ld=dcls_ld, d_reg_ld=dreg_ld)
         ctx.head, ctx.aux = head, aux
         ctx.save_for_backward(*tensors, cls_rows, reg_rows, d_cls, d_reg, d_im)
@@ -258,7 +270,8 @@ class _LDLossFn(torch.autograd.Function):
         x_dense = None
         if aux['im_active']:
             x_dense = torch.zeros(tg.pyr.rows, xs[0].shape[-1], dtype=torch.bfloat16, device=dev)
-            ops.scatter_add_rows(x_dense, d_im, tg.fg_rows, tg.counts[1:2])
+            tg_im = aux['targets_im']
+            ops.scatter_add_rows(x_dense, d_im, tg_im.fg_rows, tg_im.counts[1:2])
         for l in range(nl):
             n, h, w, _ = cls_feats[l].shape
             cnt = n * h * w
@@ -299,6 +312,7 @@ class LDHead(GFLHead):
                  loss_im=dict(type='IMLoss', loss_weight=0), imitation_method='gibox', **kwargs):
         super().__init__(num_classes, in_channels, **kwargs)
         self.imitation_method = imitation_method
+        self.gi_iou_thr, self.gi_topk = 0.3, 10    # ld_head.py:637 (hard-coded in the reference)
         self.loss_im = build_loss(loss_im)
         self.loss_ld = build_loss(loss_ld)
         self.loss_ld_vlr = build_loss(loss_ld_vlr)
@@ -328,8 +342,10 @@ class LDHead(GFLHead):
         if static and self._static_targets is not None and gt_bboxes is None:
             return self._static_targets
         if self.imitation_method not in IM_MODES:
-            raise NotImplementedError(f"imitation_method='{self.imitation_method}' (GI boxes + NMS, ld_head.py:613-638) "
-                                      f"is not implemented; use 'finegrained' (configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py:47)")
+            # 'decouple' (ld_head.py:177-185) pairs x[non-region rows] with teacher_x[region rows] in one mse_loss:
+            # the reference itself fails on the shape mismatch unless the two row counts happen to coincide
+            raise NotImplementedError(f"imitation_method='{self.imitation_method}' is not one of {sorted(IM_MODES)} "
+                                      f"(ld_head.py:170-191)")
         if getattr(self.train_cfg, 'allowed_border', -1) >= 0:
             raise NotImplementedError('allowed_border >= 0 (LD configs use -1)')
         pyr = L.Pyramid.make(len(img_metas), featmap_sizes, [s[0] for s in self.anchor_generator.strides])
@@ -392,10 +408,16 @@ class _LossOnlyFn(torch.autograd.Function):
             xr, txr = xr.float(), txr.float()
         wsum, _ = ops.ld_loss_prepass(cfg, rows[0], rows[1], tg)
         norm = ops.loss_normalisers(tg, wsum)
-        losses, d_cls, d_reg, d_im = ops.ld_loss_fused(cfg, rows[0], rows[1], rows[2], rows[3], xr, txr, tg, norm,
-                                                       term_grad=True, grad_dtype=torch.float32)
+        tg_im, max_fg = tg, None
+        if head.imitation_method == 'gibox' and head.loss_im.loss_weight != 0:   # ld_head.py:170-176
+            gi_rows, gi_counts = ops.gi_region(cfg, rows[0], rows[1], rows[2], rows[3], tg, iou_thr=head.gi_iou_thr,
+                                               topk=head.gi_topk)
+            tg_im, max_fg = dataclasses.replace(tg, fg_rows=gi_rows, counts=gi_counts), gi_rows.numel()
+        head._last_im_targets = tg_im    # (rows, counts) the imitation term used: inspected by the parity tests
+        losses, d_cls, d_reg, d_im = ops.ld_loss_fused(cfg, rows[0], rows[1], rows[2], rows[3], xr, txr, tg_im, norm,
+                                                       term_grad=True, grad_dtype=torch.float32, max_fg=max_fg)
         d_x = torch.zeros(tg.pyr.rows, xr.shape[1], dtype=torch.float32, device=xr.device)
-        ops.scatter_add_rows(d_x, d_im, tg.fg_rows, tg.counts[1:2])
+        ops.scatter_add_rows(d_x, d_im, tg_im.fg_rows, tg_im.counts[1:2])
         ctx.pyr, ctx.nl = tg.pyr, nl
         ctx.save_for_backward(d_cls, d_reg, d_x)
         return losses

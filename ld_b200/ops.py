@@ -158,6 +158,23 @@ def ld_loss_fused(cfg: L.LossCfg, cls, reg, t_cls, t_reg, x, t_x, tg: LDTargets,
     return losses, d_cls, d_reg, d_im
 
 
+def gi_region(cfg: L.LossCfg, cls, reg, t_cls, t_reg, tg: LDTargets, iou_thr=0.3, topk=10):
+    """`LDHead.get_gi_region` for all levels (ldb200_gi_region): -> (gi_rows i32 [L*topk], counts i32) to be used
+    as (fg_rows, counts) of the fused loss when imitation_method='gibox'."""
+    lib = L.load()
+    dev = cls.device
+    nl = tg.pyr.num_levels
+    ws = torch.empty(int(lib.ldb200_gi_region_workspace_bytes(C.byref(tg.pyr), int(topk))), dtype=torch.uint8, device=dev)
+    gi_rows = torch.empty(nl * topk, dtype=torch.int32, device=dev)
+    counts = torch.empty_like(tg.counts)
+    for t in (cls, reg, t_cls, t_reg):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    L.check(lib.ldb200_gi_region(C.byref(tg.pyr), C.byref(cfg), L.ptr(cls), L.ptr(reg), L.ptr(t_cls), L.ptr(t_reg),
+                                 float(iou_thr), int(topk), L.ptr(tg.counts), L.ptr(gi_rows), L.ptr(counts), L.ptr(ws),
+                                 L.stream_ptr()), 'ldb200_gi_region')
+    return gi_rows, counts
+
+
 def scatter_add_rows(dst, src, rows, n_rows_dev, max_rows=None):
     lib = L.load()
     max_rows = src.shape[0] if max_rows is None else max_rows

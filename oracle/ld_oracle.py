@@ -245,12 +245,64 @@ def integral(reg, reg_max=16):
     return F.linear(p, proj).reshape(-1, 4)
 
 
+def nms_topk(boxes, scores, iou_thr, k):
+    """The first `k` indices `torchvision.ops.nms(boxes, scores, iou_thr)` keeps (ld_head.py:637
+    `torch.ops.torchvision.nms(gibox, giscore, 0.3)[:10]`).  torchvision 0.x CPU kernel
+    (torchvision/csrc/ops/cpu/nms_kernel.cpp, not vendored in /root/reference): candidates in
+    stable descending score order; a kept box i suppresses every later j with
+    inter / (area_i + area_j - inter) > iou_thr, areas = (x2-x1)*(y2-y1), inter from clamped
+    widths/heights, all in the dtype of `boxes`."""
+    order = torch.sort(scores, descending=True, stable=True)[1]
+    x1, y1, x2, y2 = boxes.unbind(1)
+    areas = (x2 - x1) * (y2 - y1)
+    suppressed = torch.zeros(boxes.shape[0], dtype=torch.bool)
+    keep = []
+    pos = 0
+    n = boxes.shape[0]
+    while len(keep) < k and pos < n:
+        # next unsuppressed candidate in score order
+        rest = order[pos:]
+        alive = (~suppressed[rest]).nonzero()
+        if alive.numel() == 0:
+            break
+        pos += int(alive[0])
+        i = int(order[pos])
+        pos += 1
+        keep.append(i)
+        w = (torch.minimum(x2[i], x2) - torch.maximum(x1[i], x1)).clamp(min=0)
+        h = (torch.minimum(y2[i], y2) - torch.maximum(y1[i], y1)).clamp(min=0)
+        inter = w * h
+        ovr = inter / (areas[i] + areas - inter)
+        suppressed |= ovr > iou_thr
+        suppressed[i] = True
+    return torch.tensor(keep, dtype=torch.long)
+
+
+def gi_region(t_cls, cls, anchors, reg, t_reg, stride, reg_max=16, iou_thr=0.3, k=10):
+    """`LDHead.get_gi_region` (ld_head.py:613-638): General-Instance boxes of one level.  Per location the GI
+    score is max_c |sigmoid(teacher) - sigmoid(student)|, the GI box the teacher's decoded box where the teacher
+    scores higher at that class, else the student's; NMS (IoU 0.3) over ALL locations of the level (the images of
+    the batch share one coordinate frame here, as in the reference) and the first 10 keeps are returned."""
+    ts, ss = t_cls.detach().sigmoid(), cls.detach().sigmoid()
+    ctr = torch.stack([(anchors[:, 0] + anchors[:, 2]) / 2, (anchors[:, 1] + anchors[:, 3]) / 2], 1) / stride
+    sd, td = integral(reg.detach(), reg_max), integral(t_reg.detach(), reg_max)
+
+    def d2b(d):   # distance2bbox (core/bbox/transforms.py:119-156), no max_shape
+        return torch.stack([ctr[:, 0] - d[:, 0], ctr[:, 1] - d[:, 1], ctr[:, 0] + d[:, 2], ctr[:, 1] + d[:, 3]], 1)
+
+    z = ts - ss
+    giscore, index = z.abs().max(1)
+    teacher_bigger = z.gather(1, index[:, None]).squeeze(1) >= 0
+    gibox = torch.where(teacher_bigger[:, None], d2b(td), d2b(sd))
+    return nms_topk(gibox, giscore, iou_thr, k)
+
+
 DEFAULT_LOSS_CFG = dict(w_qfl=1.0, beta=2.0, w_giou=2.0, w_dfl=0.25, w_ld=0.25, T_ld=10.0,
                         w_ld_vlr=0.25, T_ld_vlr=10.0, w_kd=10.0, T_kd=2.0, w_im=2.0, reg_max=16)
 
 
 def ld_loss_level(anchors, cls, reg, labels, label_w, bbox_t, stride, t_reg, t_cls, x, t_x,
-                  vlr, im, num_total_samples, cfg=DEFAULT_LOSS_CFG):
+                  vlr, im, num_total_samples, cfg=DEFAULT_LOSS_CFG, imitation='finegrained', gi_out=None):
     """`LDHead.loss_single` (ld_head.py:116-282) on flattened NHWC rows.
 
     anchors [R,4]; cls [R,C]; reg/t_reg [R,4*(reg_max+1)]; t_cls [R,C]; x,t_x [R,F].
@@ -262,6 +314,10 @@ def ld_loss_level(anchors, cls, reg, labels, label_w, bbox_t, stride, t_reg, t_c
     fg = (im > 0).nonzero().squeeze(1)
     zero = reg.sum() * 0
     score = label_w.new_zeros(labels.shape)
+    if imitation == 'gibox':   # ld_head.py:170-176
+        fg = gi_region(t_cls, cls, anchors, reg, t_reg, stride, rm)
+        if gi_out is not None:
+            gi_out.append(fg)
     loss_im = cfg['w_im'] * F.mse_loss(x[fg], t_x[fg]) if fg.numel() else zero
     if pos.numel():
         a = anchors[pos]
@@ -310,7 +366,7 @@ def nhwc_rows(t):
 
 
 def ld_loss(cls_scores, bbox_preds, t_cls_scores, t_bbox_preds, feats, t_feats, targets,
-            strides, cfg=DEFAULT_LOSS_CFG, world_size=1):
+            strides, cfg=DEFAULT_LOSS_CFG, world_size=1, imitation='finegrained', gi_out=None):
     """`LDHead.loss` (ld_head.py:284-375) given NCHW per-level tensors and `ld_targets` output.
     Single process: reduce_mean is the identity."""
     nts = max(float(targets["num_total_pos"]), 1.0)
@@ -326,7 +382,7 @@ def ld_loss(cls_scores, bbox_preds, t_cls_scores, t_bbox_preds, feats, t_feats, 
                              nhwc_rows(t_bbox_preds[l]), nhwc_rows(t_cls_scores[l]),
                              nhwc_rows(feats[l]), nhwc_rows(t_feats[l]),
                              targets['vlr'][l].reshape(-1), targets['im'][l].reshape(-1),
-                             nts, cfg)
+                             nts, cfg, imitation, gi_out)
         per.append(d)
         wsum = wsum + w
     avg = float(wsum + 1e-6)

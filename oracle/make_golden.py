@@ -77,6 +77,49 @@ def gen_losses(head):
         print(name, {k: [round(float(x), 5) for x in v] for k, v in gold['losses'].items()})
 
 
+def gen_losses_gibox(head):
+    """`imitation_method='gibox'` (the LDHead constructor default, ld_head.py:55): the reference's
+    `get_gi_region` calls `.cuda()` on an index tensor (ld_head.py:628) -- on this CPU-only container
+    `Tensor.cuda` is patched to the identity while the UNMODIFIED reference code runs, and the method is wrapped to
+    record the indices it returns."""
+    import torchvision  # noqa: F401  (registers torch.ops.torchvision.nms, which the reference calls directly)
+    orig_cuda, orig_gi = torch.Tensor.cuda, head.get_gi_region
+    picked = []
+
+    def spy(*a, **k):
+        idx = orig_gi(*a, **k)
+        picked.append(idx.clone())
+        return idx
+
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    head.get_gi_region = spy
+    head.imitation_method = 'gibox'
+    try:
+        for name, n, h, w, seed in cases.LOSS_CASES:
+            d = cases.loss_case_inputs(n, h, w, seed)
+            del picked[:]
+            leaves = {k: [t.clone().requires_grad_(True) for t in d[k]] for k in ('cls', 'reg', 'x')}
+            losses = head.loss(leaves['cls'], leaves['reg'], d['gt_bboxes'], d['gt_labels'],
+                               (d['t_cls'], d['t_reg']), leaves['x'], d['t_x'], d['img_metas'])
+            total = sum(sum(v) for v in losses.values())
+            total.backward()
+            for t in leaves['x']:
+                if t.grad is None:   # level without positives: loss_im is zeroed (ld_head.py:251)
+                    t.grad = torch.zeros_like(t)
+            gold = dict(losses={k: torch.stack([t.detach() for t in v]) for k, v in losses.items()},
+                        total=total.detach(), gi_idx=[p.to(torch.int32) for p in picked],
+                        grad_x_norm=torch.stack([t.grad.norm() for t in leaves['x']]),
+                        grad_x_rowsum=[t.grad.sum(1) for t in leaves['x']],
+                        grad_cls_norm=torch.stack([t.grad.norm() for t in leaves['cls']]),
+                        grad_reg_norm=torch.stack([t.grad.norm() for t in leaves['reg']]))
+            torch.save(gold, os.path.join(OUT, name + '_gibox.pt'))
+            print(name + '_gibox', [round(float(x), 5) for x in gold['losses']['loss_im']],
+                  [p.tolist()[:4] for p in picked])
+    finally:
+        torch.Tensor.cuda, head.get_gi_region = orig_cuda, orig_gi
+        head.imitation_method = 'finegrained'
+
+
 def gen_steps():
     for name, sd, td, n, h, w, seed in cases.STEP_CASES:
         cfg = rh.load_model_cfg()
@@ -116,6 +159,7 @@ def main():
     head = rh.reference_head()
     gen_targets(head)
     gen_losses(head)
+    gen_losses_gibox(head)
     gen_steps()
 
 

@@ -52,6 +52,46 @@ def test_ldhead_loss_api_matches_reference(golden_dir, case):
         assert float((gx.cpu().sum(1) - ref).abs().max()) <= 2e-4 * max(float(ref.abs().max()), 1e-6), l
 
 
+@pytest.mark.parametrize('case', cases.LOSS_CASES, ids=lambda c: c[0] + '_gibox')
+def test_ldhead_loss_gibox_matches_reference(golden_dir, case):
+    """imitation_method='gibox' (the LDHead default; ld_head.py:170-176, 613-638): GI-box NMS picks bit-exact
+    (`ldb200_gi_region`), loss terms and gradients against the unmodified reference."""
+    name, n, h, w, seed = case
+    gold = torch.load(os.path.join(golden_dir, name + '_gibox.pt'), weights_only=False)
+    d = cases.loss_case_inputs(n, h, w, seed)
+    head = make_head()
+    head.imitation_method = 'gibox'
+    dev = torch.device('cuda')
+    leaves = {k: [t.to(dev).requires_grad_(True) for t in d[k]] for k in ('cls', 'reg', 'x')}
+    losses = head.loss(leaves['cls'], leaves['reg'], [b.to(dev) for b in d['gt_bboxes']],
+                       [b.to(dev) for b in d['gt_labels']],
+                       ([t.to(dev) for t in d['t_cls']], [t.to(dev) for t in d['t_reg']]),
+                       leaves['x'], [t.to(dev) for t in d['t_x']], d['img_metas'])
+    sum(sum(v) for v in losses.values()).backward()
+    torch.cuda.synchronize()
+    # picked rows: row space = levels back to back, the reference's indices are level-local
+    tg = head._last_im_targets
+    counts = tg.counts.cpu()
+    rows = tg.fg_rows.cpu()[:int(counts[1])]
+    o = 0
+    for l, want in enumerate(gold['gi_idx']):
+        c = int(counts[4 + 3 * l + 2])
+        assert c == want.numel(), (l, c, want.numel())
+        r0 = sum(tg.pyr.level_anchors[:l]) * n
+        assert torch.equal(rows[o:o + c] - r0, want), (l, rows[o:o + c] - r0, want)
+        o += c
+    for k, v in gold['losses'].items():
+        got = torch.stack([t.detach().cpu() for t in losses[k]])
+        assert torch.allclose(got, v, rtol=1e-4, atol=1e-6), (k, got, v)
+    for l in range(5):
+        gx = leaves['x'][l].grad
+        gx = torch.zeros_like(leaves['x'][l]) if gx is None else gx
+        ref = gold['grad_x_rowsum'][l]
+        assert float((gx.cpu().sum(1) - ref).abs().max()) <= 2e-4 * max(float(ref.abs().max()), 1e-6), l
+        for key, gk in (('cls', 'grad_cls_norm'), ('reg', 'grad_reg_norm')):
+            assert abs(float(leaves[key][l].grad.norm()) - float(gold[gk][l])) <= 1e-4 * float(gold[gk][l]) + 1e-9
+
+
 def test_kd_kl_module_standalone():
     import ld_b200
     g = torch.Generator().manual_seed(0)

@@ -55,6 +55,33 @@ def test_loss_and_grads(golden_dir, case):
         assert torch.allclose(gx.sum(1), gold['grad_x_rowsum'][l], rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize('case', cases.LOSS_CASES, ids=lambda c: c[0] + '_gibox')
+def test_loss_gibox(golden_dir, case):
+    """imitation_method='gibox' (LDHead default, ld_head.py:170-176, 613-638): the GI-box NMS picks (indices,
+    bit-exact) and the resulting loss_im / feature gradients against the unmodified reference."""
+    name, n, h, w, seed = case
+    gold = _load(golden_dir, name + '_gibox')
+    d = cases.loss_case_inputs(n, h, w, seed)
+    leaves = {k: [t.clone().requires_grad_(True) for t in d[k]] for k in ('cls', 'reg', 'x')}
+    tg = lo.ld_targets(d['sizes'], cases.STRIDES, d['img_metas'], d['gt_bboxes'], d['gt_labels'])
+    picked = []
+    losses = lo.ld_loss(leaves['cls'], leaves['reg'], d['t_cls'], d['t_reg'], leaves['x'],
+                        d['t_x'], tg, cases.STRIDES, imitation='gibox', gi_out=picked)
+    sum(sum(v) for v in losses.values()).backward()
+    assert len(picked) == 5
+    for got, want in zip(picked, gold['gi_idx']):
+        assert torch.equal(got.to(torch.int32), want), (got, want)
+    for k, v in gold['losses'].items():
+        got = torch.stack([t.detach() for t in losses[k]])
+        assert torch.allclose(got, v, rtol=1e-5, atol=1e-6), (k, got, v)
+    for l in range(5):
+        gx = leaves['x'][l].grad
+        gx = torch.zeros_like(leaves['x'][l]) if gx is None else gx
+        assert torch.allclose(gx.sum(1), gold['grad_x_rowsum'][l], rtol=1e-4, atol=1e-6)
+        assert torch.allclose(leaves['cls'][l].grad.norm(), gold['grad_cls_norm'][l], rtol=1e-5)
+        assert torch.allclose(leaves['reg'][l].grad.norm(), gold['grad_reg_norm'][l], rtol=1e-5)
+
+
 @pytest.mark.parametrize('case', cases.STEP_CASES, ids=lambda c: c[0])
 def test_full_step(golden_dir, case):
     name, sd, td, n, h, w, seed = case
