@@ -1,6 +1,6 @@
 """Layer-by-layer comparison of the B200 backbone/FPN against the fp32 CPU oracle port."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import ld_b200
 from ld_b200 import presets, synth, ops, engine

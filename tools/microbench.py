@@ -48,9 +48,12 @@ def bench_kl():
 def bench_loss_targets(which):
     dev = torch.device('cuda')
     n, h, w = 16, 800, 1344
-    from oracle import cases
-    sizes = cases.featmap_sizes(h, w)
-    pyr = L.Pyramid.make(n, sizes, cases.STRIDES)
+    strides = (8, 16, 32, 64, 128)
+    sizes, hh, ww = [], (h + 7) // 8, (w + 7) // 8      # k3 s2 p1 convs: ceil-halving per level
+    for _ in strides:
+        sizes.append((hh, ww))
+        hh, ww = (hh + 1) // 2, (ww + 1) // 2
+    pyr = L.Pyramid.make(n, sizes, strides)
     gb, gl = synth.make_gts(n, h, w, 9)
     gb = [b.cuda() for b in gb]
     gl = [b.cuda() for b in gl]
