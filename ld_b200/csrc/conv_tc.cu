@@ -14,11 +14,19 @@
 //   from TMA out-of-bounds zero fill, stride-2 convs use the tensor map's element strides.  1x1 convs
 //   use the same map with the pixels flattened ({C, N*H*W, 1, 1}).
 // * weights are [Cout][taps*Cin] bf16 (K-major), one 2-D TMA box {64, BN} per k-block.
-// * warp-specialised persistent kernel: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma
-//   issuer (kind::f16, bf16 x bf16 -> fp32 in TMEM, M=128, N=BN, K=16), warp 2 = TMEM allocator,
-//   warps 4-7 = epilogue (tcgen05.ld 32x32b -> registers -> fused scale/bias (folded BN, conv bias,
-//   Scale), residual / nearest-upsample add, ReLU or ReLU-mask, optional accumulate -> NHWC store).
-//   Two TMEM accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+// * warp-specialised persistent kernels: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer
+//   (kind::f16, bf16 x bf16 -> fp32 in TMEM, K=16 per instruction), warp 2 = TMEM allocator, warps 4-11 = epilogue
+//   (tcgen05.ld 32x32b -> registers -> fused scale/bias (folded BN, conv bias, Scale), residual / nearest-upsample
+//   add, ReLU or ReLU-mask, optional accumulate -> NHWC).  Two TMEM accumulator stages so the epilogue of tile i
+//   overlaps the main loop of tile i+1.
+// * three kernels share that skeleton:
+//     conv2_tc_kernel          2-CTA clusters (cta_group::2, M=256 x N=256 pair tiles): 256-wide output tiles
+//     conv_tc_kernel<BN,false> 1-CTA (M=128 x N=BN): narrower layers
+//     conv_tc_kernel<BN,true>  1-CTA, two CTAs per SM: reductions of <= 4 k-blocks (HBM-bound 1x1 "expand" convs)
+//   and one epilogue (`epilogue_tile`) with two output paths: TMA-staged (32 pixel x 64 channel SWIZZLE_128B boxes,
+//   residual / mask TMA-loaded, result TMA-stored) or direct 16-byte stores (fp32 / strided / accumulating outputs).
+// * wgrad2_tc_kernel / wgrad_tc_kernel<BN>: weight gradient, both operands MN-major from the same TMA boxes,
+//   split-K over pixel tiles, fp32 vector reductions into the parameter-gradient buffer.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -27,7 +35,6 @@
 namespace ldb {
 
 constexpr int CONV_THREADS = 384;       // wgrad kernels: 4 control warps + 8 epilogue warps
-constexpr int CONV_FWD_MAX_THREADS = 640;   // 4 control warps + up to 16 epilogue warps
 constexpr int TILE_M = 128;
 constexpr int KCH = 64;                        // channels per k-block (128 B of bf16)
 constexpr int A_TILE_BYTES = TILE_M * KCH * 2;  // 16 KB
