@@ -56,3 +56,28 @@ def loss_case_inputs(n, h, w, seed, num_classes=80, reg_ch=68, feat_ch=256):
     d['img_metas'] = synth.make_img_metas(n, h, w)
     d['sizes'] = sizes
     return d
+
+
+def loss_case_inputs_v2(n, h, w, seed):
+    """Inputs of `LDv2Head.loss` (ld_gflv2.py:286-298) for one case: the v1 tensors with 81 class channels
+    (use_sigmoid=False -> cls_out_channels = num_classes + 1), `cls` / `t_cls` reinterpreted as the student's and the
+    teacher's cls_feat LOGITS, plus `score` = sigmoid(cls_feat) * quality with a random quality map in (0.2, 1): the
+    reference treats joint score and cls_feat as independent inputs of the loss, so does the fixture."""
+    d = loss_case_inputs(n, h, w, seed, num_classes=81)
+    g = torch.Generator().manual_seed(seed + 7)
+    d['cls_feat'] = d.pop('cls')
+    d['score'] = [c.sigmoid() * (0.2 + 0.8 * torch.rand(c.shape[0], 1, c.shape[2], c.shape[3], generator=g))
+                  for c in d['cls_feat']]
+    return d
+
+
+LOSS_CASES_V2 = [
+    ('l2_256x320_s14', 2, 256, 320, 14),
+    ('l2_192x192_s15', 3, 192, 192, 15),
+]
+
+# LDv2 full step: configs/ldv2/ld_r50_gflv2_r101_fpn_1x.py (LDv2Head student, GFocalHead teacher, gibox, IMLoss 2.0)
+# with both backbones swapped for R18.  (name, student depth, teacher depth, N, H, W, seed)
+STEP_CASES_V2 = [
+    ('s2_r18_r18_2x128x160', 18, 18, 2, 128, 160, 31),
+]

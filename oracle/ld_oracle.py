@@ -222,6 +222,23 @@ def qfl_rows(logits, labels, score, beta=2.0):
     return loss.sum(1)
 
 
+def qfl_prob_rows(prob, labels, score, beta=2.0):
+    """quality_focal_loss with use_sigmoid=False (gfocal_loss.py:29-49; the LDv2 / GFLv2 configs): `prob` is already
+    the joint class-quality score sigmoid(cls_feat) * quality (gfocal_head.py:215), supervised by plain
+    F.binary_cross_entropy.  C = num_classes + 1 there (anchor_head.py use_sigmoid_cls=False), so background rows
+    (label == num_classes) take the "positive" branch with score 0 -- numerically the zero-label formula."""
+    loss = F.binary_cross_entropy(prob, torch.zeros_like(prob), reduction='none') * prob.pow(beta)
+    C = prob.shape[1]
+    pos = ((labels >= 0) & (labels < C)).nonzero().squeeze(1)
+    if pos.numel():
+        pl = labels[pos]
+        x = prob[pos, pl]
+        sf = score[pos] - x
+        lp = F.binary_cross_entropy(x, score[pos], reduction='none') * sf.abs().pow(beta)
+        loss = loss.index_put((pos, pl), lp)
+    return loss.sum(1)
+
+
 def dfl_rows(logits, target):
     """distribution_focal_loss (gfocal_loss.py:68-74)."""
     dl = target.long()
@@ -278,12 +295,15 @@ def nms_topk(boxes, scores, iou_thr, k):
     return torch.tensor(keep, dtype=torch.long)
 
 
-def gi_region(t_cls, cls, anchors, reg, t_reg, stride, reg_max=16, iou_thr=0.3, k=10):
+def gi_region(t_cls, cls, anchors, reg, t_reg, stride, reg_max=16, iou_thr=0.3, k=10, raw_scores=False):
     """`LDHead.get_gi_region` (ld_head.py:613-638): General-Instance boxes of one level.  Per location the GI
     score is max_c |sigmoid(teacher) - sigmoid(student)|, the GI box the teacher's decoded box where the teacher
     scores higher at that class, else the student's; NMS (IoU 0.3) over ALL locations of the level (the images of
     the batch share one coordinate frame here, as in the reference) and the first 10 keeps are returned."""
-    ts, ss = t_cls.detach().sigmoid(), cls.detach().sigmoid()
+    if raw_scores:   # LDv2Head.get_gi_region (ld_gflv2.py): no sigmoid -- teacher LOGITS against student joint scores
+        ts, ss = t_cls.detach(), cls.detach()
+    else:
+        ts, ss = t_cls.detach().sigmoid(), cls.detach().sigmoid()
     ctr = torch.stack([(anchors[:, 0] + anchors[:, 2]) / 2, (anchors[:, 1] + anchors[:, 3]) / 2], 1) / stride
     sd, td = integral(reg.detach(), reg_max), integral(t_reg.detach(), reg_max)
 
@@ -302,12 +322,16 @@ DEFAULT_LOSS_CFG = dict(w_qfl=1.0, beta=2.0, w_giou=2.0, w_dfl=0.25, w_ld=0.25, 
 
 
 def ld_loss_level(anchors, cls, reg, labels, label_w, bbox_t, stride, t_reg, t_cls, x, t_x,
-                  vlr, im, num_total_samples, cfg=DEFAULT_LOSS_CFG, imitation='finegrained', gi_out=None):
+                  vlr, im, num_total_samples, cfg=DEFAULT_LOSS_CFG, imitation='finegrained', gi_out=None,
+                  cls_feat=None, num_classes=None):
     """`LDHead.loss_single` (ld_head.py:116-282) on flattened NHWC rows.
 
     anchors [R,4]; cls [R,C]; reg/t_reg [R,4*(reg_max+1)]; t_cls [R,C]; x,t_x [R,F].
     Returns the 8 (pre-avg_factor) loss terms and sum of weight_targets."""
-    C = cls.shape[1]
+    # LDv2Head.loss_single (ld_gflv2.py:116-285) when `cls_feat` is given: `cls` is then the joint score
+    # sigmoid(cls_feat) * quality (a probability), `t_cls` the teacher's cls_feat LOGITS (ld_gflv2.py:327)
+    v2 = cls_feat is not None
+    C = cls.shape[1] if num_classes is None else num_classes    # bg_class_ind = self.num_classes (ld_head.py:163)
     rm = cfg['reg_max']
     pos = ((labels >= 0) & (labels < C)).nonzero().squeeze(1)
     rem = (vlr > 0).nonzero().squeeze(1)
@@ -315,14 +339,14 @@ def ld_loss_level(anchors, cls, reg, labels, label_w, bbox_t, stride, t_reg, t_c
     zero = reg.sum() * 0
     score = label_w.new_zeros(labels.shape)
     if imitation == 'gibox':   # ld_head.py:170-176
-        fg = gi_region(t_cls, cls, anchors, reg, t_reg, stride, rm)
+        fg = gi_region(t_cls, cls, anchors, reg, t_reg, stride, rm, raw_scores=v2)
         if gi_out is not None:
             gi_out.append(fg)
     loss_im = cfg['w_im'] * F.mse_loss(x[fg], t_x[fg]) if fg.numel() else zero
     if pos.numel():
         a = anchors[pos]
         ctr = torch.stack([(a[:, 0] + a[:, 2]) / 2, (a[:, 1] + a[:, 3]) / 2], 1) / stride
-        wt = cls.detach().sigmoid().max(1)[0][pos]
+        wt = (cls.detach() if v2 else cls.detach().sigmoid()).max(1)[0][pos]   # ld_gflv2.py:200 / ld_head.py:198
         d = integral(reg[pos], rm)
         pred = torch.stack([ctr[:, 0] - d[:, 0], ctr[:, 1] - d[:, 1],
                             ctr[:, 0] + d[:, 2], ctr[:, 1] + d[:, 3]], 1)
@@ -337,7 +361,7 @@ def ld_loss_level(anchors, cls, reg, labels, label_w, bbox_t, stride, t_reg, t_c
         loss_bbox = cfg['w_giou'] * ((1 - aligned_overlaps(pred, tgt, 'giou')) * wt).sum() / 1.0
         loss_dfl = cfg['w_dfl'] * (dfl_rows(pc, corners) * w4).sum() / 4.0
         loss_ld = cfg['w_ld'] * (kd_kl_rows(pc, sc, cfg['T_ld']) * w4).sum() / 4.0
-        loss_kd = cfg['w_kd'] * (kd_kl_rows(cls[pos], t_cls[pos], cfg['T_kd']) * label_w[pos]
+        loss_kd = cfg['w_kd'] * (kd_kl_rows((cls_feat if v2 else cls)[pos], t_cls[pos], cfg['T_kd']) * label_w[pos]
                                  ).sum() / pos.numel()
         wsum = wt.sum()
     else:
@@ -353,8 +377,8 @@ def ld_loss_level(anchors, cls, reg, labels, label_w, bbox_t, stride, t_reg, t_c
                                           * label_w[rem]).sum() / rem.numel())
     else:
         loss_ld_vlr = loss_kd_neg = zero
-    loss_cls = cfg['w_qfl'] * (qfl_rows(cls, labels, score, cfg['beta']) * label_w).sum() \
-        / num_total_samples
+    qfl = qfl_prob_rows if v2 else qfl_rows
+    loss_cls = cfg['w_qfl'] * (qfl(cls, labels, score, cfg['beta']) * label_w).sum() / num_total_samples
     return dict(loss_cls=loss_cls, loss_bbox=loss_bbox, loss_dfl=loss_dfl, loss_ld=loss_ld,
                 loss_ld_vlr=loss_ld_vlr, loss_kd=loss_kd, loss_kd_neg=loss_kd_neg,
                 loss_im=loss_im), wsum
@@ -366,7 +390,8 @@ def nhwc_rows(t):
 
 
 def ld_loss(cls_scores, bbox_preds, t_cls_scores, t_bbox_preds, feats, t_feats, targets,
-            strides, cfg=DEFAULT_LOSS_CFG, world_size=1, imitation='finegrained', gi_out=None):
+            strides, cfg=DEFAULT_LOSS_CFG, world_size=1, imitation='finegrained', gi_out=None, cls_feats=None,
+            num_classes=None):
     """`LDHead.loss` (ld_head.py:284-375) given NCHW per-level tensors and `ld_targets` output.
     Single process: reduce_mean is the identity."""
     nts = max(float(targets["num_total_pos"]), 1.0)
@@ -382,7 +407,8 @@ def ld_loss(cls_scores, bbox_preds, t_cls_scores, t_bbox_preds, feats, t_feats, 
                              nhwc_rows(t_bbox_preds[l]), nhwc_rows(t_cls_scores[l]),
                              nhwc_rows(feats[l]), nhwc_rows(t_feats[l]),
                              targets['vlr'][l].reshape(-1), targets['im'][l].reshape(-1),
-                             nts, cfg, imitation, gi_out)
+                             nts, cfg, imitation, gi_out,
+                             None if cls_feats is None else nhwc_rows(cls_feats[l]), num_classes)
         per.append(d)
         wsum = wsum + w
     avg = float(wsum + 1e-6)
@@ -564,12 +590,46 @@ class OracleGFLHead(nn.Module):
         return cls_scores, bbox_preds
 
 
+class OracleGFocalHead(OracleGFLHead):
+    """GFLv2 head (gfocal_head.py:112-217): GFLHead + the Distribution-Guided Quality Predictor -- top-`reg_topk`
+    probabilities (+ their mean) of each side's bin distribution -> 1x1 conv -> ReLU -> 1x1 conv -> sigmoid = quality,
+    cls_score = sigmoid(cls_feat) * quality.  `use_sigmoid=False` in loss_cls makes cls_out_channels = classes + 1."""
+
+    def __init__(self, num_classes=80, c=256, reg_max=16, stacked=4, levels=5, reg_topk=4, reg_channels=64,
+                 add_mean=True):
+        super().__init__(num_classes + 1, c, reg_max, stacked, levels)
+        self.reg_max, self.reg_topk, self.add_mean = reg_max, reg_topk, add_mean
+        total_dim = reg_topk + (1 if add_mean else 0)
+        self.reg_conf = nn.Sequential(nn.Conv2d(4 * total_dim, reg_channels, 1), nn.ReLU(inplace=True),
+                                      nn.Conv2d(reg_channels, 1, 1), nn.Sigmoid())
+
+    def forward(self, feats):
+        cls_scores, bbox_preds, cls_feats = [], [], []
+        for x, sc in zip(feats, self.scales):
+            cf = rf = x
+            for m in self.cls_convs:
+                cf = m(cf)
+            for m in self.reg_convs:
+                rf = m(rf)
+            bp = sc(self.gfl_reg(rf)).float()
+            n, _, h, w = bp.shape
+            prob = F.softmax(bp.reshape(n, 4, self.reg_max + 1, h, w), dim=2)
+            stat = prob.topk(self.reg_topk, dim=2)[0]
+            if self.add_mean:
+                stat = torch.cat([stat, stat.mean(dim=2, keepdim=True)], dim=2)
+            logits = self.gfl_cls(cf)
+            cls_scores.append(logits.sigmoid() * self.reg_conf(stat.reshape(n, -1, h, w)))
+            bbox_preds.append(bp)
+            cls_feats.append(logits)
+        return cls_scores, bbox_preds, cls_feats
+
+
 class OracleGFL(nn.Module):
-    def __init__(self, depth):
+    def __init__(self, depth, v2=False):
         super().__init__()
         self.backbone = OracleResNet(depth)
         self.neck = OracleFPN(self.backbone.out_channels)
-        self.bbox_head = OracleGFLHead()
+        self.bbox_head = OracleGFocalHead() if v2 else OracleGFLHead()
 
     def extract_feat(self, img):
         return self.neck(self.backbone(img))
@@ -579,11 +639,13 @@ class OracleLDDetector(nn.Module):
     """kd_one_stage.py:12-108: student (grad) + plain-attribute teacher (no grad) + LDHead loss."""
     strides = (8, 16, 32, 64, 128)
 
-    def __init__(self, student_depth=50, teacher_depth=101, loss_cfg=None, imitation='finegrained'):
+    def __init__(self, student_depth=50, teacher_depth=101, loss_cfg=None, imitation='finegrained', v2=False):
+        """v2: LDv2Head student + GFocalHead teacher (configs/ldv2/ld_r50_gflv2_r101_fpn_1x.py)."""
         super().__init__()
-        s = OracleGFL(student_depth)
+        self.v2 = v2
+        s = OracleGFL(student_depth, v2)
         self.backbone, self.neck, self.bbox_head = s.backbone, s.neck, s.bbox_head
-        object.__setattr__(self, 'teacher_model', OracleGFL(teacher_depth))
+        object.__setattr__(self, 'teacher_model', OracleGFL(teacher_depth, v2))
         self.teacher_model.eval()
         self.loss_cfg = dict(DEFAULT_LOSS_CFG, **(loss_cfg or {}))
         self.imitation = imitation
@@ -592,12 +654,17 @@ class OracleLDDetector(nn.Module):
         x = self.neck(self.backbone(img))
         with torch.no_grad():
             tx = self.teacher_model.extract_feat(img)
-            t_cls, t_reg = self.teacher_model.bbox_head(tx)
-        cls, reg = self.bbox_head(x)
+            t_out = self.teacher_model.bbox_head(tx)
+        out = self.bbox_head(x)
+        cls, reg = out[0], out[1]
         sizes = [tuple(c.shape[-2:]) for c in cls]
         tg = ld_targets(sizes, self.strides, img_metas, gt_bboxes, gt_labels,
-                        imitation=self.imitation)
-        return ld_loss(cls, reg, t_cls, t_reg, x, tx, tg, self.strides, self.loss_cfg)
+                        imitation='finegrained' if self.imitation == 'gibox' else self.imitation)
+        if self.v2:   # ld_gflv2.py:327: soft_teacher = (teacher cls_score [unused], bbox_pred, cls_feat)
+            return ld_loss(cls, reg, t_out[2], t_out[1], x, tx, tg, self.strides, self.loss_cfg,
+                           imitation=self.imitation, cls_feats=out[2], num_classes=80)
+        return ld_loss(cls, reg, t_out[0], t_out[1], x, tx, tg, self.strides, self.loss_cfg,
+                       imitation=self.imitation)
 
     def step(self, batch, backward=True):
         for p in self.parameters():

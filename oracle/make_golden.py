@@ -120,6 +120,83 @@ def gen_losses_gibox(head):
         head.imitation_method = 'finegrained'
 
 
+def _with_cpu_gibox(fn):
+    """Run `fn` with `Tensor.cuda` patched to the identity (ld_head.py:628 / ld_gflv2.py call `.cuda()` on an index
+    tensor) and torchvision imported (registers torch.ops.torchvision.nms)."""
+    import torchvision  # noqa: F401
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        return fn()
+    finally:
+        torch.Tensor.cuda = orig
+
+
+def gen_losses_v2():
+    """`LDv2Head.loss` (ld_gflv2.py:286-375) of configs/ldv2/ld_r50_gflv2_r101_fpn_1x.py: gibox imitation, QFL on joint
+    scores (use_sigmoid=False), KD on cls_feat, 81 class channels."""
+    head = rh.reference_head(config_rel='configs/ldv2/ld_r50_gflv2_r101_fpn_1x.py')
+    assert type(head).__name__ == 'LDv2Head' and head.cls_out_channels == 81 and head.imitation_method == 'gibox'
+    picked, orig_gi = [], head.get_gi_region
+
+    def spy(*a, **k):
+        idx = orig_gi(*a, **k)
+        picked.append(idx.clone())
+        return idx
+    head.get_gi_region = spy
+    for name, n, h, w, seed in cases.LOSS_CASES_V2:
+        d = cases.loss_case_inputs_v2(n, h, w, seed)
+        del picked[:]
+        leaves = {k: [t.clone().requires_grad_(True) for t in d[k]] for k in ('score', 'cls_feat', 'reg', 'x')}
+
+        def run():
+            return head.loss(leaves['score'], leaves['reg'], leaves['cls_feat'], d['gt_bboxes'], d['gt_labels'],
+                             (None, d['t_reg'], d['t_cls']), leaves['x'], d['t_x'], d['img_metas'])
+        losses = _with_cpu_gibox(run)
+        total = sum(sum(v) for v in losses.values())
+        total.backward()
+        for grp in leaves.values():
+            for t in grp:
+                if t.grad is None:
+                    t.grad = torch.zeros_like(t)
+        gold = dict(losses={k: torch.stack([t.detach() for t in v]) for k, v in losses.items()},
+                    total=total.detach(), gi_idx=[p.to(torch.int32) for p in picked],
+                    grad_score=[t.grad for t in leaves['score']],
+                    grad_cls_feat_norm=torch.stack([t.grad.norm() for t in leaves['cls_feat']]),
+                    grad_cls_feat_rowsum=[t.grad.sum(1) for t in leaves['cls_feat']],
+                    grad_reg=[t.grad for t in leaves['reg']],
+                    grad_x_rowsum=[t.grad.sum(1) for t in leaves['x']])
+        torch.save(gold, os.path.join(OUT, name + '.pt'))
+        print(name, {k: [round(float(x), 5) for x in v] for k, v in gold['losses'].items()})
+
+
+def gen_steps_v2():
+    for name, sd, td, n, h, w, seed in cases.STEP_CASES_V2:
+        cfg = rh.load_model_cfg('configs/ldv2/ld_r50_gflv2_r101_fpn_1x.py')
+        cfg['backbone']['depth'] = sd
+        cfg['neck']['in_channels'] = [64, 128, 256, 512] if sd < 50 else [256, 512, 1024, 2048]
+        cfg['teacher_config']['model']['backbone']['depth'] = td
+        cfg['teacher_config']['model']['neck']['in_channels'] = \
+            [64, 128, 256, 512] if td < 50 else [256, 512, 1024, 2048]
+        m = rh.build_reference_detector(cfg)
+        synth.seeded_init(m, seed)
+        synth.seeded_init(m.teacher_model, seed + 1, prefix='teacher.')
+        b = synth.make_batch(n, h, w, seed=1000 + seed)
+        losses, loss, log = _with_cpu_gibox(lambda: rh.reference_step(m, b))
+        named = dict(m.named_parameters())
+        gold = dict(log_vars=log,
+                    losses={k: torch.stack([t.detach() for t in v]) for k, v in losses.items()},
+                    grad_stats={k: torch.tensor([float(p.grad.double().norm()), float(p.grad.double().sum()),
+                                                 float(p.grad.abs().max())])
+                                for k, p in named.items() if p.grad is not None},
+                    no_grad=[k for k, p in named.items() if p.grad is None],
+                    grads={k: named[k].grad.clone() for k in
+                           ('bbox_head.reg_conf.0.weight', 'bbox_head.reg_conf.2.weight', 'bbox_head.gfl_cls.bias',
+                            'bbox_head.gfl_reg.bias', 'bbox_head.scales.0.scale')})
+        torch.save(gold, os.path.join(OUT, name + '.pt'))
+        print(name, {k: round(v, 5) for k, v in log.items()})
+
+
 def gen_steps():
     for name, sd, td, n, h, w, seed in cases.STEP_CASES:
         cfg = rh.load_model_cfg()
@@ -161,6 +238,8 @@ def main():
     gen_losses(head)
     gen_losses_gibox(head)
     gen_steps()
+    gen_losses_v2()
+    gen_steps_v2()
 
 
 if __name__ == '__main__':

@@ -61,11 +61,11 @@ def reference_step(model, batch, backward=True):
     return losses, loss, log_vars
 
 
-def reference_head(cfg_overrides=None):
-    """A bare reference `LDHead` (no backbone) for target / loss_single goldens."""
+def reference_head(cfg_overrides=None, config_rel='configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py'):
+    """A bare reference `LDHead` / `LDv2Head` (no backbone) for target / loss_single goldens."""
     mmcv_standin.import_reference(REF_ROOT)
     from mmdet.models import build_head
-    model_cfg = load_model_cfg(**(cfg_overrides or {}))
+    model_cfg = load_model_cfg(config_rel, **(cfg_overrides or {}))
     head_cfg = model_cfg['bbox_head']
     head_cfg['train_cfg'] = model_cfg['train_cfg']
     head_cfg['test_cfg'] = model_cfg['test_cfg']

@@ -102,6 +102,56 @@ def test_full_step(golden_dir, case):
         assert torch.allclose(named[k].grad, g, rtol=1e-4, atol=1e-6 * float(g.abs().max())), k
 
 
+@pytest.mark.parametrize('case', cases.LOSS_CASES_V2, ids=lambda c: c[0])
+def test_loss_ldv2(golden_dir, case):
+    """`LDv2Head.loss` (ld_gflv2.py, configs/ldv2/ld_r50_gflv2_r101_fpn_1x.py): QFL on joint scores, KD on cls_feat,
+    raw-score GI boxes, 81 class channels -- restatement against the unmodified reference."""
+    name, n, h, w, seed = case
+    gold = _load(golden_dir, name)
+    d = cases.loss_case_inputs_v2(n, h, w, seed)
+    leaves = {k: [t.clone().requires_grad_(True) for t in d[k]] for k in ('score', 'cls_feat', 'reg', 'x')}
+    tg = lo.ld_targets(d['sizes'], cases.STRIDES, d['img_metas'], d['gt_bboxes'], d['gt_labels'])
+    picked = []
+    losses = lo.ld_loss(leaves['score'], leaves['reg'], d['t_cls'], d['t_reg'], leaves['x'], d['t_x'], tg,
+                        cases.STRIDES, imitation='gibox', gi_out=picked, cls_feats=leaves['cls_feat'], num_classes=80)
+    sum(sum(v) for v in losses.values()).backward()
+    for got, want in zip(picked, gold['gi_idx']):
+        assert torch.equal(got.to(torch.int32), want), (got, want)
+    for k, v in gold['losses'].items():
+        got = torch.stack([t.detach() for t in losses[k]])
+        assert torch.allclose(got, v, rtol=1e-5, atol=1e-6), (k, got, v)
+
+    def g(t):
+        return torch.zeros_like(t) if t.grad is None else t.grad
+    for l in range(5):
+        assert torch.allclose(g(leaves['score'][l]), gold['grad_score'][l], rtol=1e-5, atol=1e-7)
+        assert torch.allclose(g(leaves['reg'][l]), gold['grad_reg'][l], rtol=1e-5, atol=1e-7)
+        assert torch.allclose(g(leaves['cls_feat'][l]).sum(1), gold['grad_cls_feat_rowsum'][l], rtol=1e-4, atol=1e-7)
+        assert torch.allclose(g(leaves['x'][l]).sum(1), gold['grad_x_rowsum'][l], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize('case', cases.STEP_CASES_V2, ids=lambda c: c[0])
+def test_full_step_ldv2(golden_dir, case):
+    """Whole LDv2 iteration (GFocalHead student + teacher with the DGQP branch, gfocal_head.py:180-217)."""
+    name, sd, td, n, h, w, seed = case
+    gold = _load(golden_dir, name)
+    m = lo.OracleLDDetector(sd, td, imitation='gibox', v2=True,
+                            loss_cfg=dict(w_ld_vlr=0.25, T_ld_vlr=10.0, w_kd=10.0, T_kd=2.0, w_im=2.0)).train()
+    synth.seeded_init(m, seed)
+    synth.seeded_init(m.teacher_model, seed + 1, prefix='teacher.')
+    b = synth.make_batch(n, h, w, seed=1000 + seed)
+    losses, loss, log = m.step(b)
+    for k, v in gold['log_vars'].items():
+        assert abs(log[k] - v) <= 1e-5 * max(abs(v), 1.0), (k, log[k], v)
+    named = dict(m.named_parameters())
+    assert set(gold['no_grad']) == {k for k, p in named.items() if p.grad is None}
+    for k, ref in gold['grads'].items():
+        assert torch.allclose(named[k].grad, ref, rtol=1e-4, atol=1e-7), k
+    for k, st in gold['grad_stats'].items():
+        gn = float(named[k].grad.double().norm())
+        assert abs(gn - float(st[0])) <= 1e-4 * max(float(st[0]), 1e-6), (k, gn, float(st[0]))
+
+
 def test_reference_known_answers():
     """The only known-answer vectors the reference's own tests/doctests hold on this path
     (SURVEY.md §8c): tests/test_anchor.py:22-41 `test_strides` and the bbox_overlaps examples of
