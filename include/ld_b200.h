@@ -153,6 +153,26 @@ int ldb200_gi_region(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const floa
                      const float* t_cls, const float* t_reg, float iou_thr, int topk, const int32_t* counts_in,
                      int32_t* gi_rows, int32_t* counts_out, void* workspace, void* stream);
 
+/* GFLv2 Distribution-Guided Quality Predictor on row-space head outputs.  Replaces the tail of
+ * GFocalHead.forward_single (gfocal_head.py:198-215): per row, softmax of the four side distributions, their top-
+ * `topk` probabilities (+ mean when add_mean), reg_conf = conv1x1(4*(topk+add_mean) -> hid) + ReLU + conv1x1(hid -> 1)
+ * + sigmoid = quality, and the joint score sigmoid(cls_feat) * quality.
+ *   reg [rows, reg_ld>=4*bins] f32, cls_feat [rows, cls_ld>=C] f32 (ld 0 = dense)
+ *   W1 [hid, 4*(topk+add_mean)] = reg_conf.0.weight, b1 [hid], W2 [hid] = reg_conf.2.weight, b2 [1] (device)
+ *   quality [rows] f32, score [rows, C] f32
+ * Backward (autograd of the same lines): from d_score (d loss / d joint score) and an optional extra gradient on
+ * cls_feat (d_kd: the KD term of LDv2Head, ld_gflv2.py:242-246) it writes d_cls_feat, ADDS the predictor's
+ * contribution to d_reg and accumulates dW1/db1/dW2/db2 (fp32, atomics).  Gradient tensors are grad_dtype
+ * (LDB_F32 / LDB_BF16) with row strides dscore_ld / dreg_ld (0 = dense). */
+int ldb200_dgqp_forward(const float* reg, int reg_ld, const float* cls_feat, int cls_ld, int rows, int C, int bins,
+                        int topk, int add_mean, int hid, const float* W1, const float* b1, const float* W2,
+                        const float* b2, float* quality, float* score, void* stream);
+int ldb200_dgqp_backward(const float* reg, int reg_ld, const float* cls_feat, int cls_ld, int rows, int C, int bins,
+                         int topk, int add_mean, int hid, const float* W1, const float* b1, const float* W2,
+                         const float* b2, const float* quality, const void* d_score, const void* d_kd,
+                         int dscore_ld, void* d_cls_feat, void* d_reg, int dreg_ld, int grad_dtype, float* dW1,
+                         float* db1, float* dW2, float* db2, void* stream);
+
 /* dst[rows[i], :] += src[i, :]  (rows unique).  Adds the compact IM gradient into the dense
  * gradient of the student FPN map. */
 int ldb200_scatter_add_rows(void* dst, const void* src, const int32_t* rows, const int32_t* n_rows_dev,

@@ -431,3 +431,64 @@ class _LossOnlyFn(torch.autograd.Function):
             out += [v for v in ops.from_rows(d, ctx.pyr)]
         out += [None] * (3 * nl)
         return tuple(out)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GFLv2 / LDv2: registry surface, parameters and checkpoint keys of the reference classes.
+# The kernels behind them -- `ldb200_dgqp_forward/_backward` (quality branch, dgqp.cu), `ldb200_gi_region`
+# (raw-score GI boxes) and the v2 arithmetic of the loss (v2_math.cuh: QFL on joint scores) -- exist; the fused LDv2
+# loss launch that ties them together is the next step, so `forward_train` still raises instead of running anything
+# that is not the CUDA path.  The CPU oracle of the whole LDv2 step is pinned to the unmodified reference
+# (oracle/ld_oracle.py, tests/golden/l2_*.pt, s2_*.pt).
+@HEADS.register_module()
+class GFocalHead(GFLHead):
+    """gfocal_head.py:51-152: GFLHead + Distribution-Guided Quality Predictor (`reg_conf`)."""
+
+    def __init__(self, num_classes, in_channels, reg_topk=4, reg_channels=64, add_mean=True, **kwargs):
+        self.reg_topk, self.reg_channels, self.add_mean = reg_topk, reg_channels, add_mean
+        self.total_dim = reg_topk + (1 if add_mean else 0)
+        super().__init__(num_classes, in_channels, **kwargs)
+
+    def _init_layers(self):
+        super()._init_layers()
+        # gfocal_head.py:147-152 (an nn.Sequential: checkpoint keys reg_conf.0.* and reg_conf.2.*)
+        self.reg_conf = nn.Sequential(nn.Conv2d(4 * self.total_dim, self.reg_channels, 1), nn.ReLU(inplace=True),
+                                      nn.Conv2d(self.reg_channels, 1, 1), nn.Sigmoid())
+
+    def init_weights(self):
+        super().init_weights()
+        for m in self.reg_conf:      # gfocal_head.py:160-162: normal_init(std=0.01), bias 0
+            if isinstance(m, nn.Conv2d):
+                nn.init.normal_(m.weight, 0, 0.01)
+                nn.init.constant_(m.bias, 0)
+
+    def quality_params(self):
+        """(W1 [hid, 4*total_dim], b1, W2 [hid], b2 [1]) in the layout `ops.dgqp_forward` takes."""
+        c0, c2 = self.reg_conf[0], self.reg_conf[2]
+        return (c0.weight.reshape(self.reg_channels, -1), c0.bias, c2.weight.reshape(-1), c2.bias)
+
+    def forward_train(self, *args, **kwargs):
+        raise NotImplementedError('GFocalHead/LDv2Head training: the fused LDv2 loss launch is not built yet '
+                                  '(SURVEY.md §8 a23; kernels so far: ldb200_dgqp_forward/_backward, ldb200_gi_region)')
+
+    forward = forward_train
+
+
+@HEADS.register_module()
+class LDv2Head(GFocalHead):
+    """ld_gflv2.py:43-71: GFocalHead + the LD / VLR-LD / KD / IM losses (constructor identical to LDHead's)."""
+
+    def __init__(self, num_classes, in_channels,
+                 loss_ld=dict(type='KnowledgeDistillationKLDivLoss', loss_weight=0.25, T=10),
+                 loss_ld_vlr=dict(type='KnowledgeDistillationKLDivLoss', loss_weight=0.25, T=10),
+                 loss_kd=dict(type='KnowledgeDistillationKLDivLoss', loss_weight=10, T=2),
+                 loss_im=dict(type='IMLoss', loss_weight=0), imitation_method='gibox', **kwargs):
+        super().__init__(num_classes, in_channels, **kwargs)
+        self.imitation_method = imitation_method
+        self.gi_iou_thr, self.gi_topk = 0.3, 10
+        self.loss_im = build_loss(loss_im)
+        self.loss_ld = build_loss(loss_ld)
+        self.loss_ld_vlr = build_loss(loss_ld_vlr)
+        self.loss_kd = build_loss(loss_kd)
+        from .registry import build_iou_calculator
+        self.iou_calculator = build_iou_calculator(dict(type='BboxOverlaps2D'))

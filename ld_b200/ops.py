@@ -175,6 +175,44 @@ def gi_region(cfg: L.LossCfg, cls, reg, t_cls, t_reg, tg: LDTargets, iou_thr=0.3
     return gi_rows, counts
 
 
+def dgqp_forward(reg, cls_feat, W1, b1, W2, b2, reg_topk=4, add_mean=True):
+    """GFLv2 quality branch + joint score on row-space head outputs (ldb200_dgqp_forward, gfocal_head.py:198-215).
+    reg [R, 4*bins] f32, cls_feat [R, C] f32; W1 [hid, 4*(topk+add_mean)], b1 [hid], W2 [hid], b2 [1] (fp32, device).
+    -> (quality [R], score [R, C])."""
+    lib = L.load()
+    R, C_ = cls_feat.shape
+    bins = reg.shape[1] // 4
+    for t in (reg, cls_feat, W1, b1, W2, b2):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    hid = W1.shape[0]
+    assert W1.shape[1] == 4 * (reg_topk + int(add_mean)) and W2.numel() == hid and b1.numel() == hid and b2.numel() == 1
+    q = torch.empty(R, dtype=torch.float32, device=reg.device)
+    score = torch.empty(R, C_, dtype=torch.float32, device=reg.device)
+    L.check(lib.ldb200_dgqp_forward(L.ptr(reg), 0, L.ptr(cls_feat), 0, R, C_, bins, int(reg_topk), int(add_mean), hid,
+                                    L.ptr(W1), L.ptr(b1), L.ptr(W2), L.ptr(b2), L.ptr(q), L.ptr(score), L.stream_ptr()),
+            'ldb200_dgqp_forward')
+    return q, score
+
+
+def dgqp_backward(reg, cls_feat, W1, b1, W2, b2, quality, d_score, d_reg, d_kd=None, reg_topk=4, add_mean=True):
+    """Backward of `dgqp_forward`: -> (d_cls_feat, dW1, db1, dW2, db2); the predictor's gradient w.r.t. the box
+    distribution logits is ADDED into `d_reg` in place.  d_score / d_kd / d_reg share one dtype (f32 or bf16)."""
+    lib = L.load()
+    R, C_ = cls_feat.shape
+    bins = reg.shape[1] // 4
+    hid = W1.shape[0]
+    assert d_score.shape[0] == R and d_score.stride(1) == 1 and d_reg.stride(1) == 1 and d_reg.dtype == d_score.dtype
+    assert d_kd is None or (d_kd.dtype == d_score.dtype and d_kd.stride() == d_score.stride())
+    d_cls_feat = torch.empty_like(d_score)
+    dW1, db1, dW2, db2 = (torch.zeros_like(W1), torch.zeros_like(b1), torch.zeros_like(W2), torch.zeros_like(b2))
+    L.check(lib.ldb200_dgqp_backward(L.ptr(reg), 0, L.ptr(cls_feat), 0, R, C_, bins, int(reg_topk), int(add_mean), hid,
+                                     L.ptr(W1), L.ptr(b1), L.ptr(W2), L.ptr(b2), L.ptr(quality), L.ptr(d_score),
+                                     L.ptr(d_kd), int(d_score.stride(0)), L.ptr(d_cls_feat), L.ptr(d_reg),
+                                     int(d_reg.stride(0)), _dt(d_score.dtype), L.ptr(dW1), L.ptr(db1), L.ptr(dW2),
+                                     L.ptr(db2), L.stream_ptr()), 'ldb200_dgqp_backward')
+    return d_cls_feat, dW1, db1, dW2, db2
+
+
 def scatter_add_rows(dst, src, rows, n_rows_dev, max_rows=None):
     lib = L.load()
     max_rows = src.shape[0] if max_rows is None else max_rows

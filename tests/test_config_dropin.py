@@ -59,6 +59,28 @@ def test_r18_config_and_registry_errors(monkeypatch):
         ld_b200.build_loss(dict(type='IMLoss', bogus=1))
 
 
+@needs_ref
+def test_ldv2_config_builds_with_reference_keys(monkeypatch):
+    """configs/ldv2/ld_r50_gflv2_r101_fpn_1x.py (LDv2Head student, GFocalHead teacher): the registry
+    surface, parameters and checkpoint keys are in place; training still raises (no non-CUDA fallback)."""
+    import ld_b200
+    from oracle import ld_oracle as lo
+    monkeypatch.chdir(REF)
+    cfg = ld_b200.Config.fromfile('configs/ldv2/ld_r50_gflv2_r101_fpn_1x.py')
+    model = ld_b200.build_detector(cfg.model)
+    head = model.bbox_head
+    assert type(head).__name__ == 'LDv2Head' and type(model.teacher_model.bbox_head).__name__ == 'GFocalHead'
+    assert head.cls_out_channels == 81 and head.imitation_method == 'gibox' and head.loss_im.loss_weight == 2
+    assert (head.reg_topk, head.reg_channels, head.add_mean) == (4, 64, True)
+    o = lo.OracleLDDetector(50, 101, v2=True)
+    assert set(model.state_dict()) == set(o.state_dict())
+    assert all(model.state_dict()[k].shape == v.shape for k, v in o.state_dict().items())
+    w1, b1, w2, b2 = head.quality_params()
+    assert w1.shape == (64, 20) and b1.shape == (64,) and w2.shape == (64,) and b2.shape == (1,)
+    with pytest.raises(NotImplementedError):
+        head.forward_train(None)
+
+
 def test_state_dict_keys_match_oracle_port():
     import ld_b200
     from ld_b200 import presets
