@@ -173,6 +173,28 @@ int ldb200_dgqp_backward(const float* reg, int reg_ld, const float* cls_feat, in
                          int dscore_ld, void* d_cls_feat, void* d_reg, int dreg_ld, int grad_dtype, float* dW1,
                          float* db1, float* dW2, float* db2, void* stream);
 
+/* LDv2Head variants (ld_gflv2.py:116-375, configs/ldv2) of the three loss-side entry points.
+ * Differences to the LDHead versions above: `score` [R,C] = joint scores sigmoid(cls_feat) * quality (probabilities,
+ * from ldb200_dgqp_forward) feed QFL as F.binary_cross_entropy (gfocal_loss.py:29-49, use_sigmoid=False) and
+ * weight_targets = max_c score without sigmoid (ld_gflv2.py:200); the KD term compares the student's cls_feat logits
+ * with the teacher's (ld_gflv2.py:242-246, 327); C = cfg->num_classes = cls_out_channels = num_fg + 1 and labels >=
+ * num_fg are background; the GI score is |t_cls_feat - score| with no sigmoid on either side.
+ * Gradients: d_score (w.r.t. the joint score, dense) and d_kd (KD term w.r.t. cls_feat, zero-filled by the call,
+ * non-zero on positive rows) both [R, d_cls_ld]; feed both to ldb200_dgqp_backward. */
+int ldb200_ld_loss_prepass_v2(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const float* score, const float* reg,
+                              const int32_t* labels, const float* bbox_targets, const int32_t* sparse_rows,
+                              const int32_t* counts, int num_fg, float* iou_score, float* wsum, void* stream);
+int ldb200_ld_loss_fused_v2(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const float* score, const float* cls_feat,
+                            const float* reg, const float* t_cls_feat, const float* t_reg, const void* x,
+                            const void* t_x, int feat_dtype, const int32_t* labels, const float* label_weights,
+                            const float* bbox_targets, const float* vlr, const int32_t* sparse_rows,
+                            const int32_t* fg_rows, const int32_t* counts, const float* norm,
+                            const float* term_grad_host, int num_fg, float* losses, void* d_score, void* d_kd,
+                            void* d_reg, void* d_im, int d_cls_ld, int d_reg_ld, int grad_dtype, void* stream);
+int ldb200_gi_region_v2(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const float* score, const float* reg,
+                        const float* t_cls_feat, const float* t_reg, float iou_thr, int topk, const int32_t* counts_in,
+                        int32_t* gi_rows, int32_t* counts_out, void* workspace, void* stream);
+
 /* dst[rows[i], :] += src[i, :]  (rows unique).  Adds the compact IM gradient into the dense
  * gradient of the student FPN map. */
 int ldb200_scatter_add_rows(void* dst, const void* src, const int32_t* rows, const int32_t* n_rows_dev,

@@ -42,6 +42,9 @@ __device__ __forceinline__ float warp_integral(float z, bool active, int lane) {
   return warp_sum(active ? (float)lane * (e / S) : 0.f);
 }
 
+// RAW: LDv2Head.get_gi_region (ld_gflv2.py) compares the teacher's cls_feat LOGITS with the student's joint scores
+// without any sigmoid
+template <bool RAW>
 __global__ void __launch_bounds__(GI_THREADS) gi_score_kernel(GiParams P) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int R = P.pyr.off[P.pyr.L] * P.pyr.N;
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(GI_THREADS) gi_score_kernel(GiParams P) {
     float best = -1.f, bz = 0.f;
     int bidx = 0x7fffffff;
     for (int c = lane; c < P.C; c += 32) {
-      const float z = gi_sigmoid(__ldg(t + c)) - gi_sigmoid(__ldg(s + c));
+      const float z = RAW ? __ldg(t + c) - __ldg(s + c) : gi_sigmoid(__ldg(t + c)) - gi_sigmoid(__ldg(s + c));
       const float a = fabsf(z);
       if (a > best) { best = a; bidx = c; bz = z; }
     }
@@ -176,10 +179,9 @@ extern "C" size_t ldb200_gi_region_workspace_bytes(const ldb_pyramid* pyr, int t
          align_up((size_t)LDB_MAX_LEVELS * topk * sizeof(int), 256) + align_up(LDB_MAX_LEVELS * sizeof(int), 256);
 }
 
-extern "C" int ldb200_gi_region(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const float* cls, const float* reg,
-                                const float* t_cls, const float* t_reg, float iou_thr, int topk,
-                                const int32_t* counts_in, int32_t* gi_rows, int32_t* counts_out, void* workspace,
-                                void* stream_) {
+static int gi_region_impl(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const float* cls, const float* reg,
+                          const float* t_cls, const float* t_reg, float iou_thr, int topk, const int32_t* counts_in,
+                          int32_t* gi_rows, int32_t* counts_out, void* workspace, void* stream_, bool raw) {
   GiParams P;
   int e = make_pyr(pyr, &P.pyr);
   LDB_REQUIRE(e == 0, LDB_EINVAL, "gi_region: bad pyramid");
@@ -206,11 +208,29 @@ extern "C" int ldb200_gi_region(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg,
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   long long blocks = ((long long)R + GI_WARPS - 1) / GI_WARPS;
   if (blocks > 8LL * sms) blocks = 8LL * sms;
-  gi_score_kernel<<<(int)blocks, GI_THREADS, 0, stream>>>(P);
+  if (raw) gi_score_kernel<true><<<(int)blocks, GI_THREADS, 0, stream>>>(P);
+  else gi_score_kernel<false><<<(int)blocks, GI_THREADS, 0, stream>>>(P);
   LDB_CUDA(cudaGetLastError());
   gi_nms_kernel<<<P.pyr.L, NMS_THREADS, 0, stream>>>(P.pyr, P.score, P.box, P.flags, iou_thr, topk, lvl_rows, lvl_cnt);
   LDB_CUDA(cudaGetLastError());
   gi_finalize_kernel<<<1, 32, 0, stream>>>(P.pyr.L, topk, lvl_rows, lvl_cnt, counts_in, gi_rows, counts_out);
   LDB_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int ldb200_gi_region(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const float* cls, const float* reg,
+                                const float* t_cls, const float* t_reg, float iou_thr, int topk,
+                                const int32_t* counts_in, int32_t* gi_rows, int32_t* counts_out, void* workspace,
+                                void* stream_) {
+  return gi_region_impl(pyr, cfg, cls, reg, t_cls, t_reg, iou_thr, topk, counts_in, gi_rows, counts_out, workspace, stream_,
+                        false);
+}
+
+// LDv2Head.get_gi_region (ld_gflv2.py): `cls` = student joint scores, `t_cls` = teacher cls_feat logits, no sigmoid.
+extern "C" int ldb200_gi_region_v2(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const float* score, const float* reg,
+                                   const float* t_cls_feat, const float* t_reg, float iou_thr, int topk,
+                                   const int32_t* counts_in, int32_t* gi_rows, int32_t* counts_out, void* workspace,
+                                   void* stream_) {
+  return gi_region_impl(pyr, cfg, score, reg, t_cls_feat, t_reg, iou_thr, topk, counts_in, gi_rows, counts_out, workspace,
+                        stream_, true);
 }

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "v2_math.cuh"
 
 namespace ldb {
 
@@ -42,6 +43,11 @@ struct LossParams {
   int grad_bf16;
   float* score;  // prepass only (may be null)
   float* wsum;   // prepass only
+  // LDv2Head (ld_gflv2.py; V2 kernels only -- appended so that the layout seen by the V1 kernels is unchanged):
+  // `cls` then holds the joint scores sigmoid(cls_feat) * quality, `t_cls` the teacher's cls_feat logits
+  const float* cls_feat;   // [R, C] student cls_feat logits (KD term, ld_gflv2.py:242-246)
+  void* d_kd;              // [R, dcls_ld] gradient of the KD term w.r.t. cls_feat (zero-filled by the call)
+  int num_fg;              // foreground classes (bg_class_ind, ld_head.py:163); C = num_fg + 1 in the LDv2 configs
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -166,9 +172,16 @@ __device__ __forceinline__ float row_weight_target(const float* __restrict__ cls
   for (int c = lane; c < C; c += 32) m = fmaxf(m, cls_row[c]);
   return sigmoidf_(warp_max(m));  // max_c sigmoid(x_c) (ld_head.py:198-199), sigmoid is monotone
 }
+// LDv2: weight_targets = max_c joint score, no sigmoid (ld_gflv2.py:200-201)
+__device__ __forceinline__ float row_weight_target_prob(const float* __restrict__ score_row, int C, int lane) {
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, score_row[c]);
+  return warp_max(m);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Pre-pass: sum of weight_targets (and optional IoU score map) over the positive rows.
+template <bool V2>
 __global__ void __launch_bounds__(LOSS_THREADS) ld_prepass_kernel(LossParams P) {
   __shared__ float s_w[LOSS_WARPS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -177,9 +190,10 @@ __global__ void __launch_bounds__(LOSS_THREADS) ld_prepass_kernel(LossParams P) 
   for (int i = blockIdx.x * LOSS_WARPS + wid; i < n_sparse; i += gridDim.x * LOSS_WARPS) {
     const int r = P.sparse_rows[i];
     const int lab = P.labels[r];
-    if (lab < 0 || lab >= P.C) continue;
+    if (lab < 0 || lab >= (V2 ? P.num_fg : P.C)) continue;
     const RowGeom g = row_geom(P.pyr, r);
-    const float w = row_weight_target(P.cls + (size_t)r * P.C, P.C, lane);
+    const float w = V2 ? row_weight_target_prob(P.cls + (size_t)r * P.C, P.C, lane)
+                       : row_weight_target(P.cls + (size_t)r * P.C, P.C, lane);
     acc += w;
     if (P.score) {
       const bool active = lane < P.bins;
@@ -204,7 +218,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) ld_prepass_kernel(LossParams P) 
 
 // ---------------------------------------------------------------------------------------------
 // The fused loss kernel.
-template <typename GT, typename FT>
+template <typename GT, typename FT, bool V2>
 __global__ void __launch_bounds__(LOSS_THREADS, 3) ld_loss_fused_kernel(LossParams P) {
   __shared__ float s_loss[LDB_NUM_TERMS][LDB_MAX_LEVELS];
   __shared__ float s_red[LOSS_WARPS];
@@ -212,6 +226,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, 3) ld_loss_fused_kernel(LossPara
   for (int i = tid; i < LDB_NUM_TERMS * LDB_MAX_LEVELS; i += LOSS_THREADS) (&s_loss[0][0])[i] = 0.f;
   __syncthreads();
   const int C = P.C, bins = P.bins, N = P.pyr.N;
+  const int nfg = V2 ? P.num_fg : C;   // labels in [0, nfg) are positives (ld_head.py:163-165)
   const float nts = P.norm[0], avg = P.norm[1];
   const bool wg = P.want_grad != 0;
   GT* __restrict__ d_cls = (GT*)P.d_cls;
@@ -234,14 +249,21 @@ __global__ void __launch_bounds__(LOSS_THREADS, 3) ld_loss_fused_kernel(LossPara
            v += (long long)dense_blocks * LOSS_THREADS) {
         const int r = (int)(v / vpr);
         const int lab = __ldg(P.labels + r);
-        if (lab >= 0 && lab < C) continue;  // positive rows are owned by phase 2
+        if (lab >= 0 && lab < nfg) continue;  // positive rows are owned by phase 2
         const float sc = P.qfl_w * __ldg(P.label_w + r) / nts;
         const float4 xv = __ldg(reinterpret_cast<const float4*>(P.cls) + v);
         float lo[4], gr[4];
-        qfl_neg_fast(xv.x, P.beta, lo[0], gr[0]);
-        qfl_neg_fast(xv.y, P.beta, lo[1], gr[1]);
-        qfl_neg_fast(xv.z, P.beta, lo[2], gr[2]);
-        qfl_neg_fast(xv.w, P.beta, lo[3], gr[3]);
+        if (V2) {   // joint scores: BCE on probabilities (gfocal_loss.py:29-39, use_sigmoid=False)
+          qflp_neg(xv.x, P.beta, lo[0], gr[0]);
+          qflp_neg(xv.y, P.beta, lo[1], gr[1]);
+          qflp_neg(xv.z, P.beta, lo[2], gr[2]);
+          qflp_neg(xv.w, P.beta, lo[3], gr[3]);
+        } else {
+          qfl_neg_fast(xv.x, P.beta, lo[0], gr[0]);
+          qfl_neg_fast(xv.y, P.beta, lo[1], gr[1]);
+          qfl_neg_fast(xv.z, P.beta, lo[2], gr[2]);
+          qfl_neg_fast(xv.w, P.beta, lo[3], gr[3]);
+        }
         acc += sc * ((lo[0] + lo[1]) + (lo[2] + lo[3]));
         if (wg) {
           const float k = sc * gsc;
@@ -264,10 +286,11 @@ __global__ void __launch_bounds__(LOSS_THREADS, 3) ld_loss_fused_kernel(LossPara
            e += (long long)dense_blocks * LOSS_THREADS) {
         const int r = (int)(e / C);
         const int lab = __ldg(P.labels + r);
-        if (lab >= 0 && lab < C) continue;
+        if (lab >= 0 && lab < nfg) continue;
         const float sc = P.qfl_w * __ldg(P.label_w + r) / nts;
         float lo, gr;
-        qfl_neg(__ldg(P.cls + e), P.beta, lo, gr);
+        if (V2) qflp_neg(__ldg(P.cls + e), P.beta, lo, gr);
+        else qfl_neg(__ldg(P.cls + e), P.beta, lo, gr);
         acc += sc * lo;
         if (wg) store_grad<GT>(d_cls + (size_t)r * P.dcls_ld + (e - (long long)r * C), sc * gsc * gr);
       }
@@ -284,7 +307,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, 3) ld_loss_fused_kernel(LossPara
     const RowGeom g = row_geom(P.pyr, r);
     const int l = g.l;
     const int lab = P.labels[r];
-    const bool pos = lab >= 0 && lab < C;
+    const bool pos = lab >= 0 && lab < nfg;
     const float v = P.vlr[r];
     const float* reg_row = P.reg + (size_t)r * 4 * bins;
     const float* treg_row = P.t_reg + (size_t)r * 4 * bins;
@@ -298,7 +321,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, 3) ld_loss_fused_kernel(LossPara
     if (pos) {
       const float* cls_row = P.cls + (size_t)r * C;
       const float* tcls_row = P.t_cls + (size_t)r * C;
-      w = row_weight_target(cls_row, C, lane);
+      w = V2 ? row_weight_target_prob(cls_row, C, lane) : row_weight_target(cls_row, C, lane);
       BoxBranch b;
       decode_row(z, active, lane, g, P.bbox_t, r, (float)P.pyr.stride[l], b);
       float iou, lg, gb[4];
@@ -337,12 +360,14 @@ __global__ void __launch_bounds__(LOSS_THREADS, 3) ld_loss_fused_kernel(LossPara
       const int P_l = P.counts[4 + 3 * l + 0];
       const float k_kd = P.kd_w * P.label_w[r] / (float)P_l;
       const float invTk = 1.f / P.kd_T;
+      // V2: the KD logits are the student's cls_feat (ld_gflv2.py:243), QFL keeps reading the joint scores
+      const float* kd_row = V2 ? P.cls_feat + (size_t)r * C : cls_row;
       float xs[MAX_CPL], xt[MAX_CPL];
       float ms = -INFINITY, mt = -INFINITY;
 #pragma unroll
       for (int q = 0; q < MAX_CPL; ++q) {
         const int c = lane + 32 * q;
-        xs[q] = c < C ? cls_row[c] : -INFINITY;
+        xs[q] = c < C ? kd_row[c] : -INFINITY;
         xt[q] = c < C ? tcls_row[c] : -INFINITY;
         ms = fmaxf(ms, xs[q] * invTk);
         mt = fmaxf(mt, xt[q] * invTk);
@@ -372,12 +397,25 @@ __global__ void __launch_bounds__(LOSS_THREADS, 3) ld_loss_fused_kernel(LossPara
           const float ps = expf(lps), pt = expf(lpt);
           if (pt > 0.f) kl += pt * (lpt - lps);
           float lo, gr;
-          if (c == lab) qfl_pos(xs[q], y, P.beta, lo, gr);
-          else qfl_neg(xs[q], P.beta, lo, gr);
+          if (V2) {
+            const float pj = cls_row[c];
+            if (c == lab) qflp_pos(pj, y, P.beta, lo, gr);
+            else qflp_neg(pj, P.beta, lo, gr);
+          } else {
+            if (c == lab) qfl_pos(xs[q], y, P.beta, lo, gr);
+            else qfl_neg(xs[q], P.beta, lo, gr);
+          }
           qsum += lo;
-          if (wg)
-            store_grad<GT>(d_cls + (size_t)r * P.dcls_ld + c,
-                           P.tg[0][l] * k_cls * gr + P.tg[5][l] * k_kd * (P.kd_T / (float)C) * (ps - pt));
+          if (wg) {
+            if (V2) {
+              store_grad<GT>(d_cls + (size_t)r * P.dcls_ld + c, P.tg[0][l] * k_cls * gr);
+              store_grad<GT>((GT*)P.d_kd + (size_t)r * P.dcls_ld + c,
+                             P.tg[5][l] * k_kd * (P.kd_T / (float)C) * (ps - pt));
+            } else {
+              store_grad<GT>(d_cls + (size_t)r * P.dcls_ld + c,
+                             P.tg[0][l] * k_cls * gr + P.tg[5][l] * k_kd * (P.kd_T / (float)C) * (ps - pt));
+            }
+          }
         }
       }
       l_kd = k_kd * warp_sum(kl) * (P.kd_T * P.kd_T) / (float)C;
@@ -715,7 +753,7 @@ extern "C" int ldb200_ld_loss_prepass(const ldb_pyramid* pyr, const ldb_loss_cfg
   const size_t R = (size_t)P.pyr.N * P.pyr.off[P.pyr.L];
   if (score) LDB_CUDA(cudaMemsetAsync(score, 0, R * sizeof(float), stream));
   LDB_CUDA(cudaMemsetAsync(wsum, 0, sizeof(float), stream));
-  ld_prepass_kernel<<<num_sms(), LOSS_THREADS, 0, stream>>>(P);
+  ld_prepass_kernel<false><<<num_sms(), LOSS_THREADS, 0, stream>>>(P);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -760,10 +798,84 @@ extern "C" int ldb200_ld_loss_fused(const ldb_pyramid* pyr, const ldb_loss_cfg* 
   LDB_CUDA(cudaMemsetAsync(losses, 0, sizeof(float) * LDB_NUM_TERMS * LDB_MAX_LEVELS, stream));
   if (wg) LDB_CUDA(cudaMemsetAsync(d_reg, 0, R * P.dreg_ld * gsz, stream));
   const int grid = num_sms() * 3;
-  if (!P.grad_bf16 && !P.feat_bf16) ld_loss_fused_kernel<float, float><<<grid, LOSS_THREADS, 0, stream>>>(P);
-  else if (!P.grad_bf16 && P.feat_bf16) ld_loss_fused_kernel<float, __nv_bfloat16><<<grid, LOSS_THREADS, 0, stream>>>(P);
-  else if (P.grad_bf16 && !P.feat_bf16) ld_loss_fused_kernel<__nv_bfloat16, float><<<grid, LOSS_THREADS, 0, stream>>>(P);
-  else ld_loss_fused_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, LOSS_THREADS, 0, stream>>>(P);
+  if (!P.grad_bf16 && !P.feat_bf16) ld_loss_fused_kernel<float, float, false><<<grid, LOSS_THREADS, 0, stream>>>(P);
+  else if (!P.grad_bf16 && P.feat_bf16) ld_loss_fused_kernel<float, __nv_bfloat16, false><<<grid, LOSS_THREADS, 0, stream>>>(P);
+  else if (P.grad_bf16 && !P.feat_bf16) ld_loss_fused_kernel<__nv_bfloat16, float, false><<<grid, LOSS_THREADS, 0, stream>>>(P);
+  else ld_loss_fused_kernel<__nv_bfloat16, __nv_bfloat16, false><<<grid, LOSS_THREADS, 0, stream>>>(P);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- LDv2Head (ld_gflv2.py:116-375): same launches, V2 instantiations.  `score` = joint scores sigmoid(cls_feat) *
+// quality [R,C] (from ldb200_dgqp_forward), `cls_feat` / `t_cls_feat` = student / teacher class logits; C =
+// cfg->num_classes = cls_out_channels (num_fg + 1 when loss_cls.use_sigmoid=False), labels >= num_fg are background.
+extern "C" int ldb200_ld_loss_prepass_v2(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const float* score,
+                                         const float* reg, const int32_t* labels, const float* bbox_targets,
+                                         const int32_t* sparse_rows, const int32_t* counts, int num_fg,
+                                         float* iou_score, float* wsum, void* stream_) {
+  LossParams P;
+  int e = fill_params(pyr, cfg, &P);
+  if (e) return e;
+  LDB_REQUIRE(score && reg && labels && bbox_targets && sparse_rows && counts && wsum, LDB_EINVAL,
+              "ld_loss_prepass_v2: null pointer");
+  LDB_REQUIRE(num_fg >= 1 && num_fg <= P.C, LDB_EINVAL, "ld_loss_prepass_v2: num_fg");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  P.cls = score; P.reg = reg; P.labels = labels; P.bbox_t = bbox_targets;
+  P.sparse_rows = sparse_rows; P.counts = counts; P.score = iou_score; P.wsum = wsum;
+  P.cls_feat = nullptr; P.d_kd = nullptr; P.num_fg = num_fg;
+  const size_t R = (size_t)P.pyr.N * P.pyr.off[P.pyr.L];
+  if (iou_score) LDB_CUDA(cudaMemsetAsync(iou_score, 0, R * sizeof(float), stream));
+  LDB_CUDA(cudaMemsetAsync(wsum, 0, sizeof(float), stream));
+  ld_prepass_kernel<true><<<num_sms(), LOSS_THREADS, 0, stream>>>(P);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_ld_loss_fused_v2(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const float* score,
+                                       const float* cls_feat, const float* reg, const float* t_cls_feat,
+                                       const float* t_reg, const void* x, const void* t_x, int feat_dtype,
+                                       const int32_t* labels, const float* label_weights, const float* bbox_targets,
+                                       const float* vlr, const int32_t* sparse_rows, const int32_t* fg_rows,
+                                       const int32_t* counts, const float* norm, const float* term_grad_host,
+                                       int num_fg, float* losses, void* d_score, void* d_kd, void* d_reg, void* d_im,
+                                       int d_cls_ld, int d_reg_ld, int grad_dtype, void* stream_) {
+  LossParams P;
+  int e = fill_params(pyr, cfg, &P);
+  if (e) return e;
+  LDB_REQUIRE(score && cls_feat && reg && t_cls_feat && t_reg && x && t_x && labels && label_weights && bbox_targets &&
+              vlr && sparse_rows && fg_rows && counts && norm && losses, LDB_EINVAL, "ld_loss_fused_v2: null pointer");
+  LDB_REQUIRE(num_fg >= 1 && num_fg <= P.C, LDB_EINVAL, "ld_loss_fused_v2: num_fg");
+  LDB_REQUIRE(feat_dtype == LDB_F32 || feat_dtype == LDB_BF16, LDB_EINVAL, "ld_loss_fused_v2: feat_dtype");
+  LDB_REQUIRE(grad_dtype == LDB_F32 || grad_dtype == LDB_BF16, LDB_EINVAL, "ld_loss_fused_v2: grad_dtype");
+  const bool wg = term_grad_host != nullptr;
+  if (wg) LDB_REQUIRE(d_score && d_kd && d_reg && d_im, LDB_EINVAL, "ld_loss_fused_v2: gradients requested but null outputs");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  P.cls = score; P.reg = reg; P.t_cls = t_cls_feat; P.t_reg = t_reg; P.x = x; P.t_x = t_x;
+  P.cls_feat = cls_feat; P.d_kd = d_kd; P.num_fg = num_fg;
+  P.feat_bf16 = feat_dtype == LDB_BF16;
+  P.labels = labels; P.label_w = label_weights; P.bbox_t = bbox_targets; P.vlr = vlr;
+  P.sparse_rows = sparse_rows; P.fg_rows = fg_rows; P.counts = counts; P.norm = norm;
+  P.want_grad = wg ? 1 : 0;
+  P.phases = 7;
+  if (wg) memcpy(P.tg, term_grad_host, sizeof(P.tg));
+  P.losses = losses; P.d_cls = d_score; P.d_reg = d_reg; P.d_im = d_im;
+  P.grad_bf16 = grad_dtype == LDB_BF16;
+  P.dcls_ld = d_cls_ld > 0 ? d_cls_ld : P.C;
+  P.dreg_ld = d_reg_ld > 0 ? d_reg_ld : 4 * P.bins;
+  LDB_REQUIRE(P.dcls_ld >= P.C && P.dreg_ld >= 4 * P.bins && P.dcls_ld % 4 == 0, LDB_EINVAL,
+              "ld_loss_fused_v2: gradient leading dimensions");
+  const size_t R = (size_t)P.pyr.N * P.pyr.off[P.pyr.L];
+  const size_t gsz = P.grad_bf16 ? 2 : 4;
+  LDB_CUDA(cudaMemsetAsync(losses, 0, sizeof(float) * LDB_NUM_TERMS * LDB_MAX_LEVELS, stream));
+  if (wg) {
+    LDB_CUDA(cudaMemsetAsync(d_reg, 0, R * P.dreg_ld * gsz, stream));
+    LDB_CUDA(cudaMemsetAsync(d_kd, 0, R * P.dcls_ld * gsz, stream));
+  }
+  const int grid = num_sms() * 3;
+  if (!P.grad_bf16 && !P.feat_bf16) ld_loss_fused_kernel<float, float, true><<<grid, LOSS_THREADS, 0, stream>>>(P);
+  else if (!P.grad_bf16 && P.feat_bf16) ld_loss_fused_kernel<float, __nv_bfloat16, true><<<grid, LOSS_THREADS, 0, stream>>>(P);
+  else if (P.grad_bf16 && !P.feat_bf16) ld_loss_fused_kernel<__nv_bfloat16, float, true><<<grid, LOSS_THREADS, 0, stream>>>(P);
+  else ld_loss_fused_kernel<__nv_bfloat16, __nv_bfloat16, true><<<grid, LOSS_THREADS, 0, stream>>>(P);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }

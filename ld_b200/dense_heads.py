@@ -325,8 +325,9 @@ class LDHead(GFLHead):
         if type(self.loss_bbox).__name__ != 'GIoULoss' or type(self.loss_cls).__name__ != 'QualityFocalLoss':
             raise NotImplementedError('the fused LD loss kernel implements QualityFocalLoss + GIoULoss '
                                       '(every configs/ld/*gflv1* file)')
-        if not self.loss_cls.use_sigmoid:
-            raise NotImplementedError('QualityFocalLoss(use_sigmoid=False) (LDv2 configs) is not implemented yet')
+        if self.loss_cls.use_sigmoid == self._qfl_on_scores:
+            raise NotImplementedError(f'{type(self).__name__} needs QualityFocalLoss(use_sigmoid='
+                                      f'{not self._qfl_on_scores}) (LDHead: logits, LDv2Head: joint scores)')
         return ops.make_loss_cfg(
             num_classes=self.cls_out_channels, reg_max=self.reg_max, feat_channels=self.in_channels,
             qfl_weight=self.loss_cls.loss_weight, qfl_beta=self.loss_cls.beta,
@@ -336,6 +337,7 @@ class LDHead(GFLHead):
             kd_weight=self.loss_kd.loss_weight, kd_T=self.loss_kd.T, im_weight=self.loss_im.loss_weight)
 
     _static_targets = None   # set by LDTrainStep.capture(): targets are produced outside the CUDA graph
+    _qfl_on_scores = False   # LDv2Head: QFL runs on joint scores (use_sigmoid=False)
 
     def get_targets(self, featmap_sizes, img_metas, gt_bboxes, gt_labels, device, static=True):
         """ld_head.py:377-447 for the whole batch in one call (row space)."""
@@ -475,20 +477,66 @@ class GFocalHead(GFLHead):
 
 
 @HEADS.register_module()
-class LDv2Head(GFocalHead):
-    """ld_gflv2.py:43-71: GFocalHead + the LD / VLR-LD / KD / IM losses (constructor identical to LDHead's)."""
+class LDv2Head(LDHead, GFocalHead):
+    """ld_gflv2.py:43-71: GFocalHead + the LD / VLR-LD / KD / IM losses.  MRO LDv2Head -> LDHead -> GFocalHead ->
+    GFLHead: the constructor signature, target assignment and loss configuration are LDHead's, the layers
+    GFocalHead's."""
+    _qfl_on_scores = True
 
-    def __init__(self, num_classes, in_channels,
-                 loss_ld=dict(type='KnowledgeDistillationKLDivLoss', loss_weight=0.25, T=10),
-                 loss_ld_vlr=dict(type='KnowledgeDistillationKLDivLoss', loss_weight=0.25, T=10),
-                 loss_kd=dict(type='KnowledgeDistillationKLDivLoss', loss_weight=10, T=2),
-                 loss_im=dict(type='IMLoss', loss_weight=0), imitation_method='gibox', **kwargs):
-        super().__init__(num_classes, in_channels, **kwargs)
-        self.imitation_method = imitation_method
-        self.gi_iou_thr, self.gi_topk = 0.3, 10
-        self.loss_im = build_loss(loss_im)
-        self.loss_ld = build_loss(loss_ld)
-        self.loss_ld_vlr = build_loss(loss_ld_vlr)
-        self.loss_kd = build_loss(loss_kd)
-        from .registry import build_iou_calculator
-        self.iou_calculator = build_iou_calculator(dict(type='BboxOverlaps2D'))
+    def forward_train(self, *args, **kwargs):
+        return GFocalHead.forward_train(self, *args, **kwargs)
+
+    forward = forward_train
+
+    def loss(self, cls_scores, bbox_preds, cls_feat, gt_bboxes, gt_labels, soft_teacher, x, teacher_x, img_metas,
+             gt_bboxes_ignore=None):
+        """ld_gflv2.py:286-375 on given head outputs: `cls_scores` = joint scores sigmoid(cls_feat) * quality,
+        `soft_teacher` = (teacher joint scores [unused, ld_gflv2.py:327], teacher bbox_preds, teacher cls_feat)."""
+        sizes = [tuple(f.shape[2:]) for f in cls_scores]
+        dev = cls_scores[0].device
+        tg = self.get_targets(sizes, img_metas, gt_bboxes, gt_labels, dev)
+        _, soft_target, soft_label = soft_teacher
+        nl = len(sizes)
+        losses = _LossOnlyV2Fn.apply(self, tg, nl, *cls_scores, *bbox_preds, *cls_feat, *x, *soft_label, *soft_target,
+                                     *teacher_x)
+        return {k: [losses[i, l] for l in range(nl)] for i, k in enumerate(ops.TERMS)}
+
+
+class _LossOnlyV2Fn(torch.autograd.Function):
+    """`LDv2Head.loss` through ldb200_ld_loss_prepass_v2 / _gi_region_v2 / _ld_loss_fused_v2 (fp32 gradients)."""
+
+    @staticmethod
+    def forward(ctx, head, tg, nl, *t):
+        score, reg, feat, xs, t_feat, t_reg, t_x = (t[i * nl:(i + 1) * nl] for i in range(7))
+        cfg = head.loss_cfg()
+        nfg = head.num_classes
+        rows = [ops.to_rows([v.detach().float() for v in grp]) for grp in (score, reg, feat, t_feat, t_reg)]
+        xr = ops.to_rows([v.detach() for v in xs])
+        txr = ops.to_rows([v.detach() for v in t_x]).to(xr.dtype)
+        if xr.dtype not in (torch.float32, torch.bfloat16):
+            xr, txr = xr.float(), txr.float()
+        wsum, _ = ops.ld_loss_prepass_v2(cfg, rows[0], rows[1], tg, nfg)
+        norm = ops.loss_normalisers(tg, wsum)
+        tg_im, max_fg = tg, None
+        if head.imitation_method == 'gibox' and head.loss_im.loss_weight != 0:
+            gi_rows, gi_counts = ops.gi_region_v2(cfg, rows[0], rows[1], rows[3], rows[4], tg, iou_thr=head.gi_iou_thr,
+                                                  topk=head.gi_topk)
+            tg_im, max_fg = dataclasses.replace(tg, fg_rows=gi_rows, counts=gi_counts), gi_rows.numel()
+        head._last_im_targets = tg_im
+        losses, d_score, d_kd, d_reg, d_im = ops.ld_loss_fused_v2(
+            cfg, rows[0], rows[2], rows[1], rows[3], rows[4], xr, txr, tg_im, norm, nfg, term_grad=True,
+            grad_dtype=torch.float32, max_fg=max_fg)
+        d_x = torch.zeros(tg.pyr.rows, xr.shape[1], dtype=torch.float32, device=xr.device)
+        ops.scatter_add_rows(d_x, d_im, tg_im.fg_rows, tg_im.counts[1:2])
+        C = cfg.num_classes
+        ctx.pyr, ctx.nl = tg.pyr, nl
+        ctx.save_for_backward(d_score[:, :C].contiguous(), d_reg, d_kd[:, :C].contiguous(), d_x)
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        out = [None, None, None]
+        for d in ctx.saved_tensors:      # order of the inputs: scores, bbox_preds, cls_feat, x
+            out += [v for v in ops.from_rows(d, ctx.pyr)]
+        out += [None] * (3 * ctx.nl)
+        return tuple(out)

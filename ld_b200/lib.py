@@ -79,6 +79,12 @@ _SIGS = {
     'ldb200_ld_loss_fused': (C.c_int, [C.POINTER(Pyramid), C.POINTER(LossCfg)] + [C.c_void_p] * 6 +
                              [C.c_int] + [C.c_void_p] * 9 + [C.c_void_p] + [C.c_void_p] * 4 +
                              [C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ldb200_ld_loss_prepass_v2': (C.c_int, [C.POINTER(Pyramid), C.POINTER(LossCfg)] + [C.c_void_p] * 6 + [C.c_int]
+                                  + [C.c_void_p] * 3),
+    'ldb200_ld_loss_fused_v2': (C.c_int, [C.POINTER(Pyramid), C.POINTER(LossCfg)] + [C.c_void_p] * 7 + [C.c_int]
+                                + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ldb200_gi_region_v2': (C.c_int, [C.POINTER(Pyramid), C.POINTER(LossCfg)] + [C.c_void_p] * 4 + [C.c_float, C.c_int]
+                            + [C.c_void_p] * 5),
     'ldb200_gi_region_workspace_bytes': (C.c_size_t, [C.POINTER(Pyramid), C.c_int]),
     'ldb200_gi_region': (C.c_int, [C.POINTER(Pyramid), C.POINTER(LossCfg)] + [C.c_void_p] * 4 + [C.c_float, C.c_int]
                          + [C.c_void_p] * 5),
@@ -138,7 +144,8 @@ def load():
 # kernels launched by one call of each entry point (memsets not counted); `launch_count` is what
 # bench.py reports as "gpu_launches"
 _LAUNCHES = {'ldb200_ld_targets': 3, 'ldb200_ld_loss_prepass': 1, 'ldb200_ld_loss_fused': 1,
-             'ldb200_scatter_add_rows': 1, 'ldb200_gi_region': 3, 'ldb200_dgqp_forward': 1, 'ldb200_dgqp_backward': 1, 'ldb200_conv2d_tc': 1, 'ldb200_conv2d_tc_multi': 1, 'ldb200_conv2d_wgrad_tc': 1,
+             'ldb200_scatter_add_rows': 1, 'ldb200_gi_region': 3, 'ldb200_gi_region_v2': 3, 'ldb200_ld_loss_prepass_v2': 1,
+             'ldb200_ld_loss_fused_v2': 1, 'ldb200_dgqp_forward': 1, 'ldb200_dgqp_backward': 1, 'ldb200_conv2d_tc': 1, 'ldb200_conv2d_tc_multi': 1, 'ldb200_conv2d_wgrad_tc': 1,
              'ldb200_stem_im2col': 1, 'ldb200_maxpool3x3s2': 1, 'ldb200_gn_stats': 1, 'ldb200_gn_apply': 1,
              'ldb200_gn_relu_bwd': 2, 'ldb200_upsample_add_bwd': 1, 'ldb200_relu_bwd': 1, 'ldb200_colsum': 1,
              'ldb200_sgd_flat': 1, 'ldb200_sgd_flat_dev': 1, 'ldb200_bn_fold': 1, 'ldb200_bn_fold_bwd': 1, 'ldb200_mse_fwd_bwd': 1, 'ldb200_kl_dense_fwd_bwd': 1}

@@ -213,6 +213,66 @@ def dgqp_backward(reg, cls_feat, W1, b1, W2, b2, quality, d_score, d_reg, d_kd=N
     return d_cls_feat, dW1, db1, dW2, db2
 
 
+# ---- LDv2Head (ld_gflv2.py) -------------------------------------------------------------
+def ld_loss_prepass_v2(cfg: L.LossCfg, score, reg, tg: LDTargets, num_fg, want_score=False):
+    """`ld_loss_prepass` on joint scores (weight_targets = max_c score, ld_gflv2.py:200)."""
+    lib = L.load()
+    wsum = torch.empty(1, dtype=torch.float32, device=score.device)
+    iou = torch.empty(tg.pyr.rows, dtype=torch.float32, device=score.device) if want_score else None
+    L.check(lib.ldb200_ld_loss_prepass_v2(C.byref(tg.pyr), C.byref(cfg), L.ptr(score), L.ptr(reg), L.ptr(tg.labels),
+                                          L.ptr(tg.bbox_targets), L.ptr(tg.sparse_rows), L.ptr(tg.counts), int(num_fg),
+                                          L.ptr(iou), L.ptr(wsum), L.stream_ptr()), 'ldb200_ld_loss_prepass_v2')
+    return wsum, iou
+
+
+def ld_loss_fused_v2(cfg: L.LossCfg, score, cls_feat, reg, t_cls_feat, t_reg, x, t_x, tg: LDTargets, norm, num_fg,
+                     term_grad=None, grad_dtype=torch.float32, max_fg=None, d_cls_ld=0, d_reg_ld=0):
+    """`LDv2Head.loss_single` x L in one launch: -> (losses, d_score, d_kd, d_reg, d_im); d_score is the gradient
+    w.r.t. the joint score, d_kd the KD term's gradient w.r.t. cls_feat (both feed `dgqp_backward`)."""
+    lib = L.load()
+    dev = score.device
+    R = tg.pyr.rows
+    assert score.shape == cls_feat.shape == t_cls_feat.shape == (R, cfg.num_classes)
+    assert reg.shape == t_reg.shape == (R, 4 * (cfg.reg_max + 1))
+    assert x.dtype == t_x.dtype and x.shape == t_x.shape == (R, cfg.feat_channels)
+    losses = torch.empty(L.NUM_TERMS, L.MAX_LEVELS, dtype=torch.float32, device=dev)
+    d_score = d_kd = d_reg = d_im = None
+    tgp = None
+    if term_grad is not None:
+        if term_grad is True:
+            term_grad = torch.ones(L.NUM_TERMS - 1, L.MAX_LEVELS)
+        tgh = term_grad.detach().to('cpu', torch.float32).contiguous()
+        tgp = C.c_void_p(tgh.data_ptr())
+        max_fg = R if max_fg is None else max_fg
+        ld = d_cls_ld or (cfg.num_classes + 3) // 4 * 4
+        d_cls_ld = ld
+        d_score = torch.zeros(R, ld, dtype=grad_dtype, device=dev)    # padding columns stay zero
+        d_kd = torch.empty(R, ld, dtype=grad_dtype, device=dev)
+        d_reg = torch.empty(R, d_reg_ld or 4 * (cfg.reg_max + 1), dtype=grad_dtype, device=dev)
+        d_im = torch.empty(max_fg, cfg.feat_channels, dtype=grad_dtype, device=dev)
+    L.check(lib.ldb200_ld_loss_fused_v2(C.byref(tg.pyr), C.byref(cfg), L.ptr(score), L.ptr(cls_feat), L.ptr(reg),
+                                        L.ptr(t_cls_feat), L.ptr(t_reg), L.ptr(x), L.ptr(t_x), _dt(x.dtype),
+                                        L.ptr(tg.labels), L.ptr(tg.label_weights), L.ptr(tg.bbox_targets), L.ptr(tg.vlr),
+                                        L.ptr(tg.sparse_rows), L.ptr(tg.fg_rows), L.ptr(tg.counts), L.ptr(norm), tgp,
+                                        int(num_fg), L.ptr(losses), L.ptr(d_score), L.ptr(d_kd), L.ptr(d_reg), L.ptr(d_im),
+                                        int(d_cls_ld), int(d_reg_ld), _dt(grad_dtype), L.stream_ptr()),
+            'ldb200_ld_loss_fused_v2')
+    return losses, d_score, d_kd, d_reg, d_im
+
+
+def gi_region_v2(cfg: L.LossCfg, score, reg, t_cls_feat, t_reg, tg: LDTargets, iou_thr=0.3, topk=10):
+    """`LDv2Head.get_gi_region`: GI score |teacher cls_feat - student joint score|, no sigmoid (ldb200_gi_region_v2)."""
+    lib = L.load()
+    dev = score.device
+    ws = torch.empty(int(lib.ldb200_gi_region_workspace_bytes(C.byref(tg.pyr), int(topk))), dtype=torch.uint8, device=dev)
+    gi_rows = torch.empty(tg.pyr.num_levels * topk, dtype=torch.int32, device=dev)
+    counts = torch.empty_like(tg.counts)
+    L.check(lib.ldb200_gi_region_v2(C.byref(tg.pyr), C.byref(cfg), L.ptr(score), L.ptr(reg), L.ptr(t_cls_feat),
+                                    L.ptr(t_reg), float(iou_thr), int(topk), L.ptr(tg.counts), L.ptr(gi_rows),
+                                    L.ptr(counts), L.ptr(ws), L.stream_ptr()), 'ldb200_gi_region_v2')
+    return gi_rows, counts
+
+
 def scatter_add_rows(dst, src, rows, n_rows_dev, max_rows=None):
     lib = L.load()
     max_rows = src.shape[0] if max_rows is None else max_rows

@@ -74,3 +74,59 @@ def test_dgqp_backward_bf16_grads():
     assert float((d_reg16[:, :68].float() - d_reg32[:, :68]).abs().max()) <= 2e-2 * float(d_reg32.abs().max()) + 1e-6
     for a, b in zip(out16[1:], out32[1:]):
         assert float((a - b).abs().max()) <= 2e-2 * float(b.abs().max()) + 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# LDv2Head.loss through the V2 loss kernels against the unmodified reference (tests/golden/l2_*.pt)
+def make_v2_head():
+    import ld_b200
+    from ld_b200 import presets
+    from ld_b200.config import ConfigDict
+    cfg = ConfigDict(presets.ld_model('r50'))
+    head_cfg = cfg.bbox_head
+    # configs/ldv2/ld_r50_gflv2_r101_fpn_1x.py:27-56
+    head_cfg.update(type='LDv2Head', reg_topk=4, reg_channels=64, add_mean=True, imitation_method='gibox',
+                    loss_cls=dict(type='QualityFocalLoss', use_sigmoid=False, beta=2.0, loss_weight=1.0),
+                    loss_im=dict(type='IMLoss', loss_weight=2))
+    head_cfg['train_cfg'] = cfg.train_cfg
+    head_cfg['test_cfg'] = cfg.test_cfg
+    return ld_b200.build_head(head_cfg).cuda().train()
+
+
+def test_ldv2_head_loss_api_matches_reference(golden_dir):
+    import os
+    from oracle import cases
+    for name, n, h, w, seed in cases.LOSS_CASES_V2:
+        gold = torch.load(os.path.join(golden_dir, name + '.pt'), weights_only=False)
+        d = cases.loss_case_inputs_v2(n, h, w, seed)
+        head = make_v2_head()
+        dev = torch.device('cuda')
+        leaves = {k: [t.to(dev).requires_grad_(True) for t in d[k]] for k in ('score', 'cls_feat', 'reg', 'x')}
+        losses = head.loss(leaves['score'], leaves['reg'], leaves['cls_feat'], [b.to(dev) for b in d['gt_bboxes']],
+                           [b.to(dev) for b in d['gt_labels']],
+                           (None, [t.to(dev) for t in d['t_reg']], [t.to(dev) for t in d['t_cls']]),
+                           leaves['x'], [t.to(dev) for t in d['t_x']], d['img_metas'])
+        sum(sum(v) for v in losses.values()).backward()
+        torch.cuda.synchronize()
+        tg = head._last_im_targets
+        counts, rows = tg.counts.cpu(), tg.fg_rows.cpu()
+        o = 0
+        for l, want in enumerate(gold['gi_idx']):
+            c = int(counts[4 + 3 * l + 2])
+            r0 = sum(tg.pyr.level_anchors[:l]) * n
+            assert c == want.numel() and torch.equal(rows[o:o + c] - r0, want), (name, l)
+            o += c
+        for k, v in gold['losses'].items():
+            got = torch.stack([t.detach().cpu() for t in losses[k]])
+            assert torch.allclose(got, v, rtol=1e-4, atol=1e-6), (name, k, got, v)
+
+        def g(t):
+            return torch.zeros_like(t) if t.grad is None else t.grad
+        for l in range(5):
+            for key, gk in (('score', 'grad_score'), ('reg', 'grad_reg')):
+                got, ref = g(leaves[key][l]).cpu(), gold[gk][l]
+                assert float((got - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-9, (name, key, l)
+            ref = gold['grad_cls_feat_rowsum'][l]
+            assert float((g(leaves['cls_feat'][l]).cpu().sum(1) - ref).abs().max()) <= 2e-4 * max(float(ref.abs().max()), 1e-6)
+            ref = gold['grad_x_rowsum'][l]
+            assert float((g(leaves['x'][l]).cpu().sum(1) - ref).abs().max()) <= 2e-4 * max(float(ref.abs().max()), 1e-6)
