@@ -469,11 +469,24 @@ class GFocalHead(GFLHead):
         c0, c2 = self.reg_conf[0], self.reg_conf[2]
         return (c0.weight.reshape(self.reg_channels, -1), c0.bias, c2.weight.reshape(-1), c2.bias)
 
-    def forward_train(self, *args, **kwargs):
-        raise NotImplementedError('GFocalHead/LDv2Head training: the fused LDv2 loss launch is not built yet '
-                                  '(SURVEY.md §8 a23; kernels so far: ldb200_dgqp_forward/_backward, ldb200_gi_region)')
+    def forward(self, feats, with_scores=False):
+        """gfocal_head.py:164-217 -> (cls_scores, bbox_preds, cls_feats) as lists of NCHW-shaped fp32 level tensors
+        (inference-style, no autograd).  The joint scores cost one more launch and the LDv2 teacher's are never read
+        (ld_gflv2.py:327), so they are None unless `with_scores`."""
+        with torch.no_grad():
+            feat_rows, reg_rows, sizes = self.alloc_rows(feats)
+            self.final_convs(self.towers(feats), feat_rows, reg_rows)
+            pyr = L.Pyramid.make(feats[0].shape[0], sizes, [s[0] for s in self.anchor_generator.strides])
+            scores = None
+            if with_scores:
+                w1, b1, w2, b2 = [t.detach().float().contiguous() for t in self.quality_params()]
+                _, score_rows = ops.dgqp_forward(reg_rows, feat_rows, w1, b1, w2, b2, self.reg_topk, self.add_mean)
+                scores = ops.from_rows(score_rows, pyr)
+        return scores, ops.from_rows(reg_rows, pyr), ops.from_rows(feat_rows, pyr)
 
-    forward = forward_train
+    def forward_train(self, *args, **kwargs):
+        raise NotImplementedError('plain GFLv2 training (GFocalHead.loss, gfocal_head.py:262-352) is not part of the LD '
+                                  'hot path; LDv2Head.forward_train is')
 
 
 @HEADS.register_module()
@@ -483,10 +496,35 @@ class LDv2Head(LDHead, GFocalHead):
     GFocalHead's."""
     _qfl_on_scores = True
 
-    def forward_train(self, *args, **kwargs):
-        return GFocalHead.forward_train(self, *args, **kwargs)
+    forward = GFocalHead.forward
 
-    forward = forward_train
+    def forward_train(self, x, out_teacher, teacher_x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None,
+                      proposal_cfg=None, **kwargs):
+        """ld_gflv2.py:73-114: out_teacher = GFocalHead.forward(teacher_x) = (scores [unused], bbox_preds, cls_feats)."""
+        assert (gt_labels is not None or self._static_targets is not None) and proposal_cfg is None
+        if gt_bboxes_ignore is not None and any(g is not None and g.numel() for g in gt_bboxes_ignore):
+            raise NotImplementedError('gt_bboxes_ignore (ignore_iof_thr=-1 in all LD configs)')
+        sizes = [tuple(f.shape[2:]) for f in x]
+        assert len(sizes) == self.anchor_generator.num_levels
+        tg = self.get_targets(sizes, img_metas, gt_bboxes, gt_labels, x[0].device)
+        _, t_reg, t_feat = out_teacher
+        aux = dict(num_levels=len(sizes), pyr=tg.pyr, targets=tg, loss_cfg=self.loss_cfg(),
+                   t_cls_rows=rows_of([t.detach() for t in t_feat]).float(),
+                   t_reg_rows=rows_of([t.detach() for t in t_reg]).float(),
+                   t_x_rows=rows_of([t.detach() for t in teacher_x]),
+                   term_grad=True, im_active=self.loss_im.loss_weight != 0)
+        tow = self.towers(x)
+        xs = [nhwc(f) for f in x]
+        if aux['t_x_rows'].dtype != xs[0].dtype:
+            aux['t_x_rows'] = aux['t_x_rows'].to(xs[0].dtype)
+        c0, c2 = self.reg_conf[0], self.reg_conf[2]
+        args = [t[0] for t in tow] + [t[1] for t in tow] + xs + \
+               [self.gfl_cls._cl(), self.gfl_cls.bias, self.gfl_reg._cl(), self.gfl_reg.bias] + \
+               [s.scale for s in self.scales] + [c0.weight, c0.bias, c2.weight, c2.bias]
+        losses, norm = _LDv2LossFn.apply(self, aux, *args)
+        self._last_aux = aux
+        nl = len(sizes)
+        return {k: [losses[i, l] for l in range(nl)] for i, k in enumerate(ops.TERMS)}
 
     def loss(self, cls_scores, bbox_preds, cls_feat, gt_bboxes, gt_labels, soft_teacher, x, teacher_x, img_metas,
              gt_bboxes_ignore=None):
@@ -540,3 +578,107 @@ class _LossOnlyV2Fn(torch.autograd.Function):
             out += [v for v in ops.from_rows(d, ctx.pyr)]
         out += [None] * (3 * ctx.nl)
         return tuple(out)
+
+
+class _LDv2LossFn(torch.autograd.Function):
+    """`_LDLossFn` for LDv2Head: gfl_cls / gfl_reg output convs + DGQP quality branch (ldb200_dgqp_forward) +
+    LDv2Head.loss (V2 prepass / GI region / fused loss) forward, and the whole gradient in the same pass: the fused
+    kernel emits d_score / d_kd / d_reg / d_x, ldb200_dgqp_backward folds the quality branch back into d_cls_feat and
+    d_reg and produces the reg_conf parameter gradients; `backward` hands them to the output convs' wgrad / dgrad.
+
+    inputs: as `_LDLossFn` plus the four reg_conf tensors (conv1x1 weight/bias twice).  NOT yet run on a GPU."""
+
+    @staticmethod
+    def forward(ctx, head, aux, *tensors):
+        nl = aux['num_levels']
+        cls_feats, reg_feats, xs = tensors[:nl], tensors[nl:2 * nl], tensors[2 * nl:3 * nl]
+        scales = tensors[3 * nl + 4:4 * nl + 4]
+        q_w1, q_b1, q_w2, q_b2 = tensors[4 * nl + 4:]
+        dev = cls_feats[0].device
+        C, NB, nfg = head.cls_out_channels, 4 * (head.reg_max + 1), head.num_classes
+        x_rows = rows_of([nchw_view(x.detach()) for x in xs])
+        pyr = aux['pyr']
+        R = pyr.rows
+        feat_rows = torch.empty(R, C, dtype=torch.float32, device=dev)     # cls_feat logits
+        reg_rows = torch.empty(R, NB, dtype=torch.float32, device=dev)
+        head.final_convs(list(zip(cls_feats, reg_feats)), feat_rows, reg_rows)
+        qp = [q_w1.detach().float().reshape(head.reg_channels, -1).contiguous(), q_b1.detach().float().contiguous(),
+              q_w2.detach().float().reshape(-1).contiguous(), q_b2.detach().float().contiguous()]
+        quality, score_rows = ops.dgqp_forward(reg_rows, feat_rows, *qp, reg_topk=head.reg_topk, add_mean=head.add_mean)
+        tg = aux['targets']
+        cfg = aux['loss_cfg']
+        wsum, _ = ops.ld_loss_prepass_v2(cfg, score_rows, reg_rows, tg, nfg)
+        norm = ops.loss_normalisers(tg, wsum)
+        dcls_ld, dreg_ld = (C + 7) // 8 * 8, (NB + 7) // 8 * 8
+        tg_im, max_fg = tg, aux.get('max_fg')
+        if head.imitation_method == 'gibox' and aux['im_active']:
+            gi_rows, gi_counts = ops.gi_region_v2(cfg, score_rows, reg_rows, aux['t_cls_rows'], aux['t_reg_rows'], tg,
+                                                  iou_thr=head.gi_iou_thr, topk=head.gi_topk)
+            tg_im = dataclasses.replace(tg, fg_rows=gi_rows, counts=gi_counts)
+            max_fg = gi_rows.numel()
+        aux['targets_im'] = tg_im
+        losses, d_score, d_kd, d_reg, d_im = ops.ld_loss_fused_v2(
+            cfg, score_rows, feat_rows, reg_rows, aux['t_cls_rows'], aux['t_reg_rows'], x_rows, aux['t_x_rows'], tg_im,
+            norm, nfg, term_grad=aux['term_grad'], grad_dtype=torch.bfloat16, max_fg=max_fg, d_cls_ld=dcls_ld,
+            d_reg_ld=dreg_ld)
+        d_feat, g_w1, g_b1, g_w2, g_b2 = ops.dgqp_backward(reg_rows, feat_rows, *qp, quality, d_score, d_reg, d_kd=d_kd,
+                                                           reg_topk=head.reg_topk, add_mean=head.add_mean)
+        ctx.head, ctx.aux = head, aux
+        ctx.q_shapes = (tuple(q_w1.shape), tuple(q_w2.shape))
+        ctx.save_for_backward(*tensors, feat_rows, reg_rows, d_feat, d_reg, d_im, g_w1, g_b1, g_w2, g_b2)
+        ctx.mark_non_differentiable(norm)
+        aux['cls_rows'], aux['reg_rows'], aux['score_rows'] = feat_rows, reg_rows, score_rows
+        return losses, norm
+
+    @staticmethod
+    def backward(ctx, g_losses, _g_norm):
+        head, aux = ctx.head, ctx.aux
+        nl = aux['num_levels']
+        saved = ctx.saved_tensors
+        tensors, (feat_rows, reg_rows, d_cls, d_reg, d_im, g_w1, g_b1, g_w2, g_b2) = saved[:-9], saved[-9:]
+        cls_feats, reg_feats, xs = tensors[:nl], tensors[nl:2 * nl], tensors[2 * nl:3 * nl]
+        w_cls, b_cls, w_reg, b_reg = tensors[3 * nl:3 * nl + 4]
+        scales = tensors[3 * nl + 4:4 * nl + 4]
+        C, NB = head.cls_out_channels, 4 * (head.reg_max + 1)
+        tg = aux['targets']
+        dev = d_cls.device
+        g_bc = torch.zeros(d_cls.shape[1], dtype=torch.float32, device=dev)
+        ops.colsum(d_cls, g_bc)
+        g_bc = g_bc[:C]
+        ci = w_cls.shape[1]
+        Gc = torch.zeros(C, 9 * ci, dtype=torch.float32, device=dev)
+        g_wr = torch.zeros(NB, 9 * ci, dtype=torch.float32, device=dev)
+        g_br = torch.zeros(NB, dtype=torch.float32, device=dev)
+        g_scales, g_cf, g_rf, g_x = [], [], [], []
+        o = 0
+        x_dense = None
+        if aux['im_active']:
+            x_dense = torch.zeros(tg.pyr.rows, xs[0].shape[-1], dtype=torch.bfloat16, device=dev)
+            tg_im = aux['targets_im']
+            ops.scatter_add_rows(x_dense, d_im, tg_im.fg_rows, tg_im.counts[1:2])
+        for l in range(nl):
+            n, h, w, _ = cls_feats[l].shape
+            cnt = n * h * w
+            gc = d_cls[o:o + cnt].view(n, h, w, -1)[..., :C]
+            gr = d_reg[o:o + cnt].view(n, h, w, -1)[..., :NB]
+            s = scales[l].detach()
+            g_scales.append((gr.float() * reg_rows[o:o + cnt].view(n, h, w, NB)).sum() / s)   # gfl_head.py:182
+            ops.conv2d_wgrad_tc(gc, cls_feats[l], Gc, 3, 3, 1, 1)
+            Gr = torch.zeros(NB, 9 * ci, dtype=torch.float32, device=dev)
+            ops.conv2d_wgrad_tc(gr, reg_feats[l], Gr, 3, 3, 1, 1)
+            g_wr += Gr * s
+            blk = torch.zeros(d_reg.shape[1], dtype=torch.float32, device=dev)
+            ops.colsum(d_reg[o:o + cnt], blk)
+            g_br += blk[:NB] * s
+            g_cf.append(gc)
+            g_rf.append(engine.conv_dgrad(gr, w_reg, s.expand(NB), 1, 1, (h, w)))
+            g_x.append(None if x_dense is None else x_dense[o:o + cnt].view(n, h, w, -1))
+            o += cnt
+        wd, cop = engine.dgrad_weight(w_cls, None)
+        taps = [(1 - s_, 1 - r_, (r_ * 3 + s_) * cop) for r_ in range(3) for s_ in range(3)]
+        g_cf = ops.conv2d_tc_multi(g_cf, wd, ci, 3, 3, 1, 1, taps=taps)
+        g_wc = Gc.view(C, 3, 3, ci).permute(0, 3, 1, 2)
+        g_wr = g_wr.view(NB, 3, 3, ci).permute(0, 3, 1, 2)
+        s1, s2 = ctx.q_shapes
+        return (None, None, *g_cf, *g_rf, *g_x, g_wc, g_bc, g_wr, g_br, *g_scales,
+                g_w1.reshape(s1), g_b1, g_w2.reshape(s2), g_b2)

@@ -139,7 +139,8 @@ class KnowledgeDistillationSingleStageDetector(SingleStageDetector):
             out_teacher = self.teacher_model.bbox_head(teacher_x)
         x = self.extract_feat(img, im2col=im2col)
         main.wait_stream(side)
-        for t in list(teacher_x) + list(out_teacher[0]) + list(out_teacher[1]) + [im2col[0]]:
+        # (LDHead: (cls_scores, bbox_preds); LDv2Head: (None, bbox_preds, cls_feats))
+        for t in list(teacher_x) + [t for grp in out_teacher if grp is not None for t in grp] + [im2col[0]]:
             t.record_stream(main)
         return self.bbox_head.forward_train(x, out_teacher, teacher_x, img_metas, gt_bboxes, gt_labels,
                                             gt_bboxes_ignore)
