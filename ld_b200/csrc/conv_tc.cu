@@ -1289,8 +1289,10 @@ static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& commo
   LDB_REQUIRE(d->in && d->out, LDB_EINVAL, "conv2d_tc: null pointer");
   LDB_REQUIRE(d->in_ld >= d->Cin && d->in_ld % 8 == 0, LDB_EINVAL, "conv2d_tc: in_ld must be >= Cin and a multiple of 8");
   LDB_REQUIRE(d->N >= 1 && d->HO >= 1 && d->WO >= 1, LDB_EINVAL, "conv2d_tc: shape");
-  LDB_REQUIRE(((uintptr_t)d->in & 15) == 0 && ((uintptr_t)d->out & 15) == 0, LDB_EINVAL,
-              "conv2d_tc: pointers must be 16-byte aligned");
+  // the input feeds TMA (16-byte aligned); the output only needs element alignment -- rows that are not 16-byte
+  // aligned (e.g. fp32 rows of 81 channels, the LDv2 class logits) take the scalar epilogue path (vec_ok = 0)
+  LDB_REQUIRE(((uintptr_t)d->in & 15) == 0 && ((uintptr_t)d->out & (d->out_f32 ? 3 : 1)) == 0, LDB_EINVAL,
+              "conv2d_tc: input must be 16-byte aligned, output element-aligned");
   memset(g, 0, sizeof(*g));
   g->N = d->N; g->HO = d->HO; g->WO = d->WO;
   g->OH = d->OH ? d->OH : d->HO; g->OW = d->OW ? d->OW : d->WO;
@@ -1440,6 +1442,8 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
   p.vec_ok = (d->out_ld % (d->out_f32 ? 4 : 8) == 0) && (!d->mask_src || p.mask_ld % 8 == 0) &&
              (!d->add_src || p.add_ld % 8 == 0) && (!d->scale || ((uintptr_t)d->scale & 15) == 0) &&
              (!d->bias || ((uintptr_t)d->bias & 15) == 0);
+  for (int i = 0; i < count; ++i)
+    if ((uintptr_t)descs[i].out & 15) p.vec_ok = 0;
   const bool shortk = d->ntaps * (p.Cin / KCH) <= 4 && getenv("LDB200_NO_SHORTK") == nullptr;
   const int BN = shortk ? (d->Cout > 64 ? 128 : 64) : (d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64));
   p.tiles_n = (d->Cout + BN - 1) / BN;
