@@ -195,6 +195,15 @@ int ldb200_gi_region_v2(const ldb_pyramid* pyr, const ldb_loss_cfg* cfg, const f
                         const float* t_cls_feat, const float* t_reg, float iou_thr, int topk, const int32_t* counts_in,
                         int32_t* gi_rows, int32_t* counts_out, void* workspace, void* stream);
 
+/* Fused ResNet stem (resnet.py:626-629: conv1 7x7/2 pad 3 + eval-BN + ReLU) for one or two networks that share the
+ * input image (kd_one_stage.py:60-66: student and frozen teacher), without the im2col buffer of ldb200_stem_im2col:
+ *   img [N,3,H,W] f32 NCHW; weights [64*nets, 192] bf16, row = output channel (network 0 first),
+ *   K = (r*7+s)*3+c zero-padded from 147 to 192; scaleX/shiftX [64] f32 = folded BN of network X;
+ *   outX [N, HO, WO, 64] bf16 NHWC with HO = (H-1)/2+1, WO = (W-1)/2+1.  nets = 1 ignores the *1 arguments.
+ * Opt-in from the host side (LDB200_FUSED_STEM=1) until its first GPU run is on record. */
+int ldb200_stem_tc(const float* img, int N, int H, int W, const void* weights, int nets, const float* scale0,
+                   const float* shift0, void* out0, const float* scale1, const float* shift1, void* out1, void* stream);
+
 /* dst[rows[i], :] += src[i, :]  (rows unique).  Adds the compact IM gradient into the dense
  * gradient of the student FPN map. */
 int ldb200_scatter_add_rows(void* dst, const void* src, const int32_t* rows, const int32_t* n_rows_dev,

@@ -189,11 +189,20 @@ class ResNet(nn.Module):
                           relu=True).view(n, ho, wo, 64)
         return ops.maxpool3x3s2(y)
 
-    def forward(self, x, im2col=None):
+    def stem_params(self):
+        """(weights [64,192] bf16 with K = (r*7+s)*3+c zero-padded from 147, (scale, shift)) for `ops.stem_tc`."""
+        w = self.conv1.weight.detach()
+        wp = torch.zeros(64, 192, dtype=torch.bfloat16, device=w.device)
+        wp[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147).to(torch.bfloat16)
+        s, b = engine.bn_affine(self.bn1)
+        return wp, (s.detach(), b.detach())
+
+    def forward(self, x, im2col=None, stem_out=None):
+        """stem_out: conv1+BN+ReLU output [N,HO,WO,64] bf16 already computed by the fused stem kernel (opt-in)."""
         if any(p.requires_grad for p in (self.conv1.weight, self.bn1.weight)):
             raise NotImplementedError('the stem runs forward-only (frozen_stages >= 0 in every LD/GFL config)')
         with torch.no_grad():
-            y = self.stem(x, im2col)
+            y = ops.maxpool3x3s2(stem_out) if stem_out is not None else self.stem(x, im2col)
         outs = []
         for i, name in enumerate(self.res_layers):
             y = getattr(self, name)(y)

@@ -80,8 +80,8 @@ class SingleStageDetector(BaseDetector):
             self.neck.init_weights()
         self.bbox_head.init_weights()
 
-    def extract_feat(self, img, im2col=None):
-        x = self.backbone(img, im2col=im2col)
+    def extract_feat(self, img, im2col=None, stem_out=None):
+        x = self.backbone(img, im2col=im2col) if stem_out is None else self.backbone(img, stem_out=stem_out)
         if self.with_neck:
             x = self.neck(x)
         return x
@@ -127,6 +127,14 @@ class KnowledgeDistillationSingleStageDetector(SingleStageDetector):
         if not self.output_feature:
             raise NotImplementedError('LDHead needs output_feature=True (kd_one_stage.py:73-76 mis-binds its '
                                       'arguments otherwise; both COCO LD configs set it)')
+        # opt-in (LDB200_FUSED_STEM=1, not yet GPU-verified): both stems in one tcgen05 launch, no im2col buffer
+        fused_stem = os.environ.get('LDB200_FUSED_STEM') is not None
+        if fused_stem:
+            ws, afs = self.backbone.stem_params()
+            wt, aft = self.teacher_model.backbone.stem_params()
+            stem_s, stem_t = ops.stem_tc(img.float().contiguous(), torch.cat([ws, wt]).contiguous(), [afs, aft])
+            return self._forward_train_fused_stem(img, stem_s, stem_t, img_metas, gt_bboxes, gt_labels,
+                                                  gt_bboxes_ignore)
         im2col = ops.stem_im2col(img.float().contiguous())
         # the frozen teacher and the student only share the input: run the teacher on a second stream so its
         # kernels fill the SMs the student's tails / latency-bound epilogues leave idle (also captured as a
@@ -142,6 +150,21 @@ class KnowledgeDistillationSingleStageDetector(SingleStageDetector):
         # (LDHead: (cls_scores, bbox_preds); LDv2Head: (None, bbox_preds, cls_feats))
         for t in list(teacher_x) + [t for grp in out_teacher if grp is not None for t in grp] + [im2col[0]]:
             t.record_stream(main)
+        return self.bbox_head.forward_train(x, out_teacher, teacher_x, img_metas, gt_bboxes, gt_labels,
+                                            gt_bboxes_ignore)
+
+    def _forward_train_fused_stem(self, img, stem_s, stem_t, img_metas, gt_bboxes, gt_labels, gt_bboxes_ignore):
+        main = torch.cuda.current_stream()
+        side = self._teacher_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side), torch.no_grad():
+            teacher_x = self.teacher_model.extract_feat(img, stem_out=stem_t)
+            out_teacher = self.teacher_model.bbox_head(teacher_x)
+        x = self.extract_feat(img, stem_out=stem_s)
+        main.wait_stream(side)
+        for t in list(teacher_x) + [t for grp in out_teacher if grp is not None for t in grp]:
+            t.record_stream(main)
+        stem_t.record_stream(side)      # allocated on the main stream, read by the teacher's pool on the side stream
         return self.bbox_head.forward_train(x, out_teacher, teacher_x, img_metas, gt_bboxes, gt_labels,
                                             gt_bboxes_ignore)
 

@@ -400,6 +400,24 @@ def stem_im2col(img):
     return out, ho, wo
 
 
+def stem_tc(img, weights, affines):
+    """Fused conv1 7x7/2 + folded BN + ReLU for 1 or 2 networks sharing `img` (ldb200_stem_tc).
+    img [N,3,H,W] f32; weights [64*nets, 192] bf16; affines = [(scale, shift), ...] per network -> list of
+    [N,HO,WO,64] bf16 NHWC tensors."""
+    n, c, h, w = img.shape
+    nets = len(affines)
+    assert c == 3 and img.dtype == torch.float32 and img.is_contiguous() and nets in (1, 2)
+    assert weights.shape == (64 * nets, 192) and weights.dtype == torch.bfloat16 and weights.is_contiguous()
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    outs = [torch.empty(n, ho, wo, 64, dtype=torch.bfloat16, device=img.device) for _ in range(nets)]
+    sc = [a[0].detach().float().contiguous() for a in affines]
+    sh = [a[1].detach().float().contiguous() for a in affines]
+    L.check(L.load().ldb200_stem_tc(L.ptr(img), n, h, w, L.ptr(weights), nets, L.ptr(sc[0]), L.ptr(sh[0]), L.ptr(outs[0]),
+                                    L.ptr(sc[1]) if nets == 2 else None, L.ptr(sh[1]) if nets == 2 else None,
+                                    L.ptr(outs[1]) if nets == 2 else None, L.stream_ptr()), 'ldb200_stem_tc')
+    return outs
+
+
 def maxpool3x3s2(x):
     n, h, w, c = x.shape
     out = torch.empty(n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c, dtype=x.dtype, device=x.device)

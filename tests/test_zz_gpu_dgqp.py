@@ -168,3 +168,48 @@ def test_ldv2_step_vs_golden(golden_dir):
         mine, ref = named[k].grad.float().cpu().flatten(), g.flatten()
         cos = float(torch.dot(mine, ref) / (mine.norm() * ref.norm() + 1e-30))
         assert cos > 0.98, (k, cos)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused dual stem (ldb200_stem_tc, opt-in LDB200_FUSED_STEM=1) against the im2col + GEMM route
+@pytest.mark.parametrize('shape', [(2, 128, 160), (1, 97, 131), (3, 64, 64)])
+def test_fused_stem_matches_im2col_route(shape):
+    import ld_b200
+    from ld_b200 import ops, presets, synth
+    from ld_b200.config import ConfigDict
+    n, h, w = shape
+    m = ld_b200.build_detector(ConfigDict(presets.ld_model('r18', teacher_depth=18)))
+    synth.seeded_init(m, 5)
+    synth.seeded_init(m.teacher_model, 6, prefix='teacher.')
+    m = m.cuda().train()
+    img = torch.randn(n, 3, h, w, device='cuda', generator=torch.Generator(device='cuda').manual_seed(h))
+    with torch.no_grad():
+        want_s = m.backbone.stem(img)                    # im2col + GEMM + pool
+        want_t = m.teacher_model.backbone.stem(img)
+        ws, afs = m.backbone.stem_params()
+        wt, aft = m.teacher_model.backbone.stem_params()
+        got_s, got_t = ops.stem_tc(img.contiguous(), torch.cat([ws, wt]).contiguous(), [afs, aft])
+        one, = ops.stem_tc(img.contiguous(), wt.contiguous(), [aft])
+        got_s, got_t, one = ops.maxpool3x3s2(got_s), ops.maxpool3x3s2(got_t), ops.maxpool3x3s2(one)
+    torch.cuda.synchronize()
+    for got, want in ((got_s, want_s), (got_t, want_t), (one, want_t)):
+        assert got.shape == want.shape
+        assert float((got.float() - want.float()).abs().max()) <= 1e-2 * float(want.float().abs().max())
+
+
+def test_fused_stem_train_step_equals_default(monkeypatch):
+    import ld_b200
+    from ld_b200 import presets, synth
+    from ld_b200.config import ConfigDict
+    m = ld_b200.build_detector(ConfigDict(presets.ld_model('r18', teacher_depth=18)))
+    synth.seeded_init(m, 3)
+    synth.seeded_init(m.teacher_model, 4, prefix='teacher.')
+    m = m.cuda().train()
+    b = synth.make_batch(2, 128, 160, seed=77)
+    data = dict(img=b['img'].cuda(), img_metas=b['img_metas'], gt_bboxes=[x.cuda() for x in b['gt_bboxes']],
+                gt_labels=[x.cuda() for x in b['gt_labels']])
+    _, log0 = m._parse_losses(m(**data))
+    monkeypatch.setenv('LDB200_FUSED_STEM', '1')
+    _, log1 = m._parse_losses(m(**data))
+    for k, v in log0.items():
+        assert abs(log1[k] - v) <= 2e-2 * abs(v) + 1e-3, (k, log1[k], v)
