@@ -171,7 +171,15 @@ def test_ldv2_step_vs_golden(golden_dir):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# fused dual stem (ldb200_stem_tc, opt-in LDB200_FUSED_STEM=1) against the im2col + GEMM route
+# fused dual stem (ldb200_stem_tc, opt-in LDB200_FUSED_STEM=1) against the im2col + GEMM route.
+# Unlike the kernels above this one synchronises warps through mbarriers: a first-run bug could spin forever, so the
+# two tests only run when asked for (LDB200_RUN_PENDING=1, under `timeout`) until the kernel has a GPU run on record.
+import os as _os
+_pending = pytest.mark.skipif(_os.environ.get('LDB200_RUN_PENDING') is None,
+                              reason='new mbarrier-synchronised kernel: run by hand under a timeout first')
+
+
+@_pending
 @pytest.mark.parametrize('shape', [(2, 128, 160), (1, 97, 131), (3, 64, 64)])
 def test_fused_stem_matches_im2col_route(shape):
     import ld_b200
@@ -197,6 +205,7 @@ def test_fused_stem_matches_im2col_route(shape):
         assert float((got.float() - want.float()).abs().max()) <= 1e-2 * float(want.float().abs().max())
 
 
+@_pending
 def test_fused_stem_train_step_equals_default(monkeypatch):
     import ld_b200
     from ld_b200 import presets, synth
