@@ -81,3 +81,10 @@ LOSS_CASES_V2 = [
 STEP_CASES_V2 = [
     ('s2_r18_r18_2x128x160', 18, 18, 2, 128, 160, 31),
 ]
+
+
+# SURVEY.md §8d / BASELINE north_star: "student loss curve matching reference within 1e-3 over 100 synthetic iters".
+# (name, student depth, teacher depth, N, H, W, seed, iters, base lr, warm-up iters): the unmodified reference model
+# trained with torch.optim.SGD(momentum 0.9, wd 1e-4) under mmcv's linear warm-up formula (LrUpdaterHook,
+# warmup_ratio 0.001), a fresh synthetic batch (seed 2000 + iteration) every step.
+CURVE_CASE = ('c_r18_r18_2x128x160_100it', 18, 18, 2, 128, 160, 41, 100, 0.0002, 20)

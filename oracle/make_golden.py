@@ -227,6 +227,33 @@ def gen_steps():
         print(name, {k: round(v, 5) for k, v in log.items()})
 
 
+def gen_curve():
+    name, sd, td, n, h, w, seed, iters, base_lr, warm = cases.CURVE_CASE
+    cfg = rh.load_model_cfg()
+    cfg['backbone']['depth'] = sd
+    cfg['neck']['in_channels'] = [64, 128, 256, 512]
+    cfg['teacher_config']['model']['backbone']['depth'] = td
+    cfg['teacher_config']['model']['neck']['in_channels'] = [64, 128, 256, 512]
+    m = rh.build_reference_detector(cfg)
+    synth.seeded_init(m, seed)
+    synth.seeded_init(m.teacher_model, seed + 1, prefix='teacher.')
+    opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=base_lr, momentum=0.9, weight_decay=1e-4)
+    curve, terms = [], []
+    for it in range(iters):
+        lr = base_lr * (1 - (1 - it / warm) * (1 - 0.001)) if it < warm else base_lr   # mmcv LrUpdaterHook 'linear'
+        for gp in opt.param_groups:
+            gp['lr'] = lr
+        b = synth.make_batch(n, h, w, seed=2000 + it)
+        losses, loss, log = rh.reference_step(m, b)
+        opt.step()
+        curve.append(float(loss.detach()))
+        terms.append([log[k] for k in sorted(log) if k != 'loss'])
+    gold = dict(loss=torch.tensor(curve), terms=torch.tensor(terms), term_names=sorted(k for k in log if k != 'loss'),
+                final_checksum={k: float(p.detach().double().sum()) for k, p in list(m.named_parameters())[-6:]})
+    torch.save(gold, os.path.join(OUT, name + '.pt'))
+    print(name, [round(c, 4) for c in curve[:3]], '...', [round(c, 4) for c in curve[-3:]])
+
+
 def main():
     if not rh.reference_available():
         sys.exit('needs /root/reference (build container only)')
@@ -240,6 +267,7 @@ def main():
     gen_steps()
     gen_losses_v2()
     gen_steps_v2()
+    gen_curve()
 
 
 if __name__ == '__main__':

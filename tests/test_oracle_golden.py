@@ -152,6 +152,26 @@ def test_full_step_ldv2(golden_dir, case):
         assert abs(gn - float(st[0])) <= 1e-4 * max(float(st[0]), 1e-6), (k, gn, float(st[0]))
 
 
+def test_loss_curve_first_iterations(golden_dir):
+    """training-trajectory parity.  The oracle port under torch SGD + mmcv's linear warm-up follows the
+    unmodified reference's 100-iteration loss curve (tests/golden/c_*.pt); the first 25 iterations are replayed here
+    (the GPU test replays all 100 through LDTrainStep)."""
+    name, sd, td, n, h, w, seed, iters, base_lr, warm = cases.CURVE_CASE
+    gold = _load(golden_dir, name)
+    m = lo.OracleLDDetector(sd, td).train()
+    synth.seeded_init(m, seed)
+    synth.seeded_init(m.teacher_model, seed + 1, prefix='teacher.')
+    opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=base_lr, momentum=0.9, weight_decay=1e-4)
+    for it in range(25):
+        lr = base_lr * (1 - (1 - it / warm) * (1 - 0.001)) if it < warm else base_lr
+        for gp in opt.param_groups:
+            gp['lr'] = lr
+        losses, loss, log = m.step(synth.make_batch(n, h, w, seed=2000 + it))
+        opt.step()
+        want = float(gold['loss'][it])
+        assert abs(float(loss) - want) <= 1e-3 * abs(want), (it, float(loss), want)
+
+
 def test_reference_known_answers():
     """The only known-answer vectors the reference's own tests/doctests hold on this path
     (SURVEY.md §8c): tests/test_anchor.py:22-41 `test_strides` and the bbox_overlaps examples of
