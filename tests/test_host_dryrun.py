@@ -1,0 +1,159 @@
+"""CPU: dry run of the HOST logic -- registries, module graph, autograd wiring, row-space bookkeeping, argument
+marshalling of every C-ABI call -- with the shared library replaced by ctypes callbacks of the SAME signatures
+(`ld_b200.lib._SIGS`) that do nothing and return 0.  ctypes still converts and checks every argument, the autograd
+functions still have to hand back one gradient per input with the right shape, so Python-level mistakes in the train
+step surface here without a GPU.  Kernel outputs are uninitialised memory: nothing numeric is asserted (that is what
+the `-m gpu` parity tests are for)."""
+import contextlib
+import ctypes as C
+
+import pytest
+import torch
+
+import ld_b200
+from ld_b200 import lib as L, presets, synth
+from ld_b200.config import ConfigDict
+
+
+class _FakeStream:
+    cuda_stream = 0
+    device = torch.device('cpu')
+
+    def wait_stream(self, other):
+        pass
+
+    def wait_event(self, ev):
+        pass
+
+    def record_event(self, *a):
+        return None
+
+
+@pytest.fixture
+def fake_backend(monkeypatch):
+    calls = []
+    keep = []
+
+    def make(name, restype, argtypes):
+        def impl(*args):
+            calls.append(name)
+            if name.endswith('workspace_bytes'):
+                return 1 << 16
+            if name == 'ldb200_last_error':
+                return b''
+            return 0
+        cb = C.CFUNCTYPE(restype, *argtypes)(impl)
+        keep.append(cb)
+        return cb
+
+    class FakeLib:
+        pass
+    fake = FakeLib()
+    for name, (restype, argtypes) in L._SIGS.items():
+        setattr(fake, name, make(name, restype, argtypes))
+    monkeypatch.setattr(L, '_lib', fake)
+    monkeypatch.setattr(L, 'stream_ptr', lambda: C.c_void_p(0))
+    stream = _FakeStream()
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a, **k: stream)
+    monkeypatch.setattr(torch.cuda, 'Stream', lambda *a, **k: stream)
+    monkeypatch.setattr(torch.cuda, 'stream', lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, 'current_device', lambda: 0)
+    monkeypatch.setattr(torch.Tensor, 'record_stream', lambda self, s: None)
+    return calls
+
+
+def _batch(n=2, h=128, w=160, seed=9):
+    b = synth.make_batch(n, h, w, seed=seed)
+    return dict(img=b['img'], img_metas=b['img_metas'], gt_bboxes=b['gt_bboxes'], gt_labels=b['gt_labels'])
+
+
+def _check_grads(model):
+    missing = [k for k, p in model.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing, missing[:8]
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            assert p.grad.shape == p.shape, k
+
+
+@pytest.mark.parametrize('imitation,im_weight', [('finegrained', 2.0), ('gibox', 2.0), ('gibox', 0.0)])
+def test_ld_train_step_host_logic(fake_backend, imitation, im_weight):
+    cfg = ConfigDict(presets.ld_model('r18', teacher_depth=18))
+    cfg.bbox_head.update(imitation_method=imitation, loss_im=dict(type='IMLoss', loss_weight=im_weight))
+    m = ld_b200.build_detector(cfg).train()
+    losses = m(**_batch())
+    assert list(losses) == ['loss_cls', 'loss_bbox', 'loss_dfl', 'loss_ld', 'loss_ld_vlr', 'loss_kd', 'loss_kd_neg',
+                            'loss_im']
+    assert all(len(v) == 5 for v in losses.values())
+    loss, log = m._parse_losses(losses)
+    loss.backward()
+    _check_grads(m)
+    assert ('ldb200_gi_region' in fake_backend) == (imitation == 'gibox' and im_weight != 0)
+    for name in ('ldb200_ld_targets', 'ldb200_ld_loss_prepass', 'ldb200_ld_loss_fused', 'ldb200_conv2d_wgrad_tc',
+                 'ldb200_stem_im2col'):
+        assert name in fake_backend, name
+    assert 'ldb200_stem_tc' not in fake_backend and not any(n.endswith('_v2') for n in fake_backend)
+
+
+def test_ld_train_step_fused_stem_host_logic(fake_backend, monkeypatch):
+    monkeypatch.setenv('LDB200_FUSED_STEM', '1')
+    m = ld_b200.build_detector(ConfigDict(presets.ld_model('r18', teacher_depth=18))).train()
+    loss, _ = m._parse_losses(m(**_batch()))
+    loss.backward()
+    _check_grads(m)
+    assert fake_backend.count('ldb200_stem_tc') == 1 and 'ldb200_stem_im2col' not in fake_backend
+
+
+def test_flat_sgd_step_host_logic(fake_backend):
+    m = ld_b200.build_detector(ConfigDict(presets.ld_model('r18', teacher_depth=18))).train()
+    ts = ld_b200.LDTrainStep(m, lr=0.001, warmup_iters=4)
+    for _ in range(2):
+        ts.step(_batch(), sync_logs=False)
+    assert ts.iter == 2 and fake_backend.count('ldb200_sgd_flat') == 2
+    p = m.bbox_head.gfl_cls.weight
+    assert p.data_ptr() >= ts.flat_w.data_ptr() and p.grad.data_ptr() >= ts.flat_g.data_ptr()
+
+
+def test_ldv2_train_step_host_logic(fake_backend):
+    """configs/ldv2/ld_r50_gflv2_r101_fpn_1x.py structure (R18 backbones): LDv2Head student, GFocalHead teacher."""
+    cfg = ConfigDict(presets.ld_model('r18', teacher_depth=18))
+    v2 = dict(reg_topk=4, reg_channels=64, add_mean=True,
+              loss_cls=dict(type='QualityFocalLoss', use_sigmoid=False, beta=2.0, loss_weight=1.0))
+    cfg.bbox_head.update(type='LDv2Head', imitation_method='gibox', loss_im=dict(type='IMLoss', loss_weight=2), **v2)
+    cfg.teacher_config.model.bbox_head.update(type='GFocalHead', **v2)
+    m = ld_b200.build_detector(cfg).train()
+    losses = m(**_batch())
+    assert all(len(v) == 5 for v in losses.values())
+    loss, _ = m._parse_losses(losses)
+    loss.backward()
+    _check_grads(m)
+    for name in ('ldb200_dgqp_forward', 'ldb200_dgqp_backward', 'ldb200_ld_loss_prepass_v2', 'ldb200_ld_loss_fused_v2',
+                 'ldb200_gi_region_v2'):
+        assert fake_backend.count(name) == 1, name
+    assert 'ldb200_ld_loss_fused' not in fake_backend
+
+
+def test_head_loss_apis_host_logic(fake_backend):
+    from oracle import cases
+    d = cases.loss_case_inputs(2, 128, 160, 3)
+    cfg = ConfigDict(presets.ld_model('r50'))
+    hc = cfg.bbox_head
+    hc['train_cfg'], hc['test_cfg'] = cfg.train_cfg, cfg.test_cfg
+    head = ld_b200.build_head(hc).train()
+    leaves = {k: [t.clone().requires_grad_(True) for t in d[k]] for k in ('cls', 'reg', 'x')}
+    losses = head.loss(leaves['cls'], leaves['reg'], d['gt_bboxes'], d['gt_labels'], (d['t_cls'], d['t_reg']),
+                       leaves['x'], d['t_x'], d['img_metas'])
+    sum(sum(v) for v in losses.values()).backward()
+    assert all(t.grad is not None and t.grad.shape == t.shape for grp in leaves.values() for t in grp)
+    # LDv2Head.loss(cls_scores, bbox_preds, cls_feat, ..., soft_teacher = (scores, bbox_preds, cls_feats), ...)
+    d2 = cases.loss_case_inputs_v2(2, 128, 160, 4)
+    hc2 = ConfigDict(presets.ld_model('r50')).bbox_head
+    hc2.update(type='LDv2Head', reg_topk=4, reg_channels=64, add_mean=True, imitation_method='gibox',
+               loss_cls=dict(type='QualityFocalLoss', use_sigmoid=False, beta=2.0, loss_weight=1.0),
+               loss_im=dict(type='IMLoss', loss_weight=2))
+    hc2['train_cfg'], hc2['test_cfg'] = cfg.train_cfg, cfg.test_cfg
+    head2 = ld_b200.build_head(hc2).train()
+    lv = {k: [t.clone().requires_grad_(True) for t in d2[k]] for k in ('score', 'cls_feat', 'reg', 'x')}
+    losses = head2.loss(lv['score'], lv['reg'], lv['cls_feat'], d2['gt_bboxes'], d2['gt_labels'],
+                        (None, d2['t_reg'], d2['t_cls']), lv['x'], d2['t_x'], d2['img_metas'])
+    sum(sum(v) for v in losses.values()).backward()
+    assert all(t.grad is not None and t.grad.shape == t.shape for grp in lv.values() for t in grp)
