@@ -47,9 +47,9 @@ struct ConvSeg {            // geometry of one segment (= one FPN level of a lev
   // output addressing: element offset of pixel (n,y,x) = ((n*OH + y*oys + oyo)*OW + x*oxs + oxo)*ldc
   int OH, OW, oys, oyo, oxs, oxo;
   void* out;
-  const __nv_bfloat16* add_src;  // optional add, nearest-resampled from [N, add_H, add_W, add_ld]
+  const void* add_src;      // optional add (bf16, or fp32 when p.add_f32), nearest-resampled from [N, add_H, add_W, add_ld]
   int add_H, add_W;
-  const __nv_bfloat16* mask_src; // optional: multiply by (mask_src > 0), same addressing as out (bf16, ld = mask_ld)
+  const void* mask_src;     // optional: multiply by (mask_src > 0), same addressing as out (bf16 / fp32 when p.mask_f32, ld = mask_ld)
   int pf_add, pf_mask;      // L2-prefetch the residual / mask tile with TMA while the main loop runs
   int tl_add, tl_mask;      // TMA epilogue: residual / mask boxes are TMA-loaded into the warp's staging buffer
 };
@@ -73,6 +73,12 @@ struct ConvParams {
   int vec_ok;               // leading dimensions allow 16-byte vector accesses
   int tma_epi;              // epilogue stages 32-pixel x 64-channel boxes in shared memory and TMA-stores them
   int nt_inner;             // 1-CTA kernel: a CTA walks all output-channel tiles of one pixel tile back to back
+  // split-bf16 (fp32-accurate) mode: the input is `planes` stacked bf16 tensors [planes][N,H,W,ld] whose sum is the fp32
+  // activation, the weights [Cout][planes][w_plane]; the reduction runs over ncombo (activation plane, weight plane)
+  // pairs per tap and channel slice, all into the same fp32 TMEM accumulator.  planes = 1, ncombo = 1: plain bf16.
+  int planes, ncombo, w_plane;
+  int comb_a[6], comb_w[6];
+  int add_f32, mask_f32;    // residual / mask tensors are fp32 (fp32 activations of the split mode)
 };
 
 struct ConvMaps {           // per-segment TMA descriptors: A operand, residual prefetch, mask prefetch,
@@ -261,9 +267,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
   const bool pix_ok = live && (y < S.HO) && (x < S.WO);
   const size_t pix = pix_ok ? out_offset(S, n, y, x) : 0;
   const __nv_bfloat16* addp = nullptr;
+  const float* addpf = nullptr;
   if (S.add_src && pix_ok && !(tma && S.tl_add)) {
     const int ay = (int)(((long long)y * S.add_H) / S.HO), ax = (int)(((long long)x * S.add_W) / S.WO);
-    addp = S.add_src + (((size_t)n * S.add_H + ay) * S.add_W + ax) * (size_t)p.add_ld;
+    const size_t aoff = (((size_t)n * S.add_H + ay) * S.add_W + ax) * (size_t)p.add_ld;
+    if (p.add_f32) addpf = (const float*)S.add_src + aoff;
+    else addp = (const __nv_bfloat16*)S.add_src + aoff;
   }
   const int col0 = nt * BN + half * GCOLS;
   const uint32_t tbase = tmem_acc + ((uint32_t)(ew * 32) << 16) + (uint32_t)(half * GCOLS);
@@ -355,6 +364,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
               v[j + 2 * e + 1] += f.y;
             }
           }
+        } else if (addpf) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(addpf + cbase + j));
+            v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+          }
         } else if (addp) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -400,8 +415,18 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (!((word >> j) & 1u)) v[j] = 0.f;
+        } else if (S.mask_src && p.mask_f32) {
+          const float* mk = (const float*)S.mask_src + pix * (size_t)p.mask_ld + cbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 m4 = __ldg(reinterpret_cast<const float4*>(mk + j));
+            if (!(m4.x > 0.f)) v[j] = 0.f;
+            if (!(m4.y > 0.f)) v[j + 1] = 0.f;
+            if (!(m4.z > 0.f)) v[j + 2] = 0.f;
+            if (!(m4.w > 0.f)) v[j + 3] = 0.f;
+          }
         } else if (S.mask_src) {
-          const __nv_bfloat16* mk = S.mask_src + pix * (size_t)p.mask_ld + cbase;
+          const __nv_bfloat16* mk = (const __nv_bfloat16*)S.mask_src + pix * (size_t)p.mask_ld + cbase;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             const uint4 q = __ldg(reinterpret_cast<const uint4*>(mk + j));
@@ -445,11 +470,16 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
           if (p.scale) vv *= __ldg(p.scale + c);
           if (p.bias) vv += __ldg(p.bias + c);
           if (addp) vv += __bfloat162float(addp[c]);
+          if (addpf) vv += addpf[c];
           if (p.accumulate)
             vv += p.out_f32 ? ((const float*)S.out)[pix * (size_t)p.ldc + c]
                             : __bfloat162float(((const __nv_bfloat16*)S.out)[pix * (size_t)p.ldc + c]);
           if (p.relu) vv = fmaxf(vv, 0.f);
-          if (S.mask_src && !(__bfloat162float(S.mask_src[pix * (size_t)p.mask_ld + c]) > 0.f)) vv = 0.f;
+          if (S.mask_src) {
+            const float mv = p.mask_f32 ? ((const float*)S.mask_src)[pix * (size_t)p.mask_ld + c]
+                                        : __bfloat162float(((const __nv_bfloat16*)S.mask_src)[pix * (size_t)p.mask_ld + c]);
+            if (!(mv > 0.f)) vv = 0.f;
+          }
           if (p.out_f32) ((float*)S.out)[pix * (size_t)p.ldc + c] = vv;
           else ((__nv_bfloat16*)S.out)[pix * (size_t)p.ldc + c] = __float2bfloat16_rn(vv);
         }
@@ -487,7 +517,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cchunks = p.Cin / KCH;
-  const int kblocks = p.ntaps * cchunks;
+  const int kblocks = p.ncombo * p.ntaps * cchunks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -532,12 +562,13 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
         if (S.pf_add) tma_prefetch_4d(&maps.r[sg], nt * BN, tx * S.TW, ty * S.TH, n);
         if (S.pf_mask) tma_prefetch_4d(&maps.m[sg], nt * BN, tx * S.TW, ty * S.TH, n);
         for (int kb = 0; kb < kblocks; ++kb) {
-          const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * KCH;
+          const int tc_ = kb / cchunks, c0 = (kb - tc_ * cchunks) * KCH;
+          const int cmb = tc_ / p.ntaps, tap = tc_ - cmb * p.ntaps;   // (plane pair, tap): cmb = 0 in plain bf16 mode
           mbarrier_wait(&empty[stage], phase ^ 1);
           unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
           mbarrier_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          tma_load_4d(sa, &maps.a[sg], &full[stage], c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], n);
-          tma_load_2d(sa + A_TILE_BYTES, &tmB, &full[stage], p.tap_wk[tap] + c0, nt * BN);
+          tma_load_4d(sa, &maps.a[sg], &full[stage], c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], n + p.comb_a[cmb] * S.N);
+          tma_load_2d(sa + A_TILE_BYTES, &tmB, &full[stage], p.comb_w[cmb] * p.w_plane + p.tap_wk[tap] + c0, nt * BN);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -673,7 +704,7 @@ conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cchunks = p.Cin / KCH;
-  const int kblocks = p.ntaps * cchunks;
+  const int kblocks = p.ncombo * p.ntaps * cchunks;
   // pair-tiles: CTA rank r of pair q owns M-tile 2*(q % half_m) + r of output-channel tile q / half_m; an odd
   // M-tile count is padded with a dummy tile (fully out-of-bounds loads, no stores)
   const int mt_total = p.seg_tile0[p.nseg] / p.tiles_n;
@@ -724,20 +755,23 @@ conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ C
         const int tx = sp % S.tiles_x;
         sp /= S.tiles_x;
         const int ty = sp % S.tiles_y;
-        const int n = dummy ? S.N : sp / S.tiles_y;   // image index N is out of bounds: TMA zero-fills
+        const int n = dummy ? S.N * p.planes : sp / S.tiles_y;   // image index beyond every plane: TMA zero-fills
         const int x0 = tx * S.TW * p.sx, y0 = ty * S.TH * p.sy;
         // the epilogue will read this tile's residual / ReLU-mask rows a whole main loop from now: pull them into
         // L2 with one TMA prefetch each so those loads see L2 latency instead of HBM latency
         if (S.pf_add) tma_prefetch_4d(&maps.r[sg], nt * BN, tx * S.TW, ty * S.TH, n);
         if (S.pf_mask) tma_prefetch_4d(&maps.m[sg], nt * BN, tx * S.TW, ty * S.TH, n);
         for (int kb = 0; kb < kblocks; ++kb) {
-          const int tap = kb / cchunks, c0 = (kb - tap * cchunks) * KCH;
+          const int tc_ = kb / cchunks, c0 = (kb - tc_ * cchunks) * KCH;
+          const int cmb = tc_ / p.ntaps, tap = tc_ - cmb * p.ntaps;   // (plane pair, tap): cmb = 0 in plain bf16 mode
           mbarrier_wait(&empty[stage], phase ^ 1);
           unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
           // both CTAs' loads complete on the LEADER's barrier; only the leader arms it (bytes of the pair)
           if (rank == 0) mbarrier_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-          tma_load_4d_2sm(sa, &maps.a[sg], &full[stage], c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], n);
-          tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, &full[stage], p.tap_wk[tap] + c0, nt * BN + (int)rank * (BN / 2));
+          tma_load_4d_2sm(sa, &maps.a[sg], &full[stage], c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap],
+                          dummy ? n : n + p.comb_a[cmb] * S.N);
+          tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, &full[stage], p.comb_w[cmb] * p.w_plane + p.tap_wk[tap] + c0,
+                          nt * BN + (int)rank * (BN / 2));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -795,7 +829,7 @@ conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ C
       const int tx = sp % S.tiles_x;
       sp /= S.tiles_x;
       const int ty = sp % S.tiles_y;
-      const int n = dummy ? S.N : sp / S.tiles_y;   // image index N is out of bounds: TMA zero-fills
+      const int n = dummy ? S.N * p.planes : sp / S.tiles_y;   // image index beyond every plane: TMA zero-fills
       epilogue_tile<BN, SHORTK, Cfg::EPI_GROUPS>(p, maps, S, sg, nt, tx, ty, n, !dummy, tmem_base + (uint32_t)(acc * BN),
                                                  &tfull[acc], acc_phase, ew, half, lane, ebuf, rbar, rph);
       if (lane == 0) mbarrier_arrive_leader(&tempty[acc]);

@@ -62,7 +62,7 @@ def test_r18_config_and_registry_errors(monkeypatch):
 @needs_ref
 def test_ldv2_config_builds_with_reference_keys(monkeypatch):
     """configs/ldv2/ld_r50_gflv2_r101_fpn_1x.py (LDv2Head student, GFocalHead teacher): the registry
-    surface, parameters and checkpoint keys are in place (the compute path is CUDA-only: tests/test_zz_gpu_dgqp.py)."""
+    surface, parameters and checkpoint keys are in place (the compute path is CUDA-only: tests/test_gpu_ldv2.py)."""
     import ld_b200
     from oracle import ld_oracle as lo
     monkeypatch.chdir(REF)
