@@ -254,6 +254,13 @@ typedef struct {
   int mask_ld;
   int relu;
   int accumulate;
+  /* fp32-accurate ("parity") mode, 0 = off.  split = P in {2, 3}: `in` holds P stacked bf16 tensors
+   * [P][N,H,W,in_ld] whose SUM is the fp32 activation (ldb200_split_bf16), `weight` rows hold P planes of `w_plane`
+   * columns each ([Cout][P][w_plane], tap_wk relative to a plane); the kernel accumulates the P*(P+1)/2 plane
+   * products of leading magnitude into the same fp32 TMEM accumulator (P = 3: relative error ~2^-23, i.e. the
+   * fp32 convolution the reference runs; P = 2: ~2^-16). */
+  int split, w_plane;
+  int add_f32, mask_f32;  /* add_src / mask_src are fp32 tensors (fp32 activations of the parity mode) */
 } ldb_conv_desc;
 
 int ldb200_conv2d_tc(const ldb_conv_desc* desc, void* stream);
@@ -276,32 +283,38 @@ typedef struct {
   const float* scale;     /* optional [Cout]: dw += scale[co] * G (folded eval-BN / Scale factor) */
   const float* w_master;  /* optional fp32 weights [Cout, w_k], needed for d_scale */
   float* d_scale;         /* optional [Cout]: d_scale[co] += <w_master[co,:], G[co,:]> (gradient of the factor) */
+  int split;              /* 0, or P in {2,3}: dy and x are P stacked bf16 planes each (see ldb_conv_desc.split) */
 } ldb_wgrad_desc;
 int ldb200_conv2d_wgrad_tc(const ldb_wgrad_desc* desc, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * HBM-bound glue around the convolutions (NHWC bf16 activations unless noted).
+ * HBM-bound glue around the convolutions.  Activations are NHWC bf16 (`dtype` = LDB_BF16, the throughput mode) or
+ * NHWC fp32 (`dtype` = LDB_F32, the fp32-accurate "parity" mode whose convolutions run on split-bf16 operands).
  */
+/* fp32 -> P stacked bf16 planes with x ~= sum of planes (P = 3: exact to 2^-24): x [rows, ld_in] f32, first C columns
+ * used; out [P][rows, ld_out] bf16, columns [C, ld_out) zero-filled; ld_out % 8 == 0.  Operand preparation for
+ * ldb_conv_desc.split / ldb_wgrad_desc.split. */
+int ldb200_split_bf16(const float* x, int64_t rows, int C, int ld_in, int planes, void* out, int ld_out, void* stream);
 /* 7x7/2 pad-3 stem conv as a GEMM operand: img [N,3,H,W] f32 (NCHW) -> out [N*HO*WO, 192] bf16 with
  * column (r*7+s)*3+c, zero-padded from 147 (resnet.py:524-570, 626). */
-int ldb200_stem_im2col(const float* img, void* out, int N, int H, int W, void* stream);
+int ldb200_stem_im2col(const float* img, void* out, int N, int H, int W, int out_dtype, void* stream);
 /* 3x3 stride-2 pad-1 max pool (resnet.py:630). */
-int ldb200_maxpool3x3s2(const void* in, void* out, int N, int H, int W, int C, void* stream);
+int ldb200_maxpool3x3s2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream);
 /* GroupNorm(G) [+ReLU] of mmcv ConvModule in the GFL towers (gfl_head.py:102-133, 177-180);
  * x,y: [N, HW, C] bf16; stats: [N, G, 2] f32 (sum, sum of squares; zero-filled by gn_stats). */
-int ldb200_gn_stats(const void* x, float* stats, int N, int HW, int C, int G, void* stream);
+int ldb200_gn_stats(const void* x, float* stats, int N, int HW, int C, int G, int dtype, void* stream);
 int ldb200_gn_apply(const void* x, const float* stats, const float* gamma, const float* beta, void* y,
-                    int N, int HW, int C, int G, float eps, int relu, void* stream);
+                    int N, int HW, int C, int G, float eps, int relu, int dtype, void* stream);
 /* backward of y = relu(GN(x)): dx [N,HW,C] bf16, dgamma/dbeta [C] f32 ACCUMULATED (shared towers),
  * red_ws: [N, G, 2] f32 scratch. */
 int ldb200_gn_relu_bwd(const void* dy, const void* y, const void* x, const float* stats, const float* gamma,
                        float* red_ws, float* dgamma, float* dbeta, void* dx, int N, int HW, int C, int G,
-                       float eps, void* stream);
+                       float eps, int dtype, void* stream);
 /* backward of the FPN top-down `fine += nearest_upsample(coarse)` (fpn.py:182-191): dcoarse += gather-sum(dfine). */
 int ldb200_upsample_add_bwd(const void* dfine, void* dcoarse, int N, int Hf, int Wf, int Hc, int Wc, int C,
-                            void* stream);
-/* out = dy * (y > 0), bf16. */
-int ldb200_relu_bwd(const void* dy, const void* y, void* out, int64_t numel, void* stream);
+                            int dtype, void* stream);
+/* out = dy * (y > 0). */
+int ldb200_relu_bwd(const void* dy, const void* y, void* out, int64_t numel, int dtype, void* stream);
 /* out[c] += sum_rows x[row, c]; x [rows, ld] (dtype LDB_BF16 / LDB_F32): conv-bias and BN-beta gradients. */
 int ldb200_colsum(const void* x, float* out, int64_t rows, int C, int ld, int dtype, void* stream);
 /* eval-mode BatchNorm (norm_eval=True, resnet.py:639-649) folded into the conv epilogue's per-channel affine:

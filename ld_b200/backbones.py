@@ -16,10 +16,12 @@ from .registry import BACKBONES, NECKS
 
 
 def nhwc(x):
-    """NCHW-shaped tensor -> contiguous NHWC bf16 (zero-copy for channels-last bf16 inputs)."""
+    """NCHW-shaped tensor -> contiguous NHWC in the activation dtype of the current precision mode (bf16, or fp32 in
+    the parity mode); zero-copy for channels-last inputs of that dtype."""
     y = x.permute(0, 2, 3, 1)
-    if y.dtype != torch.bfloat16:
-        y = y.to(torch.bfloat16)
+    dt = engine.act_dtype()
+    if y.dtype != dt:
+        y = y.to(dt)
     return y if y.is_contiguous() else y.contiguous()
 
 
@@ -178,12 +180,13 @@ class ResNet(nn.Module):
     def stem(self, img=None, im2col=None):
         """conv1 7x7/2 + BN + ReLU + 3x3/2 max-pool (resnet.py:626-630) -> NHWC bf16."""
         if im2col is None:
-            im2col = ops.stem_im2col(img.float().contiguous())
+            im2col = ops.stem_im2col(img.float().contiguous(), engine.act_dtype())
         a, ho, wo = im2col
         n = a.shape[0] // (ho * wo)
         w = self.conv1.weight.detach()
-        wp = torch.zeros(64, 192, dtype=torch.bfloat16, device=w.device)
-        wp[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147).to(torch.bfloat16)
+        wp = torch.zeros(64, 192, dtype=torch.float32, device=w.device)
+        wp[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147)
+        wp = ops.split_weight(wp) if engine.parity() else wp.to(torch.bfloat16)
         s, b = engine.bn_affine(self.bn1)
         y = ops.conv2d_tc(a.view(1, 1, -1, 192), wp, 64, scale=s.detach().contiguous(), bias=b.detach().contiguous(),
                           relu=True).view(n, ho, wo, 64)
@@ -274,7 +277,7 @@ class FPN(nn.Module):
         for _ in range(len(self.fpn_convs) - nb):
             h, w = sizes[-1]
             sizes.append(((h - 1) // 2 + 1, (w - 1) // 2 + 1))
-        rows = torch.empty(n * sum(h * w for h, w in sizes), self.out_channels, dtype=torch.bfloat16,
+        rows = torch.empty(n * sum(h * w for h, w in sizes), self.out_channels, dtype=feats[0].dtype,
                            device=feats[0].device)
         outs, o = [], 0
         for i, (h, w) in enumerate(sizes):

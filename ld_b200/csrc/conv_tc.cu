@@ -863,6 +863,10 @@ struct WgradParams {
   const float* scale;     // optional per-output-channel factor applied to the accumulated gradient
   const float* w_master;  // optional fp32 weights [Cout, w_k]: d_scale[co] += <w[co,:], G[co,:]>
   float* d_scale;
+  // split-bf16 mode: dy and x are `planes` stacked bf16 tensors each; every pixel tile is reduced over ncombo
+  // (dy plane, x plane) pairs into the same accumulator (planes = ncombo = 1: plain bf16)
+  int planes, ncombo;
+  int comb_a[6], comb_b[6];
 };
 
 // MN-major SWIZZLE_128B descriptor: LBO = 16 KB between 64-element chunks, SBO = 1 KB between 8-row groups
@@ -940,17 +944,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int tx = pt % p.tiles_x;
           const int ty = (pt / p.tiles_x) % p.tiles_y;
           const int n = pt / (p.tiles_x * p.tiles_y);
-          mbarrier_wait(&empty[stage], phase ^ 1);
-          unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
-          mbarrier_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          for (int cmb = 0; cmb < p.ncombo; ++cmb) {
+            mbarrier_wait(&empty[stage], phase ^ 1);
+            unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+            mbarrier_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+            const int na = n + p.comb_a[cmb] * p.N, nb = n + p.comb_b[cmb] * p.N;
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
-            tma_load_4d(sa + j * A_TILE_BYTES, &tmA, &full[stage], co_t * TILE_M + 64 * j, tx * p.TW, ty * p.TH, n);
+            for (int j = 0; j < 2; ++j)
+              tma_load_4d(sa + j * A_TILE_BYTES, &tmA, &full[stage], co_t * TILE_M + 64 * j, tx * p.TW, ty * p.TH, na);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_4d(sa + Cfg::A_BYTES + j * A_TILE_BYTES, &tmB, &full[stage], ci_t * BN + 64 * j,
-                        tx * p.TW * p.sx + p.tap_dx[tap], ty * p.TH * p.sy + p.tap_dy[tap], n);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(sa + Cfg::A_BYTES + j * A_TILE_BYTES, &tmB, &full[stage], ci_t * BN + 64 * j,
+                          tx * p.TW * p.sx + p.tap_dx[tap], ty * p.TH * p.sy + p.tap_dy[tap], nb);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -966,18 +973,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbarrier_wait(tempty, (it & 1) ^ 1);
         tc_fence_after();
         for (int pt = pt0; pt < pt1; ++pt) {
-          mbarrier_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = s2u(smem + (size_t)stage * Cfg::STAGE_BYTES);
+          for (int cmb = 0; cmb < p.ncombo; ++cmb) {
+            mbarrier_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = s2u(smem + (size_t)stage * Cfg::STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < TILE_M / 16; ++k) {
-            // 16 pixels = two 8-row groups = 2 KB further down the tile
-            umma_bf16(tmem_base, smem_desc_mn128(sa + k * 2048), smem_desc_mn128(sa + Cfg::A_BYTES + k * 2048),
-                      Cfg::IDESC, (pt > pt0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < TILE_M / 16; ++k) {
+              // 16 pixels = two 8-row groups = 2 KB further down the tile
+              umma_bf16(tmem_base, smem_desc_mn128(sa + k * 2048), smem_desc_mn128(sa + Cfg::A_BYTES + k * 2048),
+                        Cfg::IDESC, (pt > pt0 || cmb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);
+            if (pt == pt1 - 1 && cmb == p.ncombo - 1) umma_commit(tfull);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty[stage]);
-          if (pt == pt1 - 1) umma_commit(tfull);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         if (pt1 == pt0) umma_commit(tfull);   // empty slice: nothing accumulated (epilogue skips it)
       }
@@ -1116,20 +1125,23 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int tx = pt % p.tiles_x;
           const int ty = (pt / p.tiles_x) % p.tiles_y;
           const int n = pt / (p.tiles_x * p.tiles_y);
-          mbarrier_wait(&empty[stage], phase ^ 1);
-          unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
-          // this CTA's 128 of the pair's 256 output channels and 128 of its 256 input channels; all four boxes of
-          // both CTAs complete on the leader's barrier
-          if (rank == 0) mbarrier_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+          for (int cmb = 0; cmb < p.ncombo; ++cmb) {
+            mbarrier_wait(&empty[stage], phase ^ 1);
+            unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+            // this CTA's 128 of the pair's 256 output channels and 128 of its 256 input channels; all four boxes of
+            // both CTAs complete on the leader's barrier
+            if (rank == 0) mbarrier_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+            const int na = n + p.comb_a[cmb] * p.N, nb = n + p.comb_b[cmb] * p.N;
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
-            tma_load_4d_2sm(sa + j * A_TILE_BYTES, &tmA, &full[stage], co_t * 2 * TILE_M + (int)rank * TILE_M + 64 * j,
-                            tx * p.TW, ty * p.TH, n);
+            for (int j = 0; j < 2; ++j)
+              tma_load_4d_2sm(sa + j * A_TILE_BYTES, &tmA, &full[stage], co_t * 2 * TILE_M + (int)rank * TILE_M + 64 * j,
+                              tx * p.TW, ty * p.TH, na);
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
-            tma_load_4d_2sm(sa + Cfg::A_BYTES + j * A_TILE_BYTES, &tmB, &full[stage], ci_t * BN + (int)rank * (BN / 2) + 64 * j,
-                            tx * p.TW * p.sx + p.tap_dx[tap], ty * p.TH * p.sy + p.tap_dy[tap], n);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            for (int j = 0; j < 2; ++j)
+              tma_load_4d_2sm(sa + Cfg::A_BYTES + j * A_TILE_BYTES, &tmB, &full[stage], ci_t * BN + (int)rank * (BN / 2) + 64 * j,
+                              tx * p.TW * p.sx + p.tap_dx[tap], ty * p.TH * p.sy + p.tap_dy[tap], nb);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -1145,18 +1157,20 @@ wgrad2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbarrier_wait(tempty, (it & 1) ^ 1);
         tc_fence_after();
         for (int pt = pt0; pt < pt1; ++pt) {
-          mbarrier_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = s2u(smem + (size_t)stage * Cfg::STAGE_BYTES);
+          for (int cmb = 0; cmb < p.ncombo; ++cmb) {
+            mbarrier_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = s2u(smem + (size_t)stage * Cfg::STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < TILE_M / 16; ++k) {
-            // 16 pixels = two 8-row groups = 2 KB further down the tile
-            umma_bf16_2cta(tmem_base, smem_desc_mn128(sa + k * 2048), smem_desc_mn128(sa + Cfg::A_BYTES + k * 2048),
-                      Cfg::IDESC, (pt > pt0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < TILE_M / 16; ++k) {
+              // 16 pixels = two 8-row groups = 2 KB further down the tile
+              umma_bf16_2cta(tmem_base, smem_desc_mn128(sa + k * 2048), smem_desc_mn128(sa + Cfg::A_BYTES + k * 2048),
+                        Cfg::IDESC, (pt > pt0 || cmb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2cta(&empty[stage]);
+            if (pt == pt1 - 1 && cmb == p.ncombo - 1) umma_commit_2cta(tfull);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit_2cta(&empty[stage]);
-          if (pt == pt1 - 1) umma_commit_2cta(tfull);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         if (pt1 == pt0) umma_commit_2cta(tfull);   // empty slice: nothing accumulated (epilogue skips it)
       }
@@ -1332,9 +1346,9 @@ static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& commo
   g->OH = d->OH ? d->OH : d->HO; g->OW = d->OW ? d->OW : d->WO;
   g->oys = d->oys ? d->oys : 1; g->oxs = d->oxs ? d->oxs : 1; g->oyo = d->oyo; g->oxo = d->oxo;
   g->out = d->out;
-  g->add_src = (const __nv_bfloat16*)d->add_src;
+  g->add_src = d->add_src;
   g->add_H = d->add_H ? d->add_H : g->OH; g->add_W = d->add_W ? d->add_W : g->OW;
-  g->mask_src = (const __nv_bfloat16*)d->mask_src;
+  g->mask_src = d->mask_src;
   if (g->add_src) LDB_REQUIRE(((uintptr_t)g->add_src & 15) == 0, LDB_EINVAL, "conv2d_tc: add_src alignment");
   if (d->flat) {
     LDB_REQUIRE(d->ntaps == 1 && d->sx == 1 && d->sy == 1, LDB_EINVAL, "conv2d_tc: flat mode needs a 1x1 stride-1 conv");
@@ -1344,7 +1358,8 @@ static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& commo
     g->N = 1; g->HO = 1; g->WO = (int)M; g->TH = 1; g->TW = TILE_M;
     g->OH = 1; g->OW = (int)M; g->oys = g->oxs = 1; g->oyo = g->oxo = 0;
     g->add_H = 1; g->add_W = (int)M;
-    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)M, 1, 1};
+    // split mode: the planes are the 4th coordinate (S.N = 1, so plane p is "image" p)
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)M, 1, (cuuint64_t)common.planes};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)d->in_ld * 2 * (cuuint64_t)M,
                              (cuuint64_t)d->in_ld * 2 * (cuuint64_t)M};
     cuuint32_t box[4] = {KCH, TILE_M, 1, 1}, es[4] = {1, 1, 1, 1};
@@ -1362,7 +1377,8 @@ static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& commo
       }
     }
     g->TH = best_th; g->TW = TILE_M / best_th;
-    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    // split mode: `in` holds `planes` stacked [N,H,W,in_ld] tensors = images [0, planes*N)
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N * common.planes};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)d->in_ld * 2 * d->W,
                              (cuuint64_t)d->in_ld * 2 * d->W * d->H};
     cuuint32_t box[4] = {KCH, (cuuint32_t)(g->TW * d->sx), (cuuint32_t)(g->TH * d->sy), 1};
@@ -1386,10 +1402,10 @@ static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& commo
     return encode_map(m, base, 4, dims, strides, box, es, what, CU_TENSOR_MAP_SWIZZLE_NONE);
   };
   static const bool l2_prefetch = getenv("LDB200_NO_L2_PREFETCH") == nullptr;
-  if (l2_prefetch && g->add_src && ident && g->add_H == g->OH && g->add_W == g->OW && common.add_ld % 8 == 0 && !d->out_f32) {
+  if (l2_prefetch && g->add_src && !common.add_f32 && ident && g->add_H == g->OH && g->add_W == g->OW && common.add_ld % 8 == 0 && !d->out_f32) {
     if (aux_map(tmR, g->add_src, common.add_ld, "residual prefetch") == 0) g->pf_add = 1;
   }
-  if (l2_prefetch && g->mask_src && ident && common.mask_ld % 8 == 0) {
+  if (l2_prefetch && g->mask_src && !common.mask_f32 && ident && common.mask_ld % 8 == 0) {
     if (aux_map(tmM, g->mask_src, common.mask_ld, "mask prefetch") == 0) g->pf_mask = 1;
   }
   // TMA epilogue: one box = the 32 pixels of an epilogue warp (32 x 1 of a wide tile, TW x 32/TW of a narrow one)
@@ -1448,6 +1464,7 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
                 e->accumulate == d->accumulate && e->flat == d->flat && e->in_ld == d->in_ld &&
                 (e->add_src != nullptr) == (d->add_src != nullptr) && e->add_ld == d->add_ld &&
                 (e->mask_src != nullptr) == (d->mask_src != nullptr) && e->mask_ld == d->mask_ld &&
+                e->split == d->split && e->w_plane == d->w_plane && e->add_f32 == d->add_f32 && e->mask_f32 == d->mask_f32 &&
                 memcmp(e->tap_dx, d->tap_dx, sizeof(d->tap_dx)) == 0 && memcmp(e->tap_dy, d->tap_dy, sizeof(d->tap_dy)) == 0 &&
                 memcmp(e->tap_wk, d->tap_wk, sizeof(d->tap_wk)) == 0,
                 LDB_EINVAL, "conv2d_tc_multi: segment %d does not share weights / taps / epilogue with segment 0", i);
@@ -1472,20 +1489,40 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
   p.add_ld = d->add_ld ? d->add_ld : d->Cout;
   p.mask_ld = d->mask_ld ? d->mask_ld : d->out_ld;
   p.relu = d->relu; p.accumulate = d->accumulate;
+  p.add_f32 = d->add_f32; p.mask_f32 = d->mask_f32;
+  // split-bf16 mode (fp32-accurate): x = sum of `split` bf16 planes, W likewise; keep every plane product whose
+  // magnitude is >= 2^-24 of the leading one, smallest terms first
+  LDB_REQUIRE(d->split == 0 || d->split == 2 || d->split == 3, LDB_EINVAL, "conv2d_tc: split must be 0, 2 or 3");
+  p.planes = d->split ? d->split : 1;
+  p.w_plane = d->split ? d->w_plane : 0;
+  LDB_REQUIRE(!d->split || (d->w_plane % 8 == 0 && d->w_plane * p.planes <= d->w_k), LDB_EINVAL,
+              "conv2d_tc: split weights need w_plane %% 8 == 0 and planes * w_plane <= w_k");
+  if (d->split == 3) {
+    static const int ca[6] = {2, 0, 1, 1, 0, 0}, cw[6] = {0, 2, 1, 0, 1, 0};
+    p.ncombo = 6;
+    for (int i = 0; i < 6; ++i) { p.comb_a[i] = ca[i]; p.comb_w[i] = cw[i]; }
+  } else if (d->split == 2) {
+    static const int ca[3] = {1, 0, 0}, cw[3] = {0, 1, 0};
+    p.ncombo = 3;
+    for (int i = 0; i < 3; ++i) { p.comb_a[i] = ca[i]; p.comb_w[i] = cw[i]; }
+  } else {
+    p.ncombo = 1;
+  }
   // the fast epilogue path moves 16 bytes per access: bf16 rows need ld % 8 == 0, fp32 rows ld % 4 == 0
-  p.vec_ok = (d->out_ld % (d->out_f32 ? 4 : 8) == 0) && (!d->mask_src || p.mask_ld % 8 == 0) &&
-             (!d->add_src || p.add_ld % 8 == 0) && (!d->scale || ((uintptr_t)d->scale & 15) == 0) &&
+  p.vec_ok = (d->out_ld % (d->out_f32 ? 4 : 8) == 0) && (!d->mask_src || p.mask_ld % (d->mask_f32 ? 4 : 8) == 0) &&
+             (!d->add_src || p.add_ld % (d->add_f32 ? 4 : 8) == 0) && (!d->scale || ((uintptr_t)d->scale & 15) == 0) &&
              (!d->bias || ((uintptr_t)d->bias & 15) == 0);
   for (int i = 0; i < count; ++i)
     if ((uintptr_t)descs[i].out & 15) p.vec_ok = 0;
-  const bool shortk = d->ntaps * (p.Cin / KCH) <= 4 && getenv("LDB200_NO_SHORTK") == nullptr;
+  const bool shortk = p.ncombo * d->ntaps * (p.Cin / KCH) <= 4 && getenv("LDB200_NO_SHORTK") == nullptr;
   const int BN = shortk ? (d->Cout > 64 ? 128 : 64) : (d->Cout > 128 ? 256 : (d->Cout > 64 ? 128 : 64));
   p.tiles_n = (d->Cout + BN - 1) / BN;
   p.nseg = count;
   // TMA-staged epilogue: bf16 output with the identity pixel mapping (everything but the stride-2 dgrad parity
   // classes, fp32 head outputs and accumulating launches); LDB200_NO_TMA_EPI=1 forces the direct stores
   static const bool tma_epi_env = getenv("LDB200_NO_TMA_EPI") == nullptr;
-  p.tma_epi = tma_epi_env && BN >= 128 && !d->out_f32 && !d->accumulate && p.vec_ok && d->Cout % 64 == 0;
+  p.tma_epi = tma_epi_env && BN >= 128 && !d->out_f32 && !d->accumulate && p.vec_ok && d->Cout % 64 == 0 &&
+              !d->add_f32 && !d->mask_f32;
   for (int i = 0; i < count && p.tma_epi; ++i) {
     const ldb_conv_desc* e = &descs[i];
     const bool ident = e->oys <= 1 && e->oxs <= 1 && e->oyo == 0 && e->oxo == 0 && (e->OH == 0 || e->OH == e->HO) &&
@@ -1576,6 +1613,19 @@ extern "C" int ldb200_conv2d_wgrad_tc(const ldb_wgrad_desc* d, void* stream_) {
   }
   p.sx = d->sx; p.sy = d->sy; p.dw = d->dw; p.w_k = d->w_k;
   p.scale = d->scale; p.w_master = d->w_master; p.d_scale = d->d_scale;
+  LDB_REQUIRE(d->split == 0 || d->split == 2 || d->split == 3, LDB_EINVAL, "wgrad_tc: split must be 0, 2 or 3");
+  p.planes = d->split ? d->split : 1;
+  if (d->split == 3) {
+    static const int ca[6] = {2, 0, 1, 1, 0, 0}, cb[6] = {0, 2, 1, 0, 1, 0};
+    p.ncombo = 6;
+    for (int i = 0; i < 6; ++i) { p.comb_a[i] = ca[i]; p.comb_b[i] = cb[i]; }
+  } else if (d->split == 2) {
+    static const int ca[3] = {1, 0, 0}, cb[3] = {0, 1, 0};
+    p.ncombo = 3;
+    for (int i = 0; i < 3; ++i) { p.comb_a[i] = ca[i]; p.comb_b[i] = cb[i]; }
+  } else {
+    p.ncombo = 1;
+  }
   LDB_REQUIRE(!d->d_scale || (d->w_master && ((uintptr_t)d->w_master & 15) == 0), LDB_EINVAL, "wgrad_tc: d_scale needs aligned w_master");
   int best_th = 8, best_tiles = 1 << 30;
   for (int th = 1; th <= TILE_M; th *= 2) {
@@ -1603,7 +1653,7 @@ extern "C" int ldb200_conv2d_wgrad_tc(const ldb_wgrad_desc* d, void* stream_) {
   p.splits = splits;
   CUtensorMap tmA, tmB;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->WO, (cuuint64_t)d->HO, (cuuint64_t)d->N};
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->WO, (cuuint64_t)d->HO, (cuuint64_t)d->N * p.planes};
     cuuint64_t strides[3] = {(cuuint64_t)d->dy_ld * 2, (cuuint64_t)d->dy_ld * 2 * d->WO,
                              (cuuint64_t)d->dy_ld * 2 * d->WO * d->HO};
     cuuint32_t box[4] = {KCH, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1}, es[4] = {1, 1, 1, 1};
@@ -1611,7 +1661,7 @@ extern "C" int ldb200_conv2d_wgrad_tc(const ldb_wgrad_desc* d, void* stream_) {
     if (e) return e;
   }
   {
-    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N * p.planes};
     cuuint64_t strides[3] = {(cuuint64_t)d->x_ld * 2, (cuuint64_t)d->x_ld * 2 * d->W,
                              (cuuint64_t)d->x_ld * 2 * d->W * d->H};
     cuuint32_t box[4] = {KCH, (cuuint32_t)(p.TW * d->sx), (cuuint32_t)(p.TH * d->sy), 1};

@@ -27,6 +27,25 @@ __device__ __forceinline__ uint4 pack8(const float v[8]) {
   return q;
 }
 
+// 8 consecutive elements of a bf16 (one 16-byte access) or fp32 (two) tensor; `p` is 8-element aligned.
+// fp32 activations are the "parity" mode (split-bf16 convolutions): same kernels, wider elements.
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float v[8]);
+template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float v[8]) {
+  unpack8(__ldg(reinterpret_cast<const uint4*>(p)), v);
+}
+template <> __device__ __forceinline__ void ld8<float>(const float* p, float v[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const float v[8]);
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float v[8]) {
+  *reinterpret_cast<uint4*>(p) = pack8(v);
+}
+template <> __device__ __forceinline__ void st8<float>(float* p, const float v[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Stem: 7x7 stride-2 pad-3 conv on a 3-channel NCHW fp32 image as a GEMM: A[pixel, (r*7+s)*3+c],
 // K = 147 zero-padded to 192 (3 x 64) so the tcgen05 kernel can consume it in flat mode.
@@ -34,8 +53,9 @@ __device__ __forceinline__ uint4 pack8(const float v[8]) {
 // shared memory with coalesced loads, every thread then emits 16-byte (8-column) pieces of the rows.
 constexpr int IM_PX = 64;
 constexpr int IM_COLS = 2 * IM_PX + 5;   // input columns touched by 64 outputs
+template <typename T>
 __global__ void __launch_bounds__(256)
-stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int H, int W, int HO, int WO) {
+stem_im2col_kernel(const float* __restrict__ img, T* __restrict__ out, int N, int H, int W, int HO, int WO) {
   __shared__ float tile[3][7][IM_COLS + 1];
   const int xo0 = blockIdx.x * IM_PX, yo = blockIdx.y, n = blockIdx.z;
   const int xi0 = xo0 * 2 - 3, yi0 = yo * 2 - 3;
@@ -48,7 +68,7 @@ stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ ou
   }
   __syncthreads();
   const int npx = min(IM_PX, WO - xo0);
-  uint4* orow = reinterpret_cast<uint4*>(out + (((size_t)n * HO + yo) * WO + xo0) * 192);
+  T* orow = out + (((size_t)n * HO + yo) * WO + xo0) * 192;
   for (int j = threadIdx.x; j < npx * 24; j += 256) {
     const int px = j / 24, grp = j % 24;
     float v[8];
@@ -57,12 +77,13 @@ stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ ou
       const int k = grp * 8 + e;
       v[e] = (k < 147) ? tile[k % 3][k / 21][px * 2 + (k / 3) % 7] : 0.f;
     }
-    orow[j] = pack8(v);
+    st8<T>(orow + (size_t)j * 8, v);
   }
 }
 
-// 3x3 stride-2 pad-1 max pool, NHWC bf16, 8 channels per thread.
-__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int N,
+// 3x3 stride-2 pad-1 max pool, NHWC, 8 channels per thread.
+template <typename T>
+__global__ void maxpool3x3s2_kernel(const T* __restrict__ in, T* __restrict__ out, int N,
                                     int H, int W, int C, int HO, int WO) {
   const int cg = C / 8;
   const long long total = (long long)N * HO * WO * cg;
@@ -81,12 +102,12 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
         const int x = xo * 2 - 1 + s;
         if (x < 0 || x >= W) continue;
         float v[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(in + (((size_t)n * H + y) * W + x) * C) + g), v);
+        ld8<T>(in + (((size_t)n * H + y) * W + x) * C + g * 8, v);
 #pragma unroll
         for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
       }
     }
-    reinterpret_cast<uint4*>(out)[t] = pack8(m);
+    st8<T>(out + (size_t)t * 8, m);
   }
 }
 
@@ -99,30 +120,28 @@ constexpr int GN_CPG = 8;
 constexpr int GN_PIX = 256;       // pixels per block
 constexpr int GN_THREADS = 256;
 
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats,
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restrict__ x, float* __restrict__ stats,
                                                                int HW, int C) {
   const int G = C / GN_CPG;
   const int n = blockIdx.y, g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
   const int p0 = blockIdx.x * GN_PIX, p1 = min(p0 + GN_PIX, HW);
-  const uint4* base = reinterpret_cast<const uint4*>(x + (size_t)n * HW * C) + g;
-  const int rs = C / 8;   // uint4 per pixel row
+  const T* base = x + (size_t)n * HW * C + g * 8;
   float s = 0.f, ss = 0.f;
   int p = p0 + r0;
   for (; p + 3 * lanes < p1; p += 4 * lanes) {
-    uint4 q[4];
+    float v[4][8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) q[u] = __ldg(base + (size_t)(p + u * lanes) * rs);
+    for (int u = 0; u < 4; ++u) ld8<T>(base + (size_t)(p + u * lanes) * C, v[u]);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      float v[8];
-      unpack8(q[u], v);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { s += v[e]; ss += v[e] * v[e]; }
+      for (int e = 0; e < 8; ++e) { s += v[u][e]; ss += v[u][e] * v[u][e]; }
     }
   }
   for (; p < p1; p += lanes) {
     float v[8];
-    unpack8(__ldg(base + (size_t)p * rs), v);
+    ld8<T>(base + (size_t)p * C, v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s += v[e]; ss += v[e] * v[e]; }
   }
@@ -139,9 +158,10 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __nv_bfloat1
 }
 
 // y = relu((x - mean) * rstd * gamma + beta)   (relu optional)
+template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
-gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
-                const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int N, int HW, int C, float eps, int relu) {
+gn_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, T* __restrict__ y, int N, int HW, int C, float eps, int relu) {
   const int G = C / GN_CPG;
   const int n = blockIdx.y, g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
   const int p0 = blockIdx.x * GN_PIX, p1 = min(p0 + GN_PIX, HW);
@@ -154,44 +174,42 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s
     a[e] = rstd * __ldg(gamma + g * GN_CPG + e);
     b[e] = __ldg(beta + g * GN_CPG + e) - mean * a[e];
   }
-  const int rs = C / 8;
-  const uint4* xin = reinterpret_cast<const uint4*>(x + (size_t)n * HW * C) + g;
-  uint4* yout = reinterpret_cast<uint4*>(y + (size_t)n * HW * C) + g;
+  const T* xin = x + (size_t)n * HW * C + g * 8;
+  T* yout = y + (size_t)n * HW * C + g * 8;
   int p = p0 + r0;
   for (; p + 3 * lanes < p1; p += 4 * lanes) {
-    uint4 q[4];
+    float v[4][8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) q[u] = __ldg(xin + (size_t)(p + u * lanes) * rs);
+    for (int u = 0; u < 4; ++u) ld8<T>(xin + (size_t)(p + u * lanes) * C, v[u]);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      float v[8];
-      unpack8(q[u], v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float o = v[e] * a[e] + b[e];
-        v[e] = relu ? fmaxf(o, 0.f) : o;
+        const float o = v[u][e] * a[e] + b[e];
+        v[u][e] = relu ? fmaxf(o, 0.f) : o;
       }
-      yout[(size_t)(p + u * lanes) * rs] = pack8(v);
+      st8<T>(yout + (size_t)(p + u * lanes) * C, v[u]);
     }
   }
   for (; p < p1; p += lanes) {
     float v[8];
-    unpack8(__ldg(xin + (size_t)p * rs), v);
+    ld8<T>(xin + (size_t)p * C, v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float o = v[e] * a[e] + b[e];
       v[e] = relu ? fmaxf(o, 0.f) : o;
     }
-    yout[(size_t)p * rs] = pack8(v);
+    st8<T>(yout + (size_t)p * C, v);
   }
 }
 
 // GroupNorm+ReLU backward, pass 1: per-(n,group) sums of dxh and dxh*xh, per-channel dgamma/dbeta.
 //   g = dy * (y > 0), xh = (x - mean)*rstd, dxh = g*gamma
 // red: [N, G, 2] fp32 accumulated; dgamma/dbeta: [C] fp32 accumulated.
+template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
-gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
-                    const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
+gn_bwd_stats_kernel(const T* __restrict__ dy, const T* __restrict__ y,
+                    const T* __restrict__ x, const float* __restrict__ stats,
                     const float* __restrict__ gamma, float* __restrict__ red, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, int HW, int C, float eps) {
   const int G = C / GN_CPG;
@@ -205,24 +223,22 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
   for (int e = 0; e < 8; ++e) gam[e] = __ldg(gamma + g * GN_CPG + e);
 #pragma unroll
   for (int e = 0; e < 18; ++e) acc[e] = 0.f;   // [0]=sum dxh, [1]=sum dxh*xh, [2..9]=dgamma, [10..17]=dbeta
-  const int rs = C / 8;
-  const size_t img = (size_t)n * HW * C;
-  const uint4* pdy = reinterpret_cast<const uint4*>(dy + img) + g;
-  const uint4* py = reinterpret_cast<const uint4*>(y + img) + g;
-  const uint4* px = reinterpret_cast<const uint4*>(x + img) + g;
+  const size_t img = (size_t)n * HW * C + g * 8;
+  const T* pdy = dy + img;
+  const T* py = y + img;
+  const T* px = x + img;
   for (int p = p0 + r0; p < p1; p += 2 * lanes) {
     const bool two = p + lanes < p1;
-    uint4 q[6];
-    q[0] = __ldg(pdy + (size_t)p * rs); q[1] = __ldg(py + (size_t)p * rs); q[2] = __ldg(px + (size_t)p * rs);
+    float q[6][8];
+    ld8<T>(pdy + (size_t)p * C, q[0]); ld8<T>(py + (size_t)p * C, q[1]); ld8<T>(px + (size_t)p * C, q[2]);
     if (two) {
-      q[3] = __ldg(pdy + (size_t)(p + lanes) * rs); q[4] = __ldg(py + (size_t)(p + lanes) * rs);
-      q[5] = __ldg(px + (size_t)(p + lanes) * rs);
+      ld8<T>(pdy + (size_t)(p + lanes) * C, q[3]); ld8<T>(py + (size_t)(p + lanes) * C, q[4]);
+      ld8<T>(px + (size_t)(p + lanes) * C, q[5]);
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (u == 1 && !two) break;
-      float vd[8], vy[8], vx[8];
-      unpack8(q[3 * u], vd); unpack8(q[3 * u + 1], vy); unpack8(q[3 * u + 2], vx);
+      const float *vd = q[3 * u], *vy = q[3 * u + 1], *vx = q[3 * u + 2];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float gg = vy[e] > 0.f ? vd[e] : 0.f;
@@ -250,10 +266,11 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
 }
 
 // pass 2: dx = rstd * (dxh - mean(dxh) - xh * mean(dxh*xh))
+template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
-gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
-                    const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
-                    const float* __restrict__ gamma, const float* __restrict__ red, __nv_bfloat16* __restrict__ dx,
+gn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y,
+                    const T* __restrict__ x, const float* __restrict__ stats,
+                    const float* __restrict__ gamma, const float* __restrict__ red, T* __restrict__ dx,
                     int N, int HW, int C, float eps) {
   const int G = C / GN_CPG;
   const int n = blockIdx.y, g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
@@ -265,32 +282,31 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
   float gam[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) gam[e] = __ldg(gamma + g * GN_CPG + e);
-  const int rs = C / 8;
-  const size_t img = (size_t)n * HW * C;
-  const uint4* pdy = reinterpret_cast<const uint4*>(dy + img) + g;
-  const uint4* py = reinterpret_cast<const uint4*>(y + img) + g;
-  const uint4* px = reinterpret_cast<const uint4*>(x + img) + g;
-  uint4* pdx = reinterpret_cast<uint4*>(dx + img) + g;
+  const size_t img = (size_t)n * HW * C + g * 8;
+  const T* pdy = dy + img;
+  const T* py = y + img;
+  const T* px = x + img;
+  T* pdx = dx + img;
   for (int p = p0 + r0; p < p1; p += 2 * lanes) {
     const bool two = p + lanes < p1;
-    uint4 q[6];
-    q[0] = __ldg(pdy + (size_t)p * rs); q[1] = __ldg(py + (size_t)p * rs); q[2] = __ldg(px + (size_t)p * rs);
+    float q[6][8];
+    ld8<T>(pdy + (size_t)p * C, q[0]); ld8<T>(py + (size_t)p * C, q[1]); ld8<T>(px + (size_t)p * C, q[2]);
     if (two) {
-      q[3] = __ldg(pdy + (size_t)(p + lanes) * rs); q[4] = __ldg(py + (size_t)(p + lanes) * rs);
-      q[5] = __ldg(px + (size_t)(p + lanes) * rs);
+      ld8<T>(pdy + (size_t)(p + lanes) * C, q[3]); ld8<T>(py + (size_t)(p + lanes) * C, q[4]);
+      ld8<T>(px + (size_t)(p + lanes) * C, q[5]);
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (u == 1 && !two) break;
-      float vd[8], vy[8], vx[8];
-      unpack8(q[3 * u], vd); unpack8(q[3 * u + 1], vy); unpack8(q[3 * u + 2], vx);
+      float* vd = q[3 * u];
+      const float *vy = q[3 * u + 1], *vx = q[3 * u + 2];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float gg = vy[e] > 0.f ? vd[e] : 0.f;
         const float xh = (vx[e] - mean) * rstd;
         vd[e] = rstd * (gg * gam[e] - m1 - xh * m2);
       }
-      pdx[(size_t)(p + u * lanes) * rs] = pack8(vd);
+      st8<T>(pdx + (size_t)(p + u * lanes) * C, vd);
     }
   }
 }
@@ -298,7 +314,8 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
 // ---------------------------------------------------------------------------------------------
 // Backward of `fine += nearest_upsample(coarse)` (fpn.py:182-191): coarse_grad[n,yc,xc,:] +=
 // sum of fine_grad over the fine pixels that read it (src index = floor(dst * Hc / Hf)).
-__global__ void upsample_add_bwd_kernel(const __nv_bfloat16* __restrict__ dfine, __nv_bfloat16* __restrict__ dcoarse,
+template <typename T>
+__global__ void upsample_add_bwd_kernel(const T* __restrict__ dfine, T* __restrict__ dcoarse,
                                         int N, int Hf, int Wf, int Hc, int Wc, int C) {
   const int cg = C / 8;
   const long long total = (long long)N * Hc * Wc * cg;
@@ -311,29 +328,62 @@ __global__ void upsample_add_bwd_kernel(const __nv_bfloat16* __restrict__ dfine,
     const int y0 = (yc * Hf + Hc - 1) / Hc, y1 = min(((yc + 1) * Hf + Hc - 1) / Hc, Hf);
     const int x0 = (xc * Wf + Wc - 1) / Wc, x1 = min(((xc + 1) * Wf + Wc - 1) / Wc, Wf);
     float acc[8];
-    unpack8(reinterpret_cast<const uint4*>(dcoarse)[t], acc);
+    ld8<T>(dcoarse + (size_t)t * 8, acc);
     for (int y = y0; y < y1; ++y)
       for (int x = x0; x < x1; ++x) {
         float v[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dfine + (((size_t)n * Hf + y) * Wf + x) * C) + g), v);
+        ld8<T>(dfine + (((size_t)n * Hf + y) * Wf + x) * C + g * 8, v);
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] += v[e];
       }
-    reinterpret_cast<uint4*>(dcoarse)[t] = pack8(acc);
+    st8<T>(dcoarse + (size_t)t * 8, acc);
   }
 }
 
-// out = dy * (y > 0), bf16, 8 elements per thread
-__global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
-                                __nv_bfloat16* __restrict__ out, long long n8) {
+// out = dy * (y > 0), 8 elements per thread
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ out, long long n8) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n8;
        t += (long long)gridDim.x * blockDim.x) {
     float a[8], b[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + t), a);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(y) + t), b);
+    ld8<T>(dy + (size_t)t * 8, a);
+    ld8<T>(y + (size_t)t * 8, b);
 #pragma unroll
     for (int e = 0; e < 8; ++e) a[e] = b[e] > 0.f ? a[e] : 0.f;
-    reinterpret_cast<uint4*>(out)[t] = pack8(a);
+    st8<T>(out + (size_t)t * 8, a);
+  }
+}
+
+// x [rows, ld_in] fp32 -> `planes` stacked bf16 tensors [planes][rows, ld_out] with x ~= sum of the planes:
+// p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1) (each residual is exact in fp32).  Columns [C, ld_out)
+// are zero-filled.  Operand preparation of the split-bf16 ("parity") convolutions.
+__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int C,
+                                  int ld_in, int ld_out, int planes) {
+  const int cg = ld_out / 8;
+  const long long total = rows * cg;
+  const size_t plane = (size_t)rows * ld_out;
+  const bool vec = (ld_in % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % cg);
+    const long long r = t / cg;
+    float v[8];
+    const float* src = x + (size_t)r * ld_in + g * 8;
+    if (vec && g * 8 + 8 <= C) {
+      ld8<float>(src, v);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (g * 8 + e < C) ? __ldg(src + e) : 0.f;
+    }
+    for (int pl = 0; pl < planes; ++pl) {
+      float h[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        h[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+        v[e] -= h[e];
+      }
+      *reinterpret_cast<uint4*>(out + pl * plane + (size_t)r * ld_out + g * 8) = pack8(h);
+    }
   }
 }
 
@@ -504,21 +554,38 @@ static int grid_for(long long total, int threads = 256, int cap = 148 * 16) {
 
 using namespace ldb;
 
-extern "C" int ldb200_stem_im2col(const float* img, void* out, int N, int H, int W, void* stream_) {
+extern "C" int ldb200_stem_im2col(const float* img, void* out, int N, int H, int W, int out_dtype, void* stream_) {
   LDB_REQUIRE(img && out && N > 0 && H > 0 && W > 0, LDB_EINVAL, "stem_im2col: bad argument");
   const int HO = (H + 6 - 7) / 2 + 1, WO = (W + 6 - 7) / 2 + 1;
   dim3 grid((WO + IM_PX - 1) / IM_PX, HO, N);
-  stem_im2col_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(img, (__nv_bfloat16*)out, N, H, W, HO, WO);
+  if (out_dtype == LDB_F32)
+    stem_im2col_kernel<float><<<grid, 256, 0, (cudaStream_t)stream_>>>(img, (float*)out, N, H, W, HO, WO);
+  else
+    stem_im2col_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream_>>>(img, (__nv_bfloat16*)out, N, H, W, HO, WO);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int ldb200_maxpool3x3s2(const void* in, void* out, int N, int H, int W, int C, void* stream_) {
+extern "C" int ldb200_maxpool3x3s2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream_) {
   LDB_REQUIRE(in && out && C % 8 == 0, LDB_EINVAL, "maxpool: bad argument (C %% 8)");
   const int HO = (H + 2 - 3) / 2 + 1, WO = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)N * HO * WO * (C / 8);
-  maxpool3x3s2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out,
-                                                                          N, H, W, C, HO, WO);
+  if (dtype == LDB_F32)
+    maxpool3x3s2_kernel<float><<<grid_for(total), 256, 0, (cudaStream_t)stream_>>>((const float*)in, (float*)out, N, H, W, C, HO, WO);
+  else
+    maxpool3x3s2_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out,
+                                                                                          N, H, W, C, HO, WO);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_split_bf16(const float* x, int64_t rows, int C, int ld_in, int planes, void* out, int ld_out,
+                                 void* stream_) {
+  LDB_REQUIRE(x && out && rows >= 0 && C > 0 && ld_in >= C && ld_out >= C && ld_out % 8 == 0 && planes >= 1 && planes <= 3,
+              LDB_EINVAL, "split_bf16: bad argument (ld_out %% 8, 1 <= planes <= 3)");
+  if (rows == 0) return 0;
+  split_bf16_kernel<<<grid_for(rows * (ld_out / 8)), 256, 0, (cudaStream_t)stream_>>>(x, (__nv_bfloat16*)out, rows, C, ld_in,
+                                                                                      ld_out, planes);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -529,64 +596,81 @@ static int gn_check(int C, int G) {
   return 0;
 }
 
-extern "C" int ldb200_gn_stats(const void* x, float* stats, int N, int HW, int C, int G, void* stream_) {
+extern "C" int ldb200_gn_stats(const void* x, float* stats, int N, int HW, int C, int G, int dtype, void* stream_) {
   int e = gn_check(C, G);
   if (e) return e;
   LDB_REQUIRE(x && stats, LDB_EINVAL, "gn_stats: null pointer");
   cudaStream_t s = (cudaStream_t)stream_;
   LDB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * N * G, s));
   dim3 grid((HW + GN_PIX - 1) / GN_PIX, N);
-  gn_stats_kernel<<<grid, GN_THREADS, 0, s>>>((const __nv_bfloat16*)x, stats, HW, C);
+  if (dtype == LDB_F32) gn_stats_kernel<float><<<grid, GN_THREADS, 0, s>>>((const float*)x, stats, HW, C);
+  else gn_stats_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, s>>>((const __nv_bfloat16*)x, stats, HW, C);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int ldb200_gn_apply(const void* x, const float* stats, const float* gamma, const float* beta, void* y,
-                               int N, int HW, int C, int G, float eps, int relu, void* stream_) {
+                               int N, int HW, int C, int G, float eps, int relu, int dtype, void* stream_) {
   int e = gn_check(C, G);
   if (e) return e;
   LDB_REQUIRE(x && stats && gamma && beta && y, LDB_EINVAL, "gn_apply: null pointer");
   dim3 grid((HW + GN_PIX - 1) / GN_PIX, N);
-  gn_apply_kernel<<<grid, GN_THREADS, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, stats, gamma, beta,
-                                                                  (__nv_bfloat16*)y, N, HW, C, eps, relu);
+  if (dtype == LDB_F32)
+    gn_apply_kernel<float><<<grid, GN_THREADS, 0, (cudaStream_t)stream_>>>((const float*)x, stats, gamma, beta, (float*)y, N, HW, C, eps, relu);
+  else
+    gn_apply_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, stats, gamma, beta,
+                                                                                   (__nv_bfloat16*)y, N, HW, C, eps, relu);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int ldb200_gn_relu_bwd(const void* dy, const void* y, const void* x, const float* stats, const float* gamma,
                                   float* red_ws, float* dgamma, float* dbeta, void* dx, int N, int HW, int C, int G,
-                                  float eps, void* stream_) {
+                                  float eps, int dtype, void* stream_) {
   int e = gn_check(C, G);
   if (e) return e;
   LDB_REQUIRE(dy && y && x && stats && gamma && red_ws && dgamma && dbeta && dx, LDB_EINVAL, "gn_relu_bwd: null pointer");
   cudaStream_t s = (cudaStream_t)stream_;
   LDB_CUDA(cudaMemsetAsync(red_ws, 0, sizeof(float) * 2 * N * G, s));
   dim3 grid((HW + GN_PIX - 1) / GN_PIX, N);
-  gn_bwd_stats_kernel<<<grid, GN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)x,
-                                           stats, gamma, red_ws, dgamma, dbeta, HW, C, eps);
-  LDB_CUDA(cudaGetLastError());
-  gn_bwd_apply_kernel<<<grid, GN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
-                                                      (const __nv_bfloat16*)x, stats, gamma, red_ws, (__nv_bfloat16*)dx,
-                                                      N, HW, C, eps);
+  if (dtype == LDB_F32) {
+    gn_bwd_stats_kernel<float><<<grid, GN_THREADS, 0, s>>>((const float*)dy, (const float*)y, (const float*)x, stats, gamma,
+                                                         red_ws, dgamma, dbeta, HW, C, eps);
+    LDB_CUDA(cudaGetLastError());
+    gn_bwd_apply_kernel<float><<<grid, GN_THREADS, 0, s>>>((const float*)dy, (const float*)y, (const float*)x, stats, gamma,
+                                                         red_ws, (float*)dx, N, HW, C, eps);
+  } else {
+    gn_bwd_stats_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
+                                                                 (const __nv_bfloat16*)x, stats, gamma, red_ws, dgamma, dbeta, HW, C, eps);
+    LDB_CUDA(cudaGetLastError());
+    gn_bwd_apply_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
+                                                                 (const __nv_bfloat16*)x, stats, gamma, red_ws, (__nv_bfloat16*)dx,
+                                                                 N, HW, C, eps);
+  }
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int ldb200_upsample_add_bwd(const void* dfine, void* dcoarse, int N, int Hf, int Wf, int Hc, int Wc, int C,
-                                       void* stream_) {
+                                       int dtype, void* stream_) {
   LDB_REQUIRE(dfine && dcoarse && C % 8 == 0 && Hc <= Hf && Wc <= Wf, LDB_EINVAL, "upsample_add_bwd: bad argument");
   const long long total = (long long)N * Hc * Wc * (C / 8);
-  upsample_add_bwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)dfine,
-                                                                              (__nv_bfloat16*)dcoarse, N, Hf, Wf, Hc, Wc, C);
+  if (dtype == LDB_F32)
+    upsample_add_bwd_kernel<float><<<grid_for(total), 256, 0, (cudaStream_t)stream_>>>((const float*)dfine, (float*)dcoarse, N, Hf, Wf, Hc, Wc, C);
+  else
+    upsample_add_bwd_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)dfine,
+                                                                                               (__nv_bfloat16*)dcoarse, N, Hf, Wf, Hc, Wc, C);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int ldb200_relu_bwd(const void* dy, const void* y, void* out, int64_t numel, void* stream_) {
+extern "C" int ldb200_relu_bwd(const void* dy, const void* y, void* out, int64_t numel, int dtype, void* stream_) {
   LDB_REQUIRE(dy && y && out && numel % 8 == 0, LDB_EINVAL, "relu_bwd: bad argument (numel %% 8)");
-  relu_bwd_kernel<<<grid_for(numel / 8), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)dy,
-                                                                          (const __nv_bfloat16*)y, (__nv_bfloat16*)out,
-                                                                          numel / 8);
+  if (dtype == LDB_F32)
+    relu_bwd_kernel<float><<<grid_for(numel / 8), 256, 0, (cudaStream_t)stream_>>>((const float*)dy, (const float*)y, (float*)out, numel / 8);
+  else
+    relu_bwd_kernel<__nv_bfloat16><<<grid_for(numel / 8), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)dy,
+                                                                                           (const __nv_bfloat16*)y, (__nv_bfloat16*)out, numel / 8);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -237,7 +237,7 @@ class _LDLossFn(torch.autograd.Function):
         aux['targets_im'] = tg_im
         losses, d_cls, d_reg, d_im = ops.ld_loss_fused(
             cfg, cls_rows, reg_rows, aux['t_cls_rows'], aux['t_reg_rows'], x_rows, aux['t_x_rows'], tg_im, norm,
-            term_grad=aux['term_grad'], grad_dtype=torch.bfloat16, max_fg=max_fg,
+            term_grad=aux['term_grad'], grad_dtype=xs[0].dtype, max_fg=max_fg,
             d_cls_ld=dcls_ld, d_reg_ld=dreg_ld)
         ctx.head, ctx.aux = head, aux
         ctx.save_for_backward(*tensors, cls_rows, reg_rows, d_cls, d_reg, d_im)
@@ -269,7 +269,7 @@ class _LDLossFn(torch.autograd.Function):
         o = 0
         x_dense = None
         if aux['im_active']:
-            x_dense = torch.zeros(tg.pyr.rows, xs[0].shape[-1], dtype=torch.bfloat16, device=dev)
+            x_dense = torch.zeros(tg.pyr.rows, xs[0].shape[-1], dtype=xs[0].dtype, device=dev)
             tg_im = aux['targets_im']
             ops.scatter_add_rows(x_dense, d_im, tg_im.fg_rows, tg_im.counts[1:2])
         for l in range(nl):
@@ -619,7 +619,7 @@ class _LDv2LossFn(torch.autograd.Function):
         aux['targets_im'] = tg_im
         losses, d_score, d_kd, d_reg, d_im = ops.ld_loss_fused_v2(
             cfg, score_rows, feat_rows, reg_rows, aux['t_cls_rows'], aux['t_reg_rows'], x_rows, aux['t_x_rows'], tg_im,
-            norm, nfg, term_grad=aux['term_grad'], grad_dtype=torch.bfloat16, max_fg=max_fg, d_cls_ld=dcls_ld,
+            norm, nfg, term_grad=aux['term_grad'], grad_dtype=xs[0].dtype, max_fg=max_fg, d_cls_ld=dcls_ld,
             d_reg_ld=dreg_ld)
         d_feat, g_w1, g_b1, g_w2, g_b2 = ops.dgqp_backward(reg_rows, feat_rows, *qp, quality, d_score, d_reg, d_kd=d_kd,
                                                            reg_topk=head.reg_topk, add_mean=head.add_mean)
@@ -653,7 +653,7 @@ class _LDv2LossFn(torch.autograd.Function):
         o = 0
         x_dense = None
         if aux['im_active']:
-            x_dense = torch.zeros(tg.pyr.rows, xs[0].shape[-1], dtype=torch.bfloat16, device=dev)
+            x_dense = torch.zeros(tg.pyr.rows, xs[0].shape[-1], dtype=xs[0].dtype, device=dev)
             tg_im = aux['targets_im']
             ops.scatter_add_rows(x_dense, d_im, tg_im.fg_rows, tg_im.counts[1:2])
         for l in range(nl):

@@ -128,14 +128,14 @@ class KnowledgeDistillationSingleStageDetector(SingleStageDetector):
             raise NotImplementedError('LDHead needs output_feature=True (kd_one_stage.py:73-76 mis-binds its '
                                       'arguments otherwise; both COCO LD configs set it)')
         # opt-in (LDB200_FUSED_STEM=1, not yet GPU-verified): both stems in one tcgen05 launch, no im2col buffer
-        fused_stem = os.environ.get('LDB200_FUSED_STEM') is not None
+        fused_stem = os.environ.get('LDB200_FUSED_STEM') is not None and not engine.parity()
         if fused_stem:
             ws, afs = self.backbone.stem_params()
             wt, aft = self.teacher_model.backbone.stem_params()
             stem_s, stem_t = ops.stem_tc(img.float().contiguous(), torch.cat([ws, wt]).contiguous(), [afs, aft])
             return self._forward_train_fused_stem(img, stem_s, stem_t, img_metas, gt_bboxes, gt_labels,
                                                   gt_bboxes_ignore)
-        im2col = ops.stem_im2col(img.float().contiguous())
+        im2col = ops.stem_im2col(img.float().contiguous(), engine.act_dtype())
         # the frozen teacher and the student only share the input: run the teacher on a second stream so its
         # kernels fill the SMs the student's tails / latency-bound epilogues leave idle (also captured as a
         # fork/join inside the CUDA graph)
@@ -212,7 +212,12 @@ class LDTrainStep:
     (warm-up) and torch.optim.SGD (configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py:53,
     configs/_base_/schedules/schedule_1x.py)."""
 
-    def __init__(self, model, lr=0.01, momentum=0.9, weight_decay=1e-4, warmup_iters=500, warmup_ratio=0.001):
+    def __init__(self, model, lr=0.01, momentum=0.9, weight_decay=1e-4, warmup_iters=500, warmup_ratio=0.001,
+                 precision='bf16'):
+        """precision: 'bf16' = throughput mode (bf16 activations, single-pass tcgen05 MMAs); 'fp32' = parity mode
+        (fp32 activations, split-bf16 convolutions: matches the reference's fp32 arithmetic to ~1e-6 per conv)."""
+        assert precision in ('bf16', 'fp32')
+        self.precision = precision
         self.model = model
         self.base_lr, self.momentum, self.wd = lr, momentum, weight_decay
         self.warmup_iters, self.warmup_ratio = warmup_iters, warmup_ratio
@@ -251,6 +256,10 @@ class LDTrainStep:
         return self.base_lr
 
     def step(self, data, sync_logs=True):
+        with engine.precision(self.precision):
+            return self._step(data, sync_logs)
+
+    def _step(self, data, sync_logs):
         self.flat_g.zero_()
         engine.zero_pool_begin(self.flat_g.device)
         losses = self.model(**data)
@@ -272,6 +281,10 @@ class LDTrainStep:
     # ------------------------------------------------------------------ CUDA-graph replay
     def _body(self, data):
         """Everything of one iteration that depends only on device-resident state: captured once."""
+        with engine.precision(self.precision):
+            self._body_inner(data)
+
+    def _body_inner(self, data):
         self.flat_g.zero_()
         engine.zero_pool_begin(self.flat_g.device)
         losses = self.model(**data)

@@ -20,23 +20,61 @@ import torch
 from . import ops
 
 
+# ------------------------------------------------------------------------------------------------------
+# Precision modes.  'bf16' (default, the throughput mode): NHWC bf16 activations, bf16 x bf16 -> fp32 tcgen05 MMAs.
+# 'fp32' (the parity mode, SURVEY.md 7.3-1 / north_star "loss and grads within 1e-4 fp32"): NHWC fp32 activations and
+# gradients; every convolution / weight gradient runs on split-bf16 operands (x = p0 + p1 + p2, all plane products
+# down to 2^-24 accumulated in the fp32 TMEM accumulator), i.e. fp32-accurate results from the same tcgen05 kernels.
+_PRECISION = {'mode': 'bf16'}
+
+
+def set_precision(mode):
+    assert mode in ('bf16', 'fp32')
+    prev = _PRECISION['mode']
+    _PRECISION['mode'] = mode
+    return prev
+
+
+def parity():
+    return _PRECISION['mode'] == 'fp32'
+
+
+def act_dtype():
+    return torch.float32 if parity() else torch.bfloat16
+
+
+class precision:
+    """`with engine.precision('fp32'):` -- run the enclosed forward/backward in the fp32-accurate mode."""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = set_precision(self.mode)
+
+    def __exit__(self, *a):
+        set_precision(self.prev)
+
+
 def clear_step_cache(params=()):
     """Drop the bf16 operand copies cached on the parameters.  They are keyed by `_version`, which
     torch bumps for in-place torch ops -- but the fused SGD kernel updates the flat parameter buffer
     through raw pointers, so `LDTrainStep` invalidates them explicitly after every step."""
     for p in params:
-        p.__dict__.pop('_ldb_packed', None)
-        p.__dict__.pop('_ldb_dgrad', None)
+        for k in ('_ldb_packed', '_ldb_dgrad', '_ldb_packed32', '_ldb_dgrad32'):
+            p.__dict__.pop(k, None)
 
 
 def packed_weight(w):
     """[Cout,Cin,kh,kw] channels_last fp32 -> [Cout, kh*kw*Cin] bf16 (a cast, no transpose).
     Cached on the parameter (never in an id()-keyed dict: ids are reused after garbage collection)."""
-    hit = getattr(w, '_ldb_packed', None)
+    key = '_ldb_packed32' if parity() else '_ldb_packed'
+    hit = getattr(w, key, None)
     if hit is None or hit[0] != w._version or hit[1].device != w.device:
         co, ci, kh, kw = w.shape
-        hit = (w._version, w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(torch.bfloat16))
-        w._ldb_packed = hit
+        w2 = w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
+        hit = (w._version, ops.split_weight(w2) if parity() else w2.to(torch.bfloat16))
+        setattr(w, key, hit)
     return hit[1]
 
 
@@ -52,8 +90,9 @@ def _round64(c):
 
 def dgrad_weight(w, scale):
     """(scale*W) transposed for the data-gradient conv: [Cin, kh*kw*pad64(Cout)] bf16, zero padded."""
+    key = '_ldb_dgrad32' if parity() else '_ldb_dgrad'
     if scale is None:   # level-shared head convs: reuse across the five levels of one backward pass
-        hit = getattr(w, '_ldb_dgrad', None)
+        hit = getattr(w, key, None)
         if hit is not None and hit[0] == w._version and hit[1][0].device == w.device:
             return hit[1]
     co, ci, kh, kw = w.shape
@@ -64,9 +103,10 @@ def dgrad_weight(w, scale):
     cop = _round64(co)
     if cop != co:
         t = torch.nn.functional.pad(t, (0, cop - co))
-    out = (t.reshape(ci, kh * kw * cop).to(torch.bfloat16).contiguous(), cop)
+    t = t.reshape(ci, kh * kw * cop)
+    out = (ops.split_weight(t) if parity() else t.to(torch.bfloat16).contiguous(), cop)
     if scale is None:
-        w._ldb_dgrad = (w._version, out)
+        setattr(w, key, (w._version, out))
     return out
 
 
@@ -82,7 +122,7 @@ def conv_dgrad(g, w, scale, stride, pad, in_hw, out=None, accumulate=False, mask
                              accumulate=accumulate, mask=mask, add=add)
     assert stride == 2 and add is None
     if out is None:   # parity classes write disjoint pixels; untouched ones (1x1 s2) must read as zero
-        out = torch.zeros(n, h, w_, ci, dtype=torch.bfloat16, device=g.device)
+        out = torch.zeros(n, h, w_, ci, dtype=g.dtype, device=g.device)
         accumulate = False
     for py in range(2):
         for px in range(2):
@@ -132,9 +172,9 @@ class ConvAffineAct(torch.autograd.Function):
         stride, pad, relu, resampled, x_premask = ctx.cfg
         co, ci, kh, kw = weight.shape
         need_x, need_w, need_scale, need_shift, need_res = ctx.needs_input_grad[:5]
-        if dy.dtype != torch.bfloat16:
-            # fp32 head outputs: gradients arrive from the fused loss kernel already in bf16 rows
-            dy = dy.to(torch.bfloat16)
+        if dy.dtype != x.dtype:
+            # fp32 head outputs of the bf16 mode: bring the incoming gradient to the activation dtype
+            dy = dy.to(x.dtype)
         dy = dy.contiguous()
         g = ops.relu_bwd(dy, y) if relu else dy
         d_x = d_w = d_scale = d_shift = d_res = None

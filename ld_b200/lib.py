@@ -57,7 +57,8 @@ class ConvDesc(C.Structure):
                 ('oxs', C.c_int), ('oxo', C.c_int), ('out_ld', C.c_int), ('out_f32', C.c_int),
                 ('scale', C.c_void_p), ('bias', C.c_void_p), ('add_src', C.c_void_p), ('add_H', C.c_int),
                 ('add_W', C.c_int), ('add_ld', C.c_int), ('mask_src', C.c_void_p), ('mask_ld', C.c_int),
-                ('relu', C.c_int), ('accumulate', C.c_int)]
+                ('relu', C.c_int), ('accumulate', C.c_int), ('split', C.c_int), ('w_plane', C.c_int),
+                ('add_f32', C.c_int), ('mask_f32', C.c_int)]
 
 
 class WgradDesc(C.Structure):
@@ -65,7 +66,7 @@ class WgradDesc(C.Structure):
                 ('dy_ld', C.c_int), ('x', C.c_void_p), ('H', C.c_int), ('W', C.c_int), ('Cin', C.c_int),
                 ('x_ld', C.c_int), ('ntaps', C.c_int), ('tap_dx', C.c_int * 9), ('tap_dy', C.c_int * 9),
                 ('tap_wk', C.c_int * 9), ('sx', C.c_int), ('sy', C.c_int), ('dw', C.c_void_p), ('w_k', C.c_int),
-                ('scale', C.c_void_p), ('w_master', C.c_void_p), ('d_scale', C.c_void_p)]
+                ('scale', C.c_void_p), ('w_master', C.c_void_p), ('d_scale', C.c_void_p), ('split', C.c_int)]
 
 
 _SIGS = {
@@ -95,14 +96,15 @@ _SIGS = {
     'ldb200_conv2d_tc': (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     'ldb200_conv2d_tc_multi': (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
     'ldb200_conv2d_wgrad_tc': (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
-    'ldb200_stem_im2col': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ldb200_stem_im2col': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ldb200_split_bf16': (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     'ldb200_stem_tc': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7),
-    'ldb200_maxpool3x3s2': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
-    'ldb200_gn_stats': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
-    'ldb200_gn_apply': (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_float, C.c_int, C.c_void_p]),
-    'ldb200_gn_relu_bwd': (C.c_int, [C.c_void_p] * 9 + [C.c_int] * 4 + [C.c_float, C.c_void_p]),
-    'ldb200_upsample_add_bwd': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
-    'ldb200_relu_bwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]),
+    'ldb200_maxpool3x3s2': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    'ldb200_gn_stats': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    'ldb200_gn_apply': (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_float, C.c_int, C.c_int, C.c_void_p]),
+    'ldb200_gn_relu_bwd': (C.c_int, [C.c_void_p] * 9 + [C.c_int] * 4 + [C.c_float, C.c_int, C.c_void_p]),
+    'ldb200_upsample_add_bwd': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]),
+    'ldb200_relu_bwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int, C.c_void_p]),
     'ldb200_colsum': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ldb200_sgd_flat': (C.c_int, [C.c_void_p] * 3 + [C.c_int64] + [C.c_float] * 4 + [C.c_int, C.c_void_p]),
     'ldb200_sgd_flat_dev': (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_void_p, C.c_void_p]),
@@ -147,7 +149,7 @@ def load():
 _LAUNCHES = {'ldb200_ld_targets': 3, 'ldb200_ld_loss_prepass': 1, 'ldb200_ld_loss_fused': 1,
              'ldb200_scatter_add_rows': 1, 'ldb200_gi_region': 3, 'ldb200_gi_region_v2': 3, 'ldb200_ld_loss_prepass_v2': 1,
              'ldb200_ld_loss_fused_v2': 1, 'ldb200_dgqp_forward': 1, 'ldb200_dgqp_backward': 1, 'ldb200_conv2d_tc': 1, 'ldb200_conv2d_tc_multi': 1, 'ldb200_conv2d_wgrad_tc': 1,
-             'ldb200_stem_im2col': 1, 'ldb200_stem_tc': 1, 'ldb200_maxpool3x3s2': 1, 'ldb200_gn_stats': 1, 'ldb200_gn_apply': 1,
+             'ldb200_stem_im2col': 1, 'ldb200_split_bf16': 1, 'ldb200_stem_tc': 1, 'ldb200_maxpool3x3s2': 1, 'ldb200_gn_stats': 1, 'ldb200_gn_apply': 1,
              'ldb200_gn_relu_bwd': 2, 'ldb200_upsample_add_bwd': 1, 'ldb200_relu_bwd': 1, 'ldb200_colsum': 1,
              'ldb200_sgd_flat': 1, 'ldb200_sgd_flat_dev': 1, 'ldb200_bn_fold': 1, 'ldb200_bn_fold_bwd': 1, 'ldb200_mse_fwd_bwd': 1, 'ldb200_kl_dense_fwd_bwd': 1}
 launch_count = {'n': 0}

@@ -311,9 +311,52 @@ def pack_conv_weight_dgrad(w: torch.Tensor) -> torch.Tensor:
     return pack_conv_weight(w.transpose(0, 1))
 
 
+PARITY_PLANES = 3     # bf16 planes per fp32 operand in the fp32-accurate mode (3: ~2^-23, 2: ~2^-16 per product)
+
+
+def split_bf16(x, planes=None, ld_out=None):
+    """fp32 [..., C] (last dim contiguous, uniform row stride) -> [planes, rows, ld_out] bf16 with x ~= sum of planes
+    (ldb200_split_bf16): the operand format of the split-bf16 ("parity") convolutions."""
+    planes = planes or PARITY_PLANES
+    assert x.dtype == torch.float32 and x.stride(-1) == 1
+    c = x.shape[-1]
+    ld_in = x.stride(-2) if x.dim() > 1 else c
+    rows = x.numel() // c
+    # rows must be uniformly strided (a channel slice of a contiguous [..., ld] tensor)
+    chk = ld_in
+    for i in range(x.dim() - 2, -1, -1):
+        assert x.shape[i] == 1 or x.stride(i) == chk, 'split_bf16: rows must be uniformly strided'
+        chk *= x.shape[i]
+    ld_out = ld_out or (c + 7) // 8 * 8
+    out = torch.empty(planes, rows, ld_out, dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().ldb200_split_bf16(C.c_void_p(x.data_ptr()), rows, c, ld_in, planes, L.ptr(out), ld_out,
+                                       L.stream_ptr()), 'ldb200_split_bf16')
+    return out
+
+
+def split_weight(w2d, planes=None):
+    """[Cout, K] fp32 -> [Cout, planes, K8] bf16 (K8 = K rounded up to 8): the weight operand of a split-bf16 conv."""
+    planes = planes or PARITY_PLANES
+    co, k = w2d.shape
+    sp = split_bf16(w2d.contiguous().float(), planes)        # [planes, Cout, K8]
+    return sp.permute(1, 0, 2).contiguous()
+
+
 def _conv_desc(d, x, w_packed, cout, kh, kw, stride, pad, out, out_dtype, scale, bias, add, mask, relu, accumulate,
                flat, taps, out_hw, out_map):
-    assert x.dtype == torch.bfloat16 and x.dim() == 4
+    assert x.dim() == 4
+    keep = None
+    if x.dtype == torch.float32:
+        # fp32-accurate mode: split the activation into bf16 planes, weights arrive as [Cout, planes, K8]
+        assert w_packed.dim() == 3, 'fp32 activations need split weights (ops.split_weight)'
+        planes = w_packed.shape[1]
+        n_, h_, w__, c_ = x.shape
+        keep = split_bf16(x, planes)
+        x = keep[0].view(n_, h_, w__, -1)[..., :c_]
+        d.split, d.w_plane = planes, w_packed.shape[2]
+        out_dtype = torch.float32
+        w_packed = w_packed.view(cout, -1)
+    assert x.dtype == torch.bfloat16
     n, h, w_, cin = x.shape
     in_ld = x.stride(2)
     assert x.stride(3) == 1 and x.stride(1) == w_ * in_ld and x.stride(0) == h * w_ * in_ld
@@ -353,13 +396,15 @@ def _conv_desc(d, x, w_packed, cout, kh, kw, stride, pad, out, out_dtype, scale,
             assert t.dtype == torch.float32 and t.numel() == cout and t.is_contiguous()
             setattr(d, name, t.data_ptr())
     if add is not None:
-        assert add.dtype == torch.bfloat16 and add.stride(3) == 1
+        assert add.dtype in (torch.bfloat16, torch.float32) and add.stride(3) == 1
         d.add_src, d.add_H, d.add_W, d.add_ld = add.data_ptr(), add.shape[1], add.shape[2], add.stride(2)
+        d.add_f32 = int(add.dtype == torch.float32)
     if mask is not None:
-        assert mask.dtype == torch.bfloat16 and mask.shape[:3] == out.shape[:3]
+        assert mask.dtype in (torch.bfloat16, torch.float32) and mask.shape[:3] == out.shape[:3]
         d.mask_src, d.mask_ld = mask.data_ptr(), mask.stride(2)
+        d.mask_f32 = int(mask.dtype == torch.float32)
     d.relu, d.accumulate = int(relu), int(accumulate)
-    return out
+    return out, keep    # the split planes must stay referenced until the launch is enqueued (stream-ordered allocator)
 
 
 def conv2d_tc(x, w_packed, cout, kh=1, kw=1, stride=1, pad=0, out=None, out_dtype=torch.bfloat16,
@@ -368,9 +413,10 @@ def conv2d_tc(x, w_packed, cout, kh=1, kw=1, stride=1, pad=0, out=None, out_dtyp
     """NHWC bf16 convolution on tcgen05 (ldb200_conv2d_tc).  x: [N,H,W,Cin] bf16 contiguous (or a
     channel slice with stride(2) = ld).  Returns [N,HO,WO,Cout] NHWC `out_dtype`."""
     d = L.ConvDesc()
-    out = _conv_desc(d, x, w_packed, cout, kh, kw, stride, pad, out, out_dtype, scale, bias, add, mask, relu,
-                     accumulate, flat, taps, out_hw, out_map)
+    out, keep = _conv_desc(d, x, w_packed, cout, kh, kw, stride, pad, out, out_dtype, scale, bias, add, mask, relu,
+                           accumulate, flat, taps, out_hw, out_map)
     L.check(L.load().ldb200_conv2d_tc(C.byref(d), L.stream_ptr()), 'ldb200_conv2d_tc')
+    del keep
     return out
 
 
@@ -379,24 +425,27 @@ def conv2d_tc_multi(xs, w_packed, cout, kh=1, kw=1, stride=1, pad=0, outs=None, 
     """The same convolution on several inputs (the FPN levels of a level-shared head conv) in ONE launch."""
     n = len(xs)
     descs = (L.ConvDesc * n)()
-    res = []
+    res, keep = [], []
     for i, x in enumerate(xs):
-        res.append(_conv_desc(descs[i], x, w_packed, cout, kh, kw, stride, pad, None if outs is None else outs[i],
-                              out_dtype, scale, bias, None, None if masks is None else masks[i], relu, False, False,
-                              taps, None if taps is None else tuple(x.shape[1:3]), None))
+        o, k = _conv_desc(descs[i], x, w_packed, cout, kh, kw, stride, pad, None if outs is None else outs[i],
+                          out_dtype, scale, bias, None, None if masks is None else masks[i], relu, False, False,
+                          taps, None if taps is None else tuple(x.shape[1:3]), None)
+        res.append(o)
+        keep.append(k)
     L.check(L.load().ldb200_conv2d_tc_multi(descs, n, L.stream_ptr()), 'ldb200_conv2d_tc_multi')
+    del keep
     return res
 
 
 
 # ------------------------------------------------------------------------------------ glue kernels
-def stem_im2col(img):
-    """img [N,3,H,W] f32 NCHW -> ([N*HO*WO, 192] bf16, HO, WO)."""
+def stem_im2col(img, dtype=torch.bfloat16):
+    """img [N,3,H,W] f32 NCHW -> ([N*HO*WO, 192] bf16 (or f32: parity mode), HO, WO)."""
     n, c, h, w = img.shape
     assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
     ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-    out = torch.empty(n * ho * wo, 192, dtype=torch.bfloat16, device=img.device)
-    L.check(L.load().ldb200_stem_im2col(L.ptr(img), L.ptr(out), n, h, w, L.stream_ptr()), 'ldb200_stem_im2col')
+    out = torch.empty(n * ho * wo, 192, dtype=dtype, device=img.device)
+    L.check(L.load().ldb200_stem_im2col(L.ptr(img), L.ptr(out), n, h, w, _dt(dtype), L.stream_ptr()), 'ldb200_stem_im2col')
     return out, ho, wo
 
 
@@ -421,7 +470,7 @@ def stem_tc(img, weights, affines):
 def maxpool3x3s2(x):
     n, h, w, c = x.shape
     out = torch.empty(n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c, dtype=x.dtype, device=x.device)
-    L.check(L.load().ldb200_maxpool3x3s2(L.ptr(x), L.ptr(out), n, h, w, c, L.stream_ptr()), 'ldb200_maxpool3x3s2')
+    L.check(L.load().ldb200_maxpool3x3s2(L.ptr(x), L.ptr(out), n, h, w, c, _dt(x.dtype), L.stream_ptr()), 'ldb200_maxpool3x3s2')
     return out
 
 
@@ -431,9 +480,9 @@ def gn_relu_fwd(x, gamma, beta, groups=32, eps=1e-5, relu=True):
     lib = L.load()
     stats = torch.empty(n, groups, 2, dtype=torch.float32, device=x.device)
     y = torch.empty_like(x)
-    L.check(lib.ldb200_gn_stats(L.ptr(x), L.ptr(stats), n, h * w, c, groups, L.stream_ptr()), 'ldb200_gn_stats')
+    L.check(lib.ldb200_gn_stats(L.ptr(x), L.ptr(stats), n, h * w, c, groups, _dt(x.dtype), L.stream_ptr()), 'ldb200_gn_stats')
     L.check(lib.ldb200_gn_apply(L.ptr(x), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(y), n, h * w, c, groups,
-                                float(eps), int(relu), L.stream_ptr()), 'ldb200_gn_apply')
+                                float(eps), int(relu), _dt(x.dtype), L.stream_ptr()), 'ldb200_gn_apply')
     return y, stats
 
 
@@ -442,23 +491,27 @@ def gn_relu_bwd(dy, y, x, stats, gamma, dgamma, dbeta, groups=32, eps=1e-5):
     n, h, w, c = x.shape
     ws = torch.empty(n, groups, 2, dtype=torch.float32, device=x.device)
     dx = torch.empty_like(x)
+    assert dy.dtype == y.dtype == x.dtype
     L.check(L.load().ldb200_gn_relu_bwd(L.ptr(dy), L.ptr(y), L.ptr(x), L.ptr(stats), L.ptr(gamma), L.ptr(ws),
                                         L.ptr(dgamma), L.ptr(dbeta), L.ptr(dx), n, h * w, c, groups, float(eps),
-                                        L.stream_ptr()), 'ldb200_gn_relu_bwd')
+                                        _dt(x.dtype), L.stream_ptr()), 'ldb200_gn_relu_bwd')
     return dx
 
 
 def upsample_add_bwd(dfine, dcoarse):
     n, hf, wf, c = dfine.shape
     _, hc, wc, _ = dcoarse.shape
-    L.check(L.load().ldb200_upsample_add_bwd(L.ptr(dfine), L.ptr(dcoarse), n, hf, wf, hc, wc, c, L.stream_ptr()),
-            'ldb200_upsample_add_bwd')
+    assert dfine.dtype == dcoarse.dtype
+    L.check(L.load().ldb200_upsample_add_bwd(L.ptr(dfine), L.ptr(dcoarse), n, hf, wf, hc, wc, c, _dt(dfine.dtype),
+                                             L.stream_ptr()), 'ldb200_upsample_add_bwd')
     return dcoarse
 
 
 def relu_bwd(dy, y, out=None):
     out = torch.empty_like(dy) if out is None else out
-    L.check(L.load().ldb200_relu_bwd(L.ptr(dy), L.ptr(y), L.ptr(out), dy.numel(), L.stream_ptr()), 'ldb200_relu_bwd')
+    assert dy.dtype == y.dtype
+    L.check(L.load().ldb200_relu_bwd(L.ptr(dy), L.ptr(y), L.ptr(out), dy.numel(), _dt(dy.dtype), L.stream_ptr()),
+            'ldb200_relu_bwd')
     return out
 
 
@@ -479,10 +532,17 @@ def sgd_flat(w, g, buf, lr, momentum=0.9, weight_decay=1e-4, grad_scale=1.0, fir
 def conv2d_wgrad_tc(dy, x, dw, kh=1, kw=1, stride=1, pad=0, scale=None, w_master=None, d_scale=None):
     """dw [Cout, kh*kw*Cin] f32 (packed tap-major layout) += scale[co] * wgrad(dy [N,HO,WO,Cout], x [N,H,W,Cin])
     (bf16 NHWC); optionally d_scale[co] += <w_master[co], wgrad[co]>."""
-    assert dy.dtype == x.dtype == torch.bfloat16 and dw.dtype == torch.float32 and dw.is_contiguous()
+    assert dy.dtype == x.dtype and dw.dtype == torch.float32 and dw.is_contiguous()
     n, ho, wo, cout = dy.shape
     _, h, w_, cin = x.shape
     d = L.WgradDesc()
+    keep = None
+    if dy.dtype == torch.float32:     # fp32-accurate mode: both operands as bf16 planes
+        keep = (split_bf16(dy), split_bf16(x))
+        dy = keep[0][0].view(n, ho, wo, -1)[..., :cout]
+        x = keep[1][0].view(n, h, w_, -1)[..., :cin]
+        d.split = keep[0].shape[0]
+    assert dy.dtype == torch.bfloat16
     d.dy, d.N, d.HO, d.WO, d.Cout, d.dy_ld = dy.data_ptr(), n, ho, wo, cout, dy.stride(2)
     d.x, d.H, d.W, d.Cin, d.x_ld = x.data_ptr(), h, w_, cin, x.stride(2)
     taps = [(s - pad, r - pad, (r * kw + s) * cin) for r in range(kh) for s in range(kw)]

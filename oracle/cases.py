@@ -28,6 +28,18 @@ STEP_CASES = [
     ('s_r18_r18_2x128x160', 18, 18, 2, 128, 160, 21),
     ('s_r50_r101_2x256x320', 50, 101, 2, 256, 320, 22),
 ]
+# BASELINE.json configs[0]: "ld_gflv1_r101_r50_fpn_coco_1x.py, 2 synthetic 800x800 images, CPU-only 1 iter (loss parity
+# vs reference)".  Compared only in the fp32-accurate ("parity") mode of the CUDA path.
+STEP_CASE_CONFIG1 = ('s_r50_r101_2x800x800', 50, 101, 2, 800, 800, 23)
+
+
+def grad_projection(name, grad):
+    """<grad, r_name> with a seeded standard-normal r of the gradient's shape: one number per parameter tensor that
+    moves with EVERY element (a full-gradient fingerprint small enough to commit for all 175 tensors)."""
+    import zlib
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7fffffff)
+    r = torch.randn(grad.numel(), generator=g, dtype=torch.float64)
+    return float(torch.dot(grad.detach().double().flatten().cpu(), r))
 
 
 def featmap_sizes(h, w):

@@ -197,8 +197,8 @@ def gen_steps_v2():
         print(name, {k: round(v, 5) for k, v in log.items()})
 
 
-def gen_steps():
-    for name, sd, td, n, h, w, seed in cases.STEP_CASES:
+def gen_steps(case_list=None):
+    for name, sd, td, n, h, w, seed in (case_list or cases.STEP_CASES):
         cfg = rh.load_model_cfg()
         cfg['backbone']['depth'] = sd
         cfg['neck']['in_channels'] = [64, 128, 256, 512] if sd < 50 else [256, 512, 1024, 2048]
@@ -223,6 +223,8 @@ def gen_steps():
                 'backbone.layer4.0.bn1.weight' if sd >= 50 else 'backbone.layer4.0.bn1.weight']
         named = dict(m.named_parameters())
         gold['grads'] = {k: named[k].grad.clone() for k in keep}
+        if case_list is not None:   # later fixtures: a fingerprint of EVERY gradient tensor (cases.grad_projection)
+            gold['grad_proj'] = {k: cases.grad_projection(k, p.grad) for k, p in named.items() if p.grad is not None}
         torch.save(gold, os.path.join(OUT, name + '.pt'))
         print(name, {k: round(v, 5) for k, v in log.items()})
 
@@ -260,6 +262,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
+    if '--config1' in sys.argv:      # round 2: BASELINE configs[0] only (the other fixtures stay byte-identical)
+        gen_steps([cases.STEP_CASE_CONFIG1])
+        return
     head = rh.reference_head()
     gen_targets(head)
     gen_losses(head)

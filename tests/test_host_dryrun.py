@@ -157,3 +157,17 @@ def test_head_loss_apis_host_logic(fake_backend):
                         (None, d2['t_reg'], d2['t_cls']), lv['x'], d2['t_x'], d2['img_metas'])
     sum(sum(v) for v in losses.values()).backward()
     assert all(t.grad is not None and t.grad.shape == t.shape for grp in lv.values() for t in grp)
+
+
+@pytest.mark.parametrize('student', ['r18', 'r50'])
+def test_parity_mode_train_step_host_logic(fake_backend, student):
+    """fp32 ("parity") mode: fp32 activations, every conv / wgrad on split-bf16 operands (ldb200_split_bf16 before
+    each launch), same module graph."""
+    from ld_b200 import engine
+    m = ld_b200.build_detector(ConfigDict(presets.ld_model(student, teacher_depth=18))).train()
+    ts = ld_b200.LDTrainStep(m, lr=0.001, warmup_iters=4, precision='fp32')
+    ts.step(_batch(), sync_logs=False)
+    assert not engine.parity()                      # the mode is scoped to the step
+    convs = fake_backend.count('ldb200_conv2d_tc') + fake_backend.count('ldb200_conv2d_tc_multi')
+    assert convs > 0 and fake_backend.count('ldb200_split_bf16') > convs    # activations + weights
+    _check_grads(m)

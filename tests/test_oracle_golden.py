@@ -82,7 +82,7 @@ def test_loss_gibox(golden_dir, case):
         assert torch.allclose(leaves['reg'][l].grad.norm(), gold['grad_reg_norm'][l], rtol=1e-5)
 
 
-@pytest.mark.parametrize('case', cases.STEP_CASES, ids=lambda c: c[0])
+@pytest.mark.parametrize('case', cases.STEP_CASES + [cases.STEP_CASE_CONFIG1], ids=lambda c: c[0])
 def test_full_step(golden_dir, case):
     name, sd, td, n, h, w, seed = case
     gold = _load(golden_dir, name)
@@ -100,6 +100,9 @@ def test_full_step(golden_dir, case):
         assert abs(float(g.double().norm()) - float(st[0])) <= 1e-4 * float(st[0]) + 1e-9, k
     for k, g in gold['grads'].items():
         assert torch.allclose(named[k].grad, g, rtol=1e-4, atol=1e-6 * float(g.abs().max())), k
+    for k, pr in gold.get('grad_proj', {}).items():     # fingerprint of every element of every gradient tensor
+        nrm = float(gold['grad_stats'][k][0])
+        assert abs(cases.grad_projection(k, named[k].grad) - pr) <= 1e-4 * nrm * named[k].numel() ** 0.5 + 1e-9, k
 
 
 @pytest.mark.parametrize('case', cases.LOSS_CASES_V2, ids=lambda c: c[0])
