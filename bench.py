@@ -25,6 +25,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault('LDB200_ALLOW_RANDOM_INIT', '1')   # synthetic benchmark: seeded random weights, no checkpoints
 
 FLOP_PER_IMAGE = 1.8356e12          # 917.79 GMAC (student fwd+bwd 620.26, teacher fwd 297.53) x 2
 GLOBAL_BATCH = 16

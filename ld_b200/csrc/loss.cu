@@ -259,10 +259,17 @@ __global__ void __launch_bounds__(LOSS_THREADS, 3) ld_loss_fused_kernel(LossPara
           qflp_neg(xv.z, P.beta, lo[2], gr[2]);
           qflp_neg(xv.w, P.beta, lo[3], gr[3]);
         } else {
-          qfl_neg_fast(xv.x, P.beta, lo[0], gr[0]);
-          qfl_neg_fast(xv.y, P.beta, lo[1], gr[1]);
-          qfl_neg_fast(xv.z, P.beta, lo[2], gr[2]);
-          qfl_neg_fast(xv.w, P.beta, lo[3], gr[3]);
+          if (sizeof(GT) == 4) {   // fp32 gradients (parity mode / loss API): precise exp / log1p, no approximations
+            qfl_neg(xv.x, P.beta, lo[0], gr[0]);
+            qfl_neg(xv.y, P.beta, lo[1], gr[1]);
+            qfl_neg(xv.z, P.beta, lo[2], gr[2]);
+            qfl_neg(xv.w, P.beta, lo[3], gr[3]);
+          } else {
+            qfl_neg_fast(xv.x, P.beta, lo[0], gr[0]);
+            qfl_neg_fast(xv.y, P.beta, lo[1], gr[1]);
+            qfl_neg_fast(xv.z, P.beta, lo[2], gr[2]);
+            qfl_neg_fast(xv.w, P.beta, lo[3], gr[3]);
+          }
         }
         acc += sc * ((lo[0] + lo[1]) + (lo[2] + lo[3]));
         if (wg) {

@@ -15,6 +15,66 @@ from .config import Config
 from .registry import DETECTORS, build_backbone, build_head, build_neck
 
 
+# The reference loads `pretrained` (torchvision://resnetNN, downloaded) and `teacher_ckpt` through mmcv's
+# load_checkpoint, which raises on a missing file (kd_one_stage.py:40-44, single_stage.py:35-50).  There is no network
+# here, so a checkpoint that cannot be found is an ERROR unless random initialisation is explicitly allowed
+# (synthetic-data benchmarks and tests): `with ld_b200.detectors.allow_random_init(): build_detector(cfg)` or
+# LDB200_ALLOW_RANDOM_INIT=1.
+_RANDOM_INIT = {'ok': False}
+
+
+def _random_ok():
+    return _RANDOM_INIT['ok'] or os.environ.get('LDB200_ALLOW_RANDOM_INIT') is not None
+
+
+class allow_random_init:
+    def __enter__(self):
+        self.prev = _RANDOM_INIT['ok']
+        _RANDOM_INIT['ok'] = True
+
+    def __exit__(self, *a):
+        _RANDOM_INIT['ok'] = self.prev
+
+
+def _find_checkpoint(spec):
+    """A local file for `spec`: a path, or torchvision://NAME looked up under $LD_B200_PRETRAINED_DIR and torch hub's
+    checkpoint cache (NAME*.pth).  None when nothing is found."""
+    spec = str(spec)
+    if os.path.isfile(spec):
+        return spec
+    if spec.startswith('torchvision://'):
+        import glob
+        name = spec.split('://', 1)[1]
+        roots = [os.environ.get('LD_B200_PRETRAINED_DIR', ''), os.path.join(torch.hub.get_dir(), 'checkpoints')]
+        for r in roots:
+            hits = sorted(glob.glob(os.path.join(r, name + '*.pth'))) if r else []
+            if hits:
+                return hits[0]
+    return None
+
+
+def load_checkpoint_into(module, spec, what, prefix_candidates=('',)):
+    """mmcv.runner.load_checkpoint semantics: missing file -> error (unless random init is allowed); missing /
+    unexpected keys are reported, not hidden."""
+    import warnings
+    path = _find_checkpoint(spec)
+    if path is None:
+        if _random_ok():
+            warnings.warn(f'{what}: checkpoint {spec!r} not found -- keeping the RANDOM initialisation '
+                          f'(allowed by allow_random_init / LDB200_ALLOW_RANDOM_INIT)')
+            return False
+        raise FileNotFoundError(f'{what}: checkpoint {spec!r} not found (no network on this box: put the file under '
+                                f'$LD_B200_PRETRAINED_DIR, or opt into random init with '
+                                f'ld_b200.detectors.allow_random_init() / LDB200_ALLOW_RANDOM_INIT=1)')
+    ckpt = torch.load(path, map_location='cpu', weights_only=False)
+    sd = ckpt.get('state_dict', ckpt) if isinstance(ckpt, dict) else ckpt
+    res = module.load_state_dict(sd, strict=False)
+    if res.missing_keys or res.unexpected_keys:
+        warnings.warn(f'{what}: loaded {path} with {len(res.missing_keys)} missing and {len(res.unexpected_keys)} '
+                      f'unexpected keys; missing: {res.missing_keys[:8]} unexpected: {res.unexpected_keys[:8]}')
+    return True
+
+
 class BaseDetector(nn.Module):
     """detectors/base.py: forward dispatch, train_step, _parse_losses."""
 
@@ -71,14 +131,14 @@ class SingleStageDetector(BaseDetector):
         return hasattr(self, 'neck') and self.neck is not None
 
     def init_weights(self, pretrained=None):
-        if isinstance(pretrained, str):
-            # the reference downloads torchvision://resnetNN here; there is no network on the B200 box, the
-            # caller loads weights afterwards (load_state_dict / synth.seeded_init)
-            pretrained = None
-        self.backbone.init_weights(pretrained=pretrained)
+        """single_stage.py:35-50.  A `pretrained` string is resolved to a local file (no download here); a file that
+        cannot be found raises unless random init is allowed."""
+        self.backbone.init_weights(pretrained=None)
         if self.with_neck:
             self.neck.init_weights()
         self.bbox_head.init_weights()
+        if isinstance(pretrained, str):
+            load_checkpoint_into(self.backbone, pretrained, f'{type(self).__name__}.backbone pretrained')
 
     def extract_feat(self, img, im2col=None, stem_out=None):
         x = self.backbone(img, im2col=im2col) if stem_out is None else self.backbone(img, stem_out=stem_out)
@@ -116,9 +176,8 @@ class KnowledgeDistillationSingleStageDetector(SingleStageDetector):
         tmodel = tmodel.to_dict() if hasattr(tmodel, 'to_dict') else dict(tmodel)
         from .config import ConfigDict
         self.teacher_model = build_detector(ConfigDict(tmodel))
-        if teacher_ckpt is not None and os.path.isfile(str(teacher_ckpt)):
-            ckpt = torch.load(teacher_ckpt, map_location='cpu')
-            self.teacher_model.load_state_dict(ckpt.get('state_dict', ckpt), strict=False)
+        if teacher_ckpt is not None:
+            load_checkpoint_into(self.teacher_model, teacher_ckpt, 'teacher_ckpt')
         for p in self.teacher_model.parameters():
             p.requires_grad = False
 
@@ -202,6 +261,8 @@ class KnowledgeDistillationSingleStageDetector(SingleStageDetector):
 
 
 class LDTrainStep:
+
+
     """One data-parallel LD training iteration on B200:
 
         zero flat grad -> forward (student + teacher) -> fused loss -> backward -> ONE NCCL all-reduce of
@@ -212,12 +273,17 @@ class LDTrainStep:
     (warm-up) and torch.optim.SGD (configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py:53,
     configs/_base_/schedules/schedule_1x.py)."""
 
+    lr_steps, lr_gamma = (), 0.1      # class defaults: no step decay unless the constructor is given `lr_steps`
+
     def __init__(self, model, lr=0.01, momentum=0.9, weight_decay=1e-4, warmup_iters=500, warmup_ratio=0.001,
-                 precision='bf16'):
+                 precision='bf16', lr_steps=(), lr_gamma=0.1):
         """precision: 'bf16' = throughput mode (bf16 activations, single-pass tcgen05 MMAs); 'fp32' = parity mode
         (fp32 activations, split-bf16 convolutions: matches the reference's fp32 arithmetic to ~1e-6 per conv)."""
         assert precision in ('bf16', 'fp32')
         self.precision = precision
+        # mmcv StepLrUpdaterHook (configs/_base_/schedules/schedule_1x.py: step=[8, 11] epochs): lr_steps are given in
+        # ITERATIONS here (epoch * iterations_per_epoch), lr = base * gamma ** (number of steps passed)
+        self.lr_steps, self.lr_gamma = tuple(sorted(lr_steps)), lr_gamma
         self.model = model
         self.base_lr, self.momentum, self.wd = lr, momentum, weight_decay
         self.warmup_iters, self.warmup_ratio = warmup_iters, warmup_ratio
@@ -250,10 +316,30 @@ class LDTrainStep:
 
     def lr_at(self, it):
         """mmcv LrUpdaterHook, warmup='linear': lr = base * (1 - (1 - it/warmup_iters) * (1 - ratio))."""
+        regular = self.base_lr * self.lr_gamma ** sum(1 for s_ in self.lr_steps if it >= s_)
         if it < self.warmup_iters:
             k = (1 - it / self.warmup_iters) * (1 - self.warmup_ratio)
-            return self.base_lr * (1 - k)
-        return self.base_lr
+            return regular * (1 - k)
+        return regular
+
+    def state_dict(self):
+        """Optimizer state for checkpoint / resume (mmcv CheckpointHook saves `optimizer` + `meta.iter`): momentum
+        buffer (flat, same order as `self.params`), iteration counter and hyper-parameters."""
+        return dict(iter=self.iter, momentum_buffer=self.flat_m.detach().clone(), base_lr=self.base_lr,
+                    momentum=self.momentum, weight_decay=self.wd, warmup_iters=self.warmup_iters,
+                    warmup_ratio=self.warmup_ratio, lr_steps=self.lr_steps, lr_gamma=self.lr_gamma,
+                    param_shapes=[tuple(p.shape) for p in self.params])
+
+    def load_state_dict(self, sd):
+        assert [tuple(p.shape) for p in self.params] == list(sd['param_shapes']), 'optimizer state of another model'
+        self.flat_m.copy_(sd['momentum_buffer'])
+        self.iter = int(sd['iter'])
+        self.base_lr, self.momentum, self.wd = sd['base_lr'], sd['momentum'], sd['weight_decay']
+        self.warmup_iters, self.warmup_ratio = sd['warmup_iters'], sd['warmup_ratio']
+        self.lr_steps, self.lr_gamma = tuple(sd['lr_steps']), sd['lr_gamma']
+        engine.clear_step_cache(self.params)
+        if hasattr(self, '_hyper'):
+            self._set_hyper()
 
     def step(self, data, sync_logs=True):
         with engine.precision(self.precision):

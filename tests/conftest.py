@@ -8,6 +8,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+# synthetic-weight tests: a `pretrained=` / `teacher_ckpt=` that cannot be found is an error by default
+# (ld_b200/detectors.py load_checkpoint_into); tests/test_config_dropin.py checks that default explicitly
+os.environ.setdefault('LDB200_ALLOW_RANDOM_INIT', '1')
 
 
 def pytest_configure(config):

@@ -105,3 +105,45 @@ def test_warmup_schedule():
     s.base_lr, s.warmup_iters, s.warmup_ratio = 0.01, 500, 0.001
     assert abs(s.lr_at(0) - 0.01 * 0.001) < 1e-12 and abs(s.lr_at(250) - 0.01 * (1 - 0.5 * 0.999)) < 1e-12
     assert s.lr_at(500) == 0.01
+
+
+def test_missing_checkpoints_are_errors_by_default(monkeypatch):
+    """mmcv's load_checkpoint raises on a missing file (kd_one_stage.py:40-44); so does the port unless random
+    initialisation is explicitly allowed (a silently random teacher trains against noise)."""
+    import pytest
+    import ld_b200
+    from ld_b200 import detectors, presets
+    from ld_b200.config import ConfigDict
+    monkeypatch.delenv('LDB200_ALLOW_RANDOM_INIT', raising=False)
+    cfg = ConfigDict(presets.ld_model('r18', teacher_depth=18))
+    cfg.teacher_config.model.pretrained = None
+    cfg.teacher_ckpt = '/nonexistent/gfl_r101.pth'
+    with pytest.raises(FileNotFoundError):
+        ld_b200.build_detector(cfg)
+    cfg.teacher_ckpt = None
+    cfg.pretrained = 'torchvision://resnet18'
+    monkeypatch.setenv('LD_B200_PRETRAINED_DIR', '/nonexistent')
+    monkeypatch.setattr('torch.hub.get_dir', lambda: '/nonexistent')
+    with pytest.raises(FileNotFoundError):
+        ld_b200.build_detector(cfg)
+    with detectors.allow_random_init(), pytest.warns(UserWarning, match='RANDOM'):
+        ld_b200.build_detector(cfg)
+
+
+def test_train_step_schedule_and_state_dict():
+    """LrUpdaterHook arithmetic (linear warm-up x step decay) and optimizer-state round trip of LDTrainStep."""
+    import torch
+    import ld_b200
+    from ld_b200 import presets
+    from ld_b200.config import ConfigDict
+    m = ld_b200.build_detector(ConfigDict(presets.ld_model('r18', teacher_depth=18)))
+    ts = ld_b200.LDTrainStep(m, lr=0.01, warmup_iters=500, warmup_ratio=0.001, lr_steps=(8 * 7330, 11 * 7330))
+    assert abs(ts.lr_at(0) - 0.01 * 0.001) < 1e-12 and abs(ts.lr_at(250) - 0.01 * (1 - 0.5 * 0.999)) < 1e-12
+    assert ts.lr_at(500) == 0.01 and abs(ts.lr_at(8 * 7330) - 0.001) < 1e-12 and abs(ts.lr_at(11 * 7330) - 1e-4) < 1e-12
+    ts.flat_m.normal_()
+    ts.iter = 1234
+    sd = ts.state_dict()
+    ts2 = ld_b200.LDTrainStep(m, lr=0.5)
+    ts2.load_state_dict(sd)
+    assert ts2.iter == 1234 and ts2.base_lr == 0.01 and torch.equal(ts2.flat_m, sd['momentum_buffer'])
+    assert ts2.lr_at(9 * 7330) == ts.lr_at(9 * 7330)

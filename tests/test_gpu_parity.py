@@ -38,7 +38,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize('planes,tol', [(3, 2e-6), (2, 2e-4)])
+@pytest.mark.parametrize('planes,tol', [(3, 1e-5), (2, 2e-4)])
 @pytest.mark.parametrize('case', CONV_CASES, ids=lambda c: 'x'.join(map(str, c)))
 def test_split_conv_fprop_matches_fp64(case, planes, tol):
     from ld_b200 import ops
@@ -71,7 +71,7 @@ def test_split_conv_multi_level_and_mask():
     torch.cuda.synchronize()
     for x, m, y in zip(xs, masks, ys):
         want = F.conv2d(x.double().permute(0, 3, 1, 2), wt.double(), None, 1, 1).permute(0, 2, 3, 1) * (m > 0)
-        assert relerr(y, want) <= 2e-6
+        assert relerr(y, want) <= 1e-5
 
 
 @pytest.mark.parametrize('case', [(2, 25, 42, 256, 256, 3, 1, 1), (2, 33, 47, 128, 128, 3, 2, 1), (2, 20, 28, 128, 512, 1, 1, 0),
@@ -93,8 +93,8 @@ def test_split_wgrad_and_dgrad_match_fp64(case):
     with engine.precision('fp32'):
         dx = engine.conv_dgrad(dy, wt, None, stride, pad, (h, w))
     torch.cuda.synchronize()
-    assert relerr(dw.view(cout, k, k, cin).permute(0, 3, 1, 2), wd.grad) <= 5e-6
-    assert relerr(dx, xd.grad.permute(0, 2, 3, 1)) <= 5e-6
+    assert relerr(dw.view(cout, k, k, cin).permute(0, 3, 1, 2), wd.grad) <= 1e-5
+    assert relerr(dx, xd.grad.permute(0, 2, 3, 1)) <= 1e-5
 
 
 # ---------------------------------------------------------------------------------------------- whole step

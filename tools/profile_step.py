@@ -2,6 +2,7 @@
     python tools/profile_step.py [batch] [student]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import os as _os; _os.environ.setdefault("LDB200_ALLOW_RANDOM_INIT", "1")
 import torch
 import ld_b200
 from ld_b200 import presets, synth
