@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault('LDB200_ALLOW_RANDOM_INIT', '1')   # synthetic benchmark: seeded random weights, no checkpoints
 
 FLOP_PER_IMAGE = 1.8356e12          # 917.79 GMAC (student fwd+bwd 620.26, teacher fwd 297.53) x 2
+FLOP_PER_IMAGE_R18 = 1.5435e12      # R18 student variant (BASELINE configs[1]): 771.77 GMAC x 2
 GLOBAL_BATCH = 16
 H, W = 800, 1344
 
@@ -128,28 +129,39 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
     ap.add_argument('--global-batch', type=int, default=0,
                     help='fix the global batch (strong scaling); default: 16 images per GPU (weak scaling)')
+    ap.add_argument('--per-gpu-batch', type=int, default=0, help='images per GPU (BASELINE configs[1]: --student r18 --per-gpu-batch 8)')
+    ap.add_argument('--main-ld-only', action='store_true', help='BASELINE configs[2]: VLR / KD / IM loss weights 0')
+    ap.add_argument('--no-parity', action='store_true', help='skip the fp32-accurate mode side measurement')
+    ap.add_argument('--no-micro', action='store_true', help='skip the micro records (LD-KL dense kernel)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     config = dict(workload='GFocal-R50 student + GFocal-R101 teacher LD train step, 16 x 800x1344 synthetic '
                            'COCO-shaped (configs/ld/ld_r50_gflv1_r101_fpn_coco_1x.py model section)',
-                  global_batch=args.global_batch or GLOBAL_BATCH * args.gpus, per_gpu_batch=(args.global_batch or GLOBAL_BATCH * args.gpus) // args.gpus,
+                  global_batch=args.global_batch or (args.per_gpu_batch or GLOBAL_BATCH) * args.gpus,
+                  per_gpu_batch=(args.global_batch or (args.per_gpu_batch or GLOBAL_BATCH) * args.gpus) // args.gpus,
+                  student=args.student, losses='main LD only' if args.main_ld_only else 'LD + VLR-LD + KD + IM (ld_r50 config)',
                   image=[H, W], parallelism=f'dp{args.gpus}',
                   launch='CUDA graph replay' if not args.no_graph else 'eager',
-                  timing='inputs (51.6 MB images + activations >> 126 MB L2) exceed L2; no explicit flush')
+                  timing='inputs (51.6 MB images + activations >> 126 MB L2) exceed L2; no explicit flush',
+                  value_region='per step: image D2D into the static buffer, target assignment on resident gt boxes, '
+                               'graph replay (student fwd+bwd, teacher fwd, loss, all-reduce, SGD); e2e adds H2D + loss D2H')
 
     if args.impl == 'reference':
         if rank != 0:
             return
-        config['launch'] = 'reference CPU path (oracle port, torch CPU fp32), bounded sample of 2 of the 16 images per step'
+        config['launch'] = 'reference CPU path (oracle port, torch CPU fp32)'
         n_imgs = 2
+        config['sample'] = (f'each timed step = {n_imgs} images of the 16-image 800x1344 batch (bounded sample: a full '
+                            f'batch is ~70 s of CPU work); images/s = {n_imgs} / measured step time, ms_per_step is '
+                            f'the measured time of that sample step, NOT scaled to 16 images')
         v, sec = cpu_reference_step(n_imgs, max(1, min(args.steps, 3)), min(args.warmup, 1))
         cores = host_cores()
         print(json.dumps(dict(
             metric='images/sec GFocal-R50 student + R101 teacher LD train step, 1333x800 bs=16', impl='reference',
             value=v, unit='images/s', n_gpus=args.gpus, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1),
-            ms_per_step=sec * 1e3 * (args.global_batch or GLOBAL_BATCH * args.gpus) / n_imgs, higher_is_better=True,
+            ms_per_step=sec * 1e3, higher_is_better=True,
             scaling='strong' if args.global_batch else 'weak', vs_baseline=None,
             dtype='f32', data='synthetic', config=config,
             cpu_baseline=dict(value=v, unit='images/s', cores=cores, kind='port',
@@ -160,7 +172,7 @@ def main():
     import torch
     import torch.distributed as dist
     import ld_b200
-    from ld_b200 import lib as L, presets, synth
+    from ld_b200 import lib as L, ops as _ops, presets, synth
     from ld_b200.config import ConfigDict
     assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
     torch.cuda.set_device(local_rank)
@@ -168,51 +180,16 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     L.check(L.load().ldb200_check_device(), 'check_device')
-    global_batch = args.global_batch or GLOBAL_BATCH * world
+    per_gpu = args.per_gpu_batch or GLOBAL_BATCH
+    global_batch = args.global_batch or per_gpu * world
     scaling = 'strong' if args.global_batch else 'weak'
     assert global_batch % world == 0
-    n = global_batch // world
 
-    model = ld_b200.build_detector(ConfigDict(presets.ld_model(args.student)))
+    model = ld_b200.build_detector(ConfigDict(presets.ld_model(args.student, main_ld_only=args.main_ld_only)))
     synth.seeded_init(model, 0)
     synth.seeded_init(model.teacher_model, 1, prefix='teacher.')
     model = model.to(dev).train()
-    step = ld_b200.LDTrainStep(model, lr=0.01 * global_batch / 16)   # linear scaling rule of the reference configs
-    batch = synth.make_batch(n, H, W, seed=1000 + rank)
-    img_pinned = batch['img'].pin_memory()
-    gtb_pinned = [b.pin_memory() for b in batch['gt_bboxes']]
-    gtl_pinned = [b.pin_memory() for b in batch['gt_labels']]
-    resident = dict(img=img_pinned.to(dev), img_metas=batch['img_metas'],
-                    gt_bboxes=[b.to(dev) for b in gtb_pinned], gt_labels=[b.to(dev) for b in gtl_pinned])
-
-    host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
     use_graph = not args.no_graph
-    if use_graph:
-        step.capture(resident, warmup=2)
-
-    def run_resident():
-        if use_graph:
-            step.step_graphed(None)          # batch + targets already resident in the static buffers
-        else:
-            step.step(resident, sync_logs=False)
-
-    e2e_data = dict(img=img_pinned, img_metas=batch['img_metas'], gt_bboxes=gtb_pinned, gt_labels=gtl_pinned)
-
-    def run_e2e():
-        # public API with HOST inputs: image batch + gt boxes from pinned memory, target assignment, the
-        # captured iteration, loss read back
-        data = e2e_data
-        if use_graph:
-            if getattr(step, '_staged', None) is not data:
-                step.prefetch(data)          # first call only; afterwards the copy was started during the last step
-            loss = step.step_graphed(data)
-            step.prefetch(data)              # next batch's H2D overlaps this replay (every step still moves all bytes)
-        else:
-            data = dict(img=img_pinned.to(dev, non_blocking=True), img_metas=batch['img_metas'],
-                        gt_bboxes=[b.to(dev, non_blocking=True) for b in gtb_pinned],
-                        gt_labels=[b.to(dev, non_blocking=True) for b in gtl_pinned])
-            loss, _ = step.step(data, sync_logs=False)
-        host_loss.copy_(loss.reshape(1), non_blocking=True)
 
     def timed(fn, steps):
         if world > 1:
@@ -232,69 +209,167 @@ def main():
             ms = float(t)
         return ms
 
-    for _ in range(max(args.warmup, 3)):
-        run_resident()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    l0 = L.launch_count['n']
-    ms = timed(run_resident, args.steps)
-    launches = (L.launch_count['n'] - l0) // args.steps
-    if use_graph:
-        launches = step.launches_per_step
-    clocks = sampler.stop() if sampler else None
-    run_e2e()
-    ms_e2e = timed(run_e2e, args.steps)
-    assert torch.isfinite(host_loss).all(), 'loss diverged'
+    def measure(n, gbatch, precision='bf16', graph=True, steps=args.steps, warmup=max(args.warmup, 3), clocks=False):
+        """One configuration: `n` images per GPU.  -> dict(ms, ms_e2e, launches, clocks, bytes)."""
+        step = ld_b200.LDTrainStep(model, lr=0.01 * gbatch / 16, precision=precision)   # linear scaling rule
+        batch = synth.make_batch(n, H, W, seed=1000 + rank)
+        img_pinned = batch['img'].pin_memory()
+        gtb_pinned = [b.pin_memory() for b in batch['gt_bboxes']]
+        gtl_pinned = [b.pin_memory() for b in batch['gt_labels']]
+        resident = dict(img=img_pinned.to(dev), img_metas=batch['img_metas'],
+                        gt_bboxes=[b.to(dev) for b in gtb_pinned], gt_labels=[b.to(dev) for b in gtl_pinned])
+        host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+        if graph:
+            step.capture(resident, warmup=2)
+
+        def run_resident():
+            # inputs resident in HBM; everything else of the step runs: image D2D into the graph's static buffer,
+            # target assignment (ldb200_ld_targets) on the resident gt boxes, the captured iteration
+            if graph:
+                step.step_graphed(resident)
+            else:
+                step.step(resident, sync_logs=False)
+
+        e2e_data = dict(img=img_pinned, img_metas=batch['img_metas'], gt_bboxes=gtb_pinned, gt_labels=gtl_pinned)
+
+        def run_e2e():
+            # public API with HOST inputs: image batch + gt boxes from pinned memory, target assignment, the
+            # captured iteration, loss read back
+            data = e2e_data
+            if graph:
+                if getattr(step, '_staged', None) is not data:
+                    step.prefetch(data)          # first call only; afterwards the copy was started during the last step
+                loss = step.step_graphed(data)
+                step.prefetch(data)              # next batch's H2D overlaps this replay (every step still moves all bytes)
+            else:
+                data = dict(img=img_pinned.to(dev, non_blocking=True), img_metas=batch['img_metas'],
+                            gt_bboxes=[b.to(dev, non_blocking=True) for b in gtb_pinned],
+                            gt_labels=[b.to(dev, non_blocking=True) for b in gtl_pinned])
+                loss, _ = step.step(data, sync_logs=False)
+            host_loss.copy_(loss.reshape(1), non_blocking=True)
+
+        for _ in range(warmup):
+            run_resident()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank) if (rank == 0 and clocks) else None
+        if sampler:
+            sampler.start()
+        l0 = L.launch_count['n']
+        ms = timed(run_resident, steps)
+        launches = (L.launch_count['n'] - l0) // steps
+        if graph:
+            launches = step.launches_per_step + 3      # + the eager target-assignment kernels of every step
+        ck = sampler.stop() if sampler else None
+        run_e2e()
+        ms_e2e = timed(run_e2e, steps)
+        assert torch.isfinite(host_loss).all(), 'loss diverged'
+        h2d = int(img_pinned.numel() * 4 + sum(b.numel() * 4 for b in gtb_pinned) + sum(b.numel() * 8 for b in gtl_pinned))
+        res = dict(ms=ms / steps, ms_e2e=ms_e2e / steps, launches=int(launches), clocks=ck, h2d=h2d)
+        # release the graph, its static buffers and the flat optimizer state before the next configuration
+        model.bbox_head._static_targets = None
+        del step
+        torch.cuda.empty_cache()
+        return res
+
+    n = global_batch // world
+    main_res = measure(n, global_batch, graph=use_graph, clocks=True)
+    ms, ms_e2e = main_res['ms'], main_res['ms_e2e']
+
+    # BASELINE configs[2] as stated (8 x 2 images: GLOBAL batch 16): the same step with 16 / N images per GPU
+    strong = None
+    if world > 1 and not args.global_batch and not args.per_gpu_batch and GLOBAL_BATCH % world == 0:
+        r = measure(GLOBAL_BATCH // world, GLOBAL_BATCH, graph=use_graph)
+        strong = dict(value=GLOBAL_BATCH / (r['ms'] / 1e3), unit='images/s', ms_per_step=r['ms'], global_batch=GLOBAL_BATCH,
+                      per_gpu_batch=GLOBAL_BATCH // world, scaling='strong',
+                      e2e=dict(value=GLOBAL_BATCH / (r['ms_e2e'] / 1e3), unit='images/s'))
+
+    # fp32-accurate ("parity") mode of the same step: fp32 activations, split-bf16 convolutions (tests/test_gpu_parity.py
+    # holds it to 1e-4 against the reference).  Eager launches, 3 timed steps.
+    parity = None
+    if world == 1 and not args.no_parity:
+        try:
+            r = measure(n, global_batch, precision='fp32', graph=False, steps=3, warmup=2)
+            parity = dict(img_s=global_batch / (r['ms'] / 1e3), ms_per_step=r['ms'], launch='eager',
+                          note='LDTrainStep(precision="fp32"): fp32 NHWC activations, every conv / dgrad / wgrad as 6 '
+                               'bf16 plane products in one fp32 TMEM accumulator; loss+grads within 1e-4 of the reference')
+        except torch.OutOfMemoryError as e:      # never let the side measurement take the headline down
+            parity = dict(error=str(e)[:120])
+            torch.cuda.empty_cache()
 
     # dominant kernel, timed live: conv2_tc_kernel on the head-tower shape (P3 level, 3x3 256->256), the
-    # single largest-FLOP launch of the step (32 forward + 16 dgrad launches of this shape per step)
-    from ld_b200 import ops as _ops
+    # single largest-FLOP launch shape of the step (the 5-level head launches are 48 of the step's tcgen05 launches)
     time.sleep(2.0)   # 'timed alone': let the power-capped clocks recover from the step loop before the burst measurement
     kx = torch.randn(n, 100, 168, 256, device=dev).bfloat16()
     kw = _ops.pack_conv_weight(torch.randn(256, 256, 3, 3, device=dev) * 0.02)
     ko = torch.empty(n, 100, 168, 256, device=dev, dtype=torch.bfloat16)
-    for _ in range(3):
-        _ops.conv2d_tc(kx, kw, 256, 3, 3, 1, 1, out=ko)
-    torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(20):
-        _ops.conv2d_tc(kx, kw, 256, 3, 3, 1, 1, out=ko)
-    k1.record()
-    torch.cuda.synchronize()
-    k_ms = k0.elapsed_time(k1) / 20
+
+    def ktime(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(reps):
+            fn()
+        k1.record()
+        torch.cuda.synchronize()
+        return k0.elapsed_time(k1) / reps
+
+    k_ms = ktime(lambda: _ops.conv2d_tc(kx, kw, 256, 3, 3, 1, 1, out=ko))
     k_flop = 2.0 * n * 100 * 168 * 256 * 256 * 9
+
+    # micro records (BASELINE configs[4] and the fused loss kernel north_star singles out), HBM-bound
+    micro = None
+    if rank == 0 and not args.no_micro:
+        pk_hbm = peaks().get('hbm_gbs', 6500.0)
+        rows = 5 * 200000 * 4
+        S = torch.randn(rows, 17, device=dev) * 2
+        Tt = torch.randn(rows, 17, device=dev) * 2
+        wv = torch.rand(rows, device=dev)
+        lossb, dS = torch.zeros(1, device=dev), torch.empty_like(S)
+        t_kl = ktime(lambda: _ops.kl_dense_fwd_bwd(S, Tt, wv, 10.0, 0.25, 4.0, loss=lossb, d_student=dS))
+        micro = dict(ld_kl_dense=dict(rows=rows, bins=17, ms=t_kl, bytes=208 * rows, achieved_gbs=208 * rows / t_kl / 1e6,
+                                      peak_gbs=pk_hbm, frac=208 * rows / t_kl / 1e6 / pk_hbm,
+                                      note='BASELINE configs[4]: 5 levels x 200k anchors x 4 sides x 17 bins, fwd+bwd, '
+                                           '208 algorithmic B/row (SURVEY 8d)'))
+        del S, Tt, wv, dS
 
     if rank == 0:
         pk = peaks()
-        ips = global_batch * args.steps / (ms / 1e3)
-        ips_e2e = global_batch * args.steps / (ms_e2e / 1e3)
+        ips = global_batch / (ms / 1e3)
+        ips_e2e = global_batch / (ms_e2e / 1e3)
         peak_tf = pk.get('bf16_tflops_sustained', 1400.0)
-        ach = ips * FLOP_PER_IMAGE / 1e12 / world
+        flop_img = FLOP_PER_IMAGE if args.student == 'r50' else FLOP_PER_IMAGE_R18
+        ach = ips * flop_img / 1e12 / world
+        prof = profile_numbers()
         out = dict(metric='images/sec GFocal-R50 student + R101 teacher LD train step, 1333x800 bs=16',
                    value=ips, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-                   ms_per_step=ms / args.steps, higher_is_better=True, scaling=scaling, vs_baseline=None,
+                   ms_per_step=ms, higher_is_better=True, scaling=scaling, vs_baseline=None,
                    dtype='bf16', data='synthetic', config=config,
-                   e2e=dict(value=ips_e2e, unit='images/s',
-                            h2d_bytes_per_step=int(img_pinned.numel() * 4 + sum(b.numel() * 4 for b in gtb_pinned)
-                                                   + sum(b.numel() * 8 for b in gtl_pinned)) * world,
+                   e2e=dict(value=ips_e2e, unit='images/s', h2d_bytes_per_step=main_res['h2d'] * world,
                             d2h_bytes_per_step=4 * world),
-                   gpu_launches=int(launches),
+                   gpu_launches=main_res['launches'],
                    roofline=dict(bound='tensor', kernel='conv2_tc_kernel (2-CTA tcgen05, 256x256 pair tile) head tower P3 3x3 256->256',
                                  achieved=k_flop / k_ms / 1e9, peak=pk.get('bf16_tflops', 1590.0), unit='TFLOP/s',
                                  frac=k_flop / k_ms / 1e9 / pk.get('bf16_tflops', 1590.0),
-                                 traffic=230.7e6 * n / 16,
+                                 traffic=prof.get('traffic'), traffic_source=prof.get('traffic_source'),
+                                 share_of_step=prof.get('share'), share_source=prof.get('share_source'),
                                  note='algorithmic 2*N*H*W*Cin*Cout*9 FLOP per launch / live CUDA-event duration (20 '
                                       'back-to-back launches), of ' + ('measured' if 'bf16_tflops' in pk else 'fallback')
-                                      + ' burst bf16 peak; traffic = dram read+write of the same launch from '
-                                        'profiles/r01_conv2_head_p3_summary.txt (ncu --set full, batch 16)'),
+                                      + ' burst bf16 peak; traffic = dram read+write per launch of the committed ncu '
+                                        '--set full capture (batch 16), share_of_step = this kernel\'s share of the '
+                                        'kernel time in the committed launch list'),
                    roofline_step=dict(bound='tensor', achieved=ach, peak=peak_tf, unit='TFLOP/s', frac=ach / peak_tf,
-                                      note='conv MACs of the whole step (1.8356 TFLOP/image) / step time per GPU, of '
+                                      note=f'conv MACs of the whole step ({flop_img / 1e12:.4f} TFLOP/image) / step time per GPU, of '
                                            + ('measured' if 'bf16_tflops_sustained' in pk else 'fallback')
                                            + ' sustained bf16 peak'),
-                   clocks=clocks)
+                   clocks=main_res['clocks'])
+        if strong is not None:
+            out['strong'] = strong
+        if parity is not None:
+            out['parity_mode'] = parity
+        if micro is not None:
+            out['micro'] = micro
         if world == 1 and not args.no_cpu_baseline:
             v, sec = cpu_reference_step(2, 1, 1)
             out['cpu_baseline'] = dict(value=v, unit='images/s', cores=host_cores(), kind='port',
@@ -308,6 +383,33 @@ def main():
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def profile_numbers():
+    """Numbers that only a profiler can give, read from the COMMITTED ncu summaries (never typed into the source):
+    DRAM traffic per launch of the roofline kernel and its share of the step's kernel time."""
+    import glob
+    import re
+    out = {}
+    prof = os.path.join(ROOT, 'profiles')
+    for f in sorted(glob.glob(os.path.join(prof, 'r*_conv2_head_p3_summary.txt')), reverse=True):
+        txt = open(f).read()
+        rd = re.search(r'dram__bytes_read\.sum = ([0-9.]+) (\w+)', txt)
+        wr = re.search(r'dram__bytes_write\.sum = ([0-9.]+) (\w+)', txt)
+        if rd and wr:
+            mul = {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}
+            out['traffic'] = float(rd.group(1)) * mul[rd.group(2)] + float(wr.group(1)) * mul[wr.group(2)]
+            out['traffic_source'] = os.path.relpath(f, ROOT)
+            break
+    for f in sorted(glob.glob(os.path.join(prof, 'r*_launches*share.json')), reverse=True):
+        try:
+            d = json.load(open(f))
+            out['share'] = d['conv2_tc_kernel']['share']
+            out['share_source'] = os.path.relpath(f, ROOT)
+            break
+        except Exception:
+            pass
+    return out
 
 
 if __name__ == '__main__':

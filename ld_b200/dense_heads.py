@@ -199,6 +199,22 @@ class GFLHead(nn.Module):
 IM_MODES = {'finegrained': L.IM_FINEGRAINED, 'fitnet': L.IM_CENTER, 'gibox': L.IM_FINEGRAINED}
 
 
+def _upstream_term_grad(head, g_losses, nl):
+    """The fused kernels emit the input gradients in the FORWARD pass for upstream weight 1 on every (term, level) --
+    what `BaseDetector._parse_losses` (sum of all terms) produces.  Any other upstream gradient (loss scaling, a
+    re-weighted or partial sum of the returned terms) is honoured by re-running the gradient pass with
+    `term_grad = g_losses`, which the kernel supports per term and level.  Returns None when the precomputed gradients
+    are valid, else the [8, MAX_LEVELS] host tensor to re-run with.  The check costs one device->host read, so it is
+    skipped during CUDA-graph capture and when the caller vouches for the plain sum (`LDTrainStep`)."""
+    if g_losses is None or getattr(head, '_unit_loss_grad', False) or \
+            (g_losses.is_cuda and torch.cuda.is_current_stream_capturing()):
+        return None
+    g = g_losses[:L.NUM_TERMS - 1].detach().float().cpu()
+    if bool((g[:, :nl] == 1).all()):
+        return None
+    return g.contiguous()
+
+
 class _LDLossFn(torch.autograd.Function):
     """gfl_cls/gfl_reg output convs + LDHead.loss (ld_head.py:284-375) as one autograd node.
 
@@ -227,6 +243,8 @@ class _LDLossFn(torch.autograd.Function):
         norm = ops.loss_normalisers(tg, wsum)
         dcls_ld, dreg_ld = (C + 7) // 8 * 8, (NB + 7) // 8 * 8
         tg_im, max_fg = tg, aux.get('max_fg')
+        if not aux['im_active']:
+            max_fg = 1      # IM weight 0: no imitation rows are written (the kernel skips phase 3), keep d_im a stub
         if head.imitation_method == 'gibox' and aux['im_active']:
             # ld_head.py:170-176: imitate on the General-Instance rows (GI-box NMS picks, 10 per level) instead of a
             # target-derived region; they depend on this iteration's student and teacher head outputs
@@ -235,10 +253,13 @@ class _LDLossFn(torch.autograd.Function):
             tg_im = dataclasses.replace(tg, fg_rows=gi_rows, counts=gi_counts)
             max_fg = gi_rows.numel()
         aux['targets_im'] = tg_im
-        losses, d_cls, d_reg, d_im = ops.ld_loss_fused(
-            cfg, cls_rows, reg_rows, aux['t_cls_rows'], aux['t_reg_rows'], x_rows, aux['t_x_rows'], tg_im, norm,
-            term_grad=aux['term_grad'], grad_dtype=xs[0].dtype, max_fg=max_fg,
-            d_cls_ld=dcls_ld, d_reg_ld=dreg_ld)
+
+        def run(term_grad):
+            return ops.ld_loss_fused(
+                cfg, cls_rows, reg_rows, aux['t_cls_rows'], aux['t_reg_rows'], x_rows, aux['t_x_rows'], tg_im, norm,
+                term_grad=term_grad, grad_dtype=xs[0].dtype, max_fg=max_fg, d_cls_ld=dcls_ld, d_reg_ld=dreg_ld)
+        losses, d_cls, d_reg, d_im = run(aux['term_grad'])
+        ctx.regrad = run
         ctx.head, ctx.aux = head, aux
         ctx.save_for_backward(*tensors, cls_rows, reg_rows, d_cls, d_reg, d_im)
         ctx.mark_non_differentiable(norm)
@@ -256,6 +277,9 @@ class _LDLossFn(torch.autograd.Function):
         scales = tensors[3 * nl + 4:]
         C, NB = head.cls_out_channels, 4 * (head.reg_max + 1)
         tg = aux['targets']
+        tgrad = _upstream_term_grad(head, g_losses, nl)
+        if tgrad is not None:     # non-unit upstream gradient: redo the gradient pass with it
+            _, d_cls, d_reg, d_im = ctx.regrad(tgrad)
         dev = d_cls.device
         # conv biases: column sums of the row-space gradients
         g_bc = torch.zeros(d_cls.shape[1], dtype=torch.float32, device=dev)
@@ -416,11 +440,14 @@ class _LossOnlyFn(torch.autograd.Function):
                                                topk=head.gi_topk)
             tg_im, max_fg = dataclasses.replace(tg, fg_rows=gi_rows, counts=gi_counts), gi_rows.numel()
         head._last_im_targets = tg_im    # (rows, counts) the imitation term used: inspected by the parity tests
-        losses, d_cls, d_reg, d_im = ops.ld_loss_fused(cfg, rows[0], rows[1], rows[2], rows[3], xr, txr, tg_im, norm,
-                                                       term_grad=True, grad_dtype=torch.float32, max_fg=max_fg)
-        d_x = torch.zeros(tg.pyr.rows, xr.shape[1], dtype=torch.float32, device=xr.device)
-        ops.scatter_add_rows(d_x, d_im, tg_im.fg_rows, tg_im.counts[1:2])
-        ctx.pyr, ctx.nl = tg.pyr, nl
+        def run(term_grad):
+            losses, d_cls, d_reg, d_im = ops.ld_loss_fused(cfg, rows[0], rows[1], rows[2], rows[3], xr, txr, tg_im, norm,
+                                                           term_grad=term_grad, grad_dtype=torch.float32, max_fg=max_fg)
+            d_x = torch.zeros(tg.pyr.rows, xr.shape[1], dtype=torch.float32, device=xr.device)
+            ops.scatter_add_rows(d_x, d_im, tg_im.fg_rows, tg_im.counts[1:2])
+            return losses, d_cls, d_reg, d_x
+        losses, d_cls, d_reg, d_x = run(True)
+        ctx.pyr, ctx.nl, ctx.head, ctx.regrad = tg.pyr, nl, head, run
         ctx.save_for_backward(d_cls, d_reg, d_x)
         return losses
 
@@ -428,6 +455,9 @@ class _LossOnlyFn(torch.autograd.Function):
     def backward(ctx, g):
         d_cls, d_reg, d_x = ctx.saved_tensors
         nl = ctx.nl
+        tgrad = _upstream_term_grad(ctx.head, g, nl)
+        if tgrad is not None:
+            _, d_cls, d_reg, d_x = ctx.regrad(tgrad)
         out = [None, None, None]
         for d in (d_cls, d_reg, d_x):
             out += [v for v in ops.from_rows(d, ctx.pyr)]
@@ -436,12 +466,10 @@ class _LossOnlyFn(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# GFLv2 / LDv2: registry surface, parameters and checkpoint keys of the reference classes.
-# The kernels behind them -- `ldb200_dgqp_forward/_backward` (quality branch, dgqp.cu), `ldb200_gi_region`
-# (raw-score GI boxes) and the v2 arithmetic of the loss (v2_math.cuh: QFL on joint scores) -- exist; the fused LDv2
-# loss launch that ties them together is the next step, so `forward_train` still raises instead of running anything
-# that is not the CUDA path.  The CPU oracle of the whole LDv2 step is pinned to the unmodified reference
-# (oracle/ld_oracle.py, tests/golden/l2_*.pt, s2_*.pt).
+# GFLv2 / LDv2: registry surface, parameters and checkpoint keys of the reference classes on the
+# kernels `ldb200_dgqp_forward/_backward` (quality branch, dgqp.cu), `ldb200_gi_region_v2` (raw-score GI boxes) and the
+# V2 instantiations of the prepass / fused loss (QFL on joint scores, KD on cls_feat).  GPU parity against the unmodified
+# reference: tests/test_gpu_ldv2.py (goldens tests/golden/l2_*.pt, s2_*.pt; first GPU run in round 2).
 @HEADS.register_module()
 class GFocalHead(GFLHead):
     """gfocal_head.py:51-152: GFLHead + Distribution-Guided Quality Predictor (`reg_conf`)."""
@@ -561,20 +589,28 @@ class _LossOnlyV2Fn(torch.autograd.Function):
                                                   topk=head.gi_topk)
             tg_im, max_fg = dataclasses.replace(tg, fg_rows=gi_rows, counts=gi_counts), gi_rows.numel()
         head._last_im_targets = tg_im
-        losses, d_score, d_kd, d_reg, d_im = ops.ld_loss_fused_v2(
-            cfg, rows[0], rows[2], rows[1], rows[3], rows[4], xr, txr, tg_im, norm, nfg, term_grad=True,
-            grad_dtype=torch.float32, max_fg=max_fg)
-        d_x = torch.zeros(tg.pyr.rows, xr.shape[1], dtype=torch.float32, device=xr.device)
-        ops.scatter_add_rows(d_x, d_im, tg_im.fg_rows, tg_im.counts[1:2])
         C = cfg.num_classes
-        ctx.pyr, ctx.nl = tg.pyr, nl
-        ctx.save_for_backward(d_score[:, :C].contiguous(), d_reg, d_kd[:, :C].contiguous(), d_x)
+
+        def run(term_grad):
+            losses, d_score, d_kd, d_reg, d_im = ops.ld_loss_fused_v2(
+                cfg, rows[0], rows[2], rows[1], rows[3], rows[4], xr, txr, tg_im, norm, nfg, term_grad=term_grad,
+                grad_dtype=torch.float32, max_fg=max_fg)
+            d_x = torch.zeros(tg.pyr.rows, xr.shape[1], dtype=torch.float32, device=xr.device)
+            ops.scatter_add_rows(d_x, d_im, tg_im.fg_rows, tg_im.counts[1:2])
+            return losses, (d_score[:, :C].contiguous(), d_reg, d_kd[:, :C].contiguous(), d_x)
+        losses, grads = run(True)
+        ctx.pyr, ctx.nl, ctx.head, ctx.regrad = tg.pyr, nl, head, run
+        ctx.save_for_backward(*grads)
         return losses
 
     @staticmethod
     def backward(ctx, g):
         out = [None, None, None]
-        for d in ctx.saved_tensors:      # order of the inputs: scores, bbox_preds, cls_feat, x
+        grads = ctx.saved_tensors
+        tgrad = _upstream_term_grad(ctx.head, g, ctx.nl)
+        if tgrad is not None:
+            grads = ctx.regrad(tgrad)[1]
+        for d in grads:      # order of the inputs: scores, bbox_preds, cls_feat, x
             out += [v for v in ops.from_rows(d, ctx.pyr)]
         out += [None] * (3 * ctx.nl)
         return tuple(out)
@@ -586,7 +622,7 @@ class _LDv2LossFn(torch.autograd.Function):
     kernel emits d_score / d_kd / d_reg / d_x, ldb200_dgqp_backward folds the quality branch back into d_cls_feat and
     d_reg and produces the reg_conf parameter gradients; `backward` hands them to the output convs' wgrad / dgrad.
 
-    inputs: as `_LDLossFn` plus the four reg_conf tensors (conv1x1 weight/bias twice).  NOT yet run on a GPU."""
+    inputs: as `_LDLossFn` plus the four reg_conf tensors (conv1x1 weight/bias twice)."""
 
     @staticmethod
     def forward(ctx, head, aux, *tensors):
@@ -611,18 +647,25 @@ class _LDv2LossFn(torch.autograd.Function):
         norm = ops.loss_normalisers(tg, wsum)
         dcls_ld, dreg_ld = (C + 7) // 8 * 8, (NB + 7) // 8 * 8
         tg_im, max_fg = tg, aux.get('max_fg')
+        if not aux['im_active']:
+            max_fg = 1
         if head.imitation_method == 'gibox' and aux['im_active']:
             gi_rows, gi_counts = ops.gi_region_v2(cfg, score_rows, reg_rows, aux['t_cls_rows'], aux['t_reg_rows'], tg,
                                                   iou_thr=head.gi_iou_thr, topk=head.gi_topk)
             tg_im = dataclasses.replace(tg, fg_rows=gi_rows, counts=gi_counts)
             max_fg = gi_rows.numel()
         aux['targets_im'] = tg_im
-        losses, d_score, d_kd, d_reg, d_im = ops.ld_loss_fused_v2(
-            cfg, score_rows, feat_rows, reg_rows, aux['t_cls_rows'], aux['t_reg_rows'], x_rows, aux['t_x_rows'], tg_im,
-            norm, nfg, term_grad=aux['term_grad'], grad_dtype=xs[0].dtype, max_fg=max_fg, d_cls_ld=dcls_ld,
-            d_reg_ld=dreg_ld)
-        d_feat, g_w1, g_b1, g_w2, g_b2 = ops.dgqp_backward(reg_rows, feat_rows, *qp, quality, d_score, d_reg, d_kd=d_kd,
-                                                           reg_topk=head.reg_topk, add_mean=head.add_mean)
+
+        def run(term_grad):
+            losses, d_score, d_kd, d_reg, d_im = ops.ld_loss_fused_v2(
+                cfg, score_rows, feat_rows, reg_rows, aux['t_cls_rows'], aux['t_reg_rows'], x_rows, aux['t_x_rows'], tg_im,
+                norm, nfg, term_grad=term_grad, grad_dtype=xs[0].dtype, max_fg=max_fg, d_cls_ld=dcls_ld,
+                d_reg_ld=dreg_ld)
+            d_feat, g_w1, g_b1, g_w2, g_b2 = ops.dgqp_backward(reg_rows, feat_rows, *qp, quality, d_score, d_reg,
+                                                               d_kd=d_kd, reg_topk=head.reg_topk, add_mean=head.add_mean)
+            return losses, (d_feat, d_reg, d_im, g_w1, g_b1, g_w2, g_b2)
+        losses, (d_feat, d_reg, d_im, g_w1, g_b1, g_w2, g_b2) = run(aux['term_grad'])
+        ctx.regrad = run
         ctx.head, ctx.aux = head, aux
         ctx.q_shapes = (tuple(q_w1.shape), tuple(q_w2.shape))
         ctx.save_for_backward(*tensors, feat_rows, reg_rows, d_feat, d_reg, d_im, g_w1, g_b1, g_w2, g_b2)
@@ -641,6 +684,9 @@ class _LDv2LossFn(torch.autograd.Function):
         scales = tensors[3 * nl + 4:4 * nl + 4]
         C, NB = head.cls_out_channels, 4 * (head.reg_max + 1)
         tg = aux['targets']
+        tgrad = _upstream_term_grad(head, g_losses, nl)
+        if tgrad is not None:
+            d_cls, d_reg, d_im, g_w1, g_b1, g_w2, g_b2 = ctx.regrad(tgrad)[1]
         dev = d_cls.device
         g_bc = torch.zeros(d_cls.shape[1], dtype=torch.float32, device=dev)
         ops.colsum(d_cls, g_bc)

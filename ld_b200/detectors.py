@@ -313,6 +313,111 @@ class LDTrainStep:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         if self.world > 1:
             dist.broadcast(self.flat_w, src=0)
+        self._init_overlap()
+
+    # ------------------------------------------------------------------ overlapped gradient exchange
+    # DDP semantics (mmdet/apis/train.py:78-82: bucketed all-reduce overlapped with backward): the flat gradient
+    # buffer is exchanged in segments ordered by BACKWARD COMPLETION -- head, neck, layer4, layer3, rest -- each on a
+    # communication stream as soon as the last kernel writing into it has been issued, so only the last segment's
+    # exchange (the first backbone stage that trains) is exposed after the backward pass.  The parameter order of
+    # `model.parameters()` (backbone, neck, bbox_head) makes every segment one contiguous slice of flat_g.
+    SEGMENT_PREFIXES = ('bbox_head.', 'neck.', 'backbone.layer4.', 'backbone.layer3.')
+
+    def _init_overlap(self):
+        names = [k for k, p in self.model.named_parameters() if p.requires_grad]
+        assert len(names) == len(self.params)
+        spans, o = {}, 0
+        for k, p in zip(names, self.params):
+            for pre in self.SEGMENT_PREFIXES:
+                if k.startswith(pre):
+                    a, b = spans.get(pre, (o, o))
+                    assert b == o or a == b, f'parameters of {pre} are not contiguous in the flat buffer'
+                    spans[pre] = (a if b > a else o, o + p.numel())
+                    break
+            o += p.numel()
+        self._segments = spans            # prefix -> (start, end) in flat_g
+        self._reduced = []                # slices already exchanged in the current iteration
+        self.overlap = os.environ.get('LDB200_NO_AR_OVERLAP') is None
+        self._hook_handle = None
+        if self.world > 1 and self.overlap and hasattr(self.model, 'neck'):
+            self._hook_handle = self.model.neck.register_forward_hook(self._neck_forward_hook)
+
+    def _neck_forward_hook(self, module, inputs, outputs):
+        """Tensor hooks at the stage boundaries of THIS forward pass: the gradient of a stage's input is complete only
+        after every backward node of the later stages (and their parameter-gradient kernels) has been issued."""
+        if not (self._in_step and torch.is_grad_enabled()):
+            return
+        feats = inputs[0]
+        marks = [(list(outputs), 'bbox_head.')]
+        if len(feats) >= 1:
+            marks.append(([feats[-1]], 'neck.'))
+        if len(feats) >= 2:
+            marks.append(([feats[-2]], 'backbone.layer4.'))
+        if len(feats) >= 3:
+            marks.append(([feats[-3]], 'backbone.layer3.'))
+        for tensors, seg in marks:
+            for t in tensors:
+                if isinstance(t, torch.Tensor) and t.requires_grad:
+                    t.register_hook(self._make_grad_hook(seg))
+
+    def _make_grad_hook(self, seg):
+        def hook(grad):
+            self._reduce_span(seg)
+            return None
+        return hook
+
+    def _comm(self):
+        st = self.__dict__.get('_comm_stream')
+        if st is None:
+            st = torch.cuda.Stream(device=self.flat_g.device)
+            self.__dict__['_comm_stream'] = st
+        return st
+
+    def _reduce_span(self, seg):
+        """All-reduce one segment of flat_g on the communication stream, after everything issued so far on the compute
+        streams (main + the head's regression-tower stream)."""
+        if seg in self._done or seg not in self._segments:
+            return
+        self._done.add(seg)
+        a, b = self._segments[seg]
+        if b <= a:
+            return
+        comm = self._comm()
+        comm.wait_stream(torch.cuda.current_stream())
+        side = self.model.bbox_head.__dict__.get('_side_stream')
+        if side is not None:
+            comm.wait_stream(side)
+        with torch.cuda.stream(comm):
+            dist.all_reduce(self.flat_g[a:b])
+        self._reduced.append((a, b))
+
+    def _begin_exchange(self):
+        self._done, self._reduced, self._in_step = set(), [], True
+        # the step's loss is the plain sum of all terms (base.py:185-218): the loss node may hand out the gradients it
+        # precomputed in the forward pass without checking its upstream gradient (a device->host read)
+        self.model.bbox_head._unit_loss_grad = True
+
+    def _finish_exchange(self):
+        """Exchange whatever the hooks have not covered (the earliest training stage; everything when overlap is off),
+        then make the main stream wait for the communication stream."""
+        self._in_step = False
+        self.model.bbox_head._unit_loss_grad = False
+        if self.world == 1:
+            return
+        if not self._reduced:
+            dist.all_reduce(self.flat_g)
+            return
+        comm = self._comm()
+        comm.wait_stream(torch.cuda.current_stream())
+        cur = 0
+        with torch.cuda.stream(comm):
+            for a, b in sorted(self._reduced) + [(self.flat_g.numel(), self.flat_g.numel())]:
+                if a > cur:
+                    dist.all_reduce(self.flat_g[cur:a])
+                cur = max(cur, b)
+        torch.cuda.current_stream().wait_stream(comm)
+
+    _in_step = False
 
     def lr_at(self, it):
         """mmcv LrUpdaterHook, warmup='linear': lr = base * (1 - (1 - it/warmup_iters) * (1 - ratio))."""
@@ -348,6 +453,7 @@ class LDTrainStep:
     def _step(self, data, sync_logs):
         self.flat_g.zero_()
         engine.zero_pool_begin(self.flat_g.device)
+        self._begin_exchange()
         losses = self.model(**data)
         if sync_logs:
             loss, log_vars = self.model._parse_losses(losses)
@@ -356,8 +462,7 @@ class LDTrainStep:
             log_vars = None
         loss.backward()
         engine.zero_pool_end()
-        if self.world > 1:
-            dist.all_reduce(self.flat_g)
+        self._finish_exchange()
         ops.sgd_flat(self.flat_w, self.flat_g, self.flat_m, self.lr_at(self.iter), self.momentum, self.wd,
                      1.0 / self.world, first_step=(self.iter == 0))
         engine.clear_step_cache(self.params)
@@ -373,13 +478,13 @@ class LDTrainStep:
     def _body_inner(self, data):
         self.flat_g.zero_()
         engine.zero_pool_begin(self.flat_g.device)
+        self._begin_exchange()
         losses = self.model(**data)
         terms = torch.stack([sum(v) for v in losses.values()])
         loss = terms.sum()
         loss.backward()
         engine.zero_pool_end()
-        if self.world > 1:
-            dist.all_reduce(self.flat_g)
+        self._finish_exchange()
         ops.sgd_flat_dev(self.flat_w, self.flat_g, self.flat_m, self._hyper)
         self._terms.copy_(terms.detach())
         self._loss.copy_(loss.detach())

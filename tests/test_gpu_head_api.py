@@ -127,3 +127,34 @@ def test_imloss_module_standalone():
     torch.cuda.synchronize()
     assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref))
     assert float((xg.grad.cpu() - x.grad).abs().max()) <= 1e-5 * float(x.grad.abs().max())
+
+
+def test_ldhead_loss_honours_upstream_gradients():
+    """the loss node precomputes its input gradients for the plain sum of all terms; a scaled loss, a
+    re-weighted sum or a subset of the returned terms must still give the right gradients (oracle autograd)."""
+    n, h, w, seed = 2, 192, 256, 17
+    d = cases.loss_case_inputs(n, h, w, seed)
+    dev = torch.device('cuda')
+    tg = lo.ld_targets(d['sizes'], cases.STRIDES, d['img_metas'], d['gt_bboxes'], d['gt_labels'])
+
+    def weights(losses):     # 3 x (cls + kd of level 0 only) + 0.5 x bbox, everything else dropped
+        return 3.0 * (losses['loss_cls'][0] + losses['loss_kd'][0]) + 0.5 * sum(losses['loss_bbox'])
+
+    ref = {k: [t.clone().requires_grad_(True) for t in d[k]] for k in ('cls', 'reg', 'x')}
+    weights(lo.ld_loss(ref['cls'], ref['reg'], d['t_cls'], d['t_reg'], ref['x'], d['t_x'], tg, cases.STRIDES)).backward()
+    head = make_head()
+    leaves = {k: [t.to(dev).requires_grad_(True) for t in d[k]] for k in ('cls', 'reg', 'x')}
+    losses = head.loss(leaves['cls'], leaves['reg'], [b.to(dev) for b in d['gt_bboxes']], [b.to(dev) for b in d['gt_labels']],
+                       ([t.to(dev) for t in d['t_cls']], [t.to(dev) for t in d['t_reg']]),
+                       leaves['x'], [t.to(dev) for t in d['t_x']], d['img_metas'])
+    weights(losses).backward()
+    torch.cuda.synchronize()
+    for key in ('cls', 'reg'):
+        for l in range(5):
+            want = ref[key][l].grad
+            want = torch.zeros_like(ref[key][l]) if want is None else want
+            got = leaves[key][l].grad.cpu()
+            assert float((got - want).abs().max()) <= 1e-4 * float(want.abs().max()) + 1e-9, (key, l)
+    for l in range(5):       # the imitation term was not part of the sum: no gradient reaches x
+        gx = leaves['x'][l].grad
+        assert gx is None or float(gx.abs().max()) == 0.0

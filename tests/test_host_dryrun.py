@@ -171,3 +171,28 @@ def test_parity_mode_train_step_host_logic(fake_backend, student):
     convs = fake_backend.count('ldb200_conv2d_tc') + fake_backend.count('ldb200_conv2d_tc_multi')
     assert convs > 0 and fake_backend.count('ldb200_split_bf16') > convs    # activations + weights
     _check_grads(m)
+
+
+def test_overlapped_gradient_exchange_covers_flat_buffer_once(fake_backend, monkeypatch):
+    """Data-parallel exchange of LDTrainStep: segments of the flat gradient buffer are all-reduced from
+    backward hooks in completion order (head, neck, layer4, layer3) and the remainder after the backward pass; together
+    they cover every element exactly once."""
+    import torch.distributed as dist
+    m = ld_b200.build_detector(ConfigDict(presets.ld_model('r50', teacher_depth=18))).train()
+    calls = []
+    monkeypatch.setattr(dist, 'all_reduce', lambda t, *a, **k: calls.append((t.data_ptr(), t.numel())))
+    ts = ld_b200.LDTrainStep(m, lr=0.001, warmup_iters=4)
+    ts.world = 2                                  # pretend to be one of two ranks
+    ts._init_overlap()
+    assert ts._hook_handle is not None
+    order = []
+    orig = ts._reduce_span
+    monkeypatch.setattr(ts, '_reduce_span', lambda seg: (order.append(seg), orig(seg))[1])
+    ts.step(_batch(), sync_logs=False)
+    base, es = ts.flat_g.data_ptr(), ts.flat_g.element_size()
+    spans = sorted(((p - base) // es, (p - base) // es + n) for p, n in calls if n > 8)    # (8-byte normaliser excluded)
+    assert spans[0][0] == 0 and spans[-1][1] == ts.flat_g.numel()
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:])), spans                       # disjoint, no gaps
+    first = [s for i, s in enumerate(order) if s not in order[:i]]
+    assert first == ['bbox_head.', 'neck.', 'backbone.layer4.', 'backbone.layer3.'], first
+    assert len(spans) == 5                         # + the remainder (layer2) after the backward pass
