@@ -220,6 +220,22 @@ int ldb200_kl_dense_fwd_bwd(const float* student, const float* teacher, const fl
                             int64_t rows, int bins, float T, float loss_weight, float avg_factor,
                             float grad_out, float* loss, float* d_student, void* stream);
 
+/* Stand-alone loss modules of the registry surface (`build_loss(cfg)(pred, target, weight, avg_factor, ...)` outside
+ * LDHead): forward value and d/d pred in one launch, fp32.  row_loss (optional, [rows]) receives scale * w_r * l_r for
+ * reduction='none'; loss (optional, f32[1], ACCUMULATED) += scale * sum_r w_r * l_r; d_pred (optional) = scale * w_r *
+ * d l_r / d pred.  `scale` folds loss_weight and 1 / avg_factor (losses/utils.py:27-54, 57-100); weight may be NULL.
+ *   qfl:  quality_focal_loss (gfocal_loss.py:8-50): pred [rows, C] logits (use_sigmoid = 1) or probabilities
+ *         (use_sigmoid = 0, the GFLv2/LDv2 configs), label [rows] i32 (>= C or < 0 = background), score [rows]
+ *   dfl:  distribution_focal_loss (gfocal_loss.py:53-74): pred [rows, bins] logits, label [rows] f32 in [0, bins-1)
+ *   giou: giou_loss (iou_loss.py:85-102, eps 1e-6): pred, target [rows, 4] xyxy */
+int ldb200_qfl_fwd_bwd(const float* pred, const int32_t* label, const float* score, const float* weight, int64_t rows,
+                       int C, float beta, int use_sigmoid, float scale, float* row_loss, float* loss, float* d_pred,
+                       void* stream);
+int ldb200_dfl_fwd_bwd(const float* pred, const float* label, const float* weight, int64_t rows, int bins, float scale,
+                       float* row_loss, float* loss, float* d_pred, void* stream);
+int ldb200_giou_fwd_bwd(const float* pred, const float* target, const float* weight, int64_t rows, float eps, float scale,
+                        float* row_loss, float* loss, float* d_pred, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (bf16 x bf16 -> fp32 accumulate), NHWC.
  * Replaces the cuDNN `nn.Conv2d` calls of the reference's ResNet / FPN / GFLHead forward

@@ -933,3 +933,152 @@ extern "C" int ldb200_kl_dense_fwd_bwd(const float* student, const float* teache
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
+
+
+// =============================================================================================
+// Stand-alone loss modules of the registry surface ("Loss modules: forward(pred, target, weight,
+// avg_factor, reduction_override)"): QualityFocalLoss (gfocal_loss.py:8-50, 77-135), DistributionFocalLoss
+// (gfocal_loss.py:53-74, 138-179) and GIoULoss (iou_loss.py:85-102, 325-360) outside LDHead, forward + gradient in
+// one launch, on the same row arithmetic as the fused kernel.  `scale` = loss_weight / avg_factor (or 1/rows, or 1):
+//   row_loss[r] (optional, reduction='none') = loss_weight * w_r * l_r ;  loss[0] += scale * sum_r w_r * l_r
+//   d_pred = scale * w_r * d l_r / d pred      (row_loss mode: scale = loss_weight, upstream applied by the caller)
+namespace ldb {
+
+__device__ __forceinline__ void block_accumulate(float v, float* out) {
+  __shared__ float sh[32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    if (t != 0.f) atomicAdd(out, t);
+  }
+}
+
+// one warp per row: lanes stride over the C class columns
+__global__ void __launch_bounds__(256)
+qfl_rows_kernel(const float* __restrict__ pred, const int* __restrict__ label, const float* __restrict__ score,
+                const float* __restrict__ weight, int R, int C, float beta, int use_sigmoid, float scale,
+                float* __restrict__ row_loss, float* __restrict__ loss, float* __restrict__ d_pred) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float acc = 0.f;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += gridDim.x * wpb) {
+    const int lab = label[r];
+    const float w = weight ? weight[r] : 1.f, y = score[r];
+    float rl = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float x = pred[(size_t)r * C + c];
+      float lo, gr;
+      if (use_sigmoid) {
+        if (c == lab) qfl_pos(x, y, beta, lo, gr); else qfl_neg(x, beta, lo, gr);
+      } else {
+        if (c == lab) qflp_pos(x, y, beta, lo, gr); else qflp_neg(x, beta, lo, gr);
+      }
+      rl += lo;
+      if (d_pred) d_pred[(size_t)r * C + c] = scale * w * gr;
+    }
+    rl = warp_sum(rl);
+    if (lane == 0) {
+      if (row_loss) row_loss[r] = scale * w * rl;
+      acc += w * rl;
+    }
+  }
+  if (loss) block_accumulate(acc * scale, loss);
+}
+
+// one warp per row of `bins` logits (bins <= 32)
+__global__ void __launch_bounds__(256)
+dfl_rows_kernel(const float* __restrict__ pred, const float* __restrict__ label, const float* __restrict__ weight, int R,
+                int bins, float scale, float* __restrict__ row_loss, float* __restrict__ loss,
+                float* __restrict__ d_pred) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float acc = 0.f;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += gridDim.x * wpb) {
+    const bool active = lane < bins;
+    const float z = active ? pred[(size_t)r * bins + lane] : 0.f;
+    float p, logp;
+    warp_softmax(z, active, p, logp);
+    const float y = label[r], w = weight ? weight[r] : 1.f;
+    const int left = (int)y;                       // label.long(): truncation, labels are >= 0
+    const float wl = (float)(left + 1) - y, wr = y - (float)left;
+    // cross_entropy(pred, left) * wl + cross_entropy(pred, right) * wr (gfocal_loss.py:69-73)
+    float contrib = 0.f;
+    if (active && lane == left) contrib -= logp * wl;
+    if (active && lane == left + 1) contrib -= logp * wr;
+    const float rl = warp_sum(contrib);
+    if (d_pred && active) {
+      float g = p * (wl + wr);
+      if (lane == left) g -= wl;
+      if (lane == left + 1) g -= wr;
+      d_pred[(size_t)r * bins + lane] = scale * w * g;
+    }
+    if (lane == 0) {
+      if (row_loss) row_loss[r] = scale * w * rl;
+      acc += w * rl;
+    }
+  }
+  if (loss) block_accumulate(acc * scale, loss);
+}
+
+// one thread per box pair
+__global__ void __launch_bounds__(256)
+giou_rows_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ weight,
+                 int R, float eps, float scale, float* __restrict__ row_loss, float* __restrict__ loss,
+                 float* __restrict__ d_pred) {
+  float acc = 0.f;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
+    const float4 pv = reinterpret_cast<const float4*>(pred)[r], tv = reinterpret_cast<const float4*>(target)[r];
+    const float p[4] = {pv.x, pv.y, pv.z, pv.w}, t[4] = {tv.x, tv.y, tv.z, tv.w};
+    float iou, l, g[4];
+    giou_fwd_bwd(p, t, eps, iou, l, g);
+    const float w = weight ? weight[r] : 1.f;
+    if (d_pred) reinterpret_cast<float4*>(d_pred)[r] = make_float4(scale * w * g[0], scale * w * g[1], scale * w * g[2], scale * w * g[3]);
+    if (row_loss) row_loss[r] = scale * w * l;
+    acc += w * l;
+  }
+  if (loss) block_accumulate(acc * scale, loss);
+}
+
+}  // namespace ldb
+
+extern "C" int ldb200_qfl_fwd_bwd(const float* pred, const int32_t* label, const float* score, const float* weight,
+                                  int64_t rows, int C, float beta, int use_sigmoid, float scale, float* row_loss,
+                                  float* loss, float* d_pred, void* stream_) {
+  LDB_REQUIRE(rows >= 0 && C >= 1 && rows < (1LL << 31), LDB_EINVAL, "qfl_fwd_bwd: bad shape");
+  if (rows == 0) return 0;
+  LDB_REQUIRE(pred && label && score && (row_loss || loss), LDB_EINVAL, "qfl_fwd_bwd: null pointer");
+  long long blocks = (rows + 7) / 8;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  ldb::qfl_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(pred, label, score, weight, (int)rows, C, beta,
+                                                                           use_sigmoid, scale, row_loss, loss, d_pred);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_dfl_fwd_bwd(const float* pred, const float* label, const float* weight, int64_t rows, int bins,
+                                  float scale, float* row_loss, float* loss, float* d_pred, void* stream_) {
+  LDB_REQUIRE(rows >= 0 && bins >= 2 && bins <= 32 && rows < (1LL << 31), LDB_EINVAL, "dfl_fwd_bwd: 2 <= bins <= 32");
+  if (rows == 0) return 0;
+  LDB_REQUIRE(pred && label && (row_loss || loss), LDB_EINVAL, "dfl_fwd_bwd: null pointer");
+  long long blocks = (rows + 7) / 8;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  ldb::dfl_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(pred, label, weight, (int)rows, bins, scale,
+                                                                           row_loss, loss, d_pred);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_giou_fwd_bwd(const float* pred, const float* target, const float* weight, int64_t rows, float eps,
+                                   float scale, float* row_loss, float* loss, float* d_pred, void* stream_) {
+  LDB_REQUIRE(rows >= 0 && rows < (1LL << 31), LDB_EINVAL, "giou_fwd_bwd: bad shape");
+  if (rows == 0) return 0;
+  LDB_REQUIRE(pred && target && (row_loss || loss), LDB_EINVAL, "giou_fwd_bwd: null pointer");
+  LDB_REQUIRE((((uintptr_t)pred | (uintptr_t)target | (uintptr_t)d_pred) & 15) == 0, LDB_EINVAL, "giou_fwd_bwd: 16-byte alignment");
+  long long blocks = (rows + 255) / 256;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  ldb::giou_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(pred, target, weight, (int)rows, eps, scale,
+                                                                            row_loss, loss, d_pred);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}

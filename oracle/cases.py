@@ -100,3 +100,29 @@ STEP_CASES_V2 = [
 # trained with torch.optim.SGD(momentum 0.9, wd 1e-4) under mmcv's linear warm-up formula (LrUpdaterHook,
 # warmup_ratio 0.001), a fresh synthetic batch (seed 2000 + iteration) every step.
 CURVE_CASE = ('c_r18_r18_2x128x160_100it', 18, 18, 2, 128, 160, 41, 100, 0.0002, 20)
+
+
+# Stand-alone loss modules (registry surface): seeded inputs for QualityFocalLoss / DistributionFocalLoss /
+# GIoULoss called on their own.  (name, rows, seed); the call variants are listed in LOSS_MODULE_CALLS.
+LOSS_MODULE_CASES = [('m_rows300_s51', 300, 51), ('m_rows64_s52', 64, 52)]
+# (tag, kwargs of forward): reduction_override / avg_factor / with or without weight
+LOSS_MODULE_CALLS = [('mean', dict()), ('avg', dict(avg_factor=37.5)), ('sum', dict(reduction_override='sum')),
+                     ('none', dict(reduction_override='none')), ('mean_now', dict(no_weight=True))]
+
+
+def loss_module_inputs(rows, seed, num_classes=80, reg_max=16):
+    g = torch.Generator().manual_seed(seed)
+    d = dict(
+        qfl_pred=torch.randn(rows, num_classes, generator=g) * 1.5 - 2.0,
+        qfl_prob=torch.rand(rows, num_classes + 1, generator=g) * 0.9 + 0.02,       # use_sigmoid=False: 81 joint scores
+        label=torch.randint(0, num_classes + 12, (rows,), generator=g).clamp(max=num_classes),   # ~13 % background
+        score=torch.rand(rows, generator=g),
+        weight=torch.rand(rows, generator=g) + 0.1,
+        dfl_pred=torch.randn(rows, reg_max + 1, generator=g) * 2.0,
+        dfl_target=torch.rand(rows, generator=g) * (reg_max - 0.1),
+    )
+    xy = torch.rand(rows, 2, generator=g) * 40
+    wh = torch.rand(rows, 2, generator=g) * 30 + 1
+    d['box_target'] = torch.cat([xy, xy + wh], 1)
+    d['box_pred'] = d['box_target'] + torch.randn(rows, 4, generator=g) * 6     # some pairs end up disjoint / inverted
+    return d

@@ -256,12 +256,45 @@ def gen_curve():
     print(name, [round(c, 4) for c in curve[:3]], '...', [round(c, 4) for c in curve[-3:]])
 
 
+def gen_loss_modules():
+    """QualityFocalLoss / DistributionFocalLoss / GIoULoss of the unmodified reference called stand-alone
+    (gfocal_loss.py:77-179, iou_loss.py:325-360): values and d/d pred for every call variant of cases.LOSS_MODULE_CALLS."""
+    from oracle import mmcv_standin
+    mmcv_standin.import_reference(rh.REF_ROOT)
+    from mmdet.models import build_loss
+    mods = dict(qfl=build_loss(dict(type='QualityFocalLoss', use_sigmoid=True, beta=2.0, loss_weight=1.0)),
+                qflp=build_loss(dict(type='QualityFocalLoss', use_sigmoid=False, beta=2.0, loss_weight=1.0)),
+                dfl=build_loss(dict(type='DistributionFocalLoss', loss_weight=0.25)),
+                giou=build_loss(dict(type='GIoULoss', loss_weight=2.0)))
+    for name, rows, seed in cases.LOSS_MODULE_CASES:
+        d = cases.loss_module_inputs(rows, seed)
+        gold = {}
+        for tag, kw in cases.LOSS_MODULE_CALLS:
+            kw = dict(kw)
+            w = None if kw.pop('no_weight', False) else d['weight']
+            for key, pred, target in (('qfl', d['qfl_pred'], (d['label'], d['score'])),
+                                      ('qflp', d['qfl_prob'], (d['label'], d['score'])),
+                                      ('dfl', d['dfl_pred'], d['dfl_target']),
+                                      ('giou', d['box_pred'], d['box_target'])):
+                p = pred.clone().requires_grad_(True)
+                out = mods[key](p, target, weight=w, **kw)
+                # reduction='none': contract with a fixed seeded vector so that one backward covers every row
+                up = torch.linspace(0.5, 1.5, out.numel()).reshape(out.shape) if out.dim() else torch.tensor(1.0)
+                (out * up).sum().backward()
+                gold[f'{key}_{tag}'] = dict(out=out.detach().clone(), grad=p.grad.clone())
+        torch.save(gold, os.path.join(OUT, name + '.pt'))
+        print(name, {k: float(v['out'].sum()) for k, v in list(gold.items())[:4]})
+
+
 def main():
     if not rh.reference_available():
         sys.exit('needs /root/reference (build container only)')
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
+    if '--loss-modules' in sys.argv:
+        gen_loss_modules()
+        return
     if '--config1' in sys.argv:      # round 2: BASELINE configs[0] only (the other fixtures stay byte-identical)
         gen_steps([cases.STEP_CASE_CONFIG1])
         return
