@@ -277,6 +277,10 @@ typedef struct {
    * fp32 convolution the reference runs; P = 2: ~2^-16). */
   int split, w_plane;
   int add_f32, mask_f32;  /* add_src / mask_src are fp32 tensors (fp32 activations of the parity mode) */
+  /* optional [N, Cout/8, 2] f32, zero-filled by the caller: the epilogue ADDS, per image and group of 8 output
+   * channels, the sum and the sum of squares of the values it stores -- the GroupNorm(32) statistics of a 256-channel
+   * GFL tower conv (gfl_head.py:102-133) without a separate pass over the output.  Non-flat convs, Cout % 32 == 0. */
+  float* gn_stats;
 } ldb_conv_desc;
 
 int ldb200_conv2d_tc(const ldb_conv_desc* desc, void* stream);
@@ -319,6 +323,24 @@ int ldb200_maxpool3x3s2(const void* in, void* out, int N, int H, int W, int C, i
 /* GroupNorm(G) [+ReLU] of mmcv ConvModule in the GFL towers (gfl_head.py:102-133, 177-180);
  * x,y: [N, HW, C] bf16; stats: [N, G, 2] f32 (sum, sum of squares; zero-filled by gn_stats). */
 int ldb200_gn_stats(const void* x, float* stats, int N, int HW, int C, int G, int dtype, void* stream);
+/* The same GroupNorm on up to LDB_GN_MAX_SEG tensors sharing gamma / beta -- the pyramid levels of one level-shared
+ * tower layer -- in ONE launch each (forward apply; backward = reduction pass + apply pass).  The statistics of the
+ * forward pass may come from ldb200_gn_stats or from the producing convolution's epilogue (ldb_conv_desc.gn_stats). */
+#define LDB_GN_MAX_SEG 5
+typedef struct {
+  const void* x;        /* [N, HW, C] conv output (pre-norm) */
+  const void* y;        /* backward: relu(GN(x)) of the forward pass */
+  const void* dy;       /* backward: gradient w.r.t. y */
+  void* out;            /* apply: y; backward: dx */
+  const float* stats;   /* [N, G, 2] sum, sum of squares of x */
+  float* red_ws;        /* backward: [N, G, 2] f32 scratch */
+  int red_zeroed;       /* backward: 1 = the caller zero-filled red_ws already */
+  int N, HW;
+} ldb_gn_seg;
+int ldb200_gn_apply_multi(const ldb_gn_seg* segs, int count, const float* gamma, const float* beta, int C, int G,
+                          float eps, int relu, int dtype, void* stream);
+int ldb200_gn_relu_bwd_multi(const ldb_gn_seg* segs, int count, const float* gamma, float* dgamma, float* dbeta, int C,
+                             int G, float eps, int dtype, void* stream);
 int ldb200_gn_apply(const void* x, const float* stats, const float* gamma, const float* beta, void* y,
                     int N, int HW, int C, int G, float eps, int relu, int dtype, void* stream);
 /* backward of y = relu(GN(x)): dx [N,HW,C] bf16, dgamma/dbeta [C] f32 ACCUMULATED (shared towers),

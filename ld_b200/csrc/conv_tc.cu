@@ -50,6 +50,8 @@ struct ConvSeg {            // geometry of one segment (= one FPN level of a lev
   const void* add_src;      // optional add (bf16, or fp32 when p.add_f32), nearest-resampled from [N, add_H, add_W, add_ld]
   int add_H, add_W;
   const void* mask_src;     // optional: multiply by (mask_src > 0), same addressing as out (bf16 / fp32 when p.mask_f32, ld = mask_ld)
+  float* gn_stats;          // optional [N, Cout/8, 2]: the epilogue accumulates sum / sum of squares of the output per
+                            // (image, group of 8 channels) -- GroupNorm(32) statistics without a pass over the output
   int pf_add, pf_mask;      // L2-prefetch the residual / mask tile with TMA while the main loop runs
   int tl_add, tl_mask;      // TMA epilogue: residual / mask boxes are TMA-loaded into the warp's staging buffer
 };
@@ -332,6 +334,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
     tmem_ld_wait();
     if (!SHORTK && ch + 1 < NCH && cbase + 32 < p.Cout) tmem_ld32_nowait(tbase + (ch + 1) * 32, rbuf[(ch + 1) & 1]);
     const uint32_t* r = rbuf[SHORTK ? 0 : (ch & 1)];
+    float gs[8];   // GroupNorm partials of this lane's pixel: {sum, sum of squares} of the chunk's four 8-channel groups
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gs[i] = 0.f;
     if (pix_ok) {
       const bool full = (cbase + 32 <= p.Cout) && p.vec_ok;   // warp-uniform fast path
       float v[32];
@@ -436,6 +441,16 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
               if (!(__bfloat162float(hb[e]) > 0.f)) v[j + e] = 0.f;
           }
         }
+        if (S.gn_stats) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              gs[2 * q] += v[8 * q + e];
+              gs[2 * q + 1] += v[8 * q + e] * v[8 * q + e];
+            }
+          }
+        }
         if (tma) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -483,6 +498,38 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
           if (p.out_f32) ((float*)S.out)[pix * (size_t)p.ldc + c] = vv;
           else ((__nv_bfloat16*)S.out)[pix * (size_t)p.ldc + c] = __float2bfloat16_rn(vv);
         }
+      }
+    }
+    if (S.gn_stats && live && cbase + 32 <= p.Cout) {   // warp-uniform
+      // 8 partials x 32 pixels -> 8 sums with 9 shuffles: each step halves the values a lane carries (the half it
+      // keeps is chosen by one lane bit), the last two steps are a plain butterfly; lanes with (lane & 3) == 0 end
+      // up with value index bit4*4 + bit3*2 + bit2
+      {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = hi ? gs[i] : gs[i + 4], keep = hi ? gs[i + 4] : gs[i];
+          gs[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+      }
+      {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float send = hi ? gs[i] : gs[i + 2], keep = hi ? gs[i + 2] : gs[i];
+          gs[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+      }
+      {
+        const bool hi = lane & 4;
+        const float send = hi ? gs[0] : gs[1], keep = hi ? gs[1] : gs[0];
+        gs[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      gs[0] += __shfl_xor_sync(0xffffffffu, gs[0], 2);
+      gs[0] += __shfl_xor_sync(0xffffffffu, gs[0], 1);
+      if ((lane & 3) == 0) {
+        const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        atomicAdd(S.gn_stats + ((size_t)n * (p.Cout >> 3) + (cbase >> 3) + (idx >> 1)) * 2 + (idx & 1), gs[0]);
       }
     }
     if (tma && (ch & 1)) {   // 64 columns staged: hand the box to the TMA (rows outside the tensor are clipped)
@@ -1349,6 +1396,9 @@ static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& commo
   g->add_src = d->add_src;
   g->add_H = d->add_H ? d->add_H : g->OH; g->add_W = d->add_W ? d->add_W : g->OW;
   g->mask_src = d->mask_src;
+  g->gn_stats = d->gn_stats;
+  LDB_REQUIRE(!d->gn_stats || (!d->flat && d->Cout % 32 == 0 && common.vec_ok), LDB_EINVAL,
+              "conv2d_tc: gn_stats needs a non-flat conv, Cout %% 32 == 0 and 16-byte aligned rows");
   if (g->add_src) LDB_REQUIRE(((uintptr_t)g->add_src & 15) == 0, LDB_EINVAL, "conv2d_tc: add_src alignment");
   if (d->flat) {
     LDB_REQUIRE(d->ntaps == 1 && d->sx == 1 && d->sy == 1, LDB_EINVAL, "conv2d_tc: flat mode needs a 1x1 stride-1 conv");
@@ -1464,7 +1514,7 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
                 e->accumulate == d->accumulate && e->flat == d->flat && e->in_ld == d->in_ld &&
                 (e->add_src != nullptr) == (d->add_src != nullptr) && e->add_ld == d->add_ld &&
                 (e->mask_src != nullptr) == (d->mask_src != nullptr) && e->mask_ld == d->mask_ld &&
-                e->split == d->split && e->w_plane == d->w_plane && e->add_f32 == d->add_f32 && e->mask_f32 == d->mask_f32 &&
+                (e->gn_stats != nullptr) == (d->gn_stats != nullptr) && e->split == d->split && e->w_plane == d->w_plane && e->add_f32 == d->add_f32 && e->mask_f32 == d->mask_f32 &&
                 memcmp(e->tap_dx, d->tap_dx, sizeof(d->tap_dx)) == 0 && memcmp(e->tap_dy, d->tap_dy, sizeof(d->tap_dy)) == 0 &&
                 memcmp(e->tap_wk, d->tap_wk, sizeof(d->tap_wk)) == 0,
                 LDB_EINVAL, "conv2d_tc_multi: segment %d does not share weights / taps / epilogue with segment 0", i);

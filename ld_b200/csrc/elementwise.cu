@@ -120,12 +120,40 @@ constexpr int GN_CPG = 8;
 constexpr int GN_PIX = 256;       // pixels per block
 constexpr int GN_THREADS = 256;
 
+// Up to LDB_GN_MAX_SEG tensors (the pyramid levels of one level-shared tower layer) per launch: the 1-D grid is the
+// concatenation of every segment's (image, 256-pixel block) list, so the small levels no longer pay a launch each.
+struct GnSegs {
+  int count, C;
+  int blk0[LDB_GN_MAX_SEG + 1];          // first block of each segment; [count] = grid size
+  int HW[LDB_GN_MAX_SEG], bpi[LDB_GN_MAX_SEG];   // pixels per image, blocks per image
+  const void* x[LDB_GN_MAX_SEG];
+  const void* y[LDB_GN_MAX_SEG];
+  const void* dy[LDB_GN_MAX_SEG];
+  void* out[LDB_GN_MAX_SEG];             // y (apply) or dx (backward)
+  const float* stats[LDB_GN_MAX_SEG];    // [N, G, 2] sum / sum of squares of x
+  float* acc[LDB_GN_MAX_SEG];            // [N, G, 2]: stats being accumulated, or the backward reductions
+};
+struct GnBlock { int sg, n, p0, p1; };
+__device__ __forceinline__ GnBlock gn_block(const GnSegs& S) {
+  GnBlock b;
+  b.sg = 0;
+#pragma unroll
+  for (int i = 1; i < LDB_GN_MAX_SEG; ++i) b.sg += (i < S.count && (int)blockIdx.x >= S.blk0[i]) ? 1 : 0;
+  const int local = blockIdx.x - S.blk0[b.sg];
+  b.n = local / S.bpi[b.sg];
+  b.p0 = (local - b.n * S.bpi[b.sg]) * GN_PIX;
+  b.p1 = min(b.p0 + GN_PIX, S.HW[b.sg]);
+  return b;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restrict__ x, float* __restrict__ stats,
-                                                               int HW, int C) {
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __grid_constant__ GnSegs S) {
+  const GnBlock B = gn_block(S);
+  const int C = S.C, HW = S.HW[B.sg], n = B.n, p0 = B.p0, p1 = B.p1;
+  const T* __restrict__ x = (const T*)S.x[B.sg];
+  float* __restrict__ stats = S.acc[B.sg];
   const int G = C / GN_CPG;
-  const int n = blockIdx.y, g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
-  const int p0 = blockIdx.x * GN_PIX, p1 = min(p0 + GN_PIX, HW);
+  const int g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
   const T* base = x + (size_t)n * HW * C + g * 8;
   float s = 0.f, ss = 0.f;
   int p = p0 + r0;
@@ -160,11 +188,15 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restric
 // y = relu((x - mean) * rstd * gamma + beta)   (relu optional)
 template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
-gn_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
-                const float* __restrict__ beta, T* __restrict__ y, int N, int HW, int C, float eps, int relu) {
+gn_apply_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float eps, int relu) {
+  const GnBlock B = gn_block(S);
+  const int C = S.C, HW = S.HW[B.sg], n = B.n, p0 = B.p0, p1 = B.p1;
+  const T* __restrict__ x = (const T*)S.x[B.sg];
+  const float* __restrict__ stats = S.stats[B.sg];
+  T* __restrict__ y = (T*)S.out[B.sg];
   const int G = C / GN_CPG;
-  const int n = blockIdx.y, g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
-  const int p0 = blockIdx.x * GN_PIX, p1 = min(p0 + GN_PIX, HW);
+  const int g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
   const float inv_m = 1.f / ((float)HW * GN_CPG);
   const float mean = __ldg(stats + ((size_t)n * G + g) * 2) * inv_m;
   const float rstd = rsqrtf(fmaxf(__ldg(stats + ((size_t)n * G + g) * 2 + 1) * inv_m - mean * mean, 0.f) + eps);
@@ -208,13 +240,17 @@ gn_apply_kernel(const T* __restrict__ x, const float* __restrict__ stats, const 
 // red: [N, G, 2] fp32 accumulated; dgamma/dbeta: [C] fp32 accumulated.
 template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
-gn_bwd_stats_kernel(const T* __restrict__ dy, const T* __restrict__ y,
-                    const T* __restrict__ x, const float* __restrict__ stats,
-                    const float* __restrict__ gamma, float* __restrict__ red, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta, int HW, int C, float eps) {
+gn_bwd_stats_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ gamma, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, float eps) {
+  const GnBlock B = gn_block(S);
+  const int C = S.C, HW = S.HW[B.sg], n = B.n, p0 = B.p0, p1 = B.p1;
+  const T* __restrict__ dy = (const T*)S.dy[B.sg];
+  const T* __restrict__ y = (const T*)S.y[B.sg];
+  const T* __restrict__ x = (const T*)S.x[B.sg];
+  const float* __restrict__ stats = S.stats[B.sg];
+  float* __restrict__ red = S.acc[B.sg];
   const int G = C / GN_CPG;
-  const int n = blockIdx.y, g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
-  const int p0 = blockIdx.x * GN_PIX, p1 = min(p0 + GN_PIX, HW);
+  const int g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
   const float inv_m = 1.f / ((float)HW * GN_CPG);
   const float mean = __ldg(stats + ((size_t)n * G + g) * 2) * inv_m;
   const float rstd = rsqrtf(fmaxf(__ldg(stats + ((size_t)n * G + g) * 2 + 1) * inv_m - mean * mean, 0.f) + eps);
@@ -268,13 +304,17 @@ gn_bwd_stats_kernel(const T* __restrict__ dy, const T* __restrict__ y,
 // pass 2: dx = rstd * (dxh - mean(dxh) - xh * mean(dxh*xh))
 template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
-gn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y,
-                    const T* __restrict__ x, const float* __restrict__ stats,
-                    const float* __restrict__ gamma, const float* __restrict__ red, T* __restrict__ dx,
-                    int N, int HW, int C, float eps) {
+gn_bwd_apply_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ gamma, float eps) {
+  const GnBlock B = gn_block(S);
+  const int C = S.C, HW = S.HW[B.sg], n = B.n, p0 = B.p0, p1 = B.p1;
+  const T* __restrict__ dy = (const T*)S.dy[B.sg];
+  const T* __restrict__ y = (const T*)S.y[B.sg];
+  const T* __restrict__ x = (const T*)S.x[B.sg];
+  const float* __restrict__ stats = S.stats[B.sg];
+  const float* __restrict__ red = S.acc[B.sg];
+  T* __restrict__ dx = (T*)S.out[B.sg];
   const int G = C / GN_CPG;
-  const int n = blockIdx.y, g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
-  const int p0 = blockIdx.x * GN_PIX, p1 = min(p0 + GN_PIX, HW);
+  const int g = threadIdx.x % G, lanes = GN_THREADS / G, r0 = threadIdx.x / G;
   const float inv_m = 1.f / ((float)HW * GN_CPG);
   const float mean = __ldg(stats + ((size_t)n * G + g) * 2) * inv_m;
   const float rstd = rsqrtf(fmaxf(__ldg(stats + ((size_t)n * G + g) * 2 + 1) * inv_m - mean * mean, 0.f) + eps);
@@ -596,30 +636,95 @@ static int gn_check(int C, int G) {
   return 0;
 }
 
-extern "C" int ldb200_gn_stats(const void* x, float* stats, int N, int HW, int C, int G, int dtype, void* stream_) {
+// segment table of a launch: `segs[i]` describes one tensor of [N, HW, C]
+static int gn_make_segs(const ldb_gn_seg* segs, int count, int C, int G, GnSegs* S) {
   int e = gn_check(C, G);
   if (e) return e;
+  LDB_REQUIRE(segs && count >= 1 && count <= LDB_GN_MAX_SEG, LDB_EINVAL, "group norm: 1..%d segments", LDB_GN_MAX_SEG);
+  memset(S, 0, sizeof(*S));
+  S->count = count;
+  S->C = C;
+  int blk = 0;
+  for (int i = 0; i < count; ++i) {
+    LDB_REQUIRE(segs[i].N >= 1 && segs[i].HW >= 1, LDB_EINVAL, "group norm: segment %d shape", i);
+    S->blk0[i] = blk;
+    S->HW[i] = segs[i].HW;
+    S->bpi[i] = (segs[i].HW + GN_PIX - 1) / GN_PIX;
+    blk += S->bpi[i] * segs[i].N;
+    S->x[i] = segs[i].x; S->y[i] = segs[i].y; S->dy[i] = segs[i].dy;
+    S->stats[i] = segs[i].stats;
+  }
+  for (int i = count; i <= LDB_GN_MAX_SEG; ++i) S->blk0[i] = blk;
+  return 0;
+}
+
+extern "C" int ldb200_gn_stats(const void* x, float* stats, int N, int HW, int C, int G, int dtype, void* stream_) {
   LDB_REQUIRE(x && stats, LDB_EINVAL, "gn_stats: null pointer");
+  ldb_gn_seg seg;
+  memset(&seg, 0, sizeof(seg));
+  seg.x = x; seg.N = N; seg.HW = HW;
+  GnSegs S;
+  int e = gn_make_segs(&seg, 1, C, G, &S);
+  if (e) return e;
+  S.acc[0] = stats;
   cudaStream_t s = (cudaStream_t)stream_;
   LDB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * N * G, s));
-  dim3 grid((HW + GN_PIX - 1) / GN_PIX, N);
-  if (dtype == LDB_F32) gn_stats_kernel<float><<<grid, GN_THREADS, 0, s>>>((const float*)x, stats, HW, C);
-  else gn_stats_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, s>>>((const __nv_bfloat16*)x, stats, HW, C);
+  if (dtype == LDB_F32) gn_stats_kernel<float><<<S.blk0[1], GN_THREADS, 0, s>>>(S);
+  else gn_stats_kernel<__nv_bfloat16><<<S.blk0[1], GN_THREADS, 0, s>>>(S);
+  LDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ldb200_gn_apply_multi(const ldb_gn_seg* segs, int count, const float* gamma, const float* beta, int C,
+                                     int G, float eps, int relu, int dtype, void* stream_) {
+  GnSegs S;
+  int e = gn_make_segs(segs, count, C, G, &S);
+  if (e) return e;
+  LDB_REQUIRE(gamma && beta, LDB_EINVAL, "gn_apply: null pointer");
+  for (int i = 0; i < count; ++i) {
+    LDB_REQUIRE(segs[i].x && segs[i].stats && segs[i].out, LDB_EINVAL, "gn_apply: null pointer in segment %d", i);
+    S.out[i] = segs[i].out;
+  }
+  if (dtype == LDB_F32)
+    gn_apply_kernel<float><<<S.blk0[count], GN_THREADS, 0, (cudaStream_t)stream_>>>(S, gamma, beta, eps, relu);
+  else
+    gn_apply_kernel<__nv_bfloat16><<<S.blk0[count], GN_THREADS, 0, (cudaStream_t)stream_>>>(S, gamma, beta, eps, relu);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int ldb200_gn_apply(const void* x, const float* stats, const float* gamma, const float* beta, void* y,
                                int N, int HW, int C, int G, float eps, int relu, int dtype, void* stream_) {
-  int e = gn_check(C, G);
+  ldb_gn_seg seg;
+  memset(&seg, 0, sizeof(seg));
+  seg.x = x; seg.stats = stats; seg.out = y; seg.N = N; seg.HW = HW;
+  return ldb200_gn_apply_multi(&seg, 1, gamma, beta, C, G, eps, relu, dtype, stream_);
+}
+
+extern "C" int ldb200_gn_relu_bwd_multi(const ldb_gn_seg* segs, int count, const float* gamma, float* dgamma,
+                                        float* dbeta, int C, int G, float eps, int dtype, void* stream_) {
+  GnSegs S;
+  int e = gn_make_segs(segs, count, C, G, &S);
   if (e) return e;
-  LDB_REQUIRE(x && stats && gamma && beta && y, LDB_EINVAL, "gn_apply: null pointer");
-  dim3 grid((HW + GN_PIX - 1) / GN_PIX, N);
-  if (dtype == LDB_F32)
-    gn_apply_kernel<float><<<grid, GN_THREADS, 0, (cudaStream_t)stream_>>>((const float*)x, stats, gamma, beta, (float*)y, N, HW, C, eps, relu);
-  else
-    gn_apply_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)x, stats, gamma, beta,
-                                                                                   (__nv_bfloat16*)y, N, HW, C, eps, relu);
+  LDB_REQUIRE(gamma && dgamma && dbeta, LDB_EINVAL, "gn_relu_bwd: null pointer");
+  cudaStream_t s = (cudaStream_t)stream_;
+  for (int i = 0; i < count; ++i) {
+    LDB_REQUIRE(segs[i].dy && segs[i].y && segs[i].x && segs[i].stats && segs[i].red_ws && segs[i].out, LDB_EINVAL,
+                "gn_relu_bwd: null pointer in segment %d", i);
+    S.out[i] = segs[i].out;
+    S.acc[i] = segs[i].red_ws;
+    // the per-segment scratch may be slices of one buffer the caller zeroed itself (red_zeroed)
+    if (!segs[i].red_zeroed) LDB_CUDA(cudaMemsetAsync(segs[i].red_ws, 0, sizeof(float) * 2 * segs[i].N * G, s));
+  }
+  if (dtype == LDB_F32) {
+    gn_bwd_stats_kernel<float><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, dgamma, dbeta, eps);
+    LDB_CUDA(cudaGetLastError());
+    gn_bwd_apply_kernel<float><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, eps);
+  } else {
+    gn_bwd_stats_kernel<__nv_bfloat16><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, dgamma, dbeta, eps);
+    LDB_CUDA(cudaGetLastError());
+    gn_bwd_apply_kernel<__nv_bfloat16><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, eps);
+  }
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -627,28 +732,10 @@ extern "C" int ldb200_gn_apply(const void* x, const float* stats, const float* g
 extern "C" int ldb200_gn_relu_bwd(const void* dy, const void* y, const void* x, const float* stats, const float* gamma,
                                   float* red_ws, float* dgamma, float* dbeta, void* dx, int N, int HW, int C, int G,
                                   float eps, int dtype, void* stream_) {
-  int e = gn_check(C, G);
-  if (e) return e;
-  LDB_REQUIRE(dy && y && x && stats && gamma && red_ws && dgamma && dbeta && dx, LDB_EINVAL, "gn_relu_bwd: null pointer");
-  cudaStream_t s = (cudaStream_t)stream_;
-  LDB_CUDA(cudaMemsetAsync(red_ws, 0, sizeof(float) * 2 * N * G, s));
-  dim3 grid((HW + GN_PIX - 1) / GN_PIX, N);
-  if (dtype == LDB_F32) {
-    gn_bwd_stats_kernel<float><<<grid, GN_THREADS, 0, s>>>((const float*)dy, (const float*)y, (const float*)x, stats, gamma,
-                                                         red_ws, dgamma, dbeta, HW, C, eps);
-    LDB_CUDA(cudaGetLastError());
-    gn_bwd_apply_kernel<float><<<grid, GN_THREADS, 0, s>>>((const float*)dy, (const float*)y, (const float*)x, stats, gamma,
-                                                         red_ws, (float*)dx, N, HW, C, eps);
-  } else {
-    gn_bwd_stats_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
-                                                                 (const __nv_bfloat16*)x, stats, gamma, red_ws, dgamma, dbeta, HW, C, eps);
-    LDB_CUDA(cudaGetLastError());
-    gn_bwd_apply_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
-                                                                 (const __nv_bfloat16*)x, stats, gamma, red_ws, (__nv_bfloat16*)dx,
-                                                                 N, HW, C, eps);
-  }
-  LDB_CUDA(cudaGetLastError());
-  return 0;
+  ldb_gn_seg seg;
+  memset(&seg, 0, sizeof(seg));
+  seg.dy = dy; seg.y = y; seg.x = x; seg.stats = stats; seg.red_ws = red_ws; seg.out = dx; seg.N = N; seg.HW = HW;
+  return ldb200_gn_relu_bwd_multi(&seg, 1, gamma, dgamma, dbeta, C, G, eps, dtype, stream_);
 }
 
 extern "C" int ldb200_upsample_add_bwd(const void* dfine, void* dcoarse, int N, int Hf, int Wf, int Hc, int Wc, int C,

@@ -129,23 +129,29 @@ class GFLHead(nn.Module):
         use_side = xs[0].is_cuda and os.environ.get('LDB200_NO_TOWER_STREAM') is None
         main = torch.cuda.current_stream() if use_side else None
         side = self._tower_stream() if use_side else None
+        # one tower layer = one node: conv of all levels (1 launch, GroupNorm statistics from its epilogue) +
+        # normalise/ReLU of all levels (1 launch).  LDB200_GN_PER_LEVEL=1: the per-level GroupNorm launches (A/B).
+        fused = os.environ.get('LDB200_GN_PER_LEVEL') is None and xs[0].shape[-1] % 32 == 0
+
+        def layer(m, fs):
+            if fused and m.gn.num_groups * 8 == m.conv.out_channels:
+                return engine.conv_gn_relu_levels(m.conv._cl(), m.gn.weight, m.gn.bias, fs, 1, m.gn.num_groups, m.gn.eps)
+            cs = engine.conv_levels(m.conv._cl(), fs)
+            return [engine.gn_relu(c, m.gn.weight, m.gn.bias, m.gn.num_groups, m.gn.eps) for c in cs]
         if use_side:
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                for mr in self.reg_convs:     # all levels of one tower layer in one launch
-                    rs = engine.conv_levels(mr.conv._cl(), rfs)
-                    rfs = [engine.gn_relu(r, mr.gn.weight, mr.gn.bias, mr.gn.num_groups, mr.gn.eps) for r in rs]
+                for mr in self.reg_convs:
+                    rfs = layer(mr, rfs)
         for mc in self.cls_convs:
-            cs = engine.conv_levels(mc.conv._cl(), cfs)
-            cfs = [engine.gn_relu(c, mc.gn.weight, mc.gn.bias, mc.gn.num_groups, mc.gn.eps) for c in cs]
+            cfs = layer(mc, cfs)
         if use_side:
             main.wait_stream(side)
             for r in rfs:
                 r.record_stream(main)
         else:
             for mr in self.reg_convs:
-                rs = engine.conv_levels(mr.conv._cl(), rfs)
-                rfs = [engine.gn_relu(r, mr.gn.weight, mr.gn.bias, mr.gn.num_groups, mr.gn.eps) for r in rs]
+                rfs = layer(mr, rfs)
         return list(zip(cfs, rfs))
 
     def _tower_stream(self):

@@ -58,7 +58,12 @@ class ConvDesc(C.Structure):
                 ('scale', C.c_void_p), ('bias', C.c_void_p), ('add_src', C.c_void_p), ('add_H', C.c_int),
                 ('add_W', C.c_int), ('add_ld', C.c_int), ('mask_src', C.c_void_p), ('mask_ld', C.c_int),
                 ('relu', C.c_int), ('accumulate', C.c_int), ('split', C.c_int), ('w_plane', C.c_int),
-                ('add_f32', C.c_int), ('mask_f32', C.c_int)]
+                ('add_f32', C.c_int), ('mask_f32', C.c_int), ('gn_stats', C.c_void_p)]
+
+
+class GnSeg(C.Structure):
+    _fields_ = [('x', C.c_void_p), ('y', C.c_void_p), ('dy', C.c_void_p), ('out', C.c_void_p), ('stats', C.c_void_p),
+                ('red_ws', C.c_void_p), ('red_zeroed', C.c_int), ('N', C.c_int), ('HW', C.c_int)]
 
 
 class WgradDesc(C.Structure):
@@ -103,6 +108,10 @@ _SIGS = {
     'ldb200_gn_stats': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     'ldb200_gn_apply': (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_float, C.c_int, C.c_int, C.c_void_p]),
     'ldb200_gn_relu_bwd': (C.c_int, [C.c_void_p] * 9 + [C.c_int] * 4 + [C.c_float, C.c_int, C.c_void_p]),
+    'ldb200_gn_apply_multi': (C.c_int, [C.POINTER(GnSeg), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                        C.c_int, C.c_int, C.c_void_p]),
+    'ldb200_gn_relu_bwd_multi': (C.c_int, [C.POINTER(GnSeg), C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_float,
+                                                                                          C.c_int, C.c_void_p]),
     'ldb200_upsample_add_bwd': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]),
     'ldb200_relu_bwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int, C.c_void_p]),
     'ldb200_colsum': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -153,7 +162,7 @@ _LAUNCHES = {'ldb200_ld_targets': 3, 'ldb200_ld_loss_prepass': 1, 'ldb200_ld_los
              'ldb200_scatter_add_rows': 1, 'ldb200_gi_region': 3, 'ldb200_gi_region_v2': 3, 'ldb200_ld_loss_prepass_v2': 1,
              'ldb200_ld_loss_fused_v2': 1, 'ldb200_dgqp_forward': 1, 'ldb200_dgqp_backward': 1, 'ldb200_conv2d_tc': 1, 'ldb200_conv2d_tc_multi': 1, 'ldb200_conv2d_wgrad_tc': 1,
              'ldb200_stem_im2col': 1, 'ldb200_split_bf16': 1, 'ldb200_stem_tc': 1, 'ldb200_maxpool3x3s2': 1, 'ldb200_gn_stats': 1, 'ldb200_gn_apply': 1,
-             'ldb200_gn_relu_bwd': 2, 'ldb200_upsample_add_bwd': 1, 'ldb200_relu_bwd': 1, 'ldb200_colsum': 1,
+             'ldb200_gn_relu_bwd': 2, 'ldb200_gn_apply_multi': 1, 'ldb200_gn_relu_bwd_multi': 2, 'ldb200_upsample_add_bwd': 1, 'ldb200_relu_bwd': 1, 'ldb200_colsum': 1,
              'ldb200_sgd_flat': 1, 'ldb200_sgd_flat_dev': 1, 'ldb200_bn_fold': 1, 'ldb200_bn_fold_bwd': 1, 'ldb200_mse_fwd_bwd': 1, 'ldb200_kl_dense_fwd_bwd': 1,
              'ldb200_qfl_fwd_bwd': 1, 'ldb200_dfl_fwd_bwd': 1, 'ldb200_giou_fwd_bwd': 1}
 launch_count = {'n': 0}

@@ -421,8 +421,10 @@ def conv2d_tc(x, w_packed, cout, kh=1, kw=1, stride=1, pad=0, out=None, out_dtyp
 
 
 def conv2d_tc_multi(xs, w_packed, cout, kh=1, kw=1, stride=1, pad=0, outs=None, out_dtype=torch.bfloat16,
-                    scale=None, bias=None, masks=None, relu=False, taps=None):
-    """The same convolution on several inputs (the FPN levels of a level-shared head conv) in ONE launch."""
+                    scale=None, bias=None, masks=None, relu=False, taps=None, gn_stats=None):
+    """The same convolution on several inputs (the FPN levels of a level-shared head conv) in ONE launch.
+    gn_stats: optional list of zero-filled [N, cout/8, 2] f32 tensors the epilogue accumulates the GroupNorm
+    statistics of each output into."""
     n = len(xs)
     descs = (L.ConvDesc * n)()
     res, keep = [], []
@@ -430,6 +432,9 @@ def conv2d_tc_multi(xs, w_packed, cout, kh=1, kw=1, stride=1, pad=0, outs=None, 
         o, k = _conv_desc(descs[i], x, w_packed, cout, kh, kw, stride, pad, None if outs is None else outs[i],
                           out_dtype, scale, bias, None, None if masks is None else masks[i], relu, False, False,
                           taps, None if taps is None else tuple(x.shape[1:3]), None)
+        if gn_stats is not None:
+            assert gn_stats[i].dtype == torch.float32 and gn_stats[i].numel() == x.shape[0] * (cout // 8) * 2
+            descs[i].gn_stats = gn_stats[i].data_ptr()
         res.append(o)
         keep.append(k)
     L.check(L.load().ldb200_conv2d_tc_multi(descs, n, L.stream_ptr()), 'ldb200_conv2d_tc_multi')
@@ -484,6 +489,48 @@ def gn_relu_fwd(x, gamma, beta, groups=32, eps=1e-5, relu=True):
     L.check(lib.ldb200_gn_apply(L.ptr(x), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(y), n, h * w, c, groups,
                                 float(eps), int(relu), _dt(x.dtype), L.stream_ptr()), 'ldb200_gn_apply')
     return y, stats
+
+
+def gn_apply_multi(xs, stats, gamma, beta, groups=32, eps=1e-5, relu=True):
+    """y_l = relu(GroupNorm(x_l)) for all levels in ONE launch; stats[l]: [N, G, 2] (from `gn_stats` or from the
+    producing conv's epilogue)."""
+    n = len(xs)
+    segs = (L.GnSeg * n)()
+    ys = []
+    c = xs[0].shape[-1]
+    for i, x in enumerate(xs):
+        assert x.is_contiguous() and x.shape[-1] == c and x.dtype == xs[0].dtype
+        y = torch.empty_like(x)
+        segs[i].x, segs[i].out, segs[i].stats = x.data_ptr(), y.data_ptr(), stats[i].data_ptr()
+        segs[i].N, segs[i].HW = x.shape[0], x.shape[1] * x.shape[2]
+        ys.append(y)
+    L.check(L.load().ldb200_gn_apply_multi(segs, n, L.ptr(gamma), L.ptr(beta), c, groups, float(eps), int(relu),
+                                           _dt(xs[0].dtype), L.stream_ptr()), 'ldb200_gn_apply_multi')
+    return ys
+
+
+def gn_relu_bwd_multi(dys, ys, xs, stats, gamma, dgamma, dbeta, groups=32, eps=1e-5):
+    """Backward of `gn_apply_multi` (relu=True) for all levels in two launches -> list of dx; dgamma / dbeta [C] f32
+    accumulated in place."""
+    n = len(xs)
+    segs = (L.GnSeg * n)()
+    c = xs[0].shape[-1]
+    tot = sum(x.shape[0] for x in xs) * groups * 2
+    red = torch.zeros(tot, dtype=torch.float32, device=xs[0].device)     # one fill for all levels
+    dxs, o = [], 0
+    for i, (dy, y, x) in enumerate(zip(dys, ys, xs)):
+        assert dy.is_contiguous() and y.is_contiguous() and x.is_contiguous() and dy.dtype == y.dtype == x.dtype
+        dx = torch.empty_like(x)
+        k = x.shape[0] * groups * 2
+        segs[i].dy, segs[i].y, segs[i].x, segs[i].out = dy.data_ptr(), y.data_ptr(), x.data_ptr(), dx.data_ptr()
+        segs[i].stats, segs[i].red_ws, segs[i].red_zeroed = stats[i].data_ptr(), red[o:o + k].data_ptr(), 1
+        segs[i].N, segs[i].HW = x.shape[0], x.shape[1] * x.shape[2]
+        o += k
+        dxs.append(dx)
+    L.check(L.load().ldb200_gn_relu_bwd_multi(segs, n, L.ptr(gamma), L.ptr(dgamma), L.ptr(dbeta), c, groups, float(eps),
+                                              _dt(xs[0].dtype), L.stream_ptr()), 'ldb200_gn_relu_bwd_multi')
+    del red
+    return dxs
 
 
 def gn_relu_bwd(dy, y, x, stats, gamma, dgamma, dbeta, groups=32, eps=1e-5):
