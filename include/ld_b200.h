@@ -318,6 +318,15 @@ int ldb200_split_bf16(const float* x, int64_t rows, int C, int ld_in, int planes
 /* 7x7/2 pad-3 stem conv as a GEMM operand: img [N,3,H,W] f32 (NCHW) -> out [N*HO*WO, 192] bf16 with
  * column (r*7+s)*3+c, zero-padded from 147 (resnet.py:524-570, 626). */
 int ldb200_stem_im2col(const float* img, void* out, int N, int H, int W, int out_dtype, void* stream);
+/* Deformable convolution v1 forward, sampling half (frozen DCN teachers: resnext.py:64-75 / resnet.py:172-184 ->
+ * mmcv.ops.DeformConv2dPack; mmcv is not vendored in the reference, the published DCNv1 algorithm is restated):
+ *   col[n,yo,xo, k*C + c] = bilinear(x[n,:,:,c], yo*stride - pad + (k/kw)*dil + dy_k, xo*stride - pad + (k%kw)*dil + dx_k)
+ * x [N,H,W,C] (dtype bf16 / f32), offset [N,HO,WO,offset_ld] f32 with channel 2*(g*kh*kw + k) = dy, +1 = dx (the layout
+ * of mmcv and torchvision.ops.deform_conv2d), col [N*HO*WO, kh*kw*C] (dtype).  The GEMM half is ldb200_conv2d_tc in
+ * flat mode on `col` with the conv's ordinary packed weights [Cout, kh*kw*Cin]. */
+int ldb200_deform_im2col(const void* x, const float* offset, void* col, int N, int H, int W, int C, int HO, int WO,
+                         int kh, int kw, int stride, int pad, int dilation, int deform_groups, int offset_ld, int dtype,
+                         void* stream);
 /* 3x3 stride-2 pad-1 max pool (resnet.py:630). */
 int ldb200_maxpool3x3s2(const void* in, void* out, int N, int H, int W, int C, int dtype, void* stream);
 /* GroupNorm(G) [+ReLU] of mmcv ConvModule in the GFL towers (gfl_head.py:102-133, 177-180);

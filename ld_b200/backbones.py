@@ -61,25 +61,103 @@ class BasicBlock(_Block):
         return engine.res_block(x, [(self.conv1, self.bn1, self.stride, 1), (self.conv2, self.bn2, 1, 1)], ds)
 
 
+class DeformConv2dPack(nn.Module):
+    """mmcv.ops.DeformConv2dPack (type 'DCN'; mmcv is not vendored in the reference -- restated from mmcv 1.2.x):
+    parameters `weight` [Cout, Cin/groups, k, k] (no bias) and `conv_offset.{weight,bias}` (a plain conv with
+    deform_groups*2*k*k output channels, zero-initialised).  Forward only (the DCN backbones of the LD configs are frozen
+    teachers): offset conv (tcgen05) -> bilinear-sampled im2col (ldb200_deform_im2col) -> tcgen05 GEMM."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deform_groups=1, bias=False):
+        super().__init__()
+        assert not bias and in_channels % groups == 0 and out_channels % groups == 0
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, (kernel_size, kernel_size)
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.groups, self.deform_groups = groups, deform_groups
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels // groups, kernel_size, kernel_size))
+        n = in_channels * kernel_size * kernel_size
+        nn.init.uniform_(self.weight, -1.0 / math.sqrt(n), 1.0 / math.sqrt(n))      # DeformConv2d.reset_parameters
+        self.conv_offset = _Conv2d(in_channels, deform_groups * 2 * kernel_size * kernel_size, kernel_size, stride,
+                                   padding, dilation=dilation, bias=True)
+        nn.init.zeros_(self.conv_offset.weight)
+        nn.init.zeros_(self.conv_offset.bias)
+
+    def forward_nhwc(self, x, scale=None, shift=None, relu=False):
+        """x [N,H,W,Cin] NHWC (bf16, or fp32 in the parity mode) -> relu?(scale * dcn(x) + shift) [N,HO,WO,Cout]."""
+        if any(p.requires_grad for p in self.parameters()) and torch.is_grad_enabled():
+            raise NotImplementedError('DeformConv2dPack runs forward-only (the DCN backbones of the LD configs are frozen '
+                                      'teachers, kd_one_stage.py:70-72)')
+        k = self.kernel_size[0]
+        n, h, w, c = x.shape
+        co_off = self.conv_offset.out_channels
+        off = ops.conv2d_tc(x, engine.packed_weight(self.conv_offset._cl()), co_off, k, k, self.stride, self.padding,
+                            out_dtype=torch.float32, bias=self.conv_offset.bias.detach().float().contiguous())
+        ho, wo = off.shape[1:3]
+        col = ops.deform_im2col(x, off, k, k, self.stride, self.padding, self.dilation, self.deform_groups)
+        wp = engine.packed_weight(self.weight, groups=self.groups)
+        y = ops.conv2d_tc(col.view(1, 1, n * ho * wo, k * k * c), wp, self.out_channels, scale=scale, bias=shift, relu=relu)
+        return y.view(n, ho, wo, self.out_channels)
+
+
 class Bottleneck(_Block):
-    """resnet.py:95-300, style='pytorch' (the stride sits on the 3x3 conv)."""
+    """resnet.py:95-300, style='pytorch' (the stride sits on the 3x3 conv); with `groups` / `base_width` the ResNeXt
+    bottleneck (resnext.py:11-106), with `dcn` its 3x3 conv is a DeformConv2dPack (resnet.py:172-184)."""
     expansion = 4
 
-    def __init__(self, inplanes, planes, stride=1, downsample=None):
+    def __init__(self, inplanes, planes, stride=1, downsample=None, groups=1, base_width=4, base_channels=64, dcn=None):
         super().__init__()
-        self.conv1 = _Conv2d(inplanes, planes, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
-        self.conv2 = _Conv2d(planes, planes, 3, stride, 1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
-        self.conv3 = _Conv2d(planes, planes * 4, 1, bias=False)
+        width = planes if groups == 1 else math.floor(planes * (base_width / base_channels)) * groups
+        self.width, self.groups = width, groups
+        self.with_dcn = dcn is not None
+        self.conv1 = _Conv2d(inplanes, width, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(width)
+        if self.with_dcn:
+            dcn = dict(dcn)
+            if dcn.pop('type', 'DCN') != 'DCN':
+                raise NotImplementedError('only dcn=dict(type="DCN") (DCNv1) is used by the LD / GFL configs')
+            if dcn.pop('fallback_on_stride', False):
+                raise NotImplementedError('dcn.fallback_on_stride')
+            self.conv2 = DeformConv2dPack(width, width, 3, stride, 1, groups=groups, **dcn)
+        else:
+            self.conv2 = _Conv2d(width, width, 3, stride, 1, groups=groups, bias=False)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.conv3 = _Conv2d(width, planes * 4, 1, bias=False)
         self.bn3 = nn.BatchNorm2d(planes * 4)
         self.downsample = downsample
         self.stride = stride
 
     def forward(self, x):
+        if self.groups > 1 or self.with_dcn:
+            return self._forward_frozen(x)
         ds = None if self.downsample is None else (self.downsample[0], self.downsample[1])
         return engine.res_block(x, [(self.conv1, self.bn1, 1, 0), (self.conv2, self.bn2, self.stride, 1),
                                     (self.conv3, self.bn3, 1, 0)], ds)
+
+    def _forward_frozen(self, x):
+        """Grouped / deformable 3x3: forward-only path (the X101-32x4d-DCN and R101-DCN backbones are frozen teachers).
+        Grouped weights run as block-diagonal dense tcgen05 tiles."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError('grouped / deformable bottlenecks are implemented forward-only (frozen teacher)')
+
+        def aff(bn):
+            s_, b_ = engine.bn_affine(bn)
+            return s_.detach().contiguous(), b_.detach().contiguous()
+        s1, b1 = aff(self.bn1)
+        s2, b2 = aff(self.bn2)
+        s3, b3 = aff(self.bn3)
+        idt = x
+        if self.downsample is not None:
+            sd, bd = aff(self.downsample[1])
+            wd = self.downsample[0]
+            idt = ops.conv2d_tc(x, engine.packed_weight(wd._cl()), wd.out_channels, 1, 1, self.stride, 0, scale=sd, bias=bd)
+        h = ops.conv2d_tc(x, engine.packed_weight(self.conv1._cl()), self.width, scale=s1, bias=b1, relu=True)
+        if self.with_dcn:
+            h = self.conv2.forward_nhwc(h, s2, b2, relu=True)
+        else:
+            h = ops.conv2d_tc(h, engine.packed_weight(self.conv2._cl(), groups=self.groups), self.width, 3, 3, self.stride, 1,
+                              scale=s2, bias=b2, relu=True)
+        return ops.conv2d_tc(h, engine.packed_weight(self.conv3._cl()), self.conv3.out_channels, scale=s3, bias=b3,
+                             add=idt, relu=True)
 
 
 @BACKBONES.register_module()
@@ -101,7 +179,7 @@ class ResNet(nn.Module):
                            base_channels=base_channels != 64, strides=tuple(strides) != (1, 2, 2, 2)[:num_stages],
                            dilations=any(d != 1 for d in dilations), style=style != 'pytorch', deep_stem=deep_stem,
                            avg_down=avg_down, conv_cfg=conv_cfg is not None, norm=norm_cfg.get('type') != 'BN',
-                           norm_eval=not norm_eval, dcn=dcn is not None, plugins=plugins is not None, with_cp=with_cp)
+                           norm_eval=not norm_eval, plugins=plugins is not None, with_cp=with_cp)
         bad = [k for k, v in unsupported.items() if v]
         if bad:
             raise NotImplementedError(f'ld_b200 ResNet implements the LD/GFL configuration only; unsupported: {bad}')
@@ -110,6 +188,9 @@ class ResNet(nn.Module):
         self.frozen_stages, self.norm_eval, self.zero_init_residual = frozen_stages, norm_eval, zero_init_residual
         block, stage_blocks = self.arch_settings[depth]
         self.block = block
+        self.dcn, self.stage_with_dcn = dcn, tuple(stage_with_dcn)
+        if dcn is not None:
+            assert len(self.stage_with_dcn) == num_stages and block is Bottleneck, 'DCN needs Bottleneck stages'
         self.conv1 = _Conv2d(3, 64, 7, 2, 3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         inplanes = 64
@@ -124,7 +205,7 @@ class ResNet(nn.Module):
                 if j == 0 and (st != 1 or inplanes != planes * block.expansion):
                     ds = nn.Sequential(_Conv2d(inplanes, planes * block.expansion, 1, st, bias=False),
                                        nn.BatchNorm2d(planes * block.expansion))
-                blocks.append(block(inplanes, planes, st, ds))
+                blocks.append(self.make_block(block, inplanes, planes, st, ds, i))
                 inplanes = planes * block.expansion
             name = f'layer{i + 1}'
             self.add_module(name, nn.Sequential(*blocks))
@@ -136,6 +217,12 @@ class ResNet(nn.Module):
                     for p in m.parameters():
                         p.requires_grad = False
         self._freeze_stages()
+
+    def make_block(self, block, inplanes, planes, stride, downsample, stage):
+        kw = {}
+        if self.dcn is not None and self.stage_with_dcn[stage]:
+            kw['dcn'] = self.dcn
+        return block(inplanes, planes, stride, downsample, **kw)
 
     def _freeze_stages(self):
         """resnet.py:572-588."""
@@ -160,6 +247,10 @@ class ResNet(nn.Module):
             elif isinstance(m, nn.BatchNorm2d):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
+        for m in self.modules():      # resnet.py:604-608: the offset branch of every DCN starts at zero
+            if isinstance(m, DeformConv2dPack):
+                nn.init.zeros_(m.conv_offset.weight)
+                nn.init.zeros_(m.conv_offset.bias)
         if self.zero_init_residual:
             for m in self.modules():
                 if isinstance(m, Bottleneck):
@@ -212,6 +303,23 @@ class ResNet(nn.Module):
             if i in self.out_indices:
                 outs.append(nchw_view(y))
         return tuple(outs)
+
+
+@BACKBONES.register_module()
+class ResNeXt(ResNet):
+    """resnext.py:109-153: ResNet with grouped 3x3 convs (groups x base_width); the teacher of BASELINE configs[3]
+    (configs/imv2/gflv2_x101_fpn_2x_coco.py: depth 101, groups 32, base_width 4, DCN in stages 3-4)."""
+    arch_settings = {50: (Bottleneck, (3, 4, 6, 3)), 101: (Bottleneck, (3, 4, 23, 3)), 152: (Bottleneck, (3, 8, 36, 3))}
+
+    def __init__(self, groups=1, base_width=4, **kwargs):
+        self.groups, self.base_width = groups, base_width
+        super().__init__(**kwargs)
+
+    def make_block(self, block, inplanes, planes, stride, downsample, stage):
+        kw = dict(groups=self.groups, base_width=self.base_width)
+        if self.dcn is not None and self.stage_with_dcn[stage]:
+            kw['dcn'] = self.dcn
+        return block(inplanes, planes, stride, downsample, **kw)
 
 
 class _ConvOnly(nn.Module):

@@ -65,14 +65,26 @@ def clear_step_cache(params=()):
             p.__dict__.pop(k, None)
 
 
-def packed_weight(w):
+def dense_from_grouped(w, groups):
+    """[Cout, Cin/groups, kh, kw] -> block-diagonal [Cout, Cin, kh, kw]: a grouped conv (ResNeXt, resnext.py:64-75) as
+    dense tensor-core tiles."""
+    co, cig, kh, kw = w.shape
+    cog = co // groups
+    d = w.new_zeros(co, cig * groups, kh, kw)
+    for g in range(groups):
+        d[g * cog:(g + 1) * cog, g * cig:(g + 1) * cig] = w[g * cog:(g + 1) * cog]
+    return d
+
+
+def packed_weight(w, groups=1):
     """[Cout,Cin,kh,kw] channels_last fp32 -> [Cout, kh*kw*Cin] bf16 (a cast, no transpose).
     Cached on the parameter (never in an id()-keyed dict: ids are reused after garbage collection)."""
     key = '_ldb_packed32' if parity() else '_ldb_packed'
     hit = getattr(w, key, None)
     if hit is None or hit[0] != w._version or hit[1].device != w.device:
-        co, ci, kh, kw = w.shape
-        w2 = w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
+        wd = w.detach() if groups == 1 else dense_from_grouped(w.detach(), groups)
+        co, ci, kh, kw = wd.shape
+        w2 = wd.permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
         hit = (w._version, ops.split_weight(w2) if parity() else w2.to(torch.bfloat16))
         setattr(w, key, hit)
     return hit[1]

@@ -103,6 +103,7 @@ _SIGS = {
     'ldb200_conv2d_wgrad_tc': (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
     'ldb200_stem_im2col': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ldb200_split_bf16': (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    'ldb200_deform_im2col': (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 14 + [C.c_void_p]),
     'ldb200_stem_tc': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7),
     'ldb200_maxpool3x3s2': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     'ldb200_gn_stats': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
@@ -161,7 +162,7 @@ def load():
 _LAUNCHES = {'ldb200_ld_targets': 3, 'ldb200_ld_loss_prepass': 1, 'ldb200_ld_loss_fused': 1,
              'ldb200_scatter_add_rows': 1, 'ldb200_gi_region': 3, 'ldb200_gi_region_v2': 3, 'ldb200_ld_loss_prepass_v2': 1,
              'ldb200_ld_loss_fused_v2': 1, 'ldb200_dgqp_forward': 1, 'ldb200_dgqp_backward': 1, 'ldb200_conv2d_tc': 1, 'ldb200_conv2d_tc_multi': 1, 'ldb200_conv2d_wgrad_tc': 1,
-             'ldb200_stem_im2col': 1, 'ldb200_split_bf16': 1, 'ldb200_stem_tc': 1, 'ldb200_maxpool3x3s2': 1, 'ldb200_gn_stats': 1, 'ldb200_gn_apply': 1,
+             'ldb200_stem_im2col': 1, 'ldb200_split_bf16': 1, 'ldb200_deform_im2col': 1, 'ldb200_stem_tc': 1, 'ldb200_maxpool3x3s2': 1, 'ldb200_gn_stats': 1, 'ldb200_gn_apply': 1,
              'ldb200_gn_relu_bwd': 2, 'ldb200_gn_apply_multi': 1, 'ldb200_gn_relu_bwd_multi': 2, 'ldb200_upsample_add_bwd': 1, 'ldb200_relu_bwd': 1, 'ldb200_colsum': 1,
              'ldb200_sgd_flat': 1, 'ldb200_sgd_flat_dev': 1, 'ldb200_bn_fold': 1, 'ldb200_bn_fold_bwd': 1, 'ldb200_mse_fwd_bwd': 1, 'ldb200_kl_dense_fwd_bwd': 1,
              'ldb200_qfl_fwd_bwd': 1, 'ldb200_dfl_fwd_bwd': 1, 'ldb200_giou_fwd_bwd': 1}

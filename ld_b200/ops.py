@@ -472,6 +472,20 @@ def stem_tc(img, weights, affines):
     return outs
 
 
+def deform_im2col(x, offset, kh=3, kw=3, stride=1, pad=1, dilation=1, deform_groups=1):
+    """Bilinear-sampled im2col of DCNv1 (ldb200_deform_im2col): x [N,H,W,C], offset [N,HO,WO,2*dg*kh*kw] f32 ->
+    [N*HO*WO, kh*kw*C] in x's dtype (tap-major, then channel: the column order of a packed 3x3 weight)."""
+    n, h, w, c = x.shape
+    _, ho, wo, off_c = offset.shape
+    assert offset.dtype == torch.float32 and offset.is_contiguous() and x.is_contiguous()
+    assert off_c == 2 * deform_groups * kh * kw
+    col = torch.empty(n * ho * wo, kh * kw * c, dtype=x.dtype, device=x.device)
+    L.check(L.load().ldb200_deform_im2col(L.ptr(x), L.ptr(offset), L.ptr(col), n, h, w, c, ho, wo, kh, kw, int(stride),
+                                          int(pad), int(dilation), int(deform_groups), off_c, _dt(x.dtype), L.stream_ptr()),
+            'ldb200_deform_im2col')
+    return col
+
+
 def maxpool3x3s2(x):
     n, h, w, c = x.shape
     out = torch.empty(n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c, dtype=x.dtype, device=x.device)

@@ -431,13 +431,21 @@ class _Bottleneck(nn.Module):
     """mmdet/models/backbones/resnet.py:95-300, style='pytorch' (stride on the 3x3)."""
     expansion = 4
 
-    def __init__(self, inp, planes, stride, downsample):
+    def __init__(self, inp, planes, stride, downsample, groups=1, base_width=4, dcn=False):
+        """groups / base_width: ResNeXt bottleneck (resnext.py:11-106); dcn: conv2 is a DeformConv2dPack
+        (resnet.py:172-184; mmcv semantics restated in oracle/mmcv_standin.py)."""
         super().__init__()
-        self.conv1 = nn.Conv2d(inp, planes, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
-        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
-        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        import math
+        width = planes if groups == 1 else math.floor(planes * (base_width / 64)) * groups
+        self.conv1 = nn.Conv2d(inp, width, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(width)
+        if dcn:
+            from .mmcv_standin import DeformConv2dPack
+            self.conv2 = DeformConv2dPack(width, width, 3, stride, 1, groups=groups, deform_groups=1)
+        else:
+            self.conv2 = nn.Conv2d(width, width, 3, stride, 1, groups=groups, bias=False)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.conv3 = nn.Conv2d(width, planes * 4, 1, bias=False)
         self.bn3 = nn.BatchNorm2d(planes * 4)
         self.downsample = downsample
 
@@ -475,7 +483,8 @@ _ARCH = {18: (_BasicBlock, (2, 2, 2, 2)), 34: (_BasicBlock, (3, 4, 6, 3)),
 class OracleResNet(nn.Module):
     """resnet.py:303-649 with frozen_stages=1, norm_eval=True (BN always eval)."""
 
-    def __init__(self, depth):
+    def __init__(self, depth, groups=1, base_width=4, stage_with_dcn=(False, False, False, False)):
+        """groups > 1: ResNeXt (resnext.py:109-153); stage_with_dcn: DCN 3x3 convs in those stages."""
         super().__init__()
         block, layers = _ARCH[depth]
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
@@ -491,7 +500,8 @@ class OracleResNet(nn.Module):
                 if j == 0 and (st != 1 or inp != planes * block.expansion):
                     ds = nn.Sequential(nn.Conv2d(inp, planes * block.expansion, 1, st, bias=False),
                                        nn.BatchNorm2d(planes * block.expansion))
-                blocks.append(block(inp, planes, st, ds))
+                kw = dict(groups=groups, base_width=base_width, dcn=stage_with_dcn[i]) if block is _Bottleneck else {}
+                blocks.append(block(inp, planes, st, ds, **kw))
                 inp = planes * block.expansion
             setattr(self, f'layer{i + 1}', nn.Sequential(*blocks))
         self.out_channels = [64 * 2 ** i * block.expansion for i in range(4)]

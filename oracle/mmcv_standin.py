@@ -168,9 +168,38 @@ def bias_init_with_prob(prior_prob):
 
 
 # --------------------------------------------------------------------------- layers
+class DeformConv2dPack(nn.Module):
+    """mmcv.ops.DeformConv2dPack (conv type 'DCN', mmcv 1.2.x deform_conv.py) restated on torchvision.ops.deform_conv2d,
+    which shares mmcv's offset layout (channel 2k = dy, 2k+1 = dx of kernel point k, per deformable group) and sampling
+    rule (zero outside (-1, H) x (-1, W)).  Parameters: `weight`, `conv_offset.{weight,bias}` (zero-initialised).  mmcv's
+    own kernel is not available here: parity for DCN is pinned to this restatement only."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deform_groups=1, bias=False, **kw):
+        super().__init__()
+        assert not bias
+        import math
+        self.stride, self.padding, self.dilation, self.groups, self.deform_groups = stride, padding, dilation, groups, \
+            deform_groups
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels // groups, kernel_size, kernel_size))
+        n = in_channels * kernel_size * kernel_size
+        nn.init.uniform_(self.weight, -1.0 / math.sqrt(n), 1.0 / math.sqrt(n))
+        self.conv_offset = nn.Conv2d(in_channels, deform_groups * 2 * kernel_size * kernel_size, kernel_size, stride,
+                                     padding, dilation=dilation, bias=True)
+        nn.init.zeros_(self.conv_offset.weight)
+        nn.init.zeros_(self.conv_offset.bias)
+
+    def forward(self, x):
+        from torchvision.ops import deform_conv2d
+        return deform_conv2d(x, self.conv_offset(x), self.weight, None, self.stride, self.padding, self.dilation)
+
+
 def build_conv_layer(cfg, *args, **kwargs):
     if cfg is None or cfg.get('type', 'Conv2d') in ('Conv2d', 'Conv'):
         return nn.Conv2d(*args, **kwargs)
+    if cfg.get('type') == 'DCN':
+        extra = {k: v for k, v in cfg.items() if k != 'type'}
+        return DeformConv2dPack(*args, **kwargs, **extra)
     raise NotImplementedError(f'conv type {cfg} not available in the mmcv stand-in')
 
 

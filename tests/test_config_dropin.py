@@ -147,3 +147,42 @@ def test_train_step_schedule_and_state_dict():
     ts2.load_state_dict(sd)
     assert ts2.iter == 1234 and ts2.base_lr == 0.01 and torch.equal(ts2.flat_m, sd['momentum_buffer'])
     assert ts2.lr_at(9 * 7330) == ts.lr_at(9 * 7330)
+
+
+def test_x101_dcn_teacher_builds_with_reference_keys_and_oracle_matches_reference():
+    """BASELINE configs[3] teacher (configs/imv2/gflv2_x101_fpn_2x_coco.py: ResNeXt-101 32x4d, DCN in stages 3-4,
+    GFocalHead): the registry builds it from the reference's own file with the reference's state-dict keys, and the
+    oracle's ResNeXt/DCN port reproduces the UNMODIFIED reference backbone (run through the mmcv stand-in, whose
+    DeformConv2dPack restates mmcv on torchvision.ops.deform_conv2d) on a seeded input."""
+    import os
+    import pytest
+    import torch
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip('needs /root/reference')
+    import ld_b200
+    from ld_b200 import synth
+    from ld_b200.config import Config, ConfigDict
+    from oracle import ld_oracle as lo, mmcv_standin
+    cfg = Config.fromfile(os.path.join(rh.REF_ROOT, 'configs/imv2/gflv2_x101_fpn_2x_coco.py'))
+    mine = ld_b200.build_detector(ConfigDict(cfg.model.to_dict()))
+    mmcv_standin.import_reference(rh.REF_ROOT)
+    from mmdet.models import build_backbone
+    bcfg = cfg.model.backbone.to_dict()
+    ref_bb = build_backbone(dict(bcfg))
+    ref_keys = sorted('backbone.' + k for k in ref_bb.state_dict())
+    assert sorted(k for k in mine.state_dict() if k.startswith('backbone.')) == ref_keys
+    # a shallower variant of the same family for the numeric check (depth 50, same groups / DCN stages)
+    bcfg.update(depth=50)
+    ref50 = build_backbone(dict(bcfg))
+    ref50.eval()                     # (the reference's ResNet.train() does not return self)
+    ora50 = lo.OracleResNet(50, groups=32, base_width=4, stage_with_dcn=(False, False, True, True))
+    ora50.eval()
+    synth.seeded_init(ref50, 7)
+    synth.seeded_init(ora50, 7)
+    assert sorted(ref50.state_dict()) == sorted(ora50.state_dict())
+    x = torch.randn(1, 3, 96, 128, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        a, b = ref50(x), ora50(x)
+    for u, v in zip(a, b):
+        assert torch.allclose(u, v, rtol=1e-5, atol=1e-6)
