@@ -131,6 +131,8 @@ def main():
                     help='fix the global batch (strong scaling); default: 16 images per GPU (weak scaling)')
     ap.add_argument('--per-gpu-batch', type=int, default=0, help='images per GPU (BASELINE configs[1]: --student r18 --per-gpu-batch 8)')
     ap.add_argument('--main-ld-only', action='store_true', help='BASELINE configs[2]: VLR / KD / IM loss weights 0')
+    ap.add_argument('--ldv2', action='store_true',
+                    help='BASELINE configs[3]: LDv2Head R50 student + GFocalHead X101-32x4d-DCN teacher (VLR + IMLoss)')
     ap.add_argument('--no-parity', action='store_true', help='skip the fp32-accurate mode side measurement')
     ap.add_argument('--no-micro', action='store_true', help='skip the micro records (LD-KL dense kernel)')
     args = ap.parse_args()
@@ -142,6 +144,7 @@ def main():
                   global_batch=args.global_batch or (args.per_gpu_batch or GLOBAL_BATCH) * args.gpus,
                   per_gpu_batch=(args.global_batch or (args.per_gpu_batch or GLOBAL_BATCH) * args.gpus) // args.gpus,
                   student=args.student, losses='main LD only' if args.main_ld_only else 'LD + VLR-LD + KD + IM (ld_r50 config)',
+                  head='LDv2Head <- GFocalHead X101-32x4d-DCN teacher (BASELINE configs[3])' if args.ldv2 else 'LDHead <- GFLHead R101 teacher',
                   image=[H, W], parallelism=f'dp{args.gpus}',
                   launch='CUDA graph replay' if not args.no_graph else 'eager',
                   timing='inputs (51.6 MB images + activations >> 126 MB L2) exceed L2; no explicit flush',
@@ -185,7 +188,10 @@ def main():
     scaling = 'strong' if args.global_batch else 'weak'
     assert global_batch % world == 0
 
-    model = ld_b200.build_detector(ConfigDict(presets.ld_model(args.student, main_ld_only=args.main_ld_only)))
+    if args.ldv2:
+        model = ld_b200.build_detector(ConfigDict(presets.ldv2_model(args.student)))
+    else:
+        model = ld_b200.build_detector(ConfigDict(presets.ld_model(args.student, main_ld_only=args.main_ld_only)))
     synth.seeded_init(model, 0)
     synth.seeded_init(model.teacher_model, 1, prefix='teacher.')
     model = model.to(dev).train()

@@ -58,3 +58,25 @@ def ld_model(student='r50', teacher_depth=101, main_ld_only=False):
                 teacher_config=dict(model=gfl_model(teacher_depth)), teacher_ckpt=None, output_feature=True,
                 backbone=_backbone(depth), neck=_neck(depth), bbox_head=head,
                 train_cfg=copy.deepcopy(_TRAIN), test_cfg=copy.deepcopy(_TEST))
+
+
+def ldv2_model(student='r50', teacher='x101dcn'):
+    """BASELINE.json configs[3]: "LDv2 R50 / X101-DCN teacher with VLR + IMLoss(finegrain)" -- no such file ships with
+    the reference; composed as SURVEY.md 8d prescribes from configs/ldv2/ld_r50_gflv2_r101_fpn_1x.py (LDv2Head student:
+    reg_topk 4, reg_channels 64, add_mean, QFL on joint scores) with configs/imv2/gflv2_x101_fpn_2x_coco.py as teacher
+    (GFocalHead on ResNeXt-101 32x4d, DCN in stages 3-4), loss_ld_vlr + IMLoss(2.0), imitation_method='finegrained'."""
+    m = ld_model(student)
+    v2 = dict(reg_topk=4, reg_channels=64, add_mean=True,
+              loss_cls=dict(type='QualityFocalLoss', use_sigmoid=False, beta=2.0, loss_weight=1.0))
+    m['bbox_head'].update(type='LDv2Head', imitation_method='finegrained', loss_im=dict(type='IMLoss', loss_weight=2.0), **v2)
+    t = m['teacher_config']['model']
+    t['bbox_head'].update(type='GFocalHead', **copy.deepcopy(v2))
+    if teacher == 'x101dcn':
+        t['pretrained'] = 'open-mmlab://resnext101_32x4d'
+        t['backbone'] = dict(type='ResNeXt', depth=101, groups=32, base_width=4, num_stages=4, out_indices=(0, 1, 2, 3),
+                             frozen_stages=1, norm_cfg=dict(type='BN', requires_grad=True),
+                             dcn=dict(type='DCN', deform_groups=1, fallback_on_stride=False),
+                             stage_with_dcn=(False, False, True, True), norm_eval=True, style='pytorch')
+    elif teacher != 'r101':
+        raise KeyError(teacher)
+    return m

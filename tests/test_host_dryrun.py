@@ -196,3 +196,15 @@ def test_overlapped_gradient_exchange_covers_flat_buffer_once(fake_backend, monk
     first = [s for i, s in enumerate(order) if s not in order[:i]]
     assert first == ['bbox_head.', 'neck.', 'backbone.layer4.', 'backbone.layer3.'], first
     assert len(spans) == 5                         # + the remainder (layer2) after the backward pass
+
+
+def test_ldv2_x101_dcn_teacher_host_logic(fake_backend):
+    """BASELINE configs[3] structure: LDv2Head student, GFocalHead teacher on ResNeXt-101 32x4d with DCN in stages 3-4
+    (grouped convs as dense block-diagonal launches, DCN = offset conv + deform_im2col + GEMM), forward-only teacher."""
+    m = ld_b200.build_detector(ConfigDict(presets.ldv2_model('r18'))).train()
+    loss, _ = m._parse_losses(m(**_batch()))
+    loss.backward()
+    _check_grads(m)
+    # 23 + 3 DCN bottlenecks in stages 3-4 of the X101 teacher
+    assert fake_backend.count('ldb200_deform_im2col') == 26
+    assert fake_backend.count('ldb200_ld_loss_fused_v2') == 1
