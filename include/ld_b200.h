@@ -220,6 +220,20 @@ int ldb200_kl_dense_fwd_bwd(const float* student, const float* teacher, const fl
                             int64_t rows, int bins, float T, float loss_weight, float avg_factor,
                             float grad_out, float* loss, float* d_student, void* stream);
 
+/* Inference step after the path: GFLHead._get_bboxes (gfl_head.py:354-451) + multiclass_nms with
+ * nms type 'nms' (core/post_processing/bbox_nms.py:70-193 -> mmcv.ops.batched_nms) for a whole batch, on row-space
+ * head outputs: per level the nms_pre anchors of highest max_c sigmoid(cls) (exact top-k), Integral * stride,
+ * distance2bbox clipped to img_hw (divided by scale_factors when given), score threshold, per-class greedy NMS on
+ * mmcv's class-offset boxes, the first max_per_img survivors by score.
+ *   cls [R, num_classes], bbox_pred [R, 4*bins] f32; img_hw [N,2] i32 (h, w); scale_factors [N,4] f32 or NULL;
+ *   dets [N, max_per_img, 5] (x1,y1,x2,y2,score), labels [N, max_per_img] i32, counts [N] i32 (number of detections;
+ *   -1 = more than 16384 (box, class) pairs above score_thr in that image: raise score_thr or lower nms_pre). */
+size_t ldb200_get_bboxes_workspace_bytes(const ldb_pyramid* pyr, int num_classes, int nms_pre);
+int ldb200_gfl_get_bboxes(const ldb_pyramid* pyr, const float* cls, const float* bbox_pred, int num_classes, int bins,
+                          int use_sigmoid /* 1: cls = logits (GFLHead); 0: probabilities (GFocalHead joint scores) */,
+                          const int32_t* img_hw, const float* scale_factors, int nms_pre, float score_thr, float iou_thr,
+                          int max_per_img, float* dets, int32_t* labels, int32_t* counts, void* workspace, void* stream);
+
 /* Stand-alone loss modules of the registry surface (`build_loss(cfg)(pred, target, weight, avg_factor, ...)` outside
  * LDHead): forward value and d/d pred in one launch, fp32.  row_loss (optional, [rows]) receives scale * w_r * l_r for
  * reduction='none'; loss (optional, f32[1], ACCUMULATED) += scale * sum_r w_r * l_r; d_pred (optional) = scale * w_r *

@@ -189,6 +189,9 @@ class GFLHead(nn.Module):
         return (torch.empty(R, self.cls_out_channels, dtype=torch.float32, device=dev),
                 torch.empty(R, 4 * (self.reg_max + 1), dtype=torch.float32, device=dev), sizes)
 
+    def get_bboxes(self, cls_scores, bbox_preds, img_metas, cfg=None, rescale=False, with_nms=True):
+        return _get_bboxes(self, cls_scores, bbox_preds, img_metas, cfg, rescale, with_nms)
+
     def forward(self, feats):
         """gfl_head.py:145-159: -> (cls_scores, bbox_preds), lists of NCHW-shaped fp32 level tensors.
         Inference-style forward (no autograd through the two output convs); training goes through
@@ -198,6 +201,35 @@ class GFLHead(nn.Module):
             self.final_convs(self.towers(feats), cls_rows, reg_rows)
         pyr = L.Pyramid.make(feats[0].shape[0], sizes, [s[0] for s in self.anchor_generator.strides])
         return ops.from_rows(cls_rows, pyr), ops.from_rows(reg_rows, pyr)
+
+
+def _get_bboxes(head, cls_scores, bbox_preds, img_metas, cfg=None, rescale=False, with_nms=True):
+    """`AnchorHead.get_bboxes` -> `GFLHead._get_bboxes` (anchor_head.py:518-600, gfl_head.py:354-451) for the whole batch
+    in four launches (ldb200_gfl_get_bboxes): -> list of (det_bboxes [k, 5], det_labels [k]) per image."""
+    cfg = head.test_cfg if cfg is None else cfg
+    if not with_nms:
+        raise NotImplementedError('with_nms=False (only used by aug-test merging, outside the LD path)')
+    nms = cfg.get('nms', dict(type='nms', iou_threshold=0.6)) if hasattr(cfg, 'get') else cfg['nms']
+    if nms.get('type', 'nms') != 'nms':
+        raise NotImplementedError(f"nms type {nms.get('type')!r}: the kernel implements type='nms' (every GFL / LD test_cfg); "
+                                  f"'voting_cluster_diounms' (bbox_nms.py:148-181) is not built")
+    n = cls_scores[0].shape[0]
+    sizes = [tuple(c.shape[2:]) for c in cls_scores]
+    pyr = L.Pyramid.make(n, sizes, [s[0] for s in head.anchor_generator.strides])
+    cls_rows = rows_of([c.detach().float() for c in cls_scores]).contiguous()
+    reg_rows = rows_of([b.detach().float() for b in bbox_preds]).contiguous()
+    img_hw = [m['img_shape'][:2] for m in img_metas]
+    sf = None
+    if rescale:
+        import numpy as np
+        sf = [np.broadcast_to(np.asarray(m['scale_factor'], dtype=np.float32), (4,)) for m in img_metas]
+    dets, labels, counts = ops.gfl_get_bboxes(pyr, cls_rows, reg_rows, img_hw, sf, nms_pre=cfg.get('nms_pre', -1),
+                                              score_thr=cfg['score_thr'], iou_thr=nms['iou_threshold'],
+                                              max_per_img=cfg['max_per_img'], use_sigmoid=head.use_sigmoid_cls)
+    counts = counts.cpu()
+    if bool((counts < 0).any()):
+        raise RuntimeError('ldb200_gfl_get_bboxes: more than 16384 (box, class) pairs above score_thr in one image')
+    return [(dets[i, :int(counts[i])], labels[i, :int(counts[i])].long()) for i in range(n)]
 
 
 # region mask produced by the target pass; 'gibox' rows come from `ops.gi_region` at loss time instead (the mask

@@ -81,7 +81,15 @@ class BaseDetector(nn.Module):
     def forward(self, img, img_metas, return_loss=True, **kwargs):
         if return_loss:
             return self.forward_train(img, img_metas, **kwargs)
-        raise NotImplementedError('inference (forward_test / simple_test) is outside the LD train path')
+        return self.forward_test(img, img_metas, **kwargs)
+
+    def forward_test(self, imgs, img_metas, **kwargs):
+        """base.py:121-167: lists of images / metas (one entry per test-time augmentation)."""
+        if isinstance(imgs, torch.Tensor):
+            imgs, img_metas = [imgs], [img_metas]
+        if len(imgs) != 1:
+            raise NotImplementedError('aug_test (multi-scale / flip test-time augmentation) is outside the LD path')
+        return self.simple_test(imgs[0], img_metas[0], **kwargs)
 
     def _parse_losses(self, losses):
         """base.py:185-218: loss = sum over keys containing 'loss' of the per-level sums; one device->host
@@ -139,6 +147,21 @@ class SingleStageDetector(BaseDetector):
         self.bbox_head.init_weights()
         if isinstance(pretrained, str):
             load_checkpoint_into(self.backbone, pretrained, f'{type(self).__name__}.backbone pretrained')
+
+    def simple_test(self, img, img_metas, rescale=False):
+        """single_stage.py:96-121: backbone + neck + head forward, `get_bboxes` (top-k, decode, NMS on the GPU),
+        `bbox2result` (core/bbox/transforms.py:92-116): per image a list of num_classes numpy arrays [k, 5]."""
+        with torch.no_grad():
+            x = self.extract_feat(img)
+            head = self.bbox_head
+            outs = head(x, with_scores=True) if hasattr(head, 'reg_conf') else head(x)   # GFocalHead: joint scores
+            bbox_list = head.get_bboxes(outs[0], outs[1], img_metas, rescale=rescale)
+        nc = self.bbox_head.num_classes
+        results = []
+        for det, lab in bbox_list:
+            det, lab = det.cpu().numpy(), lab.cpu().numpy()
+            results.append([det[lab == c] for c in range(nc)])
+        return results
 
     def extract_feat(self, img, im2col=None, stem_out=None):
         x = self.backbone(img, im2col=im2col) if stem_out is None else self.backbone(img, stem_out=stem_out)

@@ -273,6 +273,27 @@ def gi_region_v2(cfg: L.LossCfg, score, reg, t_cls_feat, t_reg, tg: LDTargets, i
     return gi_rows, counts
 
 
+def gfl_get_bboxes(pyr: L.Pyramid, cls_rows, reg_rows, img_hw, scale_factors=None, nms_pre=1000, score_thr=0.05,
+                   iou_thr=0.6, max_per_img=100, use_sigmoid=True):
+    """ldb200_gfl_get_bboxes: -> (dets [N, max_per_img, 5] f32, labels [N, max_per_img] i32, counts [N] i32)."""
+    lib = L.load()
+    dev = cls_rows.device
+    n = pyr.num_imgs
+    C_, bins = cls_rows.shape[1], reg_rows.shape[1] // 4
+    assert cls_rows.dtype == reg_rows.dtype == torch.float32 and cls_rows.is_contiguous() and reg_rows.is_contiguous()
+    hw = torch.tensor([[int(s[0]), int(s[1])] for s in img_hw], dtype=torch.int32).to(dev)
+    sf = None if scale_factors is None else torch.tensor([list(map(float, f)) for f in scale_factors],
+                                                         dtype=torch.float32).to(dev)
+    ws = torch.empty(int(lib.ldb200_get_bboxes_workspace_bytes(C.byref(pyr), C_, int(nms_pre))), dtype=torch.uint8, device=dev)
+    dets = torch.empty(n, max_per_img, 5, dtype=torch.float32, device=dev)
+    labels = torch.empty(n, max_per_img, dtype=torch.int32, device=dev)
+    counts = torch.empty(n, dtype=torch.int32, device=dev)
+    L.check(lib.ldb200_gfl_get_bboxes(C.byref(pyr), L.ptr(cls_rows), L.ptr(reg_rows), C_, bins, int(use_sigmoid), L.ptr(hw), L.ptr(sf),
+                                      int(nms_pre), float(score_thr), float(iou_thr), int(max_per_img), L.ptr(dets),
+                                      L.ptr(labels), L.ptr(counts), L.ptr(ws), L.stream_ptr()), 'ldb200_gfl_get_bboxes')
+    return dets, labels, counts
+
+
 def scatter_add_rows(dst, src, rows, n_rows_dev, max_rows=None):
     lib = L.load()
     max_rows = src.shape[0] if max_rows is None else max_rows

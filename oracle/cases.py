@@ -126,3 +126,20 @@ def loss_module_inputs(rows, seed, num_classes=80, reg_max=16):
     d['box_target'] = torch.cat([xy, xy + wh], 1)
     d['box_pred'] = d['box_target'] + torch.randn(rows, 4, generator=g) * 6     # some pairs end up disjoint / inverted
     return d
+
+
+# Inference: `GFLHead.get_bboxes` on seeded head outputs.  (name, N, H, W, seed, rescale).  The class
+# logits are as sparse as a trained detector's (about 0.5 % of the scores pass score_thr = 0.05).
+INFER_CASES = [('i_256x320_s61', 2, 256, 320, 61, False), ('i_800x1344_s62', 2, 800, 1344, 62, True)]
+
+
+def infer_case_inputs(n, h, w, seed, num_classes=80, reg_ch=68):
+    g = torch.Generator().manual_seed(seed)
+    sizes = featmap_sizes(h, w)
+    cls = [torch.randn(n, num_classes, fh, fw, generator=g) * 1.2 - 6.0 for fh, fw in sizes]
+    reg = [torch.randn(n, reg_ch, fh, fw, generator=g) * 1.5 for fh, fw in sizes]
+    metas = synth.make_img_metas(n, h, w)
+    for i, m in enumerate(metas):     # content smaller than the padded tensor, and a non-trivial rescale factor
+        m['img_shape'] = (h - 8 * i - 3, w - 5 * i - 2, 3)
+        m['scale_factor'] = [1.25 + 0.1 * i, 1.5, 1.25 + 0.1 * i, 1.5]
+    return dict(cls=cls, reg=reg, img_metas=metas, sizes=sizes)

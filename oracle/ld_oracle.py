@@ -426,6 +426,48 @@ def parse_losses(losses):
     return total, {k: float(v.detach()) for k, v in log.items()}
 
 
+# =========================================================================== inference
+def get_bboxes(cls_scores, bbox_preds, strides, img_shapes, scale_factors=None, nms_pre=1000, score_thr=0.05,
+               iou_thr=0.6, max_per_img=100, reg_max=16):
+    """`GFLHead._get_bboxes` (gfl_head.py:354-451) + `multiclass_nms` type 'nms' (bbox_nms.py:70-193): per-level top
+    nms_pre anchors by max class score, Integral * stride, distance2bbox clipped to the image, score threshold, per-class
+    NMS through mmcv's coordinate-offset trick, top max_per_img.  -> list of (dets [k,5], labels [k]) per image."""
+    from .mmcv_standin import batched_nms
+    n = cls_scores[0].shape[0]
+    out = []
+    for i in range(n):
+        boxes_l, scores_l = [], []
+        for cls, reg, st in zip(cls_scores, bbox_preds, strides):
+            h, w = cls.shape[2:]
+            sc = cls[i].permute(1, 2, 0).reshape(h * w, -1).sigmoid()
+            d = integral(reg[i].permute(1, 2, 0).reshape(h * w, -1), reg_max) * st
+            anchors = level_anchors(h, w, st)
+            if nms_pre > 0 and sc.shape[0] > nms_pre:
+                top = sc.max(-1)[0].topk(nms_pre)[1]
+                sc, d, anchors = sc[top], d[top], anchors[top]
+            cx, cy = (anchors[:, 0] + anchors[:, 2]) / 2, (anchors[:, 1] + anchors[:, 3]) / 2
+            b = torch.stack([cx - d[:, 0], cy - d[:, 1], cx + d[:, 2], cy + d[:, 3]], -1)
+            ih, iw = img_shapes[i][:2]
+            b = torch.stack([b[:, 0].clamp(0, iw), b[:, 1].clamp(0, ih), b[:, 2].clamp(0, iw), b[:, 3].clamp(0, ih)], -1)
+            boxes_l.append(b)
+            scores_l.append(sc)
+        boxes, scores = torch.cat(boxes_l), torch.cat(scores_l)
+        if scale_factors is not None:
+            boxes = boxes / boxes.new_tensor(scale_factors[i])
+        C = scores.shape[1]
+        bb = boxes[:, None].expand(-1, C, 4).reshape(-1, 4)
+        ss = scores.reshape(-1)
+        ll = torch.arange(C).view(1, -1).expand_as(scores).reshape(-1)
+        valid = (ss > score_thr).nonzero(as_tuple=False).squeeze(1)
+        bb, ss, ll = bb[valid], ss[valid], ll[valid]
+        if bb.numel() == 0:
+            out.append((boxes.new_zeros(0, 5), ll.new_zeros(0)))
+            continue
+        dets, keep = batched_nms(bb, ss, ll, dict(type='nms', iou_threshold=iou_thr))
+        out.append((dets[:max_per_img], ll[keep][:max_per_img]))
+    return out
+
+
 # =========================================================================== network port
 class _Bottleneck(nn.Module):
     """mmdet/models/backbones/resnet.py:95-300, style='pytorch' (stride on the 3x3)."""

@@ -286,12 +286,30 @@ def gen_loss_modules():
         print(name, {k: float(v['out'].sum()) for k, v in list(gold.items())[:4]})
 
 
+def gen_infer():
+    """`GFLHead.get_bboxes` of the unmodified reference head (anchor_head.py:518-600 -> gfl_head.py:354-451 ->
+    bbox_nms.py:70-193; mmcv's batched_nms comes from the stand-in) on cases.INFER_CASES."""
+    import numpy as np
+    head = rh.reference_head()
+    head.eval()
+    for name, n, h, w, seed, rescale in cases.INFER_CASES:
+        d = cases.infer_case_inputs(n, h, w, seed)
+        metas = [dict(m, scale_factor=np.asarray(m['scale_factor'], dtype=np.float32)) for m in d['img_metas']]
+        with torch.no_grad():
+            res = head.get_bboxes(d['cls'], d['reg'], metas, rescale=rescale)
+        torch.save(dict(dets=[r[0].clone() for r in res], labels=[r[1].clone() for r in res]), os.path.join(OUT, name + '.pt'))
+        print(name, [tuple(r[0].shape) for r in res], [float(r[0][:, 4].max()) for r in res])
+
+
 def main():
     if not rh.reference_available():
         sys.exit('needs /root/reference (build container only)')
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
+    if '--infer' in sys.argv:
+        gen_infer()
+        return
     if '--loss-modules' in sys.argv:
         gen_loss_modules()
         return

@@ -339,6 +339,36 @@ class _PermissiveModule(types.ModuleType):
         return val
 
 
+def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
+    """mmcv.ops.batched_nms (mmcv 1.2.x ops/nms.py:229-292) restated: per-class NMS through the coordinate-offset trick
+    (boxes + class * (max coordinate + 1)), greedy IoU > threshold suppression (torchvision.ops.nms has the same rule),
+    results sorted by score.  Above `split_thr` boxes mmcv loops over the classes instead; both give the same keep set."""
+    from torchvision.ops import nms as tv_nms
+    nms_cfg_ = dict(nms_cfg)
+    class_agnostic = nms_cfg_.pop('class_agnostic', class_agnostic)
+    assert nms_cfg_.pop('type', 'nms') == 'nms'
+    split_thr = nms_cfg_.pop('split_thr', 10000)
+    thr = nms_cfg_['iou_threshold']
+    if class_agnostic:
+        boxes_for_nms = boxes
+    else:
+        max_coordinate = boxes.max()
+        offsets = idxs.to(boxes) * (max_coordinate + torch.tensor(1).to(boxes))
+        boxes_for_nms = boxes + offsets[:, None]
+    if len(boxes_for_nms) < split_thr:
+        keep = tv_nms(boxes_for_nms, scores, thr)
+        boxes, scores = boxes[keep], scores[keep]
+    else:
+        total_mask = scores.new_zeros(scores.size(), dtype=torch.bool)
+        for cid in torch.unique(idxs):
+            mask = (idxs == cid).nonzero(as_tuple=False).view(-1)
+            total_mask[mask[tv_nms(boxes_for_nms[mask], scores[mask], thr)]] = True
+        keep = total_mask.nonzero(as_tuple=False).view(-1)
+        keep = keep[scores[keep].argsort(descending=True)]
+        boxes, scores = boxes[keep], scores[keep]
+    return torch.cat([boxes, scores[:, None]], -1), keep
+
+
 def _mod(name, permissive=True, **attrs):
     m = (_PermissiveModule if permissive else types.ModuleType)(name)
     m.__dict__.update(attrs)
@@ -380,6 +410,8 @@ def install():
     mmcv.ops = _mod('mmcv.ops')
     for sub in ('nms', 'roi_align', 'carafe', 'merge_cells'):
         setattr(mmcv.ops, sub, _mod('mmcv.ops.' + sub))
+    mmcv.ops.nms.batched_nms = batched_nms
+    mmcv.ops.batched_nms = batched_nms
     mmcv.parallel = _mod('mmcv.parallel')
     mmcv.image = _mod('mmcv.image')
 

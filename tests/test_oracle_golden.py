@@ -192,3 +192,17 @@ def test_reference_known_answers():
     assert torch.allclose(lo.aligned_overlaps(b1, b2, 'giou'), torch.tensor([.5, -.05, -.8214]), atol=1e-4)
     d = torch.diagonal(lo.pair_overlaps(b1, b2, 'diou'))
     assert torch.allclose(d, torch.tensor([.95, -.2005, -.4889]), atol=1e-4)       # IoF-based quirk
+
+
+@pytest.mark.parametrize('case', cases.INFER_CASES, ids=lambda c: c[0])
+def test_get_bboxes(golden_dir, case):
+    """Inference restatement (`lo.get_bboxes`: top-k, Integral, distance2bbox + clip, score threshold, class-offset NMS)
+    against `GFLHead.get_bboxes` of the unmodified reference (gfl_head.py:354-451, bbox_nms.py:70-193)."""
+    name, n, h, w, seed, rescale = case
+    gold = _load(golden_dir, name)
+    d = cases.infer_case_inputs(n, h, w, seed)
+    res = lo.get_bboxes(d['cls'], d['reg'], cases.STRIDES, [m['img_shape'] for m in d['img_metas']],
+                        [m['scale_factor'] for m in d['img_metas']] if rescale else None)
+    for (det, lab), gd, gl in zip(res, gold['dets'], gold['labels']):
+        assert torch.equal(lab, gl)
+        assert torch.allclose(det, gd, rtol=1e-5, atol=1e-4)
