@@ -220,6 +220,21 @@ int ldb200_kl_dense_fwd_bwd(const float* student, const float* teacher, const fl
                             int64_t rows, int bins, float T, float loss_weight, float avg_factor,
                             float grad_out, float* loss, float* d_student, void* stream);
 
+/* Input side: Resize(keep_ratio, cv2 INTER_LINEAR) -> RandomFlip -> Normalize(mean, std, to_rgb) ->
+ * Pad(size_divisor) -> collate of the reference's train pipeline (mmdet/datasets/pipelines/transforms.py:26-600) for a
+ * batch in one launch, bit-identical to the cv2 / numpy arithmetic of mmcv.imrescale / imflip / imnormalize / impad.
+ * src_u8: the decoded uint8 HWC (BGR) images packed in one device buffer; imgs: device array of N descriptors
+ * (source and resized sizes are computed by the host: mmcv.rescale_size); out [N, 3, Hp, Wp] f32, zero outside the
+ * resized image; mean3 / std3: HOST float[3] in the OUTPUT channel order (RGB when to_rgb). */
+typedef struct {
+  long long src_off;   /* byte offset of the image inside src_u8 */
+  int sh, sw;          /* source size */
+  int dh, dw;          /* size after Resize */
+  int flip;            /* 1: horizontal flip */
+} ldb_prep_image;
+int ldb200_preprocess_batch(const void* src_u8, const ldb_prep_image* imgs, int N, float* out, int Hp, int Wp,
+                            const float* mean3, const float* std3, int to_rgb, void* stream);
+
 /* Inference step after the path: GFLHead._get_bboxes (gfl_head.py:354-451) + multiclass_nms with
  * nms type 'nms' (core/post_processing/bbox_nms.py:70-193 -> mmcv.ops.batched_nms) for a whole batch, on row-space
  * head outputs: per level the nms_pre anchors of highest max_c sigmoid(cls) (exact top-k), Integral * stride,

@@ -66,6 +66,11 @@ class GnSeg(C.Structure):
                 ('red_ws', C.c_void_p), ('red_zeroed', C.c_int), ('N', C.c_int), ('HW', C.c_int)]
 
 
+class PrepImage(C.Structure):
+    _fields_ = [('src_off', C.c_longlong), ('sh', C.c_int), ('sw', C.c_int), ('dh', C.c_int), ('dw', C.c_int),
+                ('flip', C.c_int)]
+
+
 class WgradDesc(C.Structure):
     _fields_ = [('dy', C.c_void_p), ('N', C.c_int), ('HO', C.c_int), ('WO', C.c_int), ('Cout', C.c_int),
                 ('dy_ld', C.c_int), ('x', C.c_void_p), ('H', C.c_int), ('W', C.c_int), ('Cin', C.c_int),
@@ -121,6 +126,8 @@ _SIGS = {
     'ldb200_bn_fold': (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'ldb200_bn_fold_bwd': (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'ldb200_mse_fwd_bwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'ldb200_preprocess_batch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                          C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_void_p]),
     'ldb200_get_bboxes_workspace_bytes': (C.c_size_t, [C.POINTER(Pyramid), C.c_int, C.c_int]),
     'ldb200_gfl_get_bboxes': (C.c_int, [C.POINTER(Pyramid), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int] + [C.c_void_p] * 5),
@@ -168,7 +175,7 @@ _LAUNCHES = {'ldb200_ld_targets': 3, 'ldb200_ld_loss_prepass': 1, 'ldb200_ld_los
              'ldb200_stem_im2col': 1, 'ldb200_split_bf16': 1, 'ldb200_deform_im2col': 1, 'ldb200_stem_tc': 1, 'ldb200_maxpool3x3s2': 1, 'ldb200_gn_stats': 1, 'ldb200_gn_apply': 1,
              'ldb200_gn_relu_bwd': 2, 'ldb200_gn_apply_multi': 1, 'ldb200_gn_relu_bwd_multi': 2, 'ldb200_upsample_add_bwd': 1, 'ldb200_relu_bwd': 1, 'ldb200_colsum': 1,
              'ldb200_sgd_flat': 1, 'ldb200_sgd_flat_dev': 1, 'ldb200_bn_fold': 1, 'ldb200_bn_fold_bwd': 1, 'ldb200_mse_fwd_bwd': 1, 'ldb200_kl_dense_fwd_bwd': 1,
-             'ldb200_gfl_get_bboxes': 4, 'ldb200_qfl_fwd_bwd': 1, 'ldb200_dfl_fwd_bwd': 1, 'ldb200_giou_fwd_bwd': 1}
+             'ldb200_gfl_get_bboxes': 4, 'ldb200_preprocess_batch': 1, 'ldb200_qfl_fwd_bwd': 1, 'ldb200_dfl_fwd_bwd': 1, 'ldb200_giou_fwd_bwd': 1}
 launch_count = {'n': 0}
 
 

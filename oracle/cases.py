@@ -143,3 +143,8 @@ def infer_case_inputs(n, h, w, seed, num_classes=80, reg_ch=68):
         m['img_shape'] = (h - 8 * i - 3, w - 5 * i - 2, 3)
         m['scale_factor'] = [1.25 + 0.1 * i, 1.5, 1.25 + 0.1 * i, 1.5]
     return dict(cls=cls, reg=reg, img_metas=metas, sizes=sizes)
+
+
+# Input pipeline: (name, [(h, w), ...] source sizes, seed, flips, img_scale)
+PIPELINE_CASES = [('p_small_s71', [(120, 160), (97, 141), (160, 101)], 71, [True, False, True], (333, 200)),
+                  ('p_coco_s72', [(427, 640), (480, 640)], 72, [False, True], (1333, 800))]

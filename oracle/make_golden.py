@@ -10,6 +10,7 @@ TEST INFRASTRUCTURE ONLY.
 import os
 import sys
 
+import numpy as np
 import torch
 
 from ld_b200 import synth
@@ -301,12 +302,44 @@ def gen_infer():
         print(name, [tuple(r[0].shape) for r in res], [float(r[0][:, 4].max()) for r in res])
 
 
+def gen_pipeline():
+    """The reference's own transform CLASSES (Resize / RandomFlip / Normalize / Pad, transforms.py) run through the
+    stand-in's cv2-backed mmcv functions on cases.PIPELINE_CASES; a sha256 of every output image (bit-exactness
+    fingerprint), a strided sample of it, the transformed boxes and the meta keys are kept."""
+    import hashlib
+    from oracle import mmcv_standin, pipeline_ref as pr
+    mmcv_standin.import_reference(rh.REF_ROOT)
+    from mmdet.datasets.pipelines import transforms as T
+    for name, sizes, seed, flips, img_scale in cases.PIPELINE_CASES:
+        imgs, boxes, _ = pr.synth_images(sizes, seed)
+        gold = dict(sha=[], sample=[], boxes=[], img_shape=[], pad_shape=[], scale_factor=[])
+        for img, b, flip in zip(imgs, boxes, flips):
+            r = dict(img=img, gt_bboxes=b.copy(), bbox_fields=['gt_bboxes'], img_fields=['img'], img_shape=img.shape,
+                     ori_shape=img.shape, flip=bool(flip), flip_direction='horizontal' if flip else None)
+            for t in (T.Resize(img_scale=img_scale, keep_ratio=True), T.RandomFlip(flip_ratio=0.5),
+                      T.Normalize(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_rgb=True),
+                      T.Pad(size_divisor=32)):
+                r = t(r)
+            chw = np.ascontiguousarray(r['img'].transpose(2, 0, 1))
+            gold['sha'].append(hashlib.sha256(chw.tobytes()).hexdigest())
+            gold['sample'].append(torch.from_numpy(chw[:, ::7, ::5].copy()))
+            gold['boxes'].append(torch.from_numpy(r['gt_bboxes'].copy()))
+            gold['img_shape'].append(tuple(r['img_shape']))
+            gold['pad_shape'].append(tuple(r['pad_shape']))
+            gold['scale_factor'].append(torch.from_numpy(r['scale_factor'].copy()))
+        torch.save(gold, os.path.join(OUT, name + '.pt'))
+        print(name, gold['img_shape'], [s[:8] for s in gold['sha']])
+
+
 def main():
     if not rh.reference_available():
         sys.exit('needs /root/reference (build container only)')
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
+    if '--pipeline' in sys.argv:
+        gen_pipeline()
+        return
     if '--infer' in sys.argv:
         gen_infer()
         return

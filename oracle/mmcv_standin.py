@@ -339,6 +339,69 @@ class _PermissiveModule(types.ModuleType):
         return val
 
 
+# --------------------------------------------------------------------------- mmcv.image (cv2 / numpy)
+def rescale_size(old_size, scale, return_scale=False):
+    """mmcv/image/geometric.py rescale_size."""
+    w, h = old_size
+    if isinstance(scale, (float, int)):
+        scale_factor = scale
+    else:
+        max_long_edge, max_short_edge = max(scale), min(scale)
+        scale_factor = min(max_long_edge / max(h, w), max_short_edge / min(h, w))
+    new_size = (int(w * float(scale_factor) + 0.5), int(h * float(scale_factor) + 0.5))
+    return (new_size, scale_factor) if return_scale else new_size
+
+
+def imresize(img, size, return_scale=False, interpolation='bilinear', out=None, backend=None):
+    import cv2
+    h, w = img.shape[:2]
+    codes = dict(nearest=cv2.INTER_NEAREST, bilinear=cv2.INTER_LINEAR, bicubic=cv2.INTER_CUBIC, area=cv2.INTER_AREA)
+    resized = cv2.resize(img, size, dst=out, interpolation=codes[interpolation])
+    if not return_scale:
+        return resized
+    return resized, size[0] / w, size[1] / h
+
+
+def imrescale(img, scale, return_scale=False, interpolation='bilinear', backend=None):
+    h, w = img.shape[:2]
+    new_size, scale_factor = rescale_size((w, h), scale, return_scale=True)
+    rescaled = imresize(img, new_size, interpolation=interpolation)
+    return (rescaled, scale_factor) if return_scale else rescaled
+
+
+def imflip(img, direction='horizontal'):
+    assert direction in ('horizontal', 'vertical', 'diagonal')
+    return np.flip(img, axis=1) if direction == 'horizontal' else (
+        np.flip(img, axis=0) if direction == 'vertical' else np.flip(img, axis=(0, 1)))
+
+
+def imnormalize(img, mean, std, to_rgb=True):
+    import cv2
+    img = img.copy().astype(np.float32)
+    assert img.dtype != np.uint8
+    mean = np.float64(mean.reshape(1, -1))
+    stdinv = 1 / np.float64(std.reshape(1, -1))
+    if to_rgb:
+        cv2.cvtColor(img, cv2.COLOR_BGR2RGB, img)
+    cv2.subtract(img, mean, img)
+    cv2.multiply(img, stdinv, img)
+    return img
+
+
+def impad(img, *, shape=None, padding=None, pad_val=0, padding_mode='constant'):
+    import cv2
+    assert (shape is not None) ^ (padding is not None)
+    if shape is not None:
+        padding = (0, 0, shape[1] - img.shape[1], shape[0] - img.shape[0])
+    return cv2.copyMakeBorder(img, padding[1], padding[3], padding[0], padding[2], cv2.BORDER_CONSTANT, value=pad_val)
+
+
+def impad_to_multiple(img, divisor, pad_val=0):
+    pad_h = int(np.ceil(img.shape[0] / divisor)) * divisor
+    pad_w = int(np.ceil(img.shape[1] / divisor)) * divisor
+    return impad(img, shape=(pad_h, pad_w), pad_val=pad_val)
+
+
 def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
     """mmcv.ops.batched_nms (mmcv 1.2.x ops/nms.py:229-292) restated: per-class NMS through the coordinate-offset trick
     (boxes + class * (max coordinate + 1)), greedy IoU > threshold suppression (torchvision.ops.nms has the same rule),
@@ -387,7 +450,8 @@ def install():
 
     mmcv = _mod('mmcv', __version__='1.2.7', jit=_identity_decorator_factory,
                 ConfigDict=ConfigDict, is_tuple_of=is_tuple_of, is_list_of=is_list_of,
-                is_seq_of=is_seq_of, is_str=is_str)
+                is_seq_of=is_seq_of, is_str=is_str, imrescale=imrescale, imresize=imresize, imflip=imflip,
+                imnormalize=imnormalize, impad=impad, impad_to_multiple=impad_to_multiple, rescale_size=rescale_size)
     mmcv.utils = _mod('mmcv.utils', Registry=Registry, build_from_cfg=build_from_cfg,
                       print_log=lambda *a, **k: None,
                       get_logger=lambda name, **k: __import__('logging').getLogger(name),
@@ -415,7 +479,7 @@ def install():
     mmcv.parallel = _mod('mmcv.parallel')
     mmcv.image = _mod('mmcv.image')
 
-    pc = _mod('pycocotools')
+    pc = _mod('pycocotools', __version__='12.0.2')      # mmdet/datasets/coco.py:21 asserts on it at import
     for sub in ('mask', 'coco', 'cocoeval'):
         setattr(pc, sub, _mod('pycocotools.' + sub))
     _mod('terminaltables')

@@ -206,3 +206,24 @@ def test_get_bboxes(golden_dir, case):
     for (det, lab), gd, gl in zip(res, gold['dets'], gold['labels']):
         assert torch.equal(lab, gl)
         assert torch.allclose(det, gd, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize('case', cases.PIPELINE_CASES, ids=lambda c: c[0])
+def test_input_pipeline_restatement(golden_dir, case):
+    """oracle/pipeline_ref.py (cv2 / numpy restatement of mmcv.imrescale / imflip / imnormalize / impad in the
+    reference's transform order) is BIT-identical to the reference's own Resize / RandomFlip / Normalize / Pad classes."""
+    import hashlib
+    import numpy as np
+    from oracle import pipeline_ref as pr
+    name, sizes, seed, flips, img_scale = case
+    gold = _load(golden_dir, name)
+    imgs, boxes, _ = pr.synth_images(sizes, seed)
+    batch, metas, bb = pr.train_pipeline(imgs, boxes, flips, img_scale)
+    for i in range(len(imgs)):
+        ph, pw = gold['pad_shape'][i][:2]
+        chw = np.ascontiguousarray(batch[i, :, :ph, :pw].numpy())
+        assert hashlib.sha256(chw.tobytes()).hexdigest() == gold['sha'][i]
+        assert float(batch[i, :, ph:].abs().sum()) == 0 and float(batch[i, :, :, pw:].abs().sum()) == 0
+        assert tuple(metas[i]['img_shape']) == gold['img_shape'][i] and tuple(metas[i]['pad_shape']) == gold['pad_shape'][i]
+        assert torch.equal(torch.from_numpy(bb[i]), gold['boxes'][i])
+        assert torch.equal(torch.from_numpy(metas[i]['scale_factor']), gold['scale_factor'][i])
