@@ -73,7 +73,7 @@ def d_conv(r, x, w_packed, cout, kh=1, kw=1, stride=1, pad=0, out=None, out_dtyp
 
 
 def d_multi(r, xs, w_packed, cout, kh=1, kw=1, stride=1, pad=0, outs=None, out_dtype=None, scale=None, bias=None,
-            masks=None, relu=False, taps=None):
+            masks=None, relu=False, taps=None, gn_stats=None):
     flop = byts = 0.0
     for x, y in zip(xs, r):
         nb, h, w, cin = x.shape
@@ -96,11 +96,14 @@ def d_wgrad(r, dy, x, dw, kh=1, kw=1, stride=1, pad=0, scale=None, w_master=None
 ops.conv2d_tc = wrap('conv', ops.conv2d_tc, d_conv)
 ops.conv2d_tc_multi = wrap('conv', ops.conv2d_tc_multi, d_multi)
 ops.conv2d_wgrad_tc = wrap('wgrad', ops.conv2d_wgrad_tc, d_wgrad)
-for nm in ('gn_relu_fwd', 'gn_relu_bwd', 'colsum', 'maxpool3x3s2', 'stem_im2col', 'relu_bwd', 'upsample_add_bwd',
+for nm in ('gn_relu_fwd', 'gn_relu_bwd', 'gn_apply_multi', 'gn_relu_bwd_multi', 'colsum', 'maxpool3x3s2', 'stem_im2col', 'relu_bwd', 'upsample_add_bwd',
            'ld_loss_fused', 'ld_targets', 'sgd_flat', 'scatter_add_rows', 'ld_loss_prepass'):
     def mk(nm):
         def describe(r, *a, **k):
             t = [v for v in a if isinstance(v, torch.Tensor)]
+            for v in a:
+                if isinstance(v, (list, tuple)):
+                    t += [u for u in v if isinstance(u, torch.Tensor)]
             byts = sum(v.numel() * v.element_size() for v in t)
             if isinstance(r, torch.Tensor):
                 byts += r.numel() * r.element_size()
