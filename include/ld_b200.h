@@ -310,6 +310,11 @@ typedef struct {
    * channels, the sum and the sum of squares of the values it stores -- the GroupNorm(32) statistics of a 256-channel
    * GFL tower conv (gfl_head.py:102-133) without a separate pass over the output.  Non-flat convs, Cout % 32 == 0. */
   float* gn_stats;
+  /* split mode in two launches: split_pass 1 = leading plane product only, 2 = correction products only (0 = all in one
+   * chain).  pre_src: optional fp32 tensor addressed like `out`, added to the raw accumulator before scale / bias --
+   * pass 2 reads the result of pass 1 through it.  Shortens the accumulation chain of the large terms 6x. */
+  int split_pass;
+  const float* pre_src;
 } ldb_conv_desc;
 
 int ldb200_conv2d_tc(const ldb_conv_desc* desc, void* stream);
@@ -333,6 +338,7 @@ typedef struct {
   const float* w_master;  /* optional fp32 weights [Cout, w_k], needed for d_scale */
   float* d_scale;         /* optional [Cout]: d_scale[co] += <w_master[co,:], G[co,:]> (gradient of the factor) */
   int split;              /* 0, or P in {2,3}: dy and x are P stacked bf16 planes each (see ldb_conv_desc.split) */
+  int split_pass;         /* 0 all plane products, 1 leading product only, 2 corrections only (two accumulating launches) */
 } ldb_wgrad_desc;
 int ldb200_conv2d_wgrad_tc(const ldb_wgrad_desc* desc, void* stream);
 

@@ -50,6 +50,8 @@ struct ConvSeg {            // geometry of one segment (= one FPN level of a lev
   const void* add_src;      // optional add (bf16, or fp32 when p.add_f32), nearest-resampled from [N, add_H, add_W, add_ld]
   int add_H, add_W;
   const void* mask_src;     // optional: multiply by (mask_src > 0), same addressing as out (bf16 / fp32 when p.mask_f32, ld = mask_ld)
+  const float* pre_src;     // optional fp32 tensor addressed like `out`: added to the raw accumulator BEFORE scale / bias
+                            // (second pass of a two-pass split-bf16 conv: main plane product first, corrections after)
   float* gn_stats;          // optional [N, Cout/8, 2]: the epilogue accumulates sum / sum of squares of the output per
                             // (image, group of 8 channels) -- GroupNorm(32) statistics without a pass over the output
   int pf_add, pf_mask;      // L2-prefetch the residual / mask tile with TMA while the main loop runs
@@ -342,6 +344,20 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (S.pre_src) {
+        const float* pr = S.pre_src + pix * (size_t)p.ldc + cbase;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 o4 = __ldg(reinterpret_cast<const float4*>(pr + j));
+            v[j] += o4.x; v[j + 1] += o4.y; v[j + 2] += o4.z; v[j + 3] += o4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cbase + j < p.Cout) v[j] += __ldg(pr + j);
+        }
+      }
       if (full) {
         if (p.scale) {
 #pragma unroll
@@ -1397,6 +1413,9 @@ static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& commo
   g->add_H = d->add_H ? d->add_H : g->OH; g->add_W = d->add_W ? d->add_W : g->OW;
   g->mask_src = d->mask_src;
   g->gn_stats = d->gn_stats;
+  g->pre_src = d->pre_src;
+  LDB_REQUIRE(!d->pre_src || (d->out_f32 && ((uintptr_t)d->pre_src & 15) == 0), LDB_EINVAL,
+              "conv2d_tc: pre_src needs an fp32 output and a 16-byte aligned pointer");
   LDB_REQUIRE(!d->gn_stats || (!d->flat && d->Cout % 32 == 0 && common.vec_ok), LDB_EINVAL,
               "conv2d_tc: gn_stats needs a non-flat conv, Cout %% 32 == 0 and 16-byte aligned rows");
   if (g->add_src) LDB_REQUIRE(((uintptr_t)g->add_src & 15) == 0, LDB_EINVAL, "conv2d_tc: add_src alignment");
@@ -1514,7 +1533,8 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
                 e->accumulate == d->accumulate && e->flat == d->flat && e->in_ld == d->in_ld &&
                 (e->add_src != nullptr) == (d->add_src != nullptr) && e->add_ld == d->add_ld &&
                 (e->mask_src != nullptr) == (d->mask_src != nullptr) && e->mask_ld == d->mask_ld &&
-                (e->gn_stats != nullptr) == (d->gn_stats != nullptr) && e->split == d->split && e->w_plane == d->w_plane && e->add_f32 == d->add_f32 && e->mask_f32 == d->mask_f32 &&
+                (e->gn_stats != nullptr) == (d->gn_stats != nullptr) && (e->pre_src != nullptr) == (d->pre_src != nullptr) &&
+                e->split_pass == d->split_pass && e->split == d->split && e->w_plane == d->w_plane && e->add_f32 == d->add_f32 && e->mask_f32 == d->mask_f32 &&
                 memcmp(e->tap_dx, d->tap_dx, sizeof(d->tap_dx)) == 0 && memcmp(e->tap_dy, d->tap_dy, sizeof(d->tap_dy)) == 0 &&
                 memcmp(e->tap_wk, d->tap_wk, sizeof(d->tap_wk)) == 0,
                 LDB_EINVAL, "conv2d_tc_multi: segment %d does not share weights / taps / epilogue with segment 0", i);
@@ -1547,14 +1567,20 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
   p.w_plane = d->split ? d->w_plane : 0;
   LDB_REQUIRE(!d->split || (d->w_plane % 8 == 0 && d->w_plane * p.planes <= d->w_k), LDB_EINVAL,
               "conv2d_tc: split weights need w_plane %% 8 == 0 and planes * w_plane <= w_k");
+  // split_pass: 0 = every plane product in one accumulation chain; 1 = the leading product (plane 0 x plane 0) only;
+  // 2 = the correction products only.  Two launches (1, then 2 with pre_src = the result of 1) keep the long chain of
+  // the large terms (whose round-off dominates: the tensor core accumulates with truncation) 6x shorter.
+  LDB_REQUIRE(d->split_pass >= 0 && d->split_pass <= 2 && (d->split || !d->split_pass), LDB_EINVAL, "conv2d_tc: split_pass");
   if (d->split == 3) {
     static const int ca[6] = {2, 0, 1, 1, 0, 0}, cw[6] = {0, 2, 1, 0, 1, 0};
-    p.ncombo = 6;
-    for (int i = 0; i < 6; ++i) { p.comb_a[i] = ca[i]; p.comb_w[i] = cw[i]; }
+    const int lo = d->split_pass == 1 ? 5 : 0, hi = d->split_pass == 2 ? 5 : 6;
+    p.ncombo = hi - lo;
+    for (int i = lo; i < hi; ++i) { p.comb_a[i - lo] = ca[i]; p.comb_w[i - lo] = cw[i]; }
   } else if (d->split == 2) {
     static const int ca[3] = {1, 0, 0}, cw[3] = {0, 1, 0};
-    p.ncombo = 3;
-    for (int i = 0; i < 3; ++i) { p.comb_a[i] = ca[i]; p.comb_w[i] = cw[i]; }
+    const int lo = d->split_pass == 1 ? 2 : 0, hi = d->split_pass == 2 ? 2 : 3;
+    p.ncombo = hi - lo;
+    for (int i = lo; i < hi; ++i) { p.comb_a[i - lo] = ca[i]; p.comb_w[i - lo] = cw[i]; }
   } else {
     p.ncombo = 1;
   }
@@ -1665,14 +1691,17 @@ extern "C" int ldb200_conv2d_wgrad_tc(const ldb_wgrad_desc* d, void* stream_) {
   p.scale = d->scale; p.w_master = d->w_master; p.d_scale = d->d_scale;
   LDB_REQUIRE(d->split == 0 || d->split == 2 || d->split == 3, LDB_EINVAL, "wgrad_tc: split must be 0, 2 or 3");
   p.planes = d->split ? d->split : 1;
+  LDB_REQUIRE(d->split_pass >= 0 && d->split_pass <= 2 && (d->split || !d->split_pass), LDB_EINVAL, "wgrad_tc: split_pass");
   if (d->split == 3) {
     static const int ca[6] = {2, 0, 1, 1, 0, 0}, cb[6] = {0, 2, 1, 0, 1, 0};
-    p.ncombo = 6;
-    for (int i = 0; i < 6; ++i) { p.comb_a[i] = ca[i]; p.comb_b[i] = cb[i]; }
+    const int lo = d->split_pass == 1 ? 5 : 0, hi = d->split_pass == 2 ? 5 : 6;
+    p.ncombo = hi - lo;
+    for (int i = lo; i < hi; ++i) { p.comb_a[i - lo] = ca[i]; p.comb_b[i - lo] = cb[i]; }
   } else if (d->split == 2) {
     static const int ca[3] = {1, 0, 0}, cb[3] = {0, 1, 0};
-    p.ncombo = 3;
-    for (int i = 0; i < 3; ++i) { p.comb_a[i] = ca[i]; p.comb_b[i] = cb[i]; }
+    const int lo = d->split_pass == 1 ? 2 : 0, hi = d->split_pass == 2 ? 2 : 3;
+    p.ncombo = hi - lo;
+    for (int i = lo; i < hi; ++i) { p.comb_a[i - lo] = ca[i]; p.comb_b[i - lo] = cb[i]; }
   } else {
     p.ncombo = 1;
   }

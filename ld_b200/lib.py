@@ -58,7 +58,8 @@ class ConvDesc(C.Structure):
                 ('scale', C.c_void_p), ('bias', C.c_void_p), ('add_src', C.c_void_p), ('add_H', C.c_int),
                 ('add_W', C.c_int), ('add_ld', C.c_int), ('mask_src', C.c_void_p), ('mask_ld', C.c_int),
                 ('relu', C.c_int), ('accumulate', C.c_int), ('split', C.c_int), ('w_plane', C.c_int),
-                ('add_f32', C.c_int), ('mask_f32', C.c_int), ('gn_stats', C.c_void_p)]
+                ('add_f32', C.c_int), ('mask_f32', C.c_int), ('gn_stats', C.c_void_p),
+                ('split_pass', C.c_int), ('pre_src', C.c_void_p)]
 
 
 class GnSeg(C.Structure):
@@ -76,7 +77,7 @@ class WgradDesc(C.Structure):
                 ('dy_ld', C.c_int), ('x', C.c_void_p), ('H', C.c_int), ('W', C.c_int), ('Cin', C.c_int),
                 ('x_ld', C.c_int), ('ntaps', C.c_int), ('tap_dx', C.c_int * 9), ('tap_dy', C.c_int * 9),
                 ('tap_wk', C.c_int * 9), ('sx', C.c_int), ('sy', C.c_int), ('dw', C.c_void_p), ('w_k', C.c_int),
-                ('scale', C.c_void_p), ('w_master', C.c_void_p), ('d_scale', C.c_void_p), ('split', C.c_int)]
+                ('scale', C.c_void_p), ('w_master', C.c_void_p), ('d_scale', C.c_void_p), ('split', C.c_int), ('split_pass', C.c_int)]
 
 
 _SIGS = {

@@ -363,8 +363,14 @@ def split_weight(w2d, planes=None):
     return sp.permute(1, 0, 2).contiguous()
 
 
+# fp32-accurate mode: leading plane product and corrections in two accumulation chains (LDB200_PARITY_ONE_PASS=1: all six
+# plane products in one chain, for A/B measurements of the accumulation error)
+import os as _os
+PARITY_TWO_PASS = _os.environ.get('LDB200_PARITY_ONE_PASS') is None
+
+
 def _conv_desc(d, x, w_packed, cout, kh, kw, stride, pad, out, out_dtype, scale, bias, add, mask, relu, accumulate,
-               flat, taps, out_hw, out_map):
+               flat, taps, out_hw, out_map, xsplit=None):
     assert x.dim() == 4
     keep = None
     if x.dtype == torch.float32:
@@ -372,7 +378,7 @@ def _conv_desc(d, x, w_packed, cout, kh, kw, stride, pad, out, out_dtype, scale,
         assert w_packed.dim() == 3, 'fp32 activations need split weights (ops.split_weight)'
         planes = w_packed.shape[1]
         n_, h_, w__, c_ = x.shape
-        keep = split_bf16(x, planes)
+        keep = xsplit if xsplit is not None else split_bf16(x, planes)
         x = keep[0].view(n_, h_, w__, -1)[..., :c_]
         d.split, d.w_plane = planes, w_packed.shape[2]
         out_dtype = torch.float32
@@ -433,6 +439,24 @@ def conv2d_tc(x, w_packed, cout, kh=1, kw=1, stride=1, pad=0, out=None, out_dtyp
               taps=None, out_hw=None, out_map=None):
     """NHWC bf16 convolution on tcgen05 (ldb200_conv2d_tc).  x: [N,H,W,Cin] bf16 contiguous (or a
     channel slice with stride(2) = ld).  Returns [N,HO,WO,Cout] NHWC `out_dtype`."""
+    if x.dtype == torch.float32 and PARITY_TWO_PASS:
+        # pass 1: leading plane product alone (plain fp32 store into a scratch tensor with the output's geometry);
+        # pass 2: the correction products + the result of pass 1 (pre_src), then the whole epilogue
+        d1, d2 = L.ConvDesc(), L.ConvDesc()
+        tmp_like = None
+        if out is not None:
+            tmp_like = torch.empty(out.shape, dtype=torch.float32, device=x.device)
+        t1, keep = _conv_desc(d1, x, w_packed, cout, kh, kw, stride, pad, tmp_like, torch.float32, None, None, None, None,
+                              False, False, flat, taps, out_hw, out_map)
+        d1.split_pass = 1
+        L.check(L.load().ldb200_conv2d_tc(C.byref(d1), L.stream_ptr()), 'ldb200_conv2d_tc')
+        out, _ = _conv_desc(d2, x, w_packed, cout, kh, kw, stride, pad, out, out_dtype, scale, bias, add, mask, relu,
+                            accumulate, flat, taps, out_hw, out_map, xsplit=keep)
+        assert out.stride(2) == t1.stride(2), 'two-pass split conv: scratch and output rows must have the same stride'
+        d2.split_pass, d2.pre_src = 2, t1.data_ptr()
+        L.check(L.load().ldb200_conv2d_tc(C.byref(d2), L.stream_ptr()), 'ldb200_conv2d_tc')
+        del keep, t1
+        return out
     d = L.ConvDesc()
     out, keep = _conv_desc(d, x, w_packed, cout, kh, kw, stride, pad, out, out_dtype, scale, bias, add, mask, relu,
                            accumulate, flat, taps, out_hw, out_map)
@@ -447,19 +471,34 @@ def conv2d_tc_multi(xs, w_packed, cout, kh=1, kw=1, stride=1, pad=0, outs=None, 
     gn_stats: optional list of zero-filled [N, cout/8, 2] f32 tensors the epilogue accumulates the GroupNorm
     statistics of each output into."""
     n = len(xs)
+    pre, xsplits = None, [None] * n
+    if xs[0].dtype == torch.float32 and PARITY_TWO_PASS:
+        d1 = (L.ConvDesc * n)()
+        pre, xsplits = [], []
+        for i, x in enumerate(xs):
+            tmp = None if outs is None else torch.empty(outs[i].shape, dtype=torch.float32, device=x.device)
+            t1, k = _conv_desc(d1[i], x, w_packed, cout, kh, kw, stride, pad, tmp, torch.float32, None, None, None, None,
+                               False, False, False, taps, None if taps is None else tuple(x.shape[1:3]), None)
+            d1[i].split_pass = 1
+            pre.append(t1)
+            xsplits.append(k)
+        L.check(L.load().ldb200_conv2d_tc_multi(d1, n, L.stream_ptr()), 'ldb200_conv2d_tc_multi')
     descs = (L.ConvDesc * n)()
     res, keep = [], []
     for i, x in enumerate(xs):
         o, k = _conv_desc(descs[i], x, w_packed, cout, kh, kw, stride, pad, None if outs is None else outs[i],
                           out_dtype, scale, bias, None, None if masks is None else masks[i], relu, False, False,
-                          taps, None if taps is None else tuple(x.shape[1:3]), None)
+                          taps, None if taps is None else tuple(x.shape[1:3]), None, xsplit=xsplits[i])
+        if pre is not None:
+            assert o.stride(2) == pre[i].stride(2)
+            descs[i].split_pass, descs[i].pre_src = 2, pre[i].data_ptr()
         if gn_stats is not None:
             assert gn_stats[i].dtype == torch.float32 and gn_stats[i].numel() == x.shape[0] * (cout // 8) * 2
             descs[i].gn_stats = gn_stats[i].data_ptr()
         res.append(o)
         keep.append(k)
     L.check(L.load().ldb200_conv2d_tc_multi(descs, n, L.stream_ptr()), 'ldb200_conv2d_tc_multi')
-    del keep
+    del keep, pre, xsplits
     return res
 
 
@@ -640,6 +679,11 @@ def conv2d_wgrad_tc(dy, x, dw, kh=1, kw=1, stride=1, pad=0, scale=None, w_master
         assert w_master is not None and w_master.dtype == torch.float32 and w_master.shape == dw.shape \
             and w_master.is_contiguous() and d_scale.dtype == torch.float32
         d.w_master, d.d_scale = w_master.data_ptr(), d_scale.data_ptr()
+    if d.split and PARITY_TWO_PASS:      # leading plane product, then the corrections: two accumulating launches
+        for sp in (1, 2):
+            d.split_pass = sp
+            L.check(L.load().ldb200_conv2d_wgrad_tc(C.byref(d), L.stream_ptr()), 'ldb200_conv2d_wgrad_tc')
+        return dw
     L.check(L.load().ldb200_conv2d_wgrad_tc(C.byref(d), L.stream_ptr()), 'ldb200_conv2d_wgrad_tc')
     return dw
 
