@@ -373,7 +373,7 @@ int ldb200_gn_stats(const void* x, float* stats, int N, int HW, int C, int G, in
 #define LDB_GN_MAX_SEG 5
 typedef struct {
   const void* x;        /* [N, HW, C] conv output (pre-norm) */
-  const void* y;        /* backward: relu(GN(x)) of the forward pass */
+  const void* y;        /* backward: relu(GN(x)) of the forward pass, or NULL (mask recomputed from x) */
   const void* dy;       /* backward: gradient w.r.t. y */
   void* out;            /* apply: y; backward: dx */
   const float* stats;   /* [N, G, 2] sum, sum of squares of x */
@@ -383,8 +383,10 @@ typedef struct {
 } ldb_gn_seg;
 int ldb200_gn_apply_multi(const ldb_gn_seg* segs, int count, const float* gamma, const float* beta, int C, int G,
                           float eps, int relu, int dtype, void* stream);
-int ldb200_gn_relu_bwd_multi(const ldb_gn_seg* segs, int count, const float* gamma, float* dgamma, float* dbeta, int C,
-                             int G, float eps, int dtype, void* stream);
+/* backward: a segment's `y` may be NULL -- the ReLU mask is then recomputed from x, the statistics and gamma / `beta`
+ * (y > 0 <=> x*a + b > 0), which saves reading y in both passes. */
+int ldb200_gn_relu_bwd_multi(const ldb_gn_seg* segs, int count, const float* gamma, const float* beta, float* dgamma,
+                             float* dbeta, int C, int G, float eps, int dtype, void* stream);
 int ldb200_gn_apply(const void* x, const float* stats, const float* gamma, const float* beta, void* y,
                     int N, int HW, int C, int G, float eps, int relu, int dtype, void* stream);
 /* backward of y = relu(GN(x)): dx [N,HW,C] bf16, dgamma/dbeta [C] f32 ACCUMULATED (shared towers),

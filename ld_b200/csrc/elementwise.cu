@@ -240,8 +240,8 @@ gn_apply_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ gamm
 // red: [N, G, 2] fp32 accumulated; dgamma/dbeta: [C] fp32 accumulated.
 template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
-gn_bwd_stats_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ gamma, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta, float eps) {
+gn_bwd_stats_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, float eps) {
   const GnBlock B = gn_block(S);
   const int C = S.C, HW = S.HW[B.sg], n = B.n, p0 = B.p0, p1 = B.p1;
   const T* __restrict__ dy = (const T*)S.dy[B.sg];
@@ -254,22 +254,30 @@ gn_bwd_stats_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ 
   const float inv_m = 1.f / ((float)HW * GN_CPG);
   const float mean = __ldg(stats + ((size_t)n * G + g) * 2) * inv_m;
   const float rstd = rsqrtf(fmaxf(__ldg(stats + ((size_t)n * G + g) * 2 + 1) * inv_m - mean * mean, 0.f) + eps);
-  float gam[8], acc[18];
+  // y == null: the ReLU mask is recomputed from x (y > 0  <=>  x*a + b > 0 with the forward pass's a, b: bf16 / fp32
+  // rounding of a positive value stays positive), which saves reading y in both backward passes (14 -> 10 B / element)
+  const bool remask = (y == nullptr);
+  float gam[8], ma[8], mb[8], acc[18];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) gam[e] = __ldg(gamma + g * GN_CPG + e);
+  for (int e = 0; e < 8; ++e) {
+    gam[e] = __ldg(gamma + g * GN_CPG + e);
+    ma[e] = rstd * gam[e];
+    mb[e] = remask ? __ldg(beta + g * GN_CPG + e) - mean * ma[e] : 0.f;
+  }
 #pragma unroll
   for (int e = 0; e < 18; ++e) acc[e] = 0.f;   // [0]=sum dxh, [1]=sum dxh*xh, [2..9]=dgamma, [10..17]=dbeta
   const size_t img = (size_t)n * HW * C + g * 8;
   const T* pdy = dy + img;
-  const T* py = y + img;
+  const T* py = remask ? nullptr : y + img;
   const T* px = x + img;
   for (int p = p0 + r0; p < p1; p += 2 * lanes) {
     const bool two = p + lanes < p1;
     float q[6][8];
-    ld8<T>(pdy + (size_t)p * C, q[0]); ld8<T>(py + (size_t)p * C, q[1]); ld8<T>(px + (size_t)p * C, q[2]);
+    ld8<T>(pdy + (size_t)p * C, q[0]); ld8<T>(px + (size_t)p * C, q[2]);
+    if (!remask) ld8<T>(py + (size_t)p * C, q[1]);
     if (two) {
-      ld8<T>(pdy + (size_t)(p + lanes) * C, q[3]); ld8<T>(py + (size_t)(p + lanes) * C, q[4]);
-      ld8<T>(px + (size_t)(p + lanes) * C, q[5]);
+      ld8<T>(pdy + (size_t)(p + lanes) * C, q[3]); ld8<T>(px + (size_t)(p + lanes) * C, q[5]);
+      if (!remask) ld8<T>(py + (size_t)(p + lanes) * C, q[4]);
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -277,7 +285,8 @@ gn_bwd_stats_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ 
       const float *vd = q[3 * u], *vy = q[3 * u + 1], *vx = q[3 * u + 2];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float gg = vy[e] > 0.f ? vd[e] : 0.f;
+        const bool on = remask ? (vx[e] * ma[e] + mb[e] > 0.f) : (vy[e] > 0.f);
+        const float gg = on ? vd[e] : 0.f;
         const float xh = (vx[e] - mean) * rstd;
         const float dxh = gg * gam[e];
         acc[0] += dxh;
@@ -304,7 +313,8 @@ gn_bwd_stats_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ 
 // pass 2: dx = rstd * (dxh - mean(dxh) - xh * mean(dxh*xh))
 template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
-gn_bwd_apply_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ gamma, float eps) {
+gn_bwd_apply_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float eps) {
   const GnBlock B = gn_block(S);
   const int C = S.C, HW = S.HW[B.sg], n = B.n, p0 = B.p0, p1 = B.p1;
   const T* __restrict__ dy = (const T*)S.dy[B.sg];
@@ -319,21 +329,27 @@ gn_bwd_apply_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ 
   const float mean = __ldg(stats + ((size_t)n * G + g) * 2) * inv_m;
   const float rstd = rsqrtf(fmaxf(__ldg(stats + ((size_t)n * G + g) * 2 + 1) * inv_m - mean * mean, 0.f) + eps);
   const float m1 = __ldg(red + ((size_t)n * G + g) * 2) * inv_m, m2 = __ldg(red + ((size_t)n * G + g) * 2 + 1) * inv_m;
-  float gam[8];
+  const bool remask = (y == nullptr);
+  float gam[8], ma[8], mb[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) gam[e] = __ldg(gamma + g * GN_CPG + e);
+  for (int e = 0; e < 8; ++e) {
+    gam[e] = __ldg(gamma + g * GN_CPG + e);
+    ma[e] = rstd * gam[e];
+    mb[e] = remask ? __ldg(beta + g * GN_CPG + e) - mean * ma[e] : 0.f;
+  }
   const size_t img = (size_t)n * HW * C + g * 8;
   const T* pdy = dy + img;
-  const T* py = y + img;
+  const T* py = remask ? nullptr : y + img;
   const T* px = x + img;
   T* pdx = dx + img;
   for (int p = p0 + r0; p < p1; p += 2 * lanes) {
     const bool two = p + lanes < p1;
     float q[6][8];
-    ld8<T>(pdy + (size_t)p * C, q[0]); ld8<T>(py + (size_t)p * C, q[1]); ld8<T>(px + (size_t)p * C, q[2]);
+    ld8<T>(pdy + (size_t)p * C, q[0]); ld8<T>(px + (size_t)p * C, q[2]);
+    if (!remask) ld8<T>(py + (size_t)p * C, q[1]);
     if (two) {
-      ld8<T>(pdy + (size_t)(p + lanes) * C, q[3]); ld8<T>(py + (size_t)(p + lanes) * C, q[4]);
-      ld8<T>(px + (size_t)(p + lanes) * C, q[5]);
+      ld8<T>(pdy + (size_t)(p + lanes) * C, q[3]); ld8<T>(px + (size_t)(p + lanes) * C, q[5]);
+      if (!remask) ld8<T>(py + (size_t)(p + lanes) * C, q[4]);
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -342,7 +358,8 @@ gn_bwd_apply_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ 
       const float *vy = q[3 * u + 1], *vx = q[3 * u + 2];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float gg = vy[e] > 0.f ? vd[e] : 0.f;
+        const bool on = remask ? (vx[e] * ma[e] + mb[e] > 0.f) : (vy[e] > 0.f);
+        const float gg = on ? vd[e] : 0.f;
         const float xh = (vx[e] - mean) * rstd;
         vd[e] = rstd * (gg * gam[e] - m1 - xh * m2);
       }
@@ -701,29 +718,30 @@ extern "C" int ldb200_gn_apply(const void* x, const float* stats, const float* g
   return ldb200_gn_apply_multi(&seg, 1, gamma, beta, C, G, eps, relu, dtype, stream_);
 }
 
-extern "C" int ldb200_gn_relu_bwd_multi(const ldb_gn_seg* segs, int count, const float* gamma, float* dgamma,
-                                        float* dbeta, int C, int G, float eps, int dtype, void* stream_) {
+extern "C" int ldb200_gn_relu_bwd_multi(const ldb_gn_seg* segs, int count, const float* gamma, const float* beta,
+                                        float* dgamma, float* dbeta, int C, int G, float eps, int dtype, void* stream_) {
   GnSegs S;
   int e = gn_make_segs(segs, count, C, G, &S);
   if (e) return e;
   LDB_REQUIRE(gamma && dgamma && dbeta, LDB_EINVAL, "gn_relu_bwd: null pointer");
   cudaStream_t s = (cudaStream_t)stream_;
   for (int i = 0; i < count; ++i) {
-    LDB_REQUIRE(segs[i].dy && segs[i].y && segs[i].x && segs[i].stats && segs[i].red_ws && segs[i].out, LDB_EINVAL,
+    LDB_REQUIRE(segs[i].dy && segs[i].x && segs[i].stats && segs[i].red_ws && segs[i].out, LDB_EINVAL,
                 "gn_relu_bwd: null pointer in segment %d", i);
+    LDB_REQUIRE(segs[i].y || beta, LDB_EINVAL, "gn_relu_bwd: segment %d has no y: beta is needed to recompute the mask", i);
     S.out[i] = segs[i].out;
     S.acc[i] = segs[i].red_ws;
     // the per-segment scratch may be slices of one buffer the caller zeroed itself (red_zeroed)
     if (!segs[i].red_zeroed) LDB_CUDA(cudaMemsetAsync(segs[i].red_ws, 0, sizeof(float) * 2 * segs[i].N * G, s));
   }
   if (dtype == LDB_F32) {
-    gn_bwd_stats_kernel<float><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, dgamma, dbeta, eps);
+    gn_bwd_stats_kernel<float><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, beta, dgamma, dbeta, eps);
     LDB_CUDA(cudaGetLastError());
-    gn_bwd_apply_kernel<float><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, eps);
+    gn_bwd_apply_kernel<float><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, beta, eps);
   } else {
-    gn_bwd_stats_kernel<__nv_bfloat16><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, dgamma, dbeta, eps);
+    gn_bwd_stats_kernel<__nv_bfloat16><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, beta, dgamma, dbeta, eps);
     LDB_CUDA(cudaGetLastError());
-    gn_bwd_apply_kernel<__nv_bfloat16><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, eps);
+    gn_bwd_apply_kernel<__nv_bfloat16><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, beta, eps);
   }
   LDB_CUDA(cudaGetLastError());
   return 0;
@@ -735,7 +753,7 @@ extern "C" int ldb200_gn_relu_bwd(const void* dy, const void* y, const void* x, 
   ldb_gn_seg seg;
   memset(&seg, 0, sizeof(seg));
   seg.dy = dy; seg.y = y; seg.x = x; seg.stats = stats; seg.red_ws = red_ws; seg.out = dx; seg.N = N; seg.HW = HW;
-  return ldb200_gn_relu_bwd_multi(&seg, 1, gamma, dgamma, dbeta, C, G, eps, dtype, stream_);
+  return ldb200_gn_relu_bwd_multi(&seg, 1, gamma, nullptr, dgamma, dbeta, C, G, eps, dtype, stream_);
 }
 
 extern "C" int ldb200_upsample_add_bwd(const void* dfine, void* dcoarse, int N, int Hf, int Wf, int Hc, int Wc, int C,

@@ -495,6 +495,10 @@ def conv_levels(weight, xs, pad=1):
     return list(ConvLevelsFn.apply(weight, pad, *xs))
 
 
+import os as _os
+_GN_READ_Y = _os.environ.get('LDB200_GN_READ_Y') is not None
+
+
 class ConvGNReLULevelsFn(torch.autograd.Function):
     """One GFL tower layer (gfl_head.py:102-133, 177-180: level-shared 3x3 conv without bias -> GroupNorm(32) -> ReLU)
     on ALL pyramid levels as one autograd node:
@@ -536,7 +540,9 @@ class ConvGNReLULevelsFn(torch.autograd.Function):
         dg = sg if direct else zeros_f32(gamma.numel(), xs[0].device)
         db = sb if direct else zeros_f32(gamma.numel(), xs[0].device)
         dys = [d.contiguous() if d.dtype == cs[0].dtype else d.to(cs[0].dtype).contiguous() for d in dys]
-        gs = ops.gn_relu_bwd_multi(dys, ys, cs, stats, gamma.detach().contiguous(), dg, db, groups, eps)
+        # the ReLU mask is recomputed from the conv output and the statistics: y is not read (LDB200_GN_READ_Y=1: read it)
+        gs = ops.gn_relu_bwd_multi(dys, ys if _GN_READ_Y else None, cs, stats, gamma.detach().contiguous(), dg, db,
+                                   groups, eps, beta=beta.detach().contiguous())
         if ctx.needs_input_grad[0]:
             for g, x in zip(gs, xs):
                 _wgrad_into(weight, g, x, None, 1, pad, False)

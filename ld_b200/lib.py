@@ -117,7 +117,7 @@ _SIGS = {
     'ldb200_gn_relu_bwd': (C.c_int, [C.c_void_p] * 9 + [C.c_int] * 4 + [C.c_float, C.c_int, C.c_void_p]),
     'ldb200_gn_apply_multi': (C.c_int, [C.POINTER(GnSeg), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                         C.c_int, C.c_int, C.c_void_p]),
-    'ldb200_gn_relu_bwd_multi': (C.c_int, [C.POINTER(GnSeg), C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_float,
+    'ldb200_gn_relu_bwd_multi': (C.c_int, [C.POINTER(GnSeg), C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_float,
                                                                                           C.c_int, C.c_void_p]),
     'ldb200_upsample_add_bwd': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]),
     'ldb200_relu_bwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int, C.c_void_p]),

@@ -583,9 +583,12 @@ def gn_apply_multi(xs, stats, gamma, beta, groups=32, eps=1e-5, relu=True):
     return ys
 
 
-def gn_relu_bwd_multi(dys, ys, xs, stats, gamma, dgamma, dbeta, groups=32, eps=1e-5):
+def gn_relu_bwd_multi(dys, ys, xs, stats, gamma, dgamma, dbeta, groups=32, eps=1e-5, beta=None):
     """Backward of `gn_apply_multi` (relu=True) for all levels in two launches -> list of dx; dgamma / dbeta [C] f32
-    accumulated in place."""
+    accumulated in place.  ys=None (+ beta): the ReLU mask is recomputed from x instead of being read from y."""
+    if ys is None:
+        assert beta is not None
+        ys = [None] * len(xs)
     n = len(xs)
     segs = (L.GnSeg * n)()
     c = xs[0].shape[-1]
@@ -593,15 +596,17 @@ def gn_relu_bwd_multi(dys, ys, xs, stats, gamma, dgamma, dbeta, groups=32, eps=1
     red = torch.zeros(tot, dtype=torch.float32, device=xs[0].device)     # one fill for all levels
     dxs, o = [], 0
     for i, (dy, y, x) in enumerate(zip(dys, ys, xs)):
-        assert dy.is_contiguous() and y.is_contiguous() and x.is_contiguous() and dy.dtype == y.dtype == x.dtype
+        assert dy.is_contiguous() and x.is_contiguous() and dy.dtype == x.dtype
+        assert y is None or (y.is_contiguous() and y.dtype == x.dtype)
         dx = torch.empty_like(x)
         k = x.shape[0] * groups * 2
-        segs[i].dy, segs[i].y, segs[i].x, segs[i].out = dy.data_ptr(), y.data_ptr(), x.data_ptr(), dx.data_ptr()
+        segs[i].dy, segs[i].x, segs[i].out = dy.data_ptr(), x.data_ptr(), dx.data_ptr()
+        segs[i].y = None if y is None else y.data_ptr()
         segs[i].stats, segs[i].red_ws, segs[i].red_zeroed = stats[i].data_ptr(), red[o:o + k].data_ptr(), 1
         segs[i].N, segs[i].HW = x.shape[0], x.shape[1] * x.shape[2]
         o += k
         dxs.append(dx)
-    L.check(L.load().ldb200_gn_relu_bwd_multi(segs, n, L.ptr(gamma), L.ptr(dgamma), L.ptr(dbeta), c, groups, float(eps),
+    L.check(L.load().ldb200_gn_relu_bwd_multi(segs, n, L.ptr(gamma), L.ptr(beta), L.ptr(dgamma), L.ptr(dbeta), c, groups, float(eps),
                                               _dt(xs[0].dtype), L.stream_ptr()), 'ldb200_gn_relu_bwd_multi')
     del red
     return dxs
