@@ -369,6 +369,31 @@ import os as _os
 PARITY_TWO_PASS = _os.environ.get('LDB200_PARITY_ONE_PASS') is None
 
 
+# Tensor cores accumulate with truncation (round toward zero): a chain of k MMA steps into one TMEM accumulator loses
+# about k/2 ulp of the running sum, systematically.  The fp32-accurate mode therefore keeps every chain of the LEADING
+# plane product short -- one filter tap and at most PARITY_CHAIN_CH input channels (256 -> 16 MMA steps) -- and adds the
+# partial results in the epilogue with round-to-nearest fp32 adds (`pre_src`); the correction products are 2^-8 of the
+# leading one, their (long) chain contributes 2^-8 of the error.  LDB200_PARITY_CHAIN_CH=0: one chain for the leading term.
+PARITY_CHAIN_CH = int(_os.environ.get('LDB200_PARITY_CHAIN_CH', '256'))
+
+
+def _chain_descs(d1):
+    """Sub-descriptors of a leading-product pass: one launch per (tap, <= PARITY_CHAIN_CH input channels)."""
+    if PARITY_CHAIN_CH <= 0:
+        return [d1]
+    out = []
+    cin = d1.Cin
+    for t in range(d1.ntaps):
+        for c0 in range(0, cin, PARITY_CHAIN_CH):
+            d = L.ConvDesc.from_buffer_copy(d1)
+            d.ntaps = 1
+            d.tap_dx[0], d.tap_dy[0], d.tap_wk[0] = d1.tap_dx[t], d1.tap_dy[t], d1.tap_wk[t] + c0
+            d.in_ = d1.in_ + 2 * c0
+            d.Cin = min(PARITY_CHAIN_CH, cin - c0)
+            out.append(d)
+    return out
+
+
 def _conv_desc(d, x, w_packed, cout, kh, kw, stride, pad, out, out_dtype, scale, bias, add, mask, relu, accumulate,
                flat, taps, out_hw, out_map, xsplit=None):
     assert x.dim() == 4
@@ -449,7 +474,10 @@ def conv2d_tc(x, w_packed, cout, kh=1, kw=1, stride=1, pad=0, out=None, out_dtyp
         t1, keep = _conv_desc(d1, x, w_packed, cout, kh, kw, stride, pad, tmp_like, torch.float32, None, None, None, None,
                               False, False, flat, taps, out_hw, out_map)
         d1.split_pass = 1
-        L.check(L.load().ldb200_conv2d_tc(C.byref(d1), L.stream_ptr()), 'ldb200_conv2d_tc')
+        for i, dd in enumerate(_chain_descs(d1)):     # short chains, partial sums added in place (same thread reads
+            if i:                                     # and writes an element, so pre_src == out is safe)
+                dd.pre_src = t1.data_ptr()
+            L.check(L.load().ldb200_conv2d_tc(C.byref(dd), L.stream_ptr()), 'ldb200_conv2d_tc')
         out, _ = _conv_desc(d2, x, w_packed, cout, kh, kw, stride, pad, out, out_dtype, scale, bias, add, mask, relu,
                             accumulate, flat, taps, out_hw, out_map, xsplit=keep)
         assert out.stride(2) == t1.stride(2), 'two-pass split conv: scratch and output rows must have the same stride'
@@ -482,7 +510,13 @@ def conv2d_tc_multi(xs, w_packed, cout, kh=1, kw=1, stride=1, pad=0, outs=None, 
             d1[i].split_pass = 1
             pre.append(t1)
             xsplits.append(k)
-        L.check(L.load().ldb200_conv2d_tc_multi(d1, n, L.stream_ptr()), 'ldb200_conv2d_tc_multi')
+        chains = [_chain_descs(d1[i]) for i in range(n)]
+        for j in range(len(chains[0])):
+            dj = (L.ConvDesc * n)(*[chains[i][j] for i in range(n)])
+            if j:
+                for i in range(n):
+                    dj[i].pre_src = pre[i].data_ptr()
+            L.check(L.load().ldb200_conv2d_tc_multi(dj, n, L.stream_ptr()), 'ldb200_conv2d_tc_multi')
     descs = (L.ConvDesc * n)()
     res, keep = [], []
     for i, x in enumerate(xs):

@@ -19,10 +19,9 @@ for (n, h, w, cin, cout, k) in ((2, 25, 42, 256, 256, 3), (2, 50, 84, 512, 128, 
     want = F.conv2d(x.double().permute(0, 3, 1, 2), wt.double(), None, 1, k // 2).permute(0, 2, 3, 1)
     w3 = ops.split_weight(wt.permute(0, 2, 3, 1).reshape(cout, -1))
     res = {}
-    for two in (False, True):
-        ops.PARITY_TWO_PASS = two
-        y = ops.conv2d_tc(x, w3, cout, k, k, 1, k // 2)
-        res['two chains' if two else 'one chain'] = y
+    for two, ch, name in ((False, 0, 'one chain'), (True, 0, 'lead+corr'), (True, 256, 'tap x 256ch'), (True, 64, 'tap x 64ch')):
+        ops.PARITY_TWO_PASS, ops.PARITY_CHAIN_CH = two, ch
+        res[name] = ops.conv2d_tc(x, w3, cout, k, k, 1, k // 2)
     res['torch fp32 (cuDNN)'] = F.conv2d(x.permute(0, 3, 1, 2), wt, None, 1, k // 2).permute(0, 2, 3, 1)
     res['torch fp32 (CPU)'] = F.conv2d(x.cpu().permute(0, 3, 1, 2), wt.cpu(), None, 1, k // 2).permute(0, 2, 3, 1).cuda()
     line = f'{k}x{k} {cin}->{cout} @{n}x{h}x{w}: '

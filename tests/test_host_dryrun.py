@@ -169,7 +169,9 @@ def test_parity_mode_train_step_host_logic(fake_backend, student):
     ts.step(_batch(), sync_logs=False)
     assert not engine.parity()                      # the mode is scoped to the step
     convs = fake_backend.count('ldb200_conv2d_tc') + fake_backend.count('ldb200_conv2d_tc_multi')
-    assert convs > 0 and fake_backend.count('ldb200_split_bf16') > convs    # activations + weights
+    # every conv splits its activation (and, once, its weights); the leading plane product runs as several short
+    # accumulation chains (one launch per tap and 256 input channels), so there are more launches than splits
+    assert fake_backend.count('ldb200_split_bf16') > 100 and convs > fake_backend.count('ldb200_split_bf16')
     _check_grads(m)
 
 
