@@ -624,15 +624,20 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
         // L2 with one TMA prefetch each so those loads see L2 latency instead of HBM latency
         if (S.pf_add) tma_prefetch_4d(&maps.r[sg], nt * BN, tx * S.TW, ty * S.TH, n);
         if (S.pf_mask) tma_prefetch_4d(&maps.m[sg], nt * BN, tx * S.TW, ty * S.TH, n);
-        for (int kb = 0; kb < kblocks; ++kb) {
-          const int tc_ = kb / cchunks, c0 = (kb - tc_ * cchunks) * KCH;
-          const int cmb = tc_ / p.ntaps, tap = tc_ - cmb * p.ntaps;   // (plane pair, tap): cmb = 0 in plain bf16 mode
-          mbarrier_wait(&empty[stage], phase ^ 1);
-          unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
-          mbarrier_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          tma_load_4d(sa, &maps.a[sg], &full[stage], c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], n + p.comb_a[cmb] * S.N);
-          tma_load_2d(sa + A_TILE_BYTES, &tmB, &full[stage], p.comb_w[cmb] * p.w_plane + p.tap_wk[tap] + c0, nt * BN);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        // (plane pair, tap, 64-channel slice): nested counters, no divisions on the producer's critical path
+        for (int cmb = 0; cmb < p.ncombo; ++cmb) {
+          const int na = n + p.comb_a[cmb] * S.N, wk0 = p.comb_w[cmb] * p.w_plane;
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap], wk = wk0 + p.tap_wk[tap];
+            for (int c0 = 0; c0 < p.Cin; c0 += KCH) {
+              mbarrier_wait(&empty[stage], phase ^ 1);
+              unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+              mbarrier_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+              tma_load_4d(sa, &maps.a[sg], &full[stage], c0, ax, ay, na);
+              tma_load_2d(sa + A_TILE_BYTES, &tmB, &full[stage], wk + c0, nt * BN);
+              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
         }
       }
     }
@@ -824,18 +829,22 @@ conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ C
         // L2 with one TMA prefetch each so those loads see L2 latency instead of HBM latency
         if (S.pf_add) tma_prefetch_4d(&maps.r[sg], nt * BN, tx * S.TW, ty * S.TH, n);
         if (S.pf_mask) tma_prefetch_4d(&maps.m[sg], nt * BN, tx * S.TW, ty * S.TH, n);
-        for (int kb = 0; kb < kblocks; ++kb) {
-          const int tc_ = kb / cchunks, c0 = (kb - tc_ * cchunks) * KCH;
-          const int cmb = tc_ / p.ntaps, tap = tc_ - cmb * p.ntaps;   // (plane pair, tap): cmb = 0 in plain bf16 mode
-          mbarrier_wait(&empty[stage], phase ^ 1);
-          unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
-          // both CTAs' loads complete on the LEADER's barrier; only the leader arms it (bytes of the pair)
-          if (rank == 0) mbarrier_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-          tma_load_4d_2sm(sa, &maps.a[sg], &full[stage], c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap],
-                          dummy ? n : n + p.comb_a[cmb] * S.N);
-          tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, &full[stage], p.comb_w[cmb] * p.w_plane + p.tap_wk[tap] + c0,
-                          nt * BN + (int)rank * (BN / 2));
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        // (plane pair, tap, 64-channel slice): nested counters, no divisions on the producer's critical path
+        const int wrow = nt * BN + (int)rank * (BN / 2);
+        for (int cmb = 0; cmb < p.ncombo; ++cmb) {
+          const int na = dummy ? n : n + p.comb_a[cmb] * S.N, wk0 = p.comb_w[cmb] * p.w_plane;
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            const int ax = x0 + p.tap_dx[tap], ay = y0 + p.tap_dy[tap], wk = wk0 + p.tap_wk[tap];
+            for (int c0 = 0; c0 < p.Cin; c0 += KCH) {
+              mbarrier_wait(&empty[stage], phase ^ 1);
+              unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+              // both CTAs' loads complete on the LEADER's barrier; only the leader arms it (bytes of the pair)
+              if (rank == 0) mbarrier_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+              tma_load_4d_2sm(sa, &maps.a[sg], &full[stage], c0, ax, ay, na);
+              tma_load_2d_2sm(sa + A_TILE_BYTES, &tmB, &full[stage], wk + c0, wrow);
+              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
         }
       }
     }
