@@ -229,10 +229,14 @@ def main():
             step.capture(resident, warmup=2)
 
         def run_resident():
-            # inputs resident in HBM; everything else of the step runs: image D2D into the graph's static buffer,
-            # target assignment (ldb200_ld_targets) on the resident gt boxes, the captured iteration
+            # inputs resident in HBM; everything else of the step runs every step: image move into the graph's static
+            # buffer, target assignment (ldb200_ld_targets) on the resident gt boxes -- both issued for the NEXT batch
+            # on the copy stream while the current iteration replays, as in the e2e path -- and the captured iteration
             if graph:
+                if getattr(step, '_staged', None) is not resident:
+                    step.prefetch(resident)
                 step.step_graphed(resident)
+                step.prefetch(resident)
             else:
                 step.step(resident, sync_logs=False)
 

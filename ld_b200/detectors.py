@@ -581,6 +581,10 @@ class LDTrainStep:
             self._copy_stream.wait_event(self._d2d_done)   # (NOT the whole replay that was enqueued after it)
         with torch.cuda.stream(self._copy_stream):
             self._staging_img.copy_(data['img'], non_blocking=True)
+            # target assignment of the NEXT batch too (it only needs the gt boxes): off the critical path of the replay
+            self._staged_targets = self.model.bbox_head.get_targets(
+                self._featmap_sizes(self._static_img.shape[2:]), data['img_metas'], data['gt_bboxes'], data['gt_labels'],
+                dev, static=False)
         self._staged = data
 
     def step_graphed(self, data=None):
@@ -589,18 +593,18 @@ class LDTrainStep:
             if getattr(self, '_staged', None) is data:
                 torch.cuda.current_stream().wait_stream(self._copy_stream)
                 self._static_img.copy_(self._staging_img, non_blocking=True)
+                tg = self._staged_targets
+                tg.flat.record_stream(torch.cuda.current_stream())
+                self._static_targets.flat.copy_(tg.flat, non_blocking=True)     # one copy: every field is a view of it
                 self._d2d_done = torch.cuda.Event()
                 self._d2d_done.record()
-                self._staged = None
+                self._staged = self._staged_targets = None
             else:
                 self._static_img.copy_(data['img'], non_blocking=True)
-            tg = self.model.bbox_head.get_targets(self._featmap_sizes(self._static_img.shape[2:]), data['img_metas'],
-                                                  data['gt_bboxes'], data['gt_labels'], self.flat_w.device,
-                                                  static=False)
-            st = self._static_targets
-            for name in ('labels', 'label_weights', 'bbox_targets', 'vlr', 'im', 'gt_inds', 'sparse_rows',
-                         'fg_rows', 'counts'):
-                getattr(st, name).copy_(getattr(tg, name))
+                tg = self.model.bbox_head.get_targets(self._featmap_sizes(self._static_img.shape[2:]), data['img_metas'],
+                                                      data['gt_bboxes'], data['gt_labels'], self.flat_w.device,
+                                                      static=False)
+                self._static_targets.flat.copy_(tg.flat, non_blocking=True)
         self._set_hyper()
         self._graph.replay()
         self.iter += 1

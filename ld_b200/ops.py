@@ -56,6 +56,7 @@ class LDTargets:
     sparse_rows: torch.Tensor    # [R] i32 (first counts[0] valid)
     fg_rows: torch.Tensor        # [R] i32 (first counts[1] valid)
     counts: torch.Tensor         # i32 [4 + 3*MAX_LEVELS]
+    flat: Optional[torch.Tensor] = None   # the one buffer all of the above are views of (a single copy moves a target set)
 
 
 def ld_targets(pyr: L.Pyramid, gt_bboxes: List[torch.Tensor], gt_labels: List[torch.Tensor],
@@ -77,12 +78,13 @@ def ld_targets(pyr: L.Pyramid, gt_bboxes: List[torch.Tensor], gt_labels: List[to
     meta = host.to(device, non_blocking=True)
     offsets, pad = meta[:n + 1], meta[n + 1:]
     R = pyr.rows
-    i32 = dict(dtype=torch.int32, device=device)
-    f32 = dict(dtype=torch.float32, device=device)
-    t = LDTargets(pyr, torch.empty(R, **i32), torch.empty(R, **f32), torch.empty(R, 4, **f32),
-                  torch.empty(R, **f32), torch.empty(R, **f32), torch.empty(R, **i32),
-                  torch.empty(R, **i32), torch.empty(R, **i32),
-                  torch.empty(4 + 3 * L.MAX_LEVELS, **i32))
+    # one allocation: [bbox_targets 4R | labels R | label_weights R | vlr R | im R | gt_inds R | sparse R | fg R | counts]
+    nc = 4 + 3 * L.MAX_LEVELS
+    flat = torch.empty(11 * R + nc, dtype=torch.int32, device=device)
+    seg = lambda i, k=1: flat[(3 + i) * R:(3 + i + k) * R]   # noqa: E731  (after the 4R bbox_targets block)
+    f = lambda v: v.view(torch.float32)                      # noqa: E731
+    t = LDTargets(pyr, seg(1), f(seg(2)), f(flat[:4 * R]).view(R, 4), f(seg(3)), f(seg(4)), seg(5), seg(6), seg(7),
+                  flat[11 * R:11 * R + nc], flat)
     ws = torch.empty(lib.ldb200_targets_workspace_bytes(C.byref(pyr), offs[-1]), dtype=torch.uint8,
                      device=device)
     L.check(lib.ldb200_ld_targets(C.byref(pyr), L.ptr(boxes), L.ptr(labs), L.ptr(offsets), offs[-1],
