@@ -53,14 +53,14 @@ def test_tower_layer_forward_backward(mode):
     # reference: torch autograd (fp64 in the fp32-accurate mode, fp32 on bf16-rounded operands otherwise)
     rt = torch.float64 if mode == 'fp32' else torch.float32
     rw = (wt if mode == 'fp32' else wt.bfloat16()).to(rt).requires_grad_(True)
-    rg, rb = gamma.to(rt).requires_grad_(True), beta.to(rt).requires_grad_(True)
-    rxs = [x.to(dt).to(rt).requires_grad_(True) for x in xs32]
+    rg, rb = gamma.detach().clone().to(rt).requires_grad_(True), beta.detach().clone().to(rt).requires_grad_(True)
+    rxs = [x.detach().clone().to(dt).to(rt).requires_grad_(True) for x in xs32]
     routs = _ref_layer(rxs, rw, rg, rb)
     sum((o * d.to(dt).to(rt)).sum() for o, d in zip(routs, dys32)).backward()
 
     w = wt.clone().contiguous(memory_format=torch.channels_last).requires_grad_(True)
-    ga, be = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
-    xs = [x.to(dt).requires_grad_(True) for x in xs32]
+    ga, be = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    xs = [x.detach().clone().to(dt).requires_grad_(True) for x in xs32]
     with engine.precision(mode):
         ys = engine.conv_gn_relu_levels(w, ga, be, xs)
         torch.autograd.backward(ys, [d.to(dt) for d in dys32])
