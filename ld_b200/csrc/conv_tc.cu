@@ -83,13 +83,20 @@ struct ConvParams {
   int planes, ncombo, w_plane;
   int comb_a[6], comb_w[6];
   int add_f32, mask_f32;    // residual / mask tensors are fp32 (fp32 activations of the split mode)
+  // flat 1x1 convs with wide input rows: the A operand arrives as 128-byte pieces of Cin*2-byte rows, one piece per
+  // k-block -- DRAM sees 128 scattered 128-byte reads per TMA box (ncu r02: 1x1 1024->256 at 25 % of HBM peak with
+  // exactly the algorithmic bytes).  a_pf: one tile AHEAD, the producer pulls the next tile's rows into L2 in
+  // 512-byte-per-row boxes (maps.ap), so DRAM sees long bursts and the operand loads hit L2.
+  int a_pf;
 };
 
 struct ConvMaps {           // per-segment TMA descriptors: A operand, residual prefetch, mask prefetch,
   CUtensorMap a[CONV_MAX_SEG], r[CONV_MAX_SEG], m[CONV_MAX_SEG];
   // TMA epilogue: output store, residual load, mask load (boxes of EPI_BOX_PIX pixels x 64 channels, SWIZZLE_128B)
   CUtensorMap o[CONV_MAX_SEG], rl[CONV_MAX_SEG], ml[CONV_MAX_SEG];
+  CUtensorMap ap[CONV_MAX_SEG];   // A-operand L2 prefetch: SWIZZLE_NONE boxes of APF_CH channels x 128 pixels (flat convs)
 };
+constexpr int APF_CH = 256;
 constexpr int EPI_BOX_PIX = 32;                       // one epilogue warp = 32 TMEM lanes = 32 output pixels
 constexpr int EPI_BOX_BYTES = EPI_BOX_PIX * 64 * 2;   // 4 KB staging buffer per epilogue warp
 
@@ -616,10 +623,19 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       TileCoord tc;
+      auto prefetch_a = [&](const TileCoord& t) {     // flat mode: pixel tile t.tx of segment t.sg, all channels
+        if (t.nt != 0) return;                        // the CTAs sharing a pixel tile: one of them prefetches
+        for (int c = 0; c < p.Cin; c += APF_CH) tma_prefetch_4d(&maps.ap[t.sg], c, t.tx * TILE_M, 0, 0);
+      };
+      if (p.a_pf && decode_tile(p, blockIdx.x, gridDim.x, 0, tc)) prefetch_a(tc);
       for (int i = 0; decode_tile(p, blockIdx.x, gridDim.x, i, tc); ++i) {
         const int sg = tc.sg, nt = tc.nt, tx = tc.tx, ty = tc.ty, n = tc.n;
         const ConvSeg& S = p.seg[sg];
         const int x0 = tx * S.TW * p.sx, y0 = ty * S.TH * p.sy;
+        if (p.a_pf) {
+          TileCoord nx;
+          if (decode_tile(p, blockIdx.x, gridDim.x, i + 1, nx)) prefetch_a(nx);
+        }
         // the epilogue will read this tile's residual / ReLU-mask rows a whole main loop from now: pull them into
         // L2 with one TMA prefetch each so those loads see L2 latency instead of HBM latency
         if (S.pf_add) tma_prefetch_4d(&maps.r[sg], nt * BN, tx * S.TW, ty * S.TH, n);
@@ -812,6 +828,12 @@ conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ C
       pdl_wait();   // inputs are produced by the previous kernel
       int stage = 0;
       uint32_t phase = 0;
+      auto prefetch_a = [&](int qq) {     // flat mode (one segment): this CTA's 128 pixels of pair qq, all channels
+        const int mtq = 2 * (qq % half_m) + (int)rank;
+        if (mtq >= mt_total) return;
+        for (int c = 0; c < p.Cin; c += APF_CH) tma_prefetch_4d(&maps.ap[0], c, mtq * TILE_M, 0, 0);
+      };
+      if (p.a_pf && (int)(blockIdx.x >> 1) < pairs) prefetch_a(blockIdx.x >> 1);
       for (int q = blockIdx.x >> 1; q < pairs; q += gridDim.x >> 1) {
         const int nt = q / half_m;
         const int mt = 2 * (q - nt * half_m) + (int)rank;
@@ -825,6 +847,7 @@ conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ C
         const int ty = sp % S.tiles_y;
         const int n = dummy ? S.N * p.planes : sp / S.tiles_y;   // image index beyond every plane: TMA zero-fills
         const int x0 = tx * S.TW * p.sx, y0 = ty * S.TH * p.sy;
+        if (p.a_pf && q + (int)(gridDim.x >> 1) < pairs) prefetch_a(q + (gridDim.x >> 1));
         // the epilogue will read this tile's residual / ReLU-mask rows a whole main loop from now: pull them into
         // L2 with one TMA prefetch each so those loads see L2 latency instead of HBM latency
         if (S.pf_add) tma_prefetch_4d(&maps.r[sg], nt * BN, tx * S.TW, ty * S.TH, n);
@@ -1405,7 +1428,8 @@ static int launch_conv2(const ConvMaps& maps, const CUtensorMap& tmB, const Conv
 
 // geometry + tensor maps of one segment
 static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& common, ConvSeg* g, CUtensorMap* tmA,
-                         CUtensorMap* tmR, CUtensorMap* tmM, CUtensorMap* tmO, CUtensorMap* tmRL, CUtensorMap* tmML) {
+                         CUtensorMap* tmR, CUtensorMap* tmM, CUtensorMap* tmO, CUtensorMap* tmRL, CUtensorMap* tmML,
+                         CUtensorMap* tmAP) {
   LDB_REQUIRE(d->in && d->out, LDB_EINVAL, "conv2d_tc: null pointer");
   LDB_REQUIRE(d->in_ld >= d->Cin && d->in_ld % 8 == 0, LDB_EINVAL, "conv2d_tc: in_ld must be >= Cin and a multiple of 8");
   LDB_REQUIRE(d->N >= 1 && d->HO >= 1 && d->WO >= 1, LDB_EINVAL, "conv2d_tc: shape");
@@ -1443,6 +1467,11 @@ static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& commo
     cuuint32_t box[4] = {KCH, TILE_M, 1, 1}, es[4] = {1, 1, 1, 1};
     int e = encode_map(tmA, d->in, 4, dims, strides, box, es, "A(flat)");
     if (e) return e;
+    if (tmAP) {
+      cuuint32_t pbox[4] = {(cuuint32_t)(d->Cin < APF_CH ? d->Cin : APF_CH), TILE_M, 1, 1};
+      e = encode_map(tmAP, d->in, 4, dims, strides, pbox, es, "A prefetch (flat)", CU_TENSOR_MAP_SWIZZLE_NONE);
+      if (e) return e;
+    }
   } else {
     int best_th = 8, best_tiles = 1 << 30;
     for (int th = 1; th <= TILE_M; th *= 2) {
@@ -1622,18 +1651,22 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
                                (d->add_W == 0 || d->add_W == (d->OW ? d->OW : d->WO));
     if (!same_size_add && !d->mask_src) p.tma_epi = 0;
   }
+  // A-operand L2 prefetch: flat 1x1 convs (single segment) whose input rows are at least 512 bytes wide
+  static const bool a_pf_env = getenv("LDB200_NO_A_PREFETCH") == nullptr;
+  p.a_pf = (a_pf_env && d->flat && count == 1 && !d->split && d->Cin >= 256 && d->in_ld % 8 == 0) ? 1 : 0;
   ConvMaps maps;
   int tile0 = 0;
   for (int i = 0; i < count; ++i) {
     int e = build_segment(&descs[i], BN, p, &p.seg[i], &maps.a[i], &maps.r[i], &maps.m[i], &maps.o[i], &maps.rl[i],
-                          &maps.ml[i]);
+                          &maps.ml[i], p.a_pf ? &maps.ap[i] : nullptr);
     if (e) return e;
+    if (!p.a_pf) maps.ap[i] = maps.a[i];
     p.seg_tile0[i] = tile0;
     tile0 += p.seg[i].N * p.seg[i].tiles_y * p.seg[i].tiles_x * p.tiles_n;
   }
   for (int i = count; i <= CONV_MAX_SEG; ++i) p.seg_tile0[i] = tile0;
   for (int i = count; i < CONV_MAX_SEG; ++i) {
-    maps.a[i] = maps.r[i] = maps.m[i] = maps.o[i] = maps.rl[i] = maps.ml[i] = maps.a[0];
+    maps.a[i] = maps.r[i] = maps.m[i] = maps.o[i] = maps.rl[i] = maps.ml[i] = maps.ap[i] = maps.a[0];
   }
   static const bool conv2_env = getenv("LDB200_NO_CONV2") == nullptr;   // 2-CTA kernel is the default for 256-wide tiles
   const bool use2 = conv2_env && !shortk && BN == 256 && d->Cout % 256 == 0;

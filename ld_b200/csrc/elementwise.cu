@@ -238,8 +238,29 @@ gn_apply_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ gamm
 // GroupNorm+ReLU backward, pass 1: per-(n,group) sums of dxh and dxh*xh, per-channel dgamma/dbeta.
 //   g = dy * (y > 0), xh = (x - mean)*rstd, dxh = g*gamma
 // red: [N, G, 2] fp32 accumulated; dgamma/dbeta: [C] fp32 accumulated.
-template <typename T>
-__global__ void __launch_bounds__(GN_THREADS)
+// y == null: the ReLU mask is recomputed from x (y > 0 <=> xh*gamma + beta > 0: bf16 / fp32 rounding of a positive value
+// stays positive), which saves reading y in both backward passes (14 -> 10 B / element).
+// Register diet (ncu r02: 120 registers, 2 blocks / SM, 28 % of HBM peak): three pixels in flight as raw vectors,
+// unpacked one at a time; <= 85 registers -> 3 blocks / SM.
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 q;
+  __device__ __forceinline__ void ld(const __nv_bfloat16* p) { q = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void get(float v[8]) const { unpack8(q, v); }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void ld(const float* p) {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void get(float v[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
+template <typename T, bool REMASK>
+__global__ void __launch_bounds__(GN_THREADS, 3)
 gn_bwd_stats_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, float eps) {
   const GnBlock B = gn_block(S);
@@ -254,15 +275,12 @@ gn_bwd_stats_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ 
   const float inv_m = 1.f / ((float)HW * GN_CPG);
   const float mean = __ldg(stats + ((size_t)n * G + g) * 2) * inv_m;
   const float rstd = rsqrtf(fmaxf(__ldg(stats + ((size_t)n * G + g) * 2 + 1) * inv_m - mean * mean, 0.f) + eps);
-  // y == null: the ReLU mask is recomputed from x (y > 0  <=>  x*a + b > 0 with the forward pass's a, b: bf16 / fp32
-  // rounding of a positive value stays positive), which saves reading y in both backward passes (14 -> 10 B / element)
-  const bool remask = (y == nullptr);
-  float gam[8], ma[8], mb[8], acc[18];
+  constexpr bool remask = REMASK;
+  float gam[8], bet[8], acc[18];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     gam[e] = __ldg(gamma + g * GN_CPG + e);
-    ma[e] = rstd * gam[e];
-    mb[e] = remask ? __ldg(beta + g * GN_CPG + e) - mean * ma[e] : 0.f;
+    bet[e] = remask ? __ldg(beta + g * GN_CPG + e) : 0.f;
   }
 #pragma unroll
   for (int e = 0; e < 18; ++e) acc[e] = 0.f;   // [0]=sum dxh, [1]=sum dxh*xh, [2..9]=dgamma, [10..17]=dbeta
@@ -270,24 +288,28 @@ gn_bwd_stats_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ 
   const T* pdy = dy + img;
   const T* py = remask ? nullptr : y + img;
   const T* px = x + img;
-  for (int p = p0 + r0; p < p1; p += 2 * lanes) {
-    const bool two = p + lanes < p1;
-    float q[6][8];
-    ld8<T>(pdy + (size_t)p * C, q[0]); ld8<T>(px + (size_t)p * C, q[2]);
-    if (!remask) ld8<T>(py + (size_t)p * C, q[1]);
-    if (two) {
-      ld8<T>(pdy + (size_t)(p + lanes) * C, q[3]); ld8<T>(px + (size_t)(p + lanes) * C, q[5]);
-      if (!remask) ld8<T>(py + (size_t)(p + lanes) * C, q[4]);
-    }
+  constexpr int U = 3;
+  for (int p = p0 + r0; p < p1; p += U * lanes) {
+    Raw8<T> rd[U], rx[U], ry[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 1 && !two) break;
-      const float *vd = q[3 * u], *vy = q[3 * u + 1], *vx = q[3 * u + 2];
+    for (int u = 0; u < U; ++u)
+      if (p + u * lanes < p1) {
+        rd[u].ld(pdy + (size_t)(p + u * lanes) * C);
+        rx[u].ld(px + (size_t)(p + u * lanes) * C);
+        if (!remask) ry[u].ld(py + (size_t)(p + u * lanes) * C);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p + u * lanes >= p1) break;
+      float vd[8], vx[8], vy[8];
+      rd[u].get(vd);
+      rx[u].get(vx);
+      if (!remask) ry[u].get(vy);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const bool on = remask ? (vx[e] * ma[e] + mb[e] > 0.f) : (vy[e] > 0.f);
-        const float gg = on ? vd[e] : 0.f;
         const float xh = (vx[e] - mean) * rstd;
+        const bool on = remask ? (xh * gam[e] + bet[e] > 0.f) : (vy[e] > 0.f);
+        const float gg = on ? vd[e] : 0.f;
         const float dxh = gg * gam[e];
         acc[0] += dxh;
         acc[1] += dxh * xh;
@@ -311,8 +333,8 @@ gn_bwd_stats_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ 
 }
 
 // pass 2: dx = rstd * (dxh - mean(dxh) - xh * mean(dxh*xh))
-template <typename T>
-__global__ void __launch_bounds__(GN_THREADS)
+template <typename T, bool REMASK>
+__global__ void __launch_bounds__(GN_THREADS, 3)
 gn_bwd_apply_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float eps) {
   const GnBlock B = gn_block(S);
@@ -329,38 +351,40 @@ gn_bwd_apply_kernel(const __grid_constant__ GnSegs S, const float* __restrict__ 
   const float mean = __ldg(stats + ((size_t)n * G + g) * 2) * inv_m;
   const float rstd = rsqrtf(fmaxf(__ldg(stats + ((size_t)n * G + g) * 2 + 1) * inv_m - mean * mean, 0.f) + eps);
   const float m1 = __ldg(red + ((size_t)n * G + g) * 2) * inv_m, m2 = __ldg(red + ((size_t)n * G + g) * 2 + 1) * inv_m;
-  const bool remask = (y == nullptr);
-  float gam[8], ma[8], mb[8];
+  constexpr bool remask = REMASK;
+  float gam[8], bet[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     gam[e] = __ldg(gamma + g * GN_CPG + e);
-    ma[e] = rstd * gam[e];
-    mb[e] = remask ? __ldg(beta + g * GN_CPG + e) - mean * ma[e] : 0.f;
+    bet[e] = remask ? __ldg(beta + g * GN_CPG + e) : 0.f;
   }
   const size_t img = (size_t)n * HW * C + g * 8;
   const T* pdy = dy + img;
   const T* py = remask ? nullptr : y + img;
   const T* px = x + img;
   T* pdx = dx + img;
-  for (int p = p0 + r0; p < p1; p += 2 * lanes) {
-    const bool two = p + lanes < p1;
-    float q[6][8];
-    ld8<T>(pdy + (size_t)p * C, q[0]); ld8<T>(px + (size_t)p * C, q[2]);
-    if (!remask) ld8<T>(py + (size_t)p * C, q[1]);
-    if (two) {
-      ld8<T>(pdy + (size_t)(p + lanes) * C, q[3]); ld8<T>(px + (size_t)(p + lanes) * C, q[5]);
-      if (!remask) ld8<T>(py + (size_t)(p + lanes) * C, q[4]);
-    }
+  constexpr int U = 3;
+  for (int p = p0 + r0; p < p1; p += U * lanes) {
+    Raw8<T> rd[U], rx[U], ry[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 1 && !two) break;
-      float* vd = q[3 * u];
-      const float *vy = q[3 * u + 1], *vx = q[3 * u + 2];
+    for (int u = 0; u < U; ++u)
+      if (p + u * lanes < p1) {
+        rd[u].ld(pdy + (size_t)(p + u * lanes) * C);
+        rx[u].ld(px + (size_t)(p + u * lanes) * C);
+        if (!remask) ry[u].ld(py + (size_t)(p + u * lanes) * C);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p + u * lanes >= p1) break;
+      float vd[8], vx[8], vy[8];
+      rd[u].get(vd);
+      rx[u].get(vx);
+      if (!remask) ry[u].get(vy);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const bool on = remask ? (vx[e] * ma[e] + mb[e] > 0.f) : (vy[e] > 0.f);
-        const float gg = on ? vd[e] : 0.f;
         const float xh = (vx[e] - mean) * rstd;
+        const bool on = remask ? (xh * gam[e] + bet[e] > 0.f) : (vy[e] > 0.f);
+        const float gg = on ? vd[e] : 0.f;
         vd[e] = rstd * (gg * gam[e] - m1 - xh * m2);
       }
       st8<T>(pdx + (size_t)(p + u * lanes) * C, vd);
@@ -734,15 +758,23 @@ extern "C" int ldb200_gn_relu_bwd_multi(const ldb_gn_seg* segs, int count, const
     // the per-segment scratch may be slices of one buffer the caller zeroed itself (red_zeroed)
     if (!segs[i].red_zeroed) LDB_CUDA(cudaMemsetAsync(segs[i].red_ws, 0, sizeof(float) * 2 * segs[i].N * G, s));
   }
+  // all segments read y, or none does (the mask is then recomputed from x)
+  bool remask = segs[0].y == nullptr;
+  for (int i = 1; i < count; ++i)
+    LDB_REQUIRE((segs[i].y == nullptr) == remask, LDB_EINVAL, "gn_relu_bwd: y must be given for all segments or for none");
+  const int grid = S.blk0[count];
+#define LDB_GN_BWD(T, R)                                                                               \
+  do {                                                                                                 \
+    gn_bwd_stats_kernel<T, R><<<grid, GN_THREADS, 0, s>>>(S, gamma, beta, dgamma, dbeta, eps);          \
+    LDB_CUDA(cudaGetLastError());                                                                      \
+    gn_bwd_apply_kernel<T, R><<<grid, GN_THREADS, 0, s>>>(S, gamma, beta, eps);                         \
+  } while (0)
   if (dtype == LDB_F32) {
-    gn_bwd_stats_kernel<float><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, beta, dgamma, dbeta, eps);
-    LDB_CUDA(cudaGetLastError());
-    gn_bwd_apply_kernel<float><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, beta, eps);
+    if (remask) LDB_GN_BWD(float, true); else LDB_GN_BWD(float, false);
   } else {
-    gn_bwd_stats_kernel<__nv_bfloat16><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, beta, dgamma, dbeta, eps);
-    LDB_CUDA(cudaGetLastError());
-    gn_bwd_apply_kernel<__nv_bfloat16><<<S.blk0[count], GN_THREADS, 0, s>>>(S, gamma, beta, eps);
+    if (remask) LDB_GN_BWD(__nv_bfloat16, true); else LDB_GN_BWD(__nv_bfloat16, false);
   }
+#undef LDB_GN_BWD
   LDB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -49,3 +49,43 @@ for rep in range(3):
         ops.conv2d_tc(x, w, 256, 3, 3, 1, 1, scale=sc, bias=sh, relu=True)
     torch.cuda.synchronize()
 print('done')
+
+# ---- plain timing (no profiler): python tools/hot_ops.py time
+if 'time' in sys.argv:
+    def t(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3
+    xs = [bf(n, h, w, 256) for h, w in sizes]
+    dys = [bf(*x.shape) for x in xs]
+    gamma, beta = torch.rand(256, device=dev) + 0.5, torch.randn(256, device=dev) * 0.1
+    stats = []
+    for x in xs:
+        r = x.float().reshape(n, -1, 32, 8)
+        stats.append(torch.stack([r.sum((1, 3)), (r * r).sum((1, 3))], -1).contiguous())
+    dg, db = torch.zeros(256, device=dev), torch.zeros(256, device=dev)
+    ys = ops.gn_apply_multi(xs, stats, gamma, beta)
+    el = sum(x.numel() for x in xs)
+    print(f'gn_apply_multi           {t(lambda: ops.gn_apply_multi(xs, stats, gamma, beta)):7.1f} us  (4 B/elem bound {el * 4 / 6568.7e3:6.1f})')
+    print(f'gn_relu_bwd_multi remask {t(lambda: ops.gn_relu_bwd_multi(dys, None, xs, stats, gamma, dg, db, beta=beta)):7.1f} us  (10 B/elem bound {el * 10 / 6568.7e3:6.1f})')
+    print(f'gn_relu_bwd_multi read y {t(lambda: ops.gn_relu_bwd_multi(dys, ys, xs, stats, gamma, dg, db)):7.1f} us  (14 B/elem bound {el * 14 / 6568.7e3:6.1f})')
+    for (cin, cout, hh, ww, res) in ((256, 1024, 50, 84, True), (1024, 256, 50, 84, False), (512, 128, 100, 168, False),
+                                     (128, 512, 100, 168, True), (2048, 512, 25, 42, False), (64, 256, 200, 336, True),
+                                     (512, 2048, 25, 42, True)):
+        x = bf(n, hh, ww, cin)
+        w = (torch.randn(cout, cin, device=dev, generator=g) * 0.05).bfloat16()
+        sc, sh = torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev)
+        r_ = bf(n, hh, ww, cout) if res else None
+        o = torch.empty(n, hh, ww, cout, device=dev, dtype=torch.bfloat16)
+        us = t(lambda: ops.conv2d_tc(x, w, cout, scale=sc, bias=sh, add=r_, relu=True, out=o))
+        byts = (x.numel() + o.numel() * (2 if res else 1)) * 2
+        fl = 2.0 * n * hh * ww * cin * cout
+        print(f'conv 1x1 {cin:4d}->{cout:4d} @{hh}x{ww}{" +res" if res else "     "} {us:7.1f} us  {byts / us / 1e3:6.0f} GB/s  {fl / us / 1e6:6.0f} TF/s  '
+              f'(bound {max(byts / 6568.7e3, fl / 1680.9e6):6.1f})')
