@@ -1652,7 +1652,9 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
     if (!same_size_add && !d->mask_src) p.tma_epi = 0;
   }
   // A-operand L2 prefetch: flat 1x1 convs (single segment) whose input rows are at least 512 bytes wide
-  static const bool a_pf_env = getenv("LDB200_NO_A_PREFETCH") == nullptr;
+  // (opt-in, LDB200_A_PREFETCH=1: measured 7-10 % SLOWER on the 1x1 convs of the LD step -- 1024->256 64.4 vs 58.8 us,
+  //  512->128 72.8 vs 66.9 us -- so the wide-row DRAM pattern is not what holds those launches back)
+  static const bool a_pf_env = getenv("LDB200_A_PREFETCH") != nullptr;
   p.a_pf = (a_pf_env && d->flat && count == 1 && !d->split && d->Cin >= 256 && d->in_ld % 8 == 0) ? 1 : 0;
   ConvMaps maps;
   int tile0 = 0;
