@@ -265,7 +265,9 @@ __device__ __forceinline__ bool decode_tile(const ConvParams& p, int b, int grid
 //     TMA store -- so global memory only sees full 128-byte lines instead of 32 scattered 16-byte accesses per
 //     warp instruction (the scattered form held the 1x1 "expand" convs at ~40 % of the HBM roofline).
 // Leaves the TMEM accumulator drained (caller signals tmem-empty).
-template <int BN, bool SHORTK, int EPI_GROUPS>
+// EXT selects the epilogue features compiled in (the plain bf16 hot path carries none of them):
+//   bit 0: GroupNorm statistics (S.gn_stats)      bit 1: fp32 extras of the split mode (pre_src, fp32 add / mask)
+template <int BN, bool SHORTK, int EPI_GROUPS, int EXT>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMaps& maps, const ConvSeg& S, int sg, int nt,
                                               int tx, int ty, int n, bool live, uint32_t tmem_acc, uint64_t* tfull_bar,
                                               uint32_t acc_phase, int ew, int half, int lane, unsigned char* ebuf,
@@ -282,7 +284,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
   if (S.add_src && pix_ok && !(tma && S.tl_add)) {
     const int ay = (int)(((long long)y * S.add_H) / S.HO), ax = (int)(((long long)x * S.add_W) / S.WO);
     const size_t aoff = (((size_t)n * S.add_H + ay) * S.add_W + ax) * (size_t)p.add_ld;
-    if (p.add_f32) addpf = (const float*)S.add_src + aoff;
+    if ((EXT & 2) && p.add_f32) addpf = (const float*)S.add_src + aoff;
     else addp = (const __nv_bfloat16*)S.add_src + aoff;
   }
   const int col0 = nt * BN + half * GCOLS;
@@ -351,7 +353,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (S.pre_src) {
+      if ((EXT & 2) && S.pre_src) {
         const float* pr = S.pre_src + pix * (size_t)p.ldc + cbase;
         if (full) {
 #pragma unroll
@@ -392,7 +394,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
               v[j + 2 * e + 1] += f.y;
             }
           }
-        } else if (addpf) {
+        } else if ((EXT & 2) && addpf) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 a4 = __ldg(reinterpret_cast<const float4*>(addpf + cbase + j));
@@ -443,7 +445,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (!((word >> j) & 1u)) v[j] = 0.f;
-        } else if (S.mask_src && p.mask_f32) {
+        } else if ((EXT & 2) && S.mask_src && p.mask_f32) {
           const float* mk = (const float*)S.mask_src + pix * (size_t)p.mask_ld + cbase;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -464,7 +466,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
               if (!(__bfloat162float(hb[e]) > 0.f)) v[j + e] = 0.f;
           }
         }
-        if (S.gn_stats) {
+        if ((EXT & 1) && S.gn_stats) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
 #pragma unroll
@@ -508,13 +510,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
           if (p.scale) vv *= __ldg(p.scale + c);
           if (p.bias) vv += __ldg(p.bias + c);
           if (addp) vv += __bfloat162float(addp[c]);
-          if (addpf) vv += addpf[c];
+          if ((EXT & 2) && addpf) vv += addpf[c];
           if (p.accumulate)
             vv += p.out_f32 ? ((const float*)S.out)[pix * (size_t)p.ldc + c]
                             : __bfloat162float(((const __nv_bfloat16*)S.out)[pix * (size_t)p.ldc + c]);
           if (p.relu) vv = fmaxf(vv, 0.f);
           if (S.mask_src) {
-            const float mv = p.mask_f32 ? ((const float*)S.mask_src)[pix * (size_t)p.mask_ld + c]
+            const float mv = ((EXT & 2) && p.mask_f32) ? ((const float*)S.mask_src)[pix * (size_t)p.mask_ld + c]
                                         : __bfloat162float(((const __nv_bfloat16*)S.mask_src)[pix * (size_t)p.mask_ld + c]);
             if (!(mv > 0.f)) vv = 0.f;
           }
@@ -523,7 +525,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
         }
       }
     }
-    if (S.gn_stats && live && cbase + 32 <= p.Cout) {   // warp-uniform
+    if ((EXT & 1) && S.gn_stats && live && cbase + 32 <= p.Cout) {   // warp-uniform
       // 8 partials x 32 pixels -> 8 sums with 9 shuffles: each step halves the values a lane carries (the half it
       // keeps is chosen by one lane bit), the last two steps are a plain butterfly; lanes with (lane & 3) == 0 end
       // up with value index bit4*4 + bit3*2 + bit2
@@ -569,7 +571,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
   __syncwarp();
 }
 
-template <int BN, bool SHORTK>
+template <int BN, bool SHORTK, int EXT>
 __global__ void __launch_bounds__(ConvCfg<BN, SHORTK>::THREADS, ConvCfg<BN, SHORTK>::MIN_BLOCKS)
 conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvParams p) {
@@ -704,7 +706,7 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
       const uint32_t acc_phase = (it >> 1) & 1;
       const int sg = tc.sg, nt = tc.nt, tx = tc.tx, ty = tc.ty, n = tc.n;
       const ConvSeg& S = p.seg[sg];
-      epilogue_tile<BN, SHORTK, Cfg::EPI_GROUPS>(p, maps, S, sg, nt, tx, ty, n, true, tmem_base + (uint32_t)(acc * BN),
+      epilogue_tile<BN, SHORTK, Cfg::EPI_GROUPS, EXT>(p, maps, S, sg, nt, tx, ty, n, true, tmem_base + (uint32_t)(acc * BN),
                                                  &tfull[acc], acc_phase, ew, half, lane, ebuf, rbar, rph);
       if (lane == 0) mbarrier_arrive(&tempty[acc]);
     }
@@ -767,6 +769,7 @@ __device__ __forceinline__ void mbarrier_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(s2u(bar) & PEER_MASK) : "memory");
 }
 
+template <int EXT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Conv2Cfg::THREADS, 1)
 conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvParams p) {
@@ -925,7 +928,7 @@ conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ C
       sp /= S.tiles_x;
       const int ty = sp % S.tiles_y;
       const int n = dummy ? S.N * p.planes : sp / S.tiles_y;   // image index beyond every plane: TMA zero-fills
-      epilogue_tile<BN, SHORTK, Cfg::EPI_GROUPS>(p, maps, S, sg, nt, tx, ty, n, !dummy, tmem_base + (uint32_t)(acc * BN),
+      epilogue_tile<BN, SHORTK, Cfg::EPI_GROUPS, EXT>(p, maps, S, sg, nt, tx, ty, n, !dummy, tmem_base + (uint32_t)(acc * BN),
                                                  &tfull[acc], acc_phase, ew, half, lane, ebuf, rbar, rph);
       if (lane == 0) mbarrier_arrive_leader(&tempty[acc]);
     }
@@ -1383,12 +1386,12 @@ static cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaSt
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-template <int BN, bool SHORTK>
-static int launch_conv(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+template <int BN, bool SHORTK, int EXT>
+static int launch_conv_ext(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, SHORTK>;
   static bool attr = false;
   if (!attr) {
-    LDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, SHORTK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    LDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, SHORTK, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr = true;
   }
   const int total = p.seg_tile0[p.nseg];
@@ -1399,31 +1402,45 @@ static int launch_conv(const ConvMaps& maps, const CUtensorMap& tmB, const ConvP
   static const bool nt_inner_env = getenv("LDB200_NT_INNER") != nullptr;
   q.nt_inner = (nt_inner_env && p.tiles_n > 1 && total / p.tiles_n >= slots) ? 1 : 0;
   const int grid = total < slots ? total : slots;
-  LDB_CUDA(launch_pdl(conv_tc_kernel<BN, SHORTK>, grid, Cfg::THREADS, Cfg::SMEM, stream, maps, tmB, q));
+  LDB_CUDA(launch_pdl(conv_tc_kernel<BN, SHORTK, EXT>, grid, Cfg::THREADS, Cfg::SMEM, stream, maps, tmB, q));
   return 0;
 }
 
+// ext: epilogue feature set (0 plain, 1 GroupNorm statistics, 3 statistics + fp32 extras of the split mode)
+template <int BN, bool SHORTK>
+static int launch_conv(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream, int ext) {
+  if (ext == 0) return launch_conv_ext<BN, SHORTK, 0>(maps, tmB, p, stream);
+  if (ext == 1) return launch_conv_ext<BN, SHORTK, 1>(maps, tmB, p, stream);
+  return launch_conv_ext<BN, SHORTK, 3>(maps, tmB, p, stream);
+}
+
 // 2-CTA kernel (default for Cout % 256 == 0 and more than 4 k-blocks; LDB200_NO_CONV2=1 falls back to the 1-CTA kernel): one cluster of two CTAs per pair-tile, grid = resident clusters
-static int launch_conv2(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
+template <int EXT>
+static int launch_conv2_ext(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
   static int max_clusters = 0;
   if (!max_clusters) {
-    LDB_CUDA(cudaFuncSetAttribute(conv2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Conv2Cfg::SMEM));
+    LDB_CUDA(cudaFuncSetAttribute(conv2_tc_kernel<EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Conv2Cfg::SMEM));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(g_conv_sms / 2 * 2);
     cfg.blockDim = dim3(Conv2Cfg::THREADS);
     cfg.dynamicSmemBytes = Conv2Cfg::SMEM;
     int n = 0;
-    LDB_CUDA(cudaOccupancyMaxActiveClusters(&n, conv2_tc_kernel, &cfg));
+    LDB_CUDA(cudaOccupancyMaxActiveClusters(&n, conv2_tc_kernel<EXT>, &cfg));
     LDB_REQUIRE(n >= 1, LDB_ENOSUP, "conv2d_tc: no resident 2-CTA cluster");
     max_clusters = n < g_conv_sms / 2 ? n : g_conv_sms / 2;
   }
   const int mt_total = p.seg_tile0[p.nseg] / p.tiles_n;
   const int pairs = p.tiles_n * ((mt_total + 1) / 2);
   const int clusters = pairs < max_clusters ? pairs : max_clusters;
-  conv2_tc_kernel<<<2 * clusters, Conv2Cfg::THREADS, Conv2Cfg::SMEM, stream>>>(maps, tmB, p);
+  conv2_tc_kernel<EXT><<<2 * clusters, Conv2Cfg::THREADS, Conv2Cfg::SMEM, stream>>>(maps, tmB, p);
   LDB_CUDA(cudaGetLastError());
   return 0;
+}
+static int launch_conv2(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream, int ext) {
+  if (ext == 0) return launch_conv2_ext<0>(maps, tmB, p, stream);
+  if (ext == 1) return launch_conv2_ext<1>(maps, tmB, p, stream);
+  return launch_conv2_ext<3>(maps, tmB, p, stream);
 }
 
 // geometry + tensor maps of one segment
@@ -1680,11 +1697,18 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
     int e = encode_map(&tmB, d->weight, 2, dims, strides, box, es, "B");
     if (e) return e;
   }
-  if (use2) return launch_conv2(maps, tmB, p, stream);
-  if (shortk) return BN == 128 ? launch_conv<128, true>(maps, tmB, p, stream) : launch_conv<64, true>(maps, tmB, p, stream);
-  if (BN == 256) return launch_conv<256, false>(maps, tmB, p, stream);
-  if (BN == 128) return launch_conv<128, false>(maps, tmB, p, stream);
-  return launch_conv<64, false>(maps, tmB, p, stream);
+  // epilogue feature set of this launch (compiled out of the plain bf16 path)
+  int ext = 0;
+  for (int i = 0; i < count; ++i) {
+    if (descs[i].gn_stats) ext |= 1;
+    if (descs[i].pre_src) ext |= 2;
+  }
+  if (d->add_f32 || d->mask_f32) ext |= 2;
+  if (use2) return launch_conv2(maps, tmB, p, stream, ext);
+  if (shortk) return BN == 128 ? launch_conv<128, true>(maps, tmB, p, stream, ext) : launch_conv<64, true>(maps, tmB, p, stream, ext);
+  if (BN == 256) return launch_conv<256, false>(maps, tmB, p, stream, ext);
+  if (BN == 128) return launch_conv<128, false>(maps, tmB, p, stream, ext);
+  return launch_conv<64, false>(maps, tmB, p, stream, ext);
 }
 
 extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {
