@@ -89,3 +89,29 @@ if 'time' in sys.argv:
         fl = 2.0 * n * hh * ww * cin * cout
         print(f'conv 1x1 {cin:4d}->{cout:4d} @{hh}x{ww}{" +res" if res else "     "} {us:7.1f} us  {byts / us / 1e3:6.0f} GB/s  {fl / us / 1e6:6.0f} TF/s  '
               f'(bound {max(byts / 6568.7e3, fl / 1680.9e6):6.1f})')
+
+# ---- stem routes: python tools/hot_ops.py stem
+if 'stem' in sys.argv:
+    def t(fn, reps=10):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3
+    img = torch.randn(n, 3, 800, 1344, device=dev, generator=g)
+    w2 = (torch.randn(128, 192, device=dev, generator=g) * 0.05).bfloat16()
+    w2[:, 147:] = 0
+    sc = [torch.rand(64, device=dev) + 0.5 for _ in range(2)]
+    sh = [torch.randn(64, device=dev) for _ in range(2)]
+    print(f'stem_im2col              {t(lambda: ops.stem_im2col(img)):8.1f} us')
+    a, ho, wo = ops.stem_im2col(img)
+    print(f'stem GEMM (one network)  {t(lambda: ops.conv2d_tc(a.view(1, 1, -1, 192), w2[:64].contiguous(), 64, scale=sc[0], bias=sh[0], relu=True)):8.1f} us')
+    print(f'fused stem, 2 networks   {t(lambda: ops.stem_tc(img, w2, [(sc[0], sh[0]), (sc[1], sh[1])])):8.1f} us')
+    print(f'fused stem, 1 network    {t(lambda: ops.stem_tc(img, w2[:64].contiguous(), [(sc[0], sh[0])])):8.1f} us')
+    y = ops.stem_tc(img, w2[:64].contiguous(), [(sc[0], sh[0])])[0]
+    print(f'maxpool                  {t(lambda: ops.maxpool3x3s2(y)):8.1f} us')
