@@ -31,8 +31,13 @@ constexpr int ST_A_BYTES = ST_KB * ST_A_KB_BYTES;    // 48 KB per stage
 constexpr int ST_STAGES = 2;
 constexpr int ST_B_KB_BYTES = 128 * 128;             // one k-block of B: up to 128 rows x 128 B
 constexpr int ST_B_BYTES = ST_KB * ST_B_KB_BYTES;    // 48 KB
-constexpr int ST_PRODUCERS = 128;
-constexpr int ST_THREADS = 128 + 32 + 128;           // producers, MMA warp, epilogue warps
+// ncu r02 (128 producers + 4 epilogue warps): 1.28 ms, 0.21 issued warps / scheduler with 2.25 active warps -- latency
+// of two long dependent instruction chains; DRAM traffic already the algorithmic 0.21 + 1.05 GB.  Twice the warps on
+// both sides: two threads build one operand row (even / odd 16-byte chunks), two warp groups drain the accumulator.
+constexpr int ST_PRODUCERS = 256;
+constexpr int ST_MMA_WARP = ST_PRODUCERS / 32;       // warp 8
+constexpr int ST_EPI_WARPS = 8;
+constexpr int ST_THREADS = ST_PRODUCERS + 32 + 32 * ST_EPI_WARPS;   // producers, MMA warp, epilogue warps
 constexpr size_t ST_SMEM = (size_t)ST_STAGES * ST_A_BYTES + ST_B_BYTES + 2 * ((ST_PATCH + 3) / 4 * 4) * sizeof(float) +
                            1024 + 256;
 
@@ -75,12 +80,12 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmB, const StemParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbarrier_init(&tfull[a], 1);
-      mbarrier_init(&tempty[a], 4);
+      mbarrier_init(&tempty[a], ST_EPI_WARPS);
     }
     mbarrier_init(bbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == ST_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "n"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -89,15 +94,18 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmB, const StemParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < ST_MMA_WARP) {
     // ===================================== producers: im2col into the UMMA layout ==========================
-    const int t = threadIdx.x;                 // = tile row: pixel (t / 16, t % 16)
+    const int tid = threadIdx.x;               // load_patch: all 256 threads
+    const int t = tid & 127;                   // = tile row: pixel (t / 16, t % 16)
+    const int part = tid >> 7;                 // this thread writes the 16-byte chunks grp with (grp & 1) == part
     const int ty = t >> 4, tx = t & 15;
     // the zero padding k = 147..191 never changes: chunks 19..23 of the last k-block, written once per stage
-    for (int s = 0; s < ST_STAGES; ++s) {
-      unsigned char* row = sA + (size_t)s * ST_A_BYTES + 2 * ST_A_KB_BYTES + t * 128;
-      for (int c = 3; c < 8; ++c) *reinterpret_cast<uint4*>(row + ((c ^ (t & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-    }
+    if (part == 0)
+      for (int s = 0; s < ST_STAGES; ++s) {
+        unsigned char* row = sA + (size_t)s * ST_A_BYTES + 2 * ST_A_KB_BYTES + t * 128;
+        for (int c = 3; c < 8; ++c) *reinterpret_cast<uint4*>(row + ((c ^ (t & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+      }
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -106,7 +114,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmB, const StemParams p) {
       const int r = tile / p.tiles_x;
       const int tyi = r % p.tiles_y, n = r / p.tiles_y;
       const int yi0 = tyi * ST_TH * 2 - 3, xi0 = txi * ST_TW * 2 - 3;
-      for (int i = t; i < ST_PATCH; i += ST_PRODUCERS) {
+      for (int i = tid; i < ST_PATCH; i += ST_PRODUCERS) {
         const int xx = i % ST_PW, rr = (i / ST_PW) % ST_PH, c = i / (ST_PW * ST_PH);
         const int y = yi0 + rr, x = xi0 + xx;
         float v = 0.f;
@@ -127,6 +135,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmB, const StemParams p) {
       const float* base = pt + (2 * ty) * ST_PW + 2 * tx;
 #pragma unroll
       for (int grp = 0; grp < 19; ++grp) {       // 19 chunks hold k = 0..151 (k >= 147 zero); constant offsets
+        if ((grp & 1) != part) continue;
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -145,7 +154,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmB, const StemParams p) {
       if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
       named_bar_sync(1, ST_PRODUCERS);            // patch double buffer hand-over
     }
-  } else if (warp == 4) {
+  } else if (warp == ST_MMA_WARP) {
     // ===================================== MMA issuer =====================================================
     if (lane == 0) {
       mbarrier_expect_tx(bbar, (uint32_t)ST_B_BYTES);
@@ -175,7 +184,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmB, const StemParams p) {
     }
   } else {
     // ===================================== epilogue: scale/shift + ReLU, NHWC bf16 rows ====================
-    const int ew = warp & 3;                    // TMEM lane quadrant of this warp (warps 5..8 -> 1,2,3,0)
+    const int ew = warp & 3;                    // TMEM lane quadrant of this warp (warps 9..16 -> 1,2,3,0,1,2,3,0)
+    const int grp_e = (warp - ST_MMA_WARP - 1) >> 2;   // warp group 0 / 1: the 32-column half of every network it drains
     const int m = ew * 32 + lane;               // tile row
     int it = 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
@@ -190,8 +200,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmB, const StemParams p) {
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * 128);
       for (int net = 0; net < p.nets; ++net) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {
+          const int half = grp_e;
           uint32_t rr[32];
           tmem_ld32(tbase + net * 64 + half * 32, rr);
           if (ok) {
@@ -200,12 +210,16 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmB, const StemParams p) {
             const float* sh = p.shift[net] + half * 32;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + j)), s1 = __ldg(reinterpret_cast<const float4*>(sc + j + 4));
+              const float4 h0 = __ldg(reinterpret_cast<const float4*>(sh + j)), h1 = __ldg(reinterpret_cast<const float4*>(sh + j + 4));
+              const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
               uint4 q;
               __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float v0 = fmaxf(__uint_as_float(rr[j + 2 * e]) * __ldg(sc + j + 2 * e) + __ldg(sh + j + 2 * e), 0.f);
-                const float v1 = fmaxf(__uint_as_float(rr[j + 2 * e + 1]) * __ldg(sc + j + 2 * e + 1) + __ldg(sh + j + 2 * e + 1), 0.f);
+                const float v0 = fmaxf(__uint_as_float(rr[j + 2 * e]) * sv[2 * e] + hv[2 * e], 0.f);
+                const float v1 = fmaxf(__uint_as_float(rr[j + 2 * e + 1]) * sv[2 * e + 1] + hv[2 * e + 1], 0.f);
                 h[e] = __floats2bfloat162_rn(v0, v1);
               }
               *reinterpret_cast<uint4*>(o + j) = q;
@@ -220,7 +234,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmB, const StemParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == ST_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
   }
@@ -255,6 +269,8 @@ extern "C" int ldb200_stem_tc(const float* img, int N, int H, int W, const void*
   LDB_REQUIRE(N >= 1 && H >= 1 && W >= 1, LDB_EINVAL, "stem_tc: shape");
   LDB_REQUIRE(((uintptr_t)weights & 15) == 0 && ((uintptr_t)out0 & 15) == 0 && (!out1 || ((uintptr_t)out1 & 15) == 0),
               LDB_EINVAL, "stem_tc: weights / outputs must be 16-byte aligned");
+  LDB_REQUIRE((((uintptr_t)scale0 | (uintptr_t)shift0 | (uintptr_t)scale1 | (uintptr_t)shift1) & 15) == 0, LDB_EINVAL,
+              "stem_tc: scale / shift must be 16-byte aligned");
   StemParams p;
   memset(&p, 0, sizeof(p));
   p.img = img; p.N = N; p.H = H; p.W = W;
