@@ -178,7 +178,7 @@ def test_ldv2_step_vs_golden(golden_dir):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# fused dual stem (ldb200_stem_tc, opt-in LDB200_FUSED_STEM=1) against the im2col + GEMM route.
+# fused dual stem (ldb200_stem_tc, the default; LDB200_NO_FUSED_STEM=1 = im2col + GEMM route) against that route.
 # Unlike the kernels above this one synchronises warps through mbarriers: a first-run bug could spin forever -- keep
 # the `timeout` in front of pytest.
 @pytest.mark.parametrize('shape', [(2, 128, 160), (1, 97, 131), (3, 64, 64)])
@@ -217,9 +217,9 @@ def test_fused_stem_train_step_equals_default(monkeypatch):
     b = synth.make_batch(2, 128, 160, seed=77)
     data = dict(img=b['img'].cuda(), img_metas=b['img_metas'], gt_bboxes=[x.cuda() for x in b['gt_bboxes']],
                 gt_labels=[x.cuda() for x in b['gt_labels']])
-    _, log0 = m._parse_losses(m(**data))
-    monkeypatch.setenv('LDB200_FUSED_STEM', '1')
-    _, log1 = m._parse_losses(m(**data))
+    _, log1 = m._parse_losses(m(**data))              # default: fused dual stem
+    monkeypatch.setenv('LDB200_NO_FUSED_STEM', '1')
+    _, log0 = m._parse_losses(m(**data))              # im2col + GEMM route
     for k, v in log0.items():
         assert abs(log1[k] - v) <= 2e-2 * abs(v) + 1e-3, (k, log1[k], v)
 

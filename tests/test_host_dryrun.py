@@ -89,18 +89,19 @@ def test_ld_train_step_host_logic(fake_backend, imitation, im_weight):
     _check_grads(m)
     assert ('ldb200_gi_region' in fake_backend) == (imitation == 'gibox' and im_weight != 0)
     for name in ('ldb200_ld_targets', 'ldb200_ld_loss_prepass', 'ldb200_ld_loss_fused', 'ldb200_conv2d_wgrad_tc',
-                 'ldb200_stem_im2col'):
+                 'ldb200_stem_tc'):
         assert name in fake_backend, name
-    assert 'ldb200_stem_tc' not in fake_backend and not any(n.endswith('_v2') for n in fake_backend)
+    assert 'ldb200_stem_im2col' not in fake_backend and not any(n.endswith('_v2') for n in fake_backend)
 
 
-def test_ld_train_step_fused_stem_host_logic(fake_backend, monkeypatch):
-    monkeypatch.setenv('LDB200_FUSED_STEM', '1')
+def test_ld_train_step_im2col_stem_host_logic(fake_backend, monkeypatch):
+    """The fused dual stem is the default; LDB200_NO_FUSED_STEM=1 selects the im2col + GEMM route."""
+    monkeypatch.setenv('LDB200_NO_FUSED_STEM', '1')
     m = ld_b200.build_detector(ConfigDict(presets.ld_model('r18', teacher_depth=18))).train()
     loss, _ = m._parse_losses(m(**_batch()))
     loss.backward()
     _check_grads(m)
-    assert fake_backend.count('ldb200_stem_tc') == 1 and 'ldb200_stem_im2col' not in fake_backend
+    assert fake_backend.count('ldb200_stem_im2col') == 1 and 'ldb200_stem_tc' not in fake_backend
 
 
 def test_flat_sgd_step_host_logic(fake_backend):
