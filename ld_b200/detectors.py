@@ -368,28 +368,42 @@ class LDTrainStep:
             self._hook_handle = self.model.neck.register_forward_hook(self._neck_forward_hook)
 
     def _neck_forward_hook(self, module, inputs, outputs):
-        """Tensor hooks at the stage boundaries of THIS forward pass: the gradient of a stage's input is complete only
-        after every backward node of the later stages (and their parameter-gradient kernels) has been issued."""
-        if not (self._in_step and torch.is_grad_enabled()):
-            return
-        feats = inputs[0]
-        marks = [(list(outputs), 'bbox_head.')]
-        if len(feats) >= 1:
-            marks.append(([feats[-1]], 'neck.'))
-        if len(feats) >= 2:
-            marks.append(([feats[-2]], 'backbone.layer4.'))
-        if len(feats) >= 3:
-            marks.append(([feats[-3]], 'backbone.layer3.'))
-        for tensors, seg in marks:
-            for t in tensors:
-                if isinstance(t, torch.Tensor) and t.requires_grad:
-                    t.register_hook(self._make_grad_hook(seg))
+        """Remember the stage-boundary tensors of THIS forward pass (backbone outputs, FPN outputs)."""
+        if self._in_step and torch.is_grad_enabled():
+            self._stage = dict(fpn=list(outputs), feats=list(inputs[0]))
 
-    def _make_grad_hook(self, seg):
-        def hook(grad):
-            self._reduce_span(seg)
-            return None
-        return hook
+    def _backward(self, loss):
+        """`loss.backward()`, or -- data-parallel with the overlapped exchange -- the same backward pass cut at the stage
+        boundaries (loss -> FPN outputs -> backbone outputs C5 -> C4 -> C3 -> rest): after each piece the segment of
+        the flat gradient buffer it completed goes to the communication stream, while the next piece computes.  All
+        from the calling thread (so it captures into a CUDA graph like the rest of the iteration); the gradients are the
+        ones a single backward call produces (the cuts only order the work)."""
+        st = getattr(self, '_stage', None)
+        if not (self.world > 1 and self.overlap and st is not None):
+            loss.backward()
+            return
+        self._stage = None
+        named = [(k, p) for k, p in self.model.named_parameters() if p.requires_grad]
+        seg_params = {pre: [p for k, p in named if k.startswith(pre)] for pre in self.SEGMENT_PREFIXES}
+        rest = [p for k, p in named if not k.startswith(self.SEGMENT_PREFIXES)]
+        fpn = [t for t in st['fpn'] if t.requires_grad]
+        feats = [t for t in st['feats'] if t.requires_grad][::-1]            # C5, C4, C3
+        torch.autograd.backward(loss, inputs=fpn + seg_params['bbox_head.'])
+        self._reduce_span('bbox_head.')
+        torch.autograd.backward(fpn, [t.grad for t in fpn], inputs=feats + seg_params['neck.'])
+        self._reduce_span('neck.')
+        cur = 0
+        for name in ('backbone.layer4.', 'backbone.layer3.'):
+            if cur + 1 >= len(feats):
+                break
+            torch.autograd.backward([feats[cur]], [feats[cur].grad], inputs=[feats[cur + 1]] + seg_params[name])
+            self._reduce_span(name)
+            cur += 1
+        tail = rest + [p for name in self.SEGMENT_PREFIXES[2 + cur:] for p in seg_params[name]]
+        if tail and feats:
+            torch.autograd.backward([feats[cur]], [feats[cur].grad], inputs=tail)
+        for t in fpn + feats:
+            t.grad = None
 
     def _comm(self):
         st = self.__dict__.get('_comm_stream')
@@ -401,7 +415,7 @@ class LDTrainStep:
     def _reduce_span(self, seg):
         """All-reduce one segment of flat_g on the communication stream, after everything issued so far on the compute
         streams (main + the head's regression-tower stream)."""
-        if seg in self._done or seg not in self._segments:
+        if self.world == 1 or seg in self._done or seg not in self._segments:
             return
         self._done.add(seg)
         a, b = self._segments[seg]
@@ -485,7 +499,7 @@ class LDTrainStep:
         else:
             loss = sum(sum(v) for k, v in losses.items() if 'loss' in k)
             log_vars = None
-        loss.backward()
+        self._backward(loss)
         engine.zero_pool_end()
         self._finish_exchange()
         ops.sgd_flat(self.flat_w, self.flat_g, self.flat_m, self.lr_at(self.iter), self.momentum, self.wd,
@@ -507,7 +521,7 @@ class LDTrainStep:
         losses = self.model(**data)
         terms = torch.stack([sum(v) for v in losses.values()])
         loss = terms.sum()
-        loss.backward()
+        self._backward(loss)
         engine.zero_pool_end()
         self._finish_exchange()
         ops.sgd_flat_dev(self.flat_w, self.flat_g, self.flat_m, self._hyper)

@@ -1,0 +1,84 @@
+"""Debug (2 GPUs): the overlapped gradient exchange of LDTrainStep, eager then captured, with a watchdog that dumps
+every thread's stack if an iteration does not finish.
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/debug/overlap_n2.py"""
+import faulthandler
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+os.environ.setdefault('LDB200_ALLOW_RANDOM_INIT', '1')
+import torch
+import torch.distributed as dist
+
+import ld_b200
+from ld_b200 import presets, synth
+from ld_b200.config import ConfigDict
+
+rank, local = int(os.environ['RANK']), int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(local)
+dev = torch.device('cuda', local)
+dist.init_process_group('nccl', device_id=dev)
+faulthandler.dump_traceback_later(50, exit=True)
+m = ld_b200.build_detector(ConfigDict(presets.ld_model('r18', teacher_depth=18)))
+synth.seeded_init(m, 0)
+synth.seeded_init(m.teacher_model, 1, prefix='teacher.')
+m = m.to(dev).train()
+ref = ld_b200.build_detector(ConfigDict(presets.ld_model('r18', teacher_depth=18)))
+synth.seeded_init(ref, 0)
+synth.seeded_init(ref.teacher_model, 1, prefix='teacher.')
+ref = ref.to(dev).train()
+
+
+def batch(seed):
+    b = synth.make_batch(2, 256, 320, seed=seed + 10 * rank)
+    return dict(img=b['img'].to(dev), img_metas=b['img_metas'], gt_bboxes=[x.to(dev) for x in b['gt_bboxes']],
+                gt_labels=[x.to(dev) for x in b['gt_labels']])
+
+
+os.environ['LDB200_NO_AR_OVERLAP'] = '1'
+ts_ref = ld_b200.LDTrainStep(ref, lr=0.001, warmup_iters=0)
+del os.environ['LDB200_NO_AR_OVERLAP']
+ts = ld_b200.LDTrainStep(m, lr=0.001, warmup_iters=0)
+assert ts._hook_handle is not None and ts_ref._hook_handle is None
+# which segment differs?  one step with lr = 0 on both, then the reduced gradients segment by segment
+ts.base_lr = ts_ref.base_lr = 0.0
+d = batch(100)
+ts_ref.step(d, sync_logs=False)
+ts.step(d, sync_logs=False)
+torch.cuda.synchronize()
+segs = dict(ts._segments)
+segs['rest'] = (0, min(a for a, b in ts._segments.values()))
+for k, (a, b) in sorted(segs.items(), key=lambda kv: kv[1]):
+    g0, g1 = ts_ref.flat_g[a:b], ts.flat_g[a:b]
+    print(f'[{rank}] segment {k:18s} [{a}, {b}): rel err {float((g1 - g0).norm() / (g0.norm() + 1e-30)):.3e}  '
+          f'ratio of norms {float(g1.norm() / (g0.norm() + 1e-30)):.4f}', flush=True)
+# the same two steps again without any exchange-order difference: run-to-run noise of the atomics
+ts_ref.step(d, sync_logs=False)
+g_a = ts_ref.flat_g.clone()
+ts_ref.step(d, sync_logs=False)
+torch.cuda.synchronize()
+print(f'[{rank}] reference vs itself: rel err {float((ts_ref.flat_g - g_a).norm() / g_a.norm()):.3e}', flush=True)
+ts.base_lr = ts_ref.base_lr = 0.001
+ts.iter = ts_ref.iter = 0
+for it in range(3):
+    d = batch(it)
+    l0, _ = ts_ref.step(d, sync_logs=False)
+    print(f'[{rank}] eager reference step {it} issued', flush=True)
+    l1, _ = ts.step(d, sync_logs=False)
+    torch.cuda.synchronize()
+    print(f'[{rank}] eager overlap step {it}: loss {float(l1):.5f} vs {float(l0):.5f}, spans {ts._reduced}', flush=True)
+err = float((ts.flat_w - ts_ref.flat_w).abs().max())
+print(f'[{rank}] eager: max |w - w_ref| = {err:.3e}', flush=True)
+assert err <= 5e-2      # bf16 step: fp32 atomics make two runs of the SAME step differ by ~3e-4
+faulthandler.cancel_dump_traceback_later()
+faulthandler.dump_traceback_later(60, exit=True)
+ts.capture(batch(7), warmup=1)
+print(f'[{rank}] captured', flush=True)
+for it in range(3):
+    l = ts.step_graphed(batch(20 + it))
+    torch.cuda.synchronize()
+    print(f'[{rank}] graphed step {it}: loss {float(l):.5f}', flush=True)
+faulthandler.cancel_dump_traceback_later()
+dist.barrier()
+print(f'[{rank}] done', flush=True)
+os._exit(0)

@@ -192,6 +192,7 @@ def test_overlapped_gradient_exchange_covers_flat_buffer_once(fake_backend, monk
     orig = ts._reduce_span
     monkeypatch.setattr(ts, '_reduce_span', lambda seg: (order.append(seg), orig(seg))[1])
     ts.step(_batch(), sync_logs=False)
+    _check_grads(m)
     base, es = ts.flat_g.data_ptr(), ts.flat_g.element_size()
     spans = sorted(((p - base) // es, (p - base) // es + n) for p, n in calls if n > 8)    # (8-byte normaliser excluded)
     assert spans[0][0] == 0 and spans[-1][1] == ts.flat_g.numel()
