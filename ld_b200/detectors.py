@@ -390,20 +390,29 @@ class LDTrainStep:
         feats = [t for t in st['feats'] if t.requires_grad][::-1]            # C5, C4, C3
         torch.autograd.backward(loss, inputs=fpn + seg_params['bbox_head.'])
         self._reduce_span('bbox_head.')
-        torch.autograd.backward(fpn, [t.grad for t in fpn], inputs=feats + seg_params['neck.'])
+        g_fpn = [t.grad for t in fpn]
+        for t in fpn:
+            t.grad = None
+        torch.autograd.backward(fpn, g_fpn, inputs=feats + seg_params['neck.'])
         self._reduce_span('neck.')
+        # a non-leaf tensor listed in `inputs` gets the gradient of THAT call assigned to .grad (not accumulated): the
+        # lateral-conv part of a backbone output's gradient and the part coming down the backbone are summed here
+        part = [t.grad for t in feats]           # gradients through the FPN laterals (complete for C5)
+        for t in feats:
+            t.grad = None
+        g = part[0] if feats else None
         cur = 0
         for name in ('backbone.layer4.', 'backbone.layer3.'):
             if cur + 1 >= len(feats):
                 break
-            torch.autograd.backward([feats[cur]], [feats[cur].grad], inputs=[feats[cur + 1]] + seg_params[name])
+            torch.autograd.backward([feats[cur]], [g], inputs=[feats[cur + 1]] + seg_params[name])
             self._reduce_span(name)
             cur += 1
+            g = part[cur] + feats[cur].grad
+            feats[cur].grad = None
         tail = rest + [p for name in self.SEGMENT_PREFIXES[2 + cur:] for p in seg_params[name]]
         if tail and feats:
-            torch.autograd.backward([feats[cur]], [feats[cur].grad], inputs=tail)
-        for t in fpn + feats:
-            t.grad = None
+            torch.autograd.backward([feats[cur]], [g], inputs=tail)
 
     def _comm(self):
         st = self.__dict__.get('_comm_stream')
