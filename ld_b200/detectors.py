@@ -387,13 +387,16 @@ class LDTrainStep:
         seg_params = {pre: [p for k, p in named if k.startswith(pre)] for pre in self.SEGMENT_PREFIXES}
         rest = [p for k, p in named if not k.startswith(self.SEGMENT_PREFIXES)]
         fpn = [t for t in st['fpn'] if t.requires_grad]
-        feats = [t for t in st['feats'] if t.requires_grad][::-1]            # C5, C4, C3
-        torch.autograd.backward(loss, inputs=fpn + seg_params['bbox_head.'])
+        # the backbone hands the neck NCHW-shaped VIEWS of its stage outputs and feeds the stage outputs themselves to
+        # the next stage: the cut is at the base tensor, where both gradient paths meet
+        feats = [(t._base if t._is_view() else t) for t in st['feats'] if t.requires_grad][::-1]   # C5, C4, C3
+        # (retain_graph: without it the engine also releases the saved tensors of the nodes BELOW the cut)
+        torch.autograd.backward(loss, inputs=fpn + seg_params['bbox_head.'], retain_graph=True)
         self._reduce_span('bbox_head.')
         g_fpn = [t.grad for t in fpn]
         for t in fpn:
             t.grad = None
-        torch.autograd.backward(fpn, g_fpn, inputs=feats + seg_params['neck.'])
+        torch.autograd.backward(fpn, g_fpn, inputs=feats + seg_params['neck.'], retain_graph=True)
         self._reduce_span('neck.')
         # a non-leaf tensor listed in `inputs` gets the gradient of THAT call assigned to .grad (not accumulated): the
         # lateral-conv part of a backbone output's gradient and the part coming down the backbone are summed here
@@ -405,7 +408,7 @@ class LDTrainStep:
         for name in ('backbone.layer4.', 'backbone.layer3.'):
             if cur + 1 >= len(feats):
                 break
-            torch.autograd.backward([feats[cur]], [g], inputs=[feats[cur + 1]] + seg_params[name])
+            torch.autograd.backward([feats[cur]], [g], inputs=[feats[cur + 1]] + seg_params[name], retain_graph=True)
             self._reduce_span(name)
             cur += 1
             g = part[cur] + feats[cur].grad
