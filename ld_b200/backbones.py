@@ -291,17 +291,26 @@ class ResNet(nn.Module):
         s, b = engine.bn_affine(self.bn1)
         return wp, (s.detach(), b.detach())
 
+    cut_stages = False     # set by LDTrainStep when it runs the backward pass in pieces (overlapped gradient exchange)
+
     def forward(self, x, im2col=None, stem_out=None):
         """stem_out: conv1+BN+ReLU output [N,HO,WO,64] bf16 already computed by the fused stem kernel (opt-in)."""
         if any(p.requires_grad for p in (self.conv1.weight, self.bn1.weight)):
             raise NotImplementedError('the stem runs forward-only (frozen_stages >= 0 in every LD/GFL config)')
         with torch.no_grad():
             y = ops.maxpool3x3s2(stem_out) if stem_out is not None else self.stem(x, im2col)
-        outs = []
+        outs, cuts = [], []
         for i, name in enumerate(self.res_layers):
             y = getattr(self, name)(y)
             if i in self.out_indices:
                 outs.append(nchw_view(y))
+            if self.cut_stages and y.requires_grad and i + 1 < len(self.res_layers):
+                # the next stage reads an ALIAS of this stage's output: a node whose backward does nothing, i.e. a place
+                # where LDTrainStep can cut the backward pass (`torch.autograd.backward(inputs=[t])` also runs the
+                # node that produced t)
+                y = y.view_as(y)
+                cuts.append(y)
+        self._cuts = cuts          # inputs of the trainable stages after the first, in forward order
         return tuple(outs)
 
 

@@ -369,53 +369,76 @@ class LDTrainStep:
 
     def _neck_forward_hook(self, module, inputs, outputs):
         """Remember the stage-boundary tensors of THIS forward pass (backbone outputs, FPN outputs)."""
-        if self._in_step and torch.is_grad_enabled():
+        if self._in_step and torch.is_grad_enabled() and self._staged_now():
             self._stage = dict(fpn=list(outputs), feats=list(inputs[0]))
 
     def _backward(self, loss):
         """`loss.backward()`, or -- data-parallel with the overlapped exchange -- the same backward pass cut at the stage
         boundaries (loss -> FPN outputs -> backbone outputs C5 -> C4 -> C3 -> rest): after each piece the segment of
         the flat gradient buffer it completed goes to the communication stream, while the next piece computes.  All
-        from the calling thread (so it captures into a CUDA graph like the rest of the iteration); the gradients are the
-        ones a single backward call produces (the cuts only order the work)."""
+        from the calling thread; the gradients are the ones a single backward call produces (the cuts only order the
+        work; tests/test_gpu_staged_backward.py)."""
         st = getattr(self, '_stage', None)
-        if not (self.world > 1 and self.overlap and st is not None):
+        if not (self._staged_now() and st is not None):
             loss.backward()
             return
+        log = getattr(self, '_cut_log', None)      # debugging aid: the gradients at the cuts
         self._stage = None
         named = [(k, p) for k, p in self.model.named_parameters() if p.requires_grad]
         seg_params = {pre: [p for k, p in named if k.startswith(pre)] for pre in self.SEGMENT_PREFIXES}
         rest = [p for k, p in named if not k.startswith(self.SEGMENT_PREFIXES)]
         fpn = [t for t in st['fpn'] if t.requires_grad]
-        # the backbone hands the neck NCHW-shaped VIEWS of its stage outputs and feeds the stage outputs themselves to
-        # the next stage: the cut is at the base tensor, where both gradient paths meet
-        feats = [(t._base if t._is_view() else t) for t in st['feats'] if t.requires_grad][::-1]   # C5, C4, C3
+        # Where to cut: `torch.autograd.backward(inputs=[t])` also RUNS the node that produced t, so every cut tensor
+        # must come out of a node whose backward does no work: the NCHW permute views the backbone hands the neck
+        # (their gradient is the part that arrives through the FPN laterals) and the aliases of the stage outputs the
+        # backbone feeds its next stage (`ResNet._cuts`; their gradient is the part that comes down the backbone).
+        views = [t for t in st['feats'] if t.requires_grad][::-1]             # C5, C4, C3 as the neck saw them
+        cuts = list(getattr(self.model.backbone, '_cuts', ()))[::-1]          # inputs of layer4, layer3, ...
+        self.model.backbone._cuts = []
+        aligned = bool(views) and all(v._is_view() for v in views) and len(cuts) >= len(views) - 1 and \
+            all(views[k + 1].data_ptr() == cuts[k].data_ptr() for k in range(len(views) - 1))
+        if not aligned:            # another backbone / out_indices: one piece
+            loss.backward()
+            return
         # (retain_graph: without it the engine also releases the saved tensors of the nodes BELOW the cut)
         torch.autograd.backward(loss, inputs=fpn + seg_params['bbox_head.'], retain_graph=True)
         self._reduce_span('bbox_head.')
         g_fpn = [t.grad for t in fpn]
         for t in fpn:
             t.grad = None
-        torch.autograd.backward(fpn, g_fpn, inputs=feats + seg_params['neck.'], retain_graph=True)
+        torch.autograd.backward(fpn, g_fpn, inputs=views + seg_params['neck.'], retain_graph=True)
         self._reduce_span('neck.')
-        # a non-leaf tensor listed in `inputs` gets the gradient of THAT call assigned to .grad (not accumulated): the
-        # lateral-conv part of a backbone output's gradient and the part coming down the backbone are summed here
-        part = [t.grad for t in feats]           # gradients through the FPN laterals (complete for C5)
-        for t in feats:
+        lateral = [t.grad for t in views]
+        for t in views:
             t.grad = None
-        g = part[0] if feats else None
+        if log is not None:
+            log.update({f'lateral{k}': v.clone() for k, v in enumerate(lateral) if v is not None})
+        root, g = views[0], lateral[0]
         cur = 0
         for name in ('backbone.layer4.', 'backbone.layer3.'):
-            if cur + 1 >= len(feats):
+            if cur + 1 >= len(views):
                 break
-            torch.autograd.backward([feats[cur]], [g], inputs=[feats[cur + 1]] + seg_params[name], retain_graph=True)
+            c = cuts[cur]
+            torch.autograd.backward([root], [g], inputs=[c] + seg_params[name], retain_graph=True)
             self._reduce_span(name)
             cur += 1
-            g = part[cur] + feats[cur].grad
-            feats[cur].grad = None
+            if log is not None:
+                log[f'through{cur}'] = c.grad.clone()
+            # gradient w.r.t. the view -> layout of the stage output it permutes
+            root, g = c, lateral[cur].permute(0, 2, 3, 1) + c.grad
+            c.grad = None
         tail = rest + [p for name in self.SEGMENT_PREFIXES[2 + cur:] for p in seg_params[name]]
-        if tail and feats:
-            torch.autograd.backward([feats[cur]], [g], inputs=tail)
+        if tail:
+            torch.autograd.backward([root], [g], inputs=tail)
+
+    def _staged_now(self):
+        """Backward in pieces with the exchange overlapped?  Data parallel, overlap not disabled, and not inside
+        `capture()`: replayed from a CUDA graph the segment exchanges on the communication stream gave wrong sums on
+        2 GPUs (eager: validated against the single exchange), so the captured iteration keeps the single all-reduce
+        after the backward pass unless LDB200_GRAPH_OVERLAP=1."""
+        if not ((self.world > 1 or getattr(self, '_force_staged', False)) and self.overlap):
+            return False
+        return not getattr(self, '_graph_mode', False) or os.environ.get('LDB200_GRAPH_OVERLAP') == '1'
 
     def _comm(self):
         st = self.__dict__.get('_comm_stream')
@@ -444,6 +467,9 @@ class LDTrainStep:
 
     def _begin_exchange(self):
         self._done, self._reduced, self._in_step = set(), [], True
+        bb = getattr(self.model, 'backbone', None)
+        if bb is not None and hasattr(bb, 'cut_stages'):
+            bb.cut_stages = self._staged_now()
         # the step's loss is the plain sum of all terms (base.py:185-218): the loss node may hand out the gradients it
         # precomputed in the forward pass without checking its upstream gradient (a device->host read)
         self.model.bbox_head._unit_loss_grad = True
@@ -551,6 +577,7 @@ class LDTrainStep:
                              'inside stream capture)')
         dev = self.flat_w.device
         head = self.model.bbox_head
+        self._graph_mode = True
         self._hyper = torch.zeros(5, dtype=torch.float32, device=dev)
         self._loss = torch.zeros((), dtype=torch.float32, device=dev)
         self._terms = torch.zeros(8, dtype=torch.float32, device=dev)
