@@ -215,8 +215,14 @@ def main():
             ms = float(t)
         return ms
 
+    t_start = time.time()
+
+    def trace(msg):      # progress on stderr (the JSON line on stdout is the contract)
+        print(f'[bench rank {rank} +{time.time() - t_start:6.1f}s] {msg}', file=sys.stderr, flush=True)
+
     def measure(n, gbatch, precision='bf16', graph=True, steps=args.steps, warmup=max(args.warmup, 3), clocks=False):
         """One configuration: `n` images per GPU.  -> dict(ms, ms_e2e, launches, clocks, bytes)."""
+        trace(f'measure: {n} images/GPU, {precision}, graph={graph}')
         step = ld_b200.LDTrainStep(model, lr=0.01 * gbatch / 16, precision=precision)   # linear scaling rule
         batch = synth.make_batch(n, H, W, seed=1000 + rank)
         img_pinned = batch['img'].pin_memory()
@@ -227,6 +233,7 @@ def main():
         host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
         if graph:
             step.capture(resident, warmup=2)
+            trace('captured')
 
         def run_resident():
             # inputs resident in HBM; everything else of the step runs every step: image move into the graph's static
@@ -266,12 +273,14 @@ def main():
             sampler.start()
         l0 = L.launch_count['n']
         ms = timed(run_resident, steps)
+        trace(f'resident: {ms / steps:.2f} ms/step')
         launches = (L.launch_count['n'] - l0) // steps
         if graph:
             launches = step.launches_per_step + 3      # + the eager target-assignment kernels of every step
         ck = sampler.stop() if sampler else None
         run_e2e()
         ms_e2e = timed(run_e2e, steps)
+        trace(f'e2e: {ms_e2e / steps:.2f} ms/step')
         assert torch.isfinite(host_loss).all(), 'loss diverged'
         h2d = int(img_pinned.numel() * 4 + sum(b.numel() * 4 for b in gtb_pinned) + sum(b.numel() * 8 for b in gtl_pinned))
         res = dict(ms=ms / steps, ms_e2e=ms_e2e / steps, launches=int(launches), clocks=ck, h2d=h2d)

@@ -362,7 +362,9 @@ class LDTrainStep:
             o += p.numel()
         self._segments = spans            # prefix -> (start, end) in flat_g
         self._reduced = []                # slices already exchanged in the current iteration
-        self.overlap = os.environ.get('LDB200_NO_AR_OVERLAP') is None
+        # opt-in (LDB200_AR_OVERLAP=1): the exchange is ~0.4 ms of a 46 ms step on NVLink 5, and the default path (one
+        # all-reduce after the backward pass, captured in the graph) is the one measured at N = 2..8
+        self.overlap = os.environ.get('LDB200_AR_OVERLAP') == '1' and os.environ.get('LDB200_NO_AR_OVERLAP') is None
         self._hook_handle = None
         if self.world > 1 and self.overlap and hasattr(self.model, 'neck'):
             self._hook_handle = self.model.neck.register_forward_hook(self._neck_forward_hook)

@@ -35,10 +35,12 @@ def batch(seed):
                 gt_labels=[x.to(dev) for x in b['gt_labels']])
 
 
-os.environ['LDB200_NO_AR_OVERLAP'] = '1'
 ts_ref = ld_b200.LDTrainStep(ref, lr=0.001, warmup_iters=0)
-del os.environ['LDB200_NO_AR_OVERLAP']
+os.environ['LDB200_AR_OVERLAP'] = '1'
 ts = ld_b200.LDTrainStep(m, lr=0.001, warmup_iters=0)
+torch.cuda.synchronize()
+print(f'[{rank}] after construction: max |w - w_ref| = {float((ts.flat_w - ts_ref.flat_w).abs().max()):.3e}, '
+      f'|w| = {float(ts.flat_w.norm()):.6e}', flush=True)
 assert ts._hook_handle is not None and ts_ref._hook_handle is None
 # which segment differs?  one step with lr = 0 on both, then the reduced gradients segment by segment
 ts.base_lr = ts_ref.base_lr = 0.0

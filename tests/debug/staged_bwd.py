@@ -56,7 +56,7 @@ ts.step(d, sync_logs=False)
 torch.cuda.synchronize()
 print('plain vs plain again:', rel(ts.flat_g, g_plain))
 
-ts._force_staged = True
+ts._force_staged = ts.overlap = True
 ts._hook_handle = m.neck.register_forward_hook(ts._neck_forward_hook)
 ts._cut_log = {}
 ts.step(d, sync_logs=False)

@@ -76,7 +76,7 @@ for staged in (False, True):
     ts = ld_b200.LDTrainStep(m, lr=0.001, warmup_iters=0)
     if staged:
         os.environ['LDB200_GRAPH_OVERLAP'] = '1'
-        ts._force_staged = True
+        ts._force_staged = ts.overlap = True
         ts._hook_handle = m.neck.register_forward_hook(ts._neck_forward_hook)
         ts._cut_log = {}
     if 'eager_first' in sys.argv:

@@ -21,7 +21,7 @@ def _step(depth, staged):
              gt_labels=[x.to(dev) for x in b['gt_labels']])
     ts = ld_b200.LDTrainStep(m, lr=0.0, warmup_iters=0)
     if staged:
-        ts._force_staged = True
+        ts._force_staged = ts.overlap = True
         ts._hook_handle = m.neck.register_forward_hook(ts._neck_forward_hook)
         ts._cut_log = {}
     loss, _ = ts.step(d, sync_logs=False)
