@@ -52,7 +52,7 @@ class ClockSampler:
             'clocks_event_reasons.sw_power_cap'
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -135,6 +135,7 @@ def main():
                     help='BASELINE configs[3]: LDv2Head R50 student + GFocalHead X101-32x4d-DCN teacher (VLR + IMLoss)')
     ap.add_argument('--no-parity', action='store_true', help='skip the fp32-accurate mode side measurement')
     ap.add_argument('--no-micro', action='store_true', help='skip the micro records (LD-KL dense kernel)')
+    ap.add_argument('--child', action='store_true', help=argparse.SUPPRESS)   # the measuring process under the supervisor
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -171,6 +172,9 @@ def main():
                               sample=f'{n_imgs} images of 800x1344 per step (of the 16-image batch), fp32, torch CPU'),
             e2e=dict(value=v, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
         return
+
+    if world == 1 and not args.child and os.environ.get('LDB200_BENCH_NO_SUPERVISOR') is None:
+        return supervise()
 
     import torch
     import torch.distributed as dist
@@ -216,9 +220,24 @@ def main():
         return ms
 
     t_start = time.time()
+    activity = {'t': time.time()}
 
-    def trace(msg):      # progress on stderr (the JSON line on stdout is the contract)
+    def trace(msg):      # progress on stderr (the JSON line on stdout is the contract; the supervisor watches these lines)
+        activity['t'] = time.time()
         print(f'[bench rank {rank} +{time.time() - t_start:6.1f}s] {msg}', file=sys.stderr, flush=True)
+
+    def watchdog():
+        # a phase that makes no progress for STALL_S seconds: say where every thread is and leave, so that the launcher
+        # (the supervisor at N = 1, torchrun at N > 1) sees a failed process instead of a silent hang
+        import faulthandler
+        while True:
+            time.sleep(5.0)
+            if time.time() - activity['t'] > STALL_S:
+                print(f'[bench rank {rank}] no progress for {STALL_S} s -- stacks follow, exiting 17', file=sys.stderr, flush=True)
+                faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+                os._exit(17)
+
+    threading.Thread(target=watchdog, daemon=True).start()
 
     def measure(n, gbatch, precision='bf16', graph=True, steps=args.steps, warmup=max(args.warmup, 3), clocks=False):
         """One configuration: `n` images per GPU.  -> dict(ms, ms_e2e, launches, clocks, bytes)."""
@@ -306,6 +325,7 @@ def main():
     # holds it to 1e-4 against the reference).  Eager launches, 3 timed steps.
     parity = None
     if world == 1 and not args.no_parity:
+        trace('parity-mode side measurement')
         try:
             r = measure(n, global_batch, precision='fp32', graph=False, steps=3, warmup=2)
             parity = dict(img_s=global_batch / (r['ms'] / 1e3), ms_per_step=r['ms'], launch='eager',
@@ -317,6 +337,7 @@ def main():
 
     # dominant kernel, timed live: conv2_tc_kernel on the head-tower shape (P3 level, 3x3 256->256), the
     # single largest-FLOP launch shape of the step (the 5-level head launches are 48 of the step's tcgen05 launches)
+    trace('dominant kernel, timed alone')
     time.sleep(2.0)   # 'timed alone': let the power-capped clocks recover from the step loop before the burst measurement
     kx = torch.randn(n, 100, 168, 256, device=dev).bfloat16()
     kw = _ops.pack_conv_weight(torch.randn(256, 256, 3, 3, device=dev) * 0.02)
@@ -390,7 +411,9 @@ def main():
         if micro is not None:
             out['micro'] = micro
         if world == 1 and not args.no_cpu_baseline:
+            trace('cpu baseline (oracle port on the host cores)')
             v, sec = cpu_reference_step(2, 1, 1)
+            trace('cpu baseline done')
             out['cpu_baseline'] = dict(value=v, unit='images/s', cores=host_cores(), kind='port',
                                        sample='one timed fp32 step (after one warm-up) on 2 images of 800x1344 of the batch; oracle port == reference ATen-CPU path')
         print(json.dumps(out), flush=True)
@@ -402,6 +425,68 @@ def main():
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+STALL_S = 150          # seconds without a progress line before a measuring process gives up
+SUPERVISOR_STALL_S = 200
+
+
+def supervise():
+    """N = 1: the measurement runs in a child process (`--child`); this process only watches its progress lines.  A child
+    that stops making progress (two of ~30 runs on the round-2 boxes stalled right after graph capture, cause not found)
+    is killed by PID and the measurement repeated once.  Prints the child's JSON line."""
+    import signal
+    try:        # map the CUDA library here too (no context is created): the library is the product under test
+        from ld_b200 import lib as L
+        L.load()
+    except Exception as e:     # the child will fail loudly with the real reason
+        print(f'[bench supervisor] could not load the C-ABI library: {e}', file=sys.stderr, flush=True)
+    cmd = [sys.executable, os.path.abspath(__file__), '--child'] + sys.argv[1:]
+    last_err = 'no attempt made'
+    for attempt in range(2):
+        proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        state = {'t': time.time(), 'out': []}
+
+        def pump_err():
+            for line in proc.stderr:
+                state['t'] = time.time()
+                sys.stderr.write(line)
+                sys.stderr.flush()
+
+        def pump_out():
+            for line in proc.stdout:
+                state['t'] = time.time()
+                state['out'].append(line)
+
+        th = [threading.Thread(target=pump_err, daemon=True), threading.Thread(target=pump_out, daemon=True)]
+        for t in th:
+            t.start()
+        stalled = False
+        while proc.poll() is None:
+            time.sleep(1.0)
+            if time.time() - state['t'] > SUPERVISOR_STALL_S:
+                stalled = True
+                print(f'[bench supervisor] attempt {attempt}: no progress for {SUPERVISOR_STALL_S} s, killing pid {proc.pid}',
+                      file=sys.stderr, flush=True)
+                try:
+                    os.kill(proc.pid, signal.SIGKILL)
+                except ProcessLookupError:
+                    pass
+                proc.wait()
+        for t in th:
+            t.join(timeout=5.0)
+        line = next((l for l in reversed(state['out']) if l.lstrip().startswith('{')), None)
+        if line is not None and not stalled and proc.returncode == 0:
+            if attempt:
+                d = json.loads(line)
+                d['supervisor'] = dict(retries=attempt, reason=last_err)
+                line = json.dumps(d) + '\n'
+            sys.stdout.write(line)
+            sys.stdout.flush()
+            return
+        last_err = 'stalled' if stalled else f'exit code {proc.returncode}'
+        print(f'[bench supervisor] attempt {attempt} failed: {last_err}', file=sys.stderr, flush=True)
+    sys.exit(1)
 
 
 def profile_numbers():

@@ -44,6 +44,7 @@ constexpr int CONV_MAX_SEG = 5;   // pyramid levels batched into one launch (sha
 struct ConvSeg {            // geometry of one segment (= one FPN level of a level-shared head conv, or the whole conv)
   int N, HO, WO;            // tile space = logical output pixels
   int TH, TW, tiles_y, tiles_x, tw_shift;
+  uint32_t dx_mul, dx_sh, dy_mul, dy_sh;   // fastdiv constants of tiles_x / tiles_y (host: make_div)
   // output addressing: element offset of pixel (n,y,x) = ((n*OH + y*oys + oyo)*OW + x*oxs + oxo)*ldc
   int OH, OW, oys, oyo, oxs, oxo;
   void* out;
@@ -61,6 +62,9 @@ struct ConvSeg {            // geometry of one segment (= one FPN level of a lev
 struct ConvParams {
   int nseg;
   int seg_tile0[CONV_MAX_SEG + 1];   // first tile of each segment; [nseg] = total tiles
+  int seg_mt0[CONV_MAX_SEG + 1];     // the same in pixel tiles (seg_tile0 / tiles_n)
+  uint32_t dn_mul, dn_sh;            // fastdiv constants of tiles_n
+  uint32_t dh_mul, dh_sh;            // ... of the pair count per output-channel tile of the 2-CTA kernel, ceil(pixel tiles / 2)
   ConvSeg seg[CONV_MAX_SEG];
   int tiles_n;
   int Cout, Cin;
@@ -185,6 +189,15 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// explicit shared-window vector accesses (the generic-pointer form compiles to LD.E / ST.E)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO), version 1, layout type 2.
@@ -230,27 +243,36 @@ __device__ __forceinline__ size_t out_offset(const ConvSeg& p, int n, int y, int
 // comes out of L2 a few microseconds after the first read (with the channel tile fastest ACROSS CTAs, the CTAs sharing a
 // pixel tile drift apart and big maps re-read A from HBM: 975 MB instead of 688 MB on the layer-1 expand conv).
 struct TileCoord { int sg, nt, tx, ty, n; };
+// n / d for 0 <= n < 2^31 with the host-made constants of d (make_div): three instructions instead of the ~25 of an
+// integer division -- the tile decode runs once per tile in every warp role (ncu r02: 303 instructions per tile in the
+// epilogue warps, three divisions among them)
+__device__ __forceinline__ int fastdiv(int n, uint32_t mul, uint32_t sh) {
+  return (int)((__umulhi((uint32_t)n, mul) + (uint32_t)n) >> sh);
+}
+// pixel tile mt of segment sg -> (tx, ty, n)
+__device__ __forceinline__ void decode_pixel_tile(const ConvSeg& S, int sp, int& tx, int& ty, int& n) {
+  const int q = fastdiv(sp, S.dx_mul, S.dx_sh);
+  tx = sp - q * S.tiles_x;
+  n = fastdiv(q, S.dy_mul, S.dy_sh);
+  ty = q - n * S.tiles_y;
+}
 __device__ __forceinline__ bool decode_tile(const ConvParams& p, int b, int grid, int i, TileCoord& c) {
   int mt;
   if (p.nt_inner) {
-    const int r = i / p.tiles_n;
+    const int r = fastdiv(i, p.dn_mul, p.dn_sh);
     mt = b + r * grid;
     c.nt = i - r * p.tiles_n;
   } else {
     const int t = b + i * grid;
-    mt = t / p.tiles_n;
+    mt = fastdiv(t, p.dn_mul, p.dn_sh);
     c.nt = t - mt * p.tiles_n;
   }
-  if (mt >= p.seg_tile0[p.nseg] / p.tiles_n) return false;
+  if (mt >= p.seg_mt0[p.nseg]) return false;
   int sg = 0;
-  while (sg + 1 < p.nseg && mt >= p.seg_tile0[sg + 1] / p.tiles_n) ++sg;
+  while (sg + 1 < p.nseg && mt >= p.seg_mt0[sg + 1]) ++sg;
   const ConvSeg& S = p.seg[sg];
-  int sp = mt - p.seg_tile0[sg] / p.tiles_n;
   c.sg = sg;
-  c.tx = sp % S.tiles_x;
-  sp /= S.tiles_x;
-  c.ty = sp % S.tiles_y;
-  c.n = sp / S.tiles_y;
+  decode_pixel_tile(S, mt - p.seg_mt0[sg], c.tx, c.ty, c.n);
   return true;
 }
 
@@ -571,7 +593,143 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
   __syncwarp();
 }
 
-template <int BN, bool SHORTK, int EXT>
+// ---------------------------------------------------------------------------------------------
+// Lean epilogue for the launches that make up almost all of the LD step's epilogue work: TMA-staged bf16 output, every
+// 64-column box complete (Cout % BN == 0), no accumulate / fp32 / GroupNorm extras, and the feature set known at
+// compile time (FEAT): per-channel scale AND bias (one FFMA), ReLU (on the packed bf16 pair), residual box, ReLU-mask
+// box.  ncu (r02, 1x1 256->1024 +residual): the generic epilogue issues 392 instructions per 32-column chunk and 303 per
+// tile, ~2.5x the arithmetic it carries (runtime feature tests, generic-space LD/ST, FMUL+FADD), and its warps sit at
+// 12 cycles per issued instruction: the HBM-heavy convs are bound by the epilogue's instruction count.
+constexpr int EF_AFFINE = 1, EF_RELU = 2, EF_ADD = 4, EF_MASK = 8;
+
+template <int BN, bool SHORTK, int EPI_GROUPS, int FEAT>
+__device__ __forceinline__ void epilogue_tile_fast(const ConvParams& p, const ConvMaps& maps, const ConvSeg& S, int sg, int nt,
+                                                   int tx, int ty, int n, uint32_t tmem_acc, uint64_t* tfull_bar,
+                                                   uint32_t acc_phase, int ew, int half, int lane, unsigned char* ebuf,
+                                                   uint64_t* rbar, uint32_t& rph) {
+  constexpr int GCOLS = BN / EPI_GROUPS;   // columns per warp
+  constexpr int NBOX = GCOLS / 64;         // 64-column staging boxes per warp
+  static_assert(GCOLS % 64 == 0, "the fast epilogue moves whole 64-column boxes");
+  const int col0 = nt * BN + half * GCOLS;
+  const uint32_t tbase = tmem_acc + ((uint32_t)(ew * 32) << 16) + (uint32_t)(half * GCOLS);
+  const int bx = tx * S.TW + ((ew * 32) & (S.TW - 1)), by = ty * S.TH + ((ew * 32) >> S.tw_shift);
+  const uint32_t erow = s2u(ebuf) + (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)lane & 7u;
+  uint32_t rbuf[SHORTK ? 1 : 2][32];
+#pragma unroll
+  for (int b = 0; b < NBOX; ++b) {
+    const int colb = col0 + b * 64;
+    uint32_t mb0 = 0xffffffffu, mb1 = 0xffffffffu;   // ReLU-mask bits of this lane's 64 box columns
+    // staging box free again (the previous TMA store has read it), then the mask bits and the residual box
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+    if (FEAT & EF_MASK) {
+      if (lane == 0) {
+        if (FEAT & EF_ADD) tma_prefetch_4d(&maps.rl[sg], colb, bx, by, n);   // residual box follows: start its fetch now
+        mbarrier_expect_tx(rbar, EPI_BOX_BYTES);
+        tma_load_4d(ebuf, &maps.ml[sg], rbar, colb, bx, by, n);
+      }
+      mbarrier_wait(rbar, rph);
+      rph ^= 1;
+      mb0 = mb1 = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint4 mv = lds128(erow + (((uint32_t)q ^ sw) << 4));
+        const uint32_t w4[4] = {mv.x, mv.y, mv.z, mv.w};
+        uint32_t bits = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {   // bf16 > 0: sign clear and not zero (NaN counts as positive: never produced by ReLU)
+          const uint32_t lo = w4[e] & 0xffffu, hi = w4[e] >> 16;
+          bits |= ((lo - 1u) < 0x7fffu ? 1u : 0u) << (2 * e);
+          bits |= ((hi - 1u) < 0x7fffu ? 1u : 0u) << (2 * e + 1);
+        }
+        if (q < 4) mb0 |= bits << (8 * q);
+        else mb1 |= bits << (8 * (q - 4));
+      }
+      fence_proxy_async();
+      __syncwarp();
+    }
+    if (FEAT & EF_ADD) {
+      if (lane == 0) {
+        mbarrier_expect_tx(rbar, EPI_BOX_BYTES);
+        tma_load_4d(ebuf, &maps.rl[sg], rbar, colb, bx, by, n);
+      }
+    }
+    if (b == 0) {
+      mbarrier_wait(tfull_bar, acc_phase);
+      tc_fence_after();
+    }
+    if (SHORTK || b == 0) tmem_ld32_nowait(tbase + b * 64, rbuf[0]);   // (else: issued one chunk ahead, below)
+    if (FEAT & EF_ADD) {
+      mbarrier_wait(rbar, rph);
+      rph ^= 1;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ch = 2 * b + h;
+      const int cbase = colb + 32 * h;
+      if (SHORTK && h == 1) tmem_ld32_nowait(tbase + ch * 32, rbuf[0]);
+      tmem_ld_wait();
+      if (!SHORTK && ch + 1 < 2 * NBOX) tmem_ld32_nowait(tbase + (ch + 1) * 32, rbuf[(ch + 1) & 1]);
+      const uint32_t* r = rbuf[SHORTK ? 0 : (ch & 1)];
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (FEAT & EF_AFFINE) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + cbase + j));
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+          v[j] = fmaf(v[j], s4.x, b4.x);
+          v[j + 1] = fmaf(v[j + 1], s4.y, b4.y);
+          v[j + 2] = fmaf(v[j + 2], s4.z, b4.z);
+          v[j + 3] = fmaf(v[j + 3], s4.w, b4.w);
+        }
+      }
+      if (FEAT & EF_ADD) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const uint4 q = lds128(erow + ((((uint32_t)(h * 4 + (j >> 3))) ^ sw) << 4));
+          const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[j + 2 * e] += __uint_as_float(w4[e] << 16);
+            v[j + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+          }
+        }
+      }
+      if (FEAT & EF_MASK) {
+        const uint32_t word = h ? mb1 : mb0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (!((word >> j) & 1u)) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 q;
+        uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+          if (FEAT & EF_RELU) h2 = __hmax2(h2, __floats2bfloat162_rn(0.f, 0.f));   // max(round(v), 0) == round(max(v, 0))
+          qw[e] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        sts128(erow + ((((uint32_t)(h * 4 + (j >> 3))) ^ sw) << 4), q);
+      }
+    }
+    // 64 columns staged: hand the box to the TMA (rows outside the tensor are clipped; a dummy tile is all outside)
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(&maps.o[sg], ebuf, colb, bx, by, n);
+      bulk_commit();
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+}
+
+template <int BN, bool SHORTK, int EXT, int FEAT>
 __global__ void __launch_bounds__(ConvCfg<BN, SHORTK>::THREADS, ConvCfg<BN, SHORTK>::MIN_BLOCKS)
 conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvParams p) {
@@ -706,8 +864,12 @@ conv_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CU
       const uint32_t acc_phase = (it >> 1) & 1;
       const int sg = tc.sg, nt = tc.nt, tx = tc.tx, ty = tc.ty, n = tc.n;
       const ConvSeg& S = p.seg[sg];
-      epilogue_tile<BN, SHORTK, Cfg::EPI_GROUPS, EXT>(p, maps, S, sg, nt, tx, ty, n, true, tmem_base + (uint32_t)(acc * BN),
-                                                 &tfull[acc], acc_phase, ew, half, lane, ebuf, rbar, rph);
+      if constexpr (FEAT >= 0)
+        epilogue_tile_fast<BN, SHORTK, Cfg::EPI_GROUPS, FEAT>(p, maps, S, sg, nt, tx, ty, n, tmem_base + (uint32_t)(acc * BN),
+                                                             &tfull[acc], acc_phase, ew, half, lane, ebuf, rbar, rph);
+      else
+        epilogue_tile<BN, SHORTK, Cfg::EPI_GROUPS, EXT>(p, maps, S, sg, nt, tx, ty, n, true, tmem_base + (uint32_t)(acc * BN),
+                                                   &tfull[acc], acc_phase, ew, half, lane, ebuf, rbar, rph);
       if (lane == 0) mbarrier_arrive(&tempty[acc]);
     }
     if (lane == 0) bulk_wait_all();   // staging buffers must outlive the TMA stores that read them
@@ -769,7 +931,7 @@ __device__ __forceinline__ void mbarrier_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(s2u(bar) & PEER_MASK) : "memory");
 }
 
-template <int EXT>
+template <int EXT, int FEAT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Conv2Cfg::THREADS, 1)
 conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvParams p) {
@@ -794,7 +956,7 @@ conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ C
   const int kblocks = p.ncombo * p.ntaps * cchunks;
   // pair-tiles: CTA rank r of pair q owns M-tile 2*(q % half_m) + r of output-channel tile q / half_m; an odd
   // M-tile count is padded with a dummy tile (fully out-of-bounds loads, no stores)
-  const int mt_total = p.seg_tile0[p.nseg] / p.tiles_n;
+  const int mt_total = p.seg_mt0[p.nseg];
   const int half_m = (mt_total + 1) >> 1;
   const int pairs = p.tiles_n * half_m;
 
@@ -838,17 +1000,15 @@ conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ C
       };
       if (p.a_pf && (int)(blockIdx.x >> 1) < pairs) prefetch_a(blockIdx.x >> 1);
       for (int q = blockIdx.x >> 1; q < pairs; q += gridDim.x >> 1) {
-        const int nt = q / half_m;
+        const int nt = fastdiv(q, p.dh_mul, p.dh_sh);
         const int mt = 2 * (q - nt * half_m) + (int)rank;
         const bool dummy = mt >= mt_total;
         int sg = 0;
-        while (!dummy && sg + 1 < p.nseg && mt >= p.seg_tile0[sg + 1] / p.tiles_n) ++sg;
+        while (!dummy && sg + 1 < p.nseg && mt >= p.seg_mt0[sg + 1]) ++sg;
         const ConvSeg& S = p.seg[sg];
-        int sp = dummy ? 0 : mt - p.seg_tile0[sg] / p.tiles_n;
-        const int tx = sp % S.tiles_x;
-        sp /= S.tiles_x;
-        const int ty = sp % S.tiles_y;
-        const int n = dummy ? S.N * p.planes : sp / S.tiles_y;   // image index beyond every plane: TMA zero-fills
+        int tx, ty, n;
+        decode_pixel_tile(S, dummy ? 0 : mt - p.seg_mt0[sg], tx, ty, n);
+        if (dummy) n = S.N * p.planes;   // image index beyond every plane: TMA zero-fills
         const int x0 = tx * S.TW * p.sx, y0 = ty * S.TH * p.sy;
         if (p.a_pf && q + (int)(gridDim.x >> 1) < pairs) prefetch_a(q + (gridDim.x >> 1));
         // the epilogue will read this tile's residual / ReLU-mask rows a whole main loop from now: pull them into
@@ -917,19 +1077,21 @@ conv2_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ C
     for (int q = blockIdx.x >> 1; q < pairs; q += gridDim.x >> 1, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int nt = q / half_m;
+      const int nt = fastdiv(q, p.dh_mul, p.dh_sh);
       const int mt = 2 * (q - nt * half_m) + (int)rank;
       const bool dummy = mt >= mt_total;
       int sg = 0;
-      while (!dummy && sg + 1 < p.nseg && mt >= p.seg_tile0[sg + 1] / p.tiles_n) ++sg;
+      while (!dummy && sg + 1 < p.nseg && mt >= p.seg_mt0[sg + 1]) ++sg;
       const ConvSeg& S = p.seg[sg];
-      int sp = dummy ? 0 : mt - p.seg_tile0[sg] / p.tiles_n;
-      const int tx = sp % S.tiles_x;
-      sp /= S.tiles_x;
-      const int ty = sp % S.tiles_y;
-      const int n = dummy ? S.N * p.planes : sp / S.tiles_y;   // image index beyond every plane: TMA zero-fills
-      epilogue_tile<BN, SHORTK, Cfg::EPI_GROUPS, EXT>(p, maps, S, sg, nt, tx, ty, n, !dummy, tmem_base + (uint32_t)(acc * BN),
-                                                 &tfull[acc], acc_phase, ew, half, lane, ebuf, rbar, rph);
+      int tx, ty, n;
+      decode_pixel_tile(S, dummy ? 0 : mt - p.seg_mt0[sg], tx, ty, n);
+      if (dummy) n = S.N * p.planes;   // image index beyond every plane: TMA zero-fills
+      if constexpr (FEAT >= 0)
+        epilogue_tile_fast<BN, SHORTK, Cfg::EPI_GROUPS, FEAT>(p, maps, S, sg, nt, tx, ty, n, tmem_base + (uint32_t)(acc * BN),
+                                                             &tfull[acc], acc_phase, ew, half, lane, ebuf, rbar, rph);
+      else
+        epilogue_tile<BN, SHORTK, Cfg::EPI_GROUPS, EXT>(p, maps, S, sg, nt, tx, ty, n, !dummy, tmem_base + (uint32_t)(acc * BN),
+                                                   &tfull[acc], acc_phase, ew, half, lane, ebuf, rbar, rph);
       if (lane == 0) mbarrier_arrive_leader(&tempty[acc]);
     }
     if (lane == 0) bulk_wait_all();   // staging buffers must outlive the TMA stores that read them
@@ -1386,12 +1548,12 @@ static cudaError_t launch_pdl(K kernel, int grid, int block, size_t smem, cudaSt
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-template <int BN, bool SHORTK, int EXT>
+template <int BN, bool SHORTK, int EXT, int FEAT>
 static int launch_conv_ext(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, SHORTK>;
   static bool attr = false;
   if (!attr) {
-    LDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, SHORTK, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    LDB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, SHORTK, EXT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr = true;
   }
   const int total = p.seg_tile0[p.nseg];
@@ -1402,45 +1564,79 @@ static int launch_conv_ext(const ConvMaps& maps, const CUtensorMap& tmB, const C
   static const bool nt_inner_env = getenv("LDB200_NT_INNER") != nullptr;
   q.nt_inner = (nt_inner_env && p.tiles_n > 1 && total / p.tiles_n >= slots) ? 1 : 0;
   const int grid = total < slots ? total : slots;
-  LDB_CUDA(launch_pdl(conv_tc_kernel<BN, SHORTK, EXT>, grid, Cfg::THREADS, Cfg::SMEM, stream, maps, tmB, q));
+  LDB_CUDA(launch_pdl(conv_tc_kernel<BN, SHORTK, EXT, FEAT>, grid, Cfg::THREADS, Cfg::SMEM, stream, maps, tmB, q));
   return 0;
 }
 
-// ext: epilogue feature set (0 plain, 1 GroupNorm statistics, 3 statistics + fp32 extras of the split mode)
+// ext: epilogue feature set of the generic epilogue (0 plain, 1 GroupNorm statistics, 3 statistics + fp32 extras of the
+// split mode); feat: compile-time feature set of the lean epilogue (EF_* bits), -1 = generic
 template <int BN, bool SHORTK>
-static int launch_conv(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream, int ext) {
-  if (ext == 0) return launch_conv_ext<BN, SHORTK, 0>(maps, tmB, p, stream);
-  if (ext == 1) return launch_conv_ext<BN, SHORTK, 1>(maps, tmB, p, stream);
-  return launch_conv_ext<BN, SHORTK, 3>(maps, tmB, p, stream);
+static int launch_conv(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream, int ext,
+                       int feat) {
+  if constexpr (BN == 128) {
+    if (ext == 0) {
+      switch (feat) {
+        case EF_AFFINE: return launch_conv_ext<BN, SHORTK, 0, EF_AFFINE>(maps, tmB, p, stream);
+        case EF_AFFINE | EF_RELU: return launch_conv_ext<BN, SHORTK, 0, EF_AFFINE | EF_RELU>(maps, tmB, p, stream);
+        case EF_AFFINE | EF_RELU | EF_ADD: return launch_conv_ext<BN, SHORTK, 0, EF_AFFINE | EF_RELU | EF_ADD>(maps, tmB, p, stream);
+        case EF_MASK: return launch_conv_ext<BN, SHORTK, 0, EF_MASK>(maps, tmB, p, stream);
+        case EF_MASK | EF_ADD: return launch_conv_ext<BN, SHORTK, 0, EF_MASK | EF_ADD>(maps, tmB, p, stream);
+        default: break;
+      }
+    }
+  }
+  if (ext == 0) return launch_conv_ext<BN, SHORTK, 0, -1>(maps, tmB, p, stream);
+  if (ext == 1) return launch_conv_ext<BN, SHORTK, 1, -1>(maps, tmB, p, stream);
+  return launch_conv_ext<BN, SHORTK, 3, -1>(maps, tmB, p, stream);
 }
 
 // 2-CTA kernel (default for Cout % 256 == 0 and more than 4 k-blocks; LDB200_NO_CONV2=1 falls back to the 1-CTA kernel): one cluster of two CTAs per pair-tile, grid = resident clusters
-template <int EXT>
+template <int EXT, int FEAT>
 static int launch_conv2_ext(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream) {
   static int max_clusters = 0;
   if (!max_clusters) {
-    LDB_CUDA(cudaFuncSetAttribute(conv2_tc_kernel<EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Conv2Cfg::SMEM));
+    LDB_CUDA(cudaFuncSetAttribute(conv2_tc_kernel<EXT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Conv2Cfg::SMEM));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(g_conv_sms / 2 * 2);
     cfg.blockDim = dim3(Conv2Cfg::THREADS);
     cfg.dynamicSmemBytes = Conv2Cfg::SMEM;
     int n = 0;
-    LDB_CUDA(cudaOccupancyMaxActiveClusters(&n, conv2_tc_kernel<EXT>, &cfg));
+    LDB_CUDA(cudaOccupancyMaxActiveClusters(&n, conv2_tc_kernel<EXT, FEAT>, &cfg));
     LDB_REQUIRE(n >= 1, LDB_ENOSUP, "conv2d_tc: no resident 2-CTA cluster");
     max_clusters = n < g_conv_sms / 2 ? n : g_conv_sms / 2;
   }
   const int mt_total = p.seg_tile0[p.nseg] / p.tiles_n;
   const int pairs = p.tiles_n * ((mt_total + 1) / 2);
   const int clusters = pairs < max_clusters ? pairs : max_clusters;
-  conv2_tc_kernel<EXT><<<2 * clusters, Conv2Cfg::THREADS, Conv2Cfg::SMEM, stream>>>(maps, tmB, p);
+  conv2_tc_kernel<EXT, FEAT><<<2 * clusters, Conv2Cfg::THREADS, Conv2Cfg::SMEM, stream>>>(maps, tmB, p);
   LDB_CUDA(cudaGetLastError());
   return 0;
 }
-static int launch_conv2(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream, int ext) {
-  if (ext == 0) return launch_conv2_ext<0>(maps, tmB, p, stream);
-  if (ext == 1) return launch_conv2_ext<1>(maps, tmB, p, stream);
-  return launch_conv2_ext<3>(maps, tmB, p, stream);
+static int launch_conv2(const ConvMaps& maps, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t stream, int ext,
+                        int feat) {
+  if (ext == 0) {
+    switch (feat) {
+      case EF_AFFINE: return launch_conv2_ext<0, EF_AFFINE>(maps, tmB, p, stream);
+      case EF_AFFINE | EF_RELU: return launch_conv2_ext<0, EF_AFFINE | EF_RELU>(maps, tmB, p, stream);
+      case EF_AFFINE | EF_RELU | EF_ADD: return launch_conv2_ext<0, EF_AFFINE | EF_RELU | EF_ADD>(maps, tmB, p, stream);
+      case EF_MASK: return launch_conv2_ext<0, EF_MASK>(maps, tmB, p, stream);
+      case EF_MASK | EF_ADD: return launch_conv2_ext<0, EF_MASK | EF_ADD>(maps, tmB, p, stream);
+      default: break;
+    }
+    return launch_conv2_ext<0, -1>(maps, tmB, p, stream);
+  }
+  if (ext == 1) return launch_conv2_ext<1, -1>(maps, tmB, p, stream);
+  return launch_conv2_ext<3, -1>(maps, tmB, p, stream);
+}
+
+// constants of fastdiv(n, mul, sh) = n / d for 0 <= n < 2^31 (round-up method: mul = floor((2^s - d) 2^32 / d) + 1,
+// s = ceil(log2 d); q = (umulhi(n, mul) + n) >> s)
+static void make_div(int d, uint32_t* mul, uint32_t* sh) {
+  uint32_t s = 0;
+  while ((1u << s) < (uint32_t)d) ++s;
+  *sh = s;
+  *mul = (uint32_t)(((((uint64_t)1 << s) - (uint64_t)d) << 32) / (uint64_t)d + 1);
 }
 
 // geometry + tensor maps of one segment
@@ -1512,6 +1708,8 @@ static int build_segment(const ldb_conv_desc* d, int BN, const ConvParams& commo
   }
   g->tiles_y = (g->HO + g->TH - 1) / g->TH;
   g->tiles_x = (g->WO + g->TW - 1) / g->TW;
+  make_div(g->tiles_x, &g->dx_mul, &g->dx_sh);
+  make_div(g->tiles_y, &g->dy_mul, &g->dy_sh);
   g->tw_shift = 0;
   while ((1 << g->tw_shift) < g->TW) ++g->tw_shift;
   // optional L2 prefetch maps for the residual / mask tensors (identity pixel mapping, same extent as the output)
@@ -1662,8 +1860,12 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
   }
   // 256-wide tiles push TWO 64-column boxes per warp through the one staging buffer; measured on the LD shapes this
   // only pays when a residual or mask box comes in through it too (plain 1x1 convs: 768 vs 814 TFLOP/s)
+  // (r02, after the staging path lost its generic-space LD/ST: plain 256-wide launches are faster through the boxes
+  //  too -- 1x1 1024->256 44.8 vs 52.4 us, 2048->512 34.3 vs 36.4, 3x3 256->256 67.9 vs 69.8 -- so only the
+  //  GroupNorm-statistics launches of the head towers keep the old rule; LDB200_TMA_EPI_OLD=1 restores it everywhere)
+  static const bool tma_epi_old = getenv("LDB200_TMA_EPI_OLD") != nullptr;
   static const bool tma_epi_all = getenv("LDB200_TMA_EPI_ALL") != nullptr;
-  if (p.tma_epi && BN == 256 && !tma_epi_all) {
+  if (p.tma_epi && BN == 256 && !tma_epi_all && (tma_epi_old || d->gn_stats)) {
     const bool same_size_add = d->add_src && (d->add_H == 0 || d->add_H == (d->OH ? d->OH : d->HO)) &&
                                (d->add_W == 0 || d->add_W == (d->OW ? d->OW : d->WO));
     if (!same_size_add && !d->mask_src) p.tma_epi = 0;
@@ -1684,6 +1886,9 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
     tile0 += p.seg[i].N * p.seg[i].tiles_y * p.seg[i].tiles_x * p.tiles_n;
   }
   for (int i = count; i <= CONV_MAX_SEG; ++i) p.seg_tile0[i] = tile0;
+  for (int i = 0; i <= CONV_MAX_SEG; ++i) p.seg_mt0[i] = p.seg_tile0[i] / p.tiles_n;
+  make_div(p.tiles_n, &p.dn_mul, &p.dn_sh);
+  make_div((p.seg_mt0[count] + 1) / 2, &p.dh_mul, &p.dh_sh);
   for (int i = count; i < CONV_MAX_SEG; ++i) {
     maps.a[i] = maps.r[i] = maps.m[i] = maps.o[i] = maps.rl[i] = maps.ml[i] = maps.ap[i] = maps.a[0];
   }
@@ -1704,11 +1909,23 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
     if (descs[i].pre_src) ext |= 2;
   }
   if (d->add_f32 || d->mask_f32) ext |= 2;
-  if (use2) return launch_conv2(maps, tmB, p, stream, ext);
-  if (shortk) return BN == 128 ? launch_conv<128, true>(maps, tmB, p, stream, ext) : launch_conv<64, true>(maps, tmB, p, stream, ext);
-  if (BN == 256) return launch_conv<256, false>(maps, tmB, p, stream, ext);
-  if (BN == 128) return launch_conv<128, false>(maps, tmB, p, stream, ext);
-  return launch_conv<64, false>(maps, tmB, p, stream, ext);
+  // lean epilogue: TMA-staged bf16 output of complete 64-column boxes, residual / mask through the staging boxes, scale
+  // and bias both present or both absent (LDB200_NO_FAST_EPI=1: always the generic epilogue)
+  static const bool fast_env = getenv("LDB200_NO_FAST_EPI") == nullptr;
+  int feat = -1;
+  if (fast_env && ext == 0 && p.tma_epi && d->Cout % BN == 0 && !p.accumulate && !p.out_f32 && p.vec_ok &&
+      ((p.scale != nullptr) == (p.bias != nullptr))) {
+    bool ok = true;
+    for (int i = 0; i < count; ++i)
+      ok = ok && (p.seg[i].tl_add == (p.seg[i].add_src ? 1 : 0)) && (p.seg[i].tl_mask == (p.seg[i].mask_src ? 1 : 0));
+    if (ok)
+      feat = (p.scale ? EF_AFFINE : 0) | (p.relu ? EF_RELU : 0) | (d->add_src ? EF_ADD : 0) | (d->mask_src ? EF_MASK : 0);
+  }
+  if (use2) return launch_conv2(maps, tmB, p, stream, ext, feat);
+  if (shortk) return BN == 128 ? launch_conv<128, true>(maps, tmB, p, stream, ext, feat) : launch_conv<64, true>(maps, tmB, p, stream, ext, feat);
+  if (BN == 256) return launch_conv<256, false>(maps, tmB, p, stream, ext, feat);
+  if (BN == 128) return launch_conv<128, false>(maps, tmB, p, stream, ext, feat);
+  return launch_conv<64, false>(maps, tmB, p, stream, ext, feat);
 }
 
 extern "C" int ldb200_conv2d_tc(const ldb_conv_desc* d, void* stream_) {

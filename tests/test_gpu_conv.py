@@ -122,6 +122,14 @@ def test_conv_tma_epilogue_fusions(case):
     y = ops.conv2d_tc(x, wp, cout, k, k, 1, pad, mask=mask)
     want = ref_conv(x, wt, 1, pad) * (mask.float() > 0)
     check(y, want, 5e-3)
+    # the remaining compile-time feature sets of the lean epilogue (conv_tc.cu EF_*): BN + ReLU, BN alone, and the
+    # dgrad form residual + ReLU-mask
+    y = ops.conv2d_tc(x, wp, cout, k, k, 1, pad, scale=scale, bias=bias, relu=True)
+    check(y, ref_conv(x, wt, 1, pad, scale, bias, None, True), 5e-3)
+    y = ops.conv2d_tc(x, wp, cout, k, k, 1, pad, scale=scale, bias=bias)
+    check(y, ref_conv(x, wt, 1, pad, scale, bias), 5e-3)
+    y = ops.conv2d_tc(x, wp, cout, k, k, 1, pad, add=res, mask=mask)
+    check(y, ref_conv(x, wt, 1, pad, None, None, res) * (mask.float() > 0), 5e-3)
     # output written into a channel slice of a wider buffer (row-space buffers): neighbours stay untouched
     wide = torch.full((n, h, w, cout + 64), 7.0, device='cuda', dtype=torch.bfloat16)
     ops.conv2d_tc(x, wp, cout, k, k, 1, pad, out=wide[..., :cout], bias=bias)

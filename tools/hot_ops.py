@@ -7,7 +7,7 @@ sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))
 import torch
 from ld_b200 import ops
 
-which = sys.argv[1:] or ['gn_bwd', 'gn_apply', 'expand', 'reduce', 'conv3']
+which = [] if 'convs' in sys.argv else (sys.argv[1:] or ['gn_bwd', 'gn_apply', 'expand', 'reduce', 'conv3'])
 dev = 'cuda'
 n = 16
 sizes = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
@@ -49,6 +49,37 @@ for rep in range(3):
         ops.conv2d_tc(x, w, 256, 3, 3, 1, 1, scale=sc, bias=sh, relu=True)
     torch.cuda.synchronize()
 print('done')
+
+# ---- 1x1 / 3x3 conv shapes of the backbone only (kernel-choice A/B through the LDB200_* environment toggles):
+#      python tools/hot_ops.py convs
+if 'convs' in sys.argv:
+    def t(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3
+    print('env:', {k: v for k, v in _os.environ.items() if k.startswith('LDB200_') and k != 'LDB200_ALLOW_RANDOM_INIT'})
+    for (cin, cout, hh, ww, res, k) in ((256, 1024, 50, 84, True, 1), (1024, 256, 50, 84, False, 1), (512, 128, 100, 168, False, 1),
+                                        (128, 512, 100, 168, True, 1), (2048, 512, 25, 42, False, 1), (64, 256, 200, 336, True, 1),
+                                        (512, 2048, 25, 42, True, 1), (256, 256, 50, 84, False, 3), (512, 512, 25, 42, False, 3),
+                                        (128, 128, 100, 168, False, 3)):
+        x = bf(n, hh, ww, cin)
+        w = (torch.randn(cout, k * k * cin, device=dev, generator=g) * 0.05).bfloat16()
+        sc, sh = torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev)
+        r_ = bf(n, hh, ww, cout) if res else None
+        o = torch.empty(n, hh, ww, cout, device=dev, dtype=torch.bfloat16)
+        us = t(lambda: ops.conv2d_tc(x, w, cout, k, k, 1, k // 2, scale=sc, bias=sh, add=r_, relu=True, out=o))
+        byts = (x.numel() + o.numel() * (2 if res else 1)) * 2
+        fl = 2.0 * n * hh * ww * cin * cout * k * k
+        print(f'conv {k}x{k} {cin:4d}->{cout:4d} @{hh}x{ww}{" +res" if res else "     "} {us:7.1f} us  {byts / us / 1e3:6.0f} GB/s  {fl / us / 1e6:6.0f} TF/s  '
+              f'(bound {max(byts / 6568.7e3, fl / 1680.9e6):6.1f})')
+    sys.exit(0)
 
 # ---- plain timing (no profiler): python tools/hot_ops.py time
 if 'time' in sys.argv:
