@@ -136,6 +136,11 @@ def main():
     ap.add_argument('--no-parity', action='store_true', help='skip the fp32-accurate mode side measurement')
     ap.add_argument('--no-micro', action='store_true', help='skip the micro records (LD-KL dense kernel)')
     ap.add_argument('--child', action='store_true', help=argparse.SUPPRESS)   # the measuring process under the supervisor
+    ap.add_argument('--clocks', default=None, choices=['during', 'after', 'off'],
+                    help='when nvidia-smi samples the clocks: during the timed region (the profiling recipe; default at '
+                         'N = 1), over an identical untimed loop after all measurements (default at N > 1 and for the '
+                         'supervisor\'s retry: a polling nvidia-smi next to the replay loop is the one common factor of '
+                         'the stalled runs), or not at all')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -221,6 +226,8 @@ def main():
 
     t_start = time.time()
     activity = {'t': time.time()}
+    pending = {'out': None, 'probe': False}     # result line ready while the clock probe runs (see watchdog)
+    clocks_mode = args.clocks or ('during' if world == 1 else 'after')
 
     def trace(msg):      # progress on stderr (the JSON line on stdout is the contract; the supervisor watches these lines)
         activity['t'] = time.time()
@@ -233,8 +240,13 @@ def main():
         while True:
             time.sleep(5.0)
             if time.time() - activity['t'] > STALL_S:
-                print(f'[bench rank {rank}] no progress for {STALL_S} s -- stacks follow, exiting 17', file=sys.stderr, flush=True)
+                print(f'[bench rank {rank}] no progress for {STALL_S} s -- stacks follow', file=sys.stderr, flush=True)
                 faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+                if pending['probe']:      # every measurement is done: only the clock sampling loop stalled
+                    if pending['out'] is not None:
+                        pending['out']['clocks'] = dict(error=f'the clock-sampling loop stalled for {STALL_S} s; timings were taken before it')
+                        print(json.dumps(pending['out']), flush=True)
+                    os._exit(0)
                 os._exit(17)
 
     threading.Thread(target=watchdog, daemon=True).start()
@@ -287,7 +299,7 @@ def main():
         for _ in range(warmup):
             run_resident()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank) if (rank == 0 and clocks) else None
+        sampler = ClockSampler(local_rank) if (rank == 0 and (clocks == 'probe' or (clocks and clocks_mode == 'during'))) else None
         if sampler:
             sampler.start()
         l0 = L.launch_count['n']
@@ -297,6 +309,11 @@ def main():
         if graph:
             launches = step.launches_per_step + 3      # + the eager target-assignment kernels of every step
         ck = sampler.stop() if sampler else None
+        if clocks == 'probe':
+            model.bbox_head._static_targets = None
+            del step
+            torch.cuda.empty_cache()
+            return dict(clocks=ck)
         run_e2e()
         ms_e2e = timed(run_e2e, steps)
         trace(f'e2e: {ms_e2e / steps:.2f} ms/step')
@@ -416,6 +433,17 @@ def main():
             trace('cpu baseline done')
             out['cpu_baseline'] = dict(value=v, unit='images/s', cores=host_cores(), kind='port',
                                        sample='one timed fp32 step (after one warm-up) on 2 images of 800x1344 of the batch; oracle port == reference ATen-CPU path')
+        pending['out'] = out
+    if clocks_mode == 'after':
+        # the same replay loop once more, untimed, with nvidia-smi polling next to it; every number above is final
+        pending['probe'] = True
+        trace('clock probe (identical untimed loop)')
+        ck = measure(n, global_batch, graph=use_graph, clocks='probe')['clocks']
+        if rank == 0:
+            out['clocks'] = dict(ck or {}, note='sampled over an identical untimed replay loop right after the measurements')
+        pending['probe'] = False
+    if rank == 0:
+        pending['out'] = None
         print(json.dumps(out), flush=True)
     if world > 1:
         # tearing down NCCL communicators that a captured CUDA graph still references can block forever:
@@ -427,8 +455,8 @@ def main():
         os._exit(0)
 
 
-STALL_S = 150          # seconds without a progress line before a measuring process gives up
-SUPERVISOR_STALL_S = 200
+STALL_S = 75           # seconds without a progress line before a measuring process gives up (longest quiet phase: ~35 s)
+SUPERVISOR_STALL_S = 95
 
 
 def supervise():
@@ -444,7 +472,9 @@ def supervise():
     cmd = [sys.executable, os.path.abspath(__file__), '--child'] + sys.argv[1:]
     last_err = 'no attempt made'
     for attempt in range(2):
-        proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        # the retry keeps nvidia-smi away from the timed loops (clocks sampled over an extra loop at the very end)
+        proc = subprocess.Popen(cmd + (['--clocks', 'after'] if attempt else []), stdout=subprocess.PIPE,
+                                stderr=subprocess.PIPE, text=True)
         state = {'t': time.time(), 'out': []}
 
         def pump_err():

@@ -600,7 +600,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const ConvMap
 // box.  ncu (r02, 1x1 256->1024 +residual): the generic epilogue issues 392 instructions per 32-column chunk and 303 per
 // tile, ~2.5x the arithmetic it carries (runtime feature tests, generic-space LD/ST, FMUL+FADD), and its warps sit at
 // 12 cycles per issued instruction: the HBM-heavy convs are bound by the epilogue's instruction count.
-constexpr int EF_AFFINE = 1, EF_RELU = 2, EF_ADD = 4, EF_MASK = 8;
+constexpr int EF_AFFINE = 1, EF_RELU = 2, EF_ADD = 4, EF_MASK = 8, EF_BIAS = 16;   // EF_BIAS: bias without scale
 
 template <int BN, bool SHORTK, int EPI_GROUPS, int FEAT>
 __device__ __forceinline__ void epilogue_tile_fast(const ConvParams& p, const ConvMaps& maps, const ConvSeg& S, int sg, int nt,
@@ -684,6 +684,13 @@ __device__ __forceinline__ void epilogue_tile_fast(const ConvParams& p, const Co
           v[j + 1] = fmaf(v[j + 1], s4.y, b4.y);
           v[j + 2] = fmaf(v[j + 2], s4.z, b4.z);
           v[j + 3] = fmaf(v[j + 3], s4.w, b4.w);
+        }
+      }
+      if (FEAT & EF_BIAS) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
         }
       }
       if (FEAT & EF_ADD) {
@@ -1576,6 +1583,8 @@ static int launch_conv(const ConvMaps& maps, const CUtensorMap& tmB, const ConvP
   if constexpr (BN == 128) {
     if (ext == 0) {
       switch (feat) {
+        case 0: return launch_conv_ext<BN, SHORTK, 0, 0>(maps, tmB, p, stream);
+        case EF_BIAS: return launch_conv_ext<BN, SHORTK, 0, EF_BIAS>(maps, tmB, p, stream);
         case EF_AFFINE: return launch_conv_ext<BN, SHORTK, 0, EF_AFFINE>(maps, tmB, p, stream);
         case EF_AFFINE | EF_RELU: return launch_conv_ext<BN, SHORTK, 0, EF_AFFINE | EF_RELU>(maps, tmB, p, stream);
         case EF_AFFINE | EF_RELU | EF_ADD: return launch_conv_ext<BN, SHORTK, 0, EF_AFFINE | EF_RELU | EF_ADD>(maps, tmB, p, stream);
@@ -1617,6 +1626,8 @@ static int launch_conv2(const ConvMaps& maps, const CUtensorMap& tmB, const Conv
                         int feat) {
   if (ext == 0) {
     switch (feat) {
+      case 0: return launch_conv2_ext<0, 0>(maps, tmB, p, stream);
+      case EF_BIAS: return launch_conv2_ext<0, EF_BIAS>(maps, tmB, p, stream);
       case EF_AFFINE: return launch_conv2_ext<0, EF_AFFINE>(maps, tmB, p, stream);
       case EF_AFFINE | EF_RELU: return launch_conv2_ext<0, EF_AFFINE | EF_RELU>(maps, tmB, p, stream);
       case EF_AFFINE | EF_RELU | EF_ADD: return launch_conv2_ext<0, EF_AFFINE | EF_RELU | EF_ADD>(maps, tmB, p, stream);
@@ -1860,8 +1871,8 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
   }
   // 256-wide tiles push TWO 64-column boxes per warp through the one staging buffer; measured on the LD shapes this
   // only pays when a residual or mask box comes in through it too (plain 1x1 convs: 768 vs 814 TFLOP/s)
-  // (r02, after the staging path lost its generic-space LD/ST: plain 256-wide launches are faster through the boxes
-  //  too -- 1x1 1024->256 44.8 vs 52.4 us, 2048->512 34.3 vs 36.4, 3x3 256->256 67.9 vs 69.8 -- so only the
+  // (r02 re-measurement, tools/hot_ops.py convs with LDB200_TMA_EPI_ALL=1: plain 256-wide launches are faster through
+  //  the boxes too -- 1x1 1024->256 44.8 vs 52.4 us, 2048->512 34.3 vs 36.4, 3x3 256->256 67.9 vs 69.8 -- so only the
   //  GroupNorm-statistics launches of the head towers keep the old rule; LDB200_TMA_EPI_OLD=1 restores it everywhere)
   static const bool tma_epi_old = getenv("LDB200_TMA_EPI_OLD") != nullptr;
   static const bool tma_epi_all = getenv("LDB200_TMA_EPI_ALL") != nullptr;
@@ -1914,12 +1925,12 @@ extern "C" int ldb200_conv2d_tc_multi(const ldb_conv_desc* descs, int count, voi
   static const bool fast_env = getenv("LDB200_NO_FAST_EPI") == nullptr;
   int feat = -1;
   if (fast_env && ext == 0 && p.tma_epi && d->Cout % BN == 0 && !p.accumulate && !p.out_f32 && p.vec_ok &&
-      ((p.scale != nullptr) == (p.bias != nullptr))) {
+      (p.bias != nullptr || p.scale == nullptr)) {
     bool ok = true;
     for (int i = 0; i < count; ++i)
       ok = ok && (p.seg[i].tl_add == (p.seg[i].add_src ? 1 : 0)) && (p.seg[i].tl_mask == (p.seg[i].mask_src ? 1 : 0));
     if (ok)
-      feat = (p.scale ? EF_AFFINE : 0) | (p.relu ? EF_RELU : 0) | (d->add_src ? EF_ADD : 0) | (d->mask_src ? EF_MASK : 0);
+      feat = (p.scale ? EF_AFFINE : (p.bias ? EF_BIAS : 0)) | (p.relu ? EF_RELU : 0) | (d->add_src ? EF_ADD : 0) | (d->mask_src ? EF_MASK : 0);
   }
   if (use2) return launch_conv2(maps, tmB, p, stream, ext, feat);
   if (shortk) return BN == 128 ? launch_conv<128, true>(maps, tmB, p, stream, ext, feat) : launch_conv<64, true>(maps, tmB, p, stream, ext, feat);

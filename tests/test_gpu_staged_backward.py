@@ -36,11 +36,17 @@ def _step(depth, staged):
 @pytest.mark.parametrize('depth', [18, 50])
 def test_staged_backward_equals_plain(depth):
     l0, g0, segs = _step(depth, False)
+    l0b, g0b, _ = _step(depth, False)        # the same plain step again: run-to-run noise of the bf16 step
     l1, g1, _ = _step(depth, True)
     assert abs(l0 - l1) <= 1e-3 * abs(l0)
+
+    def rel(a, b):
+        return float((a - b).norm() / (b.norm() + 1e-30))
     for name, (a, b) in segs.items():
         if b <= a:
             continue
-        err = float((g1[a:b] - g0[a:b]).norm() / (g0[a:b].norm() + 1e-30))
-        # bf16 step, fp32 atomics: two runs of the SAME plain step differ by ~5e-4
-        assert err <= 5e-3, (name, err)
+        noise = rel(g0b[a:b], g0[a:b])
+        err = rel(g1[a:b], g0[a:b])
+        # bf16 step with fp32 atomics (GroupNorm statistics, loss sums, split-K weight gradients): two runs of the SAME
+        # plain step differ by 3e-4 .. 8e-3 depending on the segment; a block run twice or not at all is O(1)
+        assert err <= max(5e-3, 4.0 * noise), (name, err, noise)
