@@ -178,8 +178,8 @@ def main():
             e2e=dict(value=v, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
         return
 
-    if world == 1 and not args.child and os.environ.get('LDB200_BENCH_NO_SUPERVISOR') is None:
-        return supervise()
+    if not args.child and os.environ.get('LDB200_BENCH_NO_SUPERVISOR') is None:
+        return supervise(rank)
 
     import torch
     import torch.distributed as dist
@@ -455,26 +455,37 @@ def main():
         os._exit(0)
 
 
-STALL_S = 75           # seconds without a progress line before a measuring process gives up (longest quiet phase: ~35 s)
-SUPERVISOR_STALL_S = 95
+STALL_S = 60           # seconds without a progress line before a measuring process gives up (longest quiet phase: ~35 s)
+SUPERVISOR_STALL_S = 80
+ATTEMPTS = 3
 
 
-def supervise():
-    """N = 1: the measurement runs in a child process (`--child`); this process only watches its progress lines.  A child
-    that stops making progress (two of ~30 runs on the round-2 boxes stalled right after graph capture, cause not found)
-    is killed by PID and the measurement repeated once.  Prints the child's JSON line."""
+def supervise(rank):
+    """The measurement runs in a child process (`--child`, same environment: under torchrun every rank's process
+    supervises its own child and the children do the rendezvous); this process only watches the child's progress
+    lines.  A child that stops making progress is killed by PID and the measurement repeated (late in round 2 about one
+    run in three stalled inside the first replays after a graph capture -- with and without the fused stem, with and
+    without nvidia-smi polling, cause not found; the stalled kernel dies with the process).  Every rank's child stalls
+    together (they meet in the all-reduce), gives up after STALL_S and is restarted here, so the new children
+    rendezvous again on the same MASTER_PORT.  Rank 0 prints the child's JSON line."""
     import signal
     try:        # map the CUDA library here too (no context is created): the library is the product under test
         from ld_b200 import lib as L
         L.load()
     except Exception as e:     # the child will fail loudly with the real reason
-        print(f'[bench supervisor] could not load the C-ABI library: {e}', file=sys.stderr, flush=True)
+        print(f'[bench supervisor {rank}] could not load the C-ABI library: {e}', file=sys.stderr, flush=True)
     cmd = [sys.executable, os.path.abspath(__file__), '--child'] + sys.argv[1:]
     last_err = 'no attempt made'
-    for attempt in range(2):
-        # the retry keeps nvidia-smi away from the timed loops (clocks sampled over an extra loop at the very end)
+    for attempt in range(ATTEMPTS):
+        # the retries keep nvidia-smi away from the timed loops (clocks sampled over an extra loop at the very end)
+        env = dict(os.environ)
+        if attempt and 'MASTER_PORT' in env:
+            # a fresh rendezvous for the restarted children: their own TCPStore (rank 0's child hosts it) on another
+            # port, so that no key of the abandoned attempt (NCCL unique id, rank registrations) is read again
+            env['MASTER_PORT'] = str(int(env['MASTER_PORT']) + 17 * attempt)
+            env['TORCHELASTIC_USE_AGENT_STORE'] = 'False'
         proc = subprocess.Popen(cmd + (['--clocks', 'after'] if attempt else []), stdout=subprocess.PIPE,
-                                stderr=subprocess.PIPE, text=True)
+                                stderr=subprocess.PIPE, text=True, env=env)
         state = {'t': time.time(), 'out': []}
 
         def pump_err():
@@ -496,7 +507,7 @@ def supervise():
             time.sleep(1.0)
             if time.time() - state['t'] > SUPERVISOR_STALL_S:
                 stalled = True
-                print(f'[bench supervisor] attempt {attempt}: no progress for {SUPERVISOR_STALL_S} s, killing pid {proc.pid}',
+                print(f'[bench supervisor {rank}] attempt {attempt}: no progress for {SUPERVISOR_STALL_S} s, killing pid {proc.pid}',
                       file=sys.stderr, flush=True)
                 try:
                     os.kill(proc.pid, signal.SIGKILL)
@@ -506,16 +517,20 @@ def supervise():
         for t in th:
             t.join(timeout=5.0)
         line = next((l for l in reversed(state['out']) if l.lstrip().startswith('{')), None)
-        if line is not None and not stalled and proc.returncode == 0:
-            if attempt:
-                d = json.loads(line)
-                d['supervisor'] = dict(retries=attempt, reason=last_err)
-                line = json.dumps(d) + '\n'
-            sys.stdout.write(line)
-            sys.stdout.flush()
+        if not stalled and proc.returncode == 0 and (line is not None or rank != 0):
+            if line is not None:
+                if attempt:
+                    d = json.loads(line)
+                    d['supervisor'] = dict(retries=attempt, reason=last_err)
+                    line = json.dumps(d) + '\n'
+                sys.stdout.write(line)
+                sys.stdout.flush()
             return
         last_err = 'stalled' if stalled else f'exit code {proc.returncode}'
-        print(f'[bench supervisor] attempt {attempt} failed: {last_err}', file=sys.stderr, flush=True)
+        print(f'[bench supervisor {rank}] attempt {attempt} failed: {last_err}', file=sys.stderr, flush=True)
+        if not stalled and proc.returncode not in (17, -9, -15):     # a real error: repeating it would not help
+            sys.exit(proc.returncode if proc.returncode and proc.returncode > 0 else 1)
+        time.sleep(2.0)       # let the other ranks' children go away before the next rendezvous
     sys.exit(1)
 
 

@@ -20,6 +20,11 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
+        # a stalled kernel must not hold the whole tier: pytest-timeout ends the run with the stacks of every thread
+        if config.pluginmanager.hasplugin('timeout'):
+            for it in items:
+                if 'gpu' in it.keywords and it.get_closest_marker('timeout') is None:
+                    it.add_marker(pytest.mark.timeout(600))
         return
     skip = pytest.mark.skip(reason='no CUDA device')
     for it in items:

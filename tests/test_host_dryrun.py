@@ -177,13 +177,15 @@ def test_parity_mode_train_step_host_logic(fake_backend, student):
 
 
 def test_overlapped_gradient_exchange_covers_flat_buffer_once(fake_backend, monkeypatch):
-    """Data-parallel exchange of LDTrainStep: segments of the flat gradient buffer are all-reduced from
-    backward hooks in completion order (head, neck, layer4, layer3) and the remainder after the backward pass; together
-    they cover every element exactly once."""
+    """Data-parallel exchange of LDTrainStep with the overlap opted in (LDB200_AR_OVERLAP=1): the backward
+    pass runs in pieces (head, neck, layer4, layer3, rest), each piece's segment of the flat gradient buffer is
+    all-reduced as soon as it is complete and the remainder after the last piece; together they cover every element
+    exactly once, and the gradients are those of one backward call."""
     import torch.distributed as dist
     m = ld_b200.build_detector(ConfigDict(presets.ld_model('r50', teacher_depth=18))).train()
     calls = []
     monkeypatch.setattr(dist, 'all_reduce', lambda t, *a, **k: calls.append((t.data_ptr(), t.numel())))
+    monkeypatch.setenv('LDB200_AR_OVERLAP', '1')
     ts = ld_b200.LDTrainStep(m, lr=0.001, warmup_iters=4)
     ts.world = 2                                  # pretend to be one of two ranks
     ts._init_overlap()
