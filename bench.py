@@ -180,6 +180,15 @@ def main():
 
     if not args.child and os.environ.get('LDB200_BENCH_NO_SUPERVISOR') is None:
         return supervise(rank)
+    if os.environ.get('LDB200_BENCH_SELFTEST'):
+        # tests/test_bench_supervisor.py (CPU): a stand-in measuring process -- progress lines, optionally one stall on
+        # the first attempt (no `--clocks after` yet), then a result line
+        print('[bench rank %d +   0.0s] selftest child' % rank, file=sys.stderr, flush=True)
+        if os.environ['LDB200_BENCH_SELFTEST'] == 'stall-once' and args.clocks is None:
+            time.sleep(3600)
+        if rank == 0:
+            print(json.dumps(dict(metric='selftest', value=1.0, clocks_mode=args.clocks)), flush=True)
+        return
 
     import torch
     import torch.distributed as dist
@@ -455,8 +464,8 @@ def main():
         os._exit(0)
 
 
-STALL_S = 60           # seconds without a progress line before a measuring process gives up (longest quiet phase: ~35 s)
-SUPERVISOR_STALL_S = 80
+STALL_S = int(os.environ.get('LDB200_BENCH_STALL_S', 60))           # seconds without a progress line before a measuring process gives up (longest quiet phase: ~35 s)
+SUPERVISOR_STALL_S = STALL_S + 20 if 'LDB200_BENCH_STALL_S' not in os.environ else STALL_S
 ATTEMPTS = 3
 
 
