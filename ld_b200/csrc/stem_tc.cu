@@ -1,16 +1,17 @@
-// Fused ResNet stem for student AND teacher in one launch (opt-in, LDB200_FUSED_STEM=1; NOT yet run on a GPU):
+// Fused ResNet stem for student AND teacher in one launch (the default route of the detector; LDB200_NO_FUSED_STEM=1
+// selects the im2col + GEMM route):
 // conv1 7x7/2 pad 3 on the 3-channel fp32 NCHW image + folded eval-BN + ReLU (mmdet/models/backbones/resnet.py:
 // 626-629) for up to two networks that share the input (kd_one_stage.py:60-66: the student and the frozen teacher see
 // the same batch), written as NHWC bf16.
 //
 // Why: the im2col route writes a [N*HO*WO, 192] bf16 operand (1.65 GB at 16 x 800 x 1344) that two GEMMs read back --
 // 2.9 % of the step for the im2col kernel alone plus ~5 GB of HBM traffic.  Here the A operand never leaves the SM:
-//   * producer warps (128 threads) stage the 3 x 21 x 37 input patch of an 8 x 16 output tile in shared memory and
+//   * producer warps (256 threads, two per operand row) stage the 3 x 21 x 37 input patch of an 8 x 16 output tile in shared memory and
 //     expand it into the K-major SWIZZLE_128B UMMA layout [128 pixels][192] (K = (r*7+s)*3+c, 147 zero-padded to 192:
 //     the same order `stem_im2col_kernel` / `ResNet.stem` use), one thread per pixel row, 16-byte swizzled stores;
 //   * the [64*nets][192] weight operand is TMA-loaded once per CTA and stays resident;
 //   * one thread issues 12 tcgen05.mma (M=128, N=64*nets, K=16) per tile into one of two TMEM accumulator stages;
-//   * 4 epilogue warps apply each network's scale/shift + ReLU and store 128-byte NHWC pixel rows.
+//   * 8 epilogue warps apply each network's scale/shift + ReLU and store NHWC pixel rows (64 bytes per warp half).
 // Persistent CTAs (one per SM) walk the tile list; generic-proxy writes of the operand are published to the tensor
 // core's async proxy with fence.proxy.async before the full-barrier arrive.
 #include <cuda.h>

@@ -530,6 +530,7 @@ class LDTrainStep:
             return self._step(data, sync_logs)
 
     def _step(self, data, sync_logs):
+        self._eager_steps = getattr(self, '_eager_steps', 0) + 1
         self.flat_g.zero_()
         engine.zero_pool_begin(self.flat_g.device)
         self._begin_exchange()
@@ -573,10 +574,20 @@ class LDTrainStep:
 
         Target assignment stays outside the graph (its grid depends on the number of gt boxes): each
         replay first runs `ldb200_ld_targets` eagerly into the static target buffers the graph reads.
-        The image batch is copied into a static device buffer; lr / first-step flag live in device memory."""
+        The image batch is copied into a static device buffer; lr / first-step flag live in device memory.
+
+        The `warmup` eager iterations are REAL training iterations on `data` (weights, momentum and `self.iter`
+        advance), run on a side stream as graph capture requires.  Call capture() before any eager `step()` of this
+        object: autograd binds a parameter's gradient-accumulation node to the stream of its first use, and nodes bound
+        to the default stream are not captured (observed: a capture after eager steps replays with garbage
+        gradients)."""
         if warmup < 1:
             raise ValueError('capture() needs >= 1 eager warm-up iteration (lazy initialisation must not happen '
                              'inside stream capture)')
+        if getattr(self, '_eager_steps', 0) and os.environ.get('LDB200_CAPTURE_AFTER_EAGER') is None:
+            raise RuntimeError('capture() after eager step() calls of the same LDTrainStep: the gradient-accumulation '
+                               'nodes of the parameters are bound to the stream of those steps and would run outside '
+                               'the capture (wrong gradients on replay).  Capture first, or build a fresh model.')
         dev = self.flat_w.device
         head = self.model.bbox_head
         self._graph_mode = True

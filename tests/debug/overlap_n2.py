@@ -73,13 +73,36 @@ err = float((ts.flat_w - ts_ref.flat_w).abs().max())
 print(f'[{rank}] eager: max |w - w_ref| = {err:.3e}', flush=True)
 assert err <= 5e-2      # bf16 step: fp32 atomics make two runs of the SAME step differ by ~3e-4
 faulthandler.cancel_dump_traceback_later()
-faulthandler.dump_traceback_later(60, exit=True)
-ts.capture(batch(7), warmup=1)
-print(f'[{rank}] captured', flush=True)
+faulthandler.dump_traceback_later(90, exit=True)
+# captured iterations: FRESH models (a capture after eager steps of the same parameters replays wrong: the gradient
+# accumulation nodes stay bound to the eager stream -- LDTrainStep.capture refuses it), the overlapped exchange inside
+# the graph opted in on one of them
+del ts, ts_ref, m, ref
+torch.cuda.empty_cache()
+
+
+def fresh():
+    mm = ld_b200.build_detector(ConfigDict(presets.ld_model('r18', teacher_depth=18)))
+    synth.seeded_init(mm, 0)
+    synth.seeded_init(mm.teacher_model, 1, prefix='teacher.')
+    return mm.to(dev).train()
+
+
+os.environ.pop('LDB200_AR_OVERLAP', None)
+g_ref = ld_b200.LDTrainStep(fresh(), lr=0.001, warmup_iters=0)
+os.environ['LDB200_AR_OVERLAP'] = '1'
+os.environ['LDB200_GRAPH_OVERLAP'] = '1'
+g_ovl = ld_b200.LDTrainStep(fresh(), lr=0.001, warmup_iters=0)
+g_ref.capture(batch(7), warmup=1)
+g_ovl.capture(batch(7), warmup=1)
+print(f'[{rank}] captured (plain exchange, and overlapped exchange inside the graph)', flush=True)
 for it in range(3):
-    l = ts.step_graphed(batch(20 + it))
+    l0 = g_ref.step_graphed(batch(20 + it))
+    l1 = g_ovl.step_graphed(batch(20 + it))
     torch.cuda.synchronize()
-    print(f'[{rank}] graphed step {it}: loss {float(l):.5f}', flush=True)
+    print(f'[{rank}] graphed step {it}: loss {float(l1):.5f} (overlapped) vs {float(l0):.5f} (plain)', flush=True)
+err = float((g_ovl.flat_w - g_ref.flat_w).abs().max())
+print(f'[{rank}] graphed: max |w - w_ref| = {err:.3e}', flush=True)
 faulthandler.cancel_dump_traceback_later()
 dist.barrier()
 print(f'[{rank}] done', flush=True)

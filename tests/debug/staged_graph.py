@@ -79,7 +79,7 @@ for staged in (False, True):
         ts._force_staged = ts.overlap = True
         ts._hook_handle = m.neck.register_forward_hook(ts._neck_forward_hook)
         ts._cut_log = {}
-    if 'eager_first' in sys.argv:
+    if 'eager_first' in sys.argv:     # (needs LDB200_CAPTURE_AFTER_EAGER=1: capture() refuses this order)
         ts.step(batch(5), sync_logs=False)
         ts_ref.step(batch(5), sync_logs=False)
     # same sequence of batches on both: capture() runs `warmup` eager iterations on its batch
