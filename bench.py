@@ -137,10 +137,9 @@ def main():
     ap.add_argument('--no-micro', action='store_true', help='skip the micro records (LD-KL dense kernel)')
     ap.add_argument('--child', action='store_true', help=argparse.SUPPRESS)   # the measuring process under the supervisor
     ap.add_argument('--clocks', default=None, choices=['during', 'after', 'off'],
-                    help='when nvidia-smi samples the clocks: during the timed region (the profiling recipe; default at '
-                         'N = 1), over an identical untimed loop after all measurements (default at N > 1 and for the '
-                         'supervisor\'s retry: a polling nvidia-smi next to the replay loop is the one common factor of '
-                         'the stalled runs), or not at all')
+                    help='when nvidia-smi samples the clocks: during the timed region (the profiling recipe; default), '
+                         'over an identical untimed loop after all measurements (kept from the stall hunt of DESIGN 10: '
+                         'the stalls also happen without nvidia-smi next to the loop), or not at all')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -184,7 +183,7 @@ def main():
         # tests/test_bench_supervisor.py (CPU): a stand-in measuring process -- progress lines, optionally one stall on
         # the first attempt (no `--clocks after` yet), then a result line
         print('[bench rank %d +   0.0s] selftest child' % rank, file=sys.stderr, flush=True)
-        if os.environ['LDB200_BENCH_SELFTEST'] == 'stall-once' and args.clocks is None:
+        if os.environ['LDB200_BENCH_SELFTEST'] == 'stall-once' and os.environ.get('LDB200_BENCH_ATTEMPT', '0') == '0':
             time.sleep(3600)
         if rank == 0:
             print(json.dumps(dict(metric='selftest', value=1.0, clocks_mode=args.clocks)), flush=True)
@@ -236,7 +235,7 @@ def main():
     t_start = time.time()
     activity = {'t': time.time()}
     pending = {'out': None, 'probe': False}     # result line ready while the clock probe runs (see watchdog)
-    clocks_mode = args.clocks or ('during' if world == 1 else 'after')
+    clocks_mode = args.clocks or 'during'
 
     def trace(msg):      # progress on stderr (the JSON line on stdout is the contract; the supervisor watches these lines)
         activity['t'] = time.time()
@@ -486,15 +485,13 @@ def supervise(rank):
     cmd = [sys.executable, os.path.abspath(__file__), '--child'] + sys.argv[1:]
     last_err = 'no attempt made'
     for attempt in range(ATTEMPTS):
-        # the retries keep nvidia-smi away from the timed loops (clocks sampled over an extra loop at the very end)
-        env = dict(os.environ)
+        env = dict(os.environ, LDB200_BENCH_ATTEMPT=str(attempt))
         if attempt and 'MASTER_PORT' in env:
             # a fresh rendezvous for the restarted children: their own TCPStore (rank 0's child hosts it) on another
             # port, so that no key of the abandoned attempt (NCCL unique id, rank registrations) is read again
             env['MASTER_PORT'] = str(int(env['MASTER_PORT']) + 17 * attempt)
             env['TORCHELASTIC_USE_AGENT_STORE'] = 'False'
-        proc = subprocess.Popen(cmd + (['--clocks', 'after'] if attempt else []), stdout=subprocess.PIPE,
-                                stderr=subprocess.PIPE, text=True, env=env)
+        proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
         state = {'t': time.time(), 'out': []}
 
         def pump_err():
