@@ -183,10 +183,17 @@ def main():
         # tests/test_bench_supervisor.py (CPU): a stand-in measuring process -- progress lines, optionally one stall on
         # the first attempt (no `--clocks after` yet), then a result line
         print('[bench rank %d +   0.0s] selftest child' % rank, file=sys.stderr, flush=True)
-        if os.environ['LDB200_BENCH_SELFTEST'] == 'stall-once' and os.environ.get('LDB200_BENCH_ATTEMPT', '0') == '0':
+        att = int(os.environ.get('LDB200_BENCH_ATTEMPT', '0'))
+        if os.environ['LDB200_BENCH_SELFTEST'] == 'stall-once' and att == 0:
             time.sleep(3600)
+        ph = None
+        if os.environ['LDB200_BENCH_SELFTEST'] == 'phases':      # phase b stalls on attempts 0 and 1
+            st = PhaseState(os.environ.get('LDB200_BENCH_STATE'), rank, att)
+            say = lambda m: print('[bench rank %d] %s' % (rank, m), file=sys.stderr, flush=True)   # noqa: E731
+            ph = dict(a=st.run('a', lambda: att, say), b=st.run('b', lambda: time.sleep(3600) if att < 2 else att, say),
+                      c=st.run('c', lambda: att, say))
         if rank == 0:
-            print(json.dumps(dict(metric='selftest', value=1.0, clocks_mode=args.clocks)), flush=True)
+            print(json.dumps(dict(metric='selftest', value=1.0, clocks_mode=args.clocks, phases=ph)), flush=True)
         return
 
     import torch
@@ -335,13 +342,14 @@ def main():
         return res
 
     n = global_batch // world
-    main_res = measure(n, global_batch, graph=use_graph, clocks=True)
+    phases = PhaseState(os.environ.get('LDB200_BENCH_STATE'), rank, int(os.environ.get('LDB200_BENCH_ATTEMPT', '0')))
+    main_res = phases.run('main', lambda: measure(n, global_batch, graph=use_graph, clocks=True), trace)
     ms, ms_e2e = main_res['ms'], main_res['ms_e2e']
 
     # BASELINE configs[2] as stated (8 x 2 images: GLOBAL batch 16): the same step with 16 / N images per GPU
     strong = None
     if world > 1 and not args.global_batch and not args.per_gpu_batch and GLOBAL_BATCH % world == 0:
-        r = measure(GLOBAL_BATCH // world, GLOBAL_BATCH, graph=use_graph)
+        r = phases.run('strong', lambda: measure(GLOBAL_BATCH // world, GLOBAL_BATCH, graph=use_graph), trace)
         strong = dict(value=GLOBAL_BATCH / (r['ms'] / 1e3), unit='images/s', ms_per_step=r['ms'], global_batch=GLOBAL_BATCH,
                       per_gpu_batch=GLOBAL_BATCH // world, scaling='strong',
                       e2e=dict(value=GLOBAL_BATCH / (r['ms_e2e'] / 1e3), unit='images/s'))
@@ -351,14 +359,17 @@ def main():
     parity = None
     if world == 1 and not args.no_parity:
         trace('parity-mode side measurement')
-        try:
-            r = measure(n, global_batch, precision='fp32', graph=False, steps=3, warmup=2)
-            parity = dict(img_s=global_batch / (r['ms'] / 1e3), ms_per_step=r['ms'], launch='eager',
-                          note='LDTrainStep(precision="fp32"): fp32 NHWC activations, every conv / dgrad / wgrad as 6 '
-                               'bf16 plane products in one fp32 TMEM accumulator; loss+grads within 1e-4 of the reference')
-        except torch.OutOfMemoryError as e:      # never let the side measurement take the headline down
-            parity = dict(error=str(e)[:120])
-            torch.cuda.empty_cache()
+
+        def parity_phase():
+            try:
+                r = measure(n, global_batch, precision='fp32', graph=False, steps=3, warmup=2)
+                return dict(img_s=global_batch / (r['ms'] / 1e3), ms_per_step=r['ms'], launch='eager',
+                            note='LDTrainStep(precision="fp32"): fp32 NHWC activations, every conv / dgrad / wgrad as 6 '
+                                 'bf16 plane products in one fp32 TMEM accumulator; loss+grads within 1e-4 of the reference')
+            except torch.OutOfMemoryError as e:      # never let the side measurement take the headline down
+                torch.cuda.empty_cache()
+                return dict(error=str(e)[:120])
+        parity = phases.run('parity', parity_phase, trace)
 
     # dominant kernel, timed live: conv2_tc_kernel on the head-tower shape (P3 level, 3x3 256->256), the
     # single largest-FLOP launch shape of the step (the 5-level head launches are 48 of the step's tcgen05 launches)
@@ -380,7 +391,7 @@ def main():
         torch.cuda.synchronize()
         return k0.elapsed_time(k1) / reps
 
-    k_ms = ktime(lambda: _ops.conv2d_tc(kx, kw, 256, 3, 3, 1, 1, out=ko))
+    k_ms = phases.run('kernel', lambda: ktime(lambda: _ops.conv2d_tc(kx, kw, 256, 3, 3, 1, 1, out=ko)), trace)
     k_flop = 2.0 * n * 100 * 168 * 256 * 256 * 9
 
     # micro records (BASELINE configs[4] and the fused loss kernel north_star singles out), HBM-bound
@@ -392,7 +403,7 @@ def main():
         Tt = torch.randn(rows, 17, device=dev) * 2
         wv = torch.rand(rows, device=dev)
         lossb, dS = torch.zeros(1, device=dev), torch.empty_like(S)
-        t_kl = ktime(lambda: _ops.kl_dense_fwd_bwd(S, Tt, wv, 10.0, 0.25, 4.0, loss=lossb, d_student=dS))
+        t_kl = phases.run('micro', lambda: ktime(lambda: _ops.kl_dense_fwd_bwd(S, Tt, wv, 10.0, 0.25, 4.0, loss=lossb, d_student=dS)), trace)
         micro = dict(ld_kl_dense=dict(rows=rows, bins=17, ms=t_kl, bytes=208 * rows, achieved_gbs=208 * rows / t_kl / 1e6,
                                       peak_gbs=pk_hbm, frac=208 * rows / t_kl / 1e6 / pk_hbm,
                                       note='BASELINE configs[4]: 5 levels x 200k anchors x 4 sides x 17 bins, fwd+bwd, '
@@ -437,7 +448,7 @@ def main():
             out['micro'] = micro
         if world == 1 and not args.no_cpu_baseline:
             trace('cpu baseline (oracle port on the host cores)')
-            v, sec = cpu_reference_step(2, 1, 1)
+            v, sec = phases.run('cpu_baseline', lambda: list(cpu_reference_step(2, 1, 1)), trace)
             trace('cpu baseline done')
             out['cpu_baseline'] = dict(value=v, unit='images/s', cores=host_cores(), kind='port',
                                        sample='one timed fp32 step (after one warm-up) on 2 images of 800x1344 of the batch; oracle port == reference ATen-CPU path')
@@ -463,9 +474,41 @@ def main():
         os._exit(0)
 
 
+class PhaseState:
+    """Results of the measurement phases that have completed (main, strong, parity, kernel, micro, cpu_baseline), kept in
+    a file that survives the supervisor's retries: a repeated attempt takes them from the file instead of measuring
+    them again, so a stall costs one phase, not the run.  Every phase is a self-contained measurement (own capture,
+    warm-up and timed region).  Rank 0 writes the file; every rank of the node reads it when its attempt starts (all
+    children of the previous attempt are gone by then, and a phase with collectives cannot complete on rank 0 alone)."""
+
+    def __init__(self, path, rank, attempt):
+        self.path, self.rank, self.done = path, rank, {}
+        if path and attempt > 0 and os.path.exists(path):
+            try:
+                with open(path) as f:
+                    self.done = json.load(f)
+            except Exception:
+                self.done = {}
+
+    def run(self, name, fn, trace=None):
+        if name in self.done:
+            if trace:
+                trace(f'{name}: taken from an earlier attempt of this run')
+            return self.done[name]
+        r = fn()
+        self.done[name] = r
+        if self.path and self.rank == 0:
+            tmp = self.path + '.tmp'
+            with open(tmp, 'w') as f:
+                json.dump(self.done, f)
+            os.replace(tmp, self.path)
+        return r
+
+
 STALL_S = int(os.environ.get('LDB200_BENCH_STALL_S', 60))           # seconds without a progress line before a measuring process gives up (longest quiet phase: ~35 s)
 SUPERVISOR_STALL_S = STALL_S + 20 if 'LDB200_BENCH_STALL_S' not in os.environ else STALL_S
-ATTEMPTS = 3
+ATTEMPTS = 8
+BUDGET_S = int(os.environ.get('LDB200_BENCH_BUDGET_S', 780))   # no new attempt after this many seconds (driver: 870 s per N)
 
 
 def supervise(rank):
@@ -484,8 +527,17 @@ def supervise(rank):
         print(f'[bench supervisor {rank}] could not load the C-ABI library: {e}', file=sys.stderr, flush=True)
     cmd = [sys.executable, os.path.abspath(__file__), '--child'] + sys.argv[1:]
     last_err = 'no attempt made'
+    # one state file per job: under torchrun every rank's supervisor is a child of the same agent process
+    job = os.getppid() if 'LOCAL_RANK' in os.environ else os.getpid()
+    state_path = os.path.join(os.environ.get('TMPDIR', '/tmp'), f'ldb200_bench_{job}.json')
+    if rank == 0 and os.path.exists(state_path):
+        os.remove(state_path)
+    t_begin = time.time()
     for attempt in range(ATTEMPTS):
-        env = dict(os.environ, LDB200_BENCH_ATTEMPT=str(attempt))
+        if attempt and time.time() - t_begin > BUDGET_S:
+            print(f'[bench supervisor {rank}] time budget of {BUDGET_S} s used up', file=sys.stderr, flush=True)
+            break
+        env = dict(os.environ, LDB200_BENCH_ATTEMPT=str(attempt), LDB200_BENCH_STATE=state_path)
         if attempt and 'MASTER_PORT' in env:
             # a fresh rendezvous for the restarted children: their own TCPStore (rank 0's child hosts it) on another
             # port, so that no key of the abandoned attempt (NCCL unique id, rank registrations) is read again
@@ -527,10 +579,13 @@ def supervise(rank):
             if line is not None:
                 if attempt:
                     d = json.loads(line)
-                    d['supervisor'] = dict(retries=attempt, reason=last_err)
+                    d['supervisor'] = dict(retries=attempt, reason=last_err,
+                                           note='phases completed before a stall were kept, the stalled phase was measured again')
                     line = json.dumps(d) + '\n'
                 sys.stdout.write(line)
                 sys.stdout.flush()
+            if rank == 0 and os.path.exists(state_path):
+                os.remove(state_path)
             return
         last_err = 'stalled' if stalled else f'exit code {proc.returncode}'
         print(f'[bench supervisor {rank}] attempt {attempt} failed: {last_err}', file=sys.stderr, flush=True)

@@ -31,7 +31,7 @@ def test_supervisor_repeats_a_stalled_measurement():
     r = _run('stall-once', LDB200_BENCH_STALL_S='4')
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith('{')][-1])
-    assert d['supervisor'] == dict(retries=1, reason='stalled')
+    assert d['supervisor']['retries'] == 1 and d['supervisor']['reason'] == 'stalled'
     assert 'no progress' in r.stderr
 
 
@@ -41,3 +41,13 @@ def test_supervisor_on_a_non_zero_rank_expects_no_result_line():
                        capture_output=True, text=True, env=e, timeout=120)
     assert r.returncode == 0, r.stderr[-2000:]
     assert not [l for l in r.stdout.splitlines() if l.startswith('{')]
+
+
+def test_phases_completed_before_a_stall_are_not_measured_again():
+    r = _run('phases', LDB200_BENCH_STALL_S='3')
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith('{')][-1])
+    # phase a ran in attempt 0 and was kept; b stalled twice and was measured in attempt 2; c followed it
+    assert d['phases'] == dict(a=0, b=2, c=2), d
+    assert d['supervisor']['retries'] == 2
+    assert r.stderr.count('a: taken from an earlier attempt') == 2
