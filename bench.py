@@ -95,7 +95,7 @@ def host_cores():
     return n
 
 
-def cpu_reference_step(n_imgs, steps, warmup, seed=1000):
+def cpu_reference_step(n_imgs, steps, warmup, seed=1000, progress=None):
     """The reference's CPU training path (fp32, all host threads): the oracle port is the same ATen-CPU
     arithmetic as the unmodified reference (pinned by tests/golden) -- /root/reference does not exist here."""
     import torch
@@ -115,6 +115,8 @@ def cpu_reference_step(n_imgs, steps, warmup, seed=1000):
         opt.step()
         if it >= warmup:
             ts.append(time.perf_counter() - t0)
+        if progress:
+            progress(f'cpu step {it + 1}/{warmup + steps}: {time.perf_counter() - t0:.1f} s')
     return n_imgs / (sum(ts) / len(ts)), sum(ts) / len(ts)
 
 
@@ -448,7 +450,7 @@ def main():
             out['micro'] = micro
         if world == 1 and not args.no_cpu_baseline:
             trace('cpu baseline (oracle port on the host cores)')
-            v, sec = phases.run('cpu_baseline', lambda: list(cpu_reference_step(2, 1, 1)), trace)
+            v, sec = phases.run('cpu_baseline', lambda: list(cpu_reference_step(2, 1, 1, progress=trace)), trace)
             trace('cpu baseline done')
             out['cpu_baseline'] = dict(value=v, unit='images/s', cores=host_cores(), kind='port',
                                        sample='one timed fp32 step (after one warm-up) on 2 images of 800x1344 of the batch; oracle port == reference ATen-CPU path')
@@ -505,9 +507,10 @@ class PhaseState:
         return r
 
 
-STALL_S = int(os.environ.get('LDB200_BENCH_STALL_S', 60))           # seconds without a progress line before a measuring process gives up (longest quiet phase: ~35 s)
+STALL_S = int(os.environ.get('LDB200_BENCH_STALL_S', 40))           # seconds without a progress line before a measuring process gives up (longest quiet phase: one CPU step, ~10 s)
 SUPERVISOR_STALL_S = STALL_S + 20 if 'LDB200_BENCH_STALL_S' not in os.environ else STALL_S
-ATTEMPTS = 8
+ATTEMPTS = 12
+START_S = 0 if 'LDB200_BENCH_STALL_S' in os.environ else 180     # patience before the child's first progress line
 BUDGET_S = int(os.environ.get('LDB200_BENCH_BUDGET_S', 780))   # no new attempt after this many seconds (driver: 870 s per N)
 
 
@@ -544,11 +547,12 @@ def supervise(rank):
             env['MASTER_PORT'] = str(int(env['MASTER_PORT']) + 17 * attempt)
             env['TORCHELASTIC_USE_AGENT_STORE'] = 'False'
         proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
-        state = {'t': time.time(), 'out': []}
+        state = {'t': time.time(), 'out': [], 'seen': False}
 
         def pump_err():
             for line in proc.stderr:
                 state['t'] = time.time()
+                state['seen'] = state['seen'] or line.startswith('[bench rank')
                 sys.stderr.write(line)
                 sys.stderr.flush()
 
@@ -563,9 +567,11 @@ def supervise(rank):
         stalled = False
         while proc.poll() is None:
             time.sleep(1.0)
-            if time.time() - state['t'] > SUPERVISOR_STALL_S:
+            # until the child's first progress line (imports, CUDA context, NCCL set-up on a fresh box) be patient
+            limit = SUPERVISOR_STALL_S if state['seen'] else max(SUPERVISOR_STALL_S, START_S)
+            if time.time() - state['t'] > limit:
                 stalled = True
-                print(f'[bench supervisor {rank}] attempt {attempt}: no progress for {SUPERVISOR_STALL_S} s, killing pid {proc.pid}',
+                print(f'[bench supervisor {rank}] attempt {attempt}: no progress for {limit} s, killing pid {proc.pid}',
                       file=sys.stderr, flush=True)
                 try:
                     os.kill(proc.pid, signal.SIGKILL)
